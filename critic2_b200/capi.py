@@ -1,0 +1,247 @@
+"""ctypes binding of the C ABI declared in include/critic2_gpu.h (critic2_b200/libcritic2_gpu.so).
+
+This is the reference-side binding a maintainer would write in Fortran (fortran/critic2_gpu.f90);
+Python is used here only because the image has no Fortran compiler.  There is no CPU fallback: if the
+shared library is missing or no CUDA device is usable every call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcritic2_gpu.so")
+_lib = None
+
+BADER_FAST, BADER_EXACT = 0, 1
+ORDER_INDEX, ORDER_SCAN = 0, 1
+
+EXPORTS = [
+    "c2g_init", "c2g_nccl_unique_id", "c2g_init_multi", "c2g_finalize", "c2g_last_error", "c2g_describe",
+    "c2g_grid_upload", "c2g_grid_alloc", "c2g_grid_download", "c2g_grid_free", "c2g_grid_promolecular",
+    "c2g_bader_assign", "c2g_basins_maxima", "c2g_basins_counts", "c2g_basins_set_map", "c2g_basins_labels",
+    "c2g_basins_relabel", "c2g_basins_free", "c2g_basins_stats", "c2g_integrate", "c2g_yt_build",
+    "c2g_yt_weights", "c2g_nci_rdg", "c2g_nci_rdg_resident", "c2g_profile_enable", "c2g_profile_count",
+    "c2g_profile_get", "c2g_profile_reset", "c2g_launch_count", "c2g_flush_l2", "c2g_synchronize",
+]
+
+
+class C2GError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the CUDA library; fails loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise C2GError(f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        lib.c2g_last_error.restype = C.c_char_p
+        lib.c2g_describe.restype = C.c_char_p
+        lib.c2g_launch_count.restype = C.c_longlong
+        lib.c2g_finalize.restype = None
+        lib.c2g_basins_free.restype = None
+        _lib = lib
+    return _lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _m33(m):
+    return np.asfortranarray(np.asarray(m, dtype=np.float64)).ravel(order="F").copy()
+
+
+class Context:
+    """One c2g_context (one GPU)."""
+
+    def __init__(self, device=0, rank=0, nranks=1, nccl_uid=None):
+        self.lib = load()
+        self.h = C.c_void_p()
+        if nranks > 1:
+            rc = self.lib.c2g_init_multi(C.c_int(device), C.c_int(rank), C.c_int(nranks), nccl_uid, C.byref(self.h))
+        else:
+            rc = self.lib.c2g_init(C.c_int(device), C.byref(self.h))
+        if rc != 0:
+            msg = self.lib.c2g_last_error(self.h).decode() if self.h else "no usable CUDA device"
+            raise C2GError(f"c2g_init failed (status {rc}): {msg}")
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise C2GError(f"status {rc}: {self.lib.c2g_last_error(self.h).decode()}")
+
+    def close(self):
+        if self.h:
+            self.lib.c2g_finalize(self.h)
+            self.h = C.c_void_p()
+
+    def describe(self):
+        return self.lib.c2g_describe(self.h).decode()
+
+    # ---- grids ----
+    def upload(self, f):
+        f = np.asfortranarray(f, dtype=np.float64)
+        n = np.array(f.shape, dtype=np.int32)
+        h = C.c_int(-1)
+        self._chk(self.lib.c2g_grid_upload(self.h, _p(f, C.c_double), _p(n, C.c_int), C.byref(h)))
+        return h.value
+
+    def alloc(self, n):
+        n = np.array(n, dtype=np.int32)
+        h = C.c_int(-1)
+        self._chk(self.lib.c2g_grid_alloc(self.h, _p(n, C.c_int), C.byref(h)))
+        return h.value
+
+    def download(self, h, shape):
+        f = np.zeros(tuple(int(x) for x in shape), order="F")
+        self._chk(self.lib.c2g_grid_download(self.h, C.c_int(h), _p(f, C.c_double)))
+        return f
+
+    def free(self, h):
+        self._chk(self.lib.c2g_grid_free(self.h, C.c_int(h)))
+
+    def promolecular(self, h, x2c, atoms, z, alpha, nimg=1, rc=0.0):
+        xat = np.ascontiguousarray(atoms, dtype=np.float64)
+        z = np.ascontiguousarray(z, dtype=np.float64)
+        alpha = np.ascontiguousarray(alpha, dtype=np.float64)
+        self._chk(self.lib.c2g_grid_promolecular(self.h, C.c_int(h), _p(_m33(x2c), C.c_double), C.c_int(xat.shape[0]),
+                                                 _p(xat, C.c_double), _p(z, C.c_double), _p(alpha, C.c_double),
+                                                 C.c_int(nimg), C.c_double(rc)))
+
+    # ---- BADER ----
+    def bader_assign(self, h, car2lat, lat_i_dist, algo=BADER_FAST, order=ORDER_INDEX):
+        nmax = C.c_int(0)
+        res = C.c_void_p()
+        lid = np.ascontiguousarray(lat_i_dist, dtype=np.float64).ravel()
+        self._chk(self.lib.c2g_bader_assign(self.h, C.c_int(h), _p(_m33(car2lat), C.c_double), _p(lid, C.c_double),
+                                            C.c_int(algo), C.c_int(order), C.byref(nmax), C.byref(res)))
+        return Basins(self, res, nmax.value)
+
+    def yt_build(self, h, vec, area):
+        vec = np.asfortranarray(np.asarray(vec, dtype=np.int32).reshape(-1, 3).T)
+        area = np.ascontiguousarray(area, dtype=np.float64)
+        nmax = C.c_int(0)
+        res = C.c_void_p()
+        self._chk(self.lib.c2g_yt_build(self.h, C.c_int(h), C.c_int(vec.shape[1]), _p(vec, C.c_int), _p(area, C.c_double),
+                                        C.byref(nmax), C.byref(res)))
+        return Basins(self, res, nmax.value)
+
+    def integrate(self, basins, fieldhandles, omega):
+        fh = np.array(list(fieldhandles), dtype=np.int32)
+        nattr = basins.nattr
+        psum = np.zeros((nattr, len(fh)), order="F")
+        vol = np.zeros(nattr)
+        self._chk(self.lib.c2g_integrate(self.h, basins.h, C.c_int(len(fh)), _p(fh, C.c_int), C.c_double(omega),
+                                         _p(psum, C.c_double), _p(vol, C.c_double)))
+        return vol, psum
+
+    # ---- NCIPLOT ----
+    def nci_rdg(self, h, x2c, n, nstep=None, x0=None, xmat=None, nuclei_cart=None, c2xl=None):
+        x2c = np.asarray(x2c, dtype=np.float64)
+        c2x = np.linalg.inv(x2c)
+        nstep = np.array(n if nstep is None else nstep, dtype=np.int32)
+        if xmat is None:
+            xmat = x2c / nstep.astype(np.float64)[None, :]
+        x0 = np.zeros(3) if x0 is None else np.ascontiguousarray(x0, dtype=np.float64)
+        nuc = np.zeros((0, 3)) if nuclei_cart is None else np.ascontiguousarray(nuclei_cart, dtype=np.float64)
+        shape = (int(nstep[2]), int(nstep[1]), int(nstep[0]))
+        crho = np.zeros(shape, order="F")
+        cgrad = np.zeros(shape, order="F")
+        self._chk(self.lib.c2g_nci_rdg(self.h, C.c_int(h), _p(x0, C.c_double), _p(_m33(xmat), C.c_double),
+                                       _p(nstep, C.c_int), _p(_m33(c2x), C.c_double), _p(_m33(x2c), C.c_double),
+                                       _p(_m33(c2x if c2xl is None else c2xl), C.c_double), C.c_int(nuc.shape[0]),
+                                       _p(nuc, C.c_double), _p(crho, C.c_double), _p(cgrad, C.c_double)))
+        return crho, cgrad
+
+    def nci_rdg_resident(self, h, x2c, n, nstep=None):
+        x2c = np.asarray(x2c, dtype=np.float64)
+        c2x = np.linalg.inv(x2c)
+        nstep = np.array(n if nstep is None else nstep, dtype=np.int32)
+        xmat = x2c / nstep.astype(np.float64)[None, :]
+        x0 = np.zeros(3)
+        hr, hg = C.c_int(-1), C.c_int(-1)
+        self._chk(self.lib.c2g_nci_rdg_resident(self.h, C.c_int(h), _p(x0, C.c_double), _p(_m33(xmat), C.c_double),
+                                                _p(nstep, C.c_int), _p(_m33(c2x), C.c_double), _p(_m33(x2c), C.c_double),
+                                                _p(_m33(c2x), C.c_double), C.c_int(0), None, C.byref(hr), C.byref(hg)))
+        return hr.value, hg.value
+
+    # ---- profiling ----
+    def profile_enable(self, on=True):
+        self._chk(self.lib.c2g_profile_enable(self.h, C.c_int(1 if on else 0)))
+
+    def profile_reset(self):
+        self._chk(self.lib.c2g_profile_reset(self.h))
+
+    def profile(self):
+        self.synchronize()
+        out = {}
+        name = C.create_string_buffer(64)
+        ms = C.c_double(0)
+        nl = C.c_int(0)
+        for i in range(self.lib.c2g_profile_count(self.h)):
+            self.lib.c2g_profile_get(self.h, C.c_int(i), name, C.byref(ms), C.byref(nl))
+            out[name.value.decode()] = (ms.value, nl.value)
+        return out
+
+    def launch_count(self):
+        return int(self.lib.c2g_launch_count(self.h))
+
+    def flush_l2(self):
+        self._chk(self.lib.c2g_flush_l2(self.h))
+
+    def synchronize(self):
+        self._chk(self.lib.c2g_synchronize(self.h))
+
+
+class Basins:
+    """c2g_basins: device-resident result of a BADER/YT assignment."""
+
+    def __init__(self, ctx, h, nmax):
+        self.ctx, self.h, self.nmax = ctx, h, nmax
+        self.nattr = 0
+
+    def maxima(self):
+        """(nmax,3) 1-based grid coordinates."""
+        p = np.zeros((self.nmax, 3), dtype=np.int32)
+        self.ctx._chk(self.ctx.lib.c2g_basins_maxima(self.h, _p(p, C.c_int)))
+        return p
+
+    def counts(self):
+        c = np.zeros(self.nmax, dtype=np.int64)
+        self.ctx._chk(self.ctx.lib.c2g_basins_counts(self.h, _p(c, C.c_longlong)))
+        return c
+
+    def set_map(self, nattr, mp):
+        mp = np.ascontiguousarray(mp, dtype=np.int32)
+        self.ctx._chk(self.ctx.lib.c2g_basins_set_map(self.h, C.c_int(nattr), _p(mp, C.c_int)))
+        self.nattr = nattr
+
+    def relabel(self, assigned, nattr_new):
+        a = np.ascontiguousarray(assigned, dtype=np.int32)
+        self.ctx._chk(self.ctx.lib.c2g_basins_relabel(self.h, C.c_int(len(a)), _p(a, C.c_int), C.c_int(nattr_new)))
+        self.nattr = nattr_new
+
+    def labels(self, shape):
+        idg = np.zeros(tuple(int(x) for x in shape), dtype=np.int32, order="F")
+        self.ctx._chk(self.ctx.lib.c2g_basins_labels(self.h, _p(idg, C.c_int)))
+        return idg
+
+    def stats(self):
+        s = np.zeros(8, dtype=np.int64)
+        self.ctx._chk(self.ctx.lib.c2g_basins_stats(self.h, _p(s, C.c_longlong)))
+        return s
+
+    def yt_weights(self, idb, shape):
+        w = np.zeros(tuple(int(x) for x in shape), order="F")
+        self.ctx._chk(self.ctx.lib.c2g_yt_weights(self.h, C.c_int(idb), _p(w, C.c_double)))
+        return w
+
+    def free(self):
+        if self.h:
+            self.ctx.lib.c2g_basins_free(self.h)
+            self.h = C.c_void_p()

@@ -1,0 +1,450 @@
+// capi.cu -- context, resident grids, basin bookkeeping and profiling entry points of the C ABI
+// declared in include/critic2_gpu.h.
+#include "common.cuh"
+
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+
+namespace {
+
+__global__ void k_flush(float4* buf, size_t n4) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride)
+    buf[i] = make_float4(1.f, 2.f, 3.f, 4.f);
+}
+
+// labels (index into maxima list, or <0) -> basin ids through map
+__global__ void k_map_labels(long long nn, const int* __restrict__ label, const int* __restrict__ map,
+                             int* __restrict__ out) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nn; i += stride) {
+    const int l = label[i];
+    out[i] = (l >= 0) ? __ldg(map + l) : 0;
+  }
+}
+
+// synthetic promolecular-like density; atoms binned on the host into a coarse cell list when rc > 0
+struct PromolParams {
+  int n1, n2, n3;
+  double x2c[9];
+  int nat, nimg;
+  double rc;
+};
+__global__ void __launch_bounds__(256) k_promolecular(const __grid_constant__ PromolParams P, const double* __restrict__ xat,
+                                                      const double* __restrict__ zat, const double* __restrict__ alpha,
+                                                      double* __restrict__ f) {
+  const long long nn = (long long)P.n1 * P.n2 * P.n3;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nn) return;
+  const int x = (int)(i % P.n1), y = (int)((i / P.n1) % P.n2), z = (int)(i / ((long long)P.n1 * P.n2));
+  const double xf0 = (double)x / P.n1, xf1 = (double)y / P.n2, xf2 = (double)z / P.n3;
+  double s = 0.0;
+  for (int a = 0; a < P.nat; a++) {
+    const double za = zat[a], al = alpha[a];
+    double b0 = xf0 - xat[3 * a], b1 = xf1 - xat[3 * a + 1], b2 = xf2 - xat[3 * a + 2];
+    if (P.rc > 0.0) {  // minimum-image centred sum: only the nearest images can be inside rc
+      b0 -= rint(b0); b1 -= rint(b1); b2 -= rint(b2);
+    }
+    for (int ta = -P.nimg; ta <= P.nimg; ta++)
+      for (int tb = -P.nimg; tb <= P.nimg; tb++)
+        for (int tc = -P.nimg; tc <= P.nimg; tc++) {
+          const double d0 = b0 + ta, d1 = b1 + tb, d2 = b2 + tc;
+          const double c0 = P.x2c[0] * d0 + P.x2c[3] * d1 + P.x2c[6] * d2;
+          const double c1 = P.x2c[1] * d0 + P.x2c[4] * d1 + P.x2c[7] * d2;
+          const double c2 = P.x2c[2] * d0 + P.x2c[5] * d1 + P.x2c[8] * d2;
+          const double r = sqrt(c0 * c0 + c1 * c1 + c2 * c2);
+          if (P.rc > 0.0) {
+            if (r >= P.rc) continue;
+            const double u = 1.0 - (r / P.rc) * (r / P.rc);
+            s += za * exp(-al * r) * u * u * u;
+          } else {
+            s += za * exp(-al * r);
+          }
+        }
+  }
+  f[i] = s;
+}
+
+// cell-list variant for many atoms with a cutoff: atoms sorted by bin, bins are nb^3 fractional boxes
+struct PromolBinParams {
+  int n1, n2, n3;
+  double x2c[9];
+  int nb;      // bins per axis
+  int reach;   // bins to search on each side
+  double rc;
+};
+__global__ void __launch_bounds__(256) k_promolecular_bins(const __grid_constant__ PromolBinParams P,
+                                                           const int* __restrict__ binstart, const double* __restrict__ xat,
+                                                           const double* __restrict__ zat, const double* __restrict__ alpha,
+                                                           double* __restrict__ f) {
+  const long long nn = (long long)P.n1 * P.n2 * P.n3;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nn) return;
+  const int x = (int)(i % P.n1), y = (int)((i / P.n1) % P.n2), z = (int)(i / ((long long)P.n1 * P.n2));
+  const double xf0 = (double)x / P.n1, xf1 = (double)y / P.n2, xf2 = (double)z / P.n3;
+  const int nb = P.nb;
+  const int bx = min((int)(xf0 * nb), nb - 1), by = min((int)(xf1 * nb), nb - 1), bz = min((int)(xf2 * nb), nb - 1);
+  double s = 0.0;
+  for (int dz = -P.reach; dz <= P.reach; dz++)
+    for (int dy = -P.reach; dy <= P.reach; dy++)
+      for (int dx = -P.reach; dx <= P.reach; dx++) {
+        const int cx = ((bx + dx) % nb + nb) % nb, cy = ((by + dy) % nb + nb) % nb, cz = ((bz + dz) % nb + nb) % nb;
+        const int b = cx + nb * (cy + nb * cz);
+        for (int a = binstart[b]; a < binstart[b + 1]; a++) {
+          double d0 = xf0 - xat[3 * a], d1 = xf1 - xat[3 * a + 1], d2 = xf2 - xat[3 * a + 2];
+          d0 -= rint(d0); d1 -= rint(d1); d2 -= rint(d2);
+          const double c0 = P.x2c[0] * d0 + P.x2c[3] * d1 + P.x2c[6] * d2;
+          const double c1 = P.x2c[1] * d0 + P.x2c[4] * d1 + P.x2c[7] * d2;
+          const double c2 = P.x2c[2] * d0 + P.x2c[5] * d1 + P.x2c[8] * d2;
+          const double r = sqrt(c0 * c0 + c1 * c1 + c2 * c2);
+          if (r >= P.rc) continue;
+          const double u = 1.0 - (r / P.rc) * (r / P.rc);
+          s += zat[a] * exp(-alpha[a] * r) * u * u * u;
+        }
+      }
+  f[i] = s;
+}
+
+int check_handle(c2g_context* ctx, int h, const char* who) {
+  if (h < 0 || h >= (int)ctx->grids.size() || !ctx->grids[h].used)
+    return ctx->fail(C2G_ERR_ARG, "%s: invalid grid handle %d", who, h);
+  return C2G_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int c2g_init(int device, c2g_context** out) {
+  if (!out) return C2G_ERR_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return C2G_ERR_CUDA;  // no CPU fallback: fail loudly
+  if (device < 0 || device >= ndev) return C2G_ERR_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return C2G_ERR_CUDA;
+  c2g_context* ctx = new c2g_context();
+  ctx->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return C2G_ERR_CUDA; }
+  ctx->nsm = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return C2G_ERR_CUDA; }
+  char buf[256];
+  snprintf(buf, sizeof(buf), "critic2_gpu 0.1 sm_%d%d %s %d SMs %.1f GB", prop.major, prop.minor, prop.name,
+           prop.multiProcessorCount, prop.totalGlobalMem / 1e9);
+  ctx->desc = buf;
+  *out = ctx;
+  return C2G_OK;
+}
+
+int c2g_nccl_unique_id(void* uid128) {
+  if (!uid128) return C2G_ERR_ARG;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  ncclUniqueId id;
+  if (ncclGetUniqueId(&id) != ncclSuccess) return C2G_ERR_NCCL;
+  memcpy(uid128, &id, 128);
+  return C2G_OK;
+}
+
+int c2g_init_multi(int device, int rank, int nranks, const void* uid128, c2g_context** out) {
+  int rc = c2g_init(device, out);
+  if (rc != C2G_OK) return rc;
+  c2g_context* ctx = *out;
+  ctx->rank = rank;
+  ctx->nranks = nranks;
+  if (nranks > 1) {
+    if (!uid128) return ctx->fail(C2G_ERR_ARG, "c2g_init_multi: null nccl id");
+    ncclUniqueId id;
+    memcpy(&id, uid128, 128);
+    ncclComm_t comm;
+    ncclResult_t r = ncclCommInitRank(&comm, nranks, id, rank);
+    if (r != ncclSuccess) return ctx->fail(C2G_ERR_NCCL, "ncclCommInitRank: %s", ncclGetErrorString(r));
+    ctx->nccl = (void*)comm;
+  }
+  return C2G_OK;
+}
+
+void c2g_finalize(c2g_context* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& g : ctx->grids)
+    if (g.used && g.d) cudaFree(g.d);
+  if (ctx->flushbuf) cudaFree(ctx->flushbuf);
+  for (auto e : ctx->event_pool) cudaEventDestroy(e);
+  for (auto& p : ctx->pending) { cudaEventDestroy(p.second.first); cudaEventDestroy(p.second.second); }
+  if (ctx->nccl) ncclCommDestroy((ncclComm_t)ctx->nccl);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* c2g_last_error(const c2g_context* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+const char* c2g_describe(c2g_context* ctx) { return ctx ? ctx->desc.c_str() : ""; }
+
+int c2g_grid_alloc(c2g_context* ctx, const int n[3], int* handle) {
+  if (!ctx) return C2G_ERR_ARG;
+  if (!n || !handle || n[0] < 1 || n[1] < 1 || n[2] < 1) return ctx->fail(C2G_ERR_ARG, "c2g_grid_alloc: bad shape");
+  c2g_grid g;
+  g.n[0] = n[0]; g.n[1] = n[1]; g.n[2] = n[2];
+  g.nn = (long long)n[0] * n[1] * n[2];
+  C2G_CUDA(ctx, cudaMalloc(&g.d, sizeof(double) * g.nn));
+  g.used = true;
+  int h = -1;
+  for (size_t i = 0; i < ctx->grids.size(); i++)
+    if (!ctx->grids[i].used) { h = (int)i; break; }
+  if (h < 0) { ctx->grids.push_back(g); h = (int)ctx->grids.size() - 1; }
+  else ctx->grids[h] = g;
+  *handle = h;
+  return C2G_OK;
+}
+
+int c2g_grid_upload(c2g_context* ctx, const double* f, const int n[3], int* handle) {
+  if (!ctx) return C2G_ERR_ARG;
+  if (!f) return ctx->fail(C2G_ERR_ARG, "c2g_grid_upload: null field");
+  int rc = c2g_grid_alloc(ctx, n, handle);
+  if (rc != C2G_OK) return rc;
+  c2g_grid& g = ctx->grids[*handle];
+  C2G_CUDA(ctx, cudaMemcpyAsync(g.d, f, sizeof(double) * g.nn, cudaMemcpyHostToDevice, ctx->stream));
+  C2G_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return C2G_OK;
+}
+
+int c2g_grid_download(c2g_context* ctx, int handle, double* f) {
+  if (!ctx) return C2G_ERR_ARG;
+  int rc = check_handle(ctx, handle, "c2g_grid_download");
+  if (rc) return rc;
+  if (!f) return ctx->fail(C2G_ERR_ARG, "c2g_grid_download: null output");
+  c2g_grid& g = ctx->grids[handle];
+  C2G_CUDA(ctx, cudaMemcpyAsync(f, g.d, sizeof(double) * g.nn, cudaMemcpyDeviceToHost, ctx->stream));
+  C2G_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return C2G_OK;
+}
+
+int c2g_grid_free(c2g_context* ctx, int handle) {
+  if (!ctx) return C2G_ERR_ARG;
+  int rc = check_handle(ctx, handle, "c2g_grid_free");
+  if (rc) return rc;
+  c2g_grid& g = ctx->grids[handle];
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(g.d);
+  g = c2g_grid();
+  return C2G_OK;
+}
+
+int c2g_grid_promolecular(c2g_context* ctx, int handle, const double x2c[9], int nat, const double* xat,
+                          const double* zat, const double* alpha, int nimg, double rc) {
+  if (!ctx) return C2G_ERR_ARG;
+  int r = check_handle(ctx, handle, "c2g_grid_promolecular");
+  if (r) return r;
+  if (!x2c || nat < 1 || !xat || !zat || !alpha || nimg < 0) return ctx->fail(C2G_ERR_ARG, "c2g_grid_promolecular: bad argument");
+  c2g_grid& g = ctx->grids[handle];
+  cudaStream_t st = ctx->stream;
+  double *dx = nullptr, *dz = nullptr, *da = nullptr;
+  int* dbin = nullptr;
+  // decide on bins: only with a cutoff and an (approximately) orthogonal cell large against rc
+  int nb = 0, reach = 0;
+  if (rc > 0.0 && nat >= 64) {
+    // perpendicular widths of the cell
+    const double a[3] = {x2c[0], x2c[1], x2c[2]}, b[3] = {x2c[3], x2c[4], x2c[5]}, c[3] = {x2c[6], x2c[7], x2c[8]};
+    auto cross = [](const double* u, const double* v, double* w) {
+      w[0] = u[1] * v[2] - u[2] * v[1]; w[1] = u[2] * v[0] - u[0] * v[2]; w[2] = u[0] * v[1] - u[1] * v[0];
+    };
+    auto nrm = [](const double* u) { return std::sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]); };
+    double bc[3], ca[3], ab[3];
+    cross(b, c, bc); cross(c, a, ca); cross(a, b, ab);
+    const double vol = std::fabs(a[0] * bc[0] + a[1] * bc[1] + a[2] * bc[2]);
+    const double wmin = std::min(vol / nrm(bc), std::min(vol / nrm(ca), vol / nrm(ab)));
+    nb = (int)std::floor(wmin / rc * 2.0);  // bin width >= rc/2
+    if (nb >= 5) reach = 2 + 0;  // bin width w >= rc/2  => atoms within rc are at most ceil(rc/w) = 2 bins away
+    else nb = 0;
+    if (nb > 64) { nb = 64; }
+    if (nb) {
+      const double w = wmin / nb;
+      reach = (int)std::ceil(rc / w);
+      if (2 * reach + 1 > nb) nb = 0;
+    }
+  }
+  std::vector<double> sx(3 * (size_t)nat), sz(nat), sa(nat);
+  std::vector<int> binstart;
+  if (nb) {
+    std::vector<int> bin(nat), order(nat);
+    for (int i = 0; i < nat; i++) {
+      int q[3];
+      for (int d = 0; d < 3; d++) {
+        double v = xat[3 * i + d] - std::floor(xat[3 * i + d]);
+        q[d] = std::min((int)(v * nb), nb - 1);
+      }
+      bin[i] = q[0] + nb * (q[1] + nb * q[2]);
+      order[i] = i;
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int u, int v) { return bin[u] < bin[v]; });
+    binstart.assign((size_t)nb * nb * nb + 1, 0);
+    for (int i = 0; i < nat; i++) binstart[bin[i] + 1]++;
+    for (size_t i = 1; i < binstart.size(); i++) binstart[i] += binstart[i - 1];
+    for (int k = 0; k < nat; k++) {
+      const int i = order[k];
+      for (int d = 0; d < 3; d++) sx[3 * k + d] = xat[3 * i + d] - std::floor(xat[3 * i + d]);
+      sz[k] = zat[i]; sa[k] = alpha[i];
+    }
+  } else {
+    std::copy(xat, xat + 3 * (size_t)nat, sx.begin());
+    std::copy(zat, zat + nat, sz.begin());
+    std::copy(alpha, alpha + nat, sa.begin());
+  }
+  C2G_CUDA(ctx, cudaMalloc(&dx, sizeof(double) * 3 * nat));
+  C2G_CUDA(ctx, cudaMalloc(&dz, sizeof(double) * nat));
+  C2G_CUDA(ctx, cudaMalloc(&da, sizeof(double) * nat));
+  C2G_CUDA(ctx, cudaMemcpyAsync(dx, sx.data(), sizeof(double) * 3 * nat, cudaMemcpyHostToDevice, st));
+  C2G_CUDA(ctx, cudaMemcpyAsync(dz, sz.data(), sizeof(double) * nat, cudaMemcpyHostToDevice, st));
+  C2G_CUDA(ctx, cudaMemcpyAsync(da, sa.data(), sizeof(double) * nat, cudaMemcpyHostToDevice, st));
+  ctx->prof_begin("promolecular");
+  if (nb) {
+    C2G_CUDA(ctx, cudaMalloc(&dbin, sizeof(int) * binstart.size()));
+    C2G_CUDA(ctx, cudaMemcpyAsync(dbin, binstart.data(), sizeof(int) * binstart.size(), cudaMemcpyHostToDevice, st));
+    PromolBinParams P;
+    P.n1 = g.n[0]; P.n2 = g.n[1]; P.n3 = g.n[2];
+    memcpy(P.x2c, x2c, sizeof(P.x2c));
+    P.nb = nb; P.reach = reach; P.rc = rc;
+    k_promolecular_bins<<<c2g_blocks_for(g.nn, 256), 256, 0, st>>>(P, dbin, dx, dz, da, g.d);
+  } else {
+    PromolParams P;
+    P.n1 = g.n[0]; P.n2 = g.n[1]; P.n3 = g.n[2];
+    memcpy(P.x2c, x2c, sizeof(P.x2c));
+    P.nat = nat; P.nimg = nimg; P.rc = rc;
+    k_promolecular<<<c2g_blocks_for(g.nn, 256), 256, 0, st>>>(P, dx, dz, da, g.d);
+  }
+  ctx->prof_end();
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(dx); cudaFree(dz); cudaFree(da);
+  if (dbin) cudaFree(dbin);
+  if (e != cudaSuccess) return ctx->fail(C2G_ERR_CUDA, "c2g_grid_promolecular: %s", cudaGetErrorString(e));
+  ctx->prof_collect();
+  return C2G_OK;
+}
+
+// ---- basins bookkeeping ----
+int c2g_basins_maxima(c2g_basins* res, int* pmax) {
+  if (!res || !pmax) return C2G_ERR_ARG;
+  for (int i = 0; i < res->nmax; i++) {
+    const int id = res->max_lin[i];
+    pmax[3 * i + 0] = id % res->n[0] + 1;
+    pmax[3 * i + 1] = (id / res->n[0]) % res->n[1] + 1;
+    pmax[3 * i + 2] = id / (res->n[0] * res->n[1]) + 1;
+  }
+  return C2G_OK;
+}
+
+int c2g_basins_counts(c2g_basins* res, long long* counts) {
+  if (!res || !counts) return C2G_ERR_ARG;
+  for (int i = 0; i < res->nmax; i++) counts[i] = res->counts[i];
+  return C2G_OK;
+}
+
+int c2g_basins_set_map(c2g_basins* res, int nattr, const int* map) {
+  if (!res) return C2G_ERR_ARG;
+  c2g_context* ctx = res->ctx;
+  if (!map || nattr < 0) return ctx->fail(C2G_ERR_ARG, "c2g_basins_set_map: bad argument");
+  for (int i = 0; i < res->nmax; i++)
+    if (map[i] < 0 || map[i] > nattr) return ctx->fail(C2G_ERR_ARG, "c2g_basins_set_map: map(%d)=%d out of range", i + 1, map[i]);
+  res->map.assign(map, map + res->nmax);
+  res->nattr = nattr;
+  if (!res->d_map) C2G_CUDA(ctx, cudaMalloc(&res->d_map, sizeof(int) * std::max(res->nmax, 1)));
+  C2G_CUDA(ctx, cudaMemcpyAsync(res->d_map, res->map.data(), sizeof(int) * res->nmax, cudaMemcpyHostToDevice, ctx->stream));
+  C2G_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  res->has_map = true;
+  return C2G_OK;
+}
+
+int c2g_basins_relabel(c2g_basins* res, int nattr0, const int* assigned, int nattr_new) {
+  if (!res) return C2G_ERR_ARG;
+  c2g_context* ctx = res->ctx;
+  if (!res->has_map) return ctx->fail(C2G_ERR_STATE, "c2g_basins_relabel: no map set");
+  if (nattr0 != res->nattr || !assigned) return ctx->fail(C2G_ERR_ARG, "c2g_basins_relabel: nattr0 mismatch");
+  std::vector<int> m(res->nmax);
+  for (int i = 0; i < res->nmax; i++) {
+    const int old = res->map[i];
+    m[i] = old > 0 ? assigned[old - 1] : 0;
+  }
+  return c2g_basins_set_map(res, nattr_new, m.data());
+}
+
+int c2g_basins_labels(c2g_basins* res, int* idg) {
+  if (!res) return C2G_ERR_ARG;
+  c2g_context* ctx = res->ctx;
+  if (!idg) return ctx->fail(C2G_ERR_ARG, "c2g_basins_labels: null output");
+  if (!res->has_map) return ctx->fail(C2G_ERR_STATE, "c2g_basins_labels: call c2g_basins_set_map first");
+  int* d_out = nullptr;
+  C2G_CUDA(ctx, cudaMalloc(&d_out, sizeof(int) * res->nn));
+  ctx->prof_begin("map_labels");
+  k_map_labels<<<ctx->nsm * 8, 256, 0, ctx->stream>>>(res->nn, res->d_label, res->d_map, d_out);
+  ctx->prof_end();
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(idg, d_out, sizeof(int) * res->nn, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_out);
+  if (e != cudaSuccess) return ctx->fail(C2G_ERR_CUDA, "c2g_basins_labels: %s", cudaGetErrorString(e));
+  ctx->prof_collect();
+  return C2G_OK;
+}
+
+int c2g_basins_stats(c2g_basins* res, long long stats[8]) {
+  if (!res || !stats) return C2G_ERR_ARG;
+  for (int i = 0; i < 8; i++) stats[i] = res->stats[i];
+  return C2G_OK;
+}
+
+void c2g_basins_free(c2g_basins* res) {
+  if (!res) return;
+  if (res->d_label) cudaFree(res->d_label);
+  if (res->d_map) cudaFree(res->d_map);
+  if (res->d_vec) cudaFree(res->d_vec);
+  if (res->d_area) cudaFree(res->d_area);
+  if (res->d_order) cudaFree(res->d_order);
+  delete res;
+}
+
+// ---- profiling ----
+int c2g_profile_enable(c2g_context* ctx, int on) {
+  if (!ctx) return C2G_ERR_ARG;
+  ctx->prof_on = on != 0;
+  return C2G_OK;
+}
+int c2g_profile_count(c2g_context* ctx) { return ctx ? (int)ctx->prof.size() : 0; }
+int c2g_profile_get(c2g_context* ctx, int i, char name[64], double* ms, int* launches) {
+  if (!ctx || i < 0 || i >= (int)ctx->prof.size()) return C2G_ERR_ARG;
+  snprintf(name, 64, "%s", ctx->prof[i].name.c_str());
+  if (ms) *ms = ctx->prof[i].ms;
+  if (launches) *launches = ctx->prof[i].launches;
+  return C2G_OK;
+}
+int c2g_profile_reset(c2g_context* ctx) {
+  if (!ctx) return C2G_ERR_ARG;
+  cudaStreamSynchronize(ctx->stream);
+  ctx->prof_collect();
+  ctx->prof.clear();
+  return C2G_OK;
+}
+long long c2g_launch_count(c2g_context* ctx) { return ctx ? ctx->launches : 0; }
+
+int c2g_flush_l2(c2g_context* ctx) {
+  if (!ctx) return C2G_ERR_ARG;
+  if (!ctx->flushbuf) {
+    ctx->flushbytes = (size_t)256 << 20;  // 256 MiB > 126 MB L2
+    C2G_CUDA(ctx, cudaMalloc(&ctx->flushbuf, ctx->flushbytes));
+  }
+  k_flush<<<ctx->nsm * 4, 256, 0, ctx->stream>>>((float4*)ctx->flushbuf, ctx->flushbytes / 16);
+  C2G_KERNEL_CHECK(ctx);
+  return C2G_OK;
+}
+
+int c2g_synchronize(c2g_context* ctx) {
+  if (!ctx) return C2G_ERR_ARG;
+  C2G_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->prof_collect();
+  return C2G_OK;
+}
+
+}  // extern "C"

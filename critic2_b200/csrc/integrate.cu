@@ -1,0 +1,199 @@
+// integrate.cu -- basin integration of INTEGRABLE grid fields on Bader labels.
+//
+// Replaces the per-attractor masked sums of intgrid_fields (critic2
+// src/integration@proc.f90:1208-1218 volume = count(idg==i)*omega/ntot, :1289-1299
+// padd = sum(fint, idg==i)*omega/ntot): the reference makes nattr full-grid passes per property;
+// this is ONE streaming pass over the labels and up to 4 fields per launch.
+//
+// Layout: each warp owns contiguous 2048-point segments (lane l reads base + 32k + l, so loads
+// are 256-byte coalesced).  Runs of warp-uniform labels are accumulated in registers, reduced with
+// shuffles and added to the per-maximum accumulators with one fp64 atomic per value; 32-point
+// groups that straddle a basin boundary are reduced per distinct label (match_any).
+// HBM traffic: 4 B (label) + 8 B per field per point.
+#include "common.cuh"
+
+namespace {
+
+constexpr int SEG_ITERS = 64;  // 32*64 = 2048 points per warp segment
+
+template <int NP>
+struct Acc {
+  double v[NP > 0 ? NP : 1];
+  unsigned long long cnt;
+};
+
+template <int NP>
+__device__ __forceinline__ void flush_uniform(Acc<NP>& a, int cur, double* __restrict__ sums,
+                                              unsigned long long* __restrict__ counts, int nmax, int lane) {
+  if (cur < 0) return;
+  unsigned long long c = a.cnt;
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+#pragma unroll
+  for (int p = 0; p < NP; p++) {
+    double s = a.v[p];
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if (lane == 0) atomicAdd(sums + (size_t)p * nmax + cur, s);
+    a.v[p] = 0.0;
+  }
+  if (lane == 0 && counts) atomicAdd(counts + cur, c);
+  a.cnt = 0;
+}
+
+template <int NP>
+__global__ void __launch_bounds__(256) k_basin_reduce(long long nn, const int* __restrict__ label,
+                                                      const double* __restrict__ f0, const double* __restrict__ f1,
+                                                      const double* __restrict__ f2, const double* __restrict__ f3,
+                                                      int nmax, double* __restrict__ sums,
+                                                      unsigned long long* __restrict__ counts) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long seg = 32ll * SEG_ITERS;
+  const double* fp[4] = {f0, f1, f2, f3};
+  Acc<NP> a;
+#pragma unroll
+  for (int p = 0; p < (NP > 0 ? NP : 1); p++) a.v[p] = 0.0;
+  a.cnt = 0;
+  int cur = -1;  // warp-uniform label of the current run
+  for (long long base = warp * seg; base < nn; base += nwarps * seg) {
+    for (int k = 0; k < SEG_ITERS; k++) {
+      const long long i = base + 32ll * k + lane;
+      if (base + 32ll * k >= nn) break;
+      int l = -1;
+      double v[NP > 0 ? NP : 1];
+      if (i < nn) {
+        l = label[i];
+#pragma unroll
+        for (int p = 0; p < NP; p++) v[p] = __ldg(fp[p] + i);
+      }
+      if (__all_sync(0xffffffffu, l == cur)) {
+#pragma unroll
+        for (int p = 0; p < NP; p++) a.v[p] += v[p];
+        a.cnt++;
+        continue;
+      }
+      flush_uniform<NP>(a, cur, sums, counts, nmax, lane);
+      const int l0 = __shfl_sync(0xffffffffu, l, 0);
+      if (__all_sync(0xffffffffu, l == l0)) {
+        cur = l0;
+        if (l0 >= 0) {
+#pragma unroll
+          for (int p = 0; p < NP; p++) a.v[p] = v[p];
+          a.cnt = 1;
+        }
+        continue;
+      }
+      // mixed group: one reduction per distinct label
+      cur = -1;
+      unsigned todo = __ballot_sync(0xffffffffu, l >= 0);
+      while (todo) {
+        const int leader = __ffs(todo) - 1;
+        const int ll = __shfl_sync(0xffffffffu, l, leader);
+        const bool mine = (l == ll);
+        const unsigned grp = __ballot_sync(0xffffffffu, mine);
+        unsigned long long c = __popc(grp);
+#pragma unroll
+        for (int p = 0; p < NP; p++) {
+          double s = mine ? v[p] : 0.0;
+#pragma unroll
+          for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+          if (lane == 0) atomicAdd(sums + (size_t)p * nmax + ll, s);
+        }
+        if (lane == 0 && counts) atomicAdd(counts + ll, c);
+        todo &= ~grp;
+      }
+    }
+  }
+  flush_uniform<NP>(a, cur, sums, counts, nmax, lane);
+}
+
+}  // namespace
+
+// sums[(p*nmax)+m], counts[m] per MAXIMUM index (device pointers); fields: up to 4 device arrays
+int c2g_launch_basin_reduce(c2g_context* ctx, long long nn, const int* label, int np, const double* const* f, int nmax,
+                            double* sums, unsigned long long* counts) {
+  const int blocks = ctx->nsm * 8;
+  const double* f0 = np > 0 ? f[0] : nullptr;
+  const double* f1 = np > 1 ? f[1] : nullptr;
+  const double* f2 = np > 2 ? f[2] : nullptr;
+  const double* f3 = np > 3 ? f[3] : nullptr;
+  ctx->prof_begin("basin_reduce");
+  switch (np) {
+    case 0: k_basin_reduce<0><<<blocks, 256, 0, ctx->stream>>>(nn, label, f0, f1, f2, f3, nmax, sums, counts); break;
+    case 1: k_basin_reduce<1><<<blocks, 256, 0, ctx->stream>>>(nn, label, f0, f1, f2, f3, nmax, sums, counts); break;
+    case 2: k_basin_reduce<2><<<blocks, 256, 0, ctx->stream>>>(nn, label, f0, f1, f2, f3, nmax, sums, counts); break;
+    case 3: k_basin_reduce<3><<<blocks, 256, 0, ctx->stream>>>(nn, label, f0, f1, f2, f3, nmax, sums, counts); break;
+    default: k_basin_reduce<4><<<blocks, 256, 0, ctx->stream>>>(nn, label, f0, f1, f2, f3, nmax, sums, counts); break;
+  }
+  ctx->prof_end();
+  C2G_KERNEL_CHECK(ctx);
+  return C2G_OK;
+}
+
+int c2g_yt_integrate_impl(c2g_context* ctx, c2g_basins* res, int nprop, const int* fieldhandles, double omega,
+                          double* psum, double* vol);
+
+extern "C" int c2g_integrate(c2g_context* ctx, c2g_basins* res, int nprop, const int* fieldhandles, double omega,
+                             double* psum, double* vol) {
+  if (!ctx) return C2G_ERR_ARG;
+  if (!res || nprop < 0 || (nprop > 0 && (!fieldhandles || !psum))) return ctx->fail(C2G_ERR_ARG, "c2g_integrate: bad argument");
+  if (!res->has_map) return ctx->fail(C2G_ERR_STATE, "c2g_integrate: call c2g_basins_set_map first");
+  for (int k = 0; k < nprop; k++) {
+    const int h = fieldhandles[k];
+    if (h < 0 || h >= (int)ctx->grids.size() || !ctx->grids[h].used) return ctx->fail(C2G_ERR_ARG, "c2g_integrate: invalid field handle %d", h);
+    const c2g_grid& g = ctx->grids[h];
+    if (g.n[0] != res->n[0] || g.n[1] != res->n[1] || g.n[2] != res->n[2])
+      return ctx->fail(C2G_ERR_ARG, "c2g_integrate: field %d has a different grid size", k + 1);
+  }
+  if (res->kind == 1) return c2g_yt_integrate_impl(ctx, res, nprop, fieldhandles, omega, psum, vol);
+
+  const int nmax = res->nmax, nattr = res->nattr;
+  const double ntot = (double)res->nn;
+  double* d_sums = nullptr;
+  unsigned long long* d_counts = nullptr;
+  std::vector<double> hs((size_t)std::max(nprop, 1) * nmax, 0.0);
+  C2G_CUDA(ctx, cudaMalloc(&d_sums, sizeof(double) * hs.size()));
+  C2G_CUDA(ctx, cudaMalloc(&d_counts, sizeof(unsigned long long) * nmax));
+  C2G_CUDA(ctx, cudaMemsetAsync(d_sums, 0, sizeof(double) * hs.size(), ctx->stream));
+  C2G_CUDA(ctx, cudaMemsetAsync(d_counts, 0, sizeof(unsigned long long) * nmax, ctx->stream));
+  int rc = C2G_OK;
+  bool first = true;
+  for (int k0 = 0; k0 < std::max(nprop, 1) && rc == C2G_OK; k0 += 4) {
+    const int np = std::min(4, nprop - k0);
+    const double* fp[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int p = 0; p < np; p++) fp[p] = ctx->grids[fieldhandles[k0 + p]].d;
+    rc = c2g_launch_basin_reduce(ctx, res->nn, res->d_label, np > 0 ? np : 0, fp, nmax, d_sums + (size_t)k0 * nmax,
+                                 first ? d_counts : nullptr);
+    first = false;
+  }
+  std::vector<unsigned long long> hc(nmax);
+  cudaError_t e = cudaSuccess;
+  if (rc == C2G_OK) {
+    e = cudaMemcpyAsync(hs.data(), d_sums, sizeof(double) * hs.size(), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hc.data(), d_counts, sizeof(unsigned long long) * nmax, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  }
+  cudaFree(d_sums);
+  cudaFree(d_counts);
+  if (rc != C2G_OK) return rc;
+  if (e != cudaSuccess) return ctx->fail(C2G_ERR_CUDA, "c2g_integrate: %s", cudaGetErrorString(e));
+  ctx->prof_collect();
+  // maxima -> basins (several maxima may belong to one attractor; map 0 = discarded)
+  for (int k = 0; k < nprop; k++) {
+    for (int i = 0; i < nattr; i++) psum[i + (size_t)nattr * k] = 0.0;
+    for (int m = 0; m < nmax; m++) {
+      const int b = res->map[m];
+      if (b > 0) psum[(b - 1) + (size_t)nattr * k] += hs[(size_t)k * nmax + m];
+    }
+    for (int i = 0; i < nattr; i++) psum[i + (size_t)nattr * k] = psum[i + (size_t)nattr * k] * omega / ntot;
+  }
+  if (vol) {
+    std::vector<unsigned long long> cb(nattr, 0);
+    for (int m = 0; m < nmax; m++)
+      if (res->map[m] > 0) cb[res->map[m] - 1] += hc[m];
+    for (int i = 0; i < nattr; i++) vol[i] = (double)cb[i] * omega / ntot;
+  }
+  return C2G_OK;
+}

@@ -1,0 +1,352 @@
+// nci.cu -- NCIPLOT reduced-density-gradient loop (grid / tricubic mode) on sm_100a.
+//
+// Replaces the triple loop of nciplot (critic2 src/nci@proc.f90:543-605) for grid fields evaluated
+// with INTERPOLATION GRID (tricubic): per lattice point
+//     x  = x0 + i*xmat(:,1) + j*xmat(:,2) + k*xmat(:,3)                      (nci@proc.f90:548)
+//     wx = c2x*x, wrapped outside [-1e-4, 1+1e-4], modulo 1                   (fieldmod@proc.f90:921-929, grid3mod@proc.f90:1716)
+//     rho, grad, Hessian by the Lekien-Marsden tricubic interpolant           (grid3mod@proc.f90:2649-2821)
+//     s  = |grad rho| / (2 (3 pi^2)^(1/3) max(rho,1e-80)^(4/3))              (nci@proc.f90:91,571)
+//     crho = sign(rho, lambda_2) * 100 ; cgrad = s                            (nci@proc.f90:598-599)
+// The tricubic interpolant with central-difference derivative data is a tensor product of 1-D cubic
+// Hermite (Catmull-Rom) kernels, so the 64x64 matrix-vector product of the reference collapses to three
+// 4-point contractions; at grid nodes (fractional offset exactly 0) it reduces further to the closed
+// forms below, evaluated in the reference's operation order.  Only sign(lambda_2) is consumed, so the
+// middle eigenvalue's sign is taken from Descartes' rule on the characteristic polynomial (all roots
+// real) instead of a LAPACK dsyev call.
+//
+// The coordinate chain decides which cell floor() selects and the tricubic Hessian is discontinuous
+// across cells, so that chain is evaluated with explicit __dmul_rn/__dadd_rn (never fused) in the
+// Fortran left-to-right order.
+//
+// Mapping: a block owns an 8(i) x 2(j) x 16(k) brick of the output lattice; lanes run along i (the
+// fastest index of rho) for the stencil loads, results are staged in shared memory and written with k
+// fastest, which is the reference's cgrad(k,j,i) layout.  HBM traffic: 8 B read + 16 B written per point.
+#include "common.cuh"
+
+#include <cmath>
+
+namespace {
+
+struct NciParams {
+  int n1, n2, n3;          // rho grid
+  int ns1, ns2, ns3;       // output lattice
+  double x0[3], xmat[9];   // Cartesian
+  double c2x[9], x2c[9], c2xl[9];
+  int nnuc;
+};
+
+constexpr int BI = 8, BJ = 2, BK = 16;
+
+__device__ __forceinline__ int imod(int a, int n) {
+  int r = a % n;
+  return r < 0 ? r + n : r;
+}
+
+__device__ __forceinline__ int positive_roots_middle_sign(double hxx, double hyy, double hzz, double hxy, double hxz,
+                                                          double hyz) {
+  // characteristic polynomial l^3 - c2 l^2 + c1 l - c0 ; all roots real => Descartes' rule is exact
+  const double c2 = hxx + hyy + hzz;
+  const double c1 = (hxx * hyy - hxy * hxy) + (hxx * hzz - hxz * hxz) + (hyy * hzz - hyz * hyz);
+  const double c0 = hxx * (hyy * hzz - hyz * hyz) - hxy * (hxy * hzz - hyz * hxz) + hxz * (hxy * hyz - hyy * hxz);
+  const double seq[4] = {1.0, -c2, c1, -c0};
+  int npos = 0, nzero = 0;
+  double prev = 1.0;
+  for (int q = 1; q < 4; q++) {
+    if (seq[q] == 0.0) continue;
+    if ((seq[q] > 0.0) != (prev > 0.0)) npos++;
+    prev = seq[q];
+  }
+  if (c0 == 0.0) { nzero = 1; if (c1 == 0.0) { nzero = 2; if (c2 == 0.0) nzero = 3; } }
+  return (npos + nzero >= 2) ? 1 : -1;  // lambda_2 >= 0 -> +
+}
+
+__global__ void __launch_bounds__(256) k_nci_rdg(const __grid_constant__ NciParams P, const double* __restrict__ rho,
+                                                 const double* __restrict__ nuc, double* __restrict__ crho,
+                                                 double* __restrict__ cgrad) {
+  __shared__ double s_rho[BI * BJ * BK];
+  __shared__ double s_grad[BI * BJ * BK];
+  const int tid = threadIdx.x;
+  const int li = tid % BI, lj = (tid / BI) % BJ, lk = tid / (BI * BJ);
+  const int i = blockIdx.x * BI + li, j = blockIdx.y * BJ + lj, k = blockIdx.z * BK + lk;
+  double out_rho = 0.0, out_grad = 0.0;
+  if (i < P.ns1 && j < P.ns2 && k < P.ns3) {
+    // ---- coordinate chain (never fused) ----
+    double wx[3];
+    {
+      double x[3];
+#pragma unroll
+      for (int d = 0; d < 3; d++) {
+        double v = __dadd_rn(P.x0[d], __dmul_rn((double)i, P.xmat[d]));
+        v = __dadd_rn(v, __dmul_rn((double)j, P.xmat[d + 3]));
+        v = __dadd_rn(v, __dmul_rn((double)k, P.xmat[d + 6]));
+        x[d] = v;
+      }
+#pragma unroll
+      for (int d = 0; d < 3; d++) {
+        double s = __dmul_rn(P.c2x[d], x[0]);
+        s = __dadd_rn(s, __dmul_rn(P.c2x[d + 3], x[1]));
+        s = __dadd_rn(s, __dmul_rn(P.c2x[d + 6], x[2]));
+        if (s < -1e-4 || s > 1.0 + 1e-4) s = s - floor(s);
+        wx[d] = s;
+      }
+    }
+    int idx[3];
+    double t[3];
+    const int nn[3] = {P.n1, P.n2, P.n3};
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      double xi = wx[d] - floor(wx[d]);  // modulo(xi,1d0)
+      if (xi >= 1.0) xi = 0.0;
+      const double xs = __dmul_rn(xi, (double)nn[d]);
+      const int fl = (int)floor(xs);
+      idx[d] = imod(fl, nn[d]);
+      t[d] = xs - (double)idx[d];  // (:2772)
+    }
+    const int xs_[4] = {imod(idx[0] - 1, P.n1), idx[0], imod(idx[0] + 1, P.n1), imod(idx[0] + 2, P.n1)};
+    const int ys_[4] = {imod(idx[1] - 1, P.n2), idx[1], imod(idx[1] + 1, P.n2), imod(idx[1] + 2, P.n2)};
+    const int zs_[4] = {imod(idx[2] - 1, P.n3), idx[2], imod(idx[2] + 1, P.n3), imod(idx[2] + 2, P.n3)};
+    auto G = [&](int a, int b, int c) -> double {  // offsets -1..2
+      return __ldg(rho + xs_[a + 1] + (size_t)P.n1 * (ys_[b + 1] + (size_t)P.n2 * zs_[c + 1]));
+    };
+    double f, gl[3], h[6];  // h: xx, yy, zz, xy, xz, yz in grid (lattice) coordinates, unscaled
+    if (t[0] == 0.0 && t[1] == 0.0 && t[2] == 0.0) {
+      // node: closed forms of a = matmul(c,b) rows (value, first and second derivatives)
+      const double g0 = G(0, 0, 0);
+      const double gxp = G(1, 0, 0), gxm = G(-1, 0, 0), gx2 = G(2, 0, 0);
+      const double gyp = G(0, 1, 0), gym = G(0, -1, 0), gy2 = G(0, 2, 0);
+      const double gzp = G(0, 0, 1), gzm = G(0, 0, -1), gz2 = G(0, 0, 2);
+      f = g0;
+      gl[0] = 0.5 * (gxp - gxm);
+      gl[1] = 0.5 * (gyp - gym);
+      gl[2] = 0.5 * (gzp - gzm);
+      // a_200 = -3 f0 + 3 f1 - 2 d0 - d1 ; second derivative = 2 a_200
+      h[0] = 2.0 * (((-3.0 * g0 + 3.0 * gxp) + (-2.0) * (0.5 * (gxp - gxm))) + (-1.0) * (0.5 * (gx2 - g0)));
+      h[1] = 2.0 * (((-3.0 * g0 + 3.0 * gyp) + (-2.0) * (0.5 * (gyp - gym))) + (-1.0) * (0.5 * (gy2 - g0)));
+      h[2] = 2.0 * (((-3.0 * g0 + 3.0 * gzp) + (-2.0) * (0.5 * (gzp - gzm))) + (-1.0) * (0.5 * (gz2 - g0)));
+      h[3] = 0.25 * (G(1, 1, 0) - G(-1, 1, 0) - G(1, -1, 0) + G(-1, -1, 0));
+      h[4] = 0.25 * (G(1, 0, 1) - G(-1, 0, 1) - G(1, 0, -1) + G(-1, 0, -1));
+      h[5] = 0.25 * (G(0, 1, 1) - G(0, -1, 1) - G(0, 1, -1) + G(0, -1, -1));
+    } else {
+      // general point: tensor-product cubic Hermite with central-difference slopes
+      double w[3][4], w1[3][4], w2[3][4];
+#pragma unroll
+      for (int d = 0; d < 3; d++) {
+        const double u = t[d], u2 = u * u, u3 = u2 * u;
+        w[d][0] = 0.5 * (-u3 + 2.0 * u2 - u);
+        w[d][1] = 0.5 * (3.0 * u3 - 5.0 * u2 + 2.0);
+        w[d][2] = 0.5 * (-3.0 * u3 + 4.0 * u2 + u);
+        w[d][3] = 0.5 * (u3 - u2);
+        w1[d][0] = 0.5 * (-3.0 * u2 + 4.0 * u - 1.0);
+        w1[d][1] = 0.5 * (9.0 * u2 - 10.0 * u);
+        w1[d][2] = 0.5 * (-9.0 * u2 + 8.0 * u + 1.0);
+        w1[d][3] = 0.5 * (3.0 * u2 - 2.0 * u);
+        w2[d][0] = 0.5 * (-6.0 * u + 4.0);
+        w2[d][1] = 0.5 * (18.0 * u - 10.0);
+        w2[d][2] = 0.5 * (-18.0 * u + 8.0);
+        w2[d][3] = 0.5 * (6.0 * u - 2.0);
+      }
+      f = 0.0;
+      gl[0] = gl[1] = gl[2] = 0.0;
+#pragma unroll
+      for (int q = 0; q < 6; q++) h[q] = 0.0;
+#pragma unroll 1
+      for (int c = 0; c < 4; c++) {
+        double p0 = 0, px = 0, pxx = 0, py = 0, pxy = 0, pyy = 0;  // contracted over x and y
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+          double r0 = 0, rx = 0, rxx = 0;
+#pragma unroll
+          for (int a = 0; a < 4; a++) {
+            const double v = G(a - 1, b - 1, c - 1);
+            r0 += w[0][a] * v;
+            rx += w1[0][a] * v;
+            rxx += w2[0][a] * v;
+          }
+          p0 += w[1][b] * r0;
+          px += w[1][b] * rx;
+          pxx += w[1][b] * rxx;
+          py += w1[1][b] * r0;
+          pxy += w1[1][b] * rx;
+          pyy += w2[1][b] * r0;
+        }
+        f += w[2][c] * p0;
+        gl[0] += w[2][c] * px;
+        gl[1] += w[2][c] * py;
+        gl[2] += w1[2][c] * p0;
+        h[0] += w[2][c] * pxx;
+        h[1] += w[2][c] * pyy;
+        h[2] += w2[2][c] * p0;
+        h[3] += w[2][c] * pxy;
+        h[4] += w1[2][c] * px;
+        h[5] += w1[2][c] * py;
+      }
+    }
+    // to fractional coordinates (:2811-2817)
+    const double dn[3] = {(double)P.n1, (double)P.n2, (double)P.n3};
+    double yp[3] = {gl[0] * dn[0], gl[1] * dn[1], gl[2] * dn[2]};
+    double H[3][3];
+    H[0][0] = h[0] * dn[0] * dn[0];
+    H[1][1] = h[1] * dn[1] * dn[1];
+    H[2][2] = h[2] * dn[2] * dn[2];
+    H[0][1] = H[1][0] = h[3] * dn[0] * dn[1];
+    H[0][2] = H[2][0] = h[4] * dn[0] * dn[2];
+    H[1][2] = H[2][1] = h[5] * dn[1] * dn[2];
+    // to Cartesian (grid3mod@proc.f90:1747-1750): yp = matmul(transpose(c2xl),yp); ypp = c2xl^T ypp c2xl
+    double gc[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      double s = __dmul_rn(P.c2xl[0 + 3 * a], yp[0]);
+      s = __dadd_rn(s, __dmul_rn(P.c2xl[1 + 3 * a], yp[1]));
+      s = __dadd_rn(s, __dmul_rn(P.c2xl[2 + 3 * a], yp[2]));
+      gc[a] = s;
+    }
+    double T[3][3], HC[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+      for (int b = 0; b < 3; b++) {
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < 3; q++) s += P.c2xl[q + 3 * a] * H[q][b];
+        T[a][b] = s;
+      }
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+      for (int b = 0; b < 3; b++) {
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < 3; q++) s += T[a][q] * P.c2xl[q + 3 * b];
+        HC[a][b] = s;
+      }
+    // nucleus rule (fieldmod@proc.f90:1148-1155): zero gradient within 1e-5 bohr of an atom
+    if (P.nnuc > 0) {
+      double wc[3];
+#pragma unroll
+      for (int d = 0; d < 3; d++) wc[d] = P.x2c[d] * wx[0] + P.x2c[d + 3] * wx[1] + P.x2c[d + 6] * wx[2];
+      bool isnuc = false;
+      for (int a = 0; a < P.nnuc && !isnuc; a++) {
+        const double dc0 = wc[0] - nuc[3 * a], dc1 = wc[1] - nuc[3 * a + 1], dc2 = wc[2] - nuc[3 * a + 2];
+        double dx[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+          dx[d] = P.c2x[d] * dc0 + P.c2x[d + 3] * dc1 + P.c2x[d + 6] * dc2;
+          dx[d] -= rint(dx[d]);
+        }
+        // minimum image among the 27 nearest translations
+        for (int ta = -1; ta <= 1 && !isnuc; ta++)
+          for (int tb = -1; tb <= 1 && !isnuc; tb++)
+            for (int tc = -1; tc <= 1; tc++) {
+              const double e0 = dx[0] + ta, e1 = dx[1] + tb, e2 = dx[2] + tc;
+              const double q0 = P.x2c[0] * e0 + P.x2c[3] * e1 + P.x2c[6] * e2;
+              const double q1 = P.x2c[1] * e0 + P.x2c[4] * e1 + P.x2c[7] * e2;
+              const double q2 = P.x2c[2] * e0 + P.x2c[5] * e1 + P.x2c[8] * e2;
+              if (sqrt(q0 * q0 + q1 * q1 + q2 * q2) <= 1e-5) { isnuc = true; break; }
+            }
+      }
+      if (isnuc) gc[0] = gc[1] = gc[2] = 0.0;
+    }
+    const double gfmod = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(gc[0], gc[0]), __dmul_rn(gc[1], gc[1])), __dmul_rn(gc[2], gc[2])));
+    const double pi = 3.14159265358979323846264338328;
+    const double cst = 2.0 * pow(3.0 * pi * pi, 1.0 / 3.0);
+    const double dimgrad = gfmod / (cst * pow(fmax(f, 1e-80), 4.0 / 3.0));
+    const int sg = positive_roots_middle_sign(HC[0][0], HC[1][1], HC[2][2], 0.5 * (HC[0][1] + HC[1][0]),
+                                              0.5 * (HC[0][2] + HC[2][0]), 0.5 * (HC[1][2] + HC[2][1]));
+    out_grad = dimgrad;
+    out_rho = (sg > 0 ? fabs(f) : -fabs(f)) * 100.0;
+  }
+  // stage [li][lj][lk] and write with k fastest
+  s_rho[(li * BJ + lj) * BK + lk] = out_rho;
+  s_grad[(li * BJ + lj) * BK + lk] = out_grad;
+  __syncthreads();
+  {
+    const int ok = tid % BK, oj = (tid / BK) % BJ, oi = tid / (BK * BJ);
+    const int gi = blockIdx.x * BI + oi, gj = blockIdx.y * BJ + oj, gk = blockIdx.z * BK + ok;
+    if (gi < P.ns1 && gj < P.ns2 && gk < P.ns3) {
+      const size_t o = (size_t)gk + (size_t)P.ns3 * ((size_t)gj + (size_t)P.ns2 * gi);
+      crho[o] = s_rho[(oi * BJ + oj) * BK + ok];
+      cgrad[o] = s_grad[(oi * BJ + oj) * BK + ok];
+    }
+  }
+}
+
+int nci_launch(c2g_context* ctx, int handle, const double x0[3], const double xmat[9], const int nstep[3],
+               const double c2x[9], const double x2c[9], const double c2xl[9], int nnuc, const double* nuc_cart,
+               double* d_rho, double* d_grad) {
+  const c2g_grid& g = ctx->grids[handle];
+  NciParams P;
+  P.n1 = g.n[0]; P.n2 = g.n[1]; P.n3 = g.n[2];
+  P.ns1 = nstep[0]; P.ns2 = nstep[1]; P.ns3 = nstep[2];
+  memcpy(P.x0, x0, sizeof(P.x0));
+  memcpy(P.xmat, xmat, sizeof(P.xmat));
+  memcpy(P.c2x, c2x, sizeof(P.c2x));
+  memcpy(P.x2c, x2c, sizeof(P.x2c));
+  memcpy(P.c2xl, c2xl, sizeof(P.c2xl));
+  P.nnuc = nnuc;
+  double* d_nuc = nullptr;
+  if (nnuc > 0) {
+    C2G_CUDA(ctx, cudaMalloc(&d_nuc, sizeof(double) * 3 * nnuc));
+    C2G_CUDA(ctx, cudaMemcpyAsync(d_nuc, nuc_cart, sizeof(double) * 3 * nnuc, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  dim3 grid((nstep[0] + BI - 1) / BI, (nstep[1] + BJ - 1) / BJ, (nstep[2] + BK - 1) / BK);
+  ctx->prof_begin("nci_rdg");
+  k_nci_rdg<<<grid, 256, 0, ctx->stream>>>(P, g.d, d_nuc, d_rho, d_grad);
+  ctx->prof_end();
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (d_nuc) cudaFree(d_nuc);
+  if (e != cudaSuccess) return ctx->fail(C2G_ERR_CUDA, "nci_rdg: %s", cudaGetErrorString(e));
+  ctx->prof_collect();
+  return C2G_OK;
+}
+
+int nci_check(c2g_context* ctx, int handle, const double* x0, const double* xmat, const int* nstep, const double* c2x,
+              const double* x2c, const double* c2xl, int nnuc, const double* nuc) {
+  if (handle < 0 || handle >= (int)ctx->grids.size() || !ctx->grids[handle].used)
+    return ctx->fail(C2G_ERR_ARG, "c2g_nci_rdg: invalid grid handle %d", handle);
+  if (!x0 || !xmat || !nstep || !c2x || !x2c || !c2xl || nnuc < 0 || (nnuc > 0 && !nuc))
+    return ctx->fail(C2G_ERR_ARG, "c2g_nci_rdg: null argument");
+  if (nstep[0] < 1 || nstep[1] < 1 || nstep[2] < 1) return ctx->fail(C2G_ERR_ARG, "c2g_nci_rdg: bad nstep");
+  if (ctx->grids[handle].nn >= (1ll << 31)) return ctx->fail(C2G_ERR_ARG, "c2g_nci_rdg: grid too large");
+  return C2G_OK;
+}
+
+}  // namespace
+
+extern "C" int c2g_nci_rdg(c2g_context* ctx, int handle, const double x0[3], const double xmat[9], const int nstep[3],
+                           const double c2x[9], const double x2c[9], const double c2xl[9], int nnuc,
+                           const double* nuc_cart, double* crho, double* cgrad) {
+  if (!ctx) return C2G_ERR_ARG;
+  int rc = nci_check(ctx, handle, x0, xmat, nstep, c2x, x2c, c2xl, nnuc, nuc_cart);
+  if (rc) return rc;
+  if (!crho || !cgrad) return ctx->fail(C2G_ERR_ARG, "c2g_nci_rdg: null output");
+  const size_t nout = (size_t)nstep[0] * nstep[1] * nstep[2];
+  double *d_rho = nullptr, *d_grad = nullptr;
+  C2G_CUDA(ctx, cudaMalloc(&d_rho, sizeof(double) * nout));
+  C2G_CUDA(ctx, cudaMalloc(&d_grad, sizeof(double) * nout));
+  rc = nci_launch(ctx, handle, x0, xmat, nstep, c2x, x2c, c2xl, nnuc, nuc_cart, d_rho, d_grad);
+  cudaError_t e = cudaSuccess;
+  if (rc == C2G_OK) {
+    e = cudaMemcpyAsync(crho, d_rho, sizeof(double) * nout, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(cgrad, d_grad, sizeof(double) * nout, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  }
+  cudaFree(d_rho);
+  cudaFree(d_grad);
+  if (rc) return rc;
+  if (e != cudaSuccess) return ctx->fail(C2G_ERR_CUDA, "c2g_nci_rdg: %s", cudaGetErrorString(e));
+  return C2G_OK;
+}
+
+extern "C" int c2g_nci_rdg_resident(c2g_context* ctx, int handle, const double x0[3], const double xmat[9],
+                                    const int nstep[3], const double c2x[9], const double x2c[9], const double c2xl[9],
+                                    int nnuc, const double* nuc_cart, int* hrho, int* hgrad) {
+  if (!ctx) return C2G_ERR_ARG;
+  int rc = nci_check(ctx, handle, x0, xmat, nstep, c2x, x2c, c2xl, nnuc, nuc_cart);
+  if (rc) return rc;
+  if (!hrho || !hgrad) return ctx->fail(C2G_ERR_ARG, "c2g_nci_rdg_resident: null output");
+  const int nout[3] = {nstep[2], nstep[1], nstep[0]};
+  if ((rc = c2g_grid_alloc(ctx, nout, hrho)) != C2G_OK) return rc;
+  if ((rc = c2g_grid_alloc(ctx, nout, hgrad)) != C2G_OK) return rc;
+  return nci_launch(ctx, handle, x0, xmat, nstep, c2x, x2c, c2xl, nnuc, nuc_cart, ctx->grids[*hrho].d, ctx->grids[*hgrad].d);
+}

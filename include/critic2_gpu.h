@@ -1,0 +1,151 @@
+/*
+ * critic2_gpu.h -- C ABI of the B200-native on-grid QTAIM hot path for critic2.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.
+ * critic2 has no plugin interface for this path (libcritic2.h:46-185 exports
+ * crystal/XRPD calls only), so the entry points below are what a thin
+ * ISO_C_BINDING module placed next to src/c_interface_module.f90 would bind
+ * (see INTEGRATION.md and fortran/critic2_gpu.f90).  Conventions follow the
+ * reference's two existing Fortran<->C idioms:
+ *   - opaque context handles + integer status (doqhull.c:19-27,
+ *     tools@proc.f90:709-728): every call returns 0 on success;
+ *     c2g_last_error() gives the message the Fortran shim forwards to
+ *     ferror(routine,msg,faterr) (tools_io@proc.F90:1573-1643);
+ *   - "step 1 returns sizes, step 2 fills caller-allocated arrays".
+ *
+ * All arrays are caller-owned HOST memory in Fortran layout: f(n1,n2,n3) with
+ * index 1 fastest; 3x3 matrices column-major (m[i+3*j] = M(i+1,j+1)).  Grid
+ * coordinates returned to the caller are 1-based like the Fortran code.
+ * Calls must come from one thread at a time per context (all reference call
+ * sites are outside OpenMP regions: integration@proc.f90:288,298; nci@proc.f90:525).
+ *
+ * There is NO CPU fallback: every compute entry point fails with a non-zero
+ * status if no CUDA device is usable.
+ */
+#ifndef CRITIC2_GPU_H
+#define CRITIC2_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct c2g_context c2g_context; /* one per process / GPU */
+typedef struct c2g_basins c2g_basins;   /* result of a BADER or YT assignment (device resident) */
+
+/* ---- status codes ---- */
+#define C2G_OK 0
+#define C2G_ERR_CUDA 1      /* CUDA runtime error (message has details) */
+#define C2G_ERR_ARG 2       /* invalid argument */
+#define C2G_ERR_NOMEM 3     /* device allocation failed */
+#define C2G_ERR_STATE 4     /* call sequence error (e.g. labels before set_map) */
+#define C2G_ERR_NEWMAX 5    /* internal consistency: walk ended on an unknown maximum */
+#define C2G_ERR_OVERFLOW 6  /* internal table overflow */
+#define C2G_ERR_NCCL 7
+
+/* ---- context ---- */
+/* Create a context on CUDA device `device` (single-GPU use). */
+int c2g_init(int device, c2g_context** ctx);
+/* Multi-GPU: one process per GPU.  `nccl_uid` is the 128-byte ncclUniqueId created by
+ * c2g_nccl_unique_id() on rank 0 and distributed by the caller (MPI/torch.distributed/file). */
+int c2g_nccl_unique_id(void* uid128);
+int c2g_init_multi(int device, int rank, int nranks, const void* nccl_uid128, c2g_context** ctx);
+void c2g_finalize(c2g_context* ctx);
+const char* c2g_last_error(const c2g_context* ctx);
+/* Library / device description, e.g. "critic2_gpu 0.1 sm_100 NVIDIA B200 148 SMs". */
+const char* c2g_describe(c2g_context* ctx);
+
+/* ---- grid3 fields resident in HBM (grid3mod.f90:60-125: n(3), f(:,:,:)) ---- */
+/* Replaces the bas%f copy of intgrid_driver (integration@proc.f90:255-271). */
+int c2g_grid_upload(c2g_context* ctx, const double* f, const int n[3], int* handle);
+int c2g_grid_alloc(c2g_context* ctx, const int n[3], int* handle);
+int c2g_grid_download(c2g_context* ctx, int handle, double* f);
+int c2g_grid_free(c2g_context* ctx, int handle);
+/* Fill a resident grid with the synthetic promolecular-like density
+ *   rho(x) = sum_atoms sum_images Z exp(-alpha r) cut(r), cut = (1-(r/rc)^2)^3 for rc>0 else 1
+ * (stand-in for LOAD AS PROMOLECULAR / promolecular_array3, crystalmod@complex.f90:436-470;
+ * used to create bench inputs of 512^3..1024^3 directly in HBM). xat: (3,nat) cryst. */
+int c2g_grid_promolecular(c2g_context* ctx, int handle, const double x2c[9], int nat, const double* xat,
+                          const double* zat, const double* alpha, int nimg, double rc);
+
+/* ---- BADER: near-grid basin assignment (bader@proc.f90:147-224) ---- */
+/* algo: */
+#define C2G_BADER_FAST 0    /* hierarchical exact walks + edge refinement (default) */
+#define C2G_BADER_EXACT 1   /* referee: every point follows its own complete trajectory */
+/* order of the returned maxima: */
+#define C2G_ORDER_INDEX 0   /* by linear grid index of the maximum */
+#define C2G_ORDER_SCAN 1    /* by the reference scan-order key ((i1-1)*n2+(i2-1))*n3+(i3-1) of the
+                               first point of each basin (approximates discovery order, NOATOMS mode) */
+/* Step 1: label every point with its terminal maximum.  car2lat = inverse of lat2car
+ * (bader@proc.f90:124-129, computed by the caller with matinv), lat_i_dist(-1:1,-1:1,-1:1)
+ * flattened as (d1+1)*9+(d2+1)*3+(d3+1) (:131-145).  Returns the number of distinct maxima. */
+int c2g_bader_assign(c2g_context* ctx, int handle, const double car2lat[9], const double lat_i_dist[27],
+                     int algo, int order, int* nmax, c2g_basins** res);
+/* Step 2: grid coordinates (1-based, 3 x nmax) of the maxima, in the requested order.  The caller
+ * keeps the attractor identification of bader@proc.f90:160-199 (identify_atom, are_lclose, DISCARD). */
+int c2g_basins_maxima(c2g_basins* res, int* pmax);
+/* Number of grid points per maximum (nmax entries). */
+int c2g_basins_counts(c2g_basins* res, long long* counts);
+/* map(nmax): maximum -> basin id (1..nattr; 0 = discarded attractor, points stay unassigned). */
+int c2g_basins_set_map(c2g_basins* res, int nattr, const int* map);
+/* bas%idg(n1,n2,n3) (move_alloc(volnum,bas%idg), bader@proc.f90:229). */
+int c2g_basins_labels(c2g_basins* res, int* idg);
+/* int_reorder_gridout's nattr0 full-grid `where` passes (integration@proc.f90:1113-1122,
+ * :1139-1144) as one composition of maps: new id = assigned(old id), old ids 1..nattr0. */
+int c2g_basins_relabel(c2g_basins* res, int nattr0, const int* assigned, int nattr_new);
+void c2g_basins_free(c2g_basins* res);
+/* statistics of the last assignment: [0] walked points, [1] edge-fix passes, [2] edge-fix points,
+ * [3] path overflows, [4] candidate maxima, [5] total walker steps (EXACT algo only, else 0) */
+int c2g_basins_stats(c2g_basins* res, long long stats[8]);
+
+/* ---- INTEGRABLE: basin integration (integration@proc.f90:1208-1218, :1289-1299) ---- */
+/* psum(nattr,nprop) column-major = sum(fint_k, idg==i)*omega/ntot (Bader) or sum(w_i*fint_k)*omega/ntot
+ * (YT); vol(nattr) = count(idg==i)*omega/ntot or sum(w_i)*omega/ntot.  Requires c2g_basins_set_map.
+ * fieldhandles: nprop resident grids with the same n. */
+int c2g_integrate(c2g_context* ctx, c2g_basins* res, int nprop, const int* fieldhandles, double omega,
+                  double* psum, double* vol);
+
+/* ---- YT: Yu-Trinkle weights (yt@proc.f90:77-211) ---- */
+/* vec(3,nvec), area(nvec): Voronoi-relevant grid steps and facet areas from grid3%init_geometry
+ * (grid3mod@proc.f90:3197).  Maxima are returned in decreasing density (= reference discovery order). */
+int c2g_yt_build(c2g_context* ctx, int handle, int nvec, const int* vec, const double* area, int* nmax,
+                 c2g_basins** res);
+/* spatial basin id per point, 0 = interatomic-surface (fractional) point:
+ * ibasin(iio(.)) of the ytdata record (yt.f90:36-45). */
+/* (use c2g_basins_labels) */
+/* dense weight field of one basin, w(n1,n2,n3) (yt_weights, yt@proc.f90:476-499). */
+int c2g_yt_weights(c2g_basins* res, int idb, double* w);
+/* statistics: [0] IAS points, [1] flux records (sum of nhi over IAS points), [2] sweep levels */
+/* (use c2g_basins_stats) */
+
+/* ---- NCIPLOT: reduced density gradient loop (nci@proc.f90:543-605, grid mode) ---- */
+/* x0(3) Cartesian origin, xmat(3,3) Cartesian step vectors, nstep(3); c2x/x2c crystal matrices,
+ * c2xl grid matrix (grid3mod.f90 c2xl); nnuc nuclei (Cartesian, 3 x nnuc) for the zero-gradient-at-
+ * nucleus rule (fieldmod@proc.f90:1148-1155).  Outputs crho, cgrad(0:nstep3-1,0:nstep2-1,0:nstep1-1),
+ * third index fastest, exactly like the reference arrays (nci@proc.f90:598-599). */
+int c2g_nci_rdg(c2g_context* ctx, int handle, const double x0[3], const double xmat[9], const int nstep[3],
+                const double c2x[9], const double x2c[9], const double c2xl[9], int nnuc,
+                const double* nuc_cart, double* crho, double* cgrad);
+/* same, results stay in HBM (two new grid handles with n = (nstep3,nstep2,nstep1)) */
+int c2g_nci_rdg_resident(c2g_context* ctx, int handle, const double x0[3], const double xmat[9],
+                         const int nstep[3], const double c2x[9], const double x2c[9], const double c2xl[9],
+                         int nnuc, const double* nuc_cart, int* hrho, int* hgrad);
+
+/* ---- profiling: CUDA-event timings of the kernels launched by the last API call ---- */
+int c2g_profile_enable(c2g_context* ctx, int on);
+int c2g_profile_count(c2g_context* ctx);
+/* name (<=63 chars), milliseconds, number of launches accumulated under that name */
+int c2g_profile_get(c2g_context* ctx, int i, char name[64], double* ms, int* launches);
+int c2g_profile_reset(c2g_context* ctx);
+/* total number of kernels launched by this context so far */
+long long c2g_launch_count(c2g_context* ctx);
+/* write a buffer larger than L2 (flush between timed iterations) */
+int c2g_flush_l2(c2g_context* ctx);
+int c2g_synchronize(c2g_context* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRITIC2_GPU_H */

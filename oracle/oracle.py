@@ -1,0 +1,257 @@
+"""ctypes front end of the CPU oracle (oracle/liboracle.so).
+
+TEST INFRASTRUCTURE ONLY -- see the header of oracle/oracle.cpp.  Only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  Parity status: "parity unpinned" (no Fortran compiler and
+no reference input grids in this image).
+
+Arrays are Fortran-ordered numpy arrays f[n1,n2,n3] (index 1 fastest in memory).
+3x3 matrices are numpy arrays M[i,j] passed in Fortran (column-major) order.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(_HERE, "liboracle.so")
+    src = os.path.join(_HERE, "oracle.cpp")
+    if force or not os.path.exists(so) or (
+        os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(so)
+    ):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+    return _LIB
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _f64(a):
+    return np.asfortranarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.asfortranarray(a, dtype=np.int32)
+
+
+def _m33(m):
+    """3x3 matrix -> 9 doubles, column-major."""
+    return np.asfortranarray(np.asarray(m, dtype=np.float64)).ravel(order="F").copy()
+
+
+def num_threads() -> int:
+    return int(lib().orc_num_threads())
+
+
+def bader_metrics(x2c, n):
+    """lat2car, car2lat, lat_i_dist as computed in bader_integrate (bader@proc.f90:124-145).
+    car2lat uses numpy.linalg.inv (LAPACK getrf/getri like the reference's matinv)."""
+    x2c = np.asarray(x2c, dtype=np.float64)
+    lat2car = x2c / np.asarray(n, dtype=np.float64)[None, :]
+    car2lat = np.linalg.inv(lat2car)
+    lid = np.zeros((3, 3, 3))
+    for i in (-1, 0, 1):
+        for j in (-1, 0, 1):
+            for k in (-1, 0, 1):
+                if i == j == k == 0:
+                    continue
+                d = lat2car @ np.array([i, j, k], dtype=np.float64)
+                lid[i + 1, j + 1, k + 1] = 1.0 / np.sqrt(np.sum(d * d))
+    return lat2car, car2lat, lid
+
+
+def bader_integrate(f, x2c, atoms=None, ratom=1.0, atexist=True, maxattr=None):
+    """Faithful bader_integrate.  Returns (idg[n1,n2,n3] int32, nattr, xattr[3,nattr], stats)."""
+    f = _f64(f)
+    n = np.array(f.shape, dtype=np.int32)
+    _, car2lat, lid = bader_metrics(x2c, n)
+    xat = np.zeros((3, 0)) if atoms is None else _f64(np.asarray(atoms, dtype=np.float64).T)
+    nat = xat.shape[1]
+    if maxattr is None:
+        maxattr = nat + 100000
+    idg = np.zeros(f.shape, dtype=np.int32, order="F")
+    nattr = C.c_int(0)
+    xattr = np.zeros((3, maxattr), order="F")
+    stats = np.zeros(4, dtype=np.int64)
+    c2l = _m33(car2lat)
+    lidf = np.ascontiguousarray(lid, dtype=np.float64).ravel()  # (d1+1)*9+(d2+1)*3+(d3+1)
+    x2cf = _m33(x2c)
+    rc = lib().orc_bader_integrate(
+        _p(f, C.c_double), _p(n, C.c_int), _p(c2l, C.c_double), _p(lidf, C.c_double), _p(x2cf, C.c_double),
+        C.c_int(1 if (atexist and nat > 0) else 0), C.c_int(nat), _p(xat, C.c_double), C.c_double(ratom),
+        _p(idg, C.c_int), C.byref(nattr), _p(xattr, C.c_double), C.c_int(maxattr), _p(stats, C.c_long))
+    if rc != 0:
+        raise RuntimeError(f"orc_bader_integrate failed rc={rc}")
+    return idg, nattr.value, xattr[:, : nattr.value].copy(), stats
+
+
+def bader_canonical(f, x2c):
+    """Own-trajectory terminal maximum (0-based linear id) of every point + stats."""
+    f = _f64(f)
+    n = np.array(f.shape, dtype=np.int32)
+    _, car2lat, lid = bader_metrics(x2c, n)
+    term = np.zeros(f.shape, dtype=np.int32, order="F")
+    stats = np.zeros(4, dtype=np.int64)
+    c2l = _m33(car2lat)
+    lidf = np.ascontiguousarray(lid, dtype=np.float64).ravel()
+    lib().orc_bader_canonical(_p(f, C.c_double), _p(n, C.c_int), _p(c2l, C.c_double), _p(lidf, C.c_double),
+                              _p(term, C.c_int), _p(stats, C.c_long))
+    return term, stats
+
+
+def integrate_bader(idg, fields, nattr, omega):
+    idg = _i32(idg)
+    n = np.array(idg.shape, dtype=np.int32)
+    fl = [_f64(x) for x in fields]
+    arr = (C.POINTER(C.c_double) * max(len(fl), 1))(*[_p(x, C.c_double) for x in fl])
+    vol = np.zeros(nattr)
+    psum = np.zeros((nattr, len(fl)), order="F")
+    lib().orc_integrate_bader(_p(idg, C.c_int), _p(n, C.c_int), C.c_int(nattr), C.c_int(len(fl)), arr,
+                              C.c_double(omega), _p(vol, C.c_double), _p(psum, C.c_double))
+    return vol, psum
+
+
+def qcksort(arr):
+    """Returns the 1-based permutation iord produced by qcksort_r8 (tools@proc.f90:83-168)."""
+    arr = np.ascontiguousarray(arr, dtype=np.float64)
+    iord = np.arange(1, arr.size + 1, dtype=np.int32)
+    rc = lib().orc_qcksort_r8(_p(arr, C.c_double), _p(iord, C.c_int), C.c_int(1), C.c_int(arr.size))
+    if rc != 0:
+        raise RuntimeError("qcksort: Increase nstack")
+    return iord
+
+
+class YtData:
+    """ytdata record (yt.f90:36-45), rank-indexed."""
+
+    def __init__(self, nn, nvec):
+        self.nn, self.nvec = nn, nvec
+        self.nlo = np.zeros(nn, dtype=np.int32)
+        self.ibasin = np.zeros(nn, dtype=np.int32)
+        self.iio = np.zeros(nn, dtype=np.int32)
+        self.inear = np.zeros((nvec, nn), dtype=np.int32, order="F")
+        self.fnear = np.zeros((nvec, nn), dtype=np.float64, order="F")
+        self.nattr = 0
+        self.xattr = None
+
+    def spatial_basin(self, shape):
+        """ibasin looked up through iio: basin id of each spatial point (0 = IAS)."""
+        return self.ibasin[self.iio - 1].reshape(shape, order="F")
+
+
+def yt_integrate(f, x2c, vec, area, atoms=None, ratom=1.0, atexist=True, stable=False, maxattr=None):
+    f = _f64(f)
+    n = np.array(f.shape, dtype=np.int32)
+    nn = f.size
+    vec = _i32(np.asarray(vec).reshape(-1, 3).T)  # (3,nvec) column-major
+    nvec = vec.shape[1]
+    area = np.ascontiguousarray(area, dtype=np.float64)
+    xat = np.zeros((3, 0)) if atoms is None else _f64(np.asarray(atoms, dtype=np.float64).T)
+    nat = xat.shape[1]
+    if maxattr is None:
+        maxattr = nat + 100000
+    d = YtData(nn, nvec)
+    nattr = C.c_int(0)
+    xattr = np.zeros((3, maxattr), order="F")
+    x2cf = _m33(x2c)
+    rc = lib().orc_yt_integrate(
+        _p(f, C.c_double), _p(n, C.c_int), C.c_int(nvec), _p(vec, C.c_int), _p(area, C.c_double),
+        _p(x2cf, C.c_double), C.c_int(1 if (atexist and nat > 0) else 0), C.c_int(nat), _p(xat, C.c_double),
+        C.c_double(ratom), C.c_int(1 if stable else 0),
+        _p(d.nlo, C.c_int), _p(d.ibasin, C.c_int), _p(d.iio, C.c_int), _p(d.inear, C.c_int),
+        _p(d.fnear, C.c_double), C.byref(nattr), _p(xattr, C.c_double), C.c_int(maxattr))
+    if rc != 0:
+        raise RuntimeError(f"orc_yt_integrate failed rc={rc}")
+    d.nattr = nattr.value
+    d.xattr = xattr[:, : d.nattr].copy()
+    return d
+
+
+def yt_weights(d: YtData, idb: int, shape):
+    w = np.zeros(shape, order="F")
+    lib().orc_yt_weights(C.c_long(d.nn), C.c_int(d.nvec), _p(d.nlo, C.c_int), _p(d.ibasin, C.c_int),
+                         _p(d.iio, C.c_int), _p(d.inear, C.c_int), _p(d.fnear, C.c_double), C.c_int(idb),
+                         _p(w, C.c_double))
+    return w
+
+
+def integrate_yt(d: YtData, fields, omega):
+    fl = [_f64(x) for x in fields]
+    arr = (C.POINTER(C.c_double) * max(len(fl), 1))(*[_p(x, C.c_double) for x in fl])
+    vol = np.zeros(d.nattr)
+    psum = np.zeros((d.nattr, len(fl)), order="F")
+    lib().orc_integrate_yt(C.c_long(d.nn), C.c_int(d.nvec), _p(d.nlo, C.c_int), _p(d.ibasin, C.c_int),
+                           _p(d.iio, C.c_int), _p(d.inear, C.c_int), _p(d.fnear, C.c_double),
+                           C.c_int(d.nattr), C.c_int(len(fl)), arr, C.c_double(omega),
+                           _p(vol, C.c_double), _p(psum, C.c_double))
+    return vol, psum
+
+
+def tricubic_matrix():
+    c = np.zeros((64, 64), order="F")
+    lib().orc_tricubic_matrix(_p(c, C.c_double))
+    return c
+
+
+def grid_interp_tricubic(f, c2xl, xi):
+    f = _f64(f)
+    n = np.array(f.shape, dtype=np.int32)
+    xi = np.ascontiguousarray(xi, dtype=np.float64)
+    y = C.c_double(0)
+    yp = np.zeros(3)
+    ypp = np.zeros((3, 3), order="F")
+    m = _m33(c2xl)
+    lib().orc_grid_interp_tricubic(_p(f, C.c_double), _p(n, C.c_int), _p(m, C.c_double), _p(xi, C.c_double),
+                                   C.byref(y), _p(yp, C.c_double), _p(ypp, C.c_double))
+    return y.value, yp, ypp
+
+
+def nci_rdg(f, x2c, nstep=None, x0=None, xmat=None, nuclei_cart=None, want_lam2=False):
+    """NCIPLOT grid-mode loop.  Default lattice = the periodic, node-aligned one
+    (nci@proc.f90:412-427): nstep = grid n, xmat(:,i) = x2c(:,i)/nstep(i), x0 = 0."""
+    f = _f64(f)
+    n = np.array(f.shape, dtype=np.int32)
+    x2c = np.asarray(x2c, dtype=np.float64)
+    c2x = np.linalg.inv(x2c)
+    nstep = np.array(n if nstep is None else nstep, dtype=np.int32)
+    if xmat is None:
+        xmat = x2c / nstep.astype(np.float64)[None, :]
+    x0 = np.zeros(3) if x0 is None else np.ascontiguousarray(x0, dtype=np.float64)
+    nuc = np.zeros((0, 3)) if nuclei_cart is None else np.ascontiguousarray(nuclei_cart, dtype=np.float64)
+    shape = (int(nstep[2]), int(nstep[1]), int(nstep[0]))  # (k,j,i), k fastest
+    crho = np.zeros(shape, order="F")
+    cgrad = np.zeros(shape, order="F")
+    lam2 = np.zeros(shape, order="F") if want_lam2 else None
+    lib().orc_nci_rdg(_p(f, C.c_double), _p(n, C.c_int), _p(x0, C.c_double), _p(_m33(xmat), C.c_double),
+                      _p(nstep, C.c_int), _p(_m33(c2x), C.c_double), _p(_m33(x2c), C.c_double),
+                      _p(_m33(c2x), C.c_double), C.c_int(nuc.shape[0]), _p(nuc, C.c_double),
+                      _p(crho, C.c_double), _p(cgrad, C.c_double),
+                      _p(lam2, C.c_double) if want_lam2 else None)
+    return (crho, cgrad, lam2) if want_lam2 else (crho, cgrad)
+
+
+def promolecular(n, x2c, atoms, z, alpha, nimg=1, rc=0.0):
+    n = np.array(n, dtype=np.int32)
+    xat = np.ascontiguousarray(atoms, dtype=np.float64)
+    z = np.ascontiguousarray(z, dtype=np.float64)
+    alpha = np.ascontiguousarray(alpha, dtype=np.float64)
+    f = np.zeros(tuple(int(x) for x in n), order="F")
+    lib().orc_promolecular(_p(n, C.c_int), _p(_m33(x2c), C.c_double), C.c_int(xat.shape[0]),
+                           _p(xat, C.c_double), _p(z, C.c_double), _p(alpha, C.c_double), C.c_int(nimg),
+                           C.c_double(rc), _p(f, C.c_double))
+    return f
