@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native critic2 on-grid QTAIM hot path.
+
+Metric (BASELINE.json): grid points/s for BADER assign + integrate.  One "step" = one pass of the hot
+path over one synthetic grid: c2g_bader_assign (near-grid basin assignment) + c2g_integrate (Volume,
+rho and a second INTEGRABLE grid; P_f = 2, 32 algorithmic bytes per grid point).
+
+Workload (config.workload): BASELINE.json configs[4] -- a 1024^3 synthetic periodic promolecular-like
+density, cubic 40 bohr cell, 512 atoms (jittered 8x8x8 lattice, seed 5), generated directly in HBM.  It
+fits one B200 (rho 8.6 GB + second field 8.6 GB + labels 4.3 GB + work lists), so it is also the N=1
+workload; at N>1 the same grid is sharded as z-slabs (strong scaling).
+
+Arms:
+  default            this repository's CUDA path through the C ABI (critic2_b200/libcritic2_gpu.so)
+  --impl reference   critic2's own CPU algorithm.  critic2 is Fortran and cannot be compiled in this
+                     image (no Fortran compiler), so this arm times the C++ restatement in oracle/
+                     (kind "port") on a bounded sample of the same density model with all host threads
+                     the reference would use (its Bader assignment is serial; the integration is
+                     OpenMP over attractors).
+
+JSON keys follow the driver's contract; see DESIGN.md section "Measurement".
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+ALG_BYTES_ASSIGN = 12.0      # read rho (8) + write label (4)            SURVEY.md 8(d)
+ALG_BYTES_INTEGRATE = 20.0   # read label (4) + 2 fp64 integrand grids   SURVEY.md 8(d)
+ALG_BYTES_TOTAL = ALG_BYTES_ASSIGN + ALG_BYTES_INTEGRATE
+
+
+def max_over_ranks(x: float) -> float:
+    """Max over ranks of a host float (identity when torch.distributed is not initialised)."""
+    try:
+        import torch
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+            t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+    except ImportError:
+        pass
+    return float(x)
+
+
+def barrier():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.barrier()
+    except ImportError:
+        pass
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}",
+                 "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def workload(size: int):
+    """Density model of configs[4] scaled to `size`^3: 5 bohr atom spacing, 128 grid points per atom
+    spacing at 1024^3 (side = size/128 atoms per axis, at least 2)."""
+    import systems as S
+    side = max(2, size // 128)
+    n = (size, size, size)
+    x2c = S.cell_x2c(5.0 * side, 5.0 * side, 5.0 * side)
+    at, z, al = S.jittered_lattice(side, 5)
+    at = S.snap_to_grid(at, n)
+    return n, x2c, at, z, al, side
+
+
+def bader_metrics(x2c, n):
+    lat2car = x2c / np.asarray(n, dtype=np.float64)[None, :]
+    car2lat = np.linalg.inv(lat2car)
+    lid = np.zeros((3, 3, 3))
+    for i in (-1, 0, 1):
+        for j in (-1, 0, 1):
+            for k in (-1, 0, 1):
+                if (i, j, k) != (0, 0, 0):
+                    lid[i + 1, j + 1, k + 1] = 1.0 / np.linalg.norm(lat2car @ np.array([i, j, k], dtype=float))
+    return car2lat, lid
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline (oracle): bounded sample of the same density model
+# ------------------------------------------------------------------------------------------------
+def cpu_baseline_run(sample_n=(256, 256, 128), steps=1):
+    """Times the oracle's faithful bader_integrate (serial, like the reference) + integrate_bader
+    (OpenMP over attractors, like the reference) on a sample grid of the same model (128 points per atom
+    spacing).  Returns points/s and a description."""
+    import systems as S
+    from oracle import oracle as orc
+    n = tuple(int(x) for x in sample_n)
+    sides = [max(1, x // 128) for x in n]
+    x2c = S.cell_x2c(5.0 * sides[0], 5.0 * sides[1], 5.0 * sides[2])
+    rng = np.random.default_rng(5)
+    g = np.stack(np.meshgrid(*[np.arange(s) for s in sides], indexing="ij"), -1).reshape(-1, 3).astype(float)
+    at = (g + 0.5) / np.array(sides)[None, :] + rng.uniform(-0.15, 0.15, g.shape) / np.array(sides)[None, :]
+    at = S.snap_to_grid(at % 1.0, n)
+    z = rng.uniform(1.0, 8.0, len(at)); al = rng.uniform(1.2, 2.7, len(at))
+    f = orc.promolecular(n, x2c, at, z, al, nimg=1, rc=8.0)
+    f2 = np.asfortranarray(np.roll(f, 3, 0) * 0.5)
+    best = None
+    for _ in range(max(1, steps)):
+        t0 = time.perf_counter()
+        idg, nattr, _, stats = orc.bader_integrate(f, x2c, atoms=at)
+        t1 = time.perf_counter()
+        orc.integrate_bader(idg, [f, f2], nattr, S.omega(x2c))
+        t2 = time.perf_counter()
+        dt = t2 - t0
+        if best is None or dt < best[0]:
+            best = (dt, t1 - t0, t2 - t1)
+    npts = float(np.prod(n))
+    return {
+        "value": npts / best[0], "unit": "grid points/s", "cores": int(orc.num_threads()), "kind": "port",
+        "sample": f"{n[0]}x{n[1]}x{n[2]} grid of the same density model ({len(at)} atoms, 128 points per atom spacing); "
+                  f"oracle bader_integrate (serial like bader@proc.f90) {best[1]:.1f} s + integrate (OpenMP over attractors) {best[2]:.2f} s",
+        "seconds": best[0],
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    t_all = time.perf_counter()
+    res = cpu_baseline_run(steps=1)
+    for _ in range(max(0, min(args.steps, 3) - 1)):
+        r2 = cpu_baseline_run(steps=1)
+        if r2["value"] > res["value"]:
+            res = r2
+    size = args.size
+    out = {
+        "impl": "reference", "metric": "grid points/s, BADER assign+integrate", "value": res["value"], "unit": "grid points/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["seconds"] * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"BADER assign + INTEGRABLE (Volume, rho, second grid) on a synthetic {size}^3 promolecular-like "
+                               "periodic density (BASELINE.json configs[4]); reference arm timed on a bounded sample",
+                   "sample": res["sample"]},
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": res["value"], "unit": "grid points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "critic2 (Fortran) cannot be compiled in this image; this is the C++ restatement in oracle/ of the reference's own CPU algorithm",
+        "wall_s": time.perf_counter() - t_all,
+    }
+    print(json.dumps(out), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    from critic2_b200 import capi
+
+    uid = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        buf = ctypes.create_string_buffer(128)
+        if rank == 0:
+            rc = capi.load().c2g_nccl_unique_id(buf)
+            if rc != 0:
+                raise SystemExit("c2g_nccl_unique_id failed")
+        t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).cuda()
+        dist.broadcast(t, 0)
+        uid = ctypes.create_string_buffer(bytes(t.cpu().numpy().tobytes()), 128)
+    ctx = capi.Context(local, rank=rank, nranks=world, nccl_uid=uid)
+
+    size = args.size
+    n, x2c, at, z, al, side = workload(size)
+    nn = float(np.prod(n))
+    car2lat, lid = bader_metrics(x2c, n)
+    omega = abs(np.linalg.det(x2c))
+
+    # inputs resident in HBM (generated on the device; every rank holds the replicated read-only field)
+    h_rho = ctx.alloc(n)
+    ctx.promolecular(h_rho, x2c, at, z, al, nimg=1, rc=8.0)
+    h_f2 = ctx.alloc(n)
+    ctx.promolecular(h_f2, x2c, at, z * 0.5, al * 1.3, nimg=1, rc=8.0)
+
+    ident = None
+
+    def step_resident():
+        nonlocal ident
+        b = ctx.bader_assign(h_rho, car2lat, lid, algo=capi.BADER_FAST)
+        if ident is None or len(ident) != b.nmax:
+            ident = np.arange(1, b.nmax + 1, dtype=np.int32)
+        b.set_map(b.nmax, ident)
+        vol, ps = ctx.integrate(b, [h_rho, h_f2], omega)
+        return b, vol, ps
+
+    # ---- warm-up ----
+    for _ in range(max(args.warmup, 3)):
+        b, vol, ps = step_resident()
+        nmax = b.nmax
+        b.free()
+    pop_sum = float(ps[:, 0].sum())
+
+    # ---- timed region: device-resident inputs ----
+    ctx.profile_enable(True)
+    ctx.profile_reset()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = ctx.launch_count()
+    barrier(); ctx.synchronize()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        b, vol, ps = step_resident()
+        b.free()
+    ms = ctx.timer_stop()
+    barrier()
+    launches = ctx.launch_count() - l0
+    clk = clocks.stop() if rank == 0 else None
+    ms_step = max_over_ranks(ms / args.steps)
+    prof = ctx.profile()
+    ctx.profile_enable(False)
+    value = nn / (ms_step * 1e-3)
+
+    # ---- roofline (measured live: CUDA events around every kernel of the timed region) ----
+    peak, peak_src = measured_peaks()
+    assign_ms = sum(v[0] for k, v in prof.items() if k.startswith("bader_")) / args.steps
+    integ_ms = sum(v[0] for k, v in prof.items() if k.startswith("basin_")) / args.steps
+    walk_ms = sum(v[0] for k, v in prof.items() if k.startswith("bader_walk")) / args.steps
+    zlo, zhi = ctx.slab_range(n[2])
+    nloc = float(n[0] * n[1] * (zhi - zlo))
+    kern_ms = max_over_ranks(assign_ms + integ_ms)
+    achieved = ALG_BYTES_TOTAL * nloc / (max(assign_ms + integ_ms, 1e-9) * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": "BADER assign+integrate kernel group (k_maxima, k_walk_*, k_classify, k_edgefix, k_compact, k_basin_reduce); "
+                                  "dominant: k_walk_list",
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+        "algorithmic_bytes_per_point": ALG_BYTES_TOTAL, "points_per_launch_group": nloc, "traffic": None,
+        "stages": {
+            "assign": {"ms": assign_ms, "GBps": ALG_BYTES_ASSIGN * nloc / max(assign_ms, 1e-9) / 1e6, "of_which_walk_ms": walk_ms},
+            "integrate": {"ms": integ_ms, "GBps": ALG_BYTES_INTEGRATE * nloc / max(integ_ms, 1e-9) / 1e6},
+        },
+        "kernels_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in prof.items()},
+        "kernel_group_ms_max_over_ranks": kern_ms,
+    }
+
+    # ---- e2e: through the C ABI with HOST buffers (pinned), H2D + D2H inside the timed region ----
+    plane = n[0] * n[1]
+    nzl = zhi - zlo
+    host_rho = torch.empty(max(1, plane * nzl), dtype=torch.float64, pin_memory=True)
+    host_f2 = torch.empty(max(1, plane * nzl), dtype=torch.float64, pin_memory=True)
+    host_idg = torch.empty(max(1, plane * nzl), dtype=torch.int32, pin_memory=True)
+    ctx.download_slab_ptr(h_rho, host_rho.data_ptr())
+    ctx.download_slab_ptr(h_f2, host_f2.data_ptr())
+
+    def step_e2e():
+        nonlocal ident
+        if world > 1:
+            ha = ctx.upload_slab_ptr(host_rho.data_ptr(), n)
+            hb = ctx.upload_slab_ptr(host_f2.data_ptr(), n)
+        else:
+            ha = ctx.upload_ptr(host_rho.data_ptr(), n)
+            hb = ctx.upload_ptr(host_f2.data_ptr(), n)
+        bb = ctx.bader_assign(ha, car2lat, lid, algo=capi.BADER_FAST)
+        if ident is None or len(ident) != bb.nmax:
+            ident = np.arange(1, bb.nmax + 1, dtype=np.int32)
+        bb.set_map(bb.nmax, ident)
+        v, p = ctx.integrate(bb, [ha, hb], omega)
+        bb.labels_ptr(host_idg.data_ptr())
+        bb.free(); ctx.free(ha); ctx.free(hb)
+        return p
+
+    e2e_steps = max(1, min(args.steps, 3))
+    step_e2e()  # warm-up
+    barrier(); ctx.synchronize()
+    ctx.timer_start()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        pe = step_e2e()
+    ms_e = ctx.timer_stop()
+    wall_e = (time.perf_counter() - t0) * 1e3
+    barrier()
+    ms_e2e = max_over_ranks(max(ms_e, wall_e) / e2e_steps)
+    e2e = {"value": nn / (ms_e2e * 1e-3), "unit": "grid points/s", "ms_per_step": ms_e2e, "steps": e2e_steps,
+           "h2d_bytes_per_step": int(2 * 8 * nn), "d2h_bytes_per_step": int(4 * nn + 8 * 3 * nmax),
+           "pop_sum_matches_resident": bool(abs(float(pe[:, 0].sum()) - pop_sum) <= 1e-9 * abs(pop_sum))}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only; bounded sample) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            cpu = cpu_baseline_run(steps=1)
+            cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as e:  # the oracle is optional test infrastructure
+            cpu = {"value": None, "unit": "grid points/s", "cores": 0, "kind": "port", "sample": f"unavailable: {e}"}
+
+    if rank == 0:
+        out = {
+            "metric": "grid points/s, BADER assign+integrate", "value": value, "unit": "grid points/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"BADER assign + INTEGRABLE (Volume, rho, second grid; P_f=2) on a synthetic {size}^3 "
+                                   f"promolecular-like periodic density, cubic {5.0 * side:.0f} bohr cell, {side**3} atoms "
+                                   "(BASELINE.json configs[4])",
+                       "grid": list(n), "atoms": side ** 3, "maxima": nmax, "parallelism": f"z-slabs x{world}" if world > 1 else "single GPU",
+                       "l2": "inputs (>= 1 GB per field) are larger than the 126 MB L2; no flush needed",
+                       "algo": "hierarchical exact near-grid walks + edge refinement (C2G_BADER_FAST)"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
+            "device": ctx.describe(), "check": {"population_sum": pop_sum, "volume_sum_over_omega": float(vol.sum() / omega)},
+        }
+        print(json.dumps(out), flush=True)
+    ctx.free(h_rho); ctx.free(h_f2)
+    ctx.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=1024, help="grid points per axis (default: the 1024^3 headline config)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -20,11 +20,11 @@ ORDER_INDEX, ORDER_SCAN = 0, 1
 
 EXPORTS = [
     "c2g_init", "c2g_nccl_unique_id", "c2g_init_multi", "c2g_finalize", "c2g_last_error", "c2g_describe",
-    "c2g_grid_upload", "c2g_grid_alloc", "c2g_grid_download", "c2g_grid_free", "c2g_grid_promolecular",
+    "c2g_grid_upload", "c2g_grid_upload_slab", "c2g_slab_range", "c2g_slab_bounds_query", "c2g_grid_alloc", "c2g_grid_download", "c2g_grid_download_slab", "c2g_grid_free", "c2g_grid_promolecular",
     "c2g_bader_assign", "c2g_basins_maxima", "c2g_basins_counts", "c2g_basins_set_map", "c2g_basins_labels",
     "c2g_basins_relabel", "c2g_basins_free", "c2g_basins_stats", "c2g_integrate", "c2g_yt_build",
     "c2g_yt_weights", "c2g_nci_rdg", "c2g_nci_rdg_resident", "c2g_profile_enable", "c2g_profile_count",
-    "c2g_profile_get", "c2g_profile_reset", "c2g_launch_count", "c2g_flush_l2", "c2g_synchronize",
+    "c2g_profile_get", "c2g_profile_reset", "c2g_launch_count", "c2g_flush_l2", "c2g_synchronize", "c2g_timer_start", "c2g_timer_stop",
 ]
 
 
@@ -55,6 +55,15 @@ def _p(a, t):
 
 def _m33(m):
     return np.asfortranarray(np.asarray(m, dtype=np.float64)).ravel(order="F").copy()
+
+
+def slab_bounds(n3, nranks, rank):
+    """z-slab [zlo, zhi) owned by `rank` (host arithmetic only, no GPU needed)."""
+    a, b = C.c_int(0), C.c_int(0)
+    rc = load().c2g_slab_bounds_query(C.c_int(int(n3)), C.c_int(int(nranks)), C.c_int(int(rank)), C.byref(a), C.byref(b))
+    if rc != 0:
+        raise C2GError(f"c2g_slab_bounds_query: status {rc}")
+    return a.value, b.value
 
 
 class Context:
@@ -89,6 +98,19 @@ class Context:
         n = np.array(f.shape, dtype=np.int32)
         h = C.c_int(-1)
         self._chk(self.lib.c2g_grid_upload(self.h, _p(f, C.c_double), _p(n, C.c_int), C.byref(h)))
+        return h.value
+
+    def slab_range(self, n3):
+        a, b = C.c_int(0), C.c_int(0)
+        self._chk(self.lib.c2g_slab_range(self.h, C.c_int(int(n3)), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def upload_slab(self, fslab, n):
+        """fslab: this rank's planes f[:, :, zlo:zhi] (Fortran order)."""
+        fslab = np.asfortranarray(fslab, dtype=np.float64)
+        n = np.array(n, dtype=np.int32)
+        h = C.c_int(-1)
+        self._chk(self.lib.c2g_grid_upload_slab(self.h, _p(fslab, C.c_double), _p(n, C.c_int), C.byref(h)))
         return h.value
 
     def alloc(self, n):
@@ -194,6 +216,33 @@ class Context:
     def flush_l2(self):
         self._chk(self.lib.c2g_flush_l2(self.h))
 
+    def timer_start(self):
+        self._chk(self.lib.c2g_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_double(0)
+        self._chk(self.lib.c2g_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def upload_ptr(self, ptr, n):
+        """Upload from a raw host pointer (e.g. pinned memory)."""
+        n = np.array(n, dtype=np.int32)
+        h = C.c_int(-1)
+        self._chk(self.lib.c2g_grid_upload(self.h, C.c_void_p(ptr), _p(n, C.c_int), C.byref(h)))
+        return h.value
+
+    def upload_slab_ptr(self, ptr, n):
+        n = np.array(n, dtype=np.int32)
+        h = C.c_int(-1)
+        self._chk(self.lib.c2g_grid_upload_slab(self.h, C.c_void_p(ptr), _p(n, C.c_int), C.byref(h)))
+        return h.value
+
+    def download_slab_ptr(self, h, ptr):
+        self._chk(self.lib.c2g_grid_download_slab(self.h, C.c_int(h), C.c_void_p(ptr)))
+
+    def download_ptr(self, h, ptr):
+        self._chk(self.lib.c2g_grid_download(self.h, C.c_int(h), C.c_void_p(ptr)))
+
     def synchronize(self):
         self._chk(self.lib.c2g_synchronize(self.h))
 
@@ -225,6 +274,10 @@ class Basins:
         a = np.ascontiguousarray(assigned, dtype=np.int32)
         self.ctx._chk(self.ctx.lib.c2g_basins_relabel(self.h, C.c_int(len(a)), _p(a, C.c_int), C.c_int(nattr_new)))
         self.nattr = nattr_new
+
+    def labels_ptr(self, ptr):
+        """idg (this rank's slab) into a raw host pointer."""
+        self.ctx._chk(self.ctx.lib.c2g_basins_labels(self.h, C.c_void_p(ptr)))
 
     def labels(self, shape):
         idg = np.zeros(tuple(int(x) for x in shape), dtype=np.int32, order="F")

@@ -38,125 +38,6 @@ __device__ __forceinline__ int wrapc(int p, int n) {
   return p;
 }
 
-// is_max, bader@proc.f90:571-597 (no neighbour strictly greater)
-__device__ bool dev_is_max(const BaderParams& P, const double* __restrict__ rho, int x, int y, int z, double r0) {
-  bool ismax = true;
-#pragma unroll 1
-  for (int d3 = -1; d3 <= 1; d3++) {
-    const int zz = wrapc(z + d3, P.n3);
-    for (int d2 = -1; d2 <= 1; d2++) {
-      const int yy = wrapc(y + d2, P.n2);
-      const int base = P.n1 * (yy + P.n2 * zz);
-      for (int d1 = -1; d1 <= 1; d1++) {
-        const int xx = wrapc(x + d1, P.n1);
-        if (__ldg(rho + base + xx) > r0) ismax = false;
-      }
-    }
-  }
-  return ismax;
-}
-
-// step_ongrid, bader@proc.f90:500-527.  Loop order d1 (outer), d2, d3 (inner), first strictly greater wins.
-__device__ void dev_step_ongrid(const BaderParams& P, const double* __restrict__ rho, int x, int y, int z,
-                                double rho_ctr, int& ox, int& oy, int& oz) {
-  double rho_max = rho_ctr;
-  int bx = x, by = y, bz = z;
-#pragma unroll 1
-  for (int d1 = -1; d1 <= 1; d1++) {
-    const int xx = wrapc(x + d1, P.n1);
-    for (int d2 = -1; d2 <= 1; d2++) {
-      const int yy = wrapc(y + d2, P.n2);
-      for (int d3 = -1; d3 <= 1; d3++) {
-        const int zz = wrapc(z + d3, P.n3);
-        double rho_tmp = __ldg(rho + xx + P.n1 * (yy + P.n2 * zz));
-        rho_tmp = rho_ctr + (rho_tmp - rho_ctr) * P.lid[(d1 + 1) * 9 + (d2 + 1) * 3 + (d3 + 1)];
-        if (rho_tmp > rho_max) {
-          rho_max = rho_tmp;
-          bx = xx; by = yy; bz = zz;
-        }
-      }
-    }
-  }
-  ox = bx; oy = by; oz = bz;
-}
-
-// One complete near-grid trajectory (max_neargrid, bader@proc.f90:427-450 on a fresh grid).
-// Returns the linear id of the terminal maximum, or -1 if the path buffer overflowed.
-// The reference's "known(pm)==1" revisit test (:484-488) is answered exactly: a visited point
-// can only be hit again when rho(pm) <= max rho along the path, and only then the stored path is
-// searched.
-__device__ int dev_walk(const BaderParams& P, const double* __restrict__ rho, int start, int* path, int cap,
-                        unsigned long long* nsteps_out) {
-  const int n1 = P.n1, n2 = P.n2, n3 = P.n3;
-  int x = start % n1;
-  int t = start / n1;
-  int y = t % n2;
-  int z = t / n2;
-  int id = start;
-  double dr0 = 0.0, dr1 = 0.0, dr2 = 0.0;
-  double rhomax = -1.0e300;
-  int len = 0;
-  double r0 = __ldg(rho + id);
-  for (;;) {
-    const int xp = (x + 1 == n1) ? 0 : x + 1, xm = (x == 0) ? n1 - 1 : x - 1;
-    const int yp = (y + 1 == n2) ? 0 : y + 1, ym = (y == 0) ? n2 - 1 : y - 1;
-    const int zp = (z + 1 == n3) ? 0 : z + 1, zm = (z == 0) ? n3 - 1 : z - 1;
-    const int row = n1 * (y + n2 * z);
-    const double rxp = __ldg(rho + row + xp), rxm = __ldg(rho + row + xm);
-    const double ryp = __ldg(rho + x + n1 * (yp + n2 * z)), rym = __ldg(rho + x + n1 * (ym + n2 * z));
-    const double rzp = __ldg(rho + x + n1 * (y + n2 * zp)), rzm = __ldg(rho + x + n1 * (y + n2 * zm));
-    // rho_grad_dir (:532-567)
-    double gl0 = (rxp - rxm) * 0.5, gl1 = (ryp - rym) * 0.5, gl2 = (rzp - rzm) * 0.5;
-    if (rxp < r0 && rxm < r0) gl0 = 0.0;
-    if (ryp < r0 && rym < r0) gl1 = 0.0;
-    if (rzp < r0 && rzm < r0) gl2 = 0.0;
-    const double gc0 = gl0 * P.c2l[0] + gl1 * P.c2l[1] + gl2 * P.c2l[2];
-    const double gc1 = gl0 * P.c2l[3] + gl1 * P.c2l[4] + gl2 * P.c2l[5];
-    const double gc2 = gl0 * P.c2l[6] + gl1 * P.c2l[7] + gl2 * P.c2l[8];
-    double g0 = P.c2l[0] * gc0 + P.c2l[3] * gc1 + P.c2l[6] * gc2;
-    double g1 = P.c2l[1] * gc0 + P.c2l[4] * gc1 + P.c2l[7] * gc2;
-    double g2 = P.c2l[2] * gc0 + P.c2l[5] * gc1 + P.c2l[8] * gc2;
-    const double gmax = fmax(fabs(g0), fmax(fabs(g1), fabs(g2)));
-    int nx, ny, nz;
-    if (gmax < 1e-30) {  // (:468-476)
-      dr0 = dr1 = dr2 = 0.0;
-      if (dev_is_max(P, rho, x, y, z, r0)) break;
-      dev_step_ongrid(P, rho, x, y, z, r0, nx, ny, nz);
-    } else {  // (:477-483)
-      const double coeff = 1.0 / gmax;
-      g0 = coeff * g0; g1 = coeff * g1; g2 = coeff * g2;
-      const double a0 = round(g0), a1 = round(g1), a2 = round(g2);
-      dr0 = dr0 + g0 - a0; dr1 = dr1 + g1 - a1; dr2 = dr2 + g2 - a2;
-      const double b0 = round(dr0), b1 = round(dr1), b2 = round(dr2);
-      dr0 = dr0 - b0; dr1 = dr1 - b1; dr2 = dr2 - b2;
-      nx = wrapc(x + (int)a0 + (int)b0, n1);
-      ny = wrapc(y + (int)a1 + (int)b1, n2);
-      nz = wrapc(z + (int)a2 + (int)b2, n3);
-    }
-    // known(p) = 1 (:484)
-    if (len >= cap) return -1;
-    path[len++] = id;
-    rhomax = fmax(rhomax, r0);
-    int nid = nx + n1 * (ny + n2 * nz);
-    double rn = __ldg(rho + nid);
-    if (rn <= rhomax) {  // only then pm can be a point of this path (:487)
-      bool found = false;
-      for (int j = len - 1; j >= 0; j--)
-        if (path[j] == nid) { found = true; break; }
-      if (found) {
-        dev_step_ongrid(P, rho, x, y, z, r0, nx, ny, nz);
-        dr0 = dr1 = dr2 = 0.0;
-        nid = nx + n1 * (ny + n2 * nz);
-        rn = __ldg(rho + nid);
-      }
-    }
-    if (nid == id) break;  // did not move: maximum (:439)
-    x = nx; y = ny; z = nz; id = nid; r0 = rn;
-  }
-  if (nsteps_out) atomicAdd(nsteps_out, (unsigned long long)len);
-  return id;
-}
-
 // open-addressing hash: linear id of a candidate maximum -> candidate index
 struct MaxHash {
   const int* keys;  // -1 = empty
@@ -173,19 +54,180 @@ __device__ __forceinline__ int hash_lookup(const MaxHash& h, int key) {
   }
 }
 
+// wrap of a coordinate that is at most 2 cells outside [0,n) (pbc, bader@proc.f90:601-617)
+__device__ __forceinline__ int wrap2(int p, int n) {
+  if (p < 0) p += n;
+  if (p < 0) p += n;
+  if (p >= n) p -= n;
+  if (p >= n) p -= n;
+  return p;
+}
+// Fortran nint (half away from zero) for |v| < 1.5, as a double
+__device__ __forceinline__ double nint_small(double v) { return v >= 0.5 ? 1.0 : (v <= -0.5 ? -1.0 : 0.0); }
+
+// is_max, bader@proc.f90:571-597 (no neighbour strictly greater)
+__device__ __noinline__ bool dev_is_max(const BaderParams& P, const double* __restrict__ rho, int x, int y, int z, double r0) {
+  bool ismax = true;
+#pragma unroll 1
+  for (int d3 = -1; d3 <= 1; d3++) {
+    const int zz = wrap2(z + d3, P.n3);
+#pragma unroll 1
+    for (int d2 = -1; d2 <= 1; d2++) {
+      const int yy = wrap2(y + d2, P.n2);
+      const int base = P.n1 * (yy + P.n2 * zz);
+#pragma unroll
+      for (int d1 = -1; d1 <= 1; d1++) {
+        const int xx = wrap2(x + d1, P.n1);
+        if (__ldg(rho + base + xx) > r0) ismax = false;
+      }
+    }
+  }
+  return ismax;
+}
+
+// step_ongrid, bader@proc.f90:500-527.  Loop order d1 (outer), d2, d3 (inner), first strictly greater wins.
+// Returns the linear id of the chosen point.
+__device__ __noinline__ int dev_step_ongrid(const BaderParams& P, const double* __restrict__ rho, int x, int y, int z,
+                                            double rho_ctr) {
+  double rho_max = rho_ctr;
+  int best = x + P.n1 * (y + P.n2 * z);
+#pragma unroll 1
+  for (int d1 = -1; d1 <= 1; d1++) {
+    const int xx = wrap2(x + d1, P.n1);
+#pragma unroll 1
+    for (int d2 = -1; d2 <= 1; d2++) {
+      const int yy = wrap2(y + d2, P.n2);
+#pragma unroll
+      for (int d3 = -1; d3 <= 1; d3++) {
+        const int zz = wrap2(z + d3, P.n3);
+        const int q = xx + P.n1 * (yy + P.n2 * zz);
+        double rho_tmp = __ldg(rho + q);
+        rho_tmp = rho_ctr + (rho_tmp - rho_ctr) * P.lid[(d1 + 1) * 9 + (d2 + 1) * 3 + (d3 + 1)];
+        if (rho_tmp > rho_max) {
+          rho_max = rho_tmp;
+          best = q;
+        }
+      }
+    }
+  }
+  return best;
+}
+
+__device__ __noinline__ bool dev_on_path(const int* path, int len, int nid) {
+  for (int j = len - 1; j >= 0; j--)
+    if (path[j] == nid) return true;
+  return false;
+}
+
+// One complete near-grid trajectory (max_neargrid, bader@proc.f90:427-450 on a fresh grid).
+// Returns the linear id of the terminal maximum, or -1 if the path buffer overflowed.
+// The reference's "known(pm)==1" revisit test (:484-488) is answered exactly: a visited point
+// can only be hit again when rho(pm) <= max rho along the path, and only then the stored path is
+// searched.  ORTHO: car2lat is diagonal (orthogonal cell); the skipped products are exact zeros,
+// so the result is bit-identical to the general expression.
+template <bool ORTHO>
+__device__ __forceinline__ int dev_walk(const BaderParams& P, const double* __restrict__ rho, const MaxHash& h, int start,
+                                        int* path, int cap, unsigned long long* nsteps_out) {
+  const int n1 = P.n1, n2 = P.n2, n3 = P.n3;
+  const int s2 = n1, s3 = n1 * n2;
+  const int wxp = 1 - n1, wxm = n1 - 1, wyp = s2 - s3, wym = s3 - s2, wzp = s3 - s3 * n3, wzm = s3 * n3 - s3;
+  int x = start % n1;
+  int t = start / n1;
+  int y = t % n2;
+  int z = t / n2;
+  int id = start;
+  double dr0 = 0.0, dr1 = 0.0, dr2 = 0.0;
+  double rhomax = -1.0e300;
+  int len = 0;
+  double r0 = __ldg(rho + id);
+  for (;;) {
+    const double* c = rho + id;
+    const double rxp = __ldg(c + ((x + 1 == n1) ? wxp : 1)), rxm = __ldg(c + ((x == 0) ? wxm : -1));
+    const double ryp = __ldg(c + ((y + 1 == n2) ? wyp : s2)), rym = __ldg(c + ((y == 0) ? wym : -s2));
+    const double rzp = __ldg(c + ((z + 1 == n3) ? wzp : s3)), rzm = __ldg(c + ((z == 0) ? wzm : -s3));
+    // rho_grad_dir (:532-567)
+    double gl0 = (rxp - rxm) * 0.5, gl1 = (ryp - rym) * 0.5, gl2 = (rzp - rzm) * 0.5;
+    if (rxp < r0 && rxm < r0) gl0 = 0.0;
+    if (ryp < r0 && rym < r0) gl1 = 0.0;
+    if (rzp < r0 && rzm < r0) gl2 = 0.0;
+    double g0, g1, g2;
+    if (ORTHO) {
+      g0 = P.c2l[0] * (gl0 * P.c2l[0]);
+      g1 = P.c2l[4] * (gl1 * P.c2l[4]);
+      g2 = P.c2l[8] * (gl2 * P.c2l[8]);
+    } else {
+      const double gc0 = gl0 * P.c2l[0] + gl1 * P.c2l[1] + gl2 * P.c2l[2];
+      const double gc1 = gl0 * P.c2l[3] + gl1 * P.c2l[4] + gl2 * P.c2l[5];
+      const double gc2 = gl0 * P.c2l[6] + gl1 * P.c2l[7] + gl2 * P.c2l[8];
+      g0 = P.c2l[0] * gc0 + P.c2l[3] * gc1 + P.c2l[6] * gc2;
+      g1 = P.c2l[1] * gc0 + P.c2l[4] * gc1 + P.c2l[7] * gc2;
+      g2 = P.c2l[2] * gc0 + P.c2l[5] * gc1 + P.c2l[8] * gc2;
+    }
+    const double gmax = fmax(fabs(g0), fmax(fabs(g1), fabs(g2)));
+    int nid, nx, ny, nz;
+    if (gmax < 1e-30) {  // (:468-476)
+      dr0 = dr1 = dr2 = 0.0;
+      // is_max (:571-597) == membership in the candidate list built by k_maxima with the same predicate
+      if (hash_lookup(h, id) >= 0) break;
+      nid = dev_step_ongrid(P, rho, x, y, z, r0);
+      nx = nid % n1; t = nid / n1; ny = t % n2; nz = t / n2;
+    } else {  // (:477-483)
+      const double coeff = 1.0 / gmax;
+      g0 = coeff * g0; g1 = coeff * g1; g2 = coeff * g2;
+      const double a0 = nint_small(g0), a1 = nint_small(g1), a2 = nint_small(g2);
+      dr0 = dr0 + g0 - a0; dr1 = dr1 + g1 - a1; dr2 = dr2 + g2 - a2;
+      const double b0 = nint_small(dr0), b1 = nint_small(dr1), b2 = nint_small(dr2);
+      dr0 = dr0 - b0; dr1 = dr1 - b1; dr2 = dr2 - b2;
+      nx = wrap2(x + (int)(a0 + b0), n1);
+      ny = wrap2(y + (int)(a1 + b1), n2);
+      nz = wrap2(z + (int)(a2 + b2), n3);
+      nid = nx + n1 * (ny + n2 * nz);
+    }
+    // known(p) = 1 (:484)
+    if (len >= cap) return -1;
+    path[len++] = id;
+    rhomax = fmax(rhomax, r0);
+    double rn = __ldg(rho + nid);
+    if (rn <= rhomax) {  // only then pm can be a point of this path (:487)
+      if (dev_on_path(path, len, nid)) {
+        nid = dev_step_ongrid(P, rho, x, y, z, r0);
+        nx = nid % n1; t = nid / n1; ny = t % n2; nz = t / n2;
+        dr0 = dr1 = dr2 = 0.0;
+        rn = __ldg(rho + nid);
+      }
+    }
+    if (nid == id) break;  // did not move: maximum (:439)
+    id = nid;
+    r0 = rn;
+    x = nx; y = ny; z = nz;
+  }
+  if (nsteps_out) atomicAdd(nsteps_out, (unsigned long long)len);
+  return id;
+}
+
 // ------------------------------------------------------------------------------------------------
+// z-slab bookkeeping.  A rank owns the global planes [zlo, zhi) (boundaries are multiples of 4 so
+// that no stride-4 cube straddles two ranks); rho is replicated on every rank, labels are sharded.
+// The label buffer holds nzl + 2 planes: local plane 0 = global plane zlo-1 (halo below), planes
+// 1..nzl = owned, plane nzl+1 = global plane zhi (halo above); halos are periodic images and are
+// filled by Exchange (NCCL send/recv between ranks, a device copy when the rank is its own neighbour).
+// ------------------------------------------------------------------------------------------------
+struct Slab {
+  int zlo, zhi, nzl;
+};
+
 // K0: candidate maxima (26-neighbour, is_max) by a separable 3x3x3 box maximum on shared-memory
 // tiles with a periodic 1-cell halo; marks the stride-4 / stride-2 cubes that contain a maximum.
-// ------------------------------------------------------------------------------------------------
 constexpr int TX = 32, TY = 8, TZ = 8;
-__global__ void __launch_bounds__(256) k_maxima(const __grid_constant__ BaderParams P, const double* __restrict__ rho,
-                                                int* __restrict__ cand, int* __restrict__ ncand, int maxcand,
-                                                unsigned char* __restrict__ cube4, unsigned char* __restrict__ cube2) {
+__global__ void __launch_bounds__(256) k_maxima(const __grid_constant__ BaderParams P, const Slab S,
+                                                const double* __restrict__ rho, int* __restrict__ cand,
+                                                int* __restrict__ ncand, int maxcand, unsigned char* __restrict__ cube4,
+                                                unsigned char* __restrict__ cube2) {
   extern __shared__ double sm[];
   double* s0 = sm;                                   // [TZ+2][TY+2][TX+2]
   double* s1 = sm + (TZ + 2) * (TY + 2) * (TX + 2);  // [TZ+2][TY+2][TX] max over x
   const int n1 = P.n1, n2 = P.n2, n3 = P.n3;
-  const int bx0 = blockIdx.x * TX, by0 = blockIdx.y * TY, bz0 = blockIdx.z * TZ;
+  const int bx0 = blockIdx.x * TX, by0 = blockIdx.y * TY, bz0 = S.zlo + blockIdx.z * TZ;
   const int tid = threadIdx.x;
   constexpr int SX = TX + 2, SY = TY + 2, SZ = TZ + 2;
   for (int e = tid; e < SX * SY * SZ; e += 256) {
@@ -212,7 +254,7 @@ __global__ void __launch_bounds__(256) k_maxima(const __grid_constant__ BaderPar
 #pragma unroll
     for (int lz = 0; lz < TZ; lz++) {
       const int gz = bz0 + lz;
-      if (gz >= n3) break;
+      if (gz >= S.zhi) break;
       const double c = s0[((lz + 1) * SY + (ly + 1)) * SX + lx + 1];
       const double bm = fmax(m[lz], fmax(m[lz + 1], m[lz + 2]));
       if (!(bm > c)) {  // no neighbour strictly greater
@@ -220,15 +262,16 @@ __global__ void __launch_bounds__(256) k_maxima(const __grid_constant__ BaderPar
         if (slot < maxcand) cand[slot] = gx + n1 * (gy + n2 * gz);
         const int c41 = (n1 + 3) / 4, c42 = (n2 + 3) / 4;
         const int c21 = (n1 + 1) / 2, c22 = (n2 + 1) / 2;
-        cube4[(gx >> 2) + c41 * ((gy >> 2) + (size_t)c42 * (gz >> 2))] = 1;
-        cube2[(gx >> 1) + c21 * ((gy >> 1) + (size_t)c22 * (gz >> 1))] = 1;
+        cube4[(gx >> 2) + c41 * ((gy >> 2) + (size_t)c42 * ((gz - S.zlo) >> 2))] = 1;
+        cube2[(gx >> 1) + c21 * ((gy >> 1) + (size_t)c22 * ((gz - S.zlo) >> 1))] = 1;
       }
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// walkers
+// walkers.  `label` is the owned part of the label buffer re-based so that label[global id] is valid
+// for every owned point.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void finish_walk(int start, int term, int* __restrict__ label, const MaxHash& h,
                                             unsigned char* __restrict__ reached, int* __restrict__ overflow,
@@ -244,21 +287,23 @@ __device__ __forceinline__ void finish_walk(int start, int term, int* __restrict
   else if (!reached[ci]) reached[ci] = 1;
 }
 
-// every point of the stride-s lattice (s = 1: every grid point = the EXACT referee)
-__global__ void __launch_bounds__(128) k_walk_lattice(const __grid_constant__ BaderParams P, const double* __restrict__ rho,
-                                                      int s, int m1, int m2, int m3, int* __restrict__ label,
-                                                      MaxHash h, unsigned char* __restrict__ reached,
+// every owned point of the stride-s lattice (s = 1: every grid point = the EXACT referee)
+template <bool ORTHO>
+__global__ void __launch_bounds__(128) k_walk_lattice(const __grid_constant__ BaderParams P, const Slab S,
+                                                      const double* __restrict__ rho, int s, int m1, int m2, int m3,
+                                                      int* __restrict__ label, MaxHash h, unsigned char* __restrict__ reached,
                                                       int* __restrict__ overflow, int* __restrict__ noverflow,
                                                       int* __restrict__ err, unsigned long long* nsteps) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)m1 * m2 * m3) return;
   const int lx = (int)(t % m1), ly = (int)((t / m1) % m2), lz = (int)(t / ((long long)m1 * m2));
-  const int start = lx * s + P.n1 * (ly * s + P.n2 * (lz * s));
+  const int start = lx * s + P.n1 * (ly * s + P.n2 * (S.zlo + lz * s));
   int path[PATHCAP];
-  const int term = dev_walk(P, rho, start, path, PATHCAP, nsteps);
+  const int term = dev_walk<ORTHO>(P, rho, h, start, path, PATHCAP, nsteps);
   finish_walk(start, term, label, h, reached, overflow, noverflow, err);
 }
 
+template <bool ORTHO>
 __global__ void __launch_bounds__(128) k_walk_list(const __grid_constant__ BaderParams P, const double* __restrict__ rho,
                                                    const int* __restrict__ list, int count, int* __restrict__ label,
                                                    MaxHash h, unsigned char* __restrict__ reached,
@@ -268,7 +313,7 @@ __global__ void __launch_bounds__(128) k_walk_list(const __grid_constant__ Bader
   if (t >= count) return;
   const int start = list[t];
   int path[PATHCAP];
-  const int term = dev_walk(P, rho, start, path, PATHCAP, nsteps);
+  const int term = dev_walk<ORTHO>(P, rho, h, start, path, PATHCAP, nsteps);
   finish_walk(start, term, label, h, reached, overflow, noverflow, err);
 }
 
@@ -280,7 +325,7 @@ __global__ void __launch_bounds__(64) k_walk_big(const __grid_constant__ BaderPa
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= count) return;
   const int start = list[t];
-  const int term = dev_walk(P, rho, start, scratch + (size_t)t * bigcap, bigcap, nsteps);
+  const int term = dev_walk<false>(P, rho, h, start, scratch + (size_t)t * bigcap, bigcap, nsteps);
   if (term < 0) { atomicExch(err, 2); return; }
   label[start] = term;
   const int ci = hash_lookup(h, term);
@@ -289,41 +334,44 @@ __global__ void __launch_bounds__(64) k_walk_big(const __grid_constant__ BaderPa
 }
 
 // ------------------------------------------------------------------------------------------------
-// classify: one thread per stride-s cube.  If its 8 corners (already labelled) agree and it holds
-// no local maximum, fill its new stride-s/2 points (label | FILLBIT); otherwise queue them.
+// classify: one thread per owned stride-s cube.  If its 8 corners (already labelled; the upper ones
+// may sit on the halo-above plane) agree and it holds no local maximum, fill its new stride-s/2
+// points (label | FILLBIT); otherwise queue them.  lbuf = label buffer including halos.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_classify(int n1, int n2, int n3, int s, int* __restrict__ label,
+__global__ void __launch_bounds__(256) k_classify(int n1, int n2, int n3, const Slab S, int s, int* __restrict__ lbuf,
                                                   const unsigned char* __restrict__ cubemax,
                                                   int* __restrict__ list, int* __restrict__ nlist) {
-  const int c1 = (n1 + s - 1) / s, c2 = (n2 + s - 1) / s, c3 = (n3 + s - 1) / s;
+  const int c1 = (n1 + s - 1) / s, c2 = (n2 + s - 1) / s, c3 = (S.nzl + s - 1) / s;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = t < (long long)c1 * c2 * c3;
   int npush = 0;
   int pts[7];
   if (active) {
     const int cx = (int)(t % c1), cy = (int)((t / c1) % c2), cz = (int)(t / ((long long)c1 * c2));
-    const int x0 = cx * s, y0 = cy * s, z0 = cz * s;
-    const int x1 = (x0 + s < n1) ? x0 + s : 0, y1 = (y0 + s < n2) ? y0 + s : 0, z1 = (z0 + s < n3) ? z0 + s : 0;
-    const int l000 = label[x0 + n1 * (y0 + n2 * z0)] & LMASK;
+    const int x0 = cx * s, y0 = cy * s, z0 = S.zlo + cz * s;
+    const int x1 = (x0 + s < n1) ? x0 + s : 0, y1 = (y0 + s < n2) ? y0 + s : 0;
+    const int p0 = z0 - S.zlo + 1;                              // local plane of z0
+    const int p1 = ((z0 + s < n3) ? z0 + s : n3) - S.zlo + 1;   // local plane of the upper corners (may be the halo)
+    const int s3 = n1 * n2;
+    const int l000 = lbuf[x0 + n1 * y0 + s3 * p0] & LMASK;
     bool uni = !cubemax[t];
-    uni = uni && ((label[x1 + n1 * (y0 + n2 * z0)] & LMASK) == l000);
-    uni = uni && ((label[x0 + n1 * (y1 + n2 * z0)] & LMASK) == l000);
-    uni = uni && ((label[x1 + n1 * (y1 + n2 * z0)] & LMASK) == l000);
-    uni = uni && ((label[x0 + n1 * (y0 + n2 * z1)] & LMASK) == l000);
-    uni = uni && ((label[x1 + n1 * (y0 + n2 * z1)] & LMASK) == l000);
-    uni = uni && ((label[x0 + n1 * (y1 + n2 * z1)] & LMASK) == l000);
-    uni = uni && ((label[x1 + n1 * (y1 + n2 * z1)] & LMASK) == l000);
-    const int h = s >> 1;
+    uni = uni && ((lbuf[x1 + n1 * y0 + s3 * p0] & LMASK) == l000);
+    uni = uni && ((lbuf[x0 + n1 * y1 + s3 * p0] & LMASK) == l000);
+    uni = uni && ((lbuf[x1 + n1 * y1 + s3 * p0] & LMASK) == l000);
+    uni = uni && ((lbuf[x0 + n1 * y0 + s3 * p1] & LMASK) == l000);
+    uni = uni && ((lbuf[x1 + n1 * y0 + s3 * p1] & LMASK) == l000);
+    uni = uni && ((lbuf[x0 + n1 * y1 + s3 * p1] & LMASK) == l000);
+    uni = uni && ((lbuf[x1 + n1 * y1 + s3 * p1] & LMASK) == l000);
+    const int hh = s >> 1;
     for (int o = 1; o < 8; o++) {
-      const int x = x0 + ((o & 1) ? h : 0), y = y0 + ((o & 2) ? h : 0), z = z0 + ((o & 4) ? h : 0);
-      if (x >= n1 || y >= n2 || z >= n3) continue;
-      const int id = x + n1 * (y + n2 * z);
-      if (uni) label[id] = (int)((unsigned)l000 | FILLBIT);
-      else pts[npush++] = id;
+      const int x = x0 + ((o & 1) ? hh : 0), y = y0 + ((o & 2) ? hh : 0), z = z0 + ((o & 4) ? hh : 0);
+      if (x >= n1 || y >= n2 || z >= S.zhi) continue;
+      if (uni) lbuf[x + n1 * y + s3 * (z - S.zlo + 1)] = (int)((unsigned)l000 | FILLBIT);
+      else pts[npush++] = x + n1 * (y + n2 * z);  // global id
     }
   }
   // block-aggregated append (keeps spatial order inside a block)
-  __shared__ int s_base, s_tot;
+  __shared__ int s_base;
   __shared__ int s_warp[8];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   int incl = npush;
@@ -336,7 +384,6 @@ __global__ void __launch_bounds__(256) k_classify(int n1, int n2, int n3, int s,
   if (threadIdx.x == 0) {
     int acc = 0;
     for (int w = 0; w < 8; w++) { const int v = s_warp[w]; s_warp[w] = acc; acc += v; }
-    s_tot = acc;
     s_base = acc ? atomicAdd(nlist, acc) : 0;
   }
   __syncthreads();
@@ -347,21 +394,24 @@ __global__ void __launch_bounds__(256) k_classify(int n1, int n2, int n3, int s,
 }
 
 // ------------------------------------------------------------------------------------------------
-// edge fix: every FILLED point with a 26-neighbour of a different label is queued for an exact walk
-// (the refine_edge criterion, is_vol_edge bader@proc.f90:730-752).
+// edge fix: every FILLED owned point with a 26-neighbour of a different label is queued for an exact
+// walk (the refine_edge criterion, is_vol_edge bader@proc.f90:730-752).  Reads both halo planes.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_edgefix(int n1, int n2, int n3, int* __restrict__ label,
+__global__ void __launch_bounds__(256) k_edgefix(int n1, int n2, const Slab S, int* __restrict__ lbuf,
                                                  int* __restrict__ list, int* __restrict__ nlist) {
   __shared__ int sl[(TZ + 2) * (TY + 2) * (TX + 2)];
   constexpr int SX = TX + 2, SY = TY + 2, SZ = TZ + 2;
-  const int bx0 = blockIdx.x * TX, by0 = blockIdx.y * TY, bz0 = blockIdx.z * TZ;
+  const int bx0 = blockIdx.x * TX, by0 = blockIdx.y * TY, lz0 = blockIdx.z * TZ;  // lz0: first owned plane (0-based)
   const int tid = threadIdx.x;
+  const int s3 = n1 * n2;
   int first = 0;
   bool uniform = true;
   for (int e = tid; e < SX * SY * SZ; e += 256) {
     const int sx = e % SX, sy = (e / SX) % SY, sz = e / (SX * SY);
-    const int gx = wrapc(bx0 + sx - 1, n1), gy = wrapc(by0 + sy - 1, n2), gz = wrapc(bz0 + sz - 1, n3);
-    const int v = label[gx + n1 * (gy + n2 * gz)];
+    const int gx = wrapc(bx0 + sx - 1, n1), gy = wrapc(by0 + sy - 1, n2);
+    int pl = lz0 + sz;  // local plane incl. halo offset: owned plane lz0+sz-1 -> buffer plane lz0+sz
+    if (pl > S.nzl + 1) pl = S.nzl + 1;
+    const int v = lbuf[gx + n1 * gy + s3 * pl];
     sl[e] = v;
     if (e == tid) first = v & LMASK;
     else uniform = uniform && ((v & LMASK) == first);
@@ -373,8 +423,7 @@ __global__ void __launch_bounds__(256) k_edgefix(int n1, int n2, int n3, int* __
   const int gx = bx0 + lx, gy = by0 + ly;
   if (gx >= n1 || gy >= n2) return;
   for (int lz = 0; lz < TZ; lz++) {
-    const int gz = bz0 + lz;
-    if (gz >= n3) break;
+    if (lz0 + lz >= S.nzl) break;
     const int c = sl[((lz + 1) * SY + (ly + 1)) * SX + lx + 1];
     if (!((unsigned)c & FILLBIT)) continue;
     const int cl = c & LMASK;
@@ -387,45 +436,51 @@ __global__ void __launch_bounds__(256) k_edgefix(int n1, int n2, int n3, int* __
         for (int dx = 0; dx < 3; dx++)
           edge = edge || ((sl[((lz + dz) * SY + (ly + dy)) * SX + lx + dx] & LMASK) != cl);
     if (edge) {
-      const int id = gx + n1 * (gy + n2 * gz);
-      label[id] = cl;  // clear FILLBIT: walked from now on
-      list[atomicAdd(nlist, 1)] = id;
+      lbuf[gx + n1 * gy + s3 * (lz0 + lz + 1)] = cl;  // clear FILLBIT: walked from now on
+      list[atomicAdd(nlist, 1)] = gx + n1 * (gy + n2 * (S.zlo + lz0 + lz));
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// compaction of labels: terminal linear id -> index in the ordered maxima list; counts points
+// compaction of the owned labels: terminal linear id -> index in the ordered maxima list
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_compact(long long nn, int* __restrict__ label, MaxHash h,
-                                                 const int* __restrict__ cand2out, unsigned long long* __restrict__ counts,
-                                                 int* __restrict__ err) {
+                                                 const int* __restrict__ cand2out, int* __restrict__ err) {
+  // 4 consecutive labels per thread (16-byte accesses); the hash lookup is repeated only when the
+  // terminal changes, which inside a basin it does not.
+  const long long nv = nn >> 2;
   const long long stride = (long long)gridDim.x * blockDim.x;
   int last_t = -1, last_o = -1;
-  unsigned long long run = 0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nn; i += stride) {
-    const int t = label[i] & LMASK;
+  auto conv = [&](int v) -> int {
+    const int t = v & LMASK;
     if (t != last_t) {
-      if (run) atomicAdd(counts + last_o, run);
-      run = 0;
       const int ci = hash_lookup(h, t);
-      if (ci < 0) { atomicExch(err, 1); last_t = -1; last_o = -1; continue; }
+      if (ci < 0) { atomicExch(err, 1); return v; }
       last_t = t;
-      last_o = cand2out[ci];
+      last_o = __ldg(cand2out + ci);
     }
-    run++;
-    label[i] = last_o;
+    return last_o;
+  };
+  int4* l4 = reinterpret_cast<int4*>(label);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+    int4 v = l4[i];
+    v.x = conv(v.x); v.y = conv(v.y); v.z = conv(v.z); v.w = conv(v.w);
+    l4[i] = v;
   }
-  if (run) atomicAdd(counts + last_o, run);
+  if (blockIdx.x == 0 && threadIdx.x < (nn & 3)) {
+    const long long i = (nv << 2) + threadIdx.x;
+    label[i] = conv(label[i]);
+  }
 }
 
-// reference scan-order key of the first point of each basin (C2G_ORDER_SCAN)
-__global__ void __launch_bounds__(256) k_firstpoint(int n1, int n2, int n3, const int* __restrict__ label,
+// reference scan-order key of the first point of each basin (C2G_ORDER_SCAN); label = owned planes
+__global__ void __launch_bounds__(256) k_firstpoint(int n1, int n2, int n3, const Slab S, const int* __restrict__ label,
                                                     int* __restrict__ first) {
-  const long long nn = (long long)n1 * n2 * n3;
+  const long long nn = (long long)n1 * n2 * S.nzl;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nn; i += stride) {
-    const int x = (int)(i % n1), y = (int)((i / n1) % n2), z = (int)(i / ((long long)n1 * n2));
+    const int x = (int)(i % n1), y = (int)((i / n1) % n2), z = S.zlo + (int)(i / ((long long)n1 * n2));
     const int key = (x * n2 + y) * n3 + z;
     const int l = label[i];
     if (key < first[l]) atomicMin(first + l, key);
@@ -443,7 +498,57 @@ struct DevBuf {
   template <class T> T* as() { return (T*)p; }
 };
 
+#define C2G_NCCL(ctx, call)                                                                         \
+  do {                                                                                              \
+    ncclResult_t r__ = (call);                                                                      \
+    if (r__ != ncclSuccess)                                                                         \
+      return (ctx)->fail(C2G_ERR_NCCL, "%s:%d: %s: %s", __FILE__, __LINE__, #call, ncclGetErrorString(r__)); \
+  } while (0)
+
+// halo planes of the label buffer.  which: 1 = halo above only (needed by classify), 3 = both.
+int exchange_halos(c2g_context* ctx, int* lbuf, size_t plane, const Slab& S, int which) {
+  cudaStream_t st = ctx->stream;
+  const int G = ctx->nranks, r = ctx->rank;
+  if (G == 1) {
+    if (S.nzl < 1) return C2G_OK;
+    // periodic images of the rank's own planes
+    C2G_CUDA(ctx, cudaMemcpyAsync(lbuf + plane * (S.nzl + 1), lbuf + plane * 1, plane * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    if (which & 2)
+      C2G_CUDA(ctx, cudaMemcpyAsync(lbuf, lbuf + plane * S.nzl, plane * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    ctx->launches += (which & 2) ? 2 : 1;
+    return C2G_OK;
+  }
+  ncclComm_t comm = (ncclComm_t)ctx->nccl;
+  const int up = (r + 1) % G, dn = (r + G - 1) % G;
+  ctx->prof_begin("bader_halo_nccl");
+  C2G_NCCL(ctx, ncclGroupStart());
+  // my first owned plane is the halo-above of the rank below; I receive my halo-above from the rank above
+  C2G_NCCL(ctx, ncclSend(lbuf + plane * 1, plane, ncclInt32, dn, comm, st));
+  C2G_NCCL(ctx, ncclRecv(lbuf + plane * (S.nzl + 1), plane, ncclInt32, up, comm, st));
+  if (which & 2) {
+    C2G_NCCL(ctx, ncclSend(lbuf + plane * S.nzl, plane, ncclInt32, up, comm, st));
+    C2G_NCCL(ctx, ncclRecv(lbuf, plane, ncclInt32, dn, comm, st));
+  }
+  C2G_NCCL(ctx, ncclGroupEnd());
+  ctx->prof_end();
+  return C2G_OK;
+}
+
 }  // namespace
+
+// slab boundaries: multiples of 4, as even as possible
+void c2g_slab_bounds(int n3, int nranks, int rank, int* zlo, int* zhi) {
+  auto bound = [&](int r) -> int {
+    if (r >= nranks) return n3;
+    long long z = (long long)n3 * r / nranks;
+    z = (z + 2) / 4 * 4;
+    if (z > n3) z = n3;
+    return (int)z;
+  };
+  *zlo = bound(rank);
+  *zhi = bound(rank + 1);
+  if (*zhi < *zlo) *zhi = *zlo;
+}
 
 // =================================================================================================
 extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2lat[9], const double lat_i_dist[27],
@@ -455,31 +560,44 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
   const c2g_grid& g = ctx->grids[handle];
   if (g.nn >= (1ll << 31)) return ctx->fail(C2G_ERR_ARG, "c2g_bader_assign: grid too large for int32 indices");
   cudaStream_t st = ctx->stream;
+  const int G = ctx->nranks;
+  ncclComm_t comm = (ncclComm_t)ctx->nccl;
   BaderParams P;
   P.n1 = g.n[0]; P.n2 = g.n[1]; P.n3 = g.n[2];
   memcpy(P.c2l, car2lat, sizeof(P.c2l));
   memcpy(P.lid, lat_i_dist, sizeof(P.lid));
   const int n1 = P.n1, n2 = P.n2, n3 = P.n3;
-  const long long nn = g.nn;
+  const size_t plane = (size_t)n1 * n2;
+  // diagonal car2lat (orthogonal cell): the off-diagonal products are exact zeros and can be skipped
+  const bool ortho = P.c2l[1] == 0.0 && P.c2l[2] == 0.0 && P.c2l[3] == 0.0 && P.c2l[5] == 0.0 && P.c2l[6] == 0.0 && P.c2l[7] == 0.0;
+  Slab S;
+  c2g_slab_bounds(n3, G, ctx->rank, &S.zlo, &S.zhi);
+  S.nzl = S.zhi - S.zlo;
+  const long long nnl = (long long)plane * S.nzl;  // owned points
 
   c2g_basins* res = new c2g_basins();
   res->ctx = ctx; res->kind = 0; res->gridh = handle;
-  res->n[0] = n1; res->n[1] = n2; res->n[2] = n3; res->nn = nn;
+  res->n[0] = n1; res->n[1] = n2; res->n[2] = n3; res->nn = g.nn;
+  res->zlo = S.zlo; res->zhi = S.zhi;
   struct Guard { c2g_basins* r; bool ok = false; ~Guard() { if (!ok) c2g_basins_free(r); } } guard{res};
 
-  C2G_CUDA(ctx, cudaMalloc(&res->d_label, sizeof(int) * nn));
-  int* label = res->d_label;
+  // the owned planes start one plane into the buffer: pad so that they are 16-byte aligned (int4 passes)
+  const size_t pad = (4 - plane % 4) % 4;
+  C2G_CUDA(ctx, cudaMalloc(&res->d_lbuf, sizeof(int) * (plane * (S.nzl + 2) + pad)));
+  int* lbuf = res->d_lbuf + pad;
+  res->d_label = lbuf + plane;                               // owned planes
+  int* label_g = lbuf + plane - (long long)plane * S.zlo;    // label_g[global id] for owned points
 
-  // ---- K0: candidate maxima ----
-  const int c41 = (n1 + 3) / 4, c42 = (n2 + 3) / 4, c43 = (n3 + 3) / 4;
-  const int c21 = (n1 + 1) / 2, c22 = (n2 + 1) / 2, c23 = (n3 + 1) / 2;
-  const size_t ncube4 = (size_t)c41 * c42 * c43, ncube2 = (size_t)c21 * c22 * c23;
+  // ---- K0: candidate maxima of the slab ----
+  const int c41 = (n1 + 3) / 4, c42 = (n2 + 3) / 4, c43 = (S.nzl + 3) / 4;
+  const int c21 = (n1 + 1) / 2, c22 = (n2 + 1) / 2, c23 = (S.nzl + 1) / 2;
+  const size_t ncube4 = std::max<size_t>(1, (size_t)c41 * c42 * c43), ncube2 = std::max<size_t>(1, (size_t)c21 * c22 * c23);
   DevBuf b_cube4, b_cube2, b_cand, b_cnt;
   C2G_CUDA(ctx, cudaMalloc(&b_cube4.p, ncube4));
   C2G_CUDA(ctx, cudaMalloc(&b_cube2.p, ncube2));
-  int maxcand = (int)std::min<long long>(nn, std::max<long long>(1 << 16, nn / 64));
+  int maxcand = (int)std::max<long long>(1, std::min<long long>(nnl, std::max<long long>(1 << 16, nnl / 64)));
   C2G_CUDA(ctx, cudaMalloc(&b_cnt.p, 64));
-  // counters: [0] ncand, [1] nlist, [2] noverflow, [3] err ; [4..5] nsteps (u64)
+  // counters: [0] ncand, [1] nlist, [2] noverflow, [3] err ; [4..5] nsteps (u64) ; [6] scratch for collectives
   int* cnt = b_cnt.as<int>();
   unsigned long long* nsteps = (unsigned long long*)(cnt + 4);
   int hcnt[8];
@@ -488,18 +606,16 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
     C2G_CUDA(ctx, cudaMemsetAsync(cnt, 0, 64, st));
     C2G_CUDA(ctx, cudaMemsetAsync(b_cube4.p, 0, ncube4, st));
     C2G_CUDA(ctx, cudaMemsetAsync(b_cube2.p, 0, ncube2, st));
-    dim3 grid((n1 + TX - 1) / TX, (n2 + TY - 1) / TY, (n3 + TZ - 1) / TZ);
-    const size_t smem = sizeof(double) * ((TZ + 2) * (TY + 2) * (TX + 2) + (TZ + 2) * (TY + 2) * TX);
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (S.nzl > 0) {
+      dim3 grid((n1 + TX - 1) / TX, (n2 + TY - 1) / TY, (S.nzl + TZ - 1) / TZ);
+      const size_t smem = sizeof(double) * ((TZ + 2) * (TY + 2) * (TX + 2) + (TZ + 2) * (TY + 2) * TX);
       C2G_CUDA(ctx, cudaFuncSetAttribute(k_maxima, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_set = true;
+      ctx->prof_begin("bader_maxima");
+      k_maxima<<<grid, 256, smem, st>>>(P, S, g.d, b_cand.as<int>(), cnt, maxcand, b_cube4.as<unsigned char>(),
+                                        b_cube2.as<unsigned char>());
+      ctx->prof_end();
+      C2G_KERNEL_CHECK(ctx);
     }
-    ctx->prof_begin("bader_maxima");
-    k_maxima<<<grid, 256, smem, st>>>(P, g.d, b_cand.as<int>(), cnt, maxcand, b_cube4.as<unsigned char>(),
-                                      b_cube2.as<unsigned char>());
-    ctx->prof_end();
-    C2G_KERNEL_CHECK(ctx);
     C2G_CUDA(ctx, cudaMemcpyAsync(hcnt, cnt, 32, cudaMemcpyDeviceToHost, st));
     C2G_CUDA(ctx, cudaStreamSynchronize(st));
     if (hcnt[0] <= maxcand) break;
@@ -507,10 +623,38 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
     cudaFree(b_cand.p); b_cand.p = nullptr;
     maxcand = hcnt[0];
   }
-  const int ncand = hcnt[0];
+  int ncand_local = hcnt[0];
+  std::vector<int> cand;
+  if (G == 1) {
+    cand.resize(ncand_local);
+    if (ncand_local) C2G_CUDA(ctx, cudaMemcpy(cand.data(), b_cand.p, sizeof(int) * ncand_local, cudaMemcpyDeviceToHost));
+  } else {
+    // all ranks need every candidate (a trajectory may end in any slab): padded all-gather
+    DevBuf b_mx, b_all;
+    C2G_CUDA(ctx, cudaMalloc(&b_mx.p, sizeof(int)));
+    C2G_CUDA(ctx, cudaMemcpyAsync(b_mx.p, &ncand_local, sizeof(int), cudaMemcpyHostToDevice, st));
+    C2G_NCCL(ctx, ncclAllReduce(b_mx.p, b_mx.p, 1, ncclInt32, ncclMax, comm, st));
+    int mx = 0;
+    C2G_CUDA(ctx, cudaMemcpyAsync(&mx, b_mx.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    C2G_CUDA(ctx, cudaStreamSynchronize(st));
+    mx = std::max(mx, 1);
+    DevBuf b_pad;
+    C2G_CUDA(ctx, cudaMalloc(&b_pad.p, sizeof(int) * (size_t)mx));
+    C2G_CUDA(ctx, cudaMemsetAsync(b_pad.p, 0xff, sizeof(int) * (size_t)mx, st));
+    if (ncand_local)
+      C2G_CUDA(ctx, cudaMemcpyAsync(b_pad.p, b_cand.p, sizeof(int) * ncand_local, cudaMemcpyDeviceToDevice, st));
+    C2G_CUDA(ctx, cudaMalloc(&b_all.p, sizeof(int) * (size_t)mx * G));
+    ctx->prof_begin("bader_cand_allgather_nccl");
+    C2G_NCCL(ctx, ncclAllGather(b_pad.p, b_all.p, mx, ncclInt32, comm, st));
+    ctx->prof_end();
+    std::vector<int> all((size_t)mx * G);
+    C2G_CUDA(ctx, cudaMemcpyAsync(all.data(), b_all.p, sizeof(int) * all.size(), cudaMemcpyDeviceToHost, st));
+    C2G_CUDA(ctx, cudaStreamSynchronize(st));
+    for (int v : all)
+      if (v >= 0) cand.push_back(v);
+  }
+  const int ncand = (int)cand.size();
   if (ncand == 0) return ctx->fail(C2G_ERR_STATE, "c2g_bader_assign: the field has no local maximum (NaN input?)");
-  std::vector<int> cand(ncand);
-  C2G_CUDA(ctx, cudaMemcpy(cand.data(), b_cand.p, sizeof(int) * ncand, cudaMemcpyDeviceToHost));
   std::sort(cand.begin(), cand.end());
   // hash table on the host, then upload
   unsigned hsize = 1024;
@@ -533,9 +677,9 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
 
   // work list / overflow list
   DevBuf b_list, b_over;
-  const long long listcap = (algo == C2G_BADER_EXACT) ? 1 : nn;
+  const long long listcap = (algo == C2G_BADER_EXACT) ? 1 : std::max<long long>(1, nnl);
   C2G_CUDA(ctx, cudaMalloc(&b_list.p, sizeof(int) * (size_t)listcap));
-  long long overcap = std::max<long long>(1024, nn / 16);
+  long long overcap = std::max<long long>(1024, nnl / 16);
   C2G_CUDA(ctx, cudaMalloc(&b_over.p, sizeof(int) * (size_t)overcap));
   int* list = b_list.as<int>();
   int* over = b_over.as<int>();
@@ -550,14 +694,14 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
     if (nov == 0) return C2G_OK;
     if (nov > overcap) return ctx->fail(C2G_ERR_OVERFLOW, "too many long trajectories (%d)", nov);
     noverflow_total += nov;
-    const int bigcap = (int)std::min<long long>(nn, 1 << 22);
+    const int bigcap = (int)std::min<long long>(g.nn, 1 << 22);
     const int chunk = (int)std::max<long long>(1, std::min<long long>(nov, (1ll << 31) / bigcap));  // <= 8 GiB scratch
     DevBuf b_scr;
     C2G_CUDA(ctx, cudaMalloc(&b_scr.p, sizeof(int) * (size_t)chunk * bigcap));
     for (int off = 0; off < nov; off += chunk) {
       const int c = std::min(chunk, nov - off);
       ctx->prof_begin("bader_walk_big");
-      k_walk_big<<<c2g_blocks_for(c, 64), 64, 0, st>>>(P, g.d, over + off, c, label, h, reached, b_scr.as<int>(), bigcap,
+      k_walk_big<<<c2g_blocks_for(c, 64), 64, 0, st>>>(P, g.d, over + off, c, label_g, h, reached, b_scr.as<int>(), bigcap,
                                                        cnt + 3, nsteps);
       ctx->prof_end();
       C2G_KERNEL_CHECK(ctx);
@@ -569,35 +713,44 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
     if (hcnt[3] == 1) return ctx->fail(C2G_ERR_NEWMAX, "bader walk ended on a point that is not a local maximum");
     return C2G_OK;
   };
-  auto walk_list = [&](int count, const char* name) -> int {
-    if (count <= 0) return C2G_OK;
-    // overflow list must be able to hold every walker of this launch in the worst case
-    if (count > overcap) {
+  auto grow_over = [&](long long need) -> int {
+    if (need > overcap) {
       cudaFree(b_over.p); b_over.p = nullptr;
-      overcap = count;
+      overcap = need;
       C2G_CUDA(ctx, cudaMalloc(&b_over.p, sizeof(int) * (size_t)overcap));
       over = b_over.as<int>();
     }
+    return C2G_OK;
+  };
+  auto walk_list = [&](int count, const char* name) -> int {
+    if (count <= 0) return C2G_OK;
+    int rc = grow_over(count);
+    if (rc) return rc;
     ctx->prof_begin(name);
-    k_walk_list<<<c2g_blocks_for(count, 128), 128, 0, st>>>(P, g.d, list, count, label, h, reached, over, cnt + 2, cnt + 3,
-                                                            algo == C2G_BADER_EXACT ? nsteps : nullptr);
+    if (ortho)
+      k_walk_list<true><<<c2g_blocks_for(count, 128), 128, 0, st>>>(P, g.d, list, count, label_g, h, reached, over, cnt + 2, cnt + 3,
+                                                                    algo == C2G_BADER_EXACT ? nsteps : nullptr);
+    else
+      k_walk_list<false><<<c2g_blocks_for(count, 128), 128, 0, st>>>(P, g.d, list, count, label_g, h, reached, over, cnt + 2, cnt + 3,
+                                                                     algo == C2G_BADER_EXACT ? nsteps : nullptr);
     ctx->prof_end();
     C2G_KERNEL_CHECK(ctx);
     walked += count;
     return drain_overflow();
   };
   auto walk_lattice = [&](int s, const char* name) -> int {
-    const int m1 = (n1 + s - 1) / s, m2 = (n2 + s - 1) / s, m3 = (n3 + s - 1) / s;
+    const int m1 = (n1 + s - 1) / s, m2 = (n2 + s - 1) / s, m3 = (S.nzl + s - 1) / s;
     const long long m = (long long)m1 * m2 * m3;
-    if (m > overcap) {
-      cudaFree(b_over.p); b_over.p = nullptr;
-      overcap = m;
-      C2G_CUDA(ctx, cudaMalloc(&b_over.p, sizeof(int) * (size_t)overcap));
-      over = b_over.as<int>();
-    }
+    if (m == 0) return C2G_OK;
+    int rc = grow_over(m);
+    if (rc) return rc;
     ctx->prof_begin(name);
-    k_walk_lattice<<<c2g_blocks_for(m, 128), 128, 0, st>>>(P, g.d, s, m1, m2, m3, label, h, reached, over, cnt + 2, cnt + 3,
-                                                           algo == C2G_BADER_EXACT ? nsteps : nullptr);
+    if (ortho)
+      k_walk_lattice<true><<<c2g_blocks_for(m, 128), 128, 0, st>>>(P, S, g.d, s, m1, m2, m3, label_g, h, reached, over, cnt + 2,
+                                                                   cnt + 3, algo == C2G_BADER_EXACT ? nsteps : nullptr);
+    else
+      k_walk_lattice<false><<<c2g_blocks_for(m, 128), 128, 0, st>>>(P, S, g.d, s, m1, m2, m3, label_g, h, reached, over, cnt + 2,
+                                                                    cnt + 3, algo == C2G_BADER_EXACT ? nsteps : nullptr);
     ctx->prof_end();
     C2G_KERNEL_CHECK(ctx);
     walked += m;
@@ -612,40 +765,53 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
     if ((rc = walk_lattice(4, "bader_walk_l4")) != C2G_OK) return rc;
     // levels 4 -> 2 -> 1
     for (int s = 4; s >= 2; s >>= 1) {
-      const int c1 = (n1 + s - 1) / s, c2 = (n2 + s - 1) / s, c3 = (n3 + s - 1) / s;
+      if ((rc = exchange_halos(ctx, lbuf, plane, S, 1)) != C2G_OK) return rc;
+      const int c1 = (n1 + s - 1) / s, c2 = (n2 + s - 1) / s, c3 = (S.nzl + s - 1) / s;
       const long long nc = (long long)c1 * c2 * c3;
       C2G_CUDA(ctx, cudaMemsetAsync(cnt + 1, 0, sizeof(int), st));
-      ctx->prof_begin(s == 4 ? "bader_classify4" : "bader_classify2");
-      k_classify<<<c2g_blocks_for(nc, 256), 256, 0, st>>>(n1, n2, n3, s, label,
-                                                          s == 4 ? b_cube4.as<unsigned char>() : b_cube2.as<unsigned char>(),
-                                                          list, cnt + 1);
-      ctx->prof_end();
-      C2G_KERNEL_CHECK(ctx);
+      if (nc > 0) {
+        ctx->prof_begin(s == 4 ? "bader_classify4" : "bader_classify2");
+        k_classify<<<c2g_blocks_for(nc, 256), 256, 0, st>>>(n1, n2, n3, S, s, lbuf,
+                                                            s == 4 ? b_cube4.as<unsigned char>() : b_cube2.as<unsigned char>(),
+                                                            list, cnt + 1);
+        ctx->prof_end();
+        C2G_KERNEL_CHECK(ctx);
+      }
       C2G_CUDA(ctx, cudaMemcpyAsync(hcnt, cnt, 32, cudaMemcpyDeviceToHost, st));
       C2G_CUDA(ctx, cudaStreamSynchronize(st));
       if ((rc = walk_list(hcnt[1], s == 4 ? "bader_walk_l2" : "bader_walk_l1")) != C2G_OK) return rc;
     }
-    // edge fix until no filled point is adjacent to a different label
+    // edge fix until no filled point (on any rank) is adjacent to a different label
     for (;;) {
+      if ((rc = exchange_halos(ctx, lbuf, plane, S, 3)) != C2G_OK) return rc;
       C2G_CUDA(ctx, cudaMemsetAsync(cnt + 1, 0, sizeof(int), st));
-      dim3 grid((n1 + TX - 1) / TX, (n2 + TY - 1) / TY, (n3 + TZ - 1) / TZ);
-      ctx->prof_begin("bader_edgefix");
-      k_edgefix<<<grid, 256, 0, st>>>(n1, n2, n3, label, list, cnt + 1);
-      ctx->prof_end();
-      C2G_KERNEL_CHECK(ctx);
+      if (S.nzl > 0) {
+        dim3 grid((n1 + TX - 1) / TX, (n2 + TY - 1) / TY, (S.nzl + TZ - 1) / TZ);
+        ctx->prof_begin("bader_edgefix");
+        k_edgefix<<<grid, 256, 0, st>>>(n1, n2, S, lbuf, list, cnt + 1);
+        ctx->prof_end();
+        C2G_KERNEL_CHECK(ctx);
+      }
+      if (G > 1) {
+        C2G_CUDA(ctx, cudaMemcpyAsync(cnt + 6, cnt + 1, sizeof(int), cudaMemcpyDeviceToDevice, st));
+        C2G_NCCL(ctx, ncclAllReduce(cnt + 6, cnt + 6, 1, ncclInt32, ncclMax, comm, st));
+      }
       C2G_CUDA(ctx, cudaMemcpyAsync(hcnt, cnt, 32, cudaMemcpyDeviceToHost, st));
       C2G_CUDA(ctx, cudaStreamSynchronize(st));
       fixpasses++;
-      if (hcnt[1] == 0) break;
+      const int any = (G > 1) ? hcnt[6] : hcnt[1];
+      if (any == 0) break;
       fixpts += hcnt[1];
       if ((rc = walk_list(hcnt[1], "bader_walk_fix")) != C2G_OK) return rc;
       if (fixpasses > 1000) return ctx->fail(C2G_ERR_STATE, "edge refinement did not converge");
     }
   }
 
-  // ---- maxima actually reached, output order, compaction ----
+  // ---- maxima actually reached (on any rank), output order, compaction ----
+  if (G > 1) C2G_NCCL(ctx, ncclAllReduce(reached, reached, ncand, ncclUint8, ncclMax, comm, st));
   std::vector<unsigned char> hreached(ncand);
-  C2G_CUDA(ctx, cudaMemcpy(hreached.data(), reached, ncand, cudaMemcpyDeviceToHost));
+  C2G_CUDA(ctx, cudaMemcpyAsync(hreached.data(), reached, ncand, cudaMemcpyDeviceToHost, st));
+  C2G_CUDA(ctx, cudaStreamSynchronize(st));
   std::vector<int> cand2out(ncand, -1);
   int nmax = 0;
   for (int i = 0; i < ncand; i++)
@@ -654,18 +820,16 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
   res->max_lin.resize(nmax);
   for (int i = 0; i < ncand; i++)
     if (cand2out[i] >= 0) res->max_lin[cand2out[i]] = cand[i];
-  DevBuf b_c2o, b_counts;
+  DevBuf b_c2o;
   C2G_CUDA(ctx, cudaMalloc(&b_c2o.p, sizeof(int) * ncand));
-  C2G_CUDA(ctx, cudaMalloc(&b_counts.p, sizeof(unsigned long long) * nmax));
   C2G_CUDA(ctx, cudaMemcpyAsync(b_c2o.p, cand2out.data(), sizeof(int) * ncand, cudaMemcpyHostToDevice, st));
-  C2G_CUDA(ctx, cudaMemsetAsync(b_counts.p, 0, sizeof(unsigned long long) * nmax, st));
   const int nblk = ctx->nsm * 8;
-  ctx->prof_begin("bader_compact");
-  k_compact<<<nblk, 256, 0, st>>>(nn, label, h, b_c2o.as<int>(), b_counts.as<unsigned long long>(), cnt + 3);
-  ctx->prof_end();
-  C2G_KERNEL_CHECK(ctx);
-  res->counts.resize(nmax);
-  C2G_CUDA(ctx, cudaMemcpyAsync(res->counts.data(), b_counts.p, sizeof(unsigned long long) * nmax, cudaMemcpyDeviceToHost, st));
+  if (nnl > 0) {
+    ctx->prof_begin("bader_compact");
+    k_compact<<<nblk, 256, 0, st>>>(nnl, res->d_label, h, b_c2o.as<int>(), cnt + 3);
+    ctx->prof_end();
+    C2G_KERNEL_CHECK(ctx);
+  }
   C2G_CUDA(ctx, cudaMemcpyAsync(hcnt, cnt, 32, cudaMemcpyDeviceToHost, st));
   C2G_CUDA(ctx, cudaStreamSynchronize(st));
   if (hcnt[3] != 0) return ctx->fail(C2G_ERR_NEWMAX, "label compaction found a terminal that is not a known maximum");
@@ -674,26 +838,30 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
     DevBuf b_first, b_perm;
     C2G_CUDA(ctx, cudaMalloc(&b_first.p, sizeof(int) * nmax));
     C2G_CUDA(ctx, cudaMemsetAsync(b_first.p, 0x7f, sizeof(int) * nmax, st));
-    ctx->prof_begin("bader_firstpoint");
-    k_firstpoint<<<nblk, 256, 0, st>>>(n1, n2, n3, label, b_first.as<int>());
-    ctx->prof_end();
-    C2G_KERNEL_CHECK(ctx);
+    if (nnl > 0) {
+      ctx->prof_begin("bader_firstpoint");
+      k_firstpoint<<<nblk, 256, 0, st>>>(n1, n2, n3, S, res->d_label, b_first.as<int>());
+      ctx->prof_end();
+      C2G_KERNEL_CHECK(ctx);
+    }
+    if (G > 1) C2G_NCCL(ctx, ncclAllReduce(b_first.p, b_first.p, nmax, ncclInt32, ncclMin, comm, st));
     std::vector<int> first(nmax);
-    C2G_CUDA(ctx, cudaMemcpy(first.data(), b_first.p, sizeof(int) * nmax, cudaMemcpyDeviceToHost));
+    C2G_CUDA(ctx, cudaMemcpyAsync(first.data(), b_first.p, sizeof(int) * nmax, cudaMemcpyDeviceToHost, st));
+    C2G_CUDA(ctx, cudaStreamSynchronize(st));
     std::vector<int> idx(nmax), perm(nmax);
     for (int i = 0; i < nmax; i++) idx[i] = i;
-    std::sort(idx.begin(), idx.end(), [&](int a, int b) { return first[a] < first[b]; });
+    std::sort(idx.begin(), idx.end(), [&](int a, int b) { return first[a] < first[b] || (first[a] == first[b] && a < b); });
     std::vector<int> ml(nmax);
-    std::vector<long long> cc(nmax);
-    for (int k = 0; k < nmax; k++) { perm[idx[k]] = k; ml[k] = res->max_lin[idx[k]]; cc[k] = res->counts[idx[k]]; }
+    for (int k = 0; k < nmax; k++) { perm[idx[k]] = k; ml[k] = res->max_lin[idx[k]]; }
     res->max_lin.swap(ml);
-    res->counts.swap(cc);
     C2G_CUDA(ctx, cudaMalloc(&b_perm.p, sizeof(int) * nmax));
     C2G_CUDA(ctx, cudaMemcpyAsync(b_perm.p, perm.data(), sizeof(int) * nmax, cudaMemcpyHostToDevice, st));
-    ctx->prof_begin("bader_permute");
-    k_permute_labels<<<nblk, 256, 0, st>>>(nn, label, b_perm.as<int>());
-    ctx->prof_end();
-    C2G_KERNEL_CHECK(ctx);
+    if (nnl > 0) {
+      ctx->prof_begin("bader_permute");
+      k_permute_labels<<<nblk, 256, 0, st>>>(nnl, res->d_label, b_perm.as<int>());
+      ctx->prof_end();
+      C2G_KERNEL_CHECK(ctx);
+    }
     C2G_CUDA(ctx, cudaStreamSynchronize(st));
   }
   unsigned long long hsteps = 0;

@@ -2,10 +2,32 @@
 // declared in include/critic2_gpu.h.
 #include "common.cuh"
 
-#include <nccl.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cmath>
+
+c2g_nccl_api& c2g_nccl() {
+  static c2g_nccl_api api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) {
+      api.err = "libnccl.so.2 not found";
+      return api;
+    }
+#define C2G_SYM(name)                                             \
+  api.name = (decltype(api.name))dlsym(h, "nccl" #name);          \
+  if (!api.name) { api.err = "missing NCCL symbol nccl" #name; return api; }
+    C2G_SYM(GetUniqueId) C2G_SYM(CommInitRank) C2G_SYM(CommDestroy) C2G_SYM(GetErrorString) C2G_SYM(GroupStart)
+    C2G_SYM(GroupEnd) C2G_SYM(Send) C2G_SYM(Recv) C2G_SYM(AllReduce) C2G_SYM(AllGather) C2G_SYM(Broadcast)
+#undef C2G_SYM
+    api.ok = true;
+  }
+  return api;
+}
 
 namespace {
 
@@ -142,6 +164,7 @@ int c2g_init(int device, c2g_context** out) {
 int c2g_nccl_unique_id(void* uid128) {
   if (!uid128) return C2G_ERR_ARG;
   static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  if (!c2g_nccl().ok) return C2G_ERR_NCCL;
   ncclUniqueId id;
   if (ncclGetUniqueId(&id) != ncclSuccess) return C2G_ERR_NCCL;
   memcpy(uid128, &id, 128);
@@ -156,6 +179,7 @@ int c2g_init_multi(int device, int rank, int nranks, const void* uid128, c2g_con
   ctx->nranks = nranks;
   if (nranks > 1) {
     if (!uid128) return ctx->fail(C2G_ERR_ARG, "c2g_init_multi: null nccl id");
+    if (!c2g_nccl().ok) return ctx->fail(C2G_ERR_NCCL, "c2g_init_multi: %s", c2g_nccl().err);
     ncclUniqueId id;
     memcpy(&id, uid128, 128);
     ncclComm_t comm;
@@ -176,6 +200,7 @@ void c2g_finalize(c2g_context* ctx) {
   for (auto e : ctx->event_pool) cudaEventDestroy(e);
   for (auto& p : ctx->pending) { cudaEventDestroy(p.second.first); cudaEventDestroy(p.second.second); }
   if (ctx->nccl) ncclCommDestroy((ncclComm_t)ctx->nccl);
+  if (ctx->t0) { cudaEventDestroy(ctx->t0); cudaEventDestroy(ctx->t1); }
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -211,6 +236,49 @@ int c2g_grid_upload(c2g_context* ctx, const double* f, const int n[3], int* hand
   return C2G_OK;
 }
 
+int c2g_slab_bounds_query(int n3, int nranks, int rank, int* zlo, int* zhi) {
+  if (!zlo || !zhi || n3 < 1 || nranks < 1 || rank < 0 || rank >= nranks) return C2G_ERR_ARG;
+  c2g_slab_bounds(n3, nranks, rank, zlo, zhi);
+  return C2G_OK;
+}
+
+int c2g_slab_range(c2g_context* ctx, int n3, int* zlo, int* zhi) {
+  if (!ctx || !zlo || !zhi || n3 < 1) return C2G_ERR_ARG;
+  c2g_slab_bounds(n3, ctx->nranks, ctx->rank, zlo, zhi);
+  return C2G_OK;
+}
+
+int c2g_grid_upload_slab(c2g_context* ctx, const double* fslab, const int n[3], int* handle) {
+  if (!ctx) return C2G_ERR_ARG;
+  int rc = c2g_grid_alloc(ctx, n, handle);
+  if (rc != C2G_OK) return rc;
+  c2g_grid& g = ctx->grids[*handle];
+  const size_t plane = (size_t)n[0] * n[1];
+  int zlo, zhi;
+  c2g_slab_bounds(n[2], ctx->nranks, ctx->rank, &zlo, &zhi);
+  if (zhi > zlo) {
+    if (!fslab) return ctx->fail(C2G_ERR_ARG, "c2g_grid_upload_slab: null slab");
+    C2G_CUDA(ctx, cudaMemcpyAsync(g.d + plane * zlo, fslab, sizeof(double) * plane * (zhi - zlo), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (ctx->nranks > 1) {
+    // replicate: every rank broadcasts its slab (NVLink); rho is read-only afterwards
+    ncclComm_t comm = (ncclComm_t)ctx->nccl;
+    ctx->prof_begin("grid_allgather_nccl");
+    ncclGroupStart();
+    for (int r = 0; r < ctx->nranks; r++) {
+      int a, b;
+      c2g_slab_bounds(n[2], ctx->nranks, r, &a, &b);
+      if (b > a) ncclBroadcast(g.d + plane * a, g.d + plane * a, plane * (b - a), ncclDouble, r, comm, ctx->stream);
+    }
+    ncclResult_t nr = ncclGroupEnd();
+    ctx->prof_end();
+    if (nr != ncclSuccess) return ctx->fail(C2G_ERR_NCCL, "c2g_grid_upload_slab: %s", ncclGetErrorString(nr));
+  }
+  C2G_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->prof_collect();
+  return C2G_OK;
+}
+
 int c2g_grid_download(c2g_context* ctx, int handle, double* f) {
   if (!ctx) return C2G_ERR_ARG;
   int rc = check_handle(ctx, handle, "c2g_grid_download");
@@ -218,6 +286,21 @@ int c2g_grid_download(c2g_context* ctx, int handle, double* f) {
   if (!f) return ctx->fail(C2G_ERR_ARG, "c2g_grid_download: null output");
   c2g_grid& g = ctx->grids[handle];
   C2G_CUDA(ctx, cudaMemcpyAsync(f, g.d, sizeof(double) * g.nn, cudaMemcpyDeviceToHost, ctx->stream));
+  C2G_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return C2G_OK;
+}
+
+int c2g_grid_download_slab(c2g_context* ctx, int handle, double* fslab) {
+  if (!ctx) return C2G_ERR_ARG;
+  int rc = check_handle(ctx, handle, "c2g_grid_download_slab");
+  if (rc) return rc;
+  c2g_grid& g = ctx->grids[handle];
+  int zlo, zhi;
+  c2g_slab_bounds(g.n[2], ctx->nranks, ctx->rank, &zlo, &zhi);
+  if (zhi <= zlo) return C2G_OK;
+  if (!fslab) return ctx->fail(C2G_ERR_ARG, "c2g_grid_download_slab: null output");
+  const size_t plane = (size_t)g.n[0] * g.n[1];
+  C2G_CUDA(ctx, cudaMemcpyAsync(fslab, g.d + plane * zlo, sizeof(double) * plane * (zhi - zlo), cudaMemcpyDeviceToHost, ctx->stream));
   C2G_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return C2G_OK;
 }
@@ -339,6 +422,26 @@ int c2g_basins_maxima(c2g_basins* res, int* pmax) {
 
 int c2g_basins_counts(c2g_basins* res, long long* counts) {
   if (!res || !counts) return C2G_ERR_ARG;
+  c2g_context* ctx = res->ctx;
+  if (res->kind != 0) return ctx->fail(C2G_ERR_STATE, "c2g_basins_counts: Bader results only");
+  if (res->counts.empty() && res->nmax > 0) {  // one 4 B/pt pass, on demand
+    unsigned long long* d_counts = nullptr;
+    C2G_CUDA(ctx, cudaMalloc(&d_counts, sizeof(unsigned long long) * res->nmax));
+    C2G_CUDA(ctx, cudaMemsetAsync(d_counts, 0, sizeof(unsigned long long) * res->nmax, ctx->stream));
+    const long long nnl = (long long)res->n[0] * res->n[1] * (res->zhi - res->zlo);
+    int rc = nnl > 0 ? c2g_launch_basin_reduce(ctx, nnl, res->d_label, 0, nullptr, res->nmax, nullptr, d_counts) : C2G_OK;
+    if (rc == C2G_OK && ctx->nranks > 1 &&
+        ncclAllReduce(d_counts, d_counts, res->nmax, ncclUint64, ncclSum, (ncclComm_t)ctx->nccl, ctx->stream) != ncclSuccess)
+      rc = ctx->fail(C2G_ERR_NCCL, "c2g_basins_counts: ncclAllReduce failed");
+    std::vector<unsigned long long> hc(res->nmax);
+    cudaError_t e = cudaMemcpyAsync(hc.data(), d_counts, sizeof(unsigned long long) * res->nmax, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_counts);
+    if (rc) return rc;
+    if (e != cudaSuccess) return ctx->fail(C2G_ERR_CUDA, "c2g_basins_counts: %s", cudaGetErrorString(e));
+    res->counts.assign(hc.begin(), hc.end());
+    ctx->prof_collect();
+  }
   for (int i = 0; i < res->nmax; i++) counts[i] = res->counts[i];
   return C2G_OK;
 }
@@ -376,13 +479,16 @@ int c2g_basins_labels(c2g_basins* res, int* idg) {
   c2g_context* ctx = res->ctx;
   if (!idg) return ctx->fail(C2G_ERR_ARG, "c2g_basins_labels: null output");
   if (!res->has_map) return ctx->fail(C2G_ERR_STATE, "c2g_basins_labels: call c2g_basins_set_map first");
+  // multi-GPU: every rank returns its own z-slab idg(:,:,zlo+1:zhi)
+  const long long nnl = (long long)res->n[0] * res->n[1] * (res->zhi - res->zlo);
+  if (nnl == 0) return C2G_OK;
   int* d_out = nullptr;
-  C2G_CUDA(ctx, cudaMalloc(&d_out, sizeof(int) * res->nn));
+  C2G_CUDA(ctx, cudaMalloc(&d_out, sizeof(int) * nnl));
   ctx->prof_begin("map_labels");
-  k_map_labels<<<ctx->nsm * 8, 256, 0, ctx->stream>>>(res->nn, res->d_label, res->d_map, d_out);
+  k_map_labels<<<ctx->nsm * 8, 256, 0, ctx->stream>>>(nnl, res->d_label, res->d_map, d_out);
   ctx->prof_end();
   cudaError_t e = cudaGetLastError();
-  if (e == cudaSuccess) e = cudaMemcpyAsync(idg, d_out, sizeof(int) * res->nn, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(idg, d_out, sizeof(int) * nnl, cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   cudaFree(d_out);
   if (e != cudaSuccess) return ctx->fail(C2G_ERR_CUDA, "c2g_basins_labels: %s", cudaGetErrorString(e));
@@ -398,11 +504,12 @@ int c2g_basins_stats(c2g_basins* res, long long stats[8]) {
 
 void c2g_basins_free(c2g_basins* res) {
   if (!res) return;
-  if (res->d_label) cudaFree(res->d_label);
+  if (res->d_lbuf) cudaFree(res->d_lbuf);
+  else if (res->d_label) cudaFree(res->d_label);
   if (res->d_map) cudaFree(res->d_map);
   if (res->d_vec) cudaFree(res->d_vec);
   if (res->d_area) cudaFree(res->d_area);
-  if (res->d_order) cudaFree(res->d_order);
+  c2g_yt_free_state(res);
   delete res;
 }
 
@@ -437,6 +544,23 @@ int c2g_flush_l2(c2g_context* ctx) {
   }
   k_flush<<<ctx->nsm * 4, 256, 0, ctx->stream>>>((float4*)ctx->flushbuf, ctx->flushbytes / 16);
   C2G_KERNEL_CHECK(ctx);
+  return C2G_OK;
+}
+
+int c2g_timer_start(c2g_context* ctx) {
+  if (!ctx) return C2G_ERR_ARG;
+  if (!ctx->t0) { C2G_CUDA(ctx, cudaEventCreate(&ctx->t0)); C2G_CUDA(ctx, cudaEventCreate(&ctx->t1)); }
+  C2G_CUDA(ctx, cudaEventRecord(ctx->t0, ctx->stream));
+  return C2G_OK;
+}
+
+int c2g_timer_stop(c2g_context* ctx, double* ms) {
+  if (!ctx || !ms || !ctx->t0) return C2G_ERR_ARG;
+  C2G_CUDA(ctx, cudaEventRecord(ctx->t1, ctx->stream));
+  C2G_CUDA(ctx, cudaEventSynchronize(ctx->t1));
+  float f = 0.f;
+  C2G_CUDA(ctx, cudaEventElapsedTime(&f, ctx->t0, ctx->t1));
+  *ms = f;
   return C2G_OK;
 }
 

@@ -3,6 +3,8 @@
 
 #include <cuda_runtime.h>
 
+#include "nccl_shim.h"
+
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -47,6 +49,7 @@ struct c2g_context {
   // multi-GPU
   int rank = 0, nranks = 1;
   void* nccl = nullptr;  // ncclComm_t
+  cudaEvent_t t0 = nullptr, t1 = nullptr;  // c2g_timer_*
 
   int fail(int code, const char* fmt, ...) {
     char buf[1024];
@@ -126,7 +129,9 @@ struct c2g_basins {
   int nmax = 0;
   // Bader: label[i] = index (0..nmax-1) into the ordered maxima list
   // YT   : label[i] = index of the basin for interior points, -1 for IAS points
-  int* d_label = nullptr;
+  int* d_label = nullptr;  // owned planes [zlo, zhi) (points into d_lbuf for Bader slabs)
+  int* d_lbuf = nullptr;   // Bader: label buffer with one halo plane below and above
+  int zlo = 0, zhi = 0;    // owned z range (single GPU: 0..n3)
   std::vector<int> max_lin;        // linear id of each maximum, in the returned order
   std::vector<long long> counts;   // points per maximum
   std::vector<int> map;            // maximum -> basin id (1-based; 0 = discarded)
@@ -140,8 +145,14 @@ struct c2g_basins {
   std::vector<double> area;
   int* d_vec = nullptr;
   double* d_area = nullptr;
-  int* d_order = nullptr;  // IAS points sorted by increasing (rho, index)  [n_ias]
+  void* yt = nullptr;  // YtState (yt.cu)
   long long n_ias = 0;
 };
+void c2g_yt_free_state(c2g_basins* res);
+void c2g_slab_bounds(int n3, int nranks, int rank, int* zlo, int* zhi);
+
+// integrate.cu: one streaming pass of per-maximum sums (sums[p*nmax+m]) and counts
+int c2g_launch_basin_reduce(c2g_context* ctx, long long nn, const int* label, int np, const double* const* f, int nmax,
+                            double* sums, unsigned long long* counts);
 
 static inline int c2g_blocks_for(long long n, int threads) { return (int)((n + threads - 1) / threads); }

@@ -160,13 +160,24 @@ extern "C" int c2g_integrate(c2g_context* ctx, c2g_basins* res, int nprop, const
   C2G_CUDA(ctx, cudaMemsetAsync(d_counts, 0, sizeof(unsigned long long) * nmax, ctx->stream));
   int rc = C2G_OK;
   bool first = true;
-  for (int k0 = 0; k0 < std::max(nprop, 1) && rc == C2G_OK; k0 += 4) {
+  // z-slab owned by this rank (single GPU: the whole grid); partial sums are all-reduced below
+  const size_t plane = (size_t)res->n[0] * res->n[1];
+  const long long nnl = (long long)plane * (res->zhi - res->zlo);
+  for (int k0 = 0; k0 < std::max(nprop, 1) && rc == C2G_OK && nnl > 0; k0 += 4) {
     const int np = std::min(4, nprop - k0);
     const double* fp[4] = {nullptr, nullptr, nullptr, nullptr};
-    for (int p = 0; p < np; p++) fp[p] = ctx->grids[fieldhandles[k0 + p]].d;
-    rc = c2g_launch_basin_reduce(ctx, res->nn, res->d_label, np > 0 ? np : 0, fp, nmax, d_sums + (size_t)k0 * nmax,
+    for (int p = 0; p < np; p++) fp[p] = ctx->grids[fieldhandles[k0 + p]].d + plane * res->zlo;
+    rc = c2g_launch_basin_reduce(ctx, nnl, res->d_label, np > 0 ? np : 0, fp, nmax, d_sums + (size_t)k0 * nmax,
                                  first ? d_counts : nullptr);
     first = false;
+  }
+  if (rc == C2G_OK && ctx->nranks > 1) {
+    ncclComm_t comm = (ncclComm_t)ctx->nccl;
+    ctx->prof_begin("basin_allreduce_nccl");
+    ncclResult_t r1 = ncclAllReduce(d_sums, d_sums, hs.size(), ncclDouble, ncclSum, comm, ctx->stream);
+    ncclResult_t r2 = ncclAllReduce(d_counts, d_counts, nmax, ncclUint64, ncclSum, comm, ctx->stream);
+    ctx->prof_end();
+    if (r1 != ncclSuccess || r2 != ncclSuccess) rc = ctx->fail(C2G_ERR_NCCL, "c2g_integrate: ncclAllReduce failed");
   }
   std::vector<unsigned long long> hc(nmax);
   cudaError_t e = cudaSuccess;

@@ -61,7 +61,17 @@ const char* c2g_describe(c2g_context* ctx);
 /* Replaces the bas%f copy of intgrid_driver (integration@proc.f90:255-271). */
 int c2g_grid_upload(c2g_context* ctx, const double* f, const int n[3], int* handle);
 int c2g_grid_alloc(c2g_context* ctx, const int n[3], int* handle);
+/* Multi-GPU (c2g_init_multi): the grid is sharded as z-slabs f(:,:,zlo+1:zhi) across the ranks
+ * (0-based half-open plane range from c2g_slab_range; boundaries are multiples of 4).  Every rank
+ * uploads only its own slab; the slabs are replicated over NVLink (NCCL) because the field is
+ * read-only and trajectories may cross slabs.  Labels and integrals stay sharded / all-reduced. */
+int c2g_slab_range(c2g_context* ctx, int n3, int* zlo, int* zhi);
+/* same without a context (pure host arithmetic; usable on a machine without a GPU) */
+int c2g_slab_bounds_query(int n3, int nranks, int rank, int* zlo, int* zhi);
+int c2g_grid_upload_slab(c2g_context* ctx, const double* fslab, const int n[3], int* handle);
 int c2g_grid_download(c2g_context* ctx, int handle, double* f);
+/* this rank's z-slab f(:,:,zlo+1:zhi) only */
+int c2g_grid_download_slab(c2g_context* ctx, int handle, double* fslab);
 int c2g_grid_free(c2g_context* ctx, int handle);
 /* Fill a resident grid with the synthetic promolecular-like density
  *   rho(x) = sum_atoms sum_images Z exp(-alpha r) cut(r), cut = (1-(r/rc)^2)^3 for rc>0 else 1
@@ -90,7 +100,8 @@ int c2g_basins_maxima(c2g_basins* res, int* pmax);
 int c2g_basins_counts(c2g_basins* res, long long* counts);
 /* map(nmax): maximum -> basin id (1..nattr; 0 = discarded attractor, points stay unassigned). */
 int c2g_basins_set_map(c2g_basins* res, int nattr, const int* map);
-/* bas%idg(n1,n2,n3) (move_alloc(volnum,bas%idg), bader@proc.f90:229). */
+/* bas%idg(n1,n2,n3) (move_alloc(volnum,bas%idg), bader@proc.f90:229).  Multi-GPU: every rank
+ * receives its own slab idg(:,:,zlo+1:zhi). */
 int c2g_basins_labels(c2g_basins* res, int* idg);
 /* int_reorder_gridout's nattr0 full-grid `where` passes (integration@proc.f90:1113-1122,
  * :1139-1144) as one composition of maps: new id = assigned(old id), old ids 1..nattr0. */
@@ -144,6 +155,10 @@ long long c2g_launch_count(c2g_context* ctx);
 /* write a buffer larger than L2 (flush between timed iterations) */
 int c2g_flush_l2(c2g_context* ctx);
 int c2g_synchronize(c2g_context* ctx);
+/* CUDA-event stopwatch on the context's stream (the stream every kernel of this library is launched on):
+ * elapsed device time between the two calls, including gaps while the host prepares the next launch. */
+int c2g_timer_start(c2g_context* ctx);
+int c2g_timer_stop(c2g_context* ctx, double* ms);
 
 #ifdef __cplusplus
 }

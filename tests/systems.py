@@ -20,7 +20,7 @@ def cell_x2c(a, b, c, alpha=90.0, beta=90.0, gamma=90.0):
     cy = c * (np.cos(al) - np.cos(be) * np.cos(ga)) / np.sin(ga)
     cz = np.sqrt(max(c * c - cx * cx - cy * cy, 0.0))
     m = np.stack([va, vb, np.array([cx, cy, cz])], axis=1)
-    m[np.abs(m) < 1e-15] = 0.0
+    m[np.abs(m) < 1e-13 * np.abs(m).max()] = 0.0
     return m
 
 

@@ -1,0 +1,150 @@
+"""GPU parity tests of YT and NCIPLOT through the C ABI (pytest -m gpu).
+
+YT bar: spatial basin ids (0 = IAS point) bit-exact against the oracle's faithful qcksort + sweep on
+tie-free data; volumes/populations <= 1e-10 relative; weight fields <= 1e-12 absolute.
+NCI bar: RDG <= 1e-12 relative; sign(lambda_2) identical except where |lambda_2| is at rounding level."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import cases
+import helpers as H
+import systems as S
+from critic2_b200 import capi
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "oracle_golden.json")
+
+
+@pytest.mark.parametrize("name", ["cubic48", "triclinic", "odd_dims", "tiny"])
+def test_yt_labels_weights_integrals(ctx, name):
+    c = cases.make_case(name)
+    n, x2c = c["n"], c["x2c"]
+    vec, area = S.wscell(x2c / np.array(n, dtype=float)[None, :])
+    d = orc.yt_integrate(c["f"], x2c, vec, area, atoms=c["atoms"])
+    f2 = cases.second_field(c["f"])
+    vref, pref = orc.integrate_yt(d, [c["f"], f2], S.omega(x2c))
+    h, h2 = ctx.upload(c["f"]), ctx.upload(f2)
+    b = ctx.yt_build(h, vec, area)
+    mp, na, xa = H.assign_attractors(b.maxima(), n, x2c, c["atoms"])
+    b.set_map(na, mp)
+    assert na == d.nattr
+    assert np.array_equal(b.labels(n), d.spatial_basin(n))
+    vol, ps = ctx.integrate(b, [h, h2], S.omega(x2c))
+    assert np.abs(vol - vref).max() <= 1e-10 * np.abs(vref).max()
+    assert np.abs(ps[:, 0] - pref[:, 0]).max() <= 1e-10 * np.abs(pref[:, 0]).max()
+    scale = np.abs(f2).sum() * S.omega(x2c) / f2.size
+    assert np.abs(ps[:, 1] - pref[:, 1]).max() <= 1e-10 * scale
+    for idb in range(1, na + 1):
+        assert np.abs(b.yt_weights(idb, n) - orc.yt_weights(d, idb, n)).max() <= 1e-12
+    b.free(); ctx.free(h); ctx.free(h2)
+
+
+def test_yt_golden(ctx):
+    g = json.load(open(GOLDEN))["yt"]
+    for name, ref in g.items():
+        c = cases.make_case(name)
+        vec, area = S.wscell(c["x2c"] / np.array(c["n"], dtype=float)[None, :])
+        assert len(area) == ref["nvec"]
+        h = ctx.upload(c["f"])
+        b = ctx.yt_build(h, vec, area)
+        mp, na, _ = H.assign_attractors(b.maxima(), c["n"], c["x2c"], c["atoms"])
+        b.set_map(na, mp)
+        lab = b.labels(c["n"])
+        assert hashlib.sha256(np.ascontiguousarray(lab.ravel(order="F")).tobytes()).hexdigest() == ref["labels_sha256"]
+        vol, ps = ctx.integrate(b, [h], S.omega(c["x2c"]))
+        assert np.allclose(ps[:, 0], ref["pop"], rtol=1e-10, atol=0)
+        assert np.allclose(vol, ref["vol"], rtol=1e-10, atol=0)
+        b.free(); ctx.free(h)
+
+
+def test_yt_chgcar_like_quantised_density(ctx):
+    """CHGCAR-like data (12 significant digits, values scaled by the cell volume): ties appear only
+    between non-neighbours, so labels and weights must still match the faithful oracle (qcksort order);
+    a coarsely quantised variant (6 digits) creates tied neighbours -- mismatches are counted and reported
+    against both the qcksort oracle and the stable-order oracle (the order the GPU defines)."""
+    c = cases.make_case("cubic48")
+    n, x2c = c["n"], c["x2c"]
+    vec, area = S.wscell(x2c / np.array(n, dtype=float)[None, :])
+    for digits, exact in ((12, True), (6, False)):
+        f = S.quantize(c["f"] * S.omega(x2c), digits)
+        d = orc.yt_integrate(f, x2c, vec, area, atoms=c["atoms"])
+        ds = orc.yt_integrate(f, x2c, vec, area, atoms=c["atoms"], stable=True)
+        h = ctx.upload(f)
+        b = ctx.yt_build(h, vec, area)
+        mp, na, _ = H.assign_attractors(b.maxima(), n, x2c, c["atoms"])
+        b.set_map(na, mp)
+        lab = b.labels(n)
+        m_q = int(np.count_nonzero(lab != d.spatial_basin(n)))
+        m_s = int(np.count_nonzero(lab != ds.spatial_basin(n)))
+        print(f"YT quantised to {digits} digits: label mismatches vs qcksort oracle {m_q}, vs stable oracle {m_s}")
+        assert m_s == 0
+        if exact:
+            assert m_q == 0 and na == d.nattr
+            vol, ps = ctx.integrate(b, [h], S.omega(x2c))
+            vref, pref = orc.integrate_yt(d, [f], S.omega(x2c))
+            assert np.abs(ps[:, 0] - pref[:, 0]).max() <= 1e-10 * np.abs(pref[:, 0]).max()
+        b.free(); ctx.free(h)
+
+
+def _nci_compare(crho, cgrad, crho_o, cgrad_o, lam2):
+    rel = np.abs(cgrad - cgrad_o) / np.maximum(np.abs(cgrad_o), 1e-300)
+    # RDG: 1e-12 relative (points with a vanishing gradient compare absolutely against the field scale)
+    ok = (rel <= 1e-12) | (np.abs(cgrad - cgrad_o) <= 1e-12 * np.median(cgrad_o))
+    assert ok.all(), f"max rel RDG error {rel.max():.3e}"
+    assert np.abs(np.abs(crho) - np.abs(crho_o)).max() <= 1e-12 * np.abs(crho_o).max()
+    flips = np.sign(crho) != np.sign(crho_o)
+    # sign(lambda_2) may only differ where lambda_2 is at rounding level
+    if flips.any():
+        assert (np.abs(lam2[flips]) <= 1e-9 * np.abs(lam2).max()).all()
+    return rel.max(), int(flips.sum())
+
+
+@pytest.mark.parametrize("name", ["triclinic", "odd_dims", "cubic48"])
+def test_nci_node_aligned(ctx, name):
+    c = cases.make_case(name)
+    crho_o, cgrad_o, lam2 = orc.nci_rdg(c["f"], c["x2c"], want_lam2=True)
+    h = ctx.upload(c["f"])
+    crho, cgrad = ctx.nci_rdg(h, c["x2c"], c["n"])
+    r, fl = _nci_compare(crho, cgrad, crho_o, cgrad_o, lam2)
+    print(f"NCI {name}: max rel RDG error {r:.2e}, sign flips {fl}")
+    ctx.free(h)
+
+
+def test_nci_general_lattice_and_nucleus_rule(ctx):
+    c = cases.make_case("triclinic")
+    x2c = c["x2c"]
+    nstep = (23, 19, 17)
+    x0 = x2c @ np.array([0.013, -0.021, 1.034])      # also exercises the wrap outside [-1e-4, 1+1e-4]
+    xmat = x2c / np.array(nstep, dtype=float)[None, :] * 0.93
+    nuc = (x2c @ c["atoms"].T).T
+    args = dict(nstep=nstep, x0=x0, xmat=xmat, nuclei_cart=nuc)
+    crho_o, cgrad_o, lam2 = orc.nci_rdg(c["f"], x2c, want_lam2=True, **args)
+    h = ctx.upload(c["f"])
+    crho, cgrad = ctx.nci_rdg(h, x2c, c["n"], **args)
+    _nci_compare(crho, cgrad, crho_o, cgrad_o, lam2)
+    # node-aligned with nuclei on nodes: RDG is exactly zero there on both sides
+    crho_o, cgrad_o, lam2 = orc.nci_rdg(c["f"], x2c, nuclei_cart=nuc, want_lam2=True)
+    crho, cgrad = ctx.nci_rdg(h, x2c, c["n"], nuclei_cart=nuc)
+    _nci_compare(crho, cgrad, crho_o, cgrad_o, lam2)
+    assert np.count_nonzero(cgrad == 0.0) >= len(nuc) and np.array_equal(cgrad == 0.0, cgrad_o == 0.0)
+    ctx.free(h)
+
+
+def test_nci_golden_and_resident(ctx):
+    ref = json.load(open(GOLDEN))["nci"]["triclinic"]
+    c = cases.make_case("triclinic")
+    h = ctx.upload(c["f"])
+    crho, cgrad = ctx.nci_rdg(h, c["x2c"], c["n"])
+    for (k, j, i), r, g in zip(ref["points_kji"], ref["crho"], ref["cgrad"]):
+        assert abs(crho[k, j, i] - r) <= 1e-12 * abs(r)
+        assert abs(cgrad[k, j, i] - g) <= 1e-12 * abs(g)
+    assert abs(cgrad.sum() - ref["sum_cgrad"]) <= 1e-11 * ref["sum_cgrad"]
+    hr, hg = ctx.nci_rdg_resident(h, c["x2c"], c["n"])
+    assert np.array_equal(ctx.download(hg, cgrad.shape), cgrad)
+    for hh in (h, hr, hg):
+        ctx.free(hh)
