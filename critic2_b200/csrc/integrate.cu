@@ -14,74 +14,114 @@
 
 namespace {
 
-constexpr int SEG_ITERS = 64;  // 32*64 = 2048 points per warp segment
+constexpr int SEG_ITERS = 64;      // 32*64 = 2048 points per warp segment
+constexpr int RED_BLOCKS_PER_SM = 8;
+constexpr int SMEM_TABLE_MAX = 6144;  // doubles per block (48 KB): nmax*(NP+1) must fit to use the shared table
 
-template <int NP>
-struct Acc {
-  double v[NP > 0 ? NP : 1];
-  unsigned long long cnt;
+// Accumulator target: a per-block shared-memory table when it fits (hot global addresses would
+// serialise in the L2 atomic unit: measured ~10 M same-address fp64 atomics/s), else global atomics.
+struct Sink {
+  double* tab;                    // shared: [(NP+1)][nmax] (slot NP = counts as double) or nullptr
+  double* gsums;                  // global sums [p*nmax+m]
+  unsigned long long* gcounts;    // global counts (may be null)
+  int nmax;
 };
 
 template <int NP>
-__device__ __forceinline__ void flush_uniform(Acc<NP>& a, int cur, double* __restrict__ sums,
-                                              unsigned long long* __restrict__ counts, int nmax, int lane) {
-  if (cur < 0) return;
-  unsigned long long c = a.cnt;
+__device__ __forceinline__ void sink_add(const Sink& k, int label, const double* s, unsigned long long c) {
+  if (k.tab) {
 #pragma unroll
-  for (int d = 16; d >= 1; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    for (int p = 0; p < NP; p++) atomicAdd(k.tab + (size_t)p * k.nmax + label, s[p]);
+    atomicAdd(k.tab + (size_t)NP * k.nmax + label, (double)c);  // exact: counts < 2^53
+  } else {
 #pragma unroll
-  for (int p = 0; p < NP; p++) {
-    double s = a.v[p];
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-    if (lane == 0) atomicAdd(sums + (size_t)p * nmax + cur, s);
-    a.v[p] = 0.0;
+    for (int p = 0; p < NP; p++) atomicAdd(k.gsums + (size_t)p * k.nmax + label, s[p]);
+    if (k.gcounts) atomicAdd(k.gcounts + label, c);
   }
-  if (lane == 0 && counts) atomicAdd(counts + cur, c);
-  a.cnt = 0;
 }
 
 template <int NP>
 __global__ void __launch_bounds__(256) k_basin_reduce(long long nn, const int* __restrict__ label,
                                                       const double* __restrict__ f0, const double* __restrict__ f1,
                                                       const double* __restrict__ f2, const double* __restrict__ f3,
-                                                      int nmax, double* __restrict__ sums,
-                                                      unsigned long long* __restrict__ counts) {
+                                                      int nmax, int use_table, double* __restrict__ sums,
+                                                      unsigned long long* __restrict__ counts,
+                                                      double* __restrict__ partials) {
+  extern __shared__ double s_tab[];
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   const long long seg = 32ll * SEG_ITERS;
   const double* fp[4] = {f0, f1, f2, f3};
-  Acc<NP> a;
+  Sink sink{use_table ? s_tab : nullptr, sums, counts, nmax};
+  if (use_table) {
+    for (int e = threadIdx.x; e < (NP + 1) * nmax; e += blockDim.x) s_tab[e] = 0.0;
+    __syncthreads();
+  }
+  double acc[NP > 0 ? NP : 1];
 #pragma unroll
-  for (int p = 0; p < (NP > 0 ? NP : 1); p++) a.v[p] = 0.0;
-  a.cnt = 0;
+  for (int p = 0; p < (NP > 0 ? NP : 1); p++) acc[p] = 0.0;
+  unsigned long long cnt = 0;
   int cur = -1;  // warp-uniform label of the current run
-  for (long long base = warp * seg; base < nn; base += nwarps * seg) {
-    for (int k = 0; k < SEG_ITERS; k++) {
-      const long long i = base + 32ll * k + lane;
-      if (base + 32ll * k >= nn) break;
-      int l = -1;
-      double v[NP > 0 ? NP : 1];
-      if (i < nn) {
-        l = label[i];
+  auto flush = [&]() {
+    if (cur >= 0 && __any_sync(0xffffffffu, cnt != 0)) {
+      unsigned long long c = cnt;
 #pragma unroll
-        for (int p = 0; p < NP; p++) v[p] = __ldg(fp[p] + i);
+      for (int d = 16; d >= 1; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+      double s[NP > 0 ? NP : 1];
+#pragma unroll
+      for (int p = 0; p < NP; p++) {
+        s[p] = acc[p];
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) s[p] += __shfl_xor_sync(0xffffffffu, s[p], d);
+      }
+      if (lane == 0) sink_add<NP>(sink, cur, s, c);
+    }
+#pragma unroll
+    for (int p = 0; p < (NP > 0 ? NP : 1); p++) acc[p] = 0.0;
+    cnt = 0;
+  };
+  for (long long base = warp * seg; base < nn; base += nwarps * seg) {
+    // software pipeline: the loads of group k+1 are in flight while group k is voted on
+    int l_next = -1;
+    double v_next[NP > 0 ? NP : 1];
+    {
+      const long long i = base + lane;
+      if (i < nn) {
+        l_next = label[i];
+#pragma unroll
+        for (int p = 0; p < NP; p++) v_next[p] = __ldg(fp[p] + i);
+      }
+    }
+    for (int k = 0; k < SEG_ITERS; k++) {
+      if (base + 32ll * k >= nn) break;
+      const int l = l_next;
+      double v[NP > 0 ? NP : 1];
+#pragma unroll
+      for (int p = 0; p < NP; p++) v[p] = v_next[p];
+      l_next = -1;
+      if (k + 1 < SEG_ITERS) {
+        const long long i = base + 32ll * (k + 1) + lane;
+        if (i < nn) {
+          l_next = label[i];
+#pragma unroll
+          for (int p = 0; p < NP; p++) v_next[p] = __ldg(fp[p] + i);
+        }
       }
       if (__all_sync(0xffffffffu, l == cur)) {
 #pragma unroll
-        for (int p = 0; p < NP; p++) a.v[p] += v[p];
-        a.cnt++;
+        for (int p = 0; p < NP; p++) acc[p] += v[p];
+        cnt++;
         continue;
       }
-      flush_uniform<NP>(a, cur, sums, counts, nmax, lane);
+      flush();
       const int l0 = __shfl_sync(0xffffffffu, l, 0);
       if (__all_sync(0xffffffffu, l == l0)) {
         cur = l0;
         if (l0 >= 0) {
 #pragma unroll
-          for (int p = 0; p < NP; p++) a.v[p] = v[p];
-          a.cnt = 1;
+          for (int p = 0; p < NP; p++) acc[p] = v[p];
+          cnt = 1;
         }
         continue;
       }
@@ -93,42 +133,69 @@ __global__ void __launch_bounds__(256) k_basin_reduce(long long nn, const int* _
         const int ll = __shfl_sync(0xffffffffu, l, leader);
         const bool mine = (l == ll);
         const unsigned grp = __ballot_sync(0xffffffffu, mine);
-        unsigned long long c = __popc(grp);
+        double s[NP > 0 ? NP : 1];
 #pragma unroll
         for (int p = 0; p < NP; p++) {
-          double s = mine ? v[p] : 0.0;
+          s[p] = mine ? v[p] : 0.0;
 #pragma unroll
-          for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-          if (lane == 0) atomicAdd(sums + (size_t)p * nmax + ll, s);
+          for (int d = 16; d >= 1; d >>= 1) s[p] += __shfl_xor_sync(0xffffffffu, s[p], d);
         }
-        if (lane == 0 && counts) atomicAdd(counts + ll, c);
+        if (lane == 0) sink_add<NP>(sink, ll, s, (unsigned long long)__popc(grp));
         todo &= ~grp;
       }
     }
   }
-  flush_uniform<NP>(a, cur, sums, counts, nmax, lane);
+  flush();
+  if (use_table) {
+    // block partials, reduced in a fixed order by k_reduce_partials (no hot global atomics)
+    __syncthreads();
+    double* out = partials + (size_t)blockIdx.x * (NP + 1) * nmax;
+    for (int e = threadIdx.x; e < (NP + 1) * nmax; e += blockDim.x) out[e] = s_tab[e];
+  }
+}
+
+// sums[p*nmax+m] += sum over blocks of partials[b][p][m]; counts from slot np
+__global__ void __launch_bounds__(256) k_reduce_partials(int nblocks, int np, int nmax, const double* __restrict__ partials,
+                                                         double* __restrict__ sums, unsigned long long* __restrict__ counts) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (np + 1) * nmax) return;
+  double s = 0.0;
+  for (int b = 0; b < nblocks; b++) s += partials[(size_t)b * (np + 1) * nmax + e];
+  if (e < np * nmax) sums[e] += s;
+  else if (counts) counts[e - np * nmax] += (unsigned long long)(s + 0.5);
 }
 
 }  // namespace
 
-// sums[(p*nmax)+m], counts[m] per MAXIMUM index (device pointers); fields: up to 4 device arrays
+// sums[(p*nmax)+m], counts[m] per MAXIMUM index (device pointers, accumulated into); fields: up to 4 device arrays
 int c2g_launch_basin_reduce(c2g_context* ctx, long long nn, const int* label, int np, const double* const* f, int nmax,
                             double* sums, unsigned long long* counts) {
-  const int blocks = ctx->nsm * 8;
+  const int blocks = ctx->nsm * RED_BLOCKS_PER_SM;
   const double* f0 = np > 0 ? f[0] : nullptr;
   const double* f1 = np > 1 ? f[1] : nullptr;
   const double* f2 = np > 2 ? f[2] : nullptr;
   const double* f3 = np > 3 ? f[3] : nullptr;
+  const int use_table = ((long long)(np + 1) * nmax <= SMEM_TABLE_MAX) ? 1 : 0;
+  const size_t smem = use_table ? sizeof(double) * (size_t)(np + 1) * nmax : 0;
+  double* partials = nullptr;
+  if (use_table) C2G_CUDA(ctx, cudaMallocAsync(&partials, sizeof(double) * (size_t)blocks * (np + 1) * nmax, ctx->stream));
   ctx->prof_begin("basin_reduce");
   switch (np) {
-    case 0: k_basin_reduce<0><<<blocks, 256, 0, ctx->stream>>>(nn, label, f0, f1, f2, f3, nmax, sums, counts); break;
-    case 1: k_basin_reduce<1><<<blocks, 256, 0, ctx->stream>>>(nn, label, f0, f1, f2, f3, nmax, sums, counts); break;
-    case 2: k_basin_reduce<2><<<blocks, 256, 0, ctx->stream>>>(nn, label, f0, f1, f2, f3, nmax, sums, counts); break;
-    case 3: k_basin_reduce<3><<<blocks, 256, 0, ctx->stream>>>(nn, label, f0, f1, f2, f3, nmax, sums, counts); break;
-    default: k_basin_reduce<4><<<blocks, 256, 0, ctx->stream>>>(nn, label, f0, f1, f2, f3, nmax, sums, counts); break;
+    case 0: k_basin_reduce<0><<<blocks, 256, smem, ctx->stream>>>(nn, label, f0, f1, f2, f3, nmax, use_table, sums, counts, partials); break;
+    case 1: k_basin_reduce<1><<<blocks, 256, smem, ctx->stream>>>(nn, label, f0, f1, f2, f3, nmax, use_table, sums, counts, partials); break;
+    case 2: k_basin_reduce<2><<<blocks, 256, smem, ctx->stream>>>(nn, label, f0, f1, f2, f3, nmax, use_table, sums, counts, partials); break;
+    case 3: k_basin_reduce<3><<<blocks, 256, smem, ctx->stream>>>(nn, label, f0, f1, f2, f3, nmax, use_table, sums, counts, partials); break;
+    default: k_basin_reduce<4><<<blocks, 256, smem, ctx->stream>>>(nn, label, f0, f1, f2, f3, nmax, use_table, sums, counts, partials); break;
   }
-  ctx->prof_end();
-  C2G_KERNEL_CHECK(ctx);
+  int nl = 1;
+  if (use_table) {
+    k_reduce_partials<<<c2g_blocks_for((long long)(np + 1) * nmax, 256), 256, 0, ctx->stream>>>(blocks, np, nmax, partials, sums, counts);
+    nl = 2;
+  }
+  ctx->prof_end(nl);
+  cudaError_t e = cudaGetLastError();
+  if (partials) cudaFreeAsync(partials, ctx->stream);
+  if (e != cudaSuccess) return ctx->fail(C2G_ERR_CUDA, "basin_reduce launch: %s", cudaGetErrorString(e));
   return C2G_OK;
 }
 

@@ -51,6 +51,27 @@ def test_labels_bit_exact_vs_reference_scan(ctx, name, algo):
     b.free(); ctx.free(h); ctx.free(h2)
 
 
+def test_degenerate_thin_cell_reported(ctx):
+    """Scan-order dependent residue of the sequential reference (see tests/cases.py): bounded and reported,
+    not bit-exact.  The exact-walk referee must still equal the oracle's own-trajectory labelling."""
+    c = cases.make_case("thin_cell")
+    idg, nattr, _, _ = orc.bader_integrate(c["f"], c["x2c"], atoms=c["atoms"])
+    term, _ = orc.bader_canonical(c["f"], c["x2c"])
+    for algo in (capi.BADER_EXACT, capi.BADER_FAST):
+        h, b, na = gpu_bader(ctx, c, algo)
+        lab = b.labels(c["n"])
+        mism = int(np.count_nonzero(lab != idg))
+        print(f"thin_cell algo={algo}: {mism} of {lab.size} labels differ from the sequential reference")
+        assert na == nattr and mism <= 1e-4 * lab.size
+        if algo == capi.BADER_EXACT:
+            pm = b.maxima() - 1
+            lin = pm[:, 0] + c["n"][0] * (pm[:, 1] + c["n"][1] * pm[:, 2])
+            t2 = np.searchsorted(np.sort(lin), term)                      # terminal -> index in the sorted maxima list
+            b.set_map(b.nmax, np.arange(1, b.nmax + 1, dtype=np.int32))
+            assert np.array_equal(b.labels(c["n"]), (t2 + 1).astype(np.int32))
+        b.free(); ctx.free(h)
+
+
 def test_golden_labels(ctx):
     g = json.load(open(GOLDEN))["bader"]
     for name, ref in g.items():
