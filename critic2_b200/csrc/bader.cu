@@ -492,12 +492,6 @@ __global__ void k_permute_labels(long long nn, int* __restrict__ label, const in
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nn; i += stride) label[i] = perm[label[i]];
 }
 
-struct DevBuf {
-  void* p = nullptr;
-  ~DevBuf() { if (p) cudaFree(p); }
-  template <class T> T* as() { return (T*)p; }
-};
-
 #define C2G_NCCL(ctx, call)                                                                         \
   do {                                                                                              \
     ncclResult_t r__ = (call);                                                                      \
@@ -583,7 +577,7 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
 
   // the owned planes start one plane into the buffer: pad so that they are 16-byte aligned (int4 passes)
   const size_t pad = (4 - plane % 4) % 4;
-  C2G_CUDA(ctx, cudaMalloc(&res->d_lbuf, sizeof(int) * (plane * (S.nzl + 2) + pad)));
+  C2G_CUDA(ctx, c2g_alloc(ctx, (void**)&res->d_lbuf, sizeof(int) * (plane * (S.nzl + 2) + pad)));
   int* lbuf = res->d_lbuf + pad;
   res->d_label = lbuf + plane;                               // owned planes
   int* label_g = lbuf + plane - (long long)plane * S.zlo;    // label_g[global id] for owned points
@@ -593,16 +587,16 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
   const int c21 = (n1 + 1) / 2, c22 = (n2 + 1) / 2, c23 = (S.nzl + 1) / 2;
   const size_t ncube4 = std::max<size_t>(1, (size_t)c41 * c42 * c43), ncube2 = std::max<size_t>(1, (size_t)c21 * c22 * c23);
   DevBuf b_cube4, b_cube2, b_cand, b_cnt;
-  C2G_CUDA(ctx, cudaMalloc(&b_cube4.p, ncube4));
-  C2G_CUDA(ctx, cudaMalloc(&b_cube2.p, ncube2));
+  C2G_CUDA(ctx, b_cube4.alloc(ctx, ncube4));
+  C2G_CUDA(ctx, b_cube2.alloc(ctx, ncube2));
   int maxcand = (int)std::max<long long>(1, std::min<long long>(nnl, std::max<long long>(1 << 16, nnl / 64)));
-  C2G_CUDA(ctx, cudaMalloc(&b_cnt.p, 64));
+  C2G_CUDA(ctx, b_cnt.alloc(ctx, 64));
   // counters: [0] ncand, [1] nlist, [2] noverflow, [3] err ; [4..5] nsteps (u64) ; [6] scratch for collectives
   int* cnt = b_cnt.as<int>();
   unsigned long long* nsteps = (unsigned long long*)(cnt + 4);
   int hcnt[8];
   for (int attempt = 0;; attempt++) {
-    C2G_CUDA(ctx, cudaMalloc(&b_cand.p, sizeof(int) * (size_t)maxcand));
+    C2G_CUDA(ctx, b_cand.alloc(ctx, sizeof(int) * (size_t)maxcand));
     C2G_CUDA(ctx, cudaMemsetAsync(cnt, 0, 64, st));
     C2G_CUDA(ctx, cudaMemsetAsync(b_cube4.p, 0, ncube4, st));
     C2G_CUDA(ctx, cudaMemsetAsync(b_cube2.p, 0, ncube2, st));
@@ -620,7 +614,7 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
     C2G_CUDA(ctx, cudaStreamSynchronize(st));
     if (hcnt[0] <= maxcand) break;
     if (attempt > 0) return ctx->fail(C2G_ERR_OVERFLOW, "candidate maxima list overflow");
-    cudaFree(b_cand.p); b_cand.p = nullptr;
+    b_cand.reset();
     maxcand = hcnt[0];
   }
   int ncand_local = hcnt[0];
@@ -631,7 +625,7 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
   } else {
     // all ranks need every candidate (a trajectory may end in any slab): padded all-gather
     DevBuf b_mx, b_all;
-    C2G_CUDA(ctx, cudaMalloc(&b_mx.p, sizeof(int)));
+    C2G_CUDA(ctx, b_mx.alloc(ctx, sizeof(int)));
     C2G_CUDA(ctx, cudaMemcpyAsync(b_mx.p, &ncand_local, sizeof(int), cudaMemcpyHostToDevice, st));
     C2G_NCCL(ctx, ncclAllReduce(b_mx.p, b_mx.p, 1, ncclInt32, ncclMax, comm, st));
     int mx = 0;
@@ -639,11 +633,11 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
     C2G_CUDA(ctx, cudaStreamSynchronize(st));
     mx = std::max(mx, 1);
     DevBuf b_pad;
-    C2G_CUDA(ctx, cudaMalloc(&b_pad.p, sizeof(int) * (size_t)mx));
+    C2G_CUDA(ctx, b_pad.alloc(ctx, sizeof(int) * (size_t)mx));
     C2G_CUDA(ctx, cudaMemsetAsync(b_pad.p, 0xff, sizeof(int) * (size_t)mx, st));
     if (ncand_local)
       C2G_CUDA(ctx, cudaMemcpyAsync(b_pad.p, b_cand.p, sizeof(int) * ncand_local, cudaMemcpyDeviceToDevice, st));
-    C2G_CUDA(ctx, cudaMalloc(&b_all.p, sizeof(int) * (size_t)mx * G));
+    C2G_CUDA(ctx, b_all.alloc(ctx, sizeof(int) * (size_t)mx * G));
     ctx->prof_begin("bader_cand_allgather_nccl");
     C2G_NCCL(ctx, ncclAllGather(b_pad.p, b_all.p, mx, ncclInt32, comm, st));
     ctx->prof_end();
@@ -666,9 +660,9 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
     hk[s] = cand[i]; hv[s] = i;
   }
   DevBuf b_hk, b_hv, b_reached;
-  C2G_CUDA(ctx, cudaMalloc(&b_hk.p, sizeof(int) * hsize));
-  C2G_CUDA(ctx, cudaMalloc(&b_hv.p, sizeof(int) * hsize));
-  C2G_CUDA(ctx, cudaMalloc(&b_reached.p, ncand));
+  C2G_CUDA(ctx, b_hk.alloc(ctx, sizeof(int) * hsize));
+  C2G_CUDA(ctx, b_hv.alloc(ctx, sizeof(int) * hsize));
+  C2G_CUDA(ctx, b_reached.alloc(ctx, ncand));
   C2G_CUDA(ctx, cudaMemcpyAsync(b_hk.p, hk.data(), sizeof(int) * hsize, cudaMemcpyHostToDevice, st));
   C2G_CUDA(ctx, cudaMemcpyAsync(b_hv.p, hv.data(), sizeof(int) * hsize, cudaMemcpyHostToDevice, st));
   C2G_CUDA(ctx, cudaMemsetAsync(b_reached.p, 0, ncand, st));
@@ -678,9 +672,9 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
   // work list / overflow list
   DevBuf b_list, b_over;
   const long long listcap = (algo == C2G_BADER_EXACT) ? 1 : std::max<long long>(1, nnl);
-  C2G_CUDA(ctx, cudaMalloc(&b_list.p, sizeof(int) * (size_t)listcap));
+  C2G_CUDA(ctx, b_list.alloc(ctx, sizeof(int) * (size_t)listcap));
   long long overcap = std::max<long long>(1024, nnl / 16);
-  C2G_CUDA(ctx, cudaMalloc(&b_over.p, sizeof(int) * (size_t)overcap));
+  C2G_CUDA(ctx, b_over.alloc(ctx, sizeof(int) * (size_t)overcap));
   int* list = b_list.as<int>();
   int* over = b_over.as<int>();
   long long walked = 0, fixpts = 0, fixpasses = 0, noverflow_total = 0;
@@ -697,7 +691,7 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
     const int bigcap = (int)std::min<long long>(g.nn, 1 << 22);
     const int chunk = (int)std::max<long long>(1, std::min<long long>(nov, (1ll << 31) / bigcap));  // <= 8 GiB scratch
     DevBuf b_scr;
-    C2G_CUDA(ctx, cudaMalloc(&b_scr.p, sizeof(int) * (size_t)chunk * bigcap));
+    C2G_CUDA(ctx, b_scr.alloc(ctx, sizeof(int) * (size_t)chunk * bigcap));
     for (int off = 0; off < nov; off += chunk) {
       const int c = std::min(chunk, nov - off);
       ctx->prof_begin("bader_walk_big");
@@ -715,9 +709,9 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
   };
   auto grow_over = [&](long long need) -> int {
     if (need > overcap) {
-      cudaFree(b_over.p); b_over.p = nullptr;
+      b_over.reset();
       overcap = need;
-      C2G_CUDA(ctx, cudaMalloc(&b_over.p, sizeof(int) * (size_t)overcap));
+      C2G_CUDA(ctx, b_over.alloc(ctx, sizeof(int) * (size_t)overcap));
       over = b_over.as<int>();
     }
     return C2G_OK;
@@ -821,7 +815,7 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
   for (int i = 0; i < ncand; i++)
     if (cand2out[i] >= 0) res->max_lin[cand2out[i]] = cand[i];
   DevBuf b_c2o;
-  C2G_CUDA(ctx, cudaMalloc(&b_c2o.p, sizeof(int) * ncand));
+  C2G_CUDA(ctx, b_c2o.alloc(ctx, sizeof(int) * ncand));
   C2G_CUDA(ctx, cudaMemcpyAsync(b_c2o.p, cand2out.data(), sizeof(int) * ncand, cudaMemcpyHostToDevice, st));
   const int nblk = ctx->nsm * 8;
   if (nnl > 0) {
@@ -836,7 +830,7 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
 
   if (order == C2G_ORDER_SCAN && nmax > 1) {
     DevBuf b_first, b_perm;
-    C2G_CUDA(ctx, cudaMalloc(&b_first.p, sizeof(int) * nmax));
+    C2G_CUDA(ctx, b_first.alloc(ctx, sizeof(int) * nmax));
     C2G_CUDA(ctx, cudaMemsetAsync(b_first.p, 0x7f, sizeof(int) * nmax, st));
     if (nnl > 0) {
       ctx->prof_begin("bader_firstpoint");
@@ -854,7 +848,7 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
     std::vector<int> ml(nmax);
     for (int k = 0; k < nmax; k++) { perm[idx[k]] = k; ml[k] = res->max_lin[idx[k]]; }
     res->max_lin.swap(ml);
-    C2G_CUDA(ctx, cudaMalloc(&b_perm.p, sizeof(int) * nmax));
+    C2G_CUDA(ctx, b_perm.alloc(ctx, sizeof(int) * nmax));
     C2G_CUDA(ctx, cudaMemcpyAsync(b_perm.p, perm.data(), sizeof(int) * nmax, cudaMemcpyHostToDevice, st));
     if (nnl > 0) {
       ctx->prof_begin("bader_permute");

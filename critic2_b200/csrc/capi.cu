@@ -153,6 +153,13 @@ int c2g_init(int device, c2g_context** out) {
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return C2G_ERR_CUDA; }
   ctx->nsm = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return C2G_ERR_CUDA; }
+  {  // keep freed blocks in the stream-ordered pool (no trimming at synchronisation points)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long thr = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+  }
   char buf[256];
   snprintf(buf, sizeof(buf), "critic2_gpu 0.1 sm_%d%d %s %d SMs %.1f GB", prop.major, prop.minor, prop.name,
            prop.multiProcessorCount, prop.totalGlobalMem / 1e9);
@@ -195,7 +202,8 @@ void c2g_finalize(c2g_context* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (auto& g : ctx->grids)
-    if (g.used && g.d) cudaFree(g.d);
+    if (g.used && g.d) cudaFreeAsync(g.d, ctx->stream);
+  cudaStreamSynchronize(ctx->stream);
   if (ctx->flushbuf) cudaFree(ctx->flushbuf);
   for (auto e : ctx->event_pool) cudaEventDestroy(e);
   for (auto& p : ctx->pending) { cudaEventDestroy(p.second.first); cudaEventDestroy(p.second.second); }
@@ -214,7 +222,7 @@ int c2g_grid_alloc(c2g_context* ctx, const int n[3], int* handle) {
   c2g_grid g;
   g.n[0] = n[0]; g.n[1] = n[1]; g.n[2] = n[2];
   g.nn = (long long)n[0] * n[1] * n[2];
-  C2G_CUDA(ctx, cudaMalloc(&g.d, sizeof(double) * g.nn));
+  C2G_CUDA(ctx, c2g_alloc(ctx, (void**)&g.d, sizeof(double) * g.nn));
   g.used = true;
   int h = -1;
   for (size_t i = 0; i < ctx->grids.size(); i++)
@@ -310,8 +318,7 @@ int c2g_grid_free(c2g_context* ctx, int handle) {
   int rc = check_handle(ctx, handle, "c2g_grid_free");
   if (rc) return rc;
   c2g_grid& g = ctx->grids[handle];
-  cudaStreamSynchronize(ctx->stream);
-  cudaFree(g.d);
+  c2g_release(ctx, g.d);
   g = c2g_grid();
   return C2G_OK;
 }
@@ -426,7 +433,7 @@ int c2g_basins_counts(c2g_basins* res, long long* counts) {
   if (res->kind != 0) return ctx->fail(C2G_ERR_STATE, "c2g_basins_counts: Bader results only");
   if (res->counts.empty() && res->nmax > 0) {  // one 4 B/pt pass, on demand
     unsigned long long* d_counts = nullptr;
-    C2G_CUDA(ctx, cudaMalloc(&d_counts, sizeof(unsigned long long) * res->nmax));
+    C2G_CUDA(ctx, c2g_alloc(ctx, (void**)&d_counts, sizeof(unsigned long long) * res->nmax));
     C2G_CUDA(ctx, cudaMemsetAsync(d_counts, 0, sizeof(unsigned long long) * res->nmax, ctx->stream));
     const long long nnl = (long long)res->n[0] * res->n[1] * (res->zhi - res->zlo);
     int rc = nnl > 0 ? c2g_launch_basin_reduce(ctx, nnl, res->d_label, 0, nullptr, res->nmax, nullptr, d_counts) : C2G_OK;
@@ -436,7 +443,7 @@ int c2g_basins_counts(c2g_basins* res, long long* counts) {
     std::vector<unsigned long long> hc(res->nmax);
     cudaError_t e = cudaMemcpyAsync(hc.data(), d_counts, sizeof(unsigned long long) * res->nmax, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_counts);
+    c2g_release(ctx, d_counts);
     if (rc) return rc;
     if (e != cudaSuccess) return ctx->fail(C2G_ERR_CUDA, "c2g_basins_counts: %s", cudaGetErrorString(e));
     res->counts.assign(hc.begin(), hc.end());
@@ -454,7 +461,7 @@ int c2g_basins_set_map(c2g_basins* res, int nattr, const int* map) {
     if (map[i] < 0 || map[i] > nattr) return ctx->fail(C2G_ERR_ARG, "c2g_basins_set_map: map(%d)=%d out of range", i + 1, map[i]);
   res->map.assign(map, map + res->nmax);
   res->nattr = nattr;
-  if (!res->d_map) C2G_CUDA(ctx, cudaMalloc(&res->d_map, sizeof(int) * std::max(res->nmax, 1)));
+  if (!res->d_map) C2G_CUDA(ctx, c2g_alloc(ctx, (void**)&res->d_map, sizeof(int) * std::max(res->nmax, 1)));
   C2G_CUDA(ctx, cudaMemcpyAsync(res->d_map, res->map.data(), sizeof(int) * res->nmax, cudaMemcpyHostToDevice, ctx->stream));
   C2G_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   res->has_map = true;
@@ -483,14 +490,14 @@ int c2g_basins_labels(c2g_basins* res, int* idg) {
   const long long nnl = (long long)res->n[0] * res->n[1] * (res->zhi - res->zlo);
   if (nnl == 0) return C2G_OK;
   int* d_out = nullptr;
-  C2G_CUDA(ctx, cudaMalloc(&d_out, sizeof(int) * nnl));
+  C2G_CUDA(ctx, c2g_alloc(ctx, (void**)&d_out, sizeof(int) * nnl));
   ctx->prof_begin("map_labels");
   k_map_labels<<<ctx->nsm * 8, 256, 0, ctx->stream>>>(nnl, res->d_label, res->d_map, d_out);
   ctx->prof_end();
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpyAsync(idg, d_out, sizeof(int) * nnl, cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(d_out);
+  c2g_release(ctx, d_out);
   if (e != cudaSuccess) return ctx->fail(C2G_ERR_CUDA, "c2g_basins_labels: %s", cudaGetErrorString(e));
   ctx->prof_collect();
   return C2G_OK;
@@ -504,9 +511,9 @@ int c2g_basins_stats(c2g_basins* res, long long stats[8]) {
 
 void c2g_basins_free(c2g_basins* res) {
   if (!res) return;
-  if (res->d_lbuf) cudaFree(res->d_lbuf);
-  else if (res->d_label) cudaFree(res->d_label);
-  if (res->d_map) cudaFree(res->d_map);
+  if (res->d_lbuf) c2g_release(res->ctx, res->d_lbuf);
+  else if (res->d_label) c2g_release(res->ctx, res->d_label);
+  if (res->d_map) c2g_release(res->ctx, res->d_map);
   if (res->d_vec) cudaFree(res->d_vec);
   if (res->d_area) cudaFree(res->d_area);
   c2g_yt_free_state(res);

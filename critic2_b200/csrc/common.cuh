@@ -155,4 +155,30 @@ void c2g_slab_bounds(int n3, int nranks, int rank, int* zlo, int* zhi);
 int c2g_launch_basin_reduce(c2g_context* ctx, long long nn, const int* label, int np, const double* const* f, int nmax,
                             double* sums, unsigned long long* counts);
 
+// stream-ordered pool allocations (cudaMallocAsync with an unbounded release threshold, set in c2g_init):
+// repeated calls reuse the same device memory instead of paying cudaMalloc/cudaFree every time
+static inline cudaError_t c2g_alloc(c2g_context* ctx, void** p, size_t bytes) {
+  return cudaMallocAsync(p, bytes ? bytes : 1, ctx->stream);
+}
+static inline void c2g_release(c2g_context* ctx, void* p) {
+  if (p) cudaFreeAsync(p, ctx->stream);
+}
+struct DevBuf {
+  c2g_context* ctx = nullptr;
+  void* p = nullptr;
+  DevBuf() {}
+  explicit DevBuf(c2g_context* c) : ctx(c) {}
+  ~DevBuf() { reset(); }
+  void reset() {
+    if (p) { if (ctx) cudaFreeAsync(p, ctx->stream); else cudaFree(p); }
+    p = nullptr;
+  }
+  cudaError_t alloc(c2g_context* c, size_t bytes) {
+    reset();
+    ctx = c;
+    return c2g_alloc(c, &p, bytes);
+  }
+  template <class T> T* as() { return (T*)p; }
+};
+
 static inline int c2g_blocks_for(long long n, int threads) { return (int)((n + threads - 1) / threads); }

@@ -221,8 +221,8 @@ extern "C" int c2g_integrate(c2g_context* ctx, c2g_basins* res, int nprop, const
   double* d_sums = nullptr;
   unsigned long long* d_counts = nullptr;
   std::vector<double> hs((size_t)std::max(nprop, 1) * nmax, 0.0);
-  C2G_CUDA(ctx, cudaMalloc(&d_sums, sizeof(double) * hs.size()));
-  C2G_CUDA(ctx, cudaMalloc(&d_counts, sizeof(unsigned long long) * nmax));
+  C2G_CUDA(ctx, c2g_alloc(ctx, (void**)&d_sums, sizeof(double) * hs.size()));
+  C2G_CUDA(ctx, c2g_alloc(ctx, (void**)&d_counts, sizeof(unsigned long long) * nmax));
   C2G_CUDA(ctx, cudaMemsetAsync(d_sums, 0, sizeof(double) * hs.size(), ctx->stream));
   C2G_CUDA(ctx, cudaMemsetAsync(d_counts, 0, sizeof(unsigned long long) * nmax, ctx->stream));
   int rc = C2G_OK;
@@ -253,8 +253,8 @@ extern "C" int c2g_integrate(c2g_context* ctx, c2g_basins* res, int nprop, const
     if (e == cudaSuccess) e = cudaMemcpyAsync(hc.data(), d_counts, sizeof(unsigned long long) * nmax, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   }
-  cudaFree(d_sums);
-  cudaFree(d_counts);
+  c2g_release(ctx, d_sums);
+  c2g_release(ctx, d_counts);
   if (rc != C2G_OK) return rc;
   if (e != cudaSuccess) return ctx->fail(C2G_ERR_CUDA, "c2g_integrate: %s", cudaGetErrorString(e));
   ctx->prof_collect();

@@ -285,7 +285,7 @@ int nci_launch(c2g_context* ctx, int handle, const double x0[3], const double xm
   P.nnuc = nnuc;
   double* d_nuc = nullptr;
   if (nnuc > 0) {
-    C2G_CUDA(ctx, cudaMalloc(&d_nuc, sizeof(double) * 3 * nnuc));
+    C2G_CUDA(ctx, c2g_alloc(ctx, (void**)&d_nuc, sizeof(double) * 3 * nnuc));
     C2G_CUDA(ctx, cudaMemcpyAsync(d_nuc, nuc_cart, sizeof(double) * 3 * nnuc, cudaMemcpyHostToDevice, ctx->stream));
   }
   dim3 grid((nstep[0] + BI - 1) / BI, (nstep[1] + BJ - 1) / BJ, (nstep[2] + BK - 1) / BK);
@@ -294,7 +294,7 @@ int nci_launch(c2g_context* ctx, int handle, const double x0[3], const double xm
   ctx->prof_end();
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  if (d_nuc) cudaFree(d_nuc);
+  if (d_nuc) c2g_release(ctx, d_nuc);
   if (e != cudaSuccess) return ctx->fail(C2G_ERR_CUDA, "nci_rdg: %s", cudaGetErrorString(e));
   ctx->prof_collect();
   return C2G_OK;
@@ -322,8 +322,8 @@ extern "C" int c2g_nci_rdg(c2g_context* ctx, int handle, const double x0[3], con
   if (!crho || !cgrad) return ctx->fail(C2G_ERR_ARG, "c2g_nci_rdg: null output");
   const size_t nout = (size_t)nstep[0] * nstep[1] * nstep[2];
   double *d_rho = nullptr, *d_grad = nullptr;
-  C2G_CUDA(ctx, cudaMalloc(&d_rho, sizeof(double) * nout));
-  C2G_CUDA(ctx, cudaMalloc(&d_grad, sizeof(double) * nout));
+  C2G_CUDA(ctx, c2g_alloc(ctx, (void**)&d_rho, sizeof(double) * nout));
+  C2G_CUDA(ctx, c2g_alloc(ctx, (void**)&d_grad, sizeof(double) * nout));
   rc = nci_launch(ctx, handle, x0, xmat, nstep, c2x, x2c, c2xl, nnuc, nuc_cart, d_rho, d_grad);
   cudaError_t e = cudaSuccess;
   if (rc == C2G_OK) {
@@ -331,8 +331,8 @@ extern "C" int c2g_nci_rdg(c2g_context* ctx, int handle, const double x0[3], con
     if (e == cudaSuccess) e = cudaMemcpyAsync(cgrad, d_grad, sizeof(double) * nout, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   }
-  cudaFree(d_rho);
-  cudaFree(d_grad);
+  c2g_release(ctx, d_rho);
+  c2g_release(ctx, d_grad);
   if (rc) return rc;
   if (e != cudaSuccess) return ctx->fail(C2G_ERR_CUDA, "c2g_nci_rdg: %s", cudaGetErrorString(e));
   return C2G_OK;

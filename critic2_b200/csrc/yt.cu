@@ -363,12 +363,6 @@ __global__ void k_init_w(long long nn, const int* __restrict__ label, const int*
   }
 }
 
-struct DevBuf {
-  void* p = nullptr;
-  ~DevBuf() { if (p) cudaFree(p); }
-  template <class T> T* as() { return (T*)p; }
-};
-
 template <class K>
 int coop_grid(c2g_context* ctx, K kernel, int threads, int* blocks) {
   int per_sm = 0;
@@ -388,12 +382,13 @@ struct YtState {
   int* lvl = nullptr;
   int nlevels = 0;
   int nias = 0;
+  c2g_context* ctx = nullptr;
   ~YtState() {
-    if (mask) cudaFree(mask);
-    if (csum) cudaFree(csum);
-    if (ias) cudaFree(ias);
-    if (order) cudaFree(order);
-    if (lvl) cudaFree(lvl);
+    c2g_release(ctx, mask);
+    c2g_release(ctx, csum);
+    c2g_release(ctx, ias);
+    c2g_release(ctx, order);
+    c2g_release(ctx, lvl);
   }
 };
 
@@ -427,6 +422,7 @@ extern "C" int c2g_yt_build(c2g_context* ctx, int handle, int nvec, const int* v
   res->zlo = 0; res->zhi = g.n[2];
   struct Guard { c2g_basins* r; bool ok = false; ~Guard() { if (!ok) c2g_basins_free(r); } } guard{res};
   YtState* S = new YtState();
+  S->ctx = ctx;
   res->yt = S;
   YtParams& P = S->P;
   P.n1 = g.n[0]; P.n2 = g.n[1]; P.n3 = g.n[2]; P.nvec = nvec;
@@ -441,19 +437,19 @@ extern "C" int c2g_yt_build(c2g_context* ctx, int handle, int nvec, const int* v
     if (P.opp[k] < 0) return ctx->fail(C2G_ERR_ARG, "c2g_yt_build: stencil is not centro-symmetric (vec %d has no opposite)", k + 1);
   }
 
-  C2G_CUDA(ctx, cudaMalloc(&res->d_label, sizeof(int) * nn));
-  C2G_CUDA(ctx, cudaMalloc(&S->mask, sizeof(unsigned) * nn));
-  C2G_CUDA(ctx, cudaMalloc(&S->csum, sizeof(double) * nn));
-  C2G_CUDA(ctx, cudaMalloc(&S->ias, ((size_t)nn + 3) / 4 * 4));
+  C2G_CUDA(ctx, c2g_alloc(ctx, (void**)&res->d_label, sizeof(int) * nn));
+  C2G_CUDA(ctx, c2g_alloc(ctx, (void**)&S->mask, sizeof(unsigned) * nn));
+  C2G_CUDA(ctx, c2g_alloc(ctx, (void**)&S->csum, sizeof(double) * nn));
+  C2G_CUDA(ctx, c2g_alloc(ctx, (void**)&S->ias, ((size_t)nn + 3) / 4 * 4));
   DevBuf b_up, b_ctl, b_maxl, b_queue, b_indeg;
-  C2G_CUDA(ctx, cudaMalloc(&b_up.p, sizeof(int) * nn));
-  C2G_CUDA(ctx, cudaMalloc(&b_ctl.p, 64));
+  C2G_CUDA(ctx, b_up.alloc(ctx, sizeof(int) * nn));
+  C2G_CUDA(ctx, b_ctl.alloc(ctx, 64));
   int maxcap = (int)std::min<long long>(nn, std::max<long long>(1 << 16, nn / 64));
   int* ctl = b_ctl.as<int>();
   int hctl[4];
   const int nb = c2g_blocks_for(nn, 256);
   for (int attempt = 0;; attempt++) {
-    C2G_CUDA(ctx, cudaMalloc(&b_maxl.p, sizeof(int) * (size_t)maxcap));
+    C2G_CUDA(ctx, b_maxl.alloc(ctx, sizeof(int) * (size_t)maxcap));
     C2G_CUDA(ctx, cudaMemsetAsync(ctl, 0, 64, st));
     ctx->prof_begin("yt_scan");
     k_scan<<<nb, 256, 0, st>>>(P, g.d, S->mask, S->csum, b_up.as<int>(), b_maxl.as<int>(), ctl, maxcap);
@@ -463,7 +459,7 @@ extern "C" int c2g_yt_build(c2g_context* ctx, int handle, int nvec, const int* v
     C2G_CUDA(ctx, cudaStreamSynchronize(st));
     if (hctl[0] <= maxcap) break;
     if (attempt > 0) return ctx->fail(C2G_ERR_OVERFLOW, "maxima list overflow");
-    cudaFree(b_maxl.p); b_maxl.p = nullptr;
+    b_maxl.reset();
     maxcap = hctl[0];
   }
   const int nmax = hctl[0];
@@ -474,7 +470,7 @@ extern "C" int c2g_yt_build(c2g_context* ctx, int handle, int nvec, const int* v
   std::vector<double> mr(nmax);
   {
     DevBuf b_r;
-    C2G_CUDA(ctx, cudaMalloc(&b_r.p, sizeof(double) * nmax));
+    C2G_CUDA(ctx, b_r.alloc(ctx, sizeof(double) * nmax));
     k_gather<<<c2g_blocks_for(nmax, 256), 256, 0, st>>>(nmax, b_maxl.as<int>(), g.d, b_r.as<double>());
     C2G_KERNEL_CHECK(ctx);
     C2G_CUDA(ctx, cudaMemcpyAsync(mr.data(), b_r.p, sizeof(double) * nmax, cudaMemcpyDeviceToHost, st));
@@ -495,8 +491,8 @@ extern "C" int c2g_yt_build(c2g_context* ctx, int handle, int nvec, const int* v
     hk[s] = res->max_lin[k]; hv[s] = k;
   }
   DevBuf b_hk, b_hv;
-  C2G_CUDA(ctx, cudaMalloc(&b_hk.p, sizeof(int) * hsize));
-  C2G_CUDA(ctx, cudaMalloc(&b_hv.p, sizeof(int) * hsize));
+  C2G_CUDA(ctx, b_hk.alloc(ctx, sizeof(int) * hsize));
+  C2G_CUDA(ctx, b_hv.alloc(ctx, sizeof(int) * hsize));
   C2G_CUDA(ctx, cudaMemcpyAsync(b_hk.p, hk.data(), sizeof(int) * hsize, cudaMemcpyHostToDevice, st));
   C2G_CUDA(ctx, cudaMemcpyAsync(b_hv.p, hv.data(), sizeof(int) * hsize, cudaMemcpyHostToDevice, st));
 
@@ -512,7 +508,7 @@ extern "C" int c2g_yt_build(c2g_context* ctx, int handle, int nvec, const int* v
     if (!hctl[2]) break;
   }
   // seeds + closure
-  C2G_CUDA(ctx, cudaMalloc(&b_queue.p, sizeof(int) * nn));
+  C2G_CUDA(ctx, b_queue.alloc(ctx, sizeof(int) * nn));
   C2G_CUDA(ctx, cudaMemsetAsync(S->ias, 0, ((size_t)nn + 3) / 4 * 4, st));
   C2G_CUDA(ctx, cudaMemsetAsync(ctl, 0, 64, st));
   ctx->prof_begin("yt_seed");
@@ -543,11 +539,11 @@ extern "C" int c2g_yt_build(c2g_context* ctx, int handle, int nvec, const int* v
   C2G_KERNEL_CHECK(ctx);
   // Kahn levels of the IAS graph
   const int maxlvl = 1 << 22;
-  C2G_CUDA(ctx, cudaMalloc(&S->order, sizeof(int) * std::max(nias, 1)));
-  C2G_CUDA(ctx, cudaMalloc(&S->lvl, sizeof(int) * (maxlvl + 1)));
+  C2G_CUDA(ctx, c2g_alloc(ctx, (void**)&S->order, sizeof(int) * std::max(nias, 1)));
+  C2G_CUDA(ctx, c2g_alloc(ctx, (void**)&S->lvl, sizeof(int) * (maxlvl + 1)));
   long long nrec = 0;
   if (nias > 0) {
-    C2G_CUDA(ctx, cudaMalloc(&b_indeg.p, ((size_t)nn + 3) / 4 * 4));
+    C2G_CUDA(ctx, b_indeg.alloc(ctx, ((size_t)nn + 3) / 4 * 4));
     C2G_CUDA(ctx, cudaMemsetAsync(b_indeg.p, 0, ((size_t)nn + 3) / 4 * 4, st));
     C2G_CUDA(ctx, cudaMemsetAsync(ctl, 0, 64, st));
     ctx->prof_begin("yt_indeg");
@@ -631,7 +627,7 @@ int c2g_yt_integrate_impl(c2g_context* ctx, c2g_basins* res, int nprop, const in
     const double* fp[4] = {nullptr, nullptr, nullptr, nullptr};
     for (int p = 0; p < npe; p++) fp[p] = ctx->grids[fieldhandles[k0 + p]].d;
     DevBuf b_y, b_sums;
-    C2G_CUDA(ctx, cudaMalloc(&b_y.p, sizeof(double) * (size_t)(npe + 1) * nn));
+    C2G_CUDA(ctx, b_y.alloc(ctx, sizeof(double) * (size_t)(npe + 1) * nn));
     int rc;
     switch (npe) {
       case 0: rc = yt_sweep_launch<0>(ctx, S, rho, fp, b_y.as<double>(), nn); break;
@@ -641,7 +637,7 @@ int c2g_yt_integrate_impl(c2g_context* ctx, c2g_basins* res, int nprop, const in
     }
     if (rc) return rc;
     // per-basin sums over interior points (label < 0 = IAS is skipped by the reduction)
-    C2G_CUDA(ctx, cudaMalloc(&b_sums.p, sizeof(double) * (size_t)(npe + 1) * nmax));
+    C2G_CUDA(ctx, b_sums.alloc(ctx, sizeof(double) * (size_t)(npe + 1) * nmax));
     C2G_CUDA(ctx, cudaMemsetAsync(b_sums.p, 0, sizeof(double) * (size_t)(npe + 1) * nmax, st));
     const double* yp[4] = {nullptr, nullptr, nullptr, nullptr};
     for (int p = 0; p <= npe; p++) yp[p] = b_y.as<double>() + (size_t)p * nn;
@@ -688,7 +684,7 @@ extern "C" int c2g_yt_weights(c2g_basins* res, int idb, double* w) {
   const double* rho = ctx->grids[res->gridh].d;
   cudaStream_t st = ctx->stream;
   DevBuf b_w;
-  C2G_CUDA(ctx, cudaMalloc(&b_w.p, sizeof(double) * nn));
+  C2G_CUDA(ctx, b_w.alloc(ctx, sizeof(double) * nn));
   ctx->prof_begin("yt_init_w");
   k_init_w<<<ctx->nsm * 8, 256, 0, st>>>(nn, res->d_label, res->d_map, idb, b_w.as<double>());
   ctx->prof_end();

@@ -1,0 +1,298 @@
+! critic2_gpu.f90 -- ISO_C_BINDING shim between critic2's Fortran host code and the CUDA library
+! libcritic2_gpu.so (C ABI: include/critic2_gpu.h).  It is meant to sit next to
+! src/c_interface_module.f90 / src/libcritic2.f90 in the critic2 tree and follows their conventions
+! (bind(c) interfaces, type(c_ptr) opaque handles, integer status codes turned into ferror calls).
+!
+! NOT COMPILED IN THIS REPOSITORY'S IMAGE (no Fortran compiler is available); the same entry points are
+! exercised from Python/ctypes in tests/ and from C++ in critic2_b200/csrc/host.  See INTEGRATION.md for
+! the four patch points in bader@proc.f90, yt@proc.f90, integration@proc.f90 and nci@proc.f90.
+module critic2_gpu
+  use iso_c_binding
+  implicit none
+  private
+
+  public :: gpu_enabled, gpu_init, gpu_end
+  public :: gpu_bader_integrate, gpu_yt_integrate, gpu_integrate_fields, gpu_nci_rdg
+
+  logical :: gpu_enabled = .false.        !< set by gpu_init (environment variable CRITIC2_GPU=1)
+  type(c_ptr) :: ctx = c_null_ptr         !< c2g_context
+  type(c_ptr) :: basins = c_null_ptr      !< c2g_basins of the last BADER/YT call (consumed by gpu_integrate_fields)
+  integer(c_int) :: hgrid = -1            !< resident copy of bas%f
+
+  interface
+     function c2g_init(device,ctx) bind(c,name="c2g_init")
+       import :: c_int, c_ptr
+       integer(c_int), value :: device
+       type(c_ptr) :: ctx
+       integer(c_int) :: c2g_init
+     end function c2g_init
+     subroutine c2g_finalize(ctx) bind(c,name="c2g_finalize")
+       import :: c_ptr
+       type(c_ptr), value :: ctx
+     end subroutine c2g_finalize
+     function c2g_last_error(ctx) bind(c,name="c2g_last_error")
+       import :: c_ptr
+       type(c_ptr), value :: ctx
+       type(c_ptr) :: c2g_last_error
+     end function c2g_last_error
+     function c2g_grid_upload(ctx,f,n,handle) bind(c,name="c2g_grid_upload")
+       import :: c_int, c_ptr, c_double
+       type(c_ptr), value :: ctx
+       real(c_double) :: f(*)
+       integer(c_int) :: n(3), handle
+       integer(c_int) :: c2g_grid_upload
+     end function c2g_grid_upload
+     function c2g_grid_free(ctx,handle) bind(c,name="c2g_grid_free")
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ctx
+       integer(c_int), value :: handle
+       integer(c_int) :: c2g_grid_free
+     end function c2g_grid_free
+     function c2g_bader_assign(ctx,handle,car2lat,lat_i_dist,algo,order,nmax,res) bind(c,name="c2g_bader_assign")
+       import :: c_int, c_ptr, c_double
+       type(c_ptr), value :: ctx
+       integer(c_int), value :: handle, algo, order
+       real(c_double) :: car2lat(3,3), lat_i_dist(27)
+       integer(c_int) :: nmax
+       type(c_ptr) :: res
+       integer(c_int) :: c2g_bader_assign
+     end function c2g_bader_assign
+     function c2g_yt_build(ctx,handle,nvec,vec,area,nmax,res) bind(c,name="c2g_yt_build")
+       import :: c_int, c_ptr, c_double
+       type(c_ptr), value :: ctx
+       integer(c_int), value :: handle, nvec
+       integer(c_int) :: vec(3,*)
+       real(c_double) :: area(*)
+       integer(c_int) :: nmax
+       type(c_ptr) :: res
+       integer(c_int) :: c2g_yt_build
+     end function c2g_yt_build
+     function c2g_basins_maxima(res,pmax) bind(c,name="c2g_basins_maxima")
+       import :: c_int, c_ptr
+       type(c_ptr), value :: res
+       integer(c_int) :: pmax(3,*)
+       integer(c_int) :: c2g_basins_maxima
+     end function c2g_basins_maxima
+     function c2g_basins_set_map(res,nattr,map) bind(c,name="c2g_basins_set_map")
+       import :: c_int, c_ptr
+       type(c_ptr), value :: res
+       integer(c_int), value :: nattr
+       integer(c_int) :: map(*)
+       integer(c_int) :: c2g_basins_set_map
+     end function c2g_basins_set_map
+     function c2g_basins_relabel(res,nattr0,assigned,nattr_new) bind(c,name="c2g_basins_relabel")
+       import :: c_int, c_ptr
+       type(c_ptr), value :: res
+       integer(c_int), value :: nattr0, nattr_new
+       integer(c_int) :: assigned(*)
+       integer(c_int) :: c2g_basins_relabel
+     end function c2g_basins_relabel
+     function c2g_basins_labels(res,idg) bind(c,name="c2g_basins_labels")
+       import :: c_int, c_ptr
+       type(c_ptr), value :: res
+       integer(c_int) :: idg(*)
+       integer(c_int) :: c2g_basins_labels
+     end function c2g_basins_labels
+     subroutine c2g_basins_free(res) bind(c,name="c2g_basins_free")
+       import :: c_ptr
+       type(c_ptr), value :: res
+     end subroutine c2g_basins_free
+     function c2g_integrate(ctx,res,nprop,fieldhandles,omega,psum,vol) bind(c,name="c2g_integrate")
+       import :: c_int, c_ptr, c_double
+       type(c_ptr), value :: ctx, res
+       integer(c_int), value :: nprop
+       integer(c_int) :: fieldhandles(*)
+       real(c_double), value :: omega
+       real(c_double) :: psum(*), vol(*)
+       integer(c_int) :: c2g_integrate
+     end function c2g_integrate
+     function c2g_nci_rdg(ctx,handle,x0,xmat,nstep,c2x,x2c,c2xl,nnuc,nuc,crho,cgrad) bind(c,name="c2g_nci_rdg")
+       import :: c_int, c_ptr, c_double
+       type(c_ptr), value :: ctx
+       integer(c_int), value :: handle, nnuc
+       real(c_double) :: x0(3), xmat(3,3), c2x(3,3), x2c(3,3), c2xl(3,3), nuc(3,*)
+       integer(c_int) :: nstep(3)
+       real(c_double) :: crho(*), cgrad(*)
+       integer(c_int) :: c2g_nci_rdg
+     end function c2g_nci_rdg
+  end interface
+
+contains
+
+  !> Turn a non-zero status into a fatal critic2 error (tools_io ferror).
+  subroutine check(ier,routine)
+    use tools_io, only: ferror, faterr
+    use c_interface_module, only: c_f_string_alloc
+    integer(c_int), intent(in) :: ier
+    character*(*), intent(in) :: routine
+    character(len=:), allocatable :: msg
+    if (ier /= 0) then
+       call c_f_string_alloc(c2g_last_error(ctx),msg)
+       call ferror(routine,"GPU: " // msg,faterr)
+    end if
+  end subroutine check
+
+  subroutine gpu_init()
+    character(len=8) :: val
+    integer :: stat
+    call get_environment_variable("CRITIC2_GPU",val,status=stat)
+    if (stat /= 0) return
+    if (trim(val) /= "1") return
+    call check(c2g_init(0_c_int,ctx),"gpu_init")
+    gpu_enabled = .true.
+  end subroutine gpu_init
+
+  subroutine gpu_end()
+    if (c_associated(basins)) call c2g_basins_free(basins)
+    if (c_associated(ctx)) call c2g_finalize(ctx)
+    basins = c_null_ptr
+    ctx = c_null_ptr
+    gpu_enabled = .false.
+  end subroutine gpu_end
+
+  !> Map the device's maxima to attractors with the host's own rules (atoms, known nnm, new nnm); this
+  !> is the per-maximum part of bader_integrate / yt_integrate that needs the crystal object.
+  subroutine identify_attractors(s,bas,nmax,pmax,vsmall_thr,map)
+    use systemmod, only: system
+    use types, only: basindat, realloc
+    use param, only: icrd_crys
+    type(system), intent(inout) :: s
+    type(basindat), intent(inout) :: bas
+    integer, intent(in) :: nmax
+    integer(c_int), intent(in) :: pmax(3,nmax)
+    real*8, intent(in) :: vsmall_thr
+    integer(c_int), intent(out) :: map(nmax)
+    integer :: i, l, nid
+    real*8 :: dv(3)
+
+    do i = 1, nmax
+       dv = real(pmax(:,i)-1,8) / real(bas%n,8)
+       map(i) = 0
+       if (bas%atexist) then
+          nid = s%c%identify_atom(dv,icrd_crys,distmax=bas%ratom)
+          if (nid > 0) map(i) = nid
+       end if
+       if (map(i) == 0 .and. bas%ratom > vsmall_thr) then
+          do l = 1, bas%nattr
+             if (s%c%are_lclose(dv,bas%xattr(:,l),bas%ratom)) then
+                map(i) = l
+                exit
+             end if
+          end do
+       end if
+       if (map(i) == 0) then
+          ! (a DISCARD expression would be evaluated here, exactly as in the CPU path)
+          bas%nattr = bas%nattr + 1
+          if (bas%nattr > size(bas%xattr,2)) call realloc(bas%xattr,3,2*bas%nattr)
+          bas%xattr(:,bas%nattr) = dv
+          map(i) = bas%nattr
+       end if
+    end do
+  end subroutine identify_attractors
+
+  !> GPU body of bader_integrate: replaces the scan + refine of src/bader@proc.f90:147-224.
+  !> lat2car, car2lat, lat_i_dist are the module variables computed at :124-145.
+  subroutine gpu_bader_integrate(s,bas,car2lat,lat_i_dist)
+    use systemmod, only: system
+    use types, only: basindat, realloc
+    use param, only: vsmall
+    type(system), intent(inout) :: s
+    type(basindat), intent(inout) :: bas
+    real*8, intent(in) :: car2lat(3,3), lat_i_dist(-1:1,-1:1,-1:1)
+    integer(c_int) :: nmax, n(3)
+    integer(c_int), allocatable :: pmax(:,:), map(:)
+    real(c_double) :: lid(27)
+    integer :: i, j, k
+
+    n = int(bas%n,c_int)
+    ! flatten lat_i_dist as (d1+1)*9+(d2+1)*3+(d3+1)
+    do i = -1, 1
+       do j = -1, 1
+          do k = -1, 1
+             lid((i+1)*9+(j+1)*3+(k+1)+1) = lat_i_dist(i,j,k)
+          end do
+       end do
+    end do
+    if (hgrid >= 0) call check(c2g_grid_free(ctx,hgrid),"gpu_bader_integrate")
+    call check(c2g_grid_upload(ctx,bas%f,n,hgrid),"gpu_bader_integrate")
+    if (c_associated(basins)) call c2g_basins_free(basins)
+    call check(c2g_bader_assign(ctx,hgrid,car2lat,lid,0_c_int,1_c_int,nmax,basins),"gpu_bader_integrate")
+    allocate(pmax(3,nmax),map(nmax))
+    call check(c2g_basins_maxima(basins,pmax),"gpu_bader_integrate")
+    call identify_attractors(s,bas,int(nmax),pmax,vsmall,map)
+    call check(c2g_basins_set_map(basins,int(bas%nattr,c_int),map),"gpu_bader_integrate")
+    if (allocated(bas%idg)) deallocate(bas%idg)
+    allocate(bas%idg(bas%n(1),bas%n(2),bas%n(3)))
+    call check(c2g_basins_labels(basins,bas%idg),"gpu_bader_integrate")
+    call realloc(bas%xattr,3,bas%nattr)
+  end subroutine gpu_bader_integrate
+
+  !> GPU body of yt_integrate (src/yt@proc.f90:77-211).  The ytdata scratch file is not written: the
+  !> weights stay on the device and gpu_integrate_fields uses them; bas%luw is left at 0.
+  subroutine gpu_yt_integrate(s,bas)
+    use systemmod, only: system
+    use types, only: basindat, realloc
+    use param, only: vsmall
+    type(system), intent(inout) :: s
+    type(basindat), intent(inout) :: bas
+    integer(c_int) :: nmax, n(3), nvec
+    integer(c_int), allocatable :: pmax(:,:), map(:)
+
+    n = int(bas%n,c_int)
+    nvec = int(s%f(s%iref)%grid%nvec,c_int)
+    if (hgrid >= 0) call check(c2g_grid_free(ctx,hgrid),"gpu_yt_integrate")
+    call check(c2g_grid_upload(ctx,bas%f,n,hgrid),"gpu_yt_integrate")
+    if (c_associated(basins)) call c2g_basins_free(basins)
+    call check(c2g_yt_build(ctx,hgrid,nvec,s%f(s%iref)%grid%vec,s%f(s%iref)%grid%area,nmax,basins),"gpu_yt_integrate")
+    allocate(pmax(3,nmax),map(nmax))
+    call check(c2g_basins_maxima(basins,pmax),"gpu_yt_integrate")
+    call identify_attractors(s,bas,int(nmax),pmax,vsmall,map)
+    call check(c2g_basins_set_map(basins,int(bas%nattr,c_int),map),"gpu_yt_integrate")
+    if (allocated(bas%idg)) deallocate(bas%idg)
+    allocate(bas%idg(bas%n(1),bas%n(2),bas%n(3)))
+    call check(c2g_basins_labels(basins,bas%idg),"gpu_yt_integrate")   ! spatial ids, 0 = IAS point
+    call realloc(bas%xattr,3,bas%nattr)
+  end subroutine gpu_yt_integrate
+
+  !> GPU body of the two per-attractor loops of intgrid_fields (src/integration@proc.f90:1205-1219 and
+  !> :1288-1301).  fint holds the nprop integrand grids already built by the host code (:1235-1280).
+  subroutine gpu_integrate_fields(bas,nprop,fint,omega,psum,vol,assigned,nattr_new)
+    use types, only: basindat
+    type(basindat), intent(in) :: bas
+    integer, intent(in) :: nprop
+    real*8, intent(in) :: fint(:,:,:,:)
+    real*8, intent(in) :: omega
+    real*8, intent(out) :: psum(:,:), vol(:)
+    integer, intent(in), optional :: assigned(:), nattr_new
+    integer(c_int) :: h(nprop), n(3)
+    integer :: k
+
+    n = int(bas%n,c_int)
+    if (present(assigned)) then   ! relabelling decided by int_reorder_gridout (:1069-1110)
+       call check(c2g_basins_relabel(basins,int(size(assigned),c_int),int(assigned,c_int),int(nattr_new,c_int)),&
+          "gpu_integrate_fields")
+    end if
+    do k = 1, nprop
+       call check(c2g_grid_upload(ctx,fint(:,:,:,k),n,h(k)),"gpu_integrate_fields")
+    end do
+    call check(c2g_integrate(ctx,basins,int(nprop,c_int),h,omega,psum,vol),"gpu_integrate_fields")
+    do k = 1, nprop
+       call check(c2g_grid_free(ctx,h(k)),"gpu_integrate_fields")
+    end do
+  end subroutine gpu_integrate_fields
+
+  !> GPU body of the nciplot loop (src/nci@proc.f90:540-606), grid interpolation mode, no fragments.
+  subroutine gpu_nci_rdg(f,x0,xmat,nstep,m_c2x,m_x2c,c2xl,nuc,crho,cgrad)
+    real*8, intent(in) :: f(:,:,:), x0(3), xmat(3,3), m_c2x(3,3), m_x2c(3,3), c2xl(3,3), nuc(:,:)
+    integer, intent(in) :: nstep(3)
+    real*8, intent(out) :: crho(0:,0:,0:), cgrad(0:,0:,0:)
+    integer(c_int) :: h, n(3)
+
+    n = int(shape(f),c_int)
+    call check(c2g_grid_upload(ctx,f,n,h),"gpu_nci_rdg")
+    call check(c2g_nci_rdg(ctx,h,x0,xmat,int(nstep,c_int),m_c2x,m_x2c,c2xl,int(size(nuc,2),c_int),nuc,crho,cgrad),&
+       "gpu_nci_rdg")
+    call check(c2g_grid_free(ctx,h),"gpu_nci_rdg")
+  end subroutine gpu_nci_rdg
+
+end module critic2_gpu
