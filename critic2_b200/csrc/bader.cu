@@ -32,6 +32,12 @@ constexpr int PATHCAP = 640;            // per-thread path buffer (local memory)
 constexpr unsigned FILLBIT = 0x80000000u;
 constexpr int LMASK = 0x7fffffff;
 
+__device__ __forceinline__ int wrapx(int p, int n) {
+  if (p < 0) p += n;
+  if (p >= n) p -= n;
+  if (p < 0 || p >= n) p = ((p % n) + n) % n;  // grids narrower than a tile
+  return p;
+}
 __device__ __forceinline__ int wrapc(int p, int n) {
   while (p < 0) p += n;
   while (p >= n) p -= n;
@@ -119,6 +125,15 @@ __device__ __noinline__ bool dev_on_path(const int* path, int len, int nid) {
   return false;
 }
 
+// Early-termination map (FAST algorithm only): safe[c] >= 0 means the stride-2^shift cube c and its 26
+// neighbouring cubes are uniformly labelled with the terminal maximum safe[c] and hold no maximum of
+// their own -- the analogue of the reference's known==2 "interior" points at which max_neargrid stops
+// (bader@proc.f90:447), with a wider margin.  Covers the owned cube layers only.
+struct SafeMap {
+  const int* safe;  // nullptr = disabled
+  int shift, c1, c2, zlo, nzl;
+};
+
 // One complete near-grid trajectory (max_neargrid, bader@proc.f90:427-450 on a fresh grid).
 // Returns the linear id of the terminal maximum, or -1 if the path buffer overflowed.
 // The reference's "known(pm)==1" revisit test (:484-488) is answered exactly: a visited point
@@ -126,8 +141,9 @@ __device__ __noinline__ bool dev_on_path(const int* path, int len, int nid) {
 // searched.  ORTHO: car2lat is diagonal (orthogonal cell); the skipped products are exact zeros,
 // so the result is bit-identical to the general expression.
 template <bool ORTHO>
-__device__ __forceinline__ int dev_walk(const BaderParams& P, const double* __restrict__ rho, const MaxHash& h, int start,
-                                        int* path, int cap, unsigned long long* nsteps_out) {
+__device__ __forceinline__ int dev_walk(const BaderParams& P, const double* __restrict__ rho, const MaxHash& h,
+                                        const SafeMap& sm, int start, int* path, int cap,
+                                        unsigned long long* nsteps_out) {
   const int n1 = P.n1, n2 = P.n2, n3 = P.n3;
   const int s2 = n1, s3 = n1 * n2;
   const int wxp = 1 - n1, wxm = n1 - 1, wyp = s2 - s3, wym = s3 - s2, wzp = s3 - s3 * n3, wzm = s3 * n3 - s3;
@@ -200,6 +216,13 @@ __device__ __forceinline__ int dev_walk(const BaderParams& P, const double* __re
     id = nid;
     r0 = rn;
     x = nx; y = ny; z = nz;
+    if (sm.safe) {  // quit at a known interior point (:447)
+      const int cz = nz - sm.zlo;
+      if (cz >= 0 && cz < sm.nzl) {
+        const int sl = __ldg(sm.safe + (nx >> sm.shift) + sm.c1 * ((ny >> sm.shift) + sm.c2 * (cz >> sm.shift)));
+        if (sl >= 0) { id = sl; break; }
+      }
+    }
   }
   if (nsteps_out) atomicAdd(nsteps_out, (unsigned long long)len);
   return id;
@@ -230,18 +253,23 @@ __global__ void __launch_bounds__(256) k_maxima(const __grid_constant__ BaderPar
   const int bx0 = blockIdx.x * TX, by0 = blockIdx.y * TY, bz0 = S.zlo + blockIdx.z * TZ;
   const int tid = threadIdx.x;
   constexpr int SX = TX + 2, SY = TY + 2, SZ = TZ + 2;
-  for (int e = tid; e < SX * SY * SZ; e += 256) {
-    const int sx = e % SX, sy = (e / SX) % SY, sz = e / (SX * SY);
-    const int gx = wrapc(bx0 + sx - 1, n1), gy = wrapc(by0 + sy - 1, n2), gz = wrapc(bz0 + sz - 1, n3);
-    s0[e] = __ldg(rho + gx + n1 * (gy + n2 * gz));
+  {  // row-wise staging: one warp per (y,z) row of 34 values, then the 3-point maximum along x
+    const int lane = tid & 31, wid = tid >> 5;
+    const int gx0 = wrapx(bx0 - 1 + lane, n1), gx1 = wrapx(bx0 - 1 + 32 + (lane & 1), n1);
+    for (int r = wid; r < SY * SZ; r += 8) {
+      const int sy = r % SY, sz = r / SY;
+      const int gy = wrapx(by0 + sy - 1, n2), gz = wrapx(bz0 + sz - 1, n3);
+      const double* row = rho + (size_t)n1 * (gy + (size_t)n2 * gz);
+      s0[r * SX + lane] = __ldg(row + gx0);
+      if (lane < 2) s0[r * SX + 32 + lane] = __ldg(row + gx1);
+    }
+    __syncthreads();
+    for (int r = wid; r < SY * SZ; r += 8) {
+      const double* p = s0 + r * SX + lane;
+      s1[r * TX + lane] = fmax(p[0], fmax(p[1], p[2]));
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  for (int e = tid; e < TX * SY * SZ; e += 256) {
-    const int sx = e % TX, r = e / TX;  // r = sy + SY*sz
-    const double* p = s0 + r * SX + sx;
-    s1[e] = fmax(p[0], fmax(p[1], p[2]));
-  }
-  __syncthreads();
   const int lx = tid % TX, ly = tid / TX;
   const int gx = bx0 + lx, gy = by0 + ly;
   double m[SZ];
@@ -299,21 +327,22 @@ __global__ void __launch_bounds__(128) k_walk_lattice(const __grid_constant__ Ba
   const int lx = (int)(t % m1), ly = (int)((t / m1) % m2), lz = (int)(t / ((long long)m1 * m2));
   const int start = lx * s + P.n1 * (ly * s + P.n2 * (S.zlo + lz * s));
   int path[PATHCAP];
-  const int term = dev_walk<ORTHO>(P, rho, h, start, path, PATHCAP, nsteps);
+  const SafeMap nosafe{nullptr, 0, 0, 0, 0, 0};
+  const int term = dev_walk<ORTHO>(P, rho, h, nosafe, start, path, PATHCAP, nsteps);
   finish_walk(start, term, label, h, reached, overflow, noverflow, err);
 }
 
 template <bool ORTHO>
 __global__ void __launch_bounds__(128) k_walk_list(const __grid_constant__ BaderParams P, const double* __restrict__ rho,
                                                    const int* __restrict__ list, int count, int* __restrict__ label,
-                                                   MaxHash h, unsigned char* __restrict__ reached,
+                                                   MaxHash h, SafeMap sm, unsigned char* __restrict__ reached,
                                                    int* __restrict__ overflow, int* __restrict__ noverflow,
                                                    int* __restrict__ err, unsigned long long* nsteps) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= count) return;
   const int start = list[t];
   int path[PATHCAP];
-  const int term = dev_walk<ORTHO>(P, rho, h, start, path, PATHCAP, nsteps);
+  const int term = dev_walk<ORTHO>(P, rho, h, sm, start, path, PATHCAP, nsteps);
   finish_walk(start, term, label, h, reached, overflow, noverflow, err);
 }
 
@@ -325,7 +354,8 @@ __global__ void __launch_bounds__(64) k_walk_big(const __grid_constant__ BaderPa
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= count) return;
   const int start = list[t];
-  const int term = dev_walk<false>(P, rho, h, start, scratch + (size_t)t * bigcap, bigcap, nsteps);
+  const SafeMap nosafe{nullptr, 0, 0, 0, 0, 0};
+  const int term = dev_walk<false>(P, rho, h, nosafe, start, scratch + (size_t)t * bigcap, bigcap, nsteps);
   if (term < 0) { atomicExch(err, 2); return; }
   label[start] = term;
   const int ci = hash_lookup(h, term);
@@ -339,7 +369,7 @@ __global__ void __launch_bounds__(64) k_walk_big(const __grid_constant__ BaderPa
 // points (label | FILLBIT); otherwise queue them.  lbuf = label buffer including halos.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_classify(int n1, int n2, int n3, const Slab S, int s, int* __restrict__ lbuf,
-                                                  const unsigned char* __restrict__ cubemax,
+                                                  const unsigned char* __restrict__ cubemax, int* __restrict__ cubeuni,
                                                   int* __restrict__ list, int* __restrict__ nlist) {
   const int c1 = (n1 + s - 1) / s, c2 = (n2 + s - 1) / s, c3 = (S.nzl + s - 1) / s;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -362,6 +392,7 @@ __global__ void __launch_bounds__(256) k_classify(int n1, int n2, int n3, const 
     uni = uni && ((lbuf[x1 + n1 * y0 + s3 * p1] & LMASK) == l000);
     uni = uni && ((lbuf[x0 + n1 * y1 + s3 * p1] & LMASK) == l000);
     uni = uni && ((lbuf[x1 + n1 * y1 + s3 * p1] & LMASK) == l000);
+    cubeuni[t] = uni ? l000 : -1;
     const int hh = s >> 1;
     for (int o = 1; o < 8; o++) {
       const int x = x0 + ((o & 1) ? hh : 0), y = y0 + ((o & 2) ? hh : 0), z = z0 + ((o & 4) ? hh : 0);
@@ -393,28 +424,64 @@ __global__ void __launch_bounds__(256) k_classify(int n1, int n2, int n3, const 
   }
 }
 
+// safe[c] = cubeuni[c] if the 26 neighbouring cubes (periodic in x,y; owned layers only in z) carry the
+// same uniform label, else -1
+__global__ void __launch_bounds__(256) k_safe(int c1, int c2, int c3, const int* __restrict__ cubeuni, int* __restrict__ safe) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)c1 * c2 * c3) return;
+  const int v = cubeuni[t];
+  int out = v;
+  if (v >= 0) {
+    const int cx = (int)(t % c1), cy = (int)((t / c1) % c2), cz = (int)(t / ((long long)c1 * c2));
+    for (int dz = -1; dz <= 1 && out >= 0; dz++) {
+      const int zz = cz + dz;
+      if (zz < 0 || zz >= c3) { out = -1; break; }
+      for (int dy = -1; dy <= 1 && out >= 0; dy++) {
+        const int yy = (cy + dy + c2) % c2;
+        for (int dx = -1; dx <= 1; dx++) {
+          const int xx = (cx + dx + c1) % c1;
+          if (cubeuni[xx + c1 * (yy + (size_t)c2 * zz)] != v) { out = -1; break; }
+        }
+      }
+    }
+  }
+  safe[t] = out;
+}
+
 // ------------------------------------------------------------------------------------------------
 // edge fix: every FILLED owned point with a 26-neighbour of a different label is queued for an exact
 // walk (the refine_edge criterion, is_vol_edge bader@proc.f90:730-752).  Reads both halo planes.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_edgefix(int n1, int n2, const Slab S, int* __restrict__ lbuf,
-                                                 int* __restrict__ list, int* __restrict__ nlist) {
+                                                 int* __restrict__ list, int* __restrict__ nlist,
+                                                 const unsigned char* __restrict__ dirty_in, unsigned char* __restrict__ dirty_out) {
+  const int tile = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  if (dirty_in && !dirty_in[tile]) return;  // nothing changed near this tile in the previous pass
   __shared__ int sl[(TZ + 2) * (TY + 2) * (TX + 2)];
   constexpr int SX = TX + 2, SY = TY + 2, SZ = TZ + 2;
   const int bx0 = blockIdx.x * TX, by0 = blockIdx.y * TY, lz0 = blockIdx.z * TZ;  // lz0: first owned plane (0-based)
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int s3 = n1 * n2;
-  int first = 0;
+  // row-wise staging: one warp per (y,z) row of 34 labels
+  const int gx0 = wrapx(bx0 - 1 + lane, n1);
+  const int gx1 = wrapx(bx0 - 1 + 32 + (lane & 1), n1);
+  int first = -1;
   bool uniform = true;
-  for (int e = tid; e < SX * SY * SZ; e += 256) {
-    const int sx = e % SX, sy = (e / SX) % SY, sz = e / (SX * SY);
-    const int gx = wrapc(bx0 + sx - 1, n1), gy = wrapc(by0 + sy - 1, n2);
-    int pl = lz0 + sz;  // local plane incl. halo offset: owned plane lz0+sz-1 -> buffer plane lz0+sz
+  for (int r = wid; r < SY * SZ; r += 8) {
+    const int sy = r % SY, sz = r / SY;
+    const int gy = wrapx(by0 + sy - 1, n2);
+    int pl = lz0 + sz;  // buffer plane (halo offset included)
     if (pl > S.nzl + 1) pl = S.nzl + 1;
-    const int v = lbuf[gx + n1 * gy + s3 * pl];
-    sl[e] = v;
-    if (e == tid) first = v & LMASK;
-    else uniform = uniform && ((v & LMASK) == first);
+    const int* row = lbuf + (size_t)s3 * pl + (size_t)n1 * gy;
+    const int v = row[gx0];
+    sl[r * SX + lane] = v;
+    if (first < 0) first = v & LMASK;
+    uniform = uniform && ((v & LMASK) == first);
+    if (lane < 2) {
+      const int v2 = row[gx1];
+      sl[r * SX + 32 + lane] = v2;
+      uniform = uniform && ((v2 & LMASK) == first);
+    }
   }
   __syncthreads();
   uniform = uniform && (first == (sl[0] & LMASK));
@@ -438,6 +505,21 @@ __global__ void __launch_bounds__(256) k_edgefix(int n1, int n2, const Slab S, i
     if (edge) {
       lbuf[gx + n1 * gy + s3 * (lz0 + lz + 1)] = cl;  // clear FILLBIT: walked from now on
       list[atomicAdd(nlist, 1)] = gx + n1 * (gy + n2 * (S.zlo + lz0 + lz));
+      // the next pass only has to look at tiles within one cell of a re-walked point
+      const int x0 = (lx == 0) ? -1 : 0, x1 = (lx == TX - 1 || gx == n1 - 1) ? 1 : 0;
+      const int y0 = (ly == 0) ? -1 : 0, y1 = (ly == TY - 1 || gy == n2 - 1) ? 1 : 0;
+      const int z0 = (lz == 0) ? -1 : 0, z1 = (lz == TZ - 1 || lz0 + lz == S.nzl - 1) ? 1 : 0;
+      for (int dz = z0; dz <= z1; dz++) {
+        const int tz = (int)blockIdx.z + dz;
+        if (tz < 0 || tz >= (int)gridDim.z) continue;  // other rank / periodic image: those layers are always rechecked
+        for (int dy = y0; dy <= y1; dy++) {
+          const int ty = ((int)blockIdx.y + dy + gridDim.y) % gridDim.y;
+          for (int dx = x0; dx <= x1; dx++) {
+            const int tx = ((int)blockIdx.x + dx + gridDim.x) % gridDim.x;
+            dirty_out[tx + gridDim.x * (ty + gridDim.y * tz)] = 1;
+          }
+        }
+      }
     }
   }
 }
@@ -716,17 +798,18 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
     }
     return C2G_OK;
   };
+  SafeMap cursafe{nullptr, 0, 0, 0, 0, 0};
   auto walk_list = [&](int count, const char* name) -> int {
     if (count <= 0) return C2G_OK;
     int rc = grow_over(count);
     if (rc) return rc;
     ctx->prof_begin(name);
     if (ortho)
-      k_walk_list<true><<<c2g_blocks_for(count, 128), 128, 0, st>>>(P, g.d, list, count, label_g, h, reached, over, cnt + 2, cnt + 3,
-                                                                    algo == C2G_BADER_EXACT ? nsteps : nullptr);
+      k_walk_list<true><<<c2g_blocks_for(count, 128), 128, 0, st>>>(P, g.d, list, count, label_g, h, cursafe, reached, over, cnt + 2,
+                                                                    cnt + 3, algo == C2G_BADER_EXACT ? nsteps : nullptr);
     else
-      k_walk_list<false><<<c2g_blocks_for(count, 128), 128, 0, st>>>(P, g.d, list, count, label_g, h, reached, over, cnt + 2, cnt + 3,
-                                                                     algo == C2G_BADER_EXACT ? nsteps : nullptr);
+      k_walk_list<false><<<c2g_blocks_for(count, 128), 128, 0, st>>>(P, g.d, list, count, label_g, h, cursafe, reached, over, cnt + 2,
+                                                                     cnt + 3, algo == C2G_BADER_EXACT ? nsteps : nullptr);
     ctx->prof_end();
     C2G_KERNEL_CHECK(ctx);
     walked += count;
@@ -758,31 +841,55 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
     // level 0: stride-4 lattice
     if ((rc = walk_lattice(4, "bader_walk_l4")) != C2G_OK) return rc;
     // levels 4 -> 2 -> 1
+    DevBuf b_uni(ctx), b_safe(ctx);
+    const bool use_safe = getenv("C2G_NO_EARLY_STOP") == nullptr;
     for (int s = 4; s >= 2; s >>= 1) {
       if ((rc = exchange_halos(ctx, lbuf, plane, S, 1)) != C2G_OK) return rc;
       const int c1 = (n1 + s - 1) / s, c2 = (n2 + s - 1) / s, c3 = (S.nzl + s - 1) / s;
       const long long nc = (long long)c1 * c2 * c3;
       C2G_CUDA(ctx, cudaMemsetAsync(cnt + 1, 0, sizeof(int), st));
+      cursafe.safe = nullptr;
       if (nc > 0) {
+        C2G_CUDA(ctx, b_uni.alloc(ctx, sizeof(int) * (size_t)nc));
+        C2G_CUDA(ctx, b_safe.alloc(ctx, sizeof(int) * (size_t)nc));
         ctx->prof_begin(s == 4 ? "bader_classify4" : "bader_classify2");
         k_classify<<<c2g_blocks_for(nc, 256), 256, 0, st>>>(n1, n2, n3, S, s, lbuf,
                                                             s == 4 ? b_cube4.as<unsigned char>() : b_cube2.as<unsigned char>(),
-                                                            list, cnt + 1);
+                                                            b_uni.as<int>(), list, cnt + 1);
         ctx->prof_end();
         C2G_KERNEL_CHECK(ctx);
+        if (use_safe) {
+          ctx->prof_begin(s == 4 ? "bader_safe4" : "bader_safe2");
+          k_safe<<<c2g_blocks_for(nc, 256), 256, 0, st>>>(c1, c2, c3, b_uni.as<int>(), b_safe.as<int>());
+          ctx->prof_end();
+          C2G_KERNEL_CHECK(ctx);
+          cursafe = SafeMap{b_safe.as<int>(), s == 4 ? 2 : 1, c1, c2, S.zlo, S.nzl};
+        }
       }
       C2G_CUDA(ctx, cudaMemcpyAsync(hcnt, cnt, 32, cudaMemcpyDeviceToHost, st));
       C2G_CUDA(ctx, cudaStreamSynchronize(st));
       if ((rc = walk_list(hcnt[1], s == 4 ? "bader_walk_l2" : "bader_walk_l1")) != C2G_OK) return rc;
     }
-    // edge fix until no filled point (on any rank) is adjacent to a different label
+    // edge fix until no filled point (on any rank) is adjacent to a different label.  After the first
+    // pass only the tiles within one cell of a re-walked point (plus the slab's face layers, whose
+    // halos may have changed on another rank) are looked at again.
+    DevBuf b_dirty[2] = {DevBuf(ctx), DevBuf(ctx)};
+    const dim3 egrid((n1 + TX - 1) / TX, (n2 + TY - 1) / TY, std::max(1, (S.nzl + TZ - 1) / TZ));
+    const size_t ntiles = (size_t)egrid.x * egrid.y * egrid.z;
+    C2G_CUDA(ctx, b_dirty[0].alloc(ctx, ntiles));
+    C2G_CUDA(ctx, b_dirty[1].alloc(ctx, ntiles));
     for (;;) {
       if ((rc = exchange_halos(ctx, lbuf, plane, S, 3)) != C2G_OK) return rc;
       C2G_CUDA(ctx, cudaMemsetAsync(cnt + 1, 0, sizeof(int), st));
+      unsigned char* din = fixpasses == 0 ? nullptr : b_dirty[fixpasses & 1].as<unsigned char>();
+      unsigned char* dout = b_dirty[(fixpasses + 1) & 1].as<unsigned char>();
+      C2G_CUDA(ctx, cudaMemsetAsync(dout, 0, ntiles, st));
+      // face layers are always rechecked
+      C2G_CUDA(ctx, cudaMemsetAsync(dout, 1, (size_t)egrid.x * egrid.y, st));
+      C2G_CUDA(ctx, cudaMemsetAsync(dout + (size_t)egrid.x * egrid.y * (egrid.z - 1), 1, (size_t)egrid.x * egrid.y, st));
       if (S.nzl > 0) {
-        dim3 grid((n1 + TX - 1) / TX, (n2 + TY - 1) / TY, (S.nzl + TZ - 1) / TZ);
         ctx->prof_begin("bader_edgefix");
-        k_edgefix<<<grid, 256, 0, st>>>(n1, n2, S, lbuf, list, cnt + 1);
+        k_edgefix<<<egrid, 256, 0, st>>>(n1, n2, S, lbuf, list, cnt + 1, din, dout);
         ctx->prof_end();
         C2G_KERNEL_CHECK(ctx);
       }
