@@ -8,12 +8,17 @@
 //     step_ongrid    :500-527                   is_max        :571-597
 // This file computes exactly that labelling:
 //   C2G_BADER_EXACT  every point walks its complete trajectory (the on-device referee);
-//   C2G_BADER_FAST   hierarchical: points of the stride-4 lattice walk; a stride-s cube whose 8
-//                    corners agree and that contains no local maximum is filled, the other points
-//                    walk; finally every filled point that has a 26-neighbour with a different
-//                    label walks too, until none is left -- the same fixed-point condition the
-//                    reference's refine_edge enforces (:300-422: every edge point carries the
-//                    label of its own trajectory).
+//   C2G_BADER_FAST   hierarchical.  The points of a stride-L0 lattice (L0 <= 32) walk.  Then, level by
+//                    level (s = L0 .. 2): a stride-s cube whose 8 corners agree and that holds no local
+//                    maximum is "uniform" and its stride-s/2 points are filled with the corner label;
+//                    the stride-s/2 points of the other cubes walk, and a walk stops as soon as it
+//                    enters a cube that is uniform together with its 26 neighbour cubes -- the analogue
+//                    of the reference's known==2 interior points at which max_neargrid stops (:447).
+//                    Finally every filled point that has a 26-neighbour with a different label walks
+//                    too, until none is left: the fixed point refine_edge enforces (:300-422, every
+//                    edge point carries the label of its own trajectory).
+// Labels are indices into the sorted list of candidate maxima; bit 31 (FILLBIT) marks points that were
+// filled, not walked (consumers mask it).
 // Arithmetic: IEEE fp64, evaluation order of the Fortran source, NO fused multiply-add (this
 // translation unit is compiled with -fmad=false; the reference is built -O3 without -march/-ffast-math).
 #include "common.cuh"
@@ -28,19 +33,16 @@ struct BaderParams {
   double lid[27];  // lat_i_dist, (d1+1)*9+(d2+1)*3+(d3+1)
 };
 
-constexpr int PATHCAP = 640;            // per-thread path buffer (local memory) of the fast walker
+constexpr int PATHCAP = 640;            // per-thread path buffer (local memory) of the walkers
 constexpr unsigned FILLBIT = 0x80000000u;
 constexpr int LMASK = 0x7fffffff;
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int MAXLEV = 5;               // cube strides 2,4,8,16,32
 
 __device__ __forceinline__ int wrapx(int p, int n) {
   if (p < 0) p += n;
   if (p >= n) p -= n;
   if (p < 0 || p >= n) p = ((p % n) + n) % n;  // grids narrower than a tile
-  return p;
-}
-__device__ __forceinline__ int wrapc(int p, int n) {
-  while (p < 0) p += n;
-  while (p >= n) p -= n;
   return p;
 }
 
@@ -71,20 +73,21 @@ __device__ __forceinline__ int wrap2(int p, int n) {
 // Fortran nint (half away from zero) for |v| < 1.5, as a double
 __device__ __forceinline__ double nint_small(double v) { return v >= 0.5 ? 1.0 : (v <= -0.5 ? -1.0 : 0.0); }
 
-// is_max, bader@proc.f90:571-597 (no neighbour strictly greater)
-__device__ __noinline__ bool dev_is_max(const BaderParams& P, const double* __restrict__ rho, int x, int y, int z, double r0) {
+// is_max, bader@proc.f90:571-597 (no neighbour strictly greater); general periodic wrap
+__device__ __noinline__ bool dev_is_max(int n1, int n2, int n3, const double* __restrict__ rho, int x, int y, int z) {
+  const double r0 = __ldg(rho + x + (size_t)n1 * (y + (size_t)n2 * z));
   bool ismax = true;
 #pragma unroll 1
   for (int d3 = -1; d3 <= 1; d3++) {
-    const int zz = wrap2(z + d3, P.n3);
+    const int zz = wrapx(z + d3, n3);
 #pragma unroll 1
     for (int d2 = -1; d2 <= 1; d2++) {
-      const int yy = wrap2(y + d2, P.n2);
-      const int base = P.n1 * (yy + P.n2 * zz);
+      const int yy = wrapx(y + d2, n2);
+      const double* row = rho + (size_t)n1 * (yy + (size_t)n2 * zz);
 #pragma unroll
       for (int d1 = -1; d1 <= 1; d1++) {
-        const int xx = wrap2(x + d1, P.n1);
-        if (__ldg(rho + base + xx) > r0) ismax = false;
+        const int xx = wrapx(x + d1, n1);
+        if (__ldg(row + xx) > r0) ismax = false;
       }
     }
   }
@@ -125,398 +128,400 @@ __device__ __noinline__ bool dev_on_path(const int* path, int len, int nid) {
   return false;
 }
 
-// Early-termination map (FAST algorithm only): safe[c] >= 0 means the stride-2^shift cube c and its 26
-// neighbouring cubes are uniformly labelled with the terminal maximum safe[c] and hold no maximum of
-// their own -- the analogue of the reference's known==2 "interior" points at which max_neargrid stops
-// (bader@proc.f90:447), with a wider margin.  Covers the owned cube layers only.
+// Early-termination map (FAST algorithm only), the analogue of the reference's known==2 interior points.
+//   octet = 0: safe[c] >= 0 means the stride-2^shift cube c and its 26 neighbouring cubes are uniformly
+//              labelled safe[c] and hold no maximum (every point of c has a uniform 5x5x5 neighbourhood);
+//   octet = 1: safe[v] >= 0 means the 8 cubes that meet at cube-grid vertex v are uniformly labelled and hold
+//              no maximum; a point q is looked up at its nearest vertex v = (q + 2^(shift-1)) >> shift, whose
+//              8 cubes contain the whole 3x3x3 neighbourhood of q.
+// Covers the owned cube layers only.
 struct SafeMap {
   const int* safe;  // nullptr = disabled
-  int shift, c1, c2, zlo, nzl;
+  int shift, c1, c2, c3, zlo, nzl, octet, wrapz;
 };
 
-// One complete near-grid trajectory (max_neargrid, bader@proc.f90:427-450 on a fresh grid).
-// Returns the linear id of the terminal maximum, or -1 if the path buffer overflowed.
-// The reference's "known(pm)==1" revisit test (:484-488) is answered exactly: a visited point
-// can only be hit again when rho(pm) <= max rho along the path, and only then the stored path is
-// searched.  ORTHO: car2lat is diagonal (orthogonal cell); the skipped products are exact zeros,
-// so the result is bit-identical to the general expression.
+// ------------------------------------------------------------------------------------------------
+// one near-grid step (step_neargrid, bader@proc.f90:455-494) of a trajectory held in WState.
+// The reference's "known(pm)==1" revisit test (:484-488) is answered exactly: a visited point can only
+// be hit again when rho(pm) <= max rho along the path, and only then the stored path is searched.
+// ORTHO: car2lat is diagonal (orthogonal cell); the skipped products are exact zeros, so the result is
+// bit-identical to the general expression.
+// returns 0 = moved on; 1 = ended on the maximum `out` (linear id); 2 = entered a safe cube labelled `out`;
+//         3 = path buffer full.
+// ------------------------------------------------------------------------------------------------
+struct WState {
+  int id, x, y, z, len;
+  double dr0, dr1, dr2, rhomax, r0;
+};
+
+__device__ __forceinline__ void walk_init(const BaderParams& P, const double* __restrict__ rho, WState& w, int start) {
+  w.id = start;
+  w.x = start % P.n1;
+  const int t = start / P.n1;
+  w.y = t % P.n2;
+  w.z = t / P.n2;
+  w.len = 0;
+  w.dr0 = w.dr1 = w.dr2 = 0.0;
+  w.rhomax = -1.0e300;
+  w.r0 = __ldg(rho + start);
+}
+
 template <bool ORTHO>
-__device__ __forceinline__ int dev_walk(const BaderParams& P, const double* __restrict__ rho, const MaxHash& h,
-                                        const SafeMap& sm, int start, int* path, int cap,
-                                        unsigned long long* nsteps_out) {
+__device__ __forceinline__ int walk_step(const BaderParams& P, const double* __restrict__ rho, const MaxHash& h,
+                                         const SafeMap& sm, WState& w, int* path, int cap, int& out) {
   const int n1 = P.n1, n2 = P.n2, n3 = P.n3;
   const int s2 = n1, s3 = n1 * n2;
-  const int wxp = 1 - n1, wxm = n1 - 1, wyp = s2 - s3, wym = s3 - s2, wzp = s3 - s3 * n3, wzm = s3 * n3 - s3;
-  int x = start % n1;
-  int t = start / n1;
-  int y = t % n2;
-  int z = t / n2;
-  int id = start;
-  double dr0 = 0.0, dr1 = 0.0, dr2 = 0.0;
-  double rhomax = -1.0e300;
-  int len = 0;
-  double r0 = __ldg(rho + id);
-  for (;;) {
-    const double* c = rho + id;
-    const double rxp = __ldg(c + ((x + 1 == n1) ? wxp : 1)), rxm = __ldg(c + ((x == 0) ? wxm : -1));
-    const double ryp = __ldg(c + ((y + 1 == n2) ? wyp : s2)), rym = __ldg(c + ((y == 0) ? wym : -s2));
-    const double rzp = __ldg(c + ((z + 1 == n3) ? wzp : s3)), rzm = __ldg(c + ((z == 0) ? wzm : -s3));
-    // rho_grad_dir (:532-567)
-    double gl0 = (rxp - rxm) * 0.5, gl1 = (ryp - rym) * 0.5, gl2 = (rzp - rzm) * 0.5;
-    if (rxp < r0 && rxm < r0) gl0 = 0.0;
-    if (ryp < r0 && rym < r0) gl1 = 0.0;
-    if (rzp < r0 && rzm < r0) gl2 = 0.0;
-    double g0, g1, g2;
-    if (ORTHO) {
-      g0 = P.c2l[0] * (gl0 * P.c2l[0]);
-      g1 = P.c2l[4] * (gl1 * P.c2l[4]);
-      g2 = P.c2l[8] * (gl2 * P.c2l[8]);
-    } else {
-      const double gc0 = gl0 * P.c2l[0] + gl1 * P.c2l[1] + gl2 * P.c2l[2];
-      const double gc1 = gl0 * P.c2l[3] + gl1 * P.c2l[4] + gl2 * P.c2l[5];
-      const double gc2 = gl0 * P.c2l[6] + gl1 * P.c2l[7] + gl2 * P.c2l[8];
-      g0 = P.c2l[0] * gc0 + P.c2l[3] * gc1 + P.c2l[6] * gc2;
-      g1 = P.c2l[1] * gc0 + P.c2l[4] * gc1 + P.c2l[7] * gc2;
-      g2 = P.c2l[2] * gc0 + P.c2l[5] * gc1 + P.c2l[8] * gc2;
-    }
-    const double gmax = fmax(fabs(g0), fmax(fabs(g1), fabs(g2)));
-    int nid, nx, ny, nz;
-    if (gmax < 1e-30) {  // (:468-476)
-      dr0 = dr1 = dr2 = 0.0;
-      // is_max (:571-597) == membership in the candidate list built by k_maxima with the same predicate
-      if (hash_lookup(h, id) >= 0) break;
+  const int x = w.x, y = w.y, z = w.z, id = w.id;
+  const double r0 = w.r0;
+  const double* c = rho + id;
+  const double rxp = __ldg(c + ((x + 1 == n1) ? 1 - n1 : 1)), rxm = __ldg(c + ((x == 0) ? n1 - 1 : -1));
+  const double ryp = __ldg(c + ((y + 1 == n2) ? s2 - s3 : s2)), rym = __ldg(c + ((y == 0) ? s3 - s2 : -s2));
+  const double rzp = __ldg(c + ((z + 1 == n3) ? s3 - s3 * n3 : s3)), rzm = __ldg(c + ((z == 0) ? s3 * n3 - s3 : -s3));
+  // rho_grad_dir (:532-567)
+  double gl0 = (rxp - rxm) * 0.5, gl1 = (ryp - rym) * 0.5, gl2 = (rzp - rzm) * 0.5;
+  if (rxp < r0 && rxm < r0) gl0 = 0.0;
+  if (ryp < r0 && rym < r0) gl1 = 0.0;
+  if (rzp < r0 && rzm < r0) gl2 = 0.0;
+  double g0, g1, g2;
+  if (ORTHO) {
+    g0 = P.c2l[0] * (gl0 * P.c2l[0]);
+    g1 = P.c2l[4] * (gl1 * P.c2l[4]);
+    g2 = P.c2l[8] * (gl2 * P.c2l[8]);
+  } else {
+    const double gc0 = gl0 * P.c2l[0] + gl1 * P.c2l[1] + gl2 * P.c2l[2];
+    const double gc1 = gl0 * P.c2l[3] + gl1 * P.c2l[4] + gl2 * P.c2l[5];
+    const double gc2 = gl0 * P.c2l[6] + gl1 * P.c2l[7] + gl2 * P.c2l[8];
+    g0 = P.c2l[0] * gc0 + P.c2l[3] * gc1 + P.c2l[6] * gc2;
+    g1 = P.c2l[1] * gc0 + P.c2l[4] * gc1 + P.c2l[7] * gc2;
+    g2 = P.c2l[2] * gc0 + P.c2l[5] * gc1 + P.c2l[8] * gc2;
+  }
+  const double gmax = fmax(fabs(g0), fmax(fabs(g1), fabs(g2)));
+  int nid, nx, ny, nz;
+  if (gmax < 1e-30) {  // (:468-476)
+    w.dr0 = w.dr1 = w.dr2 = 0.0;
+    // is_max (:571-597) == membership in the candidate list built by k_maxima with the same predicate
+    if (hash_lookup(h, id) >= 0) { out = id; return 1; }
+    nid = dev_step_ongrid(P, rho, x, y, z, r0);
+    nx = nid % n1; const int t = nid / n1; ny = t % n2; nz = t / n2;
+  } else {  // (:477-483)
+    const double coeff = 1.0 / gmax;
+    g0 = coeff * g0; g1 = coeff * g1; g2 = coeff * g2;
+    const double a0 = nint_small(g0), a1 = nint_small(g1), a2 = nint_small(g2);
+    double dr0 = w.dr0 + g0 - a0, dr1 = w.dr1 + g1 - a1, dr2 = w.dr2 + g2 - a2;
+    const double b0 = nint_small(dr0), b1 = nint_small(dr1), b2 = nint_small(dr2);
+    w.dr0 = dr0 - b0; w.dr1 = dr1 - b1; w.dr2 = dr2 - b2;
+    nx = wrap2(x + (int)(a0 + b0), n1);
+    ny = wrap2(y + (int)(a1 + b1), n2);
+    nz = wrap2(z + (int)(a2 + b2), n3);
+    nid = nx + n1 * (ny + n2 * nz);
+  }
+  // known(p) = 1 (:484)
+  if (w.len >= cap) return 3;
+  path[w.len++] = id;
+  w.rhomax = fmax(w.rhomax, r0);
+  double rn = __ldg(rho + nid);
+  if (rn <= w.rhomax) {  // only then pm can be a point of this path (:487)
+    if (dev_on_path(path, w.len, nid)) {
       nid = dev_step_ongrid(P, rho, x, y, z, r0);
-      nx = nid % n1; t = nid / n1; ny = t % n2; nz = t / n2;
-    } else {  // (:477-483)
-      const double coeff = 1.0 / gmax;
-      g0 = coeff * g0; g1 = coeff * g1; g2 = coeff * g2;
-      const double a0 = nint_small(g0), a1 = nint_small(g1), a2 = nint_small(g2);
-      dr0 = dr0 + g0 - a0; dr1 = dr1 + g1 - a1; dr2 = dr2 + g2 - a2;
-      const double b0 = nint_small(dr0), b1 = nint_small(dr1), b2 = nint_small(dr2);
-      dr0 = dr0 - b0; dr1 = dr1 - b1; dr2 = dr2 - b2;
-      nx = wrap2(x + (int)(a0 + b0), n1);
-      ny = wrap2(y + (int)(a1 + b1), n2);
-      nz = wrap2(z + (int)(a2 + b2), n3);
-      nid = nx + n1 * (ny + n2 * nz);
+      nx = nid % n1; const int t = nid / n1; ny = t % n2; nz = t / n2;
+      w.dr0 = w.dr1 = w.dr2 = 0.0;
+      rn = __ldg(rho + nid);
     }
-    // known(p) = 1 (:484)
-    if (len >= cap) return -1;
-    path[len++] = id;
-    rhomax = fmax(rhomax, r0);
-    double rn = __ldg(rho + nid);
-    if (rn <= rhomax) {  // only then pm can be a point of this path (:487)
-      if (dev_on_path(path, len, nid)) {
-        nid = dev_step_ongrid(P, rho, x, y, z, r0);
-        nx = nid % n1; t = nid / n1; ny = t % n2; nz = t / n2;
-        dr0 = dr1 = dr2 = 0.0;
-        rn = __ldg(rho + nid);
+  }
+  if (nid == id) { out = id; return 1; }  // did not move: maximum (:439)
+  w.id = nid; w.r0 = rn;
+  w.x = nx; w.y = ny; w.z = nz;
+  if (sm.safe) {  // quit at a known interior point (:447)
+    const int cz = nz - sm.zlo;
+    if (cz >= 0 && cz < sm.nzl) {
+      int vx, vy, vz;
+      if (sm.octet) {
+        const int hf = (1 << sm.shift) >> 1;
+        vx = (nx + hf) >> sm.shift; vy = (ny + hf) >> sm.shift; vz = (cz + hf) >> sm.shift;
+        if (vx == sm.c1) vx = 0;
+        if (vy == sm.c2) vy = 0;
+        if (vz == sm.c3) vz = sm.wrapz ? 0 : -1;
+      } else {
+        vx = nx >> sm.shift; vy = ny >> sm.shift; vz = cz >> sm.shift;
       }
-    }
-    if (nid == id) break;  // did not move: maximum (:439)
-    id = nid;
-    r0 = rn;
-    x = nx; y = ny; z = nz;
-    if (sm.safe) {  // quit at a known interior point (:447)
-      const int cz = nz - sm.zlo;
-      if (cz >= 0 && cz < sm.nzl) {
-        const int sl = __ldg(sm.safe + (nx >> sm.shift) + sm.c1 * ((ny >> sm.shift) + sm.c2 * (cz >> sm.shift)));
-        if (sl >= 0) { id = sl; break; }
+      if (vz >= 0) {
+        const int sl = __ldg(sm.safe + vx + sm.c1 * (vy + (size_t)sm.c2 * vz));
+        if (sl >= 0) { out = sl; return 2; }
       }
     }
   }
-  if (nsteps_out) atomicAdd(nsteps_out, (unsigned long long)len);
-  return id;
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
-// z-slab bookkeeping.  A rank owns the global planes [zlo, zhi) (boundaries are multiples of 4 so
-// that no stride-4 cube straddles two ranks); rho is replicated on every rank, labels are sharded.
-// The label buffer holds nzl + 2 planes: local plane 0 = global plane zlo-1 (halo below), planes
-// 1..nzl = owned, plane nzl+1 = global plane zhi (halo above); halos are periodic images and are
-// filled by Exchange (NCCL send/recv between ranks, a device copy when the rank is its own neighbour).
+// Software-pipelined variant used by the persistent walkers: as soon as the next point is known, ALL the
+// loads the next step will need (its density, its 6 neighbours, its early-termination label) are issued
+// together, so that a step costs one memory round trip instead of three dependent ones.  Same arithmetic,
+// same decisions, same results as walk_step.
+// ------------------------------------------------------------------------------------------------
+struct Nb {
+  double xp, xm, yp, ym, zp, zm;
+};
+__device__ __forceinline__ void load_nb(const BaderParams& P, const double* __restrict__ rho, int id, int x, int y, int z, Nb& nb) {
+  const int n1 = P.n1, n2 = P.n2, n3 = P.n3;
+  const int s2 = n1, s3 = n1 * n2;
+  const double* c = rho + id;
+  nb.xp = __ldg(c + ((x + 1 == n1) ? 1 - n1 : 1));
+  nb.xm = __ldg(c + ((x == 0) ? n1 - 1 : -1));
+  nb.yp = __ldg(c + ((y + 1 == n2) ? s2 - s3 : s2));
+  nb.ym = __ldg(c + ((y == 0) ? s3 - s2 : -s2));
+  nb.zp = __ldg(c + ((z + 1 == n3) ? s3 - s3 * n3 : s3));
+  nb.zm = __ldg(c + ((z == 0) ? s3 * n3 - s3 : -s3));
+}
+__device__ __forceinline__ int safe_lookup(const SafeMap& sm, int nx, int ny, int nz) {
+  if (!sm.safe) return -1;
+  const int cz = nz - sm.zlo;
+  if (cz < 0 || cz >= sm.nzl) return -1;
+  int vx, vy, vz;
+  if (sm.octet) {
+    const int hf = (1 << sm.shift) >> 1;
+    vx = (nx + hf) >> sm.shift; vy = (ny + hf) >> sm.shift; vz = (cz + hf) >> sm.shift;
+    if (vx == sm.c1) vx = 0;
+    if (vy == sm.c2) vy = 0;
+    if (vz == sm.c3) { if (!sm.wrapz) return -1; vz = 0; }
+  } else {
+    vx = nx >> sm.shift; vy = ny >> sm.shift; vz = cz >> sm.shift;
+  }
+  return __ldg(sm.safe + vx + sm.c1 * (vy + (size_t)sm.c2 * vz));
+}
+// w: current point with w.r0, nb = its neighbours, sl = early-termination label of its cube (all loaded by
+// the previous call or by the caller for the start point, where sl must be -1)
+template <bool ORTHO>
+__device__ __forceinline__ int walk_step_pipe(const BaderParams& P, const double* __restrict__ rho, const MaxHash& h,
+                                              const SafeMap& sm, WState& w, Nb& nb, int& sl, int* path, int cap, int& out) {
+  if (sl >= 0) { out = sl; return 2; }  // quit at a known interior point (:447)
+  const int n1 = P.n1, n2 = P.n2, n3 = P.n3;
+  const int x = w.x, y = w.y, z = w.z, id = w.id;
+  const double r0 = w.r0;
+  // rho_grad_dir (:532-567)
+  double gl0 = (nb.xp - nb.xm) * 0.5, gl1 = (nb.yp - nb.ym) * 0.5, gl2 = (nb.zp - nb.zm) * 0.5;
+  if (nb.xp < r0 && nb.xm < r0) gl0 = 0.0;
+  if (nb.yp < r0 && nb.ym < r0) gl1 = 0.0;
+  if (nb.zp < r0 && nb.zm < r0) gl2 = 0.0;
+  double g0, g1, g2;
+  if (ORTHO) {
+    g0 = P.c2l[0] * (gl0 * P.c2l[0]);
+    g1 = P.c2l[4] * (gl1 * P.c2l[4]);
+    g2 = P.c2l[8] * (gl2 * P.c2l[8]);
+  } else {
+    const double gc0 = gl0 * P.c2l[0] + gl1 * P.c2l[1] + gl2 * P.c2l[2];
+    const double gc1 = gl0 * P.c2l[3] + gl1 * P.c2l[4] + gl2 * P.c2l[5];
+    const double gc2 = gl0 * P.c2l[6] + gl1 * P.c2l[7] + gl2 * P.c2l[8];
+    g0 = P.c2l[0] * gc0 + P.c2l[3] * gc1 + P.c2l[6] * gc2;
+    g1 = P.c2l[1] * gc0 + P.c2l[4] * gc1 + P.c2l[7] * gc2;
+    g2 = P.c2l[2] * gc0 + P.c2l[5] * gc1 + P.c2l[8] * gc2;
+  }
+  const double gmax = fmax(fabs(g0), fmax(fabs(g1), fabs(g2)));
+  int nid, nx, ny, nz;
+  if (gmax < 1e-30) {  // (:468-476)
+    w.dr0 = w.dr1 = w.dr2 = 0.0;
+    if (hash_lookup(h, id) >= 0) { out = id; return 1; }
+    nid = dev_step_ongrid(P, rho, x, y, z, r0);
+    nx = nid % n1; const int t = nid / n1; ny = t % n2; nz = t / n2;
+  } else {  // (:477-483)
+    const double coeff = 1.0 / gmax;
+    g0 = coeff * g0; g1 = coeff * g1; g2 = coeff * g2;
+    const double a0 = nint_small(g0), a1 = nint_small(g1), a2 = nint_small(g2);
+    double dr0 = w.dr0 + g0 - a0, dr1 = w.dr1 + g1 - a1, dr2 = w.dr2 + g2 - a2;
+    const double b0 = nint_small(dr0), b1 = nint_small(dr1), b2 = nint_small(dr2);
+    w.dr0 = dr0 - b0; w.dr1 = dr1 - b1; w.dr2 = dr2 - b2;
+    nx = wrap2(x + (int)(a0 + b0), n1);
+    ny = wrap2(y + (int)(a1 + b1), n2);
+    nz = wrap2(z + (int)(a2 + b2), n3);
+    nid = nx + n1 * (ny + n2 * nz);
+  }
+  if (w.len >= cap) return 3;
+  path[w.len++] = id;  // known(p) = 1 (:484)
+  w.rhomax = fmax(w.rhomax, r0);
+  // everything the next step needs, in one batch
+  double rn = __ldg(rho + nid);
+  load_nb(P, rho, nid, nx, ny, nz, nb);
+  sl = safe_lookup(sm, nx, ny, nz);
+  if (rn <= w.rhomax) {  // only then pm can be a point of this path (:487)
+    if (dev_on_path(path, w.len, nid)) {
+      nid = dev_step_ongrid(P, rho, x, y, z, r0);
+      nx = nid % n1; const int t = nid / n1; ny = t % n2; nz = t / n2;
+      w.dr0 = w.dr1 = w.dr2 = 0.0;
+      rn = __ldg(rho + nid);
+      load_nb(P, rho, nid, nx, ny, nz, nb);
+      sl = safe_lookup(sm, nx, ny, nz);
+    }
+  }
+  if (nid == id) { out = id; return 1; }  // did not move: maximum (:439)
+  w.id = nid; w.r0 = rn;
+  w.x = nx; w.y = ny; w.z = nz;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// z-slab bookkeeping.  A rank owns the global planes [zlo, zhi) (interior boundaries are multiples of the
+// top lattice stride so that no cube straddles two ranks); rho is replicated on every rank, labels are
+// sharded.  The label buffer holds nzl + 2 planes: local plane 0 = global plane zlo-1 (halo below),
+// planes 1..nzl = owned, plane nzl+1 = global plane zhi (halo above); halos are periodic images and are
+// filled by exchange_halos (NCCL send/recv between ranks, a device copy when the rank is its own
+// neighbour).  periodic = 1: the rank owns every plane (single GPU) and kernels may wrap z themselves.
 // ------------------------------------------------------------------------------------------------
 struct Slab {
-  int zlo, zhi, nzl;
+  int zlo, zhi, nzl, periodic;
 };
 
-// K0: candidate maxima (26-neighbour, is_max) by a separable 3x3x3 box maximum on shared-memory
-// tiles with a periodic 1-cell halo; marks the stride-4 / stride-2 cubes that contain a maximum.
-constexpr int TX = 32, TY = 8, TZ = 8;
+// "has a local maximum" flags of the stride-(2<<i) cubes, i = 0..nlev-1
+struct CubeFlags {
+  unsigned char* p[MAXLEV];
+  int c1[MAXLEV], c2[MAXLEV];
+  int nlev;
+};
+
+// 3x3 in-plane combination on a (32 x TY) thread tile with a 1-cell halo in shared memory.
+// s: [(TY+2)][34] buffer of T.  Every thread contributes its own value; threads with hslot >= 0 also a
+// halo value.  Returns Op(3x3 neighbourhood) of the thread's point.  One __syncthreads per call; the
+// caller alternates between two buffers so that no second barrier is needed.
+struct OpMaxF {
+  static __device__ __forceinline__ float c3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+};
+struct OpAgree {  // common value of three labels, or -1
+  static __device__ __forceinline__ int c3(int a, int b, int c) { return (a == b && b == c) ? a : -1; }
+};
+template <class T, class Op>
+__device__ __forceinline__ T plane3x3(T* s, T own, int hslot, T hval, int lx, int ly) {
+  s[(ly + 1) * 34 + lx + 1] = own;
+  if (hslot >= 0) s[hslot] = hval;
+  __syncthreads();
+  const T* col = s + ly * 34 + lx + 1;
+  const T a = Op::c3(col[0], own, col[68]);
+  T l = __shfl_up_sync(FULL, a, 1), r = __shfl_down_sync(FULL, a, 1);
+  if (lx == 0) l = Op::c3(col[-1], col[33], col[67]);
+  if (lx == 31) r = Op::c3(col[1], col[35], col[69]);
+  return Op::c3(l, a, r);
+}
+constexpr int TY = 8;                       // tile rows (256 threads)
+constexpr int NHALO = 2 * 34 + 2 * TY;      // halo elements of a 32 x TY tile
+// halo element h -> (col, row) in tile coordinates (-1..32, -1..TY)
+__device__ __forceinline__ void halo_decode(int h, int& col, int& row) {
+  if (h < 34) { row = -1; col = h - 1; }
+  else if (h < 68) { row = TY; col = h - 35; }
+  else if (h < 68 + TY) { col = -1; row = h - 68; }
+  else { col = 32; row = h - 68 - TY; }
+}
+
+// K0: candidate maxima (26-neighbour, is_max).  The grid is streamed once, z-marching per (32 x TY)
+// column tile; the 3x3x3 box maximum is taken on fp32 roundings (monotone, hence a necessary
+// condition: no neighbour is strictly greater in fp64 => none is in fp32) and the rare survivors are
+// re-tested exactly in fp64.  Marks the cubes of every level that contain a maximum.
+constexpr int MZC = 32;  // planes per block
+constexpr int MPF = 2;   // planes in flight per thread
 __global__ void __launch_bounds__(256) k_maxima(const __grid_constant__ BaderParams P, const Slab S,
                                                 const double* __restrict__ rho, int* __restrict__ cand,
-                                                int* __restrict__ ncand, int maxcand, unsigned char* __restrict__ cube4,
-                                                unsigned char* __restrict__ cube2) {
-  extern __shared__ double sm[];
-  double* s0 = sm;                                   // [TZ+2][TY+2][TX+2]
-  double* s1 = sm + (TZ + 2) * (TY + 2) * (TX + 2);  // [TZ+2][TY+2][TX] max over x
+                                                int* __restrict__ ncand, int maxcand, const __grid_constant__ CubeFlags CF) {
+  __shared__ float sbuf[2][(TY + 2) * 34];
   const int n1 = P.n1, n2 = P.n2, n3 = P.n3;
-  const int bx0 = blockIdx.x * TX, by0 = blockIdx.y * TY, bz0 = S.zlo + blockIdx.z * TZ;
-  const int tid = threadIdx.x;
-  constexpr int SX = TX + 2, SY = TY + 2, SZ = TZ + 2;
-  {  // row-wise staging: one warp per (y,z) row of 34 values, then the 3-point maximum along x
-    const int lane = tid & 31, wid = tid >> 5;
-    const int gx0 = wrapx(bx0 - 1 + lane, n1), gx1 = wrapx(bx0 - 1 + 32 + (lane & 1), n1);
-    for (int r = wid; r < SY * SZ; r += 8) {
-      const int sy = r % SY, sz = r / SY;
-      const int gy = wrapx(by0 + sy - 1, n2), gz = wrapx(bz0 + sz - 1, n3);
-      const double* row = rho + (size_t)n1 * (gy + (size_t)n2 * gz);
-      s0[r * SX + lane] = __ldg(row + gx0);
-      if (lane < 2) s0[r * SX + 32 + lane] = __ldg(row + gx1);
-    }
-    __syncthreads();
-    for (int r = wid; r < SY * SZ; r += 8) {
-      const double* p = s0 + r * SX + lane;
-      s1[r * TX + lane] = fmax(p[0], fmax(p[1], p[2]));
-    }
-    __syncthreads();
-  }
-  const int lx = tid % TX, ly = tid / TX;
+  const size_t s3 = (size_t)n1 * n2;
+  const int tid = threadIdx.x, lx = tid & 31, ly = tid >> 5;
+  const int bx0 = blockIdx.x * 32, by0 = blockIdx.y * TY;
+  const int z0 = S.zlo + blockIdx.z * MZC, z1 = min(z0 + MZC, S.zhi);
   const int gx = bx0 + lx, gy = by0 + ly;
-  double m[SZ];
-#pragma unroll
-  for (int sz = 0; sz < SZ; sz++) {
-    const double* p = s1 + (sz * SY + ly) * TX + lx;
-    m[sz] = fmax(p[0], fmax(p[TX], p[2 * TX]));
+  const bool valid = gx < n1 && gy < n2;
+  const double* colp = rho + wrapx(gx, n1) + (size_t)n1 * wrapx(gy, n2);
+  int hslot = -1;
+  const double* hp = rho;
+  if (tid < NHALO) {
+    int hc, hr;
+    halo_decode(tid, hc, hr);
+    hslot = (hr + 1) * 34 + hc + 1;
+    hp = rho + wrapx(bx0 + hc, n1) + (size_t)n1 * wrapx(by0 + hr, n2);
   }
-  if (gx < n1 && gy < n2) {
+  float pm0 = 0.f, pm1 = 0.f, fc1 = 0.f;
+  // register ring: the loads of the next MPF planes are in flight while a plane is processed
+  double v[MPF], hv[MPF];
 #pragma unroll
-    for (int lz = 0; lz < TZ; lz++) {
-      const int gz = bz0 + lz;
-      if (gz >= S.zhi) break;
-      const double c = s0[((lz + 1) * SY + (ly + 1)) * SX + lx + 1];
-      const double bm = fmax(m[lz], fmax(m[lz + 1], m[lz + 2]));
-      if (!(bm > c)) {  // no neighbour strictly greater
-        const int slot = atomicAdd(ncand, 1);
-        if (slot < maxcand) cand[slot] = gx + n1 * (gy + n2 * gz);
-        const int c41 = (n1 + 3) / 4, c42 = (n2 + 3) / 4;
-        const int c21 = (n1 + 1) / 2, c22 = (n2 + 1) / 2;
-        cube4[(gx >> 2) + c41 * ((gy >> 2) + (size_t)c42 * ((gz - S.zlo) >> 2))] = 1;
-        cube2[(gx >> 1) + c21 * ((gy >> 1) + (size_t)c22 * ((gz - S.zlo) >> 1))] = 1;
+  for (int j = 0; j < MPF; j++) {
+    const int wz = wrapx(z0 - 1 + j, n3);
+    v[j] = (z0 - 1 + j <= z1) ? __ldg(colp + s3 * wz) : 0.0;
+    hv[j] = (hslot >= 0 && z0 - 1 + j <= z1) ? __ldg(hp + s3 * wz) : 0.0;
+  }
+  for (int it = z0 - 1; it <= z1; it += MPF) {
+#pragma unroll
+    for (int j = 0; j < MPF; j++) {
+      const int iz = it + j;
+      if (iz > z1) break;
+      const float fv = __double2float_rn(v[j]), fh = __double2float_rn(hv[j]);
+      if (iz + MPF <= z1) {
+        const int wz = wrapx(iz + MPF, n3);
+        v[j] = __ldg(colp + s3 * wz);
+        if (hslot >= 0) hv[j] = __ldg(hp + s3 * wz);
       }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// walkers.  `label` is the owned part of the label buffer re-based so that label[global id] is valid
-// for every owned point.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void finish_walk(int start, int term, int* __restrict__ label, const MaxHash& h,
-                                            unsigned char* __restrict__ reached, int* __restrict__ overflow,
-                                            int* __restrict__ noverflow, int* __restrict__ err) {
-  if (term < 0) {
-    const int slot = atomicAdd(noverflow, 1);
-    overflow[slot] = start;
-    return;
-  }
-  label[start] = term;
-  const int ci = hash_lookup(h, term);
-  if (ci < 0) atomicExch(err, 1);  // terminal is not a candidate maximum: cannot happen
-  else if (!reached[ci]) reached[ci] = 1;
-}
-
-// every owned point of the stride-s lattice (s = 1: every grid point = the EXACT referee)
-template <bool ORTHO>
-__global__ void __launch_bounds__(128) k_walk_lattice(const __grid_constant__ BaderParams P, const Slab S,
-                                                      const double* __restrict__ rho, int s, int m1, int m2, int m3,
-                                                      int* __restrict__ label, MaxHash h, unsigned char* __restrict__ reached,
-                                                      int* __restrict__ overflow, int* __restrict__ noverflow,
-                                                      int* __restrict__ err, unsigned long long* nsteps) {
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (long long)m1 * m2 * m3) return;
-  const int lx = (int)(t % m1), ly = (int)((t / m1) % m2), lz = (int)(t / ((long long)m1 * m2));
-  const int start = lx * s + P.n1 * (ly * s + P.n2 * (S.zlo + lz * s));
-  int path[PATHCAP];
-  const SafeMap nosafe{nullptr, 0, 0, 0, 0, 0};
-  const int term = dev_walk<ORTHO>(P, rho, h, nosafe, start, path, PATHCAP, nsteps);
-  finish_walk(start, term, label, h, reached, overflow, noverflow, err);
-}
-
-template <bool ORTHO>
-__global__ void __launch_bounds__(128) k_walk_list(const __grid_constant__ BaderParams P, const double* __restrict__ rho,
-                                                   const int* __restrict__ list, int count, int* __restrict__ label,
-                                                   MaxHash h, SafeMap sm, unsigned char* __restrict__ reached,
-                                                   int* __restrict__ overflow, int* __restrict__ noverflow,
-                                                   int* __restrict__ err, unsigned long long* nsteps) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= count) return;
-  const int start = list[t];
-  int path[PATHCAP];
-  const int term = dev_walk<ORTHO>(P, rho, h, sm, start, path, PATHCAP, nsteps);
-  finish_walk(start, term, label, h, reached, overflow, noverflow, err);
-}
-
-// rare long trajectories: path buffer in global memory (bigcap entries per walker)
-__global__ void __launch_bounds__(64) k_walk_big(const __grid_constant__ BaderParams P, const double* __restrict__ rho,
-                                                 const int* __restrict__ list, int count, int* __restrict__ label,
-                                                 MaxHash h, unsigned char* __restrict__ reached, int* __restrict__ scratch,
-                                                 int bigcap, int* __restrict__ err, unsigned long long* nsteps) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= count) return;
-  const int start = list[t];
-  const SafeMap nosafe{nullptr, 0, 0, 0, 0, 0};
-  const int term = dev_walk<false>(P, rho, h, nosafe, start, scratch + (size_t)t * bigcap, bigcap, nsteps);
-  if (term < 0) { atomicExch(err, 2); return; }
-  label[start] = term;
-  const int ci = hash_lookup(h, term);
-  if (ci < 0) atomicExch(err, 1);
-  else reached[ci] = 1;
-}
-
-// ------------------------------------------------------------------------------------------------
-// classify: one thread per owned stride-s cube.  If its 8 corners (already labelled; the upper ones
-// may sit on the halo-above plane) agree and it holds no local maximum, fill its new stride-s/2
-// points (label | FILLBIT); otherwise queue them.  lbuf = label buffer including halos.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_classify(int n1, int n2, int n3, const Slab S, int s, int* __restrict__ lbuf,
-                                                  const unsigned char* __restrict__ cubemax, int* __restrict__ cubeuni,
-                                                  int* __restrict__ list, int* __restrict__ nlist) {
-  const int c1 = (n1 + s - 1) / s, c2 = (n2 + s - 1) / s, c3 = (S.nzl + s - 1) / s;
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = t < (long long)c1 * c2 * c3;
-  int npush = 0;
-  int pts[7];
-  if (active) {
-    const int cx = (int)(t % c1), cy = (int)((t / c1) % c2), cz = (int)(t / ((long long)c1 * c2));
-    const int x0 = cx * s, y0 = cy * s, z0 = S.zlo + cz * s;
-    const int x1 = (x0 + s < n1) ? x0 + s : 0, y1 = (y0 + s < n2) ? y0 + s : 0;
-    const int p0 = z0 - S.zlo + 1;                              // local plane of z0
-    const int p1 = ((z0 + s < n3) ? z0 + s : n3) - S.zlo + 1;   // local plane of the upper corners (may be the halo)
-    const int s3 = n1 * n2;
-    const int l000 = lbuf[x0 + n1 * y0 + s3 * p0] & LMASK;
-    bool uni = !cubemax[t];
-    uni = uni && ((lbuf[x1 + n1 * y0 + s3 * p0] & LMASK) == l000);
-    uni = uni && ((lbuf[x0 + n1 * y1 + s3 * p0] & LMASK) == l000);
-    uni = uni && ((lbuf[x1 + n1 * y1 + s3 * p0] & LMASK) == l000);
-    uni = uni && ((lbuf[x0 + n1 * y0 + s3 * p1] & LMASK) == l000);
-    uni = uni && ((lbuf[x1 + n1 * y0 + s3 * p1] & LMASK) == l000);
-    uni = uni && ((lbuf[x0 + n1 * y1 + s3 * p1] & LMASK) == l000);
-    uni = uni && ((lbuf[x1 + n1 * y1 + s3 * p1] & LMASK) == l000);
-    cubeuni[t] = uni ? l000 : -1;
-    const int hh = s >> 1;
-    for (int o = 1; o < 8; o++) {
-      const int x = x0 + ((o & 1) ? hh : 0), y = y0 + ((o & 2) ? hh : 0), z = z0 + ((o & 4) ? hh : 0);
-      if (x >= n1 || y >= n2 || z >= S.zhi) continue;
-      if (uni) lbuf[x + n1 * y + s3 * (z - S.zlo + 1)] = (int)((unsigned)l000 | FILLBIT);
-      else pts[npush++] = x + n1 * (y + n2 * z);  // global id
-    }
-  }
-  // block-aggregated append (keeps spatial order inside a block)
-  __shared__ int s_base;
-  __shared__ int s_warp[8];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  int incl = npush;
-  for (int d = 1; d < 32; d <<= 1) {
-    const int v = __shfl_up_sync(0xffffffffu, incl, d);
-    if (lane >= d) incl += v;
-  }
-  if (lane == 31) s_warp[wid] = incl;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int acc = 0;
-    for (int w = 0; w < 8; w++) { const int v = s_warp[w]; s_warp[w] = acc; acc += v; }
-    s_base = acc ? atomicAdd(nlist, acc) : 0;
-  }
-  __syncthreads();
-  if (npush) {
-    int off = s_base + s_warp[wid] + incl - npush;
-    for (int k = 0; k < npush; k++) list[off + k] = pts[k];
-  }
-}
-
-// safe[c] = cubeuni[c] if the 26 neighbouring cubes (periodic in x,y; owned layers only in z) carry the
-// same uniform label, else -1
-__global__ void __launch_bounds__(256) k_safe(int c1, int c2, int c3, const int* __restrict__ cubeuni, int* __restrict__ safe) {
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (long long)c1 * c2 * c3) return;
-  const int v = cubeuni[t];
-  int out = v;
-  if (v >= 0) {
-    const int cx = (int)(t % c1), cy = (int)((t / c1) % c2), cz = (int)(t / ((long long)c1 * c2));
-    for (int dz = -1; dz <= 1 && out >= 0; dz++) {
-      const int zz = cz + dz;
-      if (zz < 0 || zz >= c3) { out = -1; break; }
-      for (int dy = -1; dy <= 1 && out >= 0; dy++) {
-        const int yy = (cy + dy + c2) % c2;
-        for (int dx = -1; dx <= 1; dx++) {
-          const int xx = (cx + dx + c1) % c1;
-          if (cubeuni[xx + c1 * (yy + (size_t)c2 * zz)] != v) { out = -1; break; }
+      const float pm2 = plane3x3<float, OpMaxF>(sbuf[(iz - z0 + 1) & 1], fv, hslot, fh, lx, ly);
+      if (iz > z0) {  // plane iz-1 is complete
+        const float bm = fmaxf(fmaxf(pm0, pm1), pm2);
+        if (valid && !(bm > fc1)) {
+          const int gz = iz - 1;
+          if (dev_is_max(n1, n2, n3, rho, gx, gy, gz)) {
+            const int slot = atomicAdd(ncand, 1);
+            if (slot < maxcand) cand[slot] = gx + n1 * (gy + n2 * gz);
+            for (int i = 0; i < CF.nlev; i++)
+              CF.p[i][(gx >> (i + 1)) + CF.c1[i] * ((gy >> (i + 1)) + (size_t)CF.c2[i] * ((gz - S.zlo) >> (i + 1)))] = 1;
+          }
         }
       }
+      pm0 = pm1; pm1 = pm2; fc1 = fv;
     }
   }
-  safe[t] = out;
 }
 
 // ------------------------------------------------------------------------------------------------
-// edge fix: every FILLED owned point with a 26-neighbour of a different label is queued for an exact
-// walk (the refine_edge criterion, is_vol_edge bader@proc.f90:730-752).  Reads both halo planes.
+// walkers: persistent warps with lane refill.  A warp takes batches of work items from a global cursor;
+// a lane whose trajectory has ended picks up the next item while the other lanes keep stepping, so the
+// long trajectories that run along an interatomic surface do not idle the rest of the warp.
+// `label_g` is the owned part of the label buffer re-based so that label_g[global id] is valid for every
+// owned point.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_edgefix(int n1, int n2, const Slab S, int* __restrict__ lbuf,
-                                                 int* __restrict__ list, int* __restrict__ nlist,
-                                                 const unsigned char* __restrict__ dirty_in, unsigned char* __restrict__ dirty_out) {
-  const int tile = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-  if (dirty_in && !dirty_in[tile]) return;  // nothing changed near this tile in the previous pass
-  __shared__ int sl[(TZ + 2) * (TY + 2) * (TX + 2)];
-  constexpr int SX = TX + 2, SY = TY + 2, SZ = TZ + 2;
-  const int bx0 = blockIdx.x * TX, by0 = blockIdx.y * TY, lz0 = blockIdx.z * TZ;  // lz0: first owned plane (0-based)
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int s3 = n1 * n2;
-  // row-wise staging: one warp per (y,z) row of 34 labels
-  const int gx0 = wrapx(bx0 - 1 + lane, n1);
-  const int gx1 = wrapx(bx0 - 1 + 32 + (lane & 1), n1);
-  int first = -1;
-  bool uniform = true;
-  for (int r = wid; r < SY * SZ; r += 8) {
-    const int sy = r % SY, sz = r / SY;
-    const int gy = wrapx(by0 + sy - 1, n2);
-    int pl = lz0 + sz;  // buffer plane (halo offset included)
-    if (pl > S.nzl + 1) pl = S.nzl + 1;
-    const int* row = lbuf + (size_t)s3 * pl + (size_t)n1 * gy;
-    const int v = row[gx0];
-    sl[r * SX + lane] = v;
-    if (first < 0) first = v & LMASK;
-    uniform = uniform && ((v & LMASK) == first);
-    if (lane < 2) {
-      const int v2 = row[gx1];
-      sl[r * SX + 32 + lane] = v2;
-      uniform = uniform && ((v2 & LMASK) == first);
-    }
-  }
-  __syncthreads();
-  uniform = uniform && (first == (sl[0] & LMASK));
-  if (__syncthreads_and(uniform)) return;
-  const int lx = tid % TX, ly = tid / TX;
-  const int gx = bx0 + lx, gy = by0 + ly;
-  if (gx >= n1 || gy >= n2) return;
-  for (int lz = 0; lz < TZ; lz++) {
-    if (lz0 + lz >= S.nzl) break;
-    const int c = sl[((lz + 1) * SY + (ly + 1)) * SX + lx + 1];
-    if (!((unsigned)c & FILLBIT)) continue;
-    const int cl = c & LMASK;
-    bool edge = false;
-#pragma unroll
-    for (int dz = 0; dz < 3; dz++)
-#pragma unroll
-      for (int dy = 0; dy < 3; dy++)
-#pragma unroll
-        for (int dx = 0; dx < 3; dx++)
-          edge = edge || ((sl[((lz + dz) * SY + (ly + dy)) * SX + lx + dx] & LMASK) != cl);
-    if (edge) {
-      lbuf[gx + n1 * gy + s3 * (lz0 + lz + 1)] = cl;  // clear FILLBIT: walked from now on
-      list[atomicAdd(nlist, 1)] = gx + n1 * (gy + n2 * (S.zlo + lz0 + lz));
-      // the next pass only has to look at tiles within one cell of a re-walked point
-      const int x0 = (lx == 0) ? -1 : 0, x1 = (lx == TX - 1 || gx == n1 - 1) ? 1 : 0;
-      const int y0 = (ly == 0) ? -1 : 0, y1 = (ly == TY - 1 || gy == n2 - 1) ? 1 : 0;
-      const int z0 = (lz == 0) ? -1 : 0, z1 = (lz == TZ - 1 || lz0 + lz == S.nzl - 1) ? 1 : 0;
-      for (int dz = z0; dz <= z1; dz++) {
-        const int tz = (int)blockIdx.z + dz;
-        if (tz < 0 || tz >= (int)gridDim.z) continue;  // other rank / periodic image: those layers are always rechecked
-        for (int dy = y0; dy <= y1; dy++) {
-          const int ty = ((int)blockIdx.y + dy + gridDim.y) % gridDim.y;
-          for (int dx = x0; dx <= x1; dx++) {
-            const int tx = ((int)blockIdx.x + dx + gridDim.x) % gridDim.x;
-            dirty_out[tx + gridDim.x * (ty + gridDim.y * tz)] = 1;
+struct WalkArgs {
+  const double* rho;
+  int* label_g;
+  MaxHash h;
+  SafeMap sm;
+  unsigned char* reached;
+  const int* list;          // nullptr: lattice mode
+  long long count;
+  const int2* items;        // non-null: work items (first list index, count) cut from a segmented list
+  int nitems;               // upper bound; the exact number is *nitems_dev
+  const int* nitems_dev;
+  int lat_s, lat_m1, lat_m2;  // lattice mode: item t -> (lx, ly, lz) -> start = lx*s + n1*(ly*s + n2*(zlo + lz*s))
+  Slab S;
+  unsigned long long* cursor;
+  int batch;
+  int refill_min;           // idle lanes that trigger a refill
+  int* overflow; int* noverflow; int overcap;
+  int* err;
+  unsigned long long* nsteps;
+  int* next; int* nnext; int nextcap;  // FIX: points whose neighbourhood became non-uniform
+};
+
+// FIX: `start` was a filled point; if its own trajectory ends elsewhere, its filled 26-neighbours now have
+// a neighbour with a different label and are queued for the next pass (claimed by clearing FILLBIT).
+__device__ __noinline__ void claim_neighbours(const BaderParams& P, const WalkArgs& A, int start) {
+  const int n1 = P.n1, n2 = P.n2, n3 = P.n3;
+  const int x = start % n1, y = (start / n1) % n2, z = start / (n1 * n2);
+  for (int dz = -1; dz <= 1; dz++) {
+    int zz = z + dz;
+    if (A.S.periodic) zz = wrapx(zz, n3);
+    else if (zz < A.S.zlo || zz >= A.S.zhi) continue;  // the owner sees the change through its halo plane
+    for (int dy = -1; dy <= 1; dy++) {
+      const int yy = wrapx(y + dy, n2);
+      for (int dx = -1; dx <= 1; dx++) {
+        const int q = wrapx(x + dx, n1) + n1 * (yy + n2 * zz);
+        if (q == start) continue;
+        if ((unsigned)A.label_g[q] & FILLBIT) {
+          const unsigned old = (unsigned)atomicAnd(A.label_g + q, LMASK);
+          if (old & FILLBIT) {
+            const int slot = atomicAdd(A.nnext, 1);
+            if (slot < A.nextcap) A.next[slot] = q;
+            else atomicExch(A.err, 4);
           }
         }
       }
@@ -524,35 +529,478 @@ __global__ void __launch_bounds__(256) k_edgefix(int n1, int n2, const Slab S, i
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// compaction of the owned labels: terminal linear id -> index in the ordered maxima list
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_compact(long long nn, int* __restrict__ label, MaxHash h,
-                                                 const int* __restrict__ cand2out, int* __restrict__ err) {
-  // 4 consecutive labels per thread (16-byte accesses); the hash lookup is repeated only when the
-  // terminal changes, which inside a basin it does not.
-  const long long nv = nn >> 2;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  int last_t = -1, last_o = -1;
-  auto conv = [&](int v) -> int {
-    const int t = v & LMASK;
-    if (t != last_t) {
-      const int ci = hash_lookup(h, t);
-      if (ci < 0) { atomicExch(err, 1); return v; }
-      last_t = t;
-      last_o = __ldg(cand2out + ci);
-    }
-    return last_o;
-  };
-  int4* l4 = reinterpret_cast<int4*>(label);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
-    int4 v = l4[i];
-    v.x = conv(v.x); v.y = conv(v.y); v.z = conv(v.z); v.w = conv(v.w);
-    l4[i] = v;
+template <bool FIX>
+__device__ __forceinline__ void walk_finish(const BaderParams& P, const WalkArgs& A, int start, int st, int out) {
+  if (st == 3) {
+    const int slot = atomicAdd(A.noverflow, 1);
+    if (slot < A.overcap) A.overflow[slot] = start;
+    else atomicExch(A.err, 3);
+    return;
   }
-  if (blockIdx.x == 0 && threadIdx.x < (nn & 3)) {
-    const long long i = (nv << 2) + threadIdx.x;
-    label[i] = conv(label[i]);
+  int lab = out;
+  if (st == 1) {
+    lab = hash_lookup(A.h, out);
+    if (lab < 0) { atomicExch(A.err, 1); return; }  // terminal is not a candidate maximum: cannot happen
+    if (!A.reached[lab]) A.reached[lab] = 1;
+  }
+  if (FIX) {
+    const int old = A.label_g[start] & LMASK;
+    A.label_g[start] = lab;
+    if (old != lab) claim_neighbours(P, A, start);
+  } else {
+    A.label_g[start] = lab;
+  }
+}
+
+__device__ __forceinline__ int walk_item(const BaderParams& P, const WalkArgs& A, long long t) {
+  if (A.list) return __ldg(A.list + t);
+  const int lx = (int)(t % A.lat_m1), ly = (int)((t / A.lat_m1) % A.lat_m2), lz = (int)(t / ((long long)A.lat_m1 * A.lat_m2));
+  return lx * A.lat_s + P.n1 * (ly * A.lat_s + P.n2 * (A.S.zlo + lz * A.lat_s));
+}
+
+constexpr int REFILL_MIN = 24;  // idle lanes that trigger a refill: high, so that the lanes of a warp stay in step and their loads coalesce
+template <bool ORTHO, bool FIX, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_walk(const __grid_constant__ BaderParams P, const __grid_constant__ WalkArgs A) {
+  const int lane = threadIdx.x & 31;
+  int path[PATHCAP];
+  long long qpos = 0, qend = 0;  // warp-uniform: items [qpos, qend) are this warp's
+  bool done = false, active = false;
+  int start = 0, sl = -1;
+  WState w;
+  Nb nb;
+  unsigned long long steps = 0;
+  for (;;) {
+    const unsigned idle = __ballot_sync(FULL, !active);
+    if (idle == FULL || (!done && __popc(idle) >= A.refill_min)) {
+      if (qpos >= qend && !done) {
+        if (A.items) {  // next work item: a spatially compact group of start points
+          unsigned long long b = 0;
+          if (lane == 0) b = atomicAdd(A.cursor, 1ull);
+          b = __shfl_sync(FULL, b, 0);
+          if (b >= (unsigned long long)__ldg(A.nitems_dev)) done = true;
+          else {
+            const int2 it = __ldg(A.items + b);
+            qpos = it.x; qend = qpos + it.y;
+          }
+        } else {
+          unsigned long long base = 0;
+          if (lane == 0) base = atomicAdd(A.cursor, (unsigned long long)A.batch);
+          base = __shfl_sync(FULL, base, 0);
+          if ((long long)base >= A.count) done = true;
+          else { qpos = (long long)base; qend = min((long long)base + A.batch, A.count); }
+        }
+      }
+      const int navail = (int)(qend - qpos);
+      if (navail > 0) {
+        const int rank = __popc(idle & ((1u << lane) - 1u));
+        if (!active && rank < navail) {
+          start = walk_item(P, A, qpos + rank);
+          walk_init(P, A.rho, w, start);
+          load_nb(P, A.rho, start, w.x, w.y, w.z, nb);
+          sl = -1;
+          active = true;
+        }
+        qpos += min(navail, __popc(idle));
+      } else if (done && idle == FULL) break;
+    }
+    if (active) {
+      int out = 0;
+      const int st = walk_step_pipe<ORTHO>(P, A.rho, A.h, A.sm, w, nb, sl, path, PATHCAP, out);
+      if (st) {
+        steps += (unsigned)w.len;
+        walk_finish<FIX>(P, A, start, st, out);
+        active = false;
+      }
+    }
+  }
+  if (A.nsteps && steps) atomicAdd(A.nsteps, steps);
+}
+
+// cut the non-empty segments of a segmented list into work items of at most `batch` entries, IN SEGMENT
+// ORDER (segments are numbered super-block by super-block, and that order is what keeps the walkers that are
+// in flight together inside one L2-sized region).  Three small launches: items per 256-segment block,
+// exclusive scan of the block sums, write.
+__device__ __forceinline__ int block_excl_scan_256(int v, int* s_warp, int& total) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int incl = v;
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_up_sync(FULL, incl, d);
+    if (lane >= d) incl += t;
+  }
+  if (lane == 31) s_warp[wid] = incl;
+  __syncthreads();
+  int base = 0;
+  total = 0;
+  for (int w = 0; w < 8; w++) {
+    if (w < wid) base += s_warp[w];
+    total += s_warp[w];
+  }
+  __syncthreads();
+  return base + incl - v;
+}
+__global__ void __launch_bounds__(256) k_items_count(int nseg, int batch, const int* __restrict__ segcnt, int* __restrict__ blocksum) {
+  __shared__ int s_warp[8];
+  const int b = blockIdx.x * 256 + threadIdx.x;
+  const int c = b < nseg ? segcnt[b] : 0;
+  int total;
+  block_excl_scan_256((c + batch - 1) / batch, s_warp, total);
+  if (threadIdx.x == 0) blocksum[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(256) k_items_scan(int nblk, int* __restrict__ blocksum, int* __restrict__ nitems) {
+  __shared__ int s_warp[8];
+  int carry = 0;
+  for (int i0 = 0; i0 < nblk; i0 += 256) {
+    const int i = i0 + threadIdx.x;
+    const int v = i < nblk ? blocksum[i] : 0;
+    int total;
+    const int ex = block_excl_scan_256(v, s_warp, total);
+    if (i < nblk) blocksum[i] = carry + ex;
+    carry += total;
+  }
+  if (threadIdx.x == 0) *nitems = carry;
+}
+__global__ void __launch_bounds__(256) k_items_write(int nseg, int segcap, int batch, const int* __restrict__ segcnt,
+                                                     const int* __restrict__ blocksum, int2* __restrict__ items) {
+  __shared__ int s_warp[8];
+  const int b = blockIdx.x * 256 + threadIdx.x;
+  const int c = b < nseg ? segcnt[b] : 0;
+  const int k = (c + batch - 1) / batch;
+  int total;
+  const int base = blocksum[blockIdx.x] + block_excl_scan_256(k, s_warp, total);
+  for (int j = 0; j < k; j++) items[base + j] = make_int2(b * segcap + j * batch, min(batch, c - j * batch));
+}
+
+// rare long trajectories: path buffer in global memory (bigcap entries per walker)
+template <bool FIX>
+__global__ void __launch_bounds__(64) k_walk_big(const __grid_constant__ BaderParams P, const __grid_constant__ WalkArgs A,
+                                                 int count, int* __restrict__ scratch, int bigcap) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  const int start = A.list[t];
+  WState w;
+  walk_init(P, A.rho, w, start);
+  const SafeMap nosafe{nullptr, 0, 0, 0, 0, 0, 0, 0, 0};
+  int out = 0, st;
+  do st = walk_step<false>(P, A.rho, A.h, nosafe, w, scratch + (size_t)t * bigcap, bigcap, out); while (st == 0);
+  if (A.nsteps) atomicAdd(A.nsteps, (unsigned long long)w.len);
+  if (st == 3) { atomicExch(A.err, 2); return; }
+  walk_finish<FIX>(P, A, start, st, out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// classify: one thread per owned stride-s cube, one block per tile of 16 x 4 x 4 cubes.
+// uni[c] = common label of the cube's 8 corners (already labelled; the upper ones may sit on the
+// halo-above plane) if they agree and the cube holds no local maximum, else -1.  The new stride-s/2 points
+// of a non-uniform cube are queued for a walk; those of a uniform cube are filled (label | FILLBIT) unless
+// FILL is false (last level: k_fill_edge writes them).  The queue is SEGMENTED: block b owns
+// list[b*CLS_SEGCAP ..) and writes its count to segcnt[b], so that consecutive work items are spatially
+// compact (the walkers of a warp then share cache lines) and no global atomic is needed.
+// lbuf = label buffer including halos.
+// ------------------------------------------------------------------------------------------------
+constexpr int CLS_TX = 16, CLS_TY = 4, CLS_TZ = 4;
+constexpr int CLS_SEGCAP = 7 * 256;
+// Blocks (tiles) are numbered super-block by super-block (SB_X x SB_Y x SB_Z tiles = 128^3 points at the last
+// level) so that the walkers in flight at any time work on a compact 3D region that fits the L2 cache.
+constexpr int SB_X = 4, SB_Y = 16, SB_Z = 16;
+__host__ __device__ inline int cls_nblocks(int t1, int t2, int t3) {
+  return ((t1 + SB_X - 1) / SB_X) * ((t2 + SB_Y - 1) / SB_Y) * ((t3 + SB_Z - 1) / SB_Z) * (SB_X * SB_Y * SB_Z);
+}
+template <bool FILL>
+__global__ void __launch_bounds__(256) k_classify(int n1, int n2, int n3, const Slab S, int s, int* __restrict__ lbuf,
+                                                  const unsigned char* __restrict__ cubemax, int* __restrict__ uni,
+                                                  int* __restrict__ list, int* __restrict__ segcnt, int* __restrict__ ntotal) {
+  __shared__ unsigned char s_nu[256];   // cube is non-uniform: its new points walk
+  __shared__ int s_row[64];             // entries per row (iz, py) of the tile, then their exclusive prefix
+  const int c1 = (n1 + s - 1) / s, c2 = (n2 + s - 1) / s, c3 = (S.nzl + s - 1) / s;
+  const int t1 = (c1 + CLS_TX - 1) / CLS_TX, t2 = (c2 + CLS_TY - 1) / CLS_TY, t3 = (c3 + CLS_TZ - 1) / CLS_TZ;
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  int tx, ty, tz;
+  {
+    const int sb = b / (SB_X * SB_Y * SB_Z), w = b % (SB_X * SB_Y * SB_Z);
+    const int s1 = (t1 + SB_X - 1) / SB_X, s2 = (t2 + SB_Y - 1) / SB_Y;
+    tx = (sb % s1) * SB_X + w % SB_X;
+    ty = ((sb / s1) % s2) * SB_Y + (w / SB_X) % SB_Y;
+    tz = (sb / (s1 * s2)) * SB_Z + w / (SB_X * SB_Y);
+  }
+  if (tx >= t1 || ty >= t2 || tz >= t3) {  // padding block of a ragged super-block
+    if (tid == 0) segcnt[b] = 0;
+    return;
+  }
+  const int cx = tx * CLS_TX + (tid & 15), cy = ty * CLS_TY + ((tid >> 4) & 3), cz = tz * CLS_TZ + (tid >> 6);
+  const bool active = cx < c1 && cy < c2 && cz < c3;
+  const size_t s3 = (size_t)n1 * n2;
+  const int hh = s >> 1;
+  bool nonuni = false;
+  if (active) {
+    const size_t t = cx + (size_t)c1 * (cy + (size_t)c2 * cz);
+    const int x0 = cx * s, y0 = cy * s, z0 = S.zlo + cz * s;
+    const int x1 = (x0 + s < n1) ? x0 + s : 0, y1 = (y0 + s < n2) ? y0 + s : 0;
+    const size_t p0 = z0 - S.zlo + 1;                              // local plane of z0
+    const size_t p1 = ((z0 + s < n3) ? z0 + s : n3) - S.zlo + 1;   // local plane of the upper corners (may be the halo)
+    const int l000 = lbuf[x0 + n1 * y0 + s3 * p0] & LMASK;
+    bool u = !cubemax[t];
+    u = u && ((lbuf[x1 + n1 * y0 + s3 * p0] & LMASK) == l000);
+    u = u && ((lbuf[x0 + n1 * y1 + s3 * p0] & LMASK) == l000);
+    u = u && ((lbuf[x1 + n1 * y1 + s3 * p0] & LMASK) == l000);
+    u = u && ((lbuf[x0 + n1 * y0 + s3 * p1] & LMASK) == l000);
+    u = u && ((lbuf[x1 + n1 * y0 + s3 * p1] & LMASK) == l000);
+    u = u && ((lbuf[x0 + n1 * y1 + s3 * p1] & LMASK) == l000);
+    u = u && ((lbuf[x1 + n1 * y1 + s3 * p1] & LMASK) == l000);
+    uni[t] = u ? l000 : -1;
+    nonuni = !u;
+    if (FILL && u) {
+      for (int o = 1; o < 8; o++) {
+        const int x = x0 + ((o & 1) ? hh : 0), y = y0 + ((o & 2) ? hh : 0), z = z0 + ((o & 4) ? hh : 0);
+        if (x >= n1 || y >= n2 || z >= S.zhi) continue;
+        lbuf[x + n1 * y + s3 * (z - S.zlo + 1)] = (int)((unsigned)l000 | FILLBIT);
+      }
+    }
+  }
+  s_nu[tid] = nonuni ? 1 : 0;
+  __syncthreads();
+  // The new points of the non-uniform cubes are queued in memory order (z, y, x): the tile spans 32 x 8 x 8
+  // positions of the stride-s/2 lattice; warp w owns the rows py = w, lane = px.
+  const int px = lane, py = wid;
+  const int gx = (tx * CLS_TX * 2 + px) * hh, gy = (ty * CLS_TY * 2 + py) * hh;
+  unsigned mask[8];
+#pragma unroll
+  for (int iz = 0; iz < 8; iz++) {
+    const int gz = S.zlo + (tz * CLS_TZ * 2 + iz) * hh;
+    const bool wk = ((px | py | iz) & 1) && s_nu[(px >> 1) + 16 * ((py >> 1) + 4 * (iz >> 1))] && gx < n1 && gy < n2 && gz < S.zhi;
+    mask[iz] = __ballot_sync(FULL, wk);
+    if (lane == 0) s_row[iz * 8 + py] = __popc(mask[iz]);
+  }
+  __syncthreads();
+  if (wid == 0) {  // exclusive prefix over the 64 rows
+    int a0 = s_row[2 * lane], a1 = s_row[2 * lane + 1];
+    int incl = a0 + a1;
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v = __shfl_up_sync(FULL, incl, d);
+      if (lane >= d) incl += v;
+    }
+    const int excl = incl - a0 - a1;
+    s_row[2 * lane] = excl;
+    s_row[2 * lane + 1] = excl + a0;
+    if (lane == 31) {
+      segcnt[b] = incl;
+      if (incl) atomicAdd(ntotal, incl);
+    }
+  }
+  __syncthreads();
+  int* out = list + (size_t)b * CLS_SEGCAP;
+#pragma unroll
+  for (int iz = 0; iz < 8; iz++) {
+    if ((mask[iz] >> lane) & 1u) {
+      const int gz = S.zlo + (tz * CLS_TZ * 2 + iz) * hh;
+      out[s_row[iz * 8 + py] + __popc(mask[iz] & ((1u << lane) - 1u))] = gx + n1 * (gy + n2 * gz);
+    }
+  }
+}
+
+// safe[c] = uni[c] if the 26 neighbouring cubes (periodic in x,y; owned layers only in z) carry the same
+// uniform label, else -1.  z-marching separable "agree" stencil, one pass over the cube array.
+__global__ void __launch_bounds__(256) k_safe(int c1, int c2, int c3, const int* __restrict__ uni, int* __restrict__ safe) {
+  __shared__ int sbuf[2][(TY + 2) * 34];
+  const int tid = threadIdx.x, lx = tid & 31, ly = tid >> 5;
+  const int bx0 = blockIdx.x * 32, by0 = blockIdx.y * TY;
+  const int z0 = blockIdx.z * MZC, z1 = min(z0 + MZC, c3);
+  const int gx = bx0 + lx, gy = by0 + ly;
+  const bool valid = gx < c1 && gy < c2;
+  const size_t s3 = (size_t)c1 * c2;
+  const int* colp = uni + wrapx(gx, c1) + (size_t)c1 * wrapx(gy, c2);
+  int hslot = -1;
+  const int* hp = uni;
+  if (tid < NHALO) {
+    int hc, hr;
+    halo_decode(tid, hc, hr);
+    hslot = (hr + 1) * 34 + hc + 1;
+    hp = uni + wrapx(bx0 + hc, c1) + (size_t)c1 * wrapx(by0 + hr, c2);
+  }
+  int pm0 = -1, pm1 = -1;
+  for (int iz = z0 - 1; iz <= z1; iz++) {
+    const bool in = iz >= 0 && iz < c3;
+    const int v = in ? __ldg(colp + s3 * iz) : -1;
+    const int hv = (in && hslot >= 0) ? __ldg(hp + s3 * iz) : -1;
+    const int pm2 = plane3x3<int, OpAgree>(sbuf[(iz - z0 + 1) & 1], v, hslot, hv, lx, ly);
+    if (iz > z0 && valid) safe[gx + (size_t)c1 * gy + s3 * (iz - 1)] = OpAgree::c3(pm0, pm1, pm2);
+    pm0 = pm1; pm1 = pm2;
+  }
+}
+
+// octet certificate: vsafe[v] = common label of the 8 cubes {v-1, v}^3 that meet at cube-grid vertex v if
+// they are all uniform with the same label, else -1.  x, y wrap periodically when the grid dimension is a
+// multiple of the cube stride (px, py), otherwise the vertices next to the ragged last cube are unsafe;
+// z: owned layers only, wrapping (pz) on a single GPU.  One thread per (vx, vy) column, marching in z.
+__global__ void __launch_bounds__(256) k_vsafe(int c1, int c2, int c3, int px, int py, int pz, int zfull,
+                                               const int* __restrict__ uni, int* __restrict__ vsafe) {
+  const int vx = blockIdx.x * 32 + (threadIdx.x & 31), vy = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (vx >= c1 || vy >= c2) return;
+  const int z0 = blockIdx.z * MZC, z1 = min(z0 + MZC, c3);
+  const int xm = vx ? vx - 1 : c1 - 1, ym = vy ? vy - 1 : c2 - 1;
+  const bool okxy = (px || (vx > 0 && vx < c1 - 1)) && (py || (vy > 0 && vy < c2 - 1));
+  const size_t s3 = (size_t)c1 * c2;
+  auto layer = [&](int cz) -> int {  // agreement of the 2 x 2 cubes of layer cz
+    const int* pl = uni + s3 * cz;
+    const int a = __ldg(pl + xm + (size_t)c1 * ym), bq = __ldg(pl + vx + (size_t)c1 * ym);
+    const int c = __ldg(pl + xm + (size_t)c1 * vy), d = __ldg(pl + vx + (size_t)c1 * vy);
+    return (a == bq && c == d && a == c) ? a : -1;
+  };
+  int prev;
+  if (z0 > 0) prev = layer(z0 - 1);
+  else prev = pz ? layer(c3 - 1) : -1;
+  for (int vz = z0; vz < z1; vz++) {
+    const int cur = layer(vz);
+    const bool okz = (vz < c3 - 1) || zfull;  // the vertex below a ragged last layer is not certified
+    vsafe[vx + (size_t)c1 * vy + s3 * vz] = (okxy && okz && cur == prev) ? cur : -1;
+    prev = cur;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fill + edge detection, one streaming pass over the label planes [za, zb) of this rank.
+// RULE: the labels of the last level are materialised here -- a point that is not on the stride-2 lattice
+// and whose stride-2 cube is uniform gets uni2 | FILLBIT, every other point keeps what the walkers wrote.
+// Every FILLED point with a 26-neighbour of a different label (the refine_edge criterion, is_vol_edge
+// bader@proc.f90:730-752) loses FILLBIT and is queued for an exact walk.  Without RULE the labels are
+// read as they are (halo planes included) and only the edge test is done.
+// SEG: the queue is segmented, one segment of FE_SEGCAP entries per warp (a 32 x 1 x MZC sheet of points);
+// otherwise entries are appended to a flat list.
+// skip_lo/skip_hi: do not test the first/last owned plane (multi-GPU: their halos are not valid yet).
+// ------------------------------------------------------------------------------------------------
+constexpr int FE_SEGCAP = 32 * MZC;
+struct FillArgs {
+  int n1, n2, n3;
+  Slab S;
+  int* lbuf;
+  const int* uni2;
+  int c1, c2;      // stride-2 cube grid
+  int za, zb;      // global planes to process
+  int skip_lo, skip_hi;
+  int* list; int* nlist; int listcap; int* err;
+  int* segcnt;     // SEG only
+  int g1, g2, g3;  // blocks per axis (32 x TY x MZC points each); SEG: numbered super-block by super-block
+};
+constexpr int FSB_X = 4, FSB_Y = 16, FSB_Z = 4;  // super-block of 128^3 points
+__host__ __device__ inline int fe_nblocks(int g1, int g2, int g3) {
+  return ((g1 + FSB_X - 1) / FSB_X) * ((g2 + FSB_Y - 1) / FSB_Y) * ((g3 + FSB_Z - 1) / FSB_Z) * (FSB_X * FSB_Y * FSB_Z);
+}
+// label of point (x, y, gz) in two dependent loads that the caller issues one plane apart:
+//   fill_u  : the uniform label of the point's stride-2 cube if the fill rule applies to the point, else -1
+//   fill_lab: u | FILLBIT, or the label the walkers / earlier levels wrote
+template <bool RULE>
+__device__ __forceinline__ int fill_u(const FillArgs& A, int x, int y, int gz) {
+  if (!RULE) return -1;
+  bool owned = true;
+  if (A.S.periodic) gz = wrapx(gz, A.n3);
+  else owned = gz >= A.S.zlo && gz < A.S.zhi;
+  if (owned && ((x | y | (gz - A.S.zlo)) & 1))
+    return __ldg(A.uni2 + (x >> 1) + A.c1 * ((y >> 1) + (size_t)A.c2 * ((gz - A.S.zlo) >> 1)));
+  return -1;
+}
+__device__ __forceinline__ int fill_lab(const FillArgs& A, int x, int y, int gz, int u) {
+  if (u >= 0) return (int)((unsigned)u | FILLBIT);
+  const int pl = A.S.periodic ? wrapx(gz, A.n3) + 1 : gz - A.S.zlo + 1;
+  return A.lbuf[x + (size_t)A.n1 * y + (size_t)A.n1 * A.n2 * pl];
+}
+template <bool RULE, bool SEG>
+__global__ void __launch_bounds__(256) k_fill_edge(const __grid_constant__ FillArgs A) {
+  __shared__ int sbuf[2][(TY + 2) * 34];
+  __shared__ int s_total;
+  const int n1 = A.n1, n2 = A.n2;
+  const int tid = threadIdx.x, lx = tid & 31, ly = tid >> 5, lane = lx;
+  int bx, by, bz;
+  if (SEG) {
+    const int b = blockIdx.x;
+    const int sb = b / (FSB_X * FSB_Y * FSB_Z), w = b % (FSB_X * FSB_Y * FSB_Z);
+    const int s1 = (A.g1 + FSB_X - 1) / FSB_X, s2 = (A.g2 + FSB_Y - 1) / FSB_Y;
+    bx = (sb % s1) * FSB_X + w % FSB_X;
+    by = ((sb / s1) % s2) * FSB_Y + (w / FSB_X) % FSB_Y;
+    bz = (sb / (s1 * s2)) * FSB_Z + w / (FSB_X * FSB_Y);
+    if (bx >= A.g1 || by >= A.g2 || bz >= A.g3) {  // padding block of a ragged super-block
+      if (lane == 0) A.segcnt[(size_t)b * TY + ly] = 0;
+      return;
+    }
+  } else {
+    bx = blockIdx.x; by = blockIdx.y; bz = blockIdx.z;
+  }
+  const int bx0 = bx * 32, by0 = by * TY;
+  const int z0 = A.za + bz * MZC, z1 = min(z0 + MZC, A.zb);
+  const int gx = bx0 + lx, gy = by0 + ly;
+  const bool valid = gx < n1 && gy < n2;
+  const int wx = wrapx(gx, n1), wy = wrapx(gy, n2);
+  int hslot = -1, hx = 0, hy = 0;
+  if (tid < NHALO) {
+    int hc, hr;
+    halo_decode(tid, hc, hr);
+    hslot = (hr + 1) * 34 + hc + 1;
+    hx = wrapx(bx0 + hc, n1); hy = wrapx(by0 + hr, n2);
+  }
+  if (SEG && tid == 0) s_total = 0;
+  const size_t s3 = (size_t)n1 * n2;
+  const size_t seg = (size_t)blockIdx.x * TY + ly;  // SEG only
+  int* segout = A.list + seg * FE_SEGCAP;
+  int nseg = 0;  // warp-uniform: entries in this warp's segment
+  int pm0 = -1, pm1 = -1, own1 = 0;
+  // software pipeline: cube labels two planes ahead, point labels one plane ahead
+  int u_a = fill_u<RULE>(A, wx, wy, z0 - 1), hu_a = (hslot >= 0) ? fill_u<RULE>(A, hx, hy, z0 - 1) : -1;
+  int own_n = fill_lab(A, wx, wy, z0 - 1, u_a), hv_n = (hslot >= 0) ? fill_lab(A, hx, hy, z0 - 1, hu_a) : 0;
+  u_a = fill_u<RULE>(A, wx, wy, z0); hu_a = (hslot >= 0) ? fill_u<RULE>(A, hx, hy, z0) : -1;
+  for (int iz = z0 - 1; iz <= z1; iz++) {
+    const int own = own_n, hv = hv_n & LMASK;
+    if (iz < z1) {
+      own_n = fill_lab(A, wx, wy, iz + 1, u_a);
+      if (hslot >= 0) hv_n = fill_lab(A, hx, hy, iz + 1, hu_a);
+      if (iz + 1 < z1) {
+        u_a = fill_u<RULE>(A, wx, wy, iz + 2);
+        if (hslot >= 0) hu_a = fill_u<RULE>(A, hx, hy, iz + 2);
+      }
+    }
+    const int pm2 = plane3x3<int, OpAgree>(sbuf[(iz - z0 + 1) & 1], own & LMASK, hslot, hv, lx, ly);
+    if (iz > z0) {  // plane iz-1 is complete
+      const int gz = iz - 1;
+      const bool test = !((A.skip_lo && gz == A.S.zlo) || (A.skip_hi && gz == A.S.zhi - 1));
+      const bool filled = ((unsigned)own1 & FILLBIT) != 0;
+      const bool edge = valid && filled && test && OpAgree::c3(pm0, pm1, pm2) < 0;
+      const size_t off = gx + (size_t)n1 * gy + s3 * (gz - A.S.zlo + 1);
+      if (valid && (RULE ? (filled || edge) : edge)) A.lbuf[off] = edge ? (own1 & LMASK) : own1;
+      const unsigned m = __ballot_sync(FULL, edge);
+      if (m) {
+        const int rank = __popc(m & ((1u << lane) - 1u));
+        if (SEG) {
+          if (edge) segout[nseg + rank] = gx + n1 * (gy + n2 * gz);
+          nseg += __popc(m);
+        } else {
+          int base = 0;
+          if (lane == __ffs(m) - 1) base = atomicAdd(A.nlist, __popc(m));
+          base = __shfl_sync(FULL, base, __ffs(m) - 1);
+          if (edge) {
+            const int slot = base + rank;
+            if (slot < A.listcap) A.list[slot] = gx + n1 * (gy + n2 * gz);
+            else atomicExch(A.err, 4);
+          }
+        }
+      }
+    }
+    pm0 = pm1; pm1 = pm2; own1 = own;
+  }
+  if (SEG) {
+    if (lane == 0) {
+      A.segcnt[seg] = nseg;
+      if (nseg) atomicAdd(&s_total, nseg);
+    }
+    __syncthreads();
+    if (tid == 0 && s_total) atomicAdd(A.nlist, s_total);
+  }
+}
+
+// terminal candidate index -> output index (only needed when a candidate maximum was reached by no
+// trajectory, e.g. the twin of a two-point plateau); keeps FILLBIT
+__global__ void k_permute_labels(long long nn, int* __restrict__ label, const int* __restrict__ perm) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nn; i += stride) {
+    const int l = label[i];
+    label[i] = (int)((unsigned)perm[l & LMASK] | ((unsigned)l & FILLBIT));
   }
 }
 
@@ -564,14 +1012,9 @@ __global__ void __launch_bounds__(256) k_firstpoint(int n1, int n2, int n3, cons
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nn; i += stride) {
     const int x = (int)(i % n1), y = (int)((i / n1) % n2), z = S.zlo + (int)(i / ((long long)n1 * n2));
     const int key = (x * n2 + y) * n3 + z;
-    const int l = label[i];
+    const int l = label[i] & LMASK;
     if (key < first[l]) atomicMin(first + l, key);
   }
-}
-
-__global__ void k_permute_labels(long long nn, int* __restrict__ label, const int* __restrict__ perm) {
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nn; i += stride) label[i] = perm[label[i]];
 }
 
 #define C2G_NCCL(ctx, call)                                                                         \
@@ -612,12 +1055,20 @@ int exchange_halos(c2g_context* ctx, int* lbuf, size_t plane, const Slab& S, int
 
 }  // namespace
 
-// slab boundaries: multiples of 4, as even as possible
+// alignment of the interior slab boundaries = largest top lattice stride the slabs allow
+int c2g_slab_align(int n3, int nranks) {
+  int a = 32;
+  while (a > 4 && (long long)a * 2 * nranks > n3) a >>= 1;
+  return a;
+}
+
+// slab boundaries: multiples of c2g_slab_align, as even as possible
 void c2g_slab_bounds(int n3, int nranks, int rank, int* zlo, int* zhi) {
+  const int a = c2g_slab_align(n3, nranks);
   auto bound = [&](int r) -> int {
     if (r >= nranks) return n3;
     long long z = (long long)n3 * r / nranks;
-    z = (z + 2) / 4 * 4;
+    z = (z + a / 2) / a * a;
     if (z > n3) z = n3;
     return (int)z;
   };
@@ -649,7 +1100,19 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
   Slab S;
   c2g_slab_bounds(n3, G, ctx->rank, &S.zlo, &S.zhi);
   S.nzl = S.zhi - S.zlo;
+  S.periodic = (G == 1) ? 1 : 0;
   const long long nnl = (long long)plane * S.nzl;  // owned points
+
+  // top lattice stride: a power of two <= 32, small against the grid, compatible with the slab boundaries
+  int L0 = 4;
+  {
+    const int minn = std::min(n1, std::min(n2, n3));
+    while (L0 < 32 && L0 * 4 <= minn) L0 <<= 1;
+    if (G > 1) L0 = std::min(L0, c2g_slab_align(n3, G));
+    if (const char* e = getenv("C2G_BADER_L0")) { const int v = atoi(e); if (v == 4 || v == 8 || v == 16 || v == 32) L0 = std::min(L0, v); }
+  }
+  int nlev = 0;
+  for (int s = 2; s <= L0; s <<= 1) nlev++;
 
   c2g_basins* res = new c2g_basins();
   res->ctx = ctx; res->kind = 0; res->gridh = handle;
@@ -664,35 +1127,47 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
   res->d_label = lbuf + plane;                               // owned planes
   int* label_g = lbuf + plane - (long long)plane * S.zlo;    // label_g[global id] for owned points
 
+  // ---- per-level cube arrays (level i: stride 2<<i) ----
+  struct Level { int s, c1, c2, c3; size_t nc; };
+  Level lev[MAXLEV];
+  DevBuf b_cubemax[MAXLEV], b_uni[MAXLEV], b_safe[MAXLEV];
+  CubeFlags CF;
+  memset(&CF, 0, sizeof(CF));
+  CF.nlev = (algo == C2G_BADER_EXACT) ? 0 : nlev;
+  for (int i = 0; i < nlev && algo != C2G_BADER_EXACT; i++) {
+    const int s = 2 << i;
+    lev[i].s = s;
+    lev[i].c1 = (n1 + s - 1) / s; lev[i].c2 = (n2 + s - 1) / s; lev[i].c3 = (S.nzl + s - 1) / s;
+    lev[i].nc = std::max<size_t>(1, (size_t)lev[i].c1 * lev[i].c2 * lev[i].c3);
+    C2G_CUDA(ctx, b_cubemax[i].alloc(ctx, lev[i].nc));
+    C2G_CUDA(ctx, b_uni[i].alloc(ctx, sizeof(int) * lev[i].nc));
+    C2G_CUDA(ctx, b_safe[i].alloc(ctx, sizeof(int) * lev[i].nc));
+    CF.p[i] = b_cubemax[i].as<unsigned char>();
+    CF.c1[i] = lev[i].c1; CF.c2[i] = lev[i].c2;
+  }
+
   // ---- K0: candidate maxima of the slab ----
-  const int c41 = (n1 + 3) / 4, c42 = (n2 + 3) / 4, c43 = (S.nzl + 3) / 4;
-  const int c21 = (n1 + 1) / 2, c22 = (n2 + 1) / 2, c23 = (S.nzl + 1) / 2;
-  const size_t ncube4 = std::max<size_t>(1, (size_t)c41 * c42 * c43), ncube2 = std::max<size_t>(1, (size_t)c21 * c22 * c23);
-  DevBuf b_cube4, b_cube2, b_cand, b_cnt;
-  C2G_CUDA(ctx, b_cube4.alloc(ctx, ncube4));
-  C2G_CUDA(ctx, b_cube2.alloc(ctx, ncube2));
+  DevBuf b_cand, b_cnt;
   int maxcand = (int)std::max<long long>(1, std::min<long long>(nnl, std::max<long long>(1 << 16, nnl / 64)));
   C2G_CUDA(ctx, b_cnt.alloc(ctx, 64));
-  // counters: [0] ncand, [1] nlist, [2] noverflow, [3] err ; [4..5] nsteps (u64) ; [6] scratch for collectives
+  // counters: [0] ncand, [1] nlist, [2] noverflow, [3] err ; [4..5] nsteps (u64) ; [6] scratch for collectives,
+  //           [7] nnext ; [8..9] work cursor (u64) ; [10] number of work items
   int* cnt = b_cnt.as<int>();
   unsigned long long* nsteps = (unsigned long long*)(cnt + 4);
-  int hcnt[8];
+  unsigned long long* cursor = (unsigned long long*)(cnt + 8);
+  int hcnt[16];
   for (int attempt = 0;; attempt++) {
     C2G_CUDA(ctx, b_cand.alloc(ctx, sizeof(int) * (size_t)maxcand));
     C2G_CUDA(ctx, cudaMemsetAsync(cnt, 0, 64, st));
-    C2G_CUDA(ctx, cudaMemsetAsync(b_cube4.p, 0, ncube4, st));
-    C2G_CUDA(ctx, cudaMemsetAsync(b_cube2.p, 0, ncube2, st));
+    for (int i = 0; i < CF.nlev; i++) C2G_CUDA(ctx, cudaMemsetAsync(CF.p[i], 0, lev[i].nc, st));
     if (S.nzl > 0) {
-      dim3 grid((n1 + TX - 1) / TX, (n2 + TY - 1) / TY, (S.nzl + TZ - 1) / TZ);
-      const size_t smem = sizeof(double) * ((TZ + 2) * (TY + 2) * (TX + 2) + (TZ + 2) * (TY + 2) * TX);
-      C2G_CUDA(ctx, cudaFuncSetAttribute(k_maxima, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      dim3 grid((n1 + 31) / 32, (n2 + TY - 1) / TY, (S.nzl + MZC - 1) / MZC);
       ctx->prof_begin("bader_maxima");
-      k_maxima<<<grid, 256, smem, st>>>(P, S, g.d, b_cand.as<int>(), cnt, maxcand, b_cube4.as<unsigned char>(),
-                                        b_cube2.as<unsigned char>());
+      k_maxima<<<grid, 256, 0, st>>>(P, S, g.d, b_cand.as<int>(), cnt, maxcand, CF);
       ctx->prof_end();
       C2G_KERNEL_CHECK(ctx);
     }
-    C2G_CUDA(ctx, cudaMemcpyAsync(hcnt, cnt, 32, cudaMemcpyDeviceToHost, st));
+    C2G_CUDA(ctx, cudaMemcpyAsync(hcnt, cnt, 64, cudaMemcpyDeviceToHost, st));
     C2G_CUDA(ctx, cudaStreamSynchronize(st));
     if (hcnt[0] <= maxcand) break;
     if (attempt > 0) return ctx->fail(C2G_ERR_OVERFLOW, "candidate maxima list overflow");
@@ -751,168 +1226,313 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
   MaxHash h{b_hk.as<int>(), b_hv.as<int>(), hsize - 1};
   unsigned char* reached = b_reached.as<unsigned char>();
 
-  // work list / overflow list
-  DevBuf b_list, b_over;
+  // top stride actually used: small against the mean basin size (a cube certified by its 8 corners must not
+  // be wide enough for another basin to pass between them unseen)
+  if (algo != C2G_BADER_EXACT) {
+    const double bsize = std::cbrt((double)g.nn / (double)ncand);
+    int lmax = 4;
+    while (lmax < 32 && lmax * 2 * 6 <= bsize) lmax <<= 1;
+    if (getenv("C2G_BADER_L0") == nullptr) L0 = std::min(L0, lmax);
+    nlev = 0;
+    for (int s = 2; s <= L0; s <<= 1) nlev++;
+  }
+
+  // work lists: [0] segmented (classify levels, fill+edge), [1],[2] flat (edge-fix ping-pong); overflow list
+  DevBuf b_list[3], b_over, b_segcnt, b_items, b_blksum;
+  size_t itemcap = 0, blksumcap = 0;
+  size_t segints = 1, nsegmax = 1;
+  int fe_gx = (n1 + 31) / 32, fe_gy = (n2 + TY - 1) / TY, fe_gz = std::max(1, (S.nzl + MZC - 1) / MZC);
+  if (algo != C2G_BADER_EXACT) {
+    for (int i = 0; i < nlev; i++) {
+      const size_t nt = (size_t)cls_nblocks((lev[i].c1 + CLS_TX - 1) / CLS_TX, (lev[i].c2 + CLS_TY - 1) / CLS_TY,
+                                            std::max(1, (lev[i].c3 + CLS_TZ - 1) / CLS_TZ));
+      segints = std::max(segints, nt * CLS_SEGCAP);
+      nsegmax = std::max(nsegmax, nt);
+    }
+    const size_t nfe = (size_t)fe_nblocks(fe_gx, fe_gy, fe_gz) * TY;
+    segints = std::max(segints, nfe * FE_SEGCAP);
+    nsegmax = std::max(nsegmax, nfe);
+  }
   const long long listcap = (algo == C2G_BADER_EXACT) ? 1 : std::max<long long>(1, nnl);
-  C2G_CUDA(ctx, b_list.alloc(ctx, sizeof(int) * (size_t)listcap));
-  long long overcap = std::max<long long>(1024, nnl / 16);
+  C2G_CUDA(ctx, b_list[0].alloc(ctx, sizeof(int) * segints));
+  C2G_CUDA(ctx, b_segcnt.alloc(ctx, sizeof(int) * nsegmax));
+  C2G_CUDA(ctx, b_list[1].alloc(ctx, sizeof(int) * (size_t)listcap));
+  C2G_CUDA(ctx, b_list[2].alloc(ctx, sizeof(int) * (size_t)listcap));
+  const long long overcap = std::max<long long>(1024, nnl / 16);
   C2G_CUDA(ctx, b_over.alloc(ctx, sizeof(int) * (size_t)overcap));
-  int* list = b_list.as<int>();
-  int* over = b_over.as<int>();
   long long walked = 0, fixpts = 0, fixpasses = 0, noverflow_total = 0;
 
-  // handle walkers whose path buffer overflowed
-  auto drain_overflow = [&]() -> int {
-    C2G_CUDA(ctx, cudaMemcpyAsync(hcnt, cnt, 32, cudaMemcpyDeviceToHost, st));
+  WalkArgs WA;
+  memset(&WA, 0, sizeof(WA));
+  WA.rho = g.d; WA.label_g = label_g; WA.h = h; WA.reached = reached; WA.S = S;
+  WA.cursor = cursor; WA.overflow = b_over.as<int>(); WA.noverflow = cnt + 2; WA.overcap = (int)std::min<long long>(overcap, 0x7fffffff);
+  WA.err = cnt + 3; WA.nsteps = nsteps; WA.nnext = cnt + 7;
+  WA.refill_min = REFILL_MIN;
+  if (const char* e = getenv("C2G_REFILL_MIN")) WA.refill_min = std::max(1, std::min(32, atoi(e)));
+  int walk_occ = 4;  // resident 256-thread walker blocks per SM (4: <= 64 registers, 3: <= 80)
+  if (const char* e = getenv("C2G_WALK_OCC")) walk_occ = atoi(e) == 3 ? 3 : 4;
+  const int wblocks = ctx->nsm * walk_occ;
+
+  auto check_err = [&]() -> int {
+    switch (hcnt[3]) {
+      case 0: return C2G_OK;
+      case 1: return ctx->fail(C2G_ERR_NEWMAX, "bader walk ended on a point that is not a local maximum");
+      case 2: return ctx->fail(C2G_ERR_OVERFLOW, "trajectory longer than the scratch path buffer");
+      case 3: return ctx->fail(C2G_ERR_OVERFLOW, "too many long trajectories");
+      default: return ctx->fail(C2G_ERR_OVERFLOW, "work list overflow");
+    }
+  };
+  // read the counters; re-walk the trajectories whose path buffer overflowed
+  auto drain = [&](bool fix) -> int {
+    C2G_CUDA(ctx, cudaMemcpyAsync(hcnt, cnt, 64, cudaMemcpyDeviceToHost, st));
     C2G_CUDA(ctx, cudaStreamSynchronize(st));
-    if (hcnt[3] == 1) return ctx->fail(C2G_ERR_NEWMAX, "bader walk ended on a point that is not a local maximum");
+    int rc = check_err();
+    if (rc) return rc;
     const int nov = hcnt[2];
     if (nov == 0) return C2G_OK;
-    if (nov > overcap) return ctx->fail(C2G_ERR_OVERFLOW, "too many long trajectories (%d)", nov);
     noverflow_total += nov;
     const int bigcap = (int)std::min<long long>(g.nn, 1 << 22);
     const int chunk = (int)std::max<long long>(1, std::min<long long>(nov, (1ll << 31) / bigcap));  // <= 8 GiB scratch
     DevBuf b_scr;
     C2G_CUDA(ctx, b_scr.alloc(ctx, sizeof(int) * (size_t)chunk * bigcap));
+    WalkArgs W2 = WA;
+    W2.items = nullptr;
     for (int off = 0; off < nov; off += chunk) {
       const int c = std::min(chunk, nov - off);
+      W2.list = b_over.as<int>() + off;
       ctx->prof_begin("bader_walk_big");
-      k_walk_big<<<c2g_blocks_for(c, 64), 64, 0, st>>>(P, g.d, over + off, c, label_g, h, reached, b_scr.as<int>(), bigcap,
-                                                       cnt + 3, nsteps);
+      if (fix) k_walk_big<true><<<c2g_blocks_for(c, 64), 64, 0, st>>>(P, W2, c, b_scr.as<int>(), bigcap);
+      else k_walk_big<false><<<c2g_blocks_for(c, 64), 64, 0, st>>>(P, W2, c, b_scr.as<int>(), bigcap);
       ctx->prof_end();
       C2G_KERNEL_CHECK(ctx);
     }
     C2G_CUDA(ctx, cudaMemsetAsync(cnt + 2, 0, sizeof(int), st));
-    C2G_CUDA(ctx, cudaMemcpyAsync(hcnt, cnt, 32, cudaMemcpyDeviceToHost, st));
+    C2G_CUDA(ctx, cudaMemcpyAsync(hcnt, cnt, 64, cudaMemcpyDeviceToHost, st));
     C2G_CUDA(ctx, cudaStreamSynchronize(st));
-    if (hcnt[3] == 2) return ctx->fail(C2G_ERR_OVERFLOW, "trajectory longer than %d steps", bigcap);
-    if (hcnt[3] == 1) return ctx->fail(C2G_ERR_NEWMAX, "bader walk ended on a point that is not a local maximum");
-    return C2G_OK;
+    hcnt[2] = 0;
+    return check_err();
   };
-  auto grow_over = [&](long long need) -> int {
-    if (need > overcap) {
-      b_over.reset();
-      overcap = need;
-      C2G_CUDA(ctx, b_over.alloc(ctx, sizeof(int) * (size_t)overcap));
-      over = b_over.as<int>();
-    }
-    return C2G_OK;
-  };
-  SafeMap cursafe{nullptr, 0, 0, 0, 0, 0};
-  auto walk_list = [&](int count, const char* name) -> int {
+  // launch the persistent walkers.  Sources: a flat list / lattice of `count` items (list == nullptr: the
+  // stride-lat_s lattice of the slab), or a segmented list (segcnt != nullptr; count = total, for statistics).
+  auto walk = [&](const int* list, long long count, int lat_s, const int* segcnt, int nseg, int segcap, bool fix, int* next,
+                  const SafeMap& sm, const char* name) -> int {
     if (count <= 0) return C2G_OK;
-    int rc = grow_over(count);
-    if (rc) return rc;
+    WA.list = list; WA.count = count; WA.sm = sm;
+    WA.items = nullptr; WA.nitems = 0;
+    if (segcnt) {  // work items of 32 or 64 consecutive entries of one segment
+      const int batch = count < 64ll * wblocks * 8 ? 32 : 64;
+      const size_t maxitems = (size_t)nseg + (size_t)(count / batch) + 1;
+      if (maxitems > itemcap) {
+        itemcap = maxitems + maxitems / 4;
+        C2G_CUDA(ctx, b_items.alloc(ctx, sizeof(int2) * itemcap));
+      }
+      const int nblk = c2g_blocks_for(nseg, 256);
+      if ((size_t)nblk > blksumcap) {
+        blksumcap = (size_t)nblk;
+        C2G_CUDA(ctx, b_blksum.alloc(ctx, sizeof(int) * blksumcap));
+      }
+      k_items_count<<<nblk, 256, 0, st>>>(nseg, batch, segcnt, b_blksum.as<int>());
+      k_items_scan<<<1, 256, 0, st>>>(nblk, b_blksum.as<int>(), cnt + 10);
+      k_items_write<<<nblk, 256, 0, st>>>(nseg, segcap, batch, segcnt, b_blksum.as<int>(), b_items.as<int2>());
+      C2G_KERNEL_CHECK(ctx);
+      ctx->launches += 3;
+      WA.items = b_items.as<int2>();
+      WA.nitems = (int)std::min<size_t>(maxitems, 0x7fffffff);
+      WA.nitems_dev = cnt + 10;
+    }
+    WA.lat_s = lat_s; WA.lat_m1 = (n1 + lat_s - 1) / lat_s; WA.lat_m2 = (n2 + lat_s - 1) / lat_s;
+    WA.next = next; WA.nextcap = (int)std::min<long long>(listcap, 0x7fffffff);
+    const long long nwarps = (long long)wblocks * 8;
+    WA.batch = (int)std::max<long long>(32, std::min<long long>(256, count / (nwarps * 4) / 32 * 32));
+    C2G_CUDA(ctx, cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), st));
+    const int blocks = (int)std::min<long long>(wblocks, (count + 255) / 256);
     ctx->prof_begin(name);
-    if (ortho)
-      k_walk_list<true><<<c2g_blocks_for(count, 128), 128, 0, st>>>(P, g.d, list, count, label_g, h, cursafe, reached, over, cnt + 2,
-                                                                    cnt + 3, algo == C2G_BADER_EXACT ? nsteps : nullptr);
-    else
-      k_walk_list<false><<<c2g_blocks_for(count, 128), 128, 0, st>>>(P, g.d, list, count, label_g, h, cursafe, reached, over, cnt + 2,
-                                                                     cnt + 3, algo == C2G_BADER_EXACT ? nsteps : nullptr);
+    if (walk_occ == 4) {
+      if (ortho) {
+        if (fix) k_walk<true, true, 4><<<blocks, 256, 0, st>>>(P, WA);
+        else k_walk<true, false, 4><<<blocks, 256, 0, st>>>(P, WA);
+      } else {
+        if (fix) k_walk<false, true, 4><<<blocks, 256, 0, st>>>(P, WA);
+        else k_walk<false, false, 4><<<blocks, 256, 0, st>>>(P, WA);
+      }
+    } else {
+      if (ortho) {
+        if (fix) k_walk<true, true, 3><<<blocks, 256, 0, st>>>(P, WA);
+        else k_walk<true, false, 3><<<blocks, 256, 0, st>>>(P, WA);
+      } else {
+        if (fix) k_walk<false, true, 3><<<blocks, 256, 0, st>>>(P, WA);
+        else k_walk<false, false, 3><<<blocks, 256, 0, st>>>(P, WA);
+      }
+    }
     ctx->prof_end();
     C2G_KERNEL_CHECK(ctx);
     walked += count;
-    return drain_overflow();
+    return C2G_OK;
   };
-  auto walk_lattice = [&](int s, const char* name) -> int {
-    const int m1 = (n1 + s - 1) / s, m2 = (n2 + s - 1) / s, m3 = (S.nzl + s - 1) / s;
-    const long long m = (long long)m1 * m2 * m3;
-    if (m == 0) return C2G_OK;
-    int rc = grow_over(m);
-    if (rc) return rc;
-    ctx->prof_begin(name);
-    if (ortho)
-      k_walk_lattice<true><<<c2g_blocks_for(m, 128), 128, 0, st>>>(P, S, g.d, s, m1, m2, m3, label_g, h, reached, over, cnt + 2,
-                                                                   cnt + 3, algo == C2G_BADER_EXACT ? nsteps : nullptr);
-    else
-      k_walk_lattice<false><<<c2g_blocks_for(m, 128), 128, 0, st>>>(P, S, g.d, s, m1, m2, m3, label_g, h, reached, over, cnt + 2,
-                                                                    cnt + 3, algo == C2G_BADER_EXACT ? nsteps : nullptr);
-    ctx->prof_end();
-    C2G_KERNEL_CHECK(ctx);
-    walked += m;
-    return drain_overflow();
-  };
+  const SafeMap nosafe{nullptr, 0, 0, 0, 0, 0, 0, 0, 0};
 
   int rc;
   if (algo == C2G_BADER_EXACT) {
-    if ((rc = walk_lattice(1, "bader_walk_all")) != C2G_OK) return rc;
+    if ((rc = walk(nullptr, nnl, 1, nullptr, 0, 0, false, nullptr, nosafe, "bader_walk_all")) != C2G_OK) return rc;
+    if ((rc = drain(false)) != C2G_OK) return rc;
   } else {
-    // level 0: stride-4 lattice
-    if ((rc = walk_lattice(4, "bader_walk_l4")) != C2G_OK) return rc;
-    // levels 4 -> 2 -> 1
-    DevBuf b_uni(ctx), b_safe(ctx);
+    // top level: the stride-L0 lattice walks complete trajectories
+    {
+      const long long m = (long long)((n1 + L0 - 1) / L0) * ((n2 + L0 - 1) / L0) * ((S.nzl + L0 - 1) / L0);
+      if ((rc = walk(nullptr, m, L0, nullptr, 0, 0, false, nullptr, nosafe, "bader_walk_top")) != C2G_OK) return rc;
+      if ((rc = drain(false)) != C2G_OK) return rc;
+    }
+    const long long ntop = walked;
     const bool use_safe = getenv("C2G_NO_EARLY_STOP") == nullptr;
-    for (int s = 4; s >= 2; s >>= 1) {
+    // Early stops are only allowed in cubes of stride <= 4: a coarser "uniform" cube is certified by corners
+    // that are far apart, which is good enough for a fill (every filled point is re-examined by the edge
+    // fix) but not for a walked label (never re-examined).
+    int safe_maxs = 4;
+    if (const char* e = getenv("C2G_SAFE_MAXS")) safe_maxs = atoi(e);
+    // certificate: 2 = cube + 26 neighbour cubes (uniform 5x5x5 point neighbourhood, the margin at which the
+    // reference's refine_edge walks stop); 1 = octet (3x3x3) -- fewer steps, but it has produced wrong labels
+    // when it rested on a wrong fill (tests/cases.py odd_dims: 11 of 143350 points), so it is opt-in.
+    int cert = 2;
+    if (const char* e = getenv("C2G_CERT")) cert = atoi(e);
+    const bool verbose = getenv("C2G_BADER_VERBOSE") != nullptr;
+    unsigned long long steps_prev = 0;
+    auto report = [&](const char* what, long long count) {
+      if (!verbose) return;
+      unsigned long long sn = 0;
+      memcpy(&sn, hcnt + 4, sizeof(sn));
+      fprintf(stderr, "[c2g bader] %-16s walkers %12lld steps %14llu (%.2f/walker)\n", what, count, sn - steps_prev,
+              count ? (double)(sn - steps_prev) / count : 0.0);
+      steps_prev = sn;
+    };
+    report("bader_walk_top", ntop);
+    static const char* wname[MAXLEV] = {"bader_walk_l1", "bader_walk_l2", "bader_walk_l4", "bader_walk_l8", "bader_walk_l16"};
+    int* seglist = b_list[0].as<int>();
+    int* segcnt = b_segcnt.as<int>();
+    SafeMap fixsafe = nosafe;
+    for (int i = nlev - 1; i >= 0; i--) {
+      const Level& L = lev[i];
       if ((rc = exchange_halos(ctx, lbuf, plane, S, 1)) != C2G_OK) return rc;
-      const int c1 = (n1 + s - 1) / s, c2 = (n2 + s - 1) / s, c3 = (S.nzl + s - 1) / s;
-      const long long nc = (long long)c1 * c2 * c3;
       C2G_CUDA(ctx, cudaMemsetAsync(cnt + 1, 0, sizeof(int), st));
-      cursafe.safe = nullptr;
-      if (nc > 0) {
-        C2G_CUDA(ctx, b_uni.alloc(ctx, sizeof(int) * (size_t)nc));
-        C2G_CUDA(ctx, b_safe.alloc(ctx, sizeof(int) * (size_t)nc));
-        ctx->prof_begin(s == 4 ? "bader_classify4" : "bader_classify2");
-        k_classify<<<c2g_blocks_for(nc, 256), 256, 0, st>>>(n1, n2, n3, S, s, lbuf,
-                                                            s == 4 ? b_cube4.as<unsigned char>() : b_cube2.as<unsigned char>(),
-                                                            b_uni.as<int>(), list, cnt + 1);
+      SafeMap sm = nosafe;
+      const int t1 = (L.c1 + CLS_TX - 1) / CLS_TX, t2 = (L.c2 + CLS_TY - 1) / CLS_TY, t3 = (L.c3 + CLS_TZ - 1) / CLS_TZ;
+      const int ntile = cls_nblocks(t1, t2, std::max(1, t3));
+      if (nnl > 0) {
+        ctx->prof_begin(i == 0 ? "bader_classify2" : "bader_classify");
+        if (i == 0)
+          k_classify<false><<<ntile, 256, 0, st>>>(n1, n2, n3, S, L.s, lbuf, b_cubemax[i].as<unsigned char>(), b_uni[i].as<int>(),
+                                                   seglist, segcnt, cnt + 1);
+        else
+          k_classify<true><<<ntile, 256, 0, st>>>(n1, n2, n3, S, L.s, lbuf, b_cubemax[i].as<unsigned char>(), b_uni[i].as<int>(),
+                                                  seglist, segcnt, cnt + 1);
         ctx->prof_end();
         C2G_KERNEL_CHECK(ctx);
-        if (use_safe) {
-          ctx->prof_begin(s == 4 ? "bader_safe4" : "bader_safe2");
-          k_safe<<<c2g_blocks_for(nc, 256), 256, 0, st>>>(c1, c2, c3, b_uni.as<int>(), b_safe.as<int>());
+        if (use_safe && L.s <= safe_maxs) {
+          const dim3 sg((L.c1 + 31) / 32, (L.c2 + TY - 1) / TY, (L.c3 + MZC - 1) / MZC);
+          ctx->prof_begin(i == 0 ? "bader_safe2" : "bader_safe");
+          if (cert == 1) {
+            const int px = (n1 % L.s) == 0, py = (n2 % L.s) == 0;
+            const int pz = (S.periodic && (n3 % L.s) == 0) ? 1 : 0;
+            k_vsafe<<<sg, 256, 0, st>>>(L.c1, L.c2, L.c3, px, py, pz, (S.nzl % L.s) == 0 ? 1 : 0, b_uni[i].as<int>(), b_safe[i].as<int>());
+            sm = SafeMap{b_safe[i].as<int>(), i + 1, L.c1, L.c2, L.c3, S.zlo, S.nzl, 1, pz};
+          } else {
+            k_safe<<<sg, 256, 0, st>>>(L.c1, L.c2, L.c3, b_uni[i].as<int>(), b_safe[i].as<int>());
+            sm = SafeMap{b_safe[i].as<int>(), i + 1, L.c1, L.c2, L.c3, S.zlo, S.nzl, 0, 0};
+          }
           ctx->prof_end();
           C2G_KERNEL_CHECK(ctx);
-          cursafe = SafeMap{b_safe.as<int>(), s == 4 ? 2 : 1, c1, c2, S.zlo, S.nzl};
+          if (i == 0) fixsafe = sm;
         }
       }
-      C2G_CUDA(ctx, cudaMemcpyAsync(hcnt, cnt, 32, cudaMemcpyDeviceToHost, st));
+      C2G_CUDA(ctx, cudaMemcpyAsync(hcnt, cnt, 64, cudaMemcpyDeviceToHost, st));
       C2G_CUDA(ctx, cudaStreamSynchronize(st));
-      if ((rc = walk_list(hcnt[1], s == 4 ? "bader_walk_l2" : "bader_walk_l1")) != C2G_OK) return rc;
+      const long long nw = hcnt[1];
+      if ((rc = walk(seglist, nw, 1, segcnt, ntile, CLS_SEGCAP, false, nullptr, sm, wname[i])) != C2G_OK) return rc;
+      if ((rc = drain(false)) != C2G_OK) return rc;
+      report(wname[i], nw);
     }
-    // edge fix until no filled point (on any rank) is adjacent to a different label.  After the first
-    // pass only the tiles within one cell of a re-walked point (plus the slab's face layers, whose
-    // halos may have changed on another rank) are looked at again.
-    DevBuf b_dirty[2] = {DevBuf(ctx), DevBuf(ctx)};
-    const dim3 egrid((n1 + TX - 1) / TX, (n2 + TY - 1) / TY, std::max(1, (S.nzl + TZ - 1) / TZ));
-    const size_t ntiles = (size_t)egrid.x * egrid.y * egrid.z;
-    C2G_CUDA(ctx, b_dirty[0].alloc(ctx, ntiles));
-    C2G_CUDA(ctx, b_dirty[1].alloc(ctx, ntiles));
-    for (;;) {
+    // ---- materialise the last level and find the filled points with a foreign 26-neighbour ----
+    FillArgs FA;
+    memset(&FA, 0, sizeof(FA));
+    FA.n1 = n1; FA.n2 = n2; FA.n3 = n3; FA.S = S; FA.lbuf = lbuf; FA.uni2 = b_uni[0].as<int>();
+    FA.c1 = lev[0].c1; FA.c2 = lev[0].c2; FA.err = cnt + 3;
+    FA.listcap = (int)std::min<long long>(listcap, 0x7fffffff);
+    FA.segcnt = segcnt;
+    C2G_CUDA(ctx, cudaMemsetAsync(cnt + 1, 0, sizeof(int), st));   // [1] segmented edge points of the first pass
+    C2G_CUDA(ctx, cudaMemsetAsync(cnt + 7, 0, sizeof(int), st));   // [7] flat list being built
+    auto edge_faces = [&](int* out, int* nout) -> int {  // multi-GPU: the two face planes against fresh halos
+      FillArgs FB = FA;
+      FB.list = out; FB.nlist = nout; FB.skip_lo = FB.skip_hi = 0;
+      const dim3 eg(fe_gx, fe_gy, 1);
+      ctx->prof_begin("bader_edge_faces");
+      FB.za = S.zlo; FB.zb = S.zlo + 1;
+      k_fill_edge<false, false><<<eg, 256, 0, st>>>(FB);
+      if (S.nzl > 1) {
+        FB.za = S.zhi - 1; FB.zb = S.zhi;
+        k_fill_edge<false, false><<<eg, 256, 0, st>>>(FB);
+      }
+      ctx->prof_end(S.nzl > 1 ? 2 : 1);
+      C2G_KERNEL_CHECK(ctx);
+      return C2G_OK;
+    };
+    int cur = 1;  // flat list being consumed next; the other one receives the claims
+    const int nfeblk = fe_nblocks(fe_gx, fe_gy, fe_gz);
+    const int nfeseg = nfeblk * TY;
+    FA.g1 = fe_gx; FA.g2 = fe_gy; FA.g3 = fe_gz;
+    if (nnl > 0) {
+      FA.list = seglist; FA.nlist = cnt + 1;
+      FA.za = S.zlo; FA.zb = S.zhi; FA.skip_lo = FA.skip_hi = (G > 1) ? 1 : 0;
+      ctx->prof_begin("bader_fill_edge");
+      k_fill_edge<true, true><<<nfeblk, 256, 0, st>>>(FA);
+      ctx->prof_end();
+      C2G_KERNEL_CHECK(ctx);
+    }
+    if (G > 1) {
       if ((rc = exchange_halos(ctx, lbuf, plane, S, 3)) != C2G_OK) return rc;
-      C2G_CUDA(ctx, cudaMemsetAsync(cnt + 1, 0, sizeof(int), st));
-      unsigned char* din = fixpasses == 0 ? nullptr : b_dirty[fixpasses & 1].as<unsigned char>();
-      unsigned char* dout = b_dirty[(fixpasses + 1) & 1].as<unsigned char>();
-      C2G_CUDA(ctx, cudaMemsetAsync(dout, 0, ntiles, st));
-      // face layers are always rechecked
-      C2G_CUDA(ctx, cudaMemsetAsync(dout, 1, (size_t)egrid.x * egrid.y, st));
-      C2G_CUDA(ctx, cudaMemsetAsync(dout + (size_t)egrid.x * egrid.y * (egrid.z - 1), 1, (size_t)egrid.x * egrid.y, st));
-      if (S.nzl > 0) {
-        ctx->prof_begin("bader_edgefix");
-        k_edgefix<<<egrid, 256, 0, st>>>(n1, n2, S, lbuf, list, cnt + 1, din, dout);
-        ctx->prof_end();
-        C2G_KERNEL_CHECK(ctx);
-      }
-      if (G > 1) {
-        C2G_CUDA(ctx, cudaMemcpyAsync(cnt + 6, cnt + 1, sizeof(int), cudaMemcpyDeviceToDevice, st));
-        C2G_NCCL(ctx, ncclAllReduce(cnt + 6, cnt + 6, 1, ncclInt32, ncclMax, comm, st));
-      }
-      C2G_CUDA(ctx, cudaMemcpyAsync(hcnt, cnt, 32, cudaMemcpyDeviceToHost, st));
+      if (nnl > 0 && (rc = edge_faces(b_list[cur].as<int>(), cnt + 7)) != C2G_OK) return rc;
+    }
+    // ---- edge fix until no filled point (on any rank) is adjacent to a different label ----
+    // pass 1 consumes the segmented list (+ the face points, multi-GPU); every pass writes the filled
+    // neighbours of the points that changed into the other flat list, which the next pass consumes.
+    bool first = true;
+    for (;;) {
+      C2G_CUDA(ctx, cudaMemcpyAsync(hcnt, cnt, 64, cudaMemcpyDeviceToHost, st));
       C2G_CUDA(ctx, cudaStreamSynchronize(st));
+      if ((rc = check_err()) != C2G_OK) return rc;
+      const int nseg1 = first ? hcnt[1] : 0, nflat = hcnt[7];
+      int any = nseg1 + nflat > 0 ? 1 : 0;
+      if (G > 1) {
+        C2G_CUDA(ctx, cudaMemcpyAsync(cnt + 6, &any, sizeof(int), cudaMemcpyHostToDevice, st));
+        C2G_NCCL(ctx, ncclAllReduce(cnt + 6, cnt + 6, 1, ncclInt32, ncclMax, comm, st));
+        C2G_CUDA(ctx, cudaMemcpyAsync(&any, cnt + 6, sizeof(int), cudaMemcpyDeviceToHost, st));
+        C2G_CUDA(ctx, cudaStreamSynchronize(st));
+      }
       fixpasses++;
-      const int any = (G > 1) ? hcnt[6] : hcnt[1];
       if (any == 0) break;
-      fixpts += hcnt[1];
-      if ((rc = walk_list(hcnt[1], "bader_walk_fix")) != C2G_OK) return rc;
-      if (fixpasses > 1000) return ctx->fail(C2G_ERR_STATE, "edge refinement did not converge");
+      fixpts += nseg1 + nflat;
+      int* in = b_list[cur].as<int>();
+      int* out = b_list[cur == 1 ? 2 : 1].as<int>();
+      C2G_CUDA(ctx, cudaMemsetAsync(cnt + 7, 0, sizeof(int), st));
+      if (nseg1 && (rc = walk(seglist, nseg1, 1, segcnt, nfeseg, FE_SEGCAP, true, out, fixsafe, "bader_walk_fix")) != C2G_OK) return rc;
+      if (nflat && (rc = walk(in, nflat, 1, nullptr, 0, 0, true, out, fixsafe, "bader_walk_fix")) != C2G_OK) return rc;
+      if ((rc = drain(true)) != C2G_OK) return rc;
+      report("bader_walk_fix", nseg1 + nflat);
+      if (G > 1) {
+        if ((rc = exchange_halos(ctx, lbuf, plane, S, 3)) != C2G_OK) return rc;
+        if (nnl > 0 && (rc = edge_faces(out, cnt + 7)) != C2G_OK) return rc;
+      }
+      cur = (cur == 1) ? 2 : 1;
+      first = false;
+      if (fixpasses > 100000) return ctx->fail(C2G_ERR_STATE, "edge refinement did not converge");
     }
   }
 
-  // ---- maxima actually reached (on any rank), output order, compaction ----
+  // ---- maxima actually reached (on any rank), output order ----
   if (G > 1) C2G_NCCL(ctx, ncclAllReduce(reached, reached, ncand, ncclUint8, ncclMax, comm, st));
   std::vector<unsigned char> hreached(ncand);
   C2G_CUDA(ctx, cudaMemcpyAsync(hreached.data(), reached, ncand, cudaMemcpyDeviceToHost, st));
+  C2G_CUDA(ctx, cudaMemcpyAsync(hcnt, cnt, 64, cudaMemcpyDeviceToHost, st));
   C2G_CUDA(ctx, cudaStreamSynchronize(st));
+  if ((rc = check_err()) != C2G_OK) return rc;
   std::vector<int> cand2out(ncand, -1);
   int nmax = 0;
   for (int i = 0; i < ncand; i++)
@@ -921,19 +1541,17 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
   res->max_lin.resize(nmax);
   for (int i = 0; i < ncand; i++)
     if (cand2out[i] >= 0) res->max_lin[cand2out[i]] = cand[i];
-  DevBuf b_c2o;
-  C2G_CUDA(ctx, b_c2o.alloc(ctx, sizeof(int) * ncand));
-  C2G_CUDA(ctx, cudaMemcpyAsync(b_c2o.p, cand2out.data(), sizeof(int) * ncand, cudaMemcpyHostToDevice, st));
   const int nblk = ctx->nsm * 8;
-  if (nnl > 0) {
+  if (nmax < ncand && nnl > 0) {  // rare: a candidate no trajectory ends on; renumber
+    DevBuf b_c2o;
+    C2G_CUDA(ctx, b_c2o.alloc(ctx, sizeof(int) * ncand));
+    C2G_CUDA(ctx, cudaMemcpyAsync(b_c2o.p, cand2out.data(), sizeof(int) * ncand, cudaMemcpyHostToDevice, st));
     ctx->prof_begin("bader_compact");
-    k_compact<<<nblk, 256, 0, st>>>(nnl, res->d_label, h, b_c2o.as<int>(), cnt + 3);
+    k_permute_labels<<<nblk, 256, 0, st>>>(nnl, res->d_label, b_c2o.as<int>());
     ctx->prof_end();
     C2G_KERNEL_CHECK(ctx);
+    C2G_CUDA(ctx, cudaStreamSynchronize(st));
   }
-  C2G_CUDA(ctx, cudaMemcpyAsync(hcnt, cnt, 32, cudaMemcpyDeviceToHost, st));
-  C2G_CUDA(ctx, cudaStreamSynchronize(st));
-  if (hcnt[3] != 0) return ctx->fail(C2G_ERR_NEWMAX, "label compaction found a terminal that is not a known maximum");
 
   if (order == C2G_ORDER_SCAN && nmax > 1) {
     DevBuf b_first, b_perm;
@@ -973,6 +1591,7 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
   res->stats[3] = noverflow_total;
   res->stats[4] = ncand;
   res->stats[5] = (long long)hsteps;
+  res->stats[6] = L0;
   ctx->prof_collect();
   guard.ok = true;
   *nmax_out = nmax;

@@ -39,10 +39,10 @@ __global__ void k_flush(float4* buf, size_t n4) {
 
 // labels (index into maxima list, or <0) -> basin ids through map
 __global__ void k_map_labels(long long nn, const int* __restrict__ label, const int* __restrict__ map,
-                             int* __restrict__ out) {
+                             int* __restrict__ out, int mask) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nn; i += stride) {
-    const int l = label[i];
+    const int l = label[i] & mask;  // Bader labels carry a flag in bit 31; YT uses -1 for IAS points
     out[i] = (l >= 0) ? __ldg(map + l) : 0;
   }
 }
@@ -492,7 +492,7 @@ int c2g_basins_labels(c2g_basins* res, int* idg) {
   int* d_out = nullptr;
   C2G_CUDA(ctx, c2g_alloc(ctx, (void**)&d_out, sizeof(int) * nnl));
   ctx->prof_begin("map_labels");
-  k_map_labels<<<ctx->nsm * 8, 256, 0, ctx->stream>>>(nnl, res->d_label, res->d_map, d_out);
+  k_map_labels<<<ctx->nsm * 8, 256, 0, ctx->stream>>>(nnl, res->d_label, res->d_map, d_out, res->kind == 0 ? 0x7fffffff : -1);
   ctx->prof_end();
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpyAsync(idg, d_out, sizeof(int) * nnl, cudaMemcpyDeviceToHost, ctx->stream);

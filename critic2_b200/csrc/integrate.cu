@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256) k_basin_reduce(long long nn, const int* _
     {
       const long long i = base + lane;
       if (i < nn) {
-        l_next = label[i];
+        l_next = label[i] & 0x7fffffff;  // bit 31 = filled-not-walked flag of bader.cu
 #pragma unroll
         for (int p = 0; p < NP; p++) v_next[p] = __ldg(fp[p] + i);
       }
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(256) k_basin_reduce(long long nn, const int* _
       if (k + 1 < SEG_ITERS) {
         const long long i = base + 32ll * (k + 1) + lane;
         if (i < nn) {
-          l_next = label[i];
+          l_next = label[i] & 0x7fffffff;
 #pragma unroll
           for (int p = 0; p < NP; p++) v_next[p] = __ldg(fp[p] + i);
         }
