@@ -136,9 +136,11 @@ __device__ __noinline__ bool dev_on_path(const int* path, int len, int nid) {
 //              8 cubes contain the whole 3x3x3 neighbourhood of q.
 // Covers the owned cube layers only.
 struct SafeMap {
-  const int* safe;  // nullptr = disabled
+  int* safe;  // nullptr = disabled; entries are set to -1 when a label inside the certified region changes
   int shift, c1, c2, c3, zlo, nzl, octet, wrapz;
 };
+constexpr int STOP_SHIFT = 28;             // stop code = (level index << 28) | map index
+constexpr int STOP_MASK = (1 << STOP_SHIFT) - 1;
 
 // ------------------------------------------------------------------------------------------------
 // one near-grid step (step_neargrid, bader@proc.f90:455-494) of a trajectory held in WState.
@@ -245,7 +247,7 @@ __device__ __forceinline__ int walk_step(const BaderParams& P, const double* __r
         vx = nx >> sm.shift; vy = ny >> sm.shift; vz = cz >> sm.shift;
       }
       if (vz >= 0) {
-        const int sl = __ldg(sm.safe + vx + sm.c1 * (vy + (size_t)sm.c2 * vz));
+        const int sl = sm.safe[vx + sm.c1 * (vy + (size_t)sm.c2 * vz)];
         if (sl >= 0) { out = sl; return 2; }
       }
     }
@@ -273,7 +275,8 @@ __device__ __forceinline__ void load_nb(const BaderParams& P, const double* __re
   nb.zp = __ldg(c + ((z + 1 == n3) ? s3 - s3 * n3 : s3));
   nb.zm = __ldg(c + ((z == 0) ? s3 * n3 - s3 : -s3));
 }
-__device__ __forceinline__ int safe_lookup(const SafeMap& sm, int nx, int ny, int nz) {
+__device__ __forceinline__ int safe_lookup(const SafeMap& sm, int nx, int ny, int nz, int& mapidx) {
+  mapidx = -1;
   if (!sm.safe) return -1;
   const int cz = nz - sm.zlo;
   if (cz < 0 || cz >= sm.nzl) return -1;
@@ -287,14 +290,16 @@ __device__ __forceinline__ int safe_lookup(const SafeMap& sm, int nx, int ny, in
   } else {
     vx = nx >> sm.shift; vy = ny >> sm.shift; vz = cz >> sm.shift;
   }
-  return __ldg(sm.safe + vx + sm.c1 * (vy + (size_t)sm.c2 * vz));
+  mapidx = vx + sm.c1 * (vy + sm.c2 * vz);
+  return sm.safe[mapidx];  // plain load: entries may be invalidated while walkers run
 }
 // w: current point with w.r0, nb = its neighbours, sl = early-termination label of its cube (all loaded by
 // the previous call or by the caller for the start point, where sl must be -1)
 template <bool ORTHO>
 __device__ __forceinline__ int walk_step_pipe(const BaderParams& P, const double* __restrict__ rho, const MaxHash& h,
-                                              const SafeMap& sm, WState& w, Nb& nb, int& sl, int* path, int cap, int& out) {
-  if (sl >= 0) { out = sl; return 2; }  // quit at a known interior point (:447)
+                                              const SafeMap& sm, WState& w, Nb& nb, int& sl, int& sli, int* path, int cap,
+                                              int& out) {
+  if (sl >= 0) { out = sl; return 2; }  // quit at a known interior point (:447); sli = where (for the stop log)
   const int n1 = P.n1, n2 = P.n2, n3 = P.n3;
   const int x = w.x, y = w.y, z = w.z, id = w.id;
   const double r0 = w.r0;
@@ -341,7 +346,7 @@ __device__ __forceinline__ int walk_step_pipe(const BaderParams& P, const double
   // everything the next step needs, in one batch
   double rn = __ldg(rho + nid);
   load_nb(P, rho, nid, nx, ny, nz, nb);
-  sl = safe_lookup(sm, nx, ny, nz);
+  sl = safe_lookup(sm, nx, ny, nz, sli);
   if (rn <= w.rhomax) {  // only then pm can be a point of this path (:487)
     if (dev_on_path(path, w.len, nid)) {
       nid = dev_step_ongrid(P, rho, x, y, z, r0);
@@ -349,7 +354,7 @@ __device__ __forceinline__ int walk_step_pipe(const BaderParams& P, const double
       w.dr0 = w.dr1 = w.dr2 = 0.0;
       rn = __ldg(rho + nid);
       load_nb(P, rho, nid, nx, ny, nz, nb);
-      sl = safe_lookup(sm, nx, ny, nz);
+      sl = safe_lookup(sm, nx, ny, nz, sli);
     }
   }
   if (nid == id) { out = id; return 1; }  // did not move: maximum (:439)
@@ -394,9 +399,11 @@ __device__ __forceinline__ T plane3x3(T* s, T own, int hslot, T hval, int lx, in
   __syncthreads();
   const T* col = s + ly * 34 + lx + 1;
   const T a = Op::c3(col[0], own, col[68]);
-  T l = __shfl_up_sync(FULL, a, 1), r = __shfl_down_sync(FULL, a, 1);
-  if (lx == 0) l = Op::c3(col[-1], col[33], col[67]);
-  if (lx == 31) r = Op::c3(col[1], col[35], col[69]);
+  // the two edge lanes take their outer neighbour column from the halo; every lane executes the same code
+  const int e = (lx == 0) ? -1 : ((lx == 31) ? 1 : 0);
+  const T ae = Op::c3(col[e], col[e + 34], col[e + 68]);
+  const T lu = __shfl_up_sync(FULL, a, 1), rd = __shfl_down_sync(FULL, a, 1);
+  const T l = (lx == 0) ? ae : lu, r = (lx == 31) ? ae : rd;
   return Op::c3(l, a, r);
 }
 constexpr int TY = 8;                       // tile rows (256 threads)
@@ -409,67 +416,60 @@ __device__ __forceinline__ void halo_decode(int h, int& col, int& row) {
   else { col = 32; row = h - 68 - TY; }
 }
 
-// K0: candidate maxima (26-neighbour, is_max).  The grid is streamed once, z-marching per (32 x TY)
-// column tile; the 3x3x3 box maximum is taken on fp32 roundings (monotone, hence a necessary
-// condition: no neighbour is strictly greater in fp64 => none is in fp32) and the rare survivors are
-// re-tested exactly in fp64.  Marks the cubes of every level that contain a maximum.
+// K0: candidate maxima (26-neighbour, is_max).  The grid is streamed once: a warp owns a row segment of 32 x
+// points and marches along z with the previous / current / next plane values in registers; the x neighbours
+// come from shuffles.  A point can only be a maximum if it is >= its two x and two z neighbours (necessary,
+// exact in fp64); the rare survivors (points near the line through a nucleus) get the full 26-neighbour test.
+// No shared memory, no barriers: one coalesced 8-byte load per point.  Marks the cubes of every level that
+// contain a maximum.
 constexpr int MZC = 32;  // planes per block
-constexpr int MPF = 2;   // planes in flight per thread
 __global__ void __launch_bounds__(256) k_maxima(const __grid_constant__ BaderParams P, const Slab S,
                                                 const double* __restrict__ rho, int* __restrict__ cand,
                                                 int* __restrict__ ncand, int maxcand, const __grid_constant__ CubeFlags CF) {
-  __shared__ float sbuf[2][(TY + 2) * 34];
   const int n1 = P.n1, n2 = P.n2, n3 = P.n3;
   const size_t s3 = (size_t)n1 * n2;
-  const int tid = threadIdx.x, lx = tid & 31, ly = tid >> 5;
-  const int bx0 = blockIdx.x * 32, by0 = blockIdx.y * TY;
+  // a block = 256 consecutive x points of one row (2 KB contiguous per plane: DRAM-row friendly)
+  const int lane = threadIdx.x & 31;
+  const int gx = blockIdx.x * 256 + threadIdx.x, gy = blockIdx.y;
+  if (gx - lane >= n1) return;  // whole warp past the end of the row
   const int z0 = S.zlo + blockIdx.z * MZC, z1 = min(z0 + MZC, S.zhi);
-  const int gx = bx0 + lx, gy = by0 + ly;
-  const bool valid = gx < n1 && gy < n2;
-  const double* colp = rho + wrapx(gx, n1) + (size_t)n1 * wrapx(gy, n2);
-  int hslot = -1;
-  const double* hp = rho;
-  if (tid < NHALO) {
-    int hc, hr;
-    halo_decode(tid, hc, hr);
-    hslot = (hr + 1) * 34 + hc + 1;
-    hp = rho + wrapx(bx0 + hc, n1) + (size_t)n1 * wrapx(by0 + hr, n2);
-  }
-  float pm0 = 0.f, pm1 = 0.f, fc1 = 0.f;
-  // register ring: the loads of the next MPF planes are in flight while a plane is processed
-  double v[MPF], hv[MPF];
-#pragma unroll
-  for (int j = 0; j < MPF; j++) {
-    const int wz = wrapx(z0 - 1 + j, n3);
-    v[j] = (z0 - 1 + j <= z1) ? __ldg(colp + s3 * wz) : 0.0;
-    hv[j] = (hslot >= 0 && z0 - 1 + j <= z1) ? __ldg(hp + s3 * wz) : 0.0;
-  }
-  for (int it = z0 - 1; it <= z1; it += MPF) {
-#pragma unroll
-    for (int j = 0; j < MPF; j++) {
-      const int iz = it + j;
-      if (iz > z1) break;
-      const float fv = __double2float_rn(v[j]), fh = __double2float_rn(hv[j]);
-      if (iz + MPF <= z1) {
-        const int wz = wrapx(iz + MPF, n3);
-        v[j] = __ldg(colp + s3 * wz);
-        if (hslot >= 0) hv[j] = __ldg(hp + s3 * wz);
-      }
-      const float pm2 = plane3x3<float, OpMaxF>(sbuf[(iz - z0 + 1) & 1], fv, hslot, fh, lx, ly);
-      if (iz > z0) {  // plane iz-1 is complete
-        const float bm = fmaxf(fmaxf(pm0, pm1), pm2);
-        if (valid && !(bm > fc1)) {
-          const int gz = iz - 1;
-          if (dev_is_max(n1, n2, n3, rho, gx, gy, gz)) {
-            const int slot = atomicAdd(ncand, 1);
-            if (slot < maxcand) cand[slot] = gx + n1 * (gy + n2 * gz);
-            for (int i = 0; i < CF.nlev; i++)
-              CF.p[i][(gx >> (i + 1)) + CF.c1[i] * ((gy >> (i + 1)) + (size_t)CF.c2[i] * ((gz - S.zlo) >> (i + 1)))] = 1;
-          }
-        }
-      }
-      pm0 = pm1; pm1 = pm2; fc1 = fv;
+  const bool valid = gx < n1;
+  // lanes past the end of the row hold the periodic images, so that the shuffles give the right neighbours
+  const double* cp = rho + wrapx(gx, n1) + (size_t)n1 * gy;
+  // lane 0 / lane 31 also fetch the neighbour outside the warp's segment
+  const bool edge = lane == 0 || lane == 31;
+  const double* ep = rho + wrapx(lane == 0 ? gx - 1 : gx + 1, n1) + (size_t)n1 * gy;
+  const size_t wrapback = s3 * (size_t)n3;
+  int wz = wrapx(z0 - 1, n3);
+  cp += s3 * wz; ep += s3 * wz;
+  auto next_plane = [&]() {
+    cp += s3; ep += s3;
+    if (++wz == n3) { wz = 0; cp -= wrapback; ep -= wrapback; }
+  };
+  double vm = __ldg(cp);                 // plane z0-1
+  next_plane();
+  double vc = __ldg(cp), ec = edge ? __ldg(ep) : 0.0;   // plane z0
+  next_plane();
+  double vp = __ldg(cp), en = edge ? __ldg(ep) : 0.0;   // plane z0+1
+  for (int iz = z0; iz < z1; iz++) {
+    double vpp = 0.0, enn = 0.0;
+    if (iz + 2 <= z1) {  // plane iz+2 in flight while plane iz is tested
+      next_plane();
+      vpp = __ldg(cp);
+      if (edge) enn = __ldg(ep);
     }
+    double xl = __shfl_up_sync(FULL, vc, 1), xr = __shfl_down_sync(FULL, vc, 1);
+    if (lane == 0) xl = ec;
+    if (lane == 31) xr = ec;
+    if (valid && vc >= xl && vc >= xr && vc >= vm && vc >= vp) {
+      if (dev_is_max(n1, n2, n3, rho, gx, gy, iz)) {
+        const int slot = atomicAdd(ncand, 1);
+        if (slot < maxcand) cand[slot] = gx + n1 * (gy + n2 * iz);
+        for (int i = 0; i < CF.nlev; i++)
+          CF.p[i][(gx >> (i + 1)) + CF.c1[i] * ((gy >> (i + 1)) + (size_t)CF.c2[i] * ((iz - S.zlo) >> (i + 1)))] = 1;
+      }
+    }
+    vm = vc; vc = vp; vp = vpp; ec = en; en = enn;
   }
 }
 
@@ -486,8 +486,14 @@ struct WalkArgs {
   MaxHash h;
   SafeMap sm;
   unsigned char* reached;
-  const int* list;          // nullptr: lattice mode
+  const int* list;          // nullptr: lattice mode; otherwise the dense list of every walker so far
+  long long flat_base;      // flat mode: items are list[flat_base .. flat_base + count)
   long long count;
+  int* stop;                // stop log parallel to `list`: where a walk was cut short (stop code), or -1
+  int sm_level;             // level index of `sm` (goes into the stop code)
+  SafeMap maps[MAXLEV];     // FIX: every early-termination map in use, for invalidation
+  int nmaps;
+  int* ninval;
   const int2* items;        // non-null: work items (first list index, count) cut from a segmented list
   int nitems;               // upper bound; the exact number is *nitems_dev
   const int* nitems_dev;
@@ -507,6 +513,28 @@ struct WalkArgs {
 __device__ __noinline__ void claim_neighbours(const BaderParams& P, const WalkArgs& A, int start) {
   const int n1 = P.n1, n2 = P.n2, n3 = P.n3;
   const int x = start % n1, y = (start / n1) % n2, z = start / (n1 * n2);
+  // the label of `start` changed: every certificate whose region contains it is void
+  for (int m = 0; m < A.nmaps; m++) {
+    const SafeMap& sm = A.maps[m];
+    if (!sm.safe) continue;
+    const int cz = z - sm.zlo;
+    if (cz < 0 || cz >= sm.nzl) continue;
+    const int cx = x >> sm.shift, cy = y >> sm.shift, cl = cz >> sm.shift;
+    const int lo = sm.octet ? 0 : -1;  // octet: vertices c, c+1; cube certificate: cubes c-1, c, c+1
+    for (int dz = lo; dz <= 1; dz++) {
+      int vz = cl + dz;
+      if (vz == sm.c3) { if (sm.octet && sm.wrapz) vz = 0; else continue; }
+      if (vz < 0) continue;
+      for (int dy = lo; dy <= 1; dy++) {
+        const int vy = wrapx(cy + dy, sm.c2);
+        for (int dx = lo; dx <= 1; dx++) {
+          const int vx = wrapx(cx + dx, sm.c1);
+          int* e = sm.safe + vx + sm.c1 * (vy + (size_t)sm.c2 * vz);
+          if (*e >= 0 && atomicExch(e, -1) >= 0) atomicAdd(A.ninval, 1);
+        }
+      }
+    }
+  }
   for (int dz = -1; dz <= 1; dz++) {
     int zz = z + dz;
     if (A.S.periodic) zz = wrapx(zz, n3);
@@ -530,7 +558,9 @@ __device__ __noinline__ void claim_neighbours(const BaderParams& P, const WalkAr
 }
 
 template <bool FIX>
-__device__ __forceinline__ void walk_finish(const BaderParams& P, const WalkArgs& A, int start, int st, int out) {
+__device__ __forceinline__ void walk_finish(const BaderParams& P, const WalkArgs& A, int start, int st, int out, long long tidx,
+                                            int sli) {
+  if (A.stop && tidx >= 0) A.stop[tidx] = (st == 2) ? ((A.sm_level << STOP_SHIFT) | sli) : -1;
   if (st == 3) {
     const int slot = atomicAdd(A.noverflow, 1);
     if (slot < A.overcap) A.overflow[slot] = start;
@@ -553,7 +583,7 @@ __device__ __forceinline__ void walk_finish(const BaderParams& P, const WalkArgs
 }
 
 __device__ __forceinline__ int walk_item(const BaderParams& P, const WalkArgs& A, long long t) {
-  if (A.list) return __ldg(A.list + t);
+  if (A.list) return A.list[t];
   const int lx = (int)(t % A.lat_m1), ly = (int)((t / A.lat_m1) % A.lat_m2), lz = (int)(t / ((long long)A.lat_m1 * A.lat_m2));
   return lx * A.lat_s + P.n1 * (ly * A.lat_s + P.n2 * (A.S.zlo + lz * A.lat_s));
 }
@@ -565,7 +595,8 @@ __global__ void __launch_bounds__(256, MINB) k_walk(const __grid_constant__ Bade
   int path[PATHCAP];
   long long qpos = 0, qend = 0;  // warp-uniform: items [qpos, qend) are this warp's
   bool done = false, active = false;
-  int start = 0, sl = -1;
+  int start = 0, sl = -1, sli = -1;
+  long long tidx = -1;
   WState w;
   Nb nb;
   unsigned long long steps = 0;
@@ -587,14 +618,15 @@ __global__ void __launch_bounds__(256, MINB) k_walk(const __grid_constant__ Bade
           if (lane == 0) base = atomicAdd(A.cursor, (unsigned long long)A.batch);
           base = __shfl_sync(FULL, base, 0);
           if ((long long)base >= A.count) done = true;
-          else { qpos = (long long)base; qend = min((long long)base + A.batch, A.count); }
+          else { qpos = A.flat_base + (long long)base; qend = A.flat_base + min((long long)base + A.batch, A.count); }
         }
       }
       const int navail = (int)(qend - qpos);
       if (navail > 0) {
         const int rank = __popc(idle & ((1u << lane) - 1u));
         if (!active && rank < navail) {
-          start = walk_item(P, A, qpos + rank);
+          tidx = qpos + rank;
+          start = walk_item(P, A, tidx);
           walk_init(P, A.rho, w, start);
           load_nb(P, A.rho, start, w.x, w.y, w.z, nb);
           sl = -1;
@@ -605,10 +637,10 @@ __global__ void __launch_bounds__(256, MINB) k_walk(const __grid_constant__ Bade
     }
     if (active) {
       int out = 0;
-      const int st = walk_step_pipe<ORTHO>(P, A.rho, A.h, A.sm, w, nb, sl, path, PATHCAP, out);
+      const int st = walk_step_pipe<ORTHO>(P, A.rho, A.h, A.sm, w, nb, sl, sli, path, PATHCAP, out);
       if (st) {
         steps += (unsigned)w.len;
-        walk_finish<FIX>(P, A, start, st, out);
+        walk_finish<FIX>(P, A, start, st, out, A.list ? tidx : -1, sli);
         active = false;
       }
     }
@@ -638,36 +670,83 @@ __device__ __forceinline__ int block_excl_scan_256(int v, int* s_warp, int& tota
   __syncthreads();
   return base + incl - v;
 }
-__global__ void __launch_bounds__(256) k_items_count(int nseg, int batch, const int* __restrict__ segcnt, int* __restrict__ blocksum) {
+__global__ void __launch_bounds__(256) k_items_count(int nseg, int batch, const int* __restrict__ segcnt, int2* __restrict__ blocksum) {
   __shared__ int s_warp[8];
   const int b = blockIdx.x * 256 + threadIdx.x;
   const int c = b < nseg ? segcnt[b] : 0;
-  int total;
-  block_excl_scan_256((c + batch - 1) / batch, s_warp, total);
-  if (threadIdx.x == 0) blocksum[blockIdx.x] = total;
+  int ti, te;
+  block_excl_scan_256((c + batch - 1) / batch, s_warp, ti);
+  block_excl_scan_256(c, s_warp, te);
+  if (threadIdx.x == 0) blocksum[blockIdx.x] = make_int2(ti, te);
 }
-__global__ void __launch_bounds__(256) k_items_scan(int nblk, int* __restrict__ blocksum, int* __restrict__ nitems) {
+__global__ void __launch_bounds__(256) k_items_scan(int nblk, int2* __restrict__ blocksum, int* __restrict__ nitems, int* __restrict__ nentries) {
   __shared__ int s_warp[8];
-  int carry = 0;
+  int ci = 0, ce = 0;
   for (int i0 = 0; i0 < nblk; i0 += 256) {
     const int i = i0 + threadIdx.x;
-    const int v = i < nblk ? blocksum[i] : 0;
-    int total;
-    const int ex = block_excl_scan_256(v, s_warp, total);
-    if (i < nblk) blocksum[i] = carry + ex;
-    carry += total;
+    const int2 v = i < nblk ? blocksum[i] : make_int2(0, 0);
+    int ti, te;
+    const int ei = block_excl_scan_256(v.x, s_warp, ti);
+    const int ee = block_excl_scan_256(v.y, s_warp, te);
+    if (i < nblk) blocksum[i] = make_int2(ci + ei, ce + ee);
+    ci += ti; ce += te;
   }
-  if (threadIdx.x == 0) *nitems = carry;
+  if (threadIdx.x == 0) { *nitems = ci; *nentries = ce; }
 }
+// writes the items and copies the entries of the segments, in segment order, into the dense list at dbase
 __global__ void __launch_bounds__(256) k_items_write(int nseg, int segcap, int batch, const int* __restrict__ segcnt,
-                                                     const int* __restrict__ blocksum, int2* __restrict__ items) {
+                                                     const int2* __restrict__ blocksum, const int* __restrict__ seglist,
+                                                     int2* __restrict__ items, int* __restrict__ dlist, long long dbase) {
   __shared__ int s_warp[8];
+  __shared__ int s_c[256], s_e[256];
   const int b = blockIdx.x * 256 + threadIdx.x;
   const int c = b < nseg ? segcnt[b] : 0;
   const int k = (c + batch - 1) / batch;
   int total;
-  const int base = blocksum[blockIdx.x] + block_excl_scan_256(k, s_warp, total);
-  for (int j = 0; j < k; j++) items[base + j] = make_int2(b * segcap + j * batch, min(batch, c - j * batch));
+  const int2 bs = blocksum[blockIdx.x];
+  const int ibase = bs.x + block_excl_scan_256(k, s_warp, total);
+  const int ebase = bs.y + block_excl_scan_256(c, s_warp, total);
+  for (int j = 0; j < k; j++) items[ibase + j] = make_int2((int)(dbase + ebase + j * batch), min(batch, c - j * batch));
+  s_c[threadIdx.x] = c; s_e[threadIdx.x] = ebase;
+  __syncthreads();
+  if (total == 0) return;
+  for (int sg = 0; sg < 256; sg++) {  // cooperative, coalesced copy of each segment's entries
+    const int cs = s_c[sg];
+    if (cs == 0) continue;
+    const int* src = seglist + (size_t)(blockIdx.x * 256 + sg) * segcap;
+    int* dst = dlist + dbase + s_e[sg];
+    for (int e = threadIdx.x; e < cs; e += 256) dst[e] = src[e];
+  }
+}
+
+// re-queue the walkers whose early stop rested on a certificate that has been invalidated since
+__global__ void __launch_bounds__(256) k_requeue(long long ntotal, const int* __restrict__ dlist, int* __restrict__ stop,
+                                                 const __grid_constant__ WalkArgs A, int* __restrict__ out, int* __restrict__ nout,
+                                                 int outcap) {
+  const int lane = threadIdx.x & 31;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long t0 = (long long)blockIdx.x * blockDim.x; t0 < ntotal; t0 += stride) {
+    const long long t = t0 + threadIdx.x;
+    bool push = false;
+    if (t < ntotal) {
+      const int code = stop[t];
+      if (code >= 0) {
+        const int lev = code >> STOP_SHIFT;
+        if (lev < A.nmaps && A.maps[lev].safe && A.maps[lev].safe[code & STOP_MASK] < 0) { push = true; stop[t] = -2; }
+      }
+    }
+    const unsigned m = __ballot_sync(FULL, push);
+    if (m) {
+      int base = 0;
+      if (lane == __ffs(m) - 1) base = atomicAdd(nout, __popc(m));
+      base = __shfl_sync(FULL, base, __ffs(m) - 1);
+      if (push) {
+        const int slot = base + __popc(m & ((1u << lane) - 1u));
+        if (slot < outcap) out[slot] = dlist[t];
+        else atomicExch(A.err, 4);
+      }
+    }
+  }
 }
 
 // rare long trajectories: path buffer in global memory (bigcap entries per walker)
@@ -676,7 +755,7 @@ __global__ void __launch_bounds__(64) k_walk_big(const __grid_constant__ BaderPa
                                                  int count, int* __restrict__ scratch, int bigcap) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= count) return;
-  const int start = A.list[t];
+  const int start = A.overflow[t];
   WState w;
   walk_init(P, A.rho, w, start);
   const SafeMap nosafe{nullptr, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -684,7 +763,7 @@ __global__ void __launch_bounds__(64) k_walk_big(const __grid_constant__ BaderPa
   do st = walk_step<false>(P, A.rho, A.h, nosafe, w, scratch + (size_t)t * bigcap, bigcap, out); while (st == 0);
   if (A.nsteps) atomicAdd(A.nsteps, (unsigned long long)w.len);
   if (st == 3) { atomicExch(A.err, 2); return; }
-  walk_finish<FIX>(P, A, start, st, out);
+  walk_finish<FIX>(P, A, start, st, out, -1, -1);  // complete trajectory: nothing to log
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -758,7 +837,10 @@ __global__ void __launch_bounds__(256) k_classify(int n1, int n2, int n3, const 
     }
   }
   s_nu[tid] = nonuni ? 1 : 0;
-  __syncthreads();
+  if (!__syncthreads_or(nonuni ? 1 : 0)) {  // nothing to queue in this tile
+    if (tid == 0) segcnt[b] = 0;
+    return;
+  }
   // The new points of the non-uniform cubes are queued in memory order (z, y, x): the tile spans 32 x 8 x 8
   // positions of the stride-s/2 lattice; warp w owns the rows py = w, lane = px.
   const int px = lane, py = wid;
@@ -864,11 +946,12 @@ __global__ void __launch_bounds__(256) k_vsafe(int c1, int c2, int c3, int px, i
 // Every FILLED point with a 26-neighbour of a different label (the refine_edge criterion, is_vol_edge
 // bader@proc.f90:730-752) loses FILLBIT and is queued for an exact walk.  Without RULE the labels are
 // read as they are (halo planes included) and only the edge test is done.
-// SEG: the queue is segmented, one segment of FE_SEGCAP entries per warp (a 32 x 1 x MZC sheet of points);
-// otherwise entries are appended to a flat list.
+// SEG: the queue is segmented, one segment of FE_SEGCAP entries per block (32 x TY x MZC points), filled in
+// memory order (z, y, x) so that the walkers of a warp start next to each other; otherwise entries are
+// appended to a flat list.
 // skip_lo/skip_hi: do not test the first/last owned plane (multi-GPU: their halos are not valid yet).
 // ------------------------------------------------------------------------------------------------
-constexpr int FE_SEGCAP = 32 * MZC;
+constexpr int FE_SEGCAP = 32 * TY * MZC;
 struct FillArgs {
   int n1, n2, n3;
   Slab S;
@@ -885,28 +968,45 @@ constexpr int FSB_X = 4, FSB_Y = 16, FSB_Z = 4;  // super-block of 128^3 points
 __host__ __device__ inline int fe_nblocks(int g1, int g2, int g3) {
   return ((g1 + FSB_X - 1) / FSB_X) * ((g2 + FSB_Y - 1) / FSB_Y) * ((g3 + FSB_Z - 1) / FSB_Z) * (FSB_X * FSB_Y * FSB_Z);
 }
-// label of point (x, y, gz) in two dependent loads that the caller issues one plane apart:
-//   fill_u  : the uniform label of the point's stride-2 cube if the fill rule applies to the point, else -1
-//   fill_lab: u | FILLBIT, or the label the walkers / earlier levels wrote
+// Label of a point in two dependent loads that the caller issues one plane apart: u = uniform label of the
+// point's stride-2 cube if the fill rule applies to the point (else -1), then u | FILLBIT or the label the
+// walkers / earlier levels wrote.  PlaneD holds the block-uniform part of the addressing of one z plane.
+struct PlaneD {
+  long long lboff, uoff;
+  int zpar, owned;
+  int rz;  // plane index relative to zlo (wrapped into [0, n3) when the slab is periodic)
+};
+__device__ __forceinline__ void plane_set(const FillArgs& A, PlaneD& d) {
+  d.owned = A.S.periodic ? 1 : ((d.rz >= 0 && d.rz < A.S.nzl) ? 1 : 0);
+  d.zpar = d.rz & 1;
+  d.lboff = (long long)(A.n1 * A.n2) * (d.rz + 1);
+  d.uoff = d.owned ? (long long)(A.c1 * A.c2) * (d.rz >> 1) : 0;
+}
+__device__ __forceinline__ PlaneD plane_desc(const FillArgs& A, int gz) {
+  PlaneD d;
+  d.rz = gz - A.S.zlo;  // periodic: zlo = 0
+  if (A.S.periodic) d.rz = wrapx(gz, A.n3);
+  plane_set(A, d);
+  return d;
+}
+__device__ __forceinline__ void plane_advance(const FillArgs& A, PlaneD& d, int k) {  // k = 1 or 2 planes up
+  d.rz += k;
+  if (A.S.periodic && d.rz >= A.n3) d.rz -= A.n3;
+  plane_set(A, d);
+}
 template <bool RULE>
-__device__ __forceinline__ int fill_u(const FillArgs& A, int x, int y, int gz) {
-  if (!RULE) return -1;
-  bool owned = true;
-  if (A.S.periodic) gz = wrapx(gz, A.n3);
-  else owned = gz >= A.S.zlo && gz < A.S.zhi;
-  if (owned && ((x | y | (gz - A.S.zlo)) & 1))
-    return __ldg(A.uni2 + (x >> 1) + A.c1 * ((y >> 1) + (size_t)A.c2 * ((gz - A.S.zlo) >> 1)));
+__device__ __forceinline__ int fill_u(const PlaneD& d, const int* __restrict__ ucol, int xyodd) {
+  if (RULE && d.owned && (xyodd | d.zpar)) return __ldg(ucol + d.uoff);
   return -1;
 }
-__device__ __forceinline__ int fill_lab(const FillArgs& A, int x, int y, int gz, int u) {
+__device__ __forceinline__ int fill_lab(const PlaneD& d, const int* lbcol, int u) {
   if (u >= 0) return (int)((unsigned)u | FILLBIT);
-  const int pl = A.S.periodic ? wrapx(gz, A.n3) + 1 : gz - A.S.zlo + 1;
-  return A.lbuf[x + (size_t)A.n1 * y + (size_t)A.n1 * A.n2 * pl];
+  return lbcol[d.lboff];
 }
 template <bool RULE, bool SEG>
 __global__ void __launch_bounds__(256) k_fill_edge(const __grid_constant__ FillArgs A) {
   __shared__ int sbuf[2][(TY + 2) * 34];
-  __shared__ int s_total;
+  __shared__ __align__(16) int s_cnt[2][TY];  // SEG: edge points per warp of a plane, double-buffered
   const int n1 = A.n1, n2 = A.n2;
   const int tid = threadIdx.x, lx = tid & 31, ly = tid >> 5, lane = lx;
   int bx, by, bz;
@@ -918,7 +1018,7 @@ __global__ void __launch_bounds__(256) k_fill_edge(const __grid_constant__ FillA
     by = ((sb / s1) % s2) * FSB_Y + (w / FSB_X) % FSB_Y;
     bz = (sb / (s1 * s2)) * FSB_Z + w / (FSB_X * FSB_Y);
     if (bx >= A.g1 || by >= A.g2 || bz >= A.g3) {  // padding block of a ragged super-block
-      if (lane == 0) A.segcnt[(size_t)b * TY + ly] = 0;
+      if (tid == 0) A.segcnt[b] = 0;
       return;
     }
   } else {
@@ -929,48 +1029,77 @@ __global__ void __launch_bounds__(256) k_fill_edge(const __grid_constant__ FillA
   const int gx = bx0 + lx, gy = by0 + ly;
   const bool valid = gx < n1 && gy < n2;
   const int wx = wrapx(gx, n1), wy = wrapx(gy, n2);
-  int hslot = -1, hx = 0, hy = 0;
+  // per-thread column bases of the own point and (first NHALO threads) of one halo point
+  const int* lbc = A.lbuf + wx + (size_t)n1 * wy;
+  const int* uc = A.uni2 + (wx >> 1) + (size_t)A.c1 * (wy >> 1);
+  const int xyodd = (wx | wy) & 1;
+  int hslot = -1, hxyodd = 0;
+  const int* hlbc = A.lbuf;
+  const int* huc = A.uni2;
   if (tid < NHALO) {
     int hc, hr;
     halo_decode(tid, hc, hr);
     hslot = (hr + 1) * 34 + hc + 1;
-    hx = wrapx(bx0 + hc, n1); hy = wrapx(by0 + hr, n2);
+    const int hx = wrapx(bx0 + hc, n1), hy = wrapx(by0 + hr, n2);
+    hlbc = A.lbuf + hx + (size_t)n1 * hy;
+    huc = A.uni2 + (hx >> 1) + (size_t)A.c1 * (hy >> 1);
+    hxyodd = (hx | hy) & 1;
   }
-  if (SEG && tid == 0) s_total = 0;
+  const bool hal = hslot >= 0;
+  if (SEG && tid < 2 * TY) (&s_cnt[0][0])[tid] = 0;
+  int* wout = A.lbuf + gx + (size_t)n1 * gy - (size_t)n1 * n2 * (A.S.zlo - 1);  // wout[s3 * gz] = label of (gx, gy, gz)
   const size_t s3 = (size_t)n1 * n2;
-  const size_t seg = (size_t)blockIdx.x * TY + ly;  // SEG only
-  int* segout = A.list + seg * FE_SEGCAP;
-  int nseg = 0;  // warp-uniform: entries in this warp's segment
+  int* segout = A.list + (size_t)blockIdx.x * FE_SEGCAP;  // SEG only
+  int nseg = 0;          // block-uniform: entries in this block's segment so far
+  unsigned m_pend = 0;   // SEG: edge mask of the previous plane, written one iteration later (see below)
+  int id_pend = 0;
   int pm0 = -1, pm1 = -1, own1 = 0;
   // software pipeline: cube labels two planes ahead, point labels one plane ahead
-  int u_a = fill_u<RULE>(A, wx, wy, z0 - 1), hu_a = (hslot >= 0) ? fill_u<RULE>(A, hx, hy, z0 - 1) : -1;
-  int own_n = fill_lab(A, wx, wy, z0 - 1, u_a), hv_n = (hslot >= 0) ? fill_lab(A, hx, hy, z0 - 1, hu_a) : 0;
-  u_a = fill_u<RULE>(A, wx, wy, z0); hu_a = (hslot >= 0) ? fill_u<RULE>(A, hx, hy, z0) : -1;
+  PlaneD d1 = plane_desc(A, z0 - 1);
+  int u_a = fill_u<RULE>(d1, uc, xyodd), hu_a = hal ? fill_u<RULE>(d1, huc, hxyodd) : -1;
+  int own_n = fill_lab(d1, lbc, u_a), hv_n = hal ? fill_lab(d1, hlbc, hu_a) : 0;
+  plane_advance(A, d1, 1);
+  u_a = fill_u<RULE>(d1, uc, xyodd); hu_a = hal ? fill_u<RULE>(d1, huc, hxyodd) : -1;
   for (int iz = z0 - 1; iz <= z1; iz++) {
     const int own = own_n, hv = hv_n & LMASK;
-    if (iz < z1) {
-      own_n = fill_lab(A, wx, wy, iz + 1, u_a);
-      if (hslot >= 0) hv_n = fill_lab(A, hx, hy, iz + 1, hu_a);
+    if (iz < z1) {  // d1 describes plane iz+1
+      own_n = fill_lab(d1, lbc, u_a);
+      if (hal) hv_n = fill_lab(d1, hlbc, hu_a);
       if (iz + 1 < z1) {
-        u_a = fill_u<RULE>(A, wx, wy, iz + 2);
-        if (hslot >= 0) hu_a = fill_u<RULE>(A, hx, hy, iz + 2);
+        plane_advance(A, d1, 1);
+        u_a = fill_u<RULE>(d1, uc, xyodd);
+        if (hal) hu_a = fill_u<RULE>(d1, huc, hxyodd);
       }
     }
     const int pm2 = plane3x3<int, OpAgree>(sbuf[(iz - z0 + 1) & 1], own & LMASK, hslot, hv, lx, ly);
+    if (SEG) {
+      // the barrier inside plane3x3 has published every warp's count of the plane tested one iteration ago:
+      // write that plane's entries at block-level positions (z, y, x order)
+      const int4* c = reinterpret_cast<const int4*>(s_cnt[(iz - z0) & 1]);
+      const int4 c0 = c[0], c1 = c[1];
+      const int cv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+      int base = nseg, total = 0;
+#pragma unroll
+      for (int w = 0; w < TY; w++) {
+        if (w < ly) base += cv[w];
+        total += cv[w];
+      }
+      if ((m_pend >> lane) & 1u) segout[base + __popc(m_pend & ((1u << lane) - 1u))] = id_pend;
+      nseg += total;
+    }
+    unsigned m = 0;
     if (iz > z0) {  // plane iz-1 is complete
       const int gz = iz - 1;
       const bool test = !((A.skip_lo && gz == A.S.zlo) || (A.skip_hi && gz == A.S.zhi - 1));
       const bool filled = ((unsigned)own1 & FILLBIT) != 0;
       const bool edge = valid && filled && test && OpAgree::c3(pm0, pm1, pm2) < 0;
-      const size_t off = gx + (size_t)n1 * gy + s3 * (gz - A.S.zlo + 1);
-      if (valid && (RULE ? (filled || edge) : edge)) A.lbuf[off] = edge ? (own1 & LMASK) : own1;
-      const unsigned m = __ballot_sync(FULL, edge);
+      if (valid && (RULE ? filled : edge)) wout[s3 * gz] = edge ? (own1 & LMASK) : own1;
+      m = __ballot_sync(FULL, edge);
       if (m) {
-        const int rank = __popc(m & ((1u << lane) - 1u));
         if (SEG) {
-          if (edge) segout[nseg + rank] = gx + n1 * (gy + n2 * gz);
-          nseg += __popc(m);
+          id_pend = gx + n1 * (gy + n2 * gz);
         } else {
+          const int rank = __popc(m & ((1u << lane) - 1u));
           int base = 0;
           if (lane == __ffs(m) - 1) base = atomicAdd(A.nlist, __popc(m));
           base = __shfl_sync(FULL, base, __ffs(m) - 1);
@@ -982,15 +1111,28 @@ __global__ void __launch_bounds__(256) k_fill_edge(const __grid_constant__ FillA
         }
       }
     }
+    if (SEG) {
+      m_pend = m;
+      if (lane == 0) s_cnt[(iz - z0 + 1) & 1][ly] = __popc(m);
+    }
     pm0 = pm1; pm1 = pm2; own1 = own;
   }
-  if (SEG) {
-    if (lane == 0) {
-      A.segcnt[seg] = nseg;
-      if (nseg) atomicAdd(&s_total, nseg);
-    }
+  if (SEG) {  // entries of the last plane
     __syncthreads();
-    if (tid == 0 && s_total) atomicAdd(A.nlist, s_total);
+    const int* c = s_cnt[(z1 + 1 - z0) & 1];
+    int base = nseg, total = 0;
+#pragma unroll
+    for (int w = 0; w < TY; w++) {
+      const int v = c[w];
+      if (w < ly) base += v;
+      total += v;
+    }
+    if ((m_pend >> lane) & 1u) segout[base + __popc(m_pend & ((1u << lane) - 1u))] = id_pend;
+    nseg += total;
+    if (tid == 0) {
+      A.segcnt[blockIdx.x] = nseg;
+      if (nseg) atomicAdd(A.nlist, nseg);
+    }
   }
 }
 
@@ -1161,7 +1303,7 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
     C2G_CUDA(ctx, cudaMemsetAsync(cnt, 0, 64, st));
     for (int i = 0; i < CF.nlev; i++) C2G_CUDA(ctx, cudaMemsetAsync(CF.p[i], 0, lev[i].nc, st));
     if (S.nzl > 0) {
-      dim3 grid((n1 + 31) / 32, (n2 + TY - 1) / TY, (S.nzl + MZC - 1) / MZC);
+      dim3 grid((n1 + 255) / 256, n2, (S.nzl + MZC - 1) / MZC);
       ctx->prof_begin("bader_maxima");
       k_maxima<<<grid, 256, 0, st>>>(P, S, g.d, b_cand.as<int>(), cnt, maxcand, CF);
       ctx->prof_end();
@@ -1237,8 +1379,9 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
     for (int s = 2; s <= L0; s <<= 1) nlev++;
   }
 
-  // work lists: [0] segmented (classify levels, fill+edge), [1],[2] flat (edge-fix ping-pong); overflow list
-  DevBuf b_list[3], b_over, b_segcnt, b_items, b_blksum;
+  // work lists: [0] segmented (classify levels, fill+edge), [1],[2] flat (edge-fix ping-pong); overflow list;
+  // dense list of every walker so far + its stop log (where its walk was cut short)
+  DevBuf b_list[3], b_over, b_segcnt, b_items, b_blksum, b_dlist, b_stop;
   size_t itemcap = 0, blksumcap = 0;
   size_t segints = 1, nsegmax = 1;
   int fe_gx = (n1 + 31) / 32, fe_gy = (n2 + TY - 1) / TY, fe_gz = std::max(1, (S.nzl + MZC - 1) / MZC);
@@ -1249,24 +1392,28 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
       segints = std::max(segints, nt * CLS_SEGCAP);
       nsegmax = std::max(nsegmax, nt);
     }
-    const size_t nfe = (size_t)fe_nblocks(fe_gx, fe_gy, fe_gz) * TY;
+    const size_t nfe = (size_t)fe_nblocks(fe_gx, fe_gy, fe_gz);
     segints = std::max(segints, nfe * FE_SEGCAP);
     nsegmax = std::max(nsegmax, nfe);
   }
   const long long listcap = (algo == C2G_BADER_EXACT) ? 1 : std::max<long long>(1, nnl);
+  const long long dcap = (algo == C2G_BADER_EXACT) ? 1 : std::min<long long>(nnl + nnl / 8 + (1 << 20), 0x7fffffffll);
+  long long doff = 0;  // entries of the dense list in use
   C2G_CUDA(ctx, b_list[0].alloc(ctx, sizeof(int) * segints));
   C2G_CUDA(ctx, b_segcnt.alloc(ctx, sizeof(int) * nsegmax));
   C2G_CUDA(ctx, b_list[1].alloc(ctx, sizeof(int) * (size_t)listcap));
   C2G_CUDA(ctx, b_list[2].alloc(ctx, sizeof(int) * (size_t)listcap));
+  C2G_CUDA(ctx, b_dlist.alloc(ctx, sizeof(int) * (size_t)dcap));
+  C2G_CUDA(ctx, b_stop.alloc(ctx, sizeof(int) * (size_t)dcap));
   const long long overcap = std::max<long long>(1024, nnl / 16);
   C2G_CUDA(ctx, b_over.alloc(ctx, sizeof(int) * (size_t)overcap));
-  long long walked = 0, fixpts = 0, fixpasses = 0, noverflow_total = 0;
+  long long walked = 0, fixpts = 0, fixpasses = 0, noverflow_total = 0, nrequeued = 0;
 
   WalkArgs WA;
   memset(&WA, 0, sizeof(WA));
   WA.rho = g.d; WA.label_g = label_g; WA.h = h; WA.reached = reached; WA.S = S;
   WA.cursor = cursor; WA.overflow = b_over.as<int>(); WA.noverflow = cnt + 2; WA.overcap = (int)std::min<long long>(overcap, 0x7fffffff);
-  WA.err = cnt + 3; WA.nsteps = nsteps; WA.nnext = cnt + 7;
+  WA.err = cnt + 3; WA.nsteps = nsteps; WA.nnext = cnt + 7; WA.ninval = cnt + 11;
   WA.refill_min = REFILL_MIN;
   if (const char* e = getenv("C2G_REFILL_MIN")) WA.refill_min = std::max(1, std::min(32, atoi(e)));
   int walk_occ = 4;  // resident 256-thread walker blocks per SM (4: <= 64 registers, 3: <= 80)
@@ -1296,10 +1443,9 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
     DevBuf b_scr;
     C2G_CUDA(ctx, b_scr.alloc(ctx, sizeof(int) * (size_t)chunk * bigcap));
     WalkArgs W2 = WA;
-    W2.items = nullptr;
     for (int off = 0; off < nov; off += chunk) {
       const int c = std::min(chunk, nov - off);
-      W2.list = b_over.as<int>() + off;
+      W2.overflow = b_over.as<int>() + off;
       ctx->prof_begin("bader_walk_big");
       if (fix) k_walk_big<true><<<c2g_blocks_for(c, 64), 64, 0, st>>>(P, W2, c, b_scr.as<int>(), bigcap);
       else k_walk_big<false><<<c2g_blocks_for(c, 64), 64, 0, st>>>(P, W2, c, b_scr.as<int>(), bigcap);
@@ -1312,38 +1458,7 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
     hcnt[2] = 0;
     return check_err();
   };
-  // launch the persistent walkers.  Sources: a flat list / lattice of `count` items (list == nullptr: the
-  // stride-lat_s lattice of the slab), or a segmented list (segcnt != nullptr; count = total, for statistics).
-  auto walk = [&](const int* list, long long count, int lat_s, const int* segcnt, int nseg, int segcap, bool fix, int* next,
-                  const SafeMap& sm, const char* name) -> int {
-    if (count <= 0) return C2G_OK;
-    WA.list = list; WA.count = count; WA.sm = sm;
-    WA.items = nullptr; WA.nitems = 0;
-    if (segcnt) {  // work items of 32 or 64 consecutive entries of one segment
-      const int batch = count < 64ll * wblocks * 8 ? 32 : 64;
-      const size_t maxitems = (size_t)nseg + (size_t)(count / batch) + 1;
-      if (maxitems > itemcap) {
-        itemcap = maxitems + maxitems / 4;
-        C2G_CUDA(ctx, b_items.alloc(ctx, sizeof(int2) * itemcap));
-      }
-      const int nblk = c2g_blocks_for(nseg, 256);
-      if ((size_t)nblk > blksumcap) {
-        blksumcap = (size_t)nblk;
-        C2G_CUDA(ctx, b_blksum.alloc(ctx, sizeof(int) * blksumcap));
-      }
-      k_items_count<<<nblk, 256, 0, st>>>(nseg, batch, segcnt, b_blksum.as<int>());
-      k_items_scan<<<1, 256, 0, st>>>(nblk, b_blksum.as<int>(), cnt + 10);
-      k_items_write<<<nblk, 256, 0, st>>>(nseg, segcap, batch, segcnt, b_blksum.as<int>(), b_items.as<int2>());
-      C2G_KERNEL_CHECK(ctx);
-      ctx->launches += 3;
-      WA.items = b_items.as<int2>();
-      WA.nitems = (int)std::min<size_t>(maxitems, 0x7fffffff);
-      WA.nitems_dev = cnt + 10;
-    }
-    WA.lat_s = lat_s; WA.lat_m1 = (n1 + lat_s - 1) / lat_s; WA.lat_m2 = (n2 + lat_s - 1) / lat_s;
-    WA.next = next; WA.nextcap = (int)std::min<long long>(listcap, 0x7fffffff);
-    const long long nwarps = (long long)wblocks * 8;
-    WA.batch = (int)std::max<long long>(32, std::min<long long>(256, count / (nwarps * 4) / 32 * 32));
+  auto launch_walk = [&](long long count, bool fix, const char* name) -> int {
     C2G_CUDA(ctx, cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), st));
     const int blocks = (int)std::min<long long>(wblocks, (count + 255) / 256);
     ctx->prof_begin(name);
@@ -1369,30 +1484,84 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
     walked += count;
     return C2G_OK;
   };
+  // walkers over the stride-lat_s lattice of the slab (complete trajectories, nothing logged)
+  auto walk_lattice = [&](long long count, int lat_s, const char* name) -> int {
+    if (count <= 0) return C2G_OK;
+    WA.list = nullptr; WA.stop = nullptr; WA.items = nullptr; WA.nitems = 0; WA.flat_base = 0; WA.count = count;
+    WA.sm = SafeMap{nullptr, 0, 0, 0, 0, 0, 0, 0, 0}; WA.sm_level = 0;
+    WA.lat_s = lat_s; WA.lat_m1 = (n1 + lat_s - 1) / lat_s; WA.lat_m2 = (n2 + lat_s - 1) / lat_s;
+    WA.next = nullptr; WA.nextcap = 0;
+    const long long nwarps = (long long)wblocks * 8;
+    WA.batch = (int)std::max<long long>(32, std::min<long long>(256, count / (nwarps * 4) / 32 * 32));
+    return launch_walk(count, false, name);
+  };
+  // walkers over a segmented list: its entries are first copied, in segment order, to the end of the dense list
+  auto walk_segments = [&](const int* seglist, const int* segcnt, int nseg, int segcap, long long count, bool fix, int* next,
+                           const SafeMap& sm, int sm_level, const char* name) -> int {
+    if (count <= 0) return C2G_OK;
+    if (doff + count > dcap) return ctx->fail(C2G_ERR_OVERFLOW, "walker list overflow");
+    const int batch = count < 64ll * wblocks * 8 ? 32 : 64;
+    const size_t maxitems = (size_t)nseg + (size_t)(count / batch) + 1;
+    if (maxitems > itemcap) {
+      itemcap = maxitems + maxitems / 4;
+      C2G_CUDA(ctx, b_items.alloc(ctx, sizeof(int2) * itemcap));
+    }
+    const int nblk = c2g_blocks_for(nseg, 256);
+    if ((size_t)nblk > blksumcap) {
+      blksumcap = (size_t)nblk;
+      C2G_CUDA(ctx, b_blksum.alloc(ctx, sizeof(int2) * blksumcap));
+    }
+    k_items_count<<<nblk, 256, 0, st>>>(nseg, batch, segcnt, b_blksum.as<int2>());
+    k_items_scan<<<1, 256, 0, st>>>(nblk, b_blksum.as<int2>(), cnt + 10, cnt + 12);
+    k_items_write<<<nblk, 256, 0, st>>>(nseg, segcap, batch, segcnt, b_blksum.as<int2>(), seglist, b_items.as<int2>(),
+                                        b_dlist.as<int>(), doff);
+    C2G_KERNEL_CHECK(ctx);
+    ctx->launches += 3;
+    WA.list = b_dlist.as<int>(); WA.stop = b_stop.as<int>(); WA.flat_base = 0; WA.count = count;
+    WA.items = b_items.as<int2>(); WA.nitems = (int)std::min<size_t>(maxitems, 0x7fffffff); WA.nitems_dev = cnt + 10;
+    WA.sm = sm; WA.sm_level = sm_level; WA.lat_s = 1; WA.lat_m1 = n1; WA.lat_m2 = n2;
+    WA.next = next; WA.nextcap = (int)std::min<long long>(listcap, 0x7fffffff);
+    WA.batch = batch;
+    doff += count;
+    return launch_walk(count, fix, name);
+  };
+  // walkers over a flat list (edge-fix passes): copied to the end of the dense list as well
+  auto walk_flat = [&](const int* list, long long count, bool fix, int* next, const SafeMap& sm, int sm_level, const char* name) -> int {
+    if (count <= 0) return C2G_OK;
+    if (doff + count > dcap) return ctx->fail(C2G_ERR_OVERFLOW, "walker list overflow");
+    C2G_CUDA(ctx, cudaMemcpyAsync(b_dlist.as<int>() + doff, list, sizeof(int) * (size_t)count, cudaMemcpyDeviceToDevice, st));
+    WA.list = b_dlist.as<int>(); WA.stop = b_stop.as<int>(); WA.flat_base = doff; WA.count = count;
+    WA.items = nullptr; WA.nitems = 0;
+    WA.sm = sm; WA.sm_level = sm_level; WA.lat_s = 1; WA.lat_m1 = n1; WA.lat_m2 = n2;
+    WA.next = next; WA.nextcap = (int)std::min<long long>(listcap, 0x7fffffff);
+    WA.batch = 32;
+    doff += count;
+    return launch_walk(count, fix, name);
+  };
   const SafeMap nosafe{nullptr, 0, 0, 0, 0, 0, 0, 0, 0};
 
   int rc;
   if (algo == C2G_BADER_EXACT) {
-    if ((rc = walk(nullptr, nnl, 1, nullptr, 0, 0, false, nullptr, nosafe, "bader_walk_all")) != C2G_OK) return rc;
+    if ((rc = walk_lattice(nnl, 1, "bader_walk_all")) != C2G_OK) return rc;
     if ((rc = drain(false)) != C2G_OK) return rc;
   } else {
     // top level: the stride-L0 lattice walks complete trajectories
     {
       const long long m = (long long)((n1 + L0 - 1) / L0) * ((n2 + L0 - 1) / L0) * ((S.nzl + L0 - 1) / L0);
-      if ((rc = walk(nullptr, m, L0, nullptr, 0, 0, false, nullptr, nosafe, "bader_walk_top")) != C2G_OK) return rc;
+      if ((rc = walk_lattice(m, L0, "bader_walk_top")) != C2G_OK) return rc;
       if ((rc = drain(false)) != C2G_OK) return rc;
     }
     const long long ntop = walked;
     const bool use_safe = getenv("C2G_NO_EARLY_STOP") == nullptr;
-    // Early stops are only allowed in cubes of stride <= 4: a coarser "uniform" cube is certified by corners
-    // that are far apart, which is good enough for a fill (every filled point is re-examined by the edge
-    // fix) but not for a walked label (never re-examined).
-    int safe_maxs = 4;
+    // Early stops: a walk may end where a certificate says that the neighbourhood is uniformly labelled (the
+    // reference's known==2 points).  Certificates rest on labels that may still change (wrong fills), so every
+    // stop is logged, every label change voids the certificates around it, and the walkers that relied on a
+    // voided certificate walk again (k_requeue).  safe_maxs: coarsest cube stride whose certificates are used.
+    int safe_maxs = 16;
     if (const char* e = getenv("C2G_SAFE_MAXS")) safe_maxs = atoi(e);
-    // certificate: 2 = cube + 26 neighbour cubes (uniform 5x5x5 point neighbourhood, the margin at which the
-    // reference's refine_edge walks stop); 1 = octet (3x3x3) -- fewer steps, but it has produced wrong labels
-    // when it rested on a wrong fill (tests/cases.py odd_dims: 11 of 143350 points), so it is opt-in.
-    int cert = 2;
+    // certificate: 1 = octet (uniform 3x3x3 point neighbourhood), 2 = cube + 26 neighbour cubes (5x5x5, the
+    // margin at which the reference's refine_edge walks stop)
+    int cert = 1;
     if (const char* e = getenv("C2G_CERT")) cert = atoi(e);
     const bool verbose = getenv("C2G_BADER_VERBOSE") != nullptr;
     unsigned long long steps_prev = 0;
@@ -1408,7 +1577,7 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
     static const char* wname[MAXLEV] = {"bader_walk_l1", "bader_walk_l2", "bader_walk_l4", "bader_walk_l8", "bader_walk_l16"};
     int* seglist = b_list[0].as<int>();
     int* segcnt = b_segcnt.as<int>();
-    SafeMap fixsafe = nosafe;
+    WA.nmaps = nlev;  // maps[i] = certificate map of level i (stride 2<<i), if any
     for (int i = nlev - 1; i >= 0; i--) {
       const Level& L = lev[i];
       if ((rc = exchange_halos(ctx, lbuf, plane, S, 1)) != C2G_OK) return rc;
@@ -1440,16 +1609,17 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
           }
           ctx->prof_end();
           C2G_KERNEL_CHECK(ctx);
-          if (i == 0) fixsafe = sm;
         }
       }
+      WA.maps[i] = sm;
       C2G_CUDA(ctx, cudaMemcpyAsync(hcnt, cnt, 64, cudaMemcpyDeviceToHost, st));
       C2G_CUDA(ctx, cudaStreamSynchronize(st));
       const long long nw = hcnt[1];
-      if ((rc = walk(seglist, nw, 1, segcnt, ntile, CLS_SEGCAP, false, nullptr, sm, wname[i])) != C2G_OK) return rc;
+      if ((rc = walk_segments(seglist, segcnt, ntile, CLS_SEGCAP, nw, false, nullptr, sm, i, wname[i])) != C2G_OK) return rc;
       if ((rc = drain(false)) != C2G_OK) return rc;
       report(wname[i], nw);
     }
+    const SafeMap fixsafe = WA.maps[0];
     // ---- materialise the last level and find the filled points with a foreign 26-neighbour ----
     FillArgs FA;
     memset(&FA, 0, sizeof(FA));
@@ -1476,7 +1646,7 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
     };
     int cur = 1;  // flat list being consumed next; the other one receives the claims
     const int nfeblk = fe_nblocks(fe_gx, fe_gy, fe_gz);
-    const int nfeseg = nfeblk * TY;
+    const int nfeseg = nfeblk;
     FA.g1 = fe_gx; FA.g2 = fe_gy; FA.g3 = fe_gz;
     if (nnl > 0) {
       FA.list = seglist; FA.nlist = cnt + 1;
@@ -1491,9 +1661,10 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
       if (nnl > 0 && (rc = edge_faces(b_list[cur].as<int>(), cnt + 7)) != C2G_OK) return rc;
     }
     // ---- edge fix until no filled point (on any rank) is adjacent to a different label ----
-    // pass 1 consumes the segmented list (+ the face points, multi-GPU); every pass writes the filled
-    // neighbours of the points that changed into the other flat list, which the next pass consumes.
+    // pass 1 consumes the segmented list (+ the face points, multi-GPU); every pass writes into the other flat
+    // list the filled neighbours of the points that changed and the walkers whose certificate was voided.
     bool first = true;
+    int ninval_seen = 0;
     for (;;) {
       C2G_CUDA(ctx, cudaMemcpyAsync(hcnt, cnt, 64, cudaMemcpyDeviceToHost, st));
       C2G_CUDA(ctx, cudaStreamSynchronize(st));
@@ -1512,10 +1683,18 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
       int* in = b_list[cur].as<int>();
       int* out = b_list[cur == 1 ? 2 : 1].as<int>();
       C2G_CUDA(ctx, cudaMemsetAsync(cnt + 7, 0, sizeof(int), st));
-      if (nseg1 && (rc = walk(seglist, nseg1, 1, segcnt, nfeseg, FE_SEGCAP, true, out, fixsafe, "bader_walk_fix")) != C2G_OK) return rc;
-      if (nflat && (rc = walk(in, nflat, 1, nullptr, 0, 0, true, out, fixsafe, "bader_walk_fix")) != C2G_OK) return rc;
+      if (nseg1 && (rc = walk_segments(seglist, segcnt, nfeseg, FE_SEGCAP, nseg1, true, out, fixsafe, 0, "bader_walk_fix")) != C2G_OK) return rc;
+      if (nflat && (rc = walk_flat(in, nflat, true, out, fixsafe, 0, "bader_walk_fix")) != C2G_OK) return rc;
       if ((rc = drain(true)) != C2G_OK) return rc;
       report("bader_walk_fix", nseg1 + nflat);
+      if (hcnt[11] != ninval_seen && doff > 0) {  // certificates were voided: re-queue the walkers that relied on them
+        ninval_seen = hcnt[11];
+        ctx->prof_begin("bader_requeue");
+        k_requeue<<<ctx->nsm * 8, 256, 0, st>>>(doff, b_dlist.as<int>(), b_stop.as<int>(), WA, out, cnt + 7,
+                                                 (int)std::min<long long>(listcap, 0x7fffffff));
+        ctx->prof_end();
+        C2G_KERNEL_CHECK(ctx);
+      }
       if (G > 1) {
         if ((rc = exchange_halos(ctx, lbuf, plane, S, 3)) != C2G_OK) return rc;
         if (nnl > 0 && (rc = edge_faces(out, cnt + 7)) != C2G_OK) return rc;
@@ -1524,6 +1703,7 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
       first = false;
       if (fixpasses > 100000) return ctx->fail(C2G_ERR_STATE, "edge refinement did not converge");
     }
+    res->stats[7] = hcnt[11];
   }
 
   // ---- maxima actually reached (on any rank), output order ----

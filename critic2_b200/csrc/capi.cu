@@ -436,7 +436,7 @@ int c2g_basins_counts(c2g_basins* res, long long* counts) {
     C2G_CUDA(ctx, c2g_alloc(ctx, (void**)&d_counts, sizeof(unsigned long long) * res->nmax));
     C2G_CUDA(ctx, cudaMemsetAsync(d_counts, 0, sizeof(unsigned long long) * res->nmax, ctx->stream));
     const long long nnl = (long long)res->n[0] * res->n[1] * (res->zhi - res->zlo);
-    int rc = nnl > 0 ? c2g_launch_basin_reduce(ctx, nnl, res->d_label, 0, nullptr, res->nmax, nullptr, d_counts) : C2G_OK;
+    int rc = nnl > 0 ? c2g_launch_basin_reduce(ctx, nnl, res->d_label, 0x7fffffff, 0, nullptr, res->nmax, nullptr, d_counts) : C2G_OK;
     if (rc == C2G_OK && ctx->nranks > 1 &&
         ncclAllReduce(d_counts, d_counts, res->nmax, ncclUint64, ncclSum, (ncclComm_t)ctx->nccl, ctx->stream) != ncclSuccess)
       rc = ctx->fail(C2G_ERR_NCCL, "c2g_basins_counts: ncclAllReduce failed");

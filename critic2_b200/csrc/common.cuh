@@ -152,8 +152,9 @@ void c2g_yt_free_state(c2g_basins* res);
 void c2g_slab_bounds(int n3, int nranks, int rank, int* zlo, int* zhi);
 
 // integrate.cu: one streaming pass of per-maximum sums (sums[p*nmax+m]) and counts
-int c2g_launch_basin_reduce(c2g_context* ctx, long long nn, const int* label, int np, const double* const* f, int nmax,
-                            double* sums, unsigned long long* counts);
+// label_mask: 0x7fffffff for Bader labels (bit 31 = filled flag), -1 for YT labels (negative = no basin)
+int c2g_launch_basin_reduce(c2g_context* ctx, long long nn, const int* label, int label_mask, int np, const double* const* f,
+                            int nmax, double* sums, unsigned long long* counts);
 
 // stream-ordered pool allocations (cudaMallocAsync with an unbounded release threshold, set in c2g_init):
 // repeated calls reuse the same device memory instead of paying cudaMalloc/cudaFree every time

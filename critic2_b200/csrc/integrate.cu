@@ -5,18 +5,20 @@
 // padd = sum(fint, idg==i)*omega/ntot): the reference makes nattr full-grid passes per property;
 // this is ONE streaming pass over the labels and up to 4 fields per launch.
 //
-// Layout: each warp owns contiguous 2048-point segments (lane l reads base + 32k + l, so loads
-// are 256-byte coalesced).  Runs of warp-uniform labels are accumulated in registers, reduced with
-// shuffles and added to the per-maximum accumulators with one fp64 atomic per value; 32-point
-// groups that straddle a basin boundary are reduced per distinct label (match_any).
+// Layout: each warp owns contiguous segments of 128*SEG_ITERS points; per iteration a lane reads 4 consecutive
+// labels (one 16-byte load) and 4 consecutive values of every field (two 16-byte loads), so a warp covers 128
+// points with fully coalesced 512 B / 1 KB requests.  Every lane accumulates privately while the points carry
+// the warp's current label; only when the label changes (a basin boundary, about once per basin width) are
+// the lanes' partial sums reduced with shuffles and added to the per-maximum accumulators.
 // HBM traffic: 4 B (label) + 8 B per field per point.
 #include "common.cuh"
 
 namespace {
 
-constexpr int SEG_ITERS = 64;      // 32*64 = 2048 points per warp segment
+constexpr int SEG_ITERS = 16;      // 128*16 = 2048 points per warp segment
 constexpr int RED_BLOCKS_PER_SM = 8;
 constexpr int SMEM_TABLE_MAX = 6144;  // doubles per block (48 KB): nmax*(NP+1) must fit to use the shared table
+constexpr int LABEL_MASK = 0x7fffffff;  // bit 31 = filled-not-walked flag of bader.cu
 
 // Accumulator target: a per-block shared-memory table when it fits (hot global addresses would
 // serialise in the L2 atomic unit: measured ~10 M same-address fp64 atomics/s), else global atomics.
@@ -41,17 +43,53 @@ __device__ __forceinline__ void sink_add(const Sink& k, int label, const double*
 }
 
 template <int NP>
+struct Group {  // 4 consecutive points of one lane
+  int l[4];
+  double v[NP > 0 ? NP : 1][4];
+  unsigned valid;  // bit j: point j exists
+};
+
+template <int NP>
+__device__ __forceinline__ void load_group(Group<NP>& g, long long i, long long nn, const int* __restrict__ label, int mask,
+                                           bool vec, const double* const* fp) {
+  g.valid = 0;
+  if (vec && i + 3 < nn) {  // vec: label and every field are 16-byte aligned
+    const int4 l4 = *reinterpret_cast<const int4*>(label + i);
+    g.l[0] = l4.x & mask; g.l[1] = l4.y & mask; g.l[2] = l4.z & mask; g.l[3] = l4.w & mask;
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+      const double2 a = __ldg(reinterpret_cast<const double2*>(fp[p] + i));
+      const double2 b = __ldg(reinterpret_cast<const double2*>(fp[p] + i + 2));
+      g.v[p][0] = a.x; g.v[p][1] = a.y; g.v[p][2] = b.x; g.v[p][3] = b.y;
+    }
+    // negative labels (YT: interatomic-surface points) belong to no basin
+    g.valid = (g.l[0] >= 0 ? 1u : 0u) | (g.l[1] >= 0 ? 2u : 0u) | (g.l[2] >= 0 ? 4u : 0u) | (g.l[3] >= 0 ? 8u : 0u);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      g.l[j] = -1;
+      if (i + j < nn) {
+        g.l[j] = label[i + j] & mask;
+#pragma unroll
+        for (int p = 0; p < NP; p++) g.v[p][j] = __ldg(fp[p] + i + j);
+        if (g.l[j] >= 0) g.valid |= 1u << j;
+      }
+    }
+  }
+}
+
+template <int NP>
 __global__ void __launch_bounds__(256) k_basin_reduce(long long nn, const int* __restrict__ label,
                                                       const double* __restrict__ f0, const double* __restrict__ f1,
                                                       const double* __restrict__ f2, const double* __restrict__ f3,
-                                                      int nmax, int use_table, double* __restrict__ sums,
+                                                      int nmax, int use_table, int mask, int vec, double* __restrict__ sums,
                                                       unsigned long long* __restrict__ counts,
                                                       double* __restrict__ partials) {
   extern __shared__ double s_tab[];
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  const long long seg = 32ll * SEG_ITERS;
+  const long long seg = 128ll * SEG_ITERS;
   const double* fp[4] = {f0, f1, f2, f3};
   Sink sink{use_table ? s_tab : nullptr, sums, counts, nmax};
   if (use_table) {
@@ -61,11 +99,11 @@ __global__ void __launch_bounds__(256) k_basin_reduce(long long nn, const int* _
   double acc[NP > 0 ? NP : 1];
 #pragma unroll
   for (int p = 0; p < (NP > 0 ? NP : 1); p++) acc[p] = 0.0;
-  unsigned long long cnt = 0;
+  unsigned cnt = 0;
   int cur = -1;  // warp-uniform label of the current run
   auto flush = [&]() {
     if (cur >= 0 && __any_sync(0xffffffffu, cnt != 0)) {
-      unsigned long long c = cnt;
+      unsigned c = cnt;
 #pragma unroll
       for (int d = 16; d >= 1; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
       double s[NP > 0 ? NP : 1];
@@ -75,73 +113,34 @@ __global__ void __launch_bounds__(256) k_basin_reduce(long long nn, const int* _
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) s[p] += __shfl_xor_sync(0xffffffffu, s[p], d);
       }
-      if (lane == 0) sink_add<NP>(sink, cur, s, c);
+      if (lane == 0) sink_add<NP>(sink, cur, s, (unsigned long long)c);
     }
 #pragma unroll
     for (int p = 0; p < (NP > 0 ? NP : 1); p++) acc[p] = 0.0;
     cnt = 0;
   };
   for (long long base = warp * seg; base < nn; base += nwarps * seg) {
-    // software pipeline: the loads of group k+1 are in flight while group k is voted on
-    int l_next = -1;
-    double v_next[NP > 0 ? NP : 1];
-    {
-      const long long i = base + lane;
-      if (i < nn) {
-        l_next = label[i] & 0x7fffffff;  // bit 31 = filled-not-walked flag of bader.cu
-#pragma unroll
-        for (int p = 0; p < NP; p++) v_next[p] = __ldg(fp[p] + i);
-      }
-    }
+    Group<NP> g, gn;
+    load_group<NP>(gn, base + 4 * lane, nn, label, mask, vec != 0, fp);
     for (int k = 0; k < SEG_ITERS; k++) {
-      if (base + 32ll * k >= nn) break;
-      const int l = l_next;
-      double v[NP > 0 ? NP : 1];
+      if (base + 128ll * k >= nn) break;
+      g = gn;
+      if (k + 1 < SEG_ITERS) load_group<NP>(gn, base + 128ll * (k + 1) + 4 * lane, nn, label, mask, vec != 0, fp);  // prefetch
+      unsigned rem = g.valid;
+      for (;;) {
 #pragma unroll
-      for (int p = 0; p < NP; p++) v[p] = v_next[p];
-      l_next = -1;
-      if (k + 1 < SEG_ITERS) {
-        const long long i = base + 32ll * (k + 1) + lane;
-        if (i < nn) {
-          l_next = label[i] & 0x7fffffff;
+        for (int j = 0; j < 4; j++)
+          if (((rem >> j) & 1u) && g.l[j] == cur) {
 #pragma unroll
-          for (int p = 0; p < NP; p++) v_next[p] = __ldg(fp[p] + i);
-        }
-      }
-      if (__all_sync(0xffffffffu, l == cur)) {
-#pragma unroll
-        for (int p = 0; p < NP; p++) acc[p] += v[p];
-        cnt++;
-        continue;
-      }
-      flush();
-      const int l0 = __shfl_sync(0xffffffffu, l, 0);
-      if (__all_sync(0xffffffffu, l == l0)) {
-        cur = l0;
-        if (l0 >= 0) {
-#pragma unroll
-          for (int p = 0; p < NP; p++) acc[p] = v[p];
-          cnt = 1;
-        }
-        continue;
-      }
-      // mixed group: one reduction per distinct label
-      cur = -1;
-      unsigned todo = __ballot_sync(0xffffffffu, l >= 0);
-      while (todo) {
-        const int leader = __ffs(todo) - 1;
-        const int ll = __shfl_sync(0xffffffffu, l, leader);
-        const bool mine = (l == ll);
-        const unsigned grp = __ballot_sync(0xffffffffu, mine);
-        double s[NP > 0 ? NP : 1];
-#pragma unroll
-        for (int p = 0; p < NP; p++) {
-          s[p] = mine ? v[p] : 0.0;
-#pragma unroll
-          for (int d = 16; d >= 1; d >>= 1) s[p] += __shfl_xor_sync(0xffffffffu, s[p], d);
-        }
-        if (lane == 0) sink_add<NP>(sink, ll, s, (unsigned long long)__popc(grp));
-        todo &= ~grp;
+            for (int p = 0; p < NP; p++) acc[p] += g.v[p][j];
+            cnt++;
+            rem &= ~(1u << j);
+          }
+        const unsigned bal = __ballot_sync(0xffffffffu, rem != 0);
+        if (!bal) break;
+        flush();  // the run of `cur` ends inside this group
+        const int candl = (rem & 1u) ? g.l[0] : (rem & 2u) ? g.l[1] : (rem & 4u) ? g.l[2] : g.l[3];
+        cur = __shfl_sync(0xffffffffu, candl, __ffs(bal) - 1);  // label of the first remaining point in memory order
       }
     }
   }
@@ -168,24 +167,27 @@ __global__ void __launch_bounds__(256) k_reduce_partials(int nblocks, int np, in
 }  // namespace
 
 // sums[(p*nmax)+m], counts[m] per MAXIMUM index (device pointers, accumulated into); fields: up to 4 device arrays
-int c2g_launch_basin_reduce(c2g_context* ctx, long long nn, const int* label, int np, const double* const* f, int nmax,
-                            double* sums, unsigned long long* counts) {
+int c2g_launch_basin_reduce(c2g_context* ctx, long long nn, const int* label, int label_mask, int np, const double* const* f,
+                            int nmax, double* sums, unsigned long long* counts) {
   const int blocks = ctx->nsm * RED_BLOCKS_PER_SM;
   const double* f0 = np > 0 ? f[0] : nullptr;
   const double* f1 = np > 1 ? f[1] : nullptr;
   const double* f2 = np > 2 ? f[2] : nullptr;
   const double* f3 = np > 3 ? f[3] : nullptr;
   const int use_table = ((long long)(np + 1) * nmax <= SMEM_TABLE_MAX) ? 1 : 0;
+  int vec = ((uintptr_t)label % 16 == 0) ? 1 : 0;
+  for (int p = 0; p < np && p < 4; p++)
+    if ((uintptr_t)f[p] % 16 != 0) vec = 0;
   const size_t smem = use_table ? sizeof(double) * (size_t)(np + 1) * nmax : 0;
   double* partials = nullptr;
   if (use_table) C2G_CUDA(ctx, cudaMallocAsync(&partials, sizeof(double) * (size_t)blocks * (np + 1) * nmax, ctx->stream));
   ctx->prof_begin("basin_reduce");
   switch (np) {
-    case 0: k_basin_reduce<0><<<blocks, 256, smem, ctx->stream>>>(nn, label, f0, f1, f2, f3, nmax, use_table, sums, counts, partials); break;
-    case 1: k_basin_reduce<1><<<blocks, 256, smem, ctx->stream>>>(nn, label, f0, f1, f2, f3, nmax, use_table, sums, counts, partials); break;
-    case 2: k_basin_reduce<2><<<blocks, 256, smem, ctx->stream>>>(nn, label, f0, f1, f2, f3, nmax, use_table, sums, counts, partials); break;
-    case 3: k_basin_reduce<3><<<blocks, 256, smem, ctx->stream>>>(nn, label, f0, f1, f2, f3, nmax, use_table, sums, counts, partials); break;
-    default: k_basin_reduce<4><<<blocks, 256, smem, ctx->stream>>>(nn, label, f0, f1, f2, f3, nmax, use_table, sums, counts, partials); break;
+    case 0: k_basin_reduce<0><<<blocks, 256, smem, ctx->stream>>>(nn, label, f0, f1, f2, f3, nmax, use_table, label_mask, vec, sums, counts, partials); break;
+    case 1: k_basin_reduce<1><<<blocks, 256, smem, ctx->stream>>>(nn, label, f0, f1, f2, f3, nmax, use_table, label_mask, vec, sums, counts, partials); break;
+    case 2: k_basin_reduce<2><<<blocks, 256, smem, ctx->stream>>>(nn, label, f0, f1, f2, f3, nmax, use_table, label_mask, vec, sums, counts, partials); break;
+    case 3: k_basin_reduce<3><<<blocks, 256, smem, ctx->stream>>>(nn, label, f0, f1, f2, f3, nmax, use_table, label_mask, vec, sums, counts, partials); break;
+    default: k_basin_reduce<4><<<blocks, 256, smem, ctx->stream>>>(nn, label, f0, f1, f2, f3, nmax, use_table, label_mask, vec, sums, counts, partials); break;
   }
   int nl = 1;
   if (use_table) {
@@ -234,7 +236,7 @@ extern "C" int c2g_integrate(c2g_context* ctx, c2g_basins* res, int nprop, const
     const int np = std::min(4, nprop - k0);
     const double* fp[4] = {nullptr, nullptr, nullptr, nullptr};
     for (int p = 0; p < np; p++) fp[p] = ctx->grids[fieldhandles[k0 + p]].d + plane * res->zlo;
-    rc = c2g_launch_basin_reduce(ctx, nnl, res->d_label, np > 0 ? np : 0, fp, nmax, d_sums + (size_t)k0 * nmax,
+    rc = c2g_launch_basin_reduce(ctx, nnl, res->d_label, LABEL_MASK, np > 0 ? np : 0, fp, nmax, d_sums + (size_t)k0 * nmax,
                                  first ? d_counts : nullptr);
     first = false;
   }

@@ -641,7 +641,7 @@ int c2g_yt_integrate_impl(c2g_context* ctx, c2g_basins* res, int nprop, const in
     C2G_CUDA(ctx, cudaMemsetAsync(b_sums.p, 0, sizeof(double) * (size_t)(npe + 1) * nmax, st));
     const double* yp[4] = {nullptr, nullptr, nullptr, nullptr};
     for (int p = 0; p <= npe; p++) yp[p] = b_y.as<double>() + (size_t)p * nn;
-    rc = c2g_launch_basin_reduce(ctx, nn, res->d_label, npe + 1, yp, nmax, b_sums.as<double>(), nullptr);
+    rc = c2g_launch_basin_reduce(ctx, nn, res->d_label, -1, npe + 1, yp, nmax, b_sums.as<double>(), nullptr);
     if (rc) return rc;
     std::vector<double> part((size_t)(npe + 1) * nmax);
     C2G_CUDA(ctx, cudaMemcpyAsync(part.data(), b_sums.p, sizeof(double) * part.size(), cudaMemcpyDeviceToHost, st));
