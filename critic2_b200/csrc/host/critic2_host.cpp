@@ -1,0 +1,213 @@
+// critic2_host.cpp -- see critic2_host.hpp.  Calls the C ABI only; no field arithmetic happens here.
+#include "critic2_host.hpp"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+namespace c2h {
+
+namespace {
+c2g_context* g_ctx = nullptr;
+c2g_basins* g_basins = nullptr;  // result of the last BADER/YT call, consumed by intgrid_fields
+int g_hgrid = -1;                // resident copy of bas%f
+
+void check(int ier, const char* routine) {
+  if (ier != 0) ferror(routine, std::string("GPU: ") + c2g_last_error(g_ctx));
+}
+
+// 3x3 inverse (adjugate); the reference uses matinv = LAPACK dgetrf/dgetri (tools_math@proc.f90:1203-1235)
+void matinv3(const double a[9], double inv[9]) {
+  auto A = [&](int i, int j) { return a[i + 3 * j]; };
+  const double det = A(0, 0) * (A(1, 1) * A(2, 2) - A(1, 2) * A(2, 1)) - A(0, 1) * (A(1, 0) * A(2, 2) - A(1, 2) * A(2, 0)) +
+                     A(0, 2) * (A(1, 0) * A(2, 1) - A(1, 1) * A(2, 0));
+  if (det == 0.0) ferror("matinv", "singular matrix");
+  const double d = 1.0 / det;
+  inv[0 + 3 * 0] = (A(1, 1) * A(2, 2) - A(1, 2) * A(2, 1)) * d;
+  inv[0 + 3 * 1] = (A(0, 2) * A(2, 1) - A(0, 1) * A(2, 2)) * d;
+  inv[0 + 3 * 2] = (A(0, 1) * A(1, 2) - A(0, 2) * A(1, 1)) * d;
+  inv[1 + 3 * 0] = (A(1, 2) * A(2, 0) - A(1, 0) * A(2, 2)) * d;
+  inv[1 + 3 * 1] = (A(0, 0) * A(2, 2) - A(0, 2) * A(2, 0)) * d;
+  inv[1 + 3 * 2] = (A(0, 2) * A(1, 0) - A(0, 0) * A(1, 2)) * d;
+  inv[2 + 3 * 0] = (A(1, 0) * A(2, 1) - A(1, 1) * A(2, 0)) * d;
+  inv[2 + 3 * 1] = (A(0, 1) * A(2, 0) - A(0, 0) * A(2, 1)) * d;
+  inv[2 + 3 * 2] = (A(0, 0) * A(1, 1) - A(0, 1) * A(1, 0)) * d;
+}
+
+// shortest Cartesian length of a crystallographic difference vector over lattice translations
+double shortest(const double x2c[9], const double dxin[3]) {
+  double dx[3];
+  for (int i = 0; i < 3; i++) dx[i] = dxin[i] - std::round(dxin[i]);
+  double best = 1e300;
+  for (int a = -2; a <= 2; a++)
+    for (int b = -2; b <= 2; b++)
+      for (int c = -2; c <= 2; c++) {
+        const double v[3] = {dx[0] + a, dx[1] + b, dx[2] + c};
+        double r2 = 0.0;
+        for (int i = 0; i < 3; i++) {
+          const double ci = x2c[i] * v[0] + x2c[i + 3] * v[1] + x2c[i + 6] * v[2];
+          r2 += ci * ci;
+        }
+        best = std::min(best, std::sqrt(r2));
+      }
+  return best;
+}
+
+// the per-maximum attractor identification of bader@proc.f90:160-199 / yt@proc.f90:129-168
+void identify_attractors(system& s, basindat& bas, int nmax, const std::vector<int>& pmax, std::vector<int>& map) {
+  map.assign(nmax, 0);
+  for (int i = 0; i < nmax; i++) {
+    const double dv[3] = {(pmax[3 * i] - 1.0) / bas.n[0], (pmax[3 * i + 1] - 1.0) / bas.n[1], (pmax[3 * i + 2] - 1.0) / bas.n[2]};
+    if (bas.atexist) {
+      const int nid = s.identify_atom(dv, bas.ratom);
+      if (nid > 0) map[i] = nid;
+    }
+    if (map[i] == 0 && bas.ratom > vsmall) {
+      for (int l = 0; l < bas.nattr; l++)
+        if (s.are_lclose(dv, &bas.xattr[3 * l], bas.ratom)) { map[i] = l + 1; break; }
+    }
+    if (map[i] == 0) {  // (a DISCARD expression would be evaluated here, exactly as in the CPU path)
+      bas.nattr++;
+      bas.xattr.insert(bas.xattr.end(), dv, dv + 3);
+      map[i] = bas.nattr;
+    }
+  }
+}
+
+void upload_field(const basindat& bas, const char* routine) {
+  if ((long long)bas.f.size() != (long long)bas.n[0] * bas.n[1] * bas.n[2]) ferror(routine, "inconsistent field size");
+  if (g_hgrid >= 0) check(c2g_grid_free(g_ctx, g_hgrid), routine);
+  g_hgrid = -1;
+  check(c2g_grid_upload(g_ctx, bas.f.data(), bas.n, &g_hgrid), routine);
+  if (g_basins) { c2g_basins_free(g_basins); g_basins = nullptr; }
+}
+
+void finish_assignment(system& s, basindat& bas, int nmax, const char* routine) {
+  std::vector<int> pmax(3 * (size_t)nmax), map;
+  check(c2g_basins_maxima(g_basins, pmax.data()), routine);
+  if (bas.atexist) {  // atoms are the first attractors (bader@proc.f90:102-111)
+    bas.nattr = s.nat();
+    bas.xattr = s.xat;
+  } else {
+    bas.nattr = 0;
+    bas.xattr.clear();
+  }
+  identify_attractors(s, bas, nmax, pmax, map);
+  check(c2g_basins_set_map(g_basins, bas.nattr, map.data()), routine);
+  bas.idg.assign(bas.f.size(), 0);
+  check(c2g_basins_labels(g_basins, bas.idg.data()), routine);
+}
+}  // namespace
+
+void ferror(const std::string& routine, const std::string& msg) {
+  std::fprintf(stderr, "ERROR : %s: %s\n", routine.c_str(), msg.c_str());
+  throw fatal_error(routine + ": " + msg);
+}
+
+void system::set_cell(const double x2c[9]) {
+  std::memcpy(m_x2c, x2c, sizeof(m_x2c));
+  omega = std::fabs(x2c[0] * (x2c[4] * x2c[8] - x2c[7] * x2c[5]) - x2c[3] * (x2c[1] * x2c[8] - x2c[7] * x2c[2]) +
+                    x2c[6] * (x2c[1] * x2c[5] - x2c[4] * x2c[2]));
+}
+
+int system::identify_atom(const double x[3], double distmax) const {
+  int best = 0;
+  double dbest = 1e300;
+  for (int i = 0; i < nat(); i++) {
+    const double dx[3] = {x[0] - xat[3 * i], x[1] - xat[3 * i + 1], x[2] - xat[3 * i + 2]};
+    const double d = shortest(m_x2c, dx);
+    if (d < dbest) { dbest = d; best = i + 1; }
+  }
+  return (best > 0 && dbest <= distmax) ? best : 0;
+}
+
+bool system::are_lclose(const double x0[3], const double x1[3], double eps) const {
+  const double dx[3] = {x0[0] - x1[0], x0[1] - x1[1], x0[2] - x1[2]};
+  return shortest(m_x2c, dx) < eps;
+}
+
+void gpu_init(int device) {
+  if (g_ctx) return;
+  const int ier = c2g_init(device, &g_ctx);
+  if (ier != 0) ferror("gpu_init", g_ctx ? c2g_last_error(g_ctx) : "no usable CUDA device (there is no CPU fallback)");
+}
+
+void gpu_end() {
+  if (g_basins) c2g_basins_free(g_basins);
+  if (g_ctx) c2g_finalize(g_ctx);
+  g_basins = nullptr; g_ctx = nullptr; g_hgrid = -1;
+}
+
+bool gpu_enabled() { return g_ctx != nullptr; }
+
+void bader_integrate(system& s, basindat& bas) {
+  if (!g_ctx) ferror("bader_integrate", "gpu_init was not called");
+  // metrics, bader@proc.f90:124-145
+  double lat2car[9], car2lat[9], lid[27];
+  for (int i = 0; i < 3; i++)
+    for (int k = 0; k < 3; k++) lat2car[k + 3 * i] = s.m_x2c[k + 3 * i] / bas.n[i];
+  matinv3(lat2car, car2lat);
+  for (int i = -1; i <= 1; i++)
+    for (int j = -1; j <= 1; j++)
+      for (int k = -1; k <= 1; k++) {
+        double r2 = 0.0;
+        for (int c = 0; c < 3; c++) {
+          const double d = lat2car[c] * i + lat2car[c + 3] * j + lat2car[c + 6] * k;
+          r2 += d * d;
+        }
+        lid[(i + 1) * 9 + (j + 1) * 3 + (k + 1)] = (i || j || k) ? 1.0 / std::sqrt(r2) : 0.0;
+      }
+  upload_field(bas, "bader_integrate");
+  int nmax = 0;
+  check(c2g_bader_assign(g_ctx, g_hgrid, car2lat, lid, C2G_BADER_FAST, C2G_ORDER_SCAN, &nmax, &g_basins), "bader_integrate");
+  bas.is_yt = false;
+  finish_assignment(s, bas, nmax, "bader_integrate");
+}
+
+void yt_integrate(system& s, basindat& bas) {
+  if (!g_ctx) ferror("yt_integrate", "gpu_init was not called");
+  if (s.grid.nvec <= 0) ferror("yt_integrate", "the grid has no Voronoi stencil (init_geometry)");
+  upload_field(bas, "yt_integrate");
+  int nmax = 0;
+  check(c2g_yt_build(g_ctx, g_hgrid, s.grid.nvec, s.grid.vec.data(), s.grid.area.data(), &nmax, &g_basins), "yt_integrate");
+  bas.is_yt = true;
+  finish_assignment(s, bas, nmax, "yt_integrate");
+}
+
+void intgrid_fields(const system& s, const basindat& bas, const std::vector<const double*>& fint, std::vector<int_result>& res,
+                    std::vector<double>& vol) {
+  if (!g_ctx || !g_basins) ferror("intgrid_fields", "no basin assignment on the device");
+  const int nprop = (int)fint.size();
+  std::vector<int> h(nprop, -1);
+  for (int k = 0; k < nprop; k++) check(c2g_grid_upload(g_ctx, fint[k], bas.n, &h[k]), "intgrid_fields");
+  std::vector<double> psum((size_t)bas.nattr * std::max(nprop, 1));
+  vol.assign(bas.nattr, 0.0);
+  check(c2g_integrate(g_ctx, g_basins, nprop, h.data(), s.omega, psum.data(), vol.data()), "intgrid_fields");
+  for (int k = 0; k < nprop; k++) check(c2g_grid_free(g_ctx, h[k]), "intgrid_fields");
+  res.assign(nprop, int_result());
+  for (int k = 0; k < nprop; k++) res[k].psum.assign(psum.begin() + (size_t)k * bas.nattr, psum.begin() + (size_t)(k + 1) * bas.nattr);
+}
+
+void yt_weights(const basindat& bas, int idb, std::vector<double>& w) {
+  if (!g_ctx || !g_basins || !bas.is_yt) ferror("yt_weights", "no YT assignment on the device");
+  w.assign(bas.f.size(), 0.0);
+  check(c2g_yt_weights(g_basins, idb, w.data()), "yt_weights");
+}
+
+void nci_rdg(const system& s, std::vector<double>& crho, std::vector<double>& cgrad) {
+  if (!g_ctx) ferror("nciplot", "gpu_init was not called");
+  const grid3& g = s.grid;
+  int h = -1;
+  check(c2g_grid_upload(g_ctx, g.f.data(), g.n, &h), "nciplot");
+  double c2x[9], xmat[9];
+  matinv3(s.m_x2c, c2x);
+  for (int i = 0; i < 3; i++)
+    for (int k = 0; k < 3; k++) xmat[k + 3 * i] = s.m_x2c[k + 3 * i] / g.n[i];  // nci@proc.f90:426
+  const double x0[3] = {0.0, 0.0, 0.0};
+  crho.assign(g.f.size(), 0.0);
+  cgrad.assign(g.f.size(), 0.0);
+  check(c2g_nci_rdg(g_ctx, h, x0, xmat, g.n, c2x, s.m_x2c, c2x, 0, nullptr, crho.data(), cgrad.data()), "nciplot");
+  check(c2g_grid_free(g_ctx, h), "nciplot");
+}
+
+}  // namespace c2h

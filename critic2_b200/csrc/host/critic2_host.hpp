@@ -1,0 +1,92 @@
+// critic2_host.hpp -- C++ mirror of the reference's driver interface for the on-grid QTAIM path.
+//
+// critic2's host code is Fortran; this image has no Fortran compiler, so the host side above the C ABI
+// (include/critic2_gpu.h) is mirrored here in C++ with the reference's names, argument meaning and error
+// behaviour.  Nothing in this directory computes on the CPU what the GPU path computes: every routine
+// marshals the reference's objects into C-ABI calls, exactly like fortran/critic2_gpu.f90.
+//
+//   types.f90:361-383          basindat      ->  c2h::basindat
+//   grid3mod.f90:60-125        grid3         ->  c2h::grid3
+//   systemmod.f90:44-86        system        ->  c2h::system (crystal cell + atoms + one reference grid field)
+//   bader@proc.f90:80-234      bader_integrate(s,bas,iref)
+//   yt@proc.f90:38-224         yt_integrate(s,bas)
+//   integration@proc.f90:1170  intgrid_fields(bas,res)
+//   nci@proc.f90:543-605       nciplot loop -> nci_rdg
+//   tools_io@proc.F90:1573     ferror(routine,msg,faterr) -> c2h::ferror (throws c2h::fatal_error)
+#pragma once
+
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../../include/critic2_gpu.h"
+
+namespace c2h {
+
+struct fatal_error : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+// ferror(routine,msg,faterr): the reference prints "ERROR : routine: msg" and stops (tools_io@proc.F90:1573-1643)
+[[noreturn]] void ferror(const std::string& routine, const std::string& msg);
+
+constexpr double vsmall = 1e-80;  // param.F90:27
+
+// grid3mod.f90:60-125 (the members the path reads)
+struct grid3 {
+  int n[3] = {0, 0, 0};
+  std::vector<double> f;       // f(n1,n2,n3), index 1 fastest
+  int nvec = 0;                // Voronoi-relevant grid steps (init_geometry, grid3mod@proc.f90:3197)
+  std::vector<int> vec;        // vec(3,nvec)
+  std::vector<double> area;    // area(nvec)
+};
+
+// crystal + field: what bader_integrate / yt_integrate read through sy%c and sy%f(iref)
+struct system {
+  double m_x2c[9] = {0};       // crystallographic -> Cartesian, column-major (crystalmod)
+  double omega = 0.0;          // cell volume
+  std::vector<double> xat;     // atoms (nuclear CPs of the reference field), crystallographic, (3,nat)
+  grid3 grid;                  // sy%f(iref)%grid
+  int nat() const { return (int)(xat.size() / 3); }
+  // crystalmod@env.f90:593-614: id (1-based) of the atom within distmax of x (cryst.), 0 if none
+  int identify_atom(const double x[3], double distmax) const;
+  // crystalmod@proc.f90:1118-1133: are two crystallographic points closer than eps (any lattice translation)?
+  bool are_lclose(const double x0[3], const double x1[3], double eps) const;
+  void set_cell(const double x2c[9]);
+};
+
+// types.f90:361-383
+struct basindat {
+  bool atexist = true;         // attractors are assigned to atoms (integration@proc.f90:243-252)
+  double ratom = 1.0;          // distance below which a maximum is an atom / a known attractor
+  int n[3] = {0, 0, 0};
+  std::vector<double> f;       // copy of the reference field (integration@proc.f90:255-271)
+  int nattr = 0;
+  std::vector<double> xattr;   // (3,nattr) crystallographic
+  std::vector<int> idg;        // idg(n1,n2,n3)
+  bool is_yt = false;          // weights live on the device (the reference's luw scratch unit)
+};
+
+// types.f90:394-410 (the sums only)
+struct int_result {
+  std::vector<double> psum;    // psum(nattr)
+};
+
+// One GPU context per process, like the module variables of fortran/critic2_gpu.f90.
+void gpu_init(int device = 0);   // CRITIC2_GPU=1 in the Fortran shim
+void gpu_end();
+bool gpu_enabled();
+
+// bader@proc.f90:80-234.  Fills bas.idg, bas.nattr, bas.xattr.
+void bader_integrate(system& s, basindat& bas);
+// yt@proc.f90:38-224.  bas.idg = spatial basin id, 0 on interatomic-surface points.
+void yt_integrate(system& s, basindat& bas);
+// integration@proc.f90:1170-1391: res[k].psum(i) = integral of fint[k] over basin i; vol(i) = basin volume.
+void intgrid_fields(const system& s, const basindat& bas, const std::vector<const double*>& fint,
+                    std::vector<int_result>& res, std::vector<double>& vol);
+// yt@proc.f90:476-499 (yt_weights with idb): dense weight field of one basin.
+void yt_weights(const basindat& bas, int idb, std::vector<double>& w);
+// nci@proc.f90:543-605, grid interpolation mode on the field's own lattice:
+// crho, cgrad(0:n3-1,0:n2-1,0:n1-1), third index fastest.
+void nci_rdg(const system& s, std::vector<double>& crho, std::vector<double>& cgrad);
+
+}  // namespace c2h

@@ -62,3 +62,17 @@ def test_product_path_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 txt = open(os.path.join(root, f)).read()
                 assert "liboracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
+
+
+def test_host_mirror_library_exports_the_reference_driver_names():
+    """critic2_b200/libcritic2_host.so: the C++ mirror of bader_integrate / yt_integrate / intgrid_fields / nciplot
+    (csrc/host/critic2_host.hpp) must build and link against the C ABI only."""
+    import subprocess
+    lib = os.path.join(ROOT, "critic2_b200", "libcritic2_host.so")
+    assert os.path.exists(lib), "run __graft_entry__.build()"
+    syms = subprocess.run(["nm", "-DC", "--defined-only", lib], capture_output=True, text=True).stdout
+    for name in ("c2h::bader_integrate", "c2h::yt_integrate", "c2h::intgrid_fields", "c2h::yt_weights", "c2h::nci_rdg",
+                 "c2h::ferror", "c2h::gpu_init", "c2h::system::identify_atom", "c2h::system::are_lclose"):
+        assert name in syms, name
+    und = subprocess.run(["nm", "-DC", "--undefined-only", lib], capture_output=True, text=True).stdout
+    assert "c2g_bader_assign" in und and "orc_" not in und
