@@ -16,6 +16,9 @@ LIB_PATH = os.path.join(_HERE, "libcritic2_gpu.so")
 _lib = None
 
 BADER_FAST, BADER_EXACT = 0, 1
+# ifformat_as_ft_* codes of the reference (param.F90:225-236)
+FT_CODES = {"x": 33, "y": 34, "z": 35, "xx": 36, "xy": 37, "xz": 38, "yy": 39, "yz": 40, "zz": 41,
+            "grad": 42, "lap": 43, "pot": 44}
 ORDER_INDEX, ORDER_SCAN = 0, 1
 
 EXPORTS = [
@@ -23,7 +26,7 @@ EXPORTS = [
     "c2g_grid_upload", "c2g_grid_upload_slab", "c2g_slab_range", "c2g_slab_bounds_query", "c2g_grid_alloc", "c2g_grid_download", "c2g_grid_download_slab", "c2g_grid_free", "c2g_grid_promolecular",
     "c2g_bader_assign", "c2g_basins_maxima", "c2g_basins_counts", "c2g_basins_set_map", "c2g_basins_labels",
     "c2g_basins_relabel", "c2g_basins_free", "c2g_basins_stats", "c2g_integrate", "c2g_yt_build",
-    "c2g_yt_weights", "c2g_nci_rdg", "c2g_nci_rdg_resident", "c2g_profile_enable", "c2g_profile_count",
+    "c2g_yt_weights", "c2g_nci_rdg", "c2g_nci_rdg_resident", "c2g_fft_derivative", "c2g_nci_rdg_fourier", "c2g_profile_enable", "c2g_profile_count",
     "c2g_profile_get", "c2g_profile_reset", "c2g_launch_count", "c2g_flush_l2", "c2g_synchronize", "c2g_timer_start", "c2g_timer_stop",
 ]
 
@@ -191,6 +194,31 @@ class Context:
                                                 _p(nstep, C.c_int), _p(_m33(c2x), C.c_double), _p(_m33(x2c), C.c_double),
                                                 _p(_m33(c2x), C.c_double), C.c_int(0), None, C.byref(hr), C.byref(hg)))
         return hr.value, hg.value
+
+    # ---- FFT-derived fields (grid3%fft) and NCIPLOT FOURIER mode ----
+    def fft_derivative(self, h, x2c, what):
+        """New resident grid = grid3%fft(h, ifformat_as_ft_<what>) (grid3mod@proc.f90:1757-1872)."""
+        iff = FT_CODES[what] if isinstance(what, str) else int(what)
+        out = C.c_int(-1)
+        self._chk(self.lib.c2g_fft_derivative(self.h, C.c_int(h), C.c_int(iff), _p(_m33(x2c), C.c_double), C.byref(out)))
+        return out.value
+
+    def nci_rdg_fourier(self, handles, x2c, n, nstep=None, x0=None, xmat=None):
+        """handles = (rho, |grad rho|, Hxx, Hyy, Hzz) resident grids (nci@proc.f90:527-565)."""
+        x2c = np.asarray(x2c, dtype=np.float64)
+        c2x = np.linalg.inv(x2c)
+        nstep = np.array(n if nstep is None else nstep, dtype=np.int32)
+        if xmat is None:
+            xmat = x2c / nstep.astype(np.float64)[None, :]
+        x0 = np.zeros(3) if x0 is None else np.ascontiguousarray(x0, dtype=np.float64)
+        hh = np.ascontiguousarray(handles, dtype=np.int32)
+        shape = (int(nstep[2]), int(nstep[1]), int(nstep[0]))
+        crho = np.zeros(shape, order="F")
+        cgrad = np.zeros(shape, order="F")
+        self._chk(self.lib.c2g_nci_rdg_fourier(self.h, _p(hh, C.c_int), _p(x0, C.c_double), _p(_m33(xmat), C.c_double),
+                                               _p(nstep, C.c_int), _p(_m33(c2x), C.c_double), _p(_m33(c2x), C.c_double),
+                                               _p(crho, C.c_double), _p(cgrad, C.c_double)))
+        return crho, cgrad
 
     # ---- profiling ----
     def profile_enable(self, on=True):

@@ -270,6 +270,139 @@ __global__ void __launch_bounds__(256) k_nci_rdg(const __grid_constant__ NciPara
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// FOURIER mode (nci@proc.f90:527-565): every quantity is a field%grd call with nder = 0, i.e. the raw node
+// value when the point is within neargrideps = 1e-12 grid units of a node (fieldmod@proc.f90:948-961), else
+// grid3%interp: tricubic for rho (the reference field keeps its mode), TRILINEAR for the FFT-derived
+// |grad rho|, Hxx, Hyy, Hzz grids (:534-537, grid3mod@proc.f90:2323-2370).
+// ------------------------------------------------------------------------------------------------
+struct GridPos {
+  bool isgrid;
+  int node[3];   // nearest node (valid when isgrid)
+  int idx[3];    // floor cell
+  double t[3];   // tricubic offset xs - idx
+  double r[3];   // trilinear weight n*x0 - idx
+};
+__device__ __forceinline__ void grid_pos(const NciParams& P, const double wx[3], GridPos& g) {
+  const int nn[3] = {P.n1, P.n2, P.n3};
+  g.isgrid = true;
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    double xi = wx[d] - floor(wx[d]);  // modulo(wx,1d0)
+    if (xi >= 1.0) xi = 0.0;
+    const double xs = __dmul_rn(xi, (double)nn[d]);
+    const double nr = floor(xs + 0.5);  // nint of a non-negative number
+    if (!(fabs(xs - nr) < 1e-12)) g.isgrid = false;
+    g.node[d] = imod((int)nr, nn[d]);
+    const int fl = (int)floor(xs);
+    g.idx[d] = imod(fl, nn[d]);
+    g.t[d] = xs - (double)g.idx[d];
+    g.r[d] = __dadd_rn(__dadd_rn(__dmul_rn((double)nn[d], xi), -(double)(g.idx[d] + 1)), 1.0);  // f%n*x0 - idx + 1, idx 1-based
+  }
+}
+__device__ __forceinline__ double tricubic_value(const NciParams& P, const double* __restrict__ rho, const GridPos& g) {
+  const int xs_[4] = {imod(g.idx[0] - 1, P.n1), g.idx[0], imod(g.idx[0] + 1, P.n1), imod(g.idx[0] + 2, P.n1)};
+  const int ys_[4] = {imod(g.idx[1] - 1, P.n2), g.idx[1], imod(g.idx[1] + 1, P.n2), imod(g.idx[1] + 2, P.n2)};
+  const int zs_[4] = {imod(g.idx[2] - 1, P.n3), g.idx[2], imod(g.idx[2] + 1, P.n3), imod(g.idx[2] + 2, P.n3)};
+  if (g.t[0] == 0.0 && g.t[1] == 0.0 && g.t[2] == 0.0) return __ldg(rho + xs_[1] + (size_t)P.n1 * (ys_[1] + (size_t)P.n2 * zs_[1]));
+  double w[3][4];
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    const double u = g.t[d], u2 = u * u, u3 = u2 * u;
+    w[d][0] = 0.5 * (-u3 + 2.0 * u2 - u);
+    w[d][1] = 0.5 * (3.0 * u3 - 5.0 * u2 + 2.0);
+    w[d][2] = 0.5 * (-3.0 * u3 + 4.0 * u2 + u);
+    w[d][3] = 0.5 * (u3 - u2);
+  }
+  double f = 0.0;
+#pragma unroll 1
+  for (int c = 0; c < 4; c++) {
+    double p0 = 0.0;
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      double r0 = 0.0;
+#pragma unroll
+      for (int a = 0; a < 4; a++) r0 += w[0][a] * __ldg(rho + xs_[a] + (size_t)P.n1 * (ys_[b] + (size_t)P.n2 * zs_[c]));
+      p0 += w[1][b] * r0;
+    }
+    f += w[2][c] * p0;
+  }
+  return f;
+}
+// grinterp_trilinear value in the reference's operation order (:2349-2362)
+__device__ __forceinline__ double trilinear_value(const NciParams& P, const double* __restrict__ f, const GridPos& g) {
+  const int x0 = g.idx[0], x1 = imod(g.idx[0] + 1, P.n1);
+  const int y0 = g.idx[1], y1 = imod(g.idx[1] + 1, P.n2);
+  const int z0 = g.idx[2], z1 = imod(g.idx[2] + 1, P.n3);
+  auto F = [&](int x, int y, int z) { return __ldg(f + x + (size_t)P.n1 * (y + (size_t)P.n2 * z)); };
+  const double r1 = g.r[0], r2 = g.r[1], r3 = g.r[2];
+  const double s1 = 1.0 - r1, s2 = 1.0 - r2, s3 = 1.0 - r3;
+  // ff(i,j,2) = ff(i,j,0)*s3 + ff(i,j,1)*r3 ; ff(i,2,2) = ff(i,0,2)*s2 + ff(i,1,2)*r2 ; ff(2,2,2) = ff(0,2,2)*s1 + ff(1,2,2)*r1
+  const double a00 = F(x0, y0, z0) * s3 + F(x0, y0, z1) * r3, a01 = F(x0, y1, z0) * s3 + F(x0, y1, z1) * r3;
+  const double a10 = F(x1, y0, z0) * s3 + F(x1, y0, z1) * r3, a11 = F(x1, y1, z0) * s3 + F(x1, y1, z1) * r3;
+  const double b0 = a00 * s2 + a01 * r2, b1 = a10 * s2 + a11 * r2;
+  return b0 * s1 + b1 * r1;
+}
+__device__ __forceinline__ double grd0_value(const NciParams& P, const double* __restrict__ f, const GridPos& g, bool trilinear) {
+  if (g.isgrid) return __ldg(f + g.node[0] + (size_t)P.n1 * (g.node[1] + (size_t)P.n2 * g.node[2]));
+  return trilinear ? trilinear_value(P, f, g) : tricubic_value(P, f, g);
+}
+
+__global__ void __launch_bounds__(256) k_nci_rdg_fourier(const __grid_constant__ NciParams P, const double* __restrict__ rho,
+                                                         const double* __restrict__ fgrad, const double* __restrict__ fxx,
+                                                         const double* __restrict__ fyy, const double* __restrict__ fzz,
+                                                         double* __restrict__ crho, double* __restrict__ cgrad) {
+  __shared__ double s_rho[BI * BJ * BK];
+  __shared__ double s_grad[BI * BJ * BK];
+  const int tid = threadIdx.x;
+  const int li = tid % BI, lj = (tid / BI) % BJ, lk = tid / (BI * BJ);
+  const int i = blockIdx.x * BI + li, j = blockIdx.y * BJ + lj, k = blockIdx.z * BK + lk;
+  double out_rho = 0.0, out_grad = 0.0;
+  if (i < P.ns1 && j < P.ns2 && k < P.ns3) {
+    double wx[3];
+    {
+      double x[3];
+#pragma unroll
+      for (int d = 0; d < 3; d++) {
+        double v = __dadd_rn(P.x0[d], __dmul_rn((double)i, P.xmat[d]));
+        v = __dadd_rn(v, __dmul_rn((double)j, P.xmat[d + 3]));
+        v = __dadd_rn(v, __dmul_rn((double)k, P.xmat[d + 6]));
+        x[d] = v;
+      }
+#pragma unroll
+      for (int d = 0; d < 3; d++) {
+        double s = __dmul_rn(P.c2x[d], x[0]);
+        s = __dadd_rn(s, __dmul_rn(P.c2x[d + 3], x[1]));
+        s = __dadd_rn(s, __dmul_rn(P.c2x[d + 6], x[2]));
+        if (s < -1e-4 || s > 1.0 + 1e-4) s = s - floor(s);
+        wx[d] = s;
+      }
+    }
+    GridPos g;
+    grid_pos(P, wx, g);
+    const double f = grd0_value(P, rho, g, false);
+    const double gm = grd0_value(P, fgrad, g, true);
+    const double hx = grd0_value(P, fxx, g, true), hy = grd0_value(P, fyy, g, true), hz = grd0_value(P, fzz, g, true);
+    const double pi = 3.14159265358979323846264338328;
+    const double cst = 2.0 * pow(3.0 * pi * pi, 1.0 / 3.0);
+    out_grad = gm / (cst * pow(fmax(f, 1e-80), 4.0 / 3.0));
+    const int npos = (hx > 0.0) + (hy > 0.0) + (hz > 0.0);
+    out_rho = (npos >= 2 ? fabs(f) : -fabs(f)) * 100.0;
+  }
+  s_rho[(li * BJ + lj) * BK + lk] = out_rho;
+  s_grad[(li * BJ + lj) * BK + lk] = out_grad;
+  __syncthreads();
+  {
+    const int ok = tid % BK, oj = (tid / BK) % BJ, oi = tid / (BK * BJ);
+    const int gi = blockIdx.x * BI + oi, gj = blockIdx.y * BJ + oj, gk = blockIdx.z * BK + ok;
+    if (gi < P.ns1 && gj < P.ns2 && gk < P.ns3) {
+      const size_t o = (size_t)gk + (size_t)P.ns3 * ((size_t)gj + (size_t)P.ns2 * gi);
+      crho[o] = s_rho[(oi * BJ + oj) * BK + ok];
+      cgrad[o] = s_grad[(oi * BJ + oj) * BK + ok];
+    }
+  }
+}
+
 int nci_launch(c2g_context* ctx, int handle, const double x0[3], const double xmat[9], const int nstep[3],
                const double c2x[9], const double x2c[9], const double c2xl[9], int nnuc, const double* nuc_cart,
                double* d_rho, double* d_grad) {
@@ -349,4 +482,47 @@ extern "C" int c2g_nci_rdg_resident(c2g_context* ctx, int handle, const double x
   if ((rc = c2g_grid_alloc(ctx, nout, hrho)) != C2G_OK) return rc;
   if ((rc = c2g_grid_alloc(ctx, nout, hgrad)) != C2G_OK) return rc;
   return nci_launch(ctx, handle, x0, xmat, nstep, c2x, x2c, c2xl, nnuc, nuc_cart, ctx->grids[*hrho].d, ctx->grids[*hgrad].d);
+}
+
+// FOURIER mode: h = {rho, |grad rho|, Hxx, Hyy, Hzz} resident grids of the same shape (the last four from
+// c2g_fft_derivative with C2G_FT_GRAD, _XX, _YY, _ZZ, as nci@proc.f90:528-531 loads them)
+extern "C" int c2g_nci_rdg_fourier(c2g_context* ctx, const int h[5], const double x0[3], const double xmat[9],
+                                   const int nstep[3], const double c2x[9], const double c2xl[9], double* crho,
+                                   double* cgrad) {
+  if (!ctx) return C2G_ERR_ARG;
+  if (!h || !crho || !cgrad) return ctx->fail(C2G_ERR_ARG, "c2g_nci_rdg_fourier: null argument");
+  int rc = nci_check(ctx, h[0], x0, xmat, nstep, c2x, c2x, c2xl, 0, nullptr);
+  if (rc) return rc;
+  const c2g_grid& g0 = ctx->grids[h[0]];
+  for (int q = 1; q < 5; q++) {
+    if (h[q] < 0 || h[q] >= (int)ctx->grids.size() || !ctx->grids[h[q]].used)
+      return ctx->fail(C2G_ERR_ARG, "c2g_nci_rdg_fourier: invalid grid handle %d", h[q]);
+    const c2g_grid& gq = ctx->grids[h[q]];
+    if (gq.n[0] != g0.n[0] || gq.n[1] != g0.n[1] || gq.n[2] != g0.n[2])
+      return ctx->fail(C2G_ERR_ARG, "c2g_nci_rdg_fourier: the derived grids must have the shape of rho");
+  }
+  NciParams P;
+  P.n1 = g0.n[0]; P.n2 = g0.n[1]; P.n3 = g0.n[2];
+  P.ns1 = nstep[0]; P.ns2 = nstep[1]; P.ns3 = nstep[2];
+  memcpy(P.x0, x0, sizeof(P.x0));
+  memcpy(P.xmat, xmat, sizeof(P.xmat));
+  memcpy(P.c2x, c2x, sizeof(P.c2x));
+  memcpy(P.x2c, c2x, sizeof(P.x2c));  // unused in this mode
+  memcpy(P.c2xl, c2xl, sizeof(P.c2xl));
+  P.nnuc = 0;
+  const size_t nout = (size_t)nstep[0] * nstep[1] * nstep[2];
+  DevBuf d_rho, d_grad;
+  C2G_CUDA(ctx, d_rho.alloc(ctx, sizeof(double) * nout));
+  C2G_CUDA(ctx, d_grad.alloc(ctx, sizeof(double) * nout));
+  dim3 grid((nstep[0] + BI - 1) / BI, (nstep[1] + BJ - 1) / BJ, (nstep[2] + BK - 1) / BK);
+  ctx->prof_begin("nci_rdg_fourier");
+  k_nci_rdg_fourier<<<grid, 256, 0, ctx->stream>>>(P, ctx->grids[h[0]].d, ctx->grids[h[1]].d, ctx->grids[h[2]].d,
+                                                   ctx->grids[h[3]].d, ctx->grids[h[4]].d, d_rho.as<double>(), d_grad.as<double>());
+  ctx->prof_end();
+  C2G_KERNEL_CHECK(ctx);
+  C2G_CUDA(ctx, cudaMemcpyAsync(crho, d_rho.p, sizeof(double) * nout, cudaMemcpyDeviceToHost, ctx->stream));
+  C2G_CUDA(ctx, cudaMemcpyAsync(cgrad, d_grad.p, sizeof(double) * nout, cudaMemcpyDeviceToHost, ctx->stream));
+  C2G_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->prof_collect();
+  return C2G_OK;
 }

@@ -144,6 +144,33 @@ int c2g_nci_rdg_resident(c2g_context* ctx, int handle, const double x0[3], const
                          const int nstep[3], const double c2x[9], const double x2c[9], const double c2xl[9],
                          int nnuc, const double* nuc_cart, int* hrho, int* hgrad);
 
+/* ---- FFT-derived fields: grid3%fft (grid3mod@proc.f90:1757-1872; LOAD AS LAP/GRAD, the `lap`/`gmod`
+ * integrables, NCIPLOT FOURIER mode) ---- */
+/* iff = the reference's ifformat_as_ft_* codes (param.F90:225-236) */
+#define C2G_FT_X 33
+#define C2G_FT_Y 34
+#define C2G_FT_Z 35
+#define C2G_FT_XX 36
+#define C2G_FT_XY 37
+#define C2G_FT_XZ 38
+#define C2G_FT_YY 39
+#define C2G_FT_YZ 40
+#define C2G_FT_ZZ 41
+#define C2G_FT_GRAD 42 /* |grad f| */
+#define C2G_FT_LAP 43
+#define C2G_FT_POT 44
+/* x2c(3,3): crystallographic -> Cartesian matrix of the grid (grid3%x2c).  The result is a new resident
+ * grid of the same shape (fnew%f); download it with c2g_grid_download or feed it to c2g_integrate.
+ * Single GPU.  Uses cuFFT for the transforms. */
+int c2g_fft_derivative(c2g_context* ctx, int handle, int iff, const double x2c[9], int* hout);
+
+/* NCIPLOT loop with FOURIER interpolation (nci@proc.f90:527-565): h = {rho, |grad rho|, Hxx, Hyy, Hzz}
+ * resident grids (the derived ones from c2g_fft_derivative with C2G_FT_GRAD, _XX, _YY, _ZZ, :528-531);
+ * rho is read with the tricubic interpolant, the derived grids TRILINEARLY (:534-537), each with the
+ * node short-cut of field%grd (fieldmod@proc.f90:948-961).  Outputs as c2g_nci_rdg. */
+int c2g_nci_rdg_fourier(c2g_context* ctx, const int h[5], const double x0[3], const double xmat[9],
+                        const int nstep[3], const double c2x[9], const double c2xl[9], double* crho, double* cgrad);
+
 /* ---- profiling: CUDA-event timings of the kernels launched by the last API call ---- */
 int c2g_profile_enable(c2g_context* ctx, int on);
 int c2g_profile_count(c2g_context* ctx);

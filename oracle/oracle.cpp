@@ -24,6 +24,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <complex>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -1090,6 +1091,273 @@ void orc_promolecular(const int* n, const double* x2c, int nat, const double* xa
                 }
               }
         f[i + (size_t)n1 * (j + (size_t)n2 * k)] = s;
+      }
+}
+
+
+// ---------------------------------------------------------------------------
+// FFT-derived fields.  Restates grid3%fft (grid3mod@proc.f90:1757-1872) on top of a plain complex
+// 3-D DFT with the conventions of cfftnd (cfftnd.f90:30-120, FFTPACK5 cmfm1f/cmfm1b): sgn = -1 is
+// the forward transform exp(-2 pi i jk/n) SCALED by 1/ntot, sgn = +1 the unscaled backward one.
+// The DFT itself is a mixed-radix decimation-in-time recursion (O(p^2) butterflies for a prime
+// factor p); it is not FFTPACK's operation order, so results agree with the reference to
+// rounding (a few ulp of max|f| log ntot), which is what the tests allow.
+// ---------------------------------------------------------------------------
+typedef std::complex<double> cplx;
+// 1-D DFT of length n (input with stride), mixed-radix decimation in time; sgn = -1 forward, +1 backward
+static void dft1_go(int n, int stride, const cplx* in, cplx* out, int sgn) {
+  if (n == 1) { out[0] = in[0]; return; }
+  int p = n;
+  for (int q = 2; q * q <= n; q++)
+    if (n % q == 0) { p = q; break; }
+  const int m = n / p;
+  const double pi = 3.14159265358979323846264338328;
+  if (m == 1) {  // prime length: direct sum
+    for (int k = 0; k < n; k++) {
+      cplx s = 0.0;
+      for (int j = 0; j < n; j++) {
+        const double a = sgn * 2.0 * pi * (double)((long long)j * k % n) / n;
+        s += in[(size_t)j * stride] * cplx(std::cos(a), std::sin(a));
+      }
+      out[k] = s;
+    }
+    return;
+  }
+  std::vector<cplx> tmp(n);  // p interleaved sub-sequences of length m
+  for (int r = 0; r < p; r++) dft1_go(m, stride * p, in + (size_t)r * stride, tmp.data() + (size_t)r * m, sgn);
+  for (int k = 0; k < m; k++)
+    for (int q = 0; q < p; q++) {
+      cplx s = 0.0;
+      const int kk = k + q * m;
+      for (int r = 0; r < p; r++) {
+        const double a = sgn * 2.0 * pi * (double)((long long)r * kk % n) / n;
+        s += tmp[(size_t)r * m + k] * cplx(std::cos(a), std::sin(a));
+      }
+      out[kk] = s;
+    }
+}
+static void dft1(int n, cplx* line, int sgn, std::vector<cplx>& a, std::vector<cplx>& b) {
+  a.assign(line, line + n);
+  b.resize(n);
+  dft1_go(n, 1, a.data(), b.data(), sgn);
+  for (int i = 0; i < n; i++) line[i] = b[i];
+}
+// cfftnd(3,n,sgn,c): in place, Fortran order, forward scaled by 1/ntot (cfftnd.f90:33-36)
+static void cfftnd3(const int* n, int sgn, std::vector<cplx>& c) {
+  const int n1 = n[0], n2 = n[1], n3 = n[2];
+  const size_t ntot = (size_t)n1 * n2 * n3;
+#pragma omp parallel
+  {
+    std::vector<cplx> line, a, b;
+#pragma omp for collapse(2) schedule(static)
+    for (int k = 0; k < n3; k++)
+      for (int j = 0; j < n2; j++) {
+        cplx* p = c.data() + (size_t)n1 * (j + (size_t)n2 * k);
+        dft1(n1, p, sgn, a, b);
+      }
+#pragma omp for collapse(2) schedule(static)
+    for (int k = 0; k < n3; k++)
+      for (int i = 0; i < n1; i++) {
+        line.resize(n2);
+        for (int j = 0; j < n2; j++) line[j] = c[i + (size_t)n1 * (j + (size_t)n2 * k)];
+        dft1(n2, line.data(), sgn, a, b);
+        for (int j = 0; j < n2; j++) c[i + (size_t)n1 * (j + (size_t)n2 * k)] = line[j];
+      }
+#pragma omp for collapse(2) schedule(static)
+    for (int j = 0; j < n2; j++)
+      for (int i = 0; i < n1; i++) {
+        line.resize(n3);
+        for (int k = 0; k < n3; k++) line[k] = c[i + (size_t)n1 * (j + (size_t)n2 * k)];
+        dft1(n3, line.data(), sgn, a, b);
+        for (int k = 0; k < n3; k++) c[i + (size_t)n1 * (j + (size_t)n2 * k)] = line[k];
+      }
+  }
+  if (sgn < 0) {
+    const double sc = 1.0 / (double)ntot;
+    for (size_t i = 0; i < ntot; i++) c[i] *= sc;
+  }
+}
+
+// iff: the reference's ifformat_as_ft_* codes (param.F90:225-236): 33 x, 34 y, 35 z, 36 xx, 37 xy,
+// 38 xz, 39 yy, 40 yz, 41 zz, 42 grad (|grad f|), 43 lap, 44 pot.   grid3mod@proc.f90:1757-1872
+int orc_fft_derivative(const double* f, const int* n, const double* x2c, int iff, double* out) {
+  if (iff < 33 || iff > 44) return 1;
+  const int n1 = n[0], n2 = n[1], n3 = n[2];
+  const size_t ntot = (size_t)n1 * n2 * n3;
+  const double pi = 3.14159265358979323846264338328;
+  // reciprocal lattice vectors (:1785-1789): bvec(:,1) = cross(x2c(:,3),x2c(:,2)) ...
+  auto cross = [](const double* a, const double* b, double* c) {
+    c[0] = a[1] * b[2] - a[2] * b[1];
+    c[1] = a[2] * b[0] - a[0] * b[2];
+    c[2] = a[0] * b[1] - a[1] * b[0];
+  };
+  double bvec[9];
+  cross(x2c + 6, x2c + 3, bvec + 0);
+  cross(x2c + 0, x2c + 6, bvec + 3);
+  cross(x2c + 3, x2c + 0, bvec + 6);
+  const double det = x2c[0] * (x2c[4] * x2c[8] - x2c[5] * x2c[7]) - x2c[3] * (x2c[1] * x2c[8] - x2c[2] * x2c[7]) +
+                     x2c[6] * (x2c[1] * x2c[5] - x2c[2] * x2c[4]);
+  for (int q = 0; q < 9; q++) bvec[q] = 2.0 * pi / std::fabs(det) * bvec[q];
+  // vgc(:,igfft) (:1791-1800)
+  std::vector<double> vgc(3 * ntot);
+  for (int i1 = n1 / 2 - n1 + 1; i1 <= n1 / 2; i1++)
+    for (int i2 = n2 / 2 - n2 + 1; i2 <= n2 / 2; i2++)
+      for (int i3 = n3 / 2 - n3 + 1; i3 <= n3 / 2; i3++) {
+        const size_t ig = (size_t)(((i3 % n3) + n3) % n3) * n2 * n1 + (size_t)(((i2 % n2) + n2) % n2) * n1 + (((i1 % n1) + n1) % n1);
+        for (int d = 0; d < 3; d++) vgc[3 * ig + d] = ((double)i1 * bvec[d] + (double)i2 * bvec[3 + d]) + (double)i3 * bvec[6 + d];
+      }
+  std::vector<cplx> z(ntot);
+  const cplx img(0.0, 1.0);
+  if (iff == 42) {  // gradient modulus (:1809-1827)
+    for (size_t i = 0; i < ntot; i++) out[i] = 0.0;
+    for (int d = 0; d < 3; d++) {
+      for (size_t i = 0; i < ntot; i++) z[i] = f[i];
+      cfftnd3(n, -1, z);
+      for (size_t i = 0; i < ntot; i++) z[i] = vgc[3 * i + d] * cplx(-z[i].imag(), z[i].real());
+      cfftnd3(n, +1, z);
+      for (size_t i = 0; i < ntot; i++) out[i] = out[i] + z[i].real() * z[i].real();
+    }
+    for (size_t i = 0; i < ntot; i++) out[i] = std::sqrt(out[i]);
+    return 0;
+  }
+  for (size_t i = 0; i < ntot; i++) z[i] = f[i];
+  cfftnd3(n, -1, z);
+  for (size_t i = 0; i < ntot; i++) {
+    const double* v = &vgc[3 * i];
+    switch (iff) {
+      case 33: z[i] = -v[0] * img * z[i]; break;
+      case 34: z[i] = -v[1] * img * z[i]; break;
+      case 35: z[i] = -v[2] * img * z[i]; break;
+      case 36: z[i] = -v[0] * v[0] * z[i]; break;
+      case 37: z[i] = -v[0] * v[1] * z[i]; break;
+      case 38: z[i] = -v[0] * v[2] * z[i]; break;
+      case 39: z[i] = -v[1] * v[1] * z[i]; break;
+      case 40: z[i] = -v[1] * v[2] * z[i]; break;
+      case 41: z[i] = -v[2] * v[2] * z[i]; break;
+      case 43: z[i] = -((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]) * z[i]; break;
+      default: {
+        const double vgc2 = (v[0] * v[0] + v[1] * v[1]) + v[2] * v[2];
+        if (vgc2 < 1e-12) z[i] = 0.0;
+        else z[i] = -z[i] / vgc2;
+      }
+    }
+  }
+  cfftnd3(n, +1, z);
+  if (iff == 44)
+    for (size_t i = 0; i < ntot; i++) out[i] = -4.0 * pi * z[i].real();
+  else
+    for (size_t i = 0; i < ntot; i++) out[i] = z[i].real();
+  return 0;
+}
+
+// grinterp_trilinear value (grid3mod@proc.f90:2323-2370); x0 in [0,1) crystallographic
+static double trilinear_value(const double* f, const int* n, const double x0[3]) {
+  int idx[3];
+  double r[3], s[3];
+  for (int d = 0; d < 3; d++) {
+    int fl = (int)std::floor(x0[d] * n[d]);     // grid_floor: floor(x*n), modulo n, +1 (:3133-3135)
+    fl = ((fl % n[d]) + n[d]) % n[d];
+    idx[d] = fl + 1;
+    r[d] = n[d] * x0[d] - idx[d] + 1;           // (:2346)
+    s[d] = 1.0 - r[d];
+  }
+  double ff[3][3][3];
+  for (int i = 0; i < 2; i++)
+    for (int j = 0; j < 2; j++)
+      for (int k = 0; k < 2; k++) {
+        const int a = (idx[0] + i - 1) % n[0], b = (idx[1] + j - 1) % n[1], c = (idx[2] + k - 1) % n[2];
+        ff[i][j][k] = f[a + (size_t)n[0] * (b + (size_t)n[1] * c)];
+      }
+  for (int i = 0; i < 2; i++)
+    for (int j = 0; j < 2; j++) {
+      ff[i][j][2] = ff[i][j][0] * s[2] + ff[i][j][1] * r[2];
+      ff[i][2][j] = ff[i][0][j] * s[1] + ff[i][1][j] * r[1];
+      ff[2][i][j] = ff[0][i][j] * s[0] + ff[1][i][j] * r[0];
+    }
+  for (int i = 0; i < 2; i++) {
+    ff[i][2][2] = ff[i][0][2] * s[1] + ff[i][1][2] * r[1];
+    ff[2][i][2] = ff[2][i][0] * s[2] + ff[2][i][1] * r[2];
+    ff[2][2][i] = ff[0][2][i] * s[0] + ff[1][2][i] * r[0];
+  }
+  return ff[0][2][2] * s[0] + ff[1][2][2] * r[0];
+}
+
+// field%grd with nder = 0 on a grid field (fieldmod@proc.f90:948-961): the raw node value when the
+// point is within neargrideps = 1e-12 (in grid units) of a node, else grid3%interp in `mode`
+// (0 = tricubic, 1 = trilinear).  wx already wrapped as in :921-929.
+static double grd0_value(const double* f, const int* n, const double* c2xl, const double wx[3], int mode) {
+  double x[3];
+  int idx[3];
+  bool isgrid = true;
+  for (int d = 0; d < 3; d++) {
+    double m = wx[d] - std::floor(wx[d]);  // modulo(wx,1d0)
+    if (m >= 1.0) m = 0.0;
+    x[d] = m * n[d];
+    idx[d] = (int)std::lround(x[d]);       // nint
+    if (!(std::fabs(x[d] - idx[d]) < 1e-12)) isgrid = false;
+  }
+  if (isgrid) {
+    for (int d = 0; d < 3; d++) idx[d] = ((idx[d] % n[d]) + n[d]) % n[d];
+    return f[idx[0] + (size_t)n[0] * (idx[1] + (size_t)n[1] * idx[2])];
+  }
+  if (mode == 1) {
+    double x0[3];
+    for (int d = 0; d < 3; d++) {
+      x0[d] = wx[d] - std::floor(wx[d]);
+      if (x0[d] >= 1.0) x0[d] = 0.0;
+    }
+    return trilinear_value(f, n, x0);
+  }
+  double y, yp[3], ypp[9];
+  orc_grid_interp_tricubic(f, n, c2xl, wx, &y, yp, ypp);
+  return y;
+}
+
+void orc_grid_interp_trilinear(const double* f, const int* n, const double* xi_in, double* y) {
+  double x0[3];
+  for (int d = 0; d < 3; d++) {
+    x0[d] = xi_in[d] - std::floor(xi_in[d]);
+    if (x0[d] >= 1.0) x0[d] = 0.0;
+  }
+  *y = trilinear_value(f, n, x0);
+}
+
+// ---------------------------------------------------------------------------
+// orc_nci_rdg_fourier: the NCIPLOT hot loop with fourierint = .true. (nci@proc.f90:527-565):
+// rho from the reference field (tricubic, nder = 0), |grad rho| and Hxx, Hyy, Hzz from the FFT-derived
+// grids (fgrad, fxx, fyy, fzz: orc_fft_derivative 42, 36, 39, 41) read with TRILINEAR interpolation
+// (:534-537); sign = + if at least two of Hxx, Hyy, Hzz are positive (:558-562).
+// ---------------------------------------------------------------------------
+void orc_nci_rdg_fourier(const double* f, const double* fgrad, const double* fxx, const double* fyy, const double* fzz,
+                         const int* n, const double* x0, const double* xmat, const int* nstep, const double* c2x,
+                         const double* c2xl, double* crho, double* cgrad) {
+  const double pi = 3.14159265358979323846264338328;
+  const double cst = 2.0 * std::pow(3.0 * pi * pi, 1.0 / 3.0);
+  const double fthirds = 4.0 / 3.0;
+  const double flooreps = 1e-4;
+#pragma omp parallel for schedule(dynamic)
+  for (int i = 0; i < nstep[0]; i++)
+    for (int j = 0; j < nstep[1]; j++)
+      for (int k = 0; k < nstep[2]; k++) {
+        double x[3], wx[3];
+        for (int d = 0; d < 3; d++) x[d] = ((x0[d] + i * xmat[d + 0]) + j * xmat[d + 3]) + k * xmat[d + 6];
+        for (int d = 0; d < 3; d++) {
+          double s = c2x[d + 0] * x[0];
+          s = s + c2x[d + 3] * x[1];
+          s = s + c2x[d + 6] * x[2];
+          wx[d] = s;
+        }
+        for (int d = 0; d < 3; d++)
+          if (wx[d] < -flooreps || wx[d] > 1.0 + flooreps) wx[d] = wx[d] - std::floor(wx[d]);
+        const double rho = grd0_value(f, n, c2xl, wx, 0);
+        const double g = grd0_value(fgrad, n, c2xl, wx, 1);
+        const double dimgrad = g / (cst * std::pow(std::max(rho, VSMALL), fthirds));  // (:552)
+        const double eh[3] = {grd0_value(fxx, n, c2xl, wx, 1), grd0_value(fyy, n, c2xl, wx, 1), grd0_value(fzz, n, c2xl, wx, 1)};
+        const int npos = (eh[0] > 0.0) + (eh[1] > 0.0) + (eh[2] > 0.0);
+        const double e2 = npos >= 2 ? 1.0 : -1.0;
+        const size_t o = (size_t)k + (size_t)nstep[2] * ((size_t)j + (size_t)nstep[1] * i);
+        cgrad[o] = dimgrad;
+        crho[o] = std::copysign(std::fabs(rho), e2) * 100.0;
       }
 }
 

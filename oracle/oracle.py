@@ -255,3 +255,54 @@ def promolecular(n, x2c, atoms, z, alpha, nimg=1, rc=0.0):
                            _p(xat, C.c_double), _p(z, C.c_double), _p(alpha, C.c_double), C.c_int(nimg),
                            C.c_double(rc), _p(f, C.c_double))
     return f
+
+
+# ifformat_as_ft_* codes of the reference (param.F90:225-236)
+FT_CODES = {"x": 33, "y": 34, "z": 35, "xx": 36, "xy": 37, "xz": 38, "yy": 39, "yz": 40, "zz": 41,
+            "grad": 42, "lap": 43, "pot": 44}
+
+
+def fft_derivative(f, x2c, what):
+    """grid3%fft (grid3mod@proc.f90:1757-1872); `what` is a key of FT_CODES or the integer code."""
+    f = _f64(f)
+    n = np.array(f.shape, dtype=np.int32)
+    iff = FT_CODES[what] if isinstance(what, str) else int(what)
+    out = np.zeros(f.shape, order="F")
+    rc = lib().orc_fft_derivative(_p(f, C.c_double), _p(n, C.c_int), _p(_m33(x2c), C.c_double), C.c_int(iff),
+                                  _p(out, C.c_double))
+    if rc:
+        raise ValueError(f"orc_fft_derivative: bad code {iff}")
+    return out
+
+
+def grid_interp_trilinear(f, xi):
+    f = _f64(f)
+    n = np.array(f.shape, dtype=np.int32)
+    xi = np.ascontiguousarray(xi, dtype=np.float64)
+    y = C.c_double(0)
+    lib().orc_grid_interp_trilinear(_p(f, C.c_double), _p(n, C.c_int), _p(xi, C.c_double), C.byref(y))
+    return y.value
+
+
+def nci_rdg_fourier(f, x2c, nstep=None, x0=None, xmat=None, derived=None):
+    """NCIPLOT loop with FOURIER interpolation (nci@proc.f90:527-565).  derived = (|grad|, Hxx, Hyy, Hzz)
+    grids; computed with fft_derivative when omitted."""
+    f = _f64(f)
+    n = np.array(f.shape, dtype=np.int32)
+    x2c = np.asarray(x2c, dtype=np.float64)
+    c2x = np.linalg.inv(x2c)
+    if derived is None:
+        derived = tuple(fft_derivative(f, x2c, w) for w in ("grad", "xx", "yy", "zz"))
+    fg, fxx, fyy, fzz = (_f64(d) for d in derived)
+    nstep = np.array(n if nstep is None else nstep, dtype=np.int32)
+    if xmat is None:
+        xmat = x2c / nstep.astype(np.float64)[None, :]
+    x0 = np.zeros(3) if x0 is None else np.ascontiguousarray(x0, dtype=np.float64)
+    shape = (int(nstep[2]), int(nstep[1]), int(nstep[0]))
+    crho = np.zeros(shape, order="F")
+    cgrad = np.zeros(shape, order="F")
+    lib().orc_nci_rdg_fourier(_p(f, C.c_double), _p(fg, C.c_double), _p(fxx, C.c_double), _p(fyy, C.c_double),
+                              _p(fzz, C.c_double), _p(n, C.c_int), _p(x0, C.c_double), _p(_m33(xmat), C.c_double),
+                              _p(nstep, C.c_int), _p(_m33(c2x), C.c_double), _p(_m33(c2x), C.c_double),
+                              _p(crho, C.c_double), _p(cgrad, C.c_double))
+    return crho, cgrad

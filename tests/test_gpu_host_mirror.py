@@ -48,5 +48,7 @@ def test_host_mirror_bader_and_integrable(name):
     r = json.loads(out.stdout)
     assert r["nattr"] == nattr
     assert r["labels_fnv"] == fnv1a(idg)
-    assert np.array_equal(np.array(r["vol"]), vref)
+    # volumes are exact point counts times omega/ntot; the host mirror evaluates omega with det3's expression
+    # (tools_math det3), numpy with an LU factorisation: the two may differ in the last bit
+    assert np.abs(np.array(r["vol"]) - vref).max() <= 4e-16 * np.abs(vref).max()
     assert np.abs(np.array(r["pop"]) - pref[:, 0]).max() <= 1e-10 * np.abs(pref[:, 0]).max()
