@@ -29,6 +29,7 @@ namespace {
 
 struct BaderParams {
   int n1, n2, n3;
+  int in1, in2, in3;  // max(n - 6, 0): points with 3 <= p < n-3 take steps that never touch a periodic seam
   double c2l[9];   // car2lat, column-major
   double lid[27];  // lat_i_dist, (d1+1)*9+(d2+1)*3+(d3+1)
 };
@@ -295,6 +296,15 @@ __device__ __forceinline__ int safe_lookup(const SafeMap& sm, int nx, int ny, in
 }
 // w: current point with w.r0, nb = its neighbours, sl = early-termination label of its cube (all loaded by
 // the previous call or by the caller for the start point, where sl must be -1)
+// nint of a double known to satisfy |v| < 1.5 (NaN -> 0), as an int, from the high word only:
+// |v| >= 0.5  <=>  (hi & 0x7fffffff) >= 0x3fe00000 (0.5 = 0x3fe0000000000000; the low word can only add).
+// Integer pipe instead of two fp64 compares; same result as nint_small for every input.
+__device__ __forceinline__ int nint_hi(double v, double& vd) {
+  const int hi = __double2hiint(v);
+  const bool big = (unsigned)((hi & 0x7fffffff) - 0x3fe00000) < (unsigned)(0x7ff00000 - 0x3fe00000);
+  vd = __hiloint2double(big ? ((hi & (int)0x80000000) | 0x3ff00000) : 0, 0);  // -1.0, 0.0 or 1.0
+  return big ? ((hi >> 31) | 1) : 0;
+}
 template <bool ORTHO>
 __device__ __forceinline__ int walk_step_pipe(const BaderParams& P, const double* __restrict__ rho, const MaxHash& h,
                                               const SafeMap& sm, WState& w, Nb& nb, int& sl, int& sli, int* path, int cap,
@@ -322,6 +332,9 @@ __device__ __forceinline__ int walk_step_pipe(const BaderParams& P, const double
     g2 = P.c2l[2] * gc0 + P.c2l[5] * gc1 + P.c2l[8] * gc2;
   }
   const double gmax = fmax(fabs(g0), fmax(fabs(g1), fabs(g2)));
+  // the point and its next point stay clear of the periodic seams: no wrapping anywhere in this step
+  const bool inner = (unsigned)(x - 3) < (unsigned)P.in1 && (unsigned)(y - 3) < (unsigned)P.in2 &&
+                     (unsigned)(z - 3) < (unsigned)P.in3;
   int nid, nx, ny, nz;
   if (gmax < 1e-30) {  // (:468-476)
     w.dr0 = w.dr1 = w.dr2 = 0.0;
@@ -331,21 +344,37 @@ __device__ __forceinline__ int walk_step_pipe(const BaderParams& P, const double
   } else {  // (:477-483)
     const double coeff = 1.0 / gmax;
     g0 = coeff * g0; g1 = coeff * g1; g2 = coeff * g2;
-    const double a0 = nint_small(g0), a1 = nint_small(g1), a2 = nint_small(g2);
-    double dr0 = w.dr0 + g0 - a0, dr1 = w.dr1 + g1 - a1, dr2 = w.dr2 + g2 - a2;
-    const double b0 = nint_small(dr0), b1 = nint_small(dr1), b2 = nint_small(dr2);
+    double a0, a1, a2, b0, b1, b2;
+    int d0 = nint_hi(g0, a0), d1 = nint_hi(g1, a1), d2 = nint_hi(g2, a2);
+    const double dr0 = w.dr0 + g0 - a0, dr1 = w.dr1 + g1 - a1, dr2 = w.dr2 + g2 - a2;
+    d0 += nint_hi(dr0, b0); d1 += nint_hi(dr1, b1); d2 += nint_hi(dr2, b2);
     w.dr0 = dr0 - b0; w.dr1 = dr1 - b1; w.dr2 = dr2 - b2;
-    nx = wrap2(x + (int)(a0 + b0), n1);
-    ny = wrap2(y + (int)(a1 + b1), n2);
-    nz = wrap2(z + (int)(a2 + b2), n3);
-    nid = nx + n1 * (ny + n2 * nz);
+    if (inner) {
+      nx = x + d0; ny = y + d1; nz = z + d2;
+      nid = id + d0 + n1 * (d1 + n2 * d2);
+    } else {
+      nx = wrap2(x + d0, n1);
+      ny = wrap2(y + d1, n2);
+      nz = wrap2(z + d2, n3);
+      nid = nx + n1 * (ny + n2 * nz);
+    }
   }
   if (w.len >= cap) return 3;
   path[w.len++] = id;  // known(p) = 1 (:484)
   w.rhomax = fmax(w.rhomax, r0);
   // everything the next step needs, in one batch
-  double rn = __ldg(rho + nid);
-  load_nb(P, rho, nid, nx, ny, nz, nb);
+  double rn;
+  if (inner) {
+    const double* c = rho + nid;
+    const int s2 = n1, s3 = n1 * n2;
+    rn = __ldg(c);
+    nb.xp = __ldg(c + 1); nb.xm = __ldg(c - 1);
+    nb.yp = __ldg(c + s2); nb.ym = __ldg(c - s2);
+    nb.zp = __ldg(c + s3); nb.zm = __ldg(c - s3);
+  } else {
+    rn = __ldg(rho + nid);
+    load_nb(P, rho, nid, nx, ny, nz, nb);
+  }
   sl = safe_lookup(sm, nx, ny, nz, sli);
   if (rn <= w.rhomax) {  // only then pm can be a point of this path (:487)
     if (dev_on_path(path, w.len, nid)) {
@@ -423,6 +452,7 @@ __device__ __forceinline__ void halo_decode(int h, int& col, int& row) {
 // No shared memory, no barriers: one coalesced 8-byte load per point.  Marks the cubes of every level that
 // contain a maximum.
 constexpr int MZC = 32;  // planes per block
+constexpr int MZP = 4;   // planes per prefetch group of k_maxima
 __global__ void __launch_bounds__(256) k_maxima(const __grid_constant__ BaderParams P, const Slab S,
                                                 const double* __restrict__ rho, int* __restrict__ cand,
                                                 int* __restrict__ ncand, int maxcand, const __grid_constant__ CubeFlags CF) {
@@ -446,30 +476,46 @@ __global__ void __launch_bounds__(256) k_maxima(const __grid_constant__ BaderPar
     cp += s3; ep += s3;
     if (++wz == n3) { wz = 0; cp -= wrapback; ep -= wrapback; }
   };
-  double vm = __ldg(cp);                 // plane z0-1
-  next_plane();
-  double vc = __ldg(cp), ec = edge ? __ldg(ep) : 0.0;   // plane z0
-  next_plane();
-  double vp = __ldg(cp), en = edge ? __ldg(ep) : 0.0;   // plane z0+1
-  for (int iz = z0; iz < z1; iz++) {
-    double vpp = 0.0, enn = 0.0;
-    if (iz + 2 <= z1) {  // plane iz+2 in flight while plane iz is tested
-      next_plane();
-      vpp = __ldg(cp);
-      if (edge) enn = __ldg(ep);
+  // Planes are fetched MZP at a time, one group ahead of the group being tested, so that every thread keeps
+  // MZP (+ MZP for the edge lanes) independent 8-byte loads in flight: ~40 KB per SM, what the HBM latency needs.
+  double a[MZP + 2], e[MZP + 2];  // values of planes zb-1 .. zb+MZP of the own point / of the edge neighbour
+#pragma unroll
+  for (int k = 0; k < MZP + 2; k++) {
+    const bool need = z0 - 1 + k <= z1;  // planes z0-1 .. z1
+    a[k] = need ? __ldg(cp) : 0.0;
+    e[k] = (need && edge) ? __ldg(ep) : 0.0;
+    if (need) next_plane();
+  }
+  for (int zb = z0; zb < z1; zb += MZP) {
+    double an[MZP], en[MZP];  // planes zb+MZP+1 .. zb+2*MZP
+#pragma unroll
+    for (int k = 0; k < MZP; k++) {
+      const bool need = zb + MZP + 1 + k <= z1;
+      an[k] = need ? __ldg(cp) : 0.0;
+      en[k] = (need && edge) ? __ldg(ep) : 0.0;
+      if (need) next_plane();
     }
-    double xl = __shfl_up_sync(FULL, vc, 1), xr = __shfl_down_sync(FULL, vc, 1);
-    if (lane == 0) xl = ec;
-    if (lane == 31) xr = ec;
-    if (valid && vc >= xl && vc >= xr && vc >= vm && vc >= vp) {
-      if (dev_is_max(n1, n2, n3, rho, gx, gy, iz)) {
-        const int slot = atomicAdd(ncand, 1);
-        if (slot < maxcand) cand[slot] = gx + n1 * (gy + n2 * iz);
-        for (int i = 0; i < CF.nlev; i++)
-          CF.p[i][(gx >> (i + 1)) + CF.c1[i] * ((gy >> (i + 1)) + (size_t)CF.c2[i] * ((iz - S.zlo) >> (i + 1)))] = 1;
+#pragma unroll
+    for (int k = 0; k < MZP; k++) {
+      const int iz = zb + k;
+      if (iz < z1) {  // warp-uniform
+        const double vm = a[k], vc = a[k + 1], vp = a[k + 2], ec = e[k + 1];
+        double xl = __shfl_up_sync(FULL, vc, 1), xr = __shfl_down_sync(FULL, vc, 1);
+        if (lane == 0) xl = ec;
+        if (lane == 31) xr = ec;
+        if (valid && vc >= xl && vc >= xr && vc >= vm && vc >= vp) {
+          if (dev_is_max(n1, n2, n3, rho, gx, gy, iz)) {
+            const int slot = atomicAdd(ncand, 1);
+            if (slot < maxcand) cand[slot] = gx + n1 * (gy + n2 * iz);
+            for (int i = 0; i < CF.nlev; i++)
+              CF.p[i][(gx >> (i + 1)) + CF.c1[i] * ((gy >> (i + 1)) + (size_t)CF.c2[i] * ((iz - S.zlo) >> (i + 1)))] = 1;
+          }
+        }
       }
     }
-    vm = vc; vc = vp; vp = vpp; ec = en; en = enn;
+    a[0] = a[MZP]; a[1] = a[MZP + 1]; e[0] = e[MZP]; e[1] = e[MZP + 1];
+#pragma unroll
+    for (int k = 0; k < MZP; k++) { a[k + 2] = an[k]; e[k + 2] = en[k]; }
   }
 }
 
@@ -557,9 +603,11 @@ __device__ __noinline__ void claim_neighbours(const BaderParams& P, const WalkAr
   }
 }
 
+// oldlab (FIX only): the label `start` carried when its walk began (read together with the first loads of the
+// walk; nobody else writes the label bits of a queued point during a pass)
 template <bool FIX>
-__device__ __forceinline__ void walk_finish(const BaderParams& P, const WalkArgs& A, int start, int st, int out, long long tidx,
-                                            int sli) {
+__device__ __forceinline__ void walk_finish(const BaderParams& P, const WalkArgs& A, int start, int st, int out, int tidx,
+                                            int sli, int oldlab) {
   if (A.stop && tidx >= 0) A.stop[tidx] = (st == 2) ? ((A.sm_level << STOP_SHIFT) | sli) : -1;
   if (st == 3) {
     const int slot = atomicAdd(A.noverflow, 1);
@@ -573,30 +621,26 @@ __device__ __forceinline__ void walk_finish(const BaderParams& P, const WalkArgs
     if (lab < 0) { atomicExch(A.err, 1); return; }  // terminal is not a candidate maximum: cannot happen
     if (!A.reached[lab]) A.reached[lab] = 1;
   }
-  if (FIX) {
-    const int old = A.label_g[start] & LMASK;
-    A.label_g[start] = lab;
-    if (old != lab) claim_neighbours(P, A, start);
-  } else {
-    A.label_g[start] = lab;
-  }
+  A.label_g[start] = lab;
+  if (FIX && oldlab != lab) claim_neighbours(P, A, start);
 }
 
-__device__ __forceinline__ int walk_item(const BaderParams& P, const WalkArgs& A, long long t) {
+__device__ __forceinline__ int walk_item(const BaderParams& P, const WalkArgs& A, int t) {
   if (A.list) return A.list[t];
   const int lx = (int)(t % A.lat_m1), ly = (int)((t / A.lat_m1) % A.lat_m2), lz = (int)(t / ((long long)A.lat_m1 * A.lat_m2));
   return lx * A.lat_s + P.n1 * (ly * A.lat_s + P.n2 * (A.S.zlo + lz * A.lat_s));
 }
 
 constexpr int REFILL_MIN = 24;  // idle lanes that trigger a refill: high, so that the lanes of a warp stay in step and their loads coalesce
-template <bool ORTHO, bool FIX, int MINB>
-__global__ void __launch_bounds__(256, MINB) k_walk(const __grid_constant__ BaderParams P, const __grid_constant__ WalkArgs A) {
+// STATS: count the walker steps (diagnostics, C2G_BADER_VERBOSE); off in production, it costs registers
+template <bool ORTHO, bool FIX, bool STATS>
+__global__ void __launch_bounds__(256, 4) k_walk(const __grid_constant__ BaderParams P, const __grid_constant__ WalkArgs A) {
   const int lane = threadIdx.x & 31;
   int path[PATHCAP];
-  long long qpos = 0, qend = 0;  // warp-uniform: items [qpos, qend) are this warp's
+  int qpos = 0, qend = 0;  // warp-uniform: items [qpos, qend) are this warp's (indices < 2^31: the lists hold at most nn entries)
   bool done = false, active = false;
-  int start = 0, sl = -1, sli = -1;
-  long long tidx = -1;
+  int start = 0, sl = -1, sli = -1, oldlab = 0;
+  int tidx = -1;
   WState w;
   Nb nb;
   unsigned long long steps = 0;
@@ -618,10 +662,10 @@ __global__ void __launch_bounds__(256, MINB) k_walk(const __grid_constant__ Bade
           if (lane == 0) base = atomicAdd(A.cursor, (unsigned long long)A.batch);
           base = __shfl_sync(FULL, base, 0);
           if ((long long)base >= A.count) done = true;
-          else { qpos = A.flat_base + (long long)base; qend = A.flat_base + min((long long)base + A.batch, A.count); }
+          else { qpos = (int)(A.flat_base + (long long)base); qend = (int)(A.flat_base + min((long long)base + A.batch, A.count)); }
         }
       }
-      const int navail = (int)(qend - qpos);
+      const int navail = qend - qpos;
       if (navail > 0) {
         const int rank = __popc(idle & ((1u << lane) - 1u));
         if (!active && rank < navail) {
@@ -629,6 +673,7 @@ __global__ void __launch_bounds__(256, MINB) k_walk(const __grid_constant__ Bade
           start = walk_item(P, A, tidx);
           walk_init(P, A.rho, w, start);
           load_nb(P, A.rho, start, w.x, w.y, w.z, nb);
+          if (FIX) oldlab = A.label_g[start] & LMASK;
           sl = -1;
           active = true;
         }
@@ -639,13 +684,13 @@ __global__ void __launch_bounds__(256, MINB) k_walk(const __grid_constant__ Bade
       int out = 0;
       const int st = walk_step_pipe<ORTHO>(P, A.rho, A.h, A.sm, w, nb, sl, sli, path, PATHCAP, out);
       if (st) {
-        steps += (unsigned)w.len;
-        walk_finish<FIX>(P, A, start, st, out, A.list ? tidx : -1, sli);
+        if (STATS) steps += (unsigned)w.len;
+        walk_finish<FIX>(P, A, start, st, out, A.list ? tidx : -1, sli, oldlab);
         active = false;
       }
     }
   }
-  if (A.nsteps && steps) atomicAdd(A.nsteps, steps);
+  if (STATS && A.nsteps && steps) atomicAdd(A.nsteps, steps);
 }
 
 // cut the non-empty segments of a segmented list into work items of at most `batch` entries, IN SEGMENT
@@ -763,7 +808,7 @@ __global__ void __launch_bounds__(64) k_walk_big(const __grid_constant__ BaderPa
   do st = walk_step<false>(P, A.rho, A.h, nosafe, w, scratch + (size_t)t * bigcap, bigcap, out); while (st == 0);
   if (A.nsteps) atomicAdd(A.nsteps, (unsigned long long)w.len);
   if (st == 3) { atomicExch(A.err, 2); return; }
-  walk_finish<FIX>(P, A, start, st, out, -1, -1);  // complete trajectory: nothing to log
+  walk_finish<FIX>(P, A, start, st, out, -1, -1, FIX ? (A.label_g[start] & LMASK) : 0);  // complete trajectory: nothing to log
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1233,6 +1278,7 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
   ncclComm_t comm = (ncclComm_t)ctx->nccl;
   BaderParams P;
   P.n1 = g.n[0]; P.n2 = g.n[1]; P.n3 = g.n[2];
+  P.in1 = std::max(P.n1 - 6, 0); P.in2 = std::max(P.n2 - 6, 0); P.in3 = std::max(P.n3 - 6, 0);
   memcpy(P.c2l, car2lat, sizeof(P.c2l));
   memcpy(P.lid, lat_i_dist, sizeof(P.lid));
   const int n1 = P.n1, n2 = P.n2, n3 = P.n3;
@@ -1416,8 +1462,8 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
   WA.err = cnt + 3; WA.nsteps = nsteps; WA.nnext = cnt + 7; WA.ninval = cnt + 11;
   WA.refill_min = REFILL_MIN;
   if (const char* e = getenv("C2G_REFILL_MIN")) WA.refill_min = std::max(1, std::min(32, atoi(e)));
-  int walk_occ = 4;  // resident 256-thread walker blocks per SM (4: <= 64 registers, 3: <= 80)
-  if (const char* e = getenv("C2G_WALK_OCC")) walk_occ = atoi(e) == 3 ? 3 : 4;
+  const int walk_occ = 4;  // resident 256-thread walker blocks per SM (<= 64 registers)
+  const bool walk_stats = getenv("C2G_BADER_VERBOSE") != nullptr || getenv("C2G_BADER_STATS") != nullptr;
   const int wblocks = ctx->nsm * walk_occ;
 
   auto check_err = [&]() -> int {
@@ -1462,22 +1508,16 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
     C2G_CUDA(ctx, cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), st));
     const int blocks = (int)std::min<long long>(wblocks, (count + 255) / 256);
     ctx->prof_begin(name);
-    if (walk_occ == 4) {
-      if (ortho) {
-        if (fix) k_walk<true, true, 4><<<blocks, 256, 0, st>>>(P, WA);
-        else k_walk<true, false, 4><<<blocks, 256, 0, st>>>(P, WA);
-      } else {
-        if (fix) k_walk<false, true, 4><<<blocks, 256, 0, st>>>(P, WA);
-        else k_walk<false, false, 4><<<blocks, 256, 0, st>>>(P, WA);
-      }
-    } else {
-      if (ortho) {
-        if (fix) k_walk<true, true, 3><<<blocks, 256, 0, st>>>(P, WA);
-        else k_walk<true, false, 3><<<blocks, 256, 0, st>>>(P, WA);
-      } else {
-        if (fix) k_walk<false, true, 3><<<blocks, 256, 0, st>>>(P, WA);
-        else k_walk<false, false, 3><<<blocks, 256, 0, st>>>(P, WA);
-      }
+    const int variant = (ortho ? 4 : 0) | (fix ? 2 : 0) | (walk_stats ? 1 : 0);
+    switch (variant) {
+      case 0: k_walk<false, false, false><<<blocks, 256, 0, st>>>(P, WA); break;
+      case 1: k_walk<false, false, true><<<blocks, 256, 0, st>>>(P, WA); break;
+      case 2: k_walk<false, true, false><<<blocks, 256, 0, st>>>(P, WA); break;
+      case 3: k_walk<false, true, true><<<blocks, 256, 0, st>>>(P, WA); break;
+      case 4: k_walk<true, false, false><<<blocks, 256, 0, st>>>(P, WA); break;
+      case 5: k_walk<true, false, true><<<blocks, 256, 0, st>>>(P, WA); break;
+      case 6: k_walk<true, true, false><<<blocks, 256, 0, st>>>(P, WA); break;
+      default: k_walk<true, true, true><<<blocks, 256, 0, st>>>(P, WA); break;
     }
     ctx->prof_end();
     C2G_KERNEL_CHECK(ctx);

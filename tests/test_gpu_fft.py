@@ -67,9 +67,9 @@ def test_fft_laplacian_integrates_to_zero_per_cell_and_feeds_integrable(ctx):
     vref, pref = orc.integrate_bader(idg, [f, lap_o], nattr, S.omega(x2c))
     h = ctx.upload(f)
     hl = ctx.fft_derivative(h, x2c, "lap")
-    car2lat, lid = orc.bader_metrics(x2c, c["n"])
+    _, car2lat, lid = orc.bader_metrics(x2c, c["n"])
     b = ctx.bader_assign(h, car2lat, lid)
-    mp, na, _ = helpers.assign_attractors(b.maxima(), c["n"], x2c, atoms=c["atoms"])
+    mp, na, _ = helpers.assign_attractors(b.maxima(), c["n"], x2c, c["atoms"])
     assert na == nattr
     b.set_map(na, mp)
     vol, ps = ctx.integrate(b, [h, hl], S.omega(x2c))
