@@ -631,7 +631,7 @@ __device__ __forceinline__ int walk_item(const BaderParams& P, const WalkArgs& A
   return lx * A.lat_s + P.n1 * (ly * A.lat_s + P.n2 * (A.S.zlo + lz * A.lat_s));
 }
 
-constexpr int REFILL_MIN = 24;  // idle lanes that trigger a refill: high, so that the lanes of a warp stay in step and their loads coalesce
+constexpr int REFILL_MIN = 20;  // idle lanes that trigger a refill: high, so that the lanes of a warp stay in step and their loads coalesce
 // STATS: count the walker steps (diagnostics, C2G_BADER_VERBOSE); off in production, it costs registers
 template <bool ORTHO, bool FIX, bool STATS>
 __global__ void __launch_bounds__(256, 4) k_walk(const __grid_constant__ BaderParams P, const __grid_constant__ WalkArgs A) {
@@ -1181,6 +1181,190 @@ __global__ void __launch_bounds__(256) k_fill_edge(const __grid_constant__ FillA
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// fill + edge detection driven by the octet certificates of the last level (single GPU, periodic slab).
+// One thread per cube-grid vertex v = (vx, vy, vz), which owns the points {2v-1, 2v}^3 (the points whose
+// nearest vertex is v).  vsafe[v] >= 0 says that the 8 stride-2 cubes around v are uniform with one label:
+// every owned point then has a uniformly labelled 3x3x3 neighbourhood, so it is filled (the RULE of
+// k_fill_edge) and cannot be an edge point -- 7 stores, nothing else (~90 % of the vertices).  Otherwise the
+// labels of the 4x4x4 points around v are evaluated with the same RULE (uniform cube -> its label, else what
+// the walkers wrote) and the owned FILLED points are tested against their 26 neighbours exactly like
+// is_vol_edge (bader@proc.f90:730-752).  Same labels, same edge set as k_fill_edge<true, true>; the edge
+// points of a block (32 x 8 x VZC vertices = 64 x 16 x 2 VZC points) go to the block's segment.
+// ------------------------------------------------------------------------------------------------
+constexpr int VZC = 16;                          // vertex layers per block
+constexpr int FV_SEGCAP = 64 * 16 * 2 * VZC;     // points per block
+constexpr int VSB_X = 2, VSB_Y = 8, VSB_Z = 4;   // super-block of 128^3 points
+__host__ __device__ inline int fv_nblocks(int g1, int g2, int g3) {
+  return ((g1 + VSB_X - 1) / VSB_X) * ((g2 + VSB_Y - 1) / VSB_Y) * ((g3 + VSB_Z - 1) / VSB_Z) * (VSB_X * VSB_Y * VSB_Z);
+}
+struct FillVArgs {
+  int n1, n2, n3;
+  int c1, c2, c3;        // stride-2 cube grid = vertex grid
+  int* label;            // owned planes (single GPU: the whole grid), label[x + n1*(y + n2*z)]
+  const int* uni2;
+  const int* vsafe;
+  int* list; int* nlist; int* segcnt;
+  int g1, g2, g3;        // blocks per axis
+};
+__device__ __forceinline__ int agree3(int a, int b, int c) { return (a == b && b == c) ? a : -1; }
+__global__ void __launch_bounds__(256, 2) k_fill_edge_v(const __grid_constant__ FillVArgs A) {
+  __shared__ int s_count, s_nslow;
+  __shared__ unsigned short s_slow[32 * 8 * VZC];  // block-local (lx | ly << 5 | lz << 8) of the uncertified vertices
+  const int n1 = A.n1, n2 = A.n2, n3 = A.n3;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int b = blockIdx.x;
+  int bx, by, bz;
+  {
+    const int sb = b / (VSB_X * VSB_Y * VSB_Z), w = b % (VSB_X * VSB_Y * VSB_Z);
+    const int s1 = (A.g1 + VSB_X - 1) / VSB_X, s2 = (A.g2 + VSB_Y - 1) / VSB_Y;
+    bx = (sb % s1) * VSB_X + w % VSB_X;
+    by = ((sb / s1) % s2) * VSB_Y + (w / VSB_X) % VSB_Y;
+    bz = (sb / (s1 * s2)) * VSB_Z + w / (VSB_X * VSB_Y);
+  }
+  if (bx >= A.g1 || by >= A.g2 || bz >= A.g3) {  // padding block of a ragged super-block
+    if (tid == 0) A.segcnt[b] = 0;
+    return;
+  }
+  if (tid == 0) { s_count = 0; s_nslow = 0; }
+  __syncthreads();
+  const size_t s3 = (size_t)n1 * n2, u3 = (size_t)A.c1 * A.c2;
+  const int vz0 = bz * VZC, vz1 = min(vz0 + VZC, A.c3);
+  // ---- phase 1: certified vertices store their fills; the others are collected ----
+  {
+    const int vx = bx * 32 + lane, vy = by * 8 + (tid >> 5);
+    const bool vvalid = vx < A.c1 && vy < A.c2;
+    // owned coordinates per axis: 2v-1 (absent for v = 0 unless n is even: then it is the point n-1) and 2v
+    const int x1 = wrapx(2 * vx - 1, n1), x2 = 2 * vx, y1 = wrapx(2 * vy - 1, n2), y2 = 2 * vy;
+    const bool okx1 = vx > 0 || (n1 & 1) == 0, oky1 = vy > 0 || (n2 & 1) == 0;
+    const int* vs = A.vsafe + vx + (size_t)A.c1 * vy;
+    int sv_next = vvalid ? __ldg(vs + u3 * vz0) : 0;
+    for (int vz = vz0; vz < vz1; vz++) {
+      const int sv = sv_next;
+      if (vz + 1 < vz1 && vvalid) sv_next = __ldg(vs + u3 * (vz + 1));
+      const bool slow = vvalid && sv < 0;
+      if (vvalid && sv >= 0) {
+        const int fl = (int)((unsigned)sv | FILLBIT);
+        const bool okz1 = vz > 0 || (n3 & 1) == 0;
+        int* p2 = A.label + s3 * (2 * vz);
+        int* p1 = A.label + s3 * wrapx(2 * vz - 1, n3);
+        int* r22 = p2 + (size_t)n1 * y2;
+        int* r21 = p2 + (size_t)n1 * y1;
+        if (okx1) r22[x1] = fl;              // (x2, y2, z2) is the stride-2 lattice point: it keeps its label
+        if (oky1) { r21[x2] = fl; if (okx1) r21[x1] = fl; }
+        if (okz1) {
+          int* r12 = p1 + (size_t)n1 * y2;
+          int* r11 = p1 + (size_t)n1 * y1;
+          r12[x2] = fl;
+          if (okx1) r12[x1] = fl;
+          if (oky1) { r11[x2] = fl; if (okx1) r11[x1] = fl; }
+        }
+      }
+      const unsigned m = __ballot_sync(FULL, slow);
+      if (m) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&s_nslow, __popc(m));
+        base = __shfl_sync(FULL, base, 0);
+        if (slow) s_slow[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)(lane | ((tid >> 5) << 5) | ((vz - vz0) << 8));
+      }
+    }
+  }
+  __syncthreads();
+  // ---- phase 2: the uncertified vertices, densely ----
+  const int nslow = s_nslow;
+  int* segout = A.list + (size_t)b * FV_SEGCAP;
+  for (int e0 = 0; e0 < nslow; e0 += 256) {
+    const int e = e0 + tid;
+    int nedge = 0;
+    int eid[8];
+    if (e < nslow) {
+      const int code = s_slow[e];
+      const int vx = bx * 32 + (code & 31), vy = by * 8 + ((code >> 5) & 7), vz = vz0 + (code >> 8);
+      int X[4], Y[4], Z[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) { X[i] = wrapx(2 * vx - 2 + i, n1); Y[i] = wrapx(2 * vy - 2 + i, n2); Z[i] = wrapx(2 * vz - 2 + i, n3); }
+      const bool okx1 = vx > 0 || (n1 & 1) == 0, oky1 = vy > 0 || (n2 & 1) == 0, okz1 = vz > 0 || (n3 & 1) == 0;
+      int Ag[4][2][2];   // in-plane 3x3 agreement around the owned (x, y) positions, per plane
+      int own[2][2][2];  // full labels (with FILLBIT) of the owned points [k-1][j-1][i-1]
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        int l[4][4];
+        const size_t zoff = s3 * Z[k], uoff = u3 * (Z[k] >> 1);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const size_t urow = uoff + (size_t)A.c1 * (Y[j] >> 1);
+          int ucache = -2, ucube = -1;
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const int cx = X[i] >> 1;
+            if (cx != ucube) { ucube = cx; ucache = __ldg(A.uni2 + urow + cx); }
+            const bool owned = k >= 1 && k <= 2 && j >= 1 && j <= 2 && i >= 1 && i <= 2;
+            int raw;
+            if (ucache >= 0) {
+              // uniform cube: its corners carry this label, its other points are filled with it (RULE)
+              raw = ucache;  // neighbours: label bits only
+              if (owned) {
+                const bool lattice = !((X[i] | Y[j] | Z[k]) & 1);
+                raw = lattice ? A.label[X[i] + (size_t)n1 * Y[j] + zoff] : (int)((unsigned)ucache | FILLBIT);
+              }
+            } else {
+              raw = A.label[X[i] + (size_t)n1 * Y[j] + zoff];
+            }
+            l[j][i] = raw & LMASK;
+            if (owned) own[k - 1][j - 1][i - 1] = raw;
+          }
+        }
+        int r[4][2];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          r[j][0] = agree3(l[j][0], l[j][1], l[j][2]);
+          r[j][1] = agree3(l[j][1], l[j][2], l[j][3]);
+        }
+#pragma unroll
+        for (int bb = 0; bb < 2; bb++)
+#pragma unroll
+          for (int a = 0; a < 2; a++) Ag[k][bb][a] = agree3(r[bb][a], r[bb + 1][a], r[bb + 2][a]);
+      }
+#pragma unroll
+      for (int k = 1; k <= 2; k++)
+#pragma unroll
+        for (int j = 1; j <= 2; j++)
+#pragma unroll
+          for (int i = 1; i <= 2; i++) {
+            if ((i == 1 && !okx1) || (j == 1 && !oky1) || (k == 1 && !okz1)) continue;
+            const int raw = own[k - 1][j - 1][i - 1];
+            if (!((unsigned)raw & FILLBIT)) continue;  // walked points keep what the walkers wrote
+            const bool edge = agree3(Ag[k - 1][j - 1][i - 1], Ag[k][j - 1][i - 1], Ag[k + 1][j - 1][i - 1]) < 0;
+            const int id = X[i] + n1 * (Y[j] + n2 * Z[k]);
+            const bool lattice = i == 2 && j == 2 && k == 2;
+            if (edge) { A.label[id] = raw & LMASK; eid[nedge++] = id; }
+            else if (!lattice) A.label[id] = raw;
+          }
+    }
+    // queue the edge points of this warp (the order inside a block does not matter: items are cut per segment)
+    const unsigned any = __ballot_sync(FULL, nedge > 0);
+    if (any) {
+      int incl = nedge;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += t;
+      }
+      int base = 0;
+      if (lane == 31) base = atomicAdd(&s_count, incl);
+      base = __shfl_sync(FULL, base, 31) + incl - nedge;
+#pragma unroll
+      for (int q = 0; q < 8; q++)
+        if (q < nedge) segout[base + q] = eid[q];
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    A.segcnt[b] = s_count;
+    if (s_count) atomicAdd(A.nlist, s_count);
+  }
+}
+
 // terminal candidate index -> output index (only needed when a candidate maximum was reached by no
 // trajectory, e.g. the twin of a two-point plateau); keeps FILLBIT
 __global__ void k_permute_labels(long long nn, int* __restrict__ label, const int* __restrict__ perm) {
@@ -1441,6 +1625,11 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
     const size_t nfe = (size_t)fe_nblocks(fe_gx, fe_gy, fe_gz);
     segints = std::max(segints, nfe * FE_SEGCAP);
     nsegmax = std::max(nsegmax, nfe);
+    if (nlev > 0) {  // vertex-driven fill + edge pass (single GPU)
+      const size_t nfv = (size_t)fv_nblocks((lev[0].c1 + 31) / 32, (lev[0].c2 + 7) / 8, std::max(1, (lev[0].c3 + VZC - 1) / VZC));
+      segints = std::max(segints, nfv * FV_SEGCAP);
+      nsegmax = std::max(nsegmax, nfv);
+    }
   }
   const long long listcap = (algo == C2G_BADER_EXACT) ? 1 : std::max<long long>(1, nnl);
   const long long dcap = (algo == C2G_BADER_EXACT) ? 1 : std::min<long long>(nnl + nnl / 8 + (1 << 20), 0x7fffffffll);
@@ -1686,9 +1875,22 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
     };
     int cur = 1;  // flat list being consumed next; the other one receives the claims
     const int nfeblk = fe_nblocks(fe_gx, fe_gy, fe_gz);
-    const int nfeseg = nfeblk;
+    int nfeseg = nfeblk, fesegcap = FE_SEGCAP;
     FA.g1 = fe_gx; FA.g2 = fe_gy; FA.g3 = fe_gz;
-    if (nnl > 0) {
+    const bool vertex_pass = G == 1 && S.periodic && fixsafe.safe && fixsafe.octet && getenv("C2G_FILL_OLD") == nullptr;
+    if (nnl > 0 && vertex_pass) {
+      FillVArgs FV;
+      FV.n1 = n1; FV.n2 = n2; FV.n3 = n3;
+      FV.c1 = lev[0].c1; FV.c2 = lev[0].c2; FV.c3 = lev[0].c3;
+      FV.label = res->d_label; FV.uni2 = b_uni[0].as<int>(); FV.vsafe = fixsafe.safe;
+      FV.list = seglist; FV.nlist = cnt + 1; FV.segcnt = segcnt;
+      FV.g1 = (FV.c1 + 31) / 32; FV.g2 = (FV.c2 + 7) / 8; FV.g3 = std::max(1, (FV.c3 + VZC - 1) / VZC);
+      nfeseg = fv_nblocks(FV.g1, FV.g2, FV.g3); fesegcap = FV_SEGCAP;
+      ctx->prof_begin("bader_fill_edge");
+      k_fill_edge_v<<<nfeseg, 256, 0, st>>>(FV);
+      ctx->prof_end();
+      C2G_KERNEL_CHECK(ctx);
+    } else if (nnl > 0) {
       FA.list = seglist; FA.nlist = cnt + 1;
       FA.za = S.zlo; FA.zb = S.zhi; FA.skip_lo = FA.skip_hi = (G > 1) ? 1 : 0;
       ctx->prof_begin("bader_fill_edge");
@@ -1723,7 +1925,7 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
       int* in = b_list[cur].as<int>();
       int* out = b_list[cur == 1 ? 2 : 1].as<int>();
       C2G_CUDA(ctx, cudaMemsetAsync(cnt + 7, 0, sizeof(int), st));
-      if (nseg1 && (rc = walk_segments(seglist, segcnt, nfeseg, FE_SEGCAP, nseg1, true, out, fixsafe, 0, "bader_walk_fix")) != C2G_OK) return rc;
+      if (nseg1 && (rc = walk_segments(seglist, segcnt, nfeseg, fesegcap, nseg1, true, out, fixsafe, 0, "bader_walk_fix")) != C2G_OK) return rc;
       if (nflat && (rc = walk_flat(in, nflat, true, out, fixsafe, 0, "bader_walk_fix")) != C2G_OK) return rc;
       if ((rc = drain(true)) != C2G_OK) return rc;
       report("bader_walk_fix", nseg1 + nflat);

@@ -49,6 +49,6 @@ def test_host_mirror_bader_and_integrable(name):
     assert r["nattr"] == nattr
     assert r["labels_fnv"] == fnv1a(idg)
     # volumes are exact point counts times omega/ntot; the host mirror evaluates omega with det3's expression
-    # (tools_math det3), numpy with an LU factorisation: the two may differ in the last bit
-    assert np.abs(np.array(r["vol"]) - vref).max() <= 4e-16 * np.abs(vref).max()
+    # (tools_math det3), numpy with an LU factorisation: the two differ by a few ulp (north_star allows 1e-10)
+    assert np.abs(np.array(r["vol"]) - vref).max() <= 1e-14 * np.abs(vref).max()
     assert np.abs(np.array(r["pop"]) - pref[:, 0]).max() <= 1e-10 * np.abs(pref[:, 0]).max()
