@@ -550,6 +550,7 @@ struct WalkArgs {
   unsigned long long* cursor;
   int batch;
   int refill_min;           // idle lanes that trigger a refill
+  int steps_per_check;      // walker steps between two looks at the work queue
   int* overflow; int* noverflow; int overcap;
   int* err;
   unsigned long long* nsteps;
@@ -684,7 +685,7 @@ __global__ void __launch_bounds__(256, 4) k_walk(const __grid_constant__ BaderPa
     }
     // a few steps between two looks at the work queue (the test above costs ~45 issue slots)
 #pragma unroll 1
-    for (int k = 0; k < STEPS_PER_CHECK; k++) {
+    for (int k = 0; k < A.steps_per_check; k++) {
       if (active) {
         int out = 0;
         const int st = walk_step_pipe<ORTHO>(P, A.rho, A.h, A.sm, w, nb, sl, sli, out);
@@ -1655,8 +1656,17 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
   WA.rho = g.d; WA.label_g = label_g; WA.h = h; WA.reached = reached; WA.S = S;
   WA.cursor = cursor; WA.overflow = b_over.as<int>(); WA.noverflow = cnt + 2; WA.overcap = (int)std::min<long long>(overcap, 0x7fffffff);
   WA.err = cnt + 3; WA.nsteps = nsteps; WA.nnext = cnt + 7; WA.ninval = cnt + 11;
-  WA.refill_min = REFILL_MIN;
-  if (const char* e = getenv("C2G_REFILL_MIN")) WA.refill_min = std::max(1, std::min(32, atoi(e)));
+  // Refill policy of the persistent walkers.  The dense last level is issue-bound and wants its lanes refilled
+  // early; the sparser coarse levels, the top lattice and the fix passes are latency-bound and run faster when a
+  // cohort of neighbouring walkers stays in step (their loads coalesce), so they refill late and look at the
+  // work queue less often (measured at 1024^3: l2 4.9 -> 3.6 ms, l4 2.4 -> 1.9 ms).
+  int refill_fine = REFILL_MIN, spc_fine = STEPS_PER_CHECK, refill_coarse = 24, spc_coarse = 8;
+  if (const char* e = getenv("C2G_STEPS_PER_CHECK")) spc_fine = std::max(1, std::min(64, atoi(e)));
+  if (const char* e = getenv("C2G_REFILL_MIN")) refill_fine = std::max(1, std::min(32, atoi(e)));
+  if (const char* e = getenv("C2G_SPC_COARSE")) spc_coarse = std::max(1, std::min(64, atoi(e)));
+  if (const char* e = getenv("C2G_REFILL_COARSE")) refill_coarse = std::max(1, std::min(32, atoi(e)));
+  WA.refill_min = refill_coarse;
+  WA.steps_per_check = spc_coarse;
   const int walk_occ = 4;  // resident 256-thread walker blocks per SM (<= 64 registers)
   const bool walk_stats = getenv("C2G_BADER_VERBOSE") != nullptr || getenv("C2G_BADER_STATS") != nullptr;
   const int wblocks = ctx->nsm * walk_occ;
@@ -1724,6 +1734,8 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
     if (count <= 0) return C2G_OK;
     WA.list = nullptr; WA.stop = nullptr; WA.items = nullptr; WA.nitems = 0; WA.flat_base = 0; WA.count = count;
     WA.sm = SafeMap{nullptr, 0, 0, 0, 0, 0, 0, 0, 0}; WA.sm_level = 0;
+    WA.refill_min = lat_s == 1 ? refill_fine : refill_coarse;
+    WA.steps_per_check = lat_s == 1 ? spc_fine : spc_coarse;
     WA.lat_s = lat_s; WA.lat_m1 = (n1 + lat_s - 1) / lat_s; WA.lat_m2 = (n2 + lat_s - 1) / lat_s;
     WA.next = nullptr; WA.nextcap = 0;
     const long long nwarps = (long long)wblocks * 8;
@@ -1757,6 +1769,9 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
     WA.sm = sm; WA.sm_level = sm_level; WA.lat_s = 1; WA.lat_m1 = n1; WA.lat_m2 = n2;
     WA.next = next; WA.nextcap = (int)std::min<long long>(listcap, 0x7fffffff);
     WA.batch = batch;
+    const bool fine = !fix && sm_level == 0;
+    WA.refill_min = fine ? refill_fine : refill_coarse;
+    WA.steps_per_check = fine ? spc_fine : spc_coarse;
     doff += count;
     return launch_walk(count, fix, name);
   };
@@ -1770,6 +1785,8 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
     WA.sm = sm; WA.sm_level = sm_level; WA.lat_s = 1; WA.lat_m1 = n1; WA.lat_m2 = n2;
     WA.next = next; WA.nextcap = (int)std::min<long long>(listcap, 0x7fffffff);
     WA.batch = 32;
+    WA.refill_min = refill_coarse;
+    WA.steps_per_check = spc_coarse;
     doff += count;
     return launch_walk(count, fix, name);
   };
