@@ -77,49 +77,89 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region, in-process through NVML (nvidia_ml_py).
+    An nvidia-smi subprocess polling in a loop was measured to stall kernel launches (it holds driver locks: a
+    34 ms step took 124 ms under `nvidia-smi -lms 100`), so it is only the fallback, queried once after the region."""
 
-    def __init__(self, index=0):
+    def __init__(self, index=0, period=0.05):
         self.index = index
-        self.rows = []
-        self.proc = None
+        self.period = period
+        self.rows = []   # (sm_mhz, sm_max_mhz, reasons bitmask)
+        self._stop = threading.Event()
+        self.thread = None
+        self.nvml = None
+        self.handle = None
 
     def start(self):
+        if os.environ.get("C2G_BENCH_NOCLOCKS"):
+            return
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}",
-                 "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-                 "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "200"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.index])
+                except (ValueError, IndexError):
+                    idx = self.index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nvml = pynvml
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
         except Exception:
-            self.proc = None
+            self.nvml = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
-
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
-        self.proc.terminate()
-        sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 7:
-                continue
+    def _loop(self):
+        nv = self.nvml
+        while not self._stop.is_set():
             try:
-                sm.append(float(f[0])); smax.append(float(f[1]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                sm = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                try:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.rows.append((sm, self.smax, rs))
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def mark(self):
+        return len(self.rows)
+
+    def stop(self, lo=0, hi=None):
+        if self.nvml is None:
+            return self._smi_once()
+        self._stop.set()
+        self.thread.join(timeout=1.0)
+        rows = self.rows[lo:hi] if hi is not None and hi > lo else self.rows[lo:]
+        if not rows:
+            rows = self.rows
+        nv = self.nvml
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        reasons = sorted(nm for nm, bit in names.items() if any(r[2] & bit for r in rows))
+        sm = [r[0] for r in rows]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.smax if sm else None,
+                "samples": len(sm), "reasons": reasons, "how": "NVML in-process, every 50 ms inside the timed region"}
+
+    def _smi_once(self):
+        try:
+            out = subprocess.run(["nvidia-smi", f"--id={self.index}",
+                                  "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+                                  "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                                  "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=20).stdout.strip().splitlines()[0]
+            f = [x.strip() for x in out.split(",")]
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            return {"sm_mhz": float(f[0]), "sm_max_mhz": float(f[1]), "samples": 1,
+                    "reasons": sorted(nm for nm, v in zip(names, f[2:6]) if v.lower().startswith("active")),
+                    "how": "nvidia-smi, once right after the timed region (NVML python binding unavailable)"}
+        except Exception:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
 
 
 def workload(size: int):
@@ -259,7 +299,10 @@ def run_ours(args):
         vol, ps = ctx.integrate(b, [h_rho, h_f2], omega)
         return b, vol, ps
 
-    # ---- warm-up ----
+    # ---- warm-up (the clock sampler starts here: its start-up must not perturb the timed region) ----
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
     for _ in range(max(args.warmup, 3)):
         b, vol, ps = step_resident()
         nmax = b.nmax
@@ -267,21 +310,25 @@ def run_ours(args):
     pop_sum = float(ps[:, 0].sum())
 
     # ---- timed region: device-resident inputs ----
-    ctx.profile_enable(True)
+    ctx.profile_enable(not os.environ.get("C2G_BENCH_NOPROF"))
     ctx.profile_reset()
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     l0 = ctx.launch_count()
     barrier(); ctx.synchronize()
+    m0 = clocks.mark()
     ctx.timer_start()
+    trace = []
     for _ in range(args.steps):
+        tw = time.perf_counter()
         b, vol, ps = step_resident()
         b.free()
+        trace.append(round((time.perf_counter() - tw) * 1e3, 2))
     ms = ctx.timer_stop()
+    if os.environ.get("C2G_BENCH_TRACE") and rank == 0:
+        print("host wall per step (ms):", trace, file=sys.stderr, flush=True)
+    m1 = clocks.mark()
     barrier()
     launches = ctx.launch_count() - l0
-    clk = clocks.stop() if rank == 0 else None
+    clk = clocks.stop(m0, m1) if rank == 0 else None
     ms_step = max_over_ranks(ms / args.steps)
     prof = ctx.profile()
     ctx.profile_enable(False)
@@ -296,11 +343,22 @@ def run_ours(args):
     nloc = float(n[0] * n[1] * (zhi - zlo))
     kern_ms = max_over_ranks(assign_ms + integ_ms)
     achieved = ALG_BYTES_TOTAL * nloc / (max(assign_ms + integ_ms, 1e-9) * 1e-3) / 1e9
+    # measured DRAM traffic of the same kernel group (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per
+    # step), from the committed capture of this workload; null when there is none for this size / GPU count
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        key = f"{size}^3x{world}"
+        if key in tj:
+            traffic, traffic_src = tj[key]["dram_bytes_per_step"], tj[key]["source"]
+    except (OSError, ValueError, KeyError):
+        pass
     roofline = {
-        "bound": "hbm", "kernel": "BADER assign+integrate kernel group (k_maxima, k_walk_*, k_classify, k_edgefix, k_compact, k_basin_reduce); "
-                                  "dominant: k_walk_list",
+        "bound": "hbm", "kernel": "BADER assign+integrate kernel group (k_maxima, k_walk, k_classify, k_vsafe, k_fill_edge_v, k_requeue, "
+                                  "k_basin_reduce); dominant: k_walk (last-level launch, bader_walk_l1)",
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-        "algorithmic_bytes_per_point": ALG_BYTES_TOTAL, "points_per_launch_group": nloc, "traffic": None,
+        "algorithmic_bytes_per_point": ALG_BYTES_TOTAL, "points_per_launch_group": nloc, "traffic": traffic,
+        "traffic_source": traffic_src,
         "stages": {
             "assign": {"ms": assign_ms, "GBps": ALG_BYTES_ASSIGN * nloc / max(assign_ms, 1e-9) / 1e6, "of_which_walk_ms": walk_ms},
             "integrate": {"ms": integ_ms, "GBps": ALG_BYTES_INTEGRATE * nloc / max(integ_ms, 1e-9) / 1e6},
@@ -385,7 +443,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=1024, help="grid points per axis (default: the 1024^3 headline config)")

@@ -202,7 +202,8 @@ void c2g_finalize(c2g_context* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (auto& g : ctx->grids)
-    if (g.used && g.d) cudaFreeAsync(g.d, ctx->stream);
+    if (g.used && g.d) c2g_release(ctx, g.d);
+  c2g_mem_trim(ctx);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->flushbuf) cudaFree(ctx->flushbuf);
   for (auto e : ctx->event_pool) cudaEventDestroy(e);

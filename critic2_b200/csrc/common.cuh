@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <unordered_map>
 #include <string>
 #include <vector>
 
@@ -50,6 +51,10 @@ struct c2g_context {
   int rank = 0, nranks = 1;
   void* nccl = nullptr;  // ncclComm_t
   cudaEvent_t t0 = nullptr, t1 = nullptr;  // c2g_timer_*
+  // device-memory cache (c2g_alloc / c2g_release below)
+  std::multimap<size_t, void*> mem_free;           // size -> cached block
+  std::unordered_map<void*, size_t> mem_live;      // block handed out -> its size
+  size_t mem_cached_bytes = 0;
 
   int fail(int code, const char* fmt, ...) {
     char buf[1024];
@@ -156,13 +161,45 @@ void c2g_slab_bounds(int n3, int nranks, int rank, int* zlo, int* zhi);
 int c2g_launch_basin_reduce(c2g_context* ctx, long long nn, const int* label, int label_mask, int np, const double* const* f,
                             int nmax, double* sums, unsigned long long* counts);
 
-// stream-ordered pool allocations (cudaMallocAsync with an unbounded release threshold, set in c2g_init):
-// repeated calls reuse the same device memory instead of paying cudaMalloc/cudaFree every time
+// Device memory of the work buffers.  Every allocation of the library is used on ONE stream (ctx->stream), so a
+// released block can be handed out again at once: program order on the stream is the only ordering needed.  The
+// blocks are therefore cached per context instead of going back to the driver's stream-ordered pool: with
+// cudaFreeAsync + cudaMallocAsync back to back (no host synchronisation between two API calls) the driver was
+// measured to map fresh physical memory for multi-GB requests instead of reusing the pending frees (a 31 ms
+// c2g_bader_assign took 50..3700 ms).  A request takes the smallest cached block of at least its size and at
+// most 1.25 x its size; on an allocation failure the cache is dropped and the request retried.
+static inline void c2g_mem_trim(c2g_context* ctx) {
+  for (auto& kv : ctx->mem_free) cudaFreeAsync(kv.second, ctx->stream);
+  ctx->mem_free.clear();
+  ctx->mem_cached_bytes = 0;
+}
 static inline cudaError_t c2g_alloc(c2g_context* ctx, void** p, size_t bytes) {
-  return cudaMallocAsync(p, bytes ? bytes : 1, ctx->stream);
+  if (bytes == 0) bytes = 1;
+  auto it = ctx->mem_free.lower_bound(bytes);
+  if (it != ctx->mem_free.end() && it->first <= bytes + bytes / 4 + 256) {
+    *p = it->second;
+    ctx->mem_live[*p] = it->first;
+    ctx->mem_cached_bytes -= it->first;
+    ctx->mem_free.erase(it);
+    return cudaSuccess;
+  }
+  cudaError_t e = cudaMallocAsync(p, bytes, ctx->stream);
+  if (e != cudaSuccess) {  // make room and retry once
+    cudaGetLastError();
+    c2g_mem_trim(ctx);
+    cudaStreamSynchronize(ctx->stream);
+    e = cudaMallocAsync(p, bytes, ctx->stream);
+  }
+  if (e == cudaSuccess) ctx->mem_live[*p] = bytes;
+  return e;
 }
 static inline void c2g_release(c2g_context* ctx, void* p) {
-  if (p) cudaFreeAsync(p, ctx->stream);
+  if (!p) return;
+  auto it = ctx->mem_live.find(p);
+  if (it == ctx->mem_live.end()) { cudaFreeAsync(p, ctx->stream); return; }  // not ours (should not happen)
+  ctx->mem_free.emplace(it->second, p);
+  ctx->mem_cached_bytes += it->second;
+  ctx->mem_live.erase(it);
 }
 struct DevBuf {
   c2g_context* ctx = nullptr;
@@ -171,7 +208,7 @@ struct DevBuf {
   explicit DevBuf(c2g_context* c) : ctx(c) {}
   ~DevBuf() { reset(); }
   void reset() {
-    if (p) { if (ctx) cudaFreeAsync(p, ctx->stream); else cudaFree(p); }
+    if (p) { if (ctx) c2g_release(ctx, p); else cudaFree(p); }
     p = nullptr;
   }
   cudaError_t alloc(c2g_context* c, size_t bytes) {

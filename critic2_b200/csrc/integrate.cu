@@ -180,7 +180,7 @@ int c2g_launch_basin_reduce(c2g_context* ctx, long long nn, const int* label, in
     if ((uintptr_t)f[p] % 16 != 0) vec = 0;
   const size_t smem = use_table ? sizeof(double) * (size_t)(np + 1) * nmax : 0;
   double* partials = nullptr;
-  if (use_table) C2G_CUDA(ctx, cudaMallocAsync(&partials, sizeof(double) * (size_t)blocks * (np + 1) * nmax, ctx->stream));
+  if (use_table) C2G_CUDA(ctx, c2g_alloc(ctx, (void**)&partials, sizeof(double) * (size_t)blocks * (np + 1) * nmax));
   ctx->prof_begin("basin_reduce");
   switch (np) {
     case 0: k_basin_reduce<0><<<blocks, 256, smem, ctx->stream>>>(nn, label, f0, f1, f2, f3, nmax, use_table, label_mask, vec, sums, counts, partials); break;
@@ -196,7 +196,7 @@ int c2g_launch_basin_reduce(c2g_context* ctx, long long nn, const int* label, in
   }
   ctx->prof_end(nl);
   cudaError_t e = cudaGetLastError();
-  if (partials) cudaFreeAsync(partials, ctx->stream);
+  if (partials) c2g_release(ctx, partials);
   if (e != cudaSuccess) return ctx->fail(C2G_ERR_CUDA, "basin_reduce launch: %s", cudaGetErrorString(e));
   return C2G_OK;
 }
