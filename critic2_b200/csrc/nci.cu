@@ -18,7 +18,7 @@
 // across cells, so that chain is evaluated with explicit __dmul_rn/__dadd_rn (never fused) in the
 // Fortran left-to-right order.
 //
-// Mapping: a block owns an 8(i) x 2(j) x 16(k) brick of the output lattice; lanes run along i (the
+// Mapping: a block owns a 32(i) x 2(j) x 4(k) brick of the output lattice; lanes run along i (the
 // fastest index of rho) for the stencil loads, results are staged in shared memory and written with k
 // fastest, which is the reference's cgrad(k,j,i) layout.  HBM traffic: 8 B read + 16 B written per point.
 #include "common.cuh"
@@ -33,12 +33,17 @@ struct NciParams {
   double x0[3], xmat[9];   // Cartesian
   double c2x[9], x2c[9], c2xl[9];
   int nnuc;
+  double cst;  // 2 (3 pi^2)^(1/3), nci@proc.f90:91, evaluated once on the host
 };
 
-constexpr int BI = 8, BJ = 2, BK = 16;
+constexpr int BI = 32, BJ = 2, BK = 4;  // lanes run along i (the contiguous index of rho): coalesced stencil loads; 4 consecutive k = one 32 B output sector
 
 __device__ __forceinline__ int imod(int a, int n) {
-  int r = a % n;
+  if (a >= -n && a < 2 * n) {  // the usual case: at most one period off (no integer division)
+    a += a < 0 ? n : 0;
+    return a >= n ? a - n : a;
+  }
+  const int r = a % n;
   return r < 0 ? r + n : r;
 }
 
@@ -46,8 +51,9 @@ __device__ __forceinline__ int positive_roots_middle_sign(double hxx, double hyy
                                                           double hyz) {
   // characteristic polynomial l^3 - c2 l^2 + c1 l - c0 ; all roots real => Descartes' rule is exact
   const double c2 = hxx + hyy + hzz;
-  const double c1 = (hxx * hyy - hxy * hxy) + (hxx * hzz - hxz * hxz) + (hyy * hzz - hyz * hyz);
-  const double c0 = hxx * (hyy * hzz - hyz * hyz) - hxy * (hxy * hzz - hyz * hxz) + hxz * (hxy * hyz - hyy * hxz);
+  const double m0 = fma(hyy, hzz, -hyz * hyz), m1 = fma(hxy, hzz, -hyz * hxz), m2 = fma(hxy, hyz, -hyy * hxz);
+  const double c1 = (fma(hxx, hyy, -hxy * hxy) + fma(hxx, hzz, -hxz * hxz)) + m0;
+  const double c0 = fma(hxz, m2, fma(hxx, m0, -hxy * m1));
   const double seq[4] = {1.0, -c2, c1, -c0};
   int npos = 0, nzero = 0;
   double prev = 1.0;
@@ -205,18 +211,19 @@ __global__ void __launch_bounds__(256) k_nci_rdg(const __grid_constant__ NciPara
     for (int a = 0; a < 3; a++)
 #pragma unroll
       for (int b = 0; b < 3; b++) {
-        double s = 0.0;
-#pragma unroll
-        for (int q = 0; q < 3; q++) s += P.c2xl[q + 3 * a] * H[q][b];
+        // (only sign(lambda_2) is taken from the Cartesian Hessian: fused multiply-adds are as good as any order)
+        double s = P.c2xl[3 * a] * H[0][b];
+        s = fma(P.c2xl[1 + 3 * a], H[1][b], s);
+        s = fma(P.c2xl[2 + 3 * a], H[2][b], s);
         T[a][b] = s;
       }
 #pragma unroll
     for (int a = 0; a < 3; a++)
 #pragma unroll
       for (int b = 0; b < 3; b++) {
-        double s = 0.0;
-#pragma unroll
-        for (int q = 0; q < 3; q++) s += T[a][q] * P.c2xl[q + 3 * b];
+        double s = T[a][0] * P.c2xl[3 * b];
+        s = fma(T[a][1], P.c2xl[1 + 3 * b], s);
+        s = fma(T[a][2], P.c2xl[2 + 3 * b], s);
         HC[a][b] = s;
       }
     // nucleus rule (fieldmod@proc.f90:1148-1155): zero gradient within 1e-5 bohr of an atom
@@ -247,9 +254,9 @@ __global__ void __launch_bounds__(256) k_nci_rdg(const __grid_constant__ NciPara
       if (isnuc) gc[0] = gc[1] = gc[2] = 0.0;
     }
     const double gfmod = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(gc[0], gc[0]), __dmul_rn(gc[1], gc[1])), __dmul_rn(gc[2], gc[2])));
-    const double pi = 3.14159265358979323846264338328;
-    const double cst = 2.0 * pow(3.0 * pi * pi, 1.0 / 3.0);
-    const double dimgrad = gfmod / (cst * pow(fmax(f, 1e-80), 4.0 / 3.0));
+    // max(rho,vsmall)**(4/3) as rho * cbrt(rho): same value to 1-2 ulp (the 1e-12 contract), a fraction of pow's cost
+    const double fm = fmax(f, 1e-80);
+    const double dimgrad = gfmod / (P.cst * (fm * cbrt(fm)));
     const int sg = positive_roots_middle_sign(HC[0][0], HC[1][1], HC[2][2], 0.5 * (HC[0][1] + HC[1][0]),
                                               0.5 * (HC[0][2] + HC[2][0]), 0.5 * (HC[1][2] + HC[2][1]));
     out_grad = dimgrad;
@@ -383,9 +390,8 @@ __global__ void __launch_bounds__(256) k_nci_rdg_fourier(const __grid_constant__
     const double f = grd0_value(P, rho, g, false);
     const double gm = grd0_value(P, fgrad, g, true);
     const double hx = grd0_value(P, fxx, g, true), hy = grd0_value(P, fyy, g, true), hz = grd0_value(P, fzz, g, true);
-    const double pi = 3.14159265358979323846264338328;
-    const double cst = 2.0 * pow(3.0 * pi * pi, 1.0 / 3.0);
-    out_grad = gm / (cst * pow(fmax(f, 1e-80), 4.0 / 3.0));
+    const double fm = fmax(f, 1e-80);
+    out_grad = gm / (P.cst * (fm * cbrt(fm)));
     const int npos = (hx > 0.0) + (hy > 0.0) + (hz > 0.0);
     out_rho = (npos >= 2 ? fabs(f) : -fabs(f)) * 100.0;
   }
@@ -416,6 +422,7 @@ int nci_launch(c2g_context* ctx, int handle, const double x0[3], const double xm
   memcpy(P.x2c, x2c, sizeof(P.x2c));
   memcpy(P.c2xl, c2xl, sizeof(P.c2xl));
   P.nnuc = nnuc;
+  P.cst = 2.0 * std::pow(3.0 * 3.14159265358979323846264338328 * 3.14159265358979323846264338328, 1.0 / 3.0);
   double* d_nuc = nullptr;
   if (nnuc > 0) {
     C2G_CUDA(ctx, c2g_alloc(ctx, (void**)&d_nuc, sizeof(double) * 3 * nnuc));
@@ -510,6 +517,7 @@ extern "C" int c2g_nci_rdg_fourier(c2g_context* ctx, const int h[5], const doubl
   memcpy(P.x2c, c2x, sizeof(P.x2c));  // unused in this mode
   memcpy(P.c2xl, c2xl, sizeof(P.c2xl));
   P.nnuc = 0;
+  P.cst = 2.0 * std::pow(3.0 * 3.14159265358979323846264338328 * 3.14159265358979323846264338328, 1.0 / 3.0);
   const size_t nout = (size_t)nstep[0] * nstep[1] * nstep[2];
   DevBuf d_rho, d_grad;
   C2G_CUDA(ctx, d_rho.alloc(ctx, sizeof(double) * nout));

@@ -1,0 +1,174 @@
+#!/usr/bin/env python
+"""Secondary measurements: the other BASELINE.json configs through the C ABI, inputs resident in HBM.
+
+One JSON line per path (stdout), each with the algorithmic bytes per grid point of SURVEY.md 8(d), the CUDA-event
+time of the call on the library's stream (best of `reps` after a warm-up), achieved GB/s against the measured HBM
+peak (MEASURED_PEAKS.json, else the 6650 GB/s fallback) and a size-independent or sub-sampled parity check
+against the oracle.  bench.py stays the headline (configs[4]); this file is evidence for the rows next to it.
+
+usage: python tools/bench_paths.py [--quick]
+"""
+import json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import systems as S
+import bench
+from critic2_b200 import capi
+from oracle import oracle as orc
+
+quick = "--quick" in sys.argv
+PEAK, PEAK_SRC = bench.measured_peaks()
+ctx = capi.Context(0)
+ctx.profile_enable(True)
+
+
+def timed(fn, reps=3, cleanup=None):
+    """Best CUDA-event time of fn() on the library stream; cleanup(out) releases the result of every call but the last."""
+    out = fn()  # warm-up
+    best, prof = 1e30, {}
+    for _ in range(reps):
+        if cleanup:
+            cleanup(out)
+        ctx.profile_reset(); ctx.synchronize(); ctx.timer_start()
+        out = fn()
+        ms = ctx.timer_stop()
+        if ms < best:
+            best, prof = ms, {k: round(v[0], 3) for k, v in ctx.profile().items()}
+    return best, prof, out
+
+
+def free_all(hs):
+    for x in hs:
+        ctx.free(x)
+
+
+def emit(path, config, n, ms, bytes_per_pt, prof, check, extra=None):
+    npts = float(np.prod(n))
+    gbs = bytes_per_pt * npts / (ms * 1e-3) / 1e9
+    rec = {"path": path, "config": config, "grid": list(map(int, n)), "ms": round(ms, 3), "points_per_s": npts / (ms * 1e-3),
+           "algorithmic_bytes_per_point": bytes_per_pt, "achieved_GBps": round(gbs, 1), "peak_GBps": PEAK, "peak_source": PEAK_SRC,
+           "frac": round(gbs / PEAK, 4), "kernels_ms": prof, "check": check}
+    if extra:
+        rec.update(extra)
+    print(json.dumps(rec), flush=True)
+
+
+# ---- config 2: urea-like tetragonal cell, 256^3: BADER + INTEGRABLE rho and FFT Laplacian ----
+def urea():
+    N = 128 if quick else 256
+    n = (N, N, N)
+    x2c = S.cell_x2c(10.52, 10.52, 8.85)
+    at, z, al = S.random_atoms(16, 2, x2c, dmin=2.0)
+    at = S.snap_to_grid(at, n)
+    h = ctx.alloc(n); ctx.promolecular(h, x2c, at, z, al, nimg=1, rc=0.0)
+    _, car2lat, lid = orc.bader_metrics(x2c, n)
+    om = S.omega(x2c)
+
+    def run():
+        hl = ctx.fft_derivative(h, x2c, "lap")
+        b = ctx.bader_assign(h, car2lat, lid)
+        b.set_map(b.nmax, np.arange(1, b.nmax + 1, dtype=np.int32))
+        vol, ps = ctx.integrate(b, [h, hl], om)
+        b.free(); ctx.free(hl)
+        return vol, ps
+    ms, prof, (vol, ps) = timed(run)
+    f = ctx.download(h, n)
+    chk = {"volume_sum_over_omega": float(vol.sum() / om), "population_sum_vs_grid_sum": float(ps[:, 0].sum() / (f.sum() * om / f.size)),
+           "laplacian_sum_over_scale": float(abs(ps[:, 1].sum()) / (np.abs(f).sum() * om / f.size))}
+    if N <= 128:  # full parity against the oracle at the quick size
+        idg, nattr, _, _ = orc.bader_integrate(f, x2c, atoms=at)
+        chk["oracle_basins"] = int(nattr)
+    emit("BADER assign + INTEGRABLE (rho, FFT lap) incl. the FFT", "configs[1] urea-like 16 atoms, tetragonal", n, ms, 32.0 + 16.0, prof, chk)
+    ctx.free(h)
+
+
+# ---- config 3: NCIPLOT on a 512^3 grid field, benzene-dimer-like 24 atoms in a 30 bohr box ----
+def nci():
+    N = 128 if quick else 512
+    n = (N, N, N)
+    x2c = S.cell_x2c(30.0, 30.0, 30.0)
+    ang = np.arange(6) * np.pi / 3
+    ring = np.stack([2.64 * np.cos(ang), 2.64 * np.sin(ang), np.zeros(6)], 1)      # C6 ring, bohr
+    hyd = np.stack([4.69 * np.cos(ang), 4.69 * np.sin(ang), np.zeros(6)], 1)
+    mono = np.concatenate([ring, hyd])
+    dimer = np.concatenate([mono + [15.0, 15.0, 11.7], mono + [15.0 + 3.0, 15.0, 11.7 + 6.6]])  # parallel displaced, 3.5 A
+    at = S.snap_to_grid(dimer / 30.0, n)
+    z = np.array(([6.0] * 6 + [1.0] * 6) * 2); al = np.array(([2.2] * 6 + [1.9] * 6) * 2)
+    h = ctx.alloc(n); ctx.promolecular(h, x2c, at, z, al, nimg=0, rc=0.0)
+
+    ms, prof, (hr, hg) = timed(lambda: ctx.nci_rdg_resident(h, x2c, n), cleanup=free_all)
+    # sub-sampled parity at the full size: a coarse node-aligned lattice evaluated by the oracle
+    f = ctx.download(h, n)
+    cg = ctx.download(hg, (n[2], n[1], n[0])); cr = ctx.download(hr, (n[2], n[1], n[0]))
+    st = N // 16
+    sub = (16, 16, 16)
+    xm = x2c / np.array(n, dtype=float)[None, :] * st
+    cro, cgo = orc.nci_rdg(f, x2c, nstep=sub, x0=np.zeros(3), xmat=xm)
+    sel_g = cg[::st, ::st, ::st]; sel_r = cr[::st, ::st, ::st]
+    chk = {"subsampled_points": int(np.prod(sub)), "max_rel_rdg_err_vs_oracle": float(np.abs(sel_g - cgo).max() / np.abs(cgo).max()),
+           "max_rel_abs_crho_err": float(np.abs(np.abs(sel_r) - np.abs(cro)).max() / np.abs(cro).max())}
+    emit("NCIPLOT RDG, tricubic, node-aligned", "configs[2] benzene-dimer-like 24 atoms, 30 bohr box", n, ms, 24.0, prof, chk)
+    ctx.free(hr); ctx.free(hg)
+
+    # FOURIER mode: 4 derived grids (one forward + one backward transform each, |grad| three backward) + the loop
+    ms_d, prof_d, hd = timed(lambda: [ctx.fft_derivative(h, x2c, w) for w in ("grad", "xx", "yy", "zz")], reps=2, cleanup=free_all)
+    emit("FFT-derived grids for NCIPLOT FOURIER (|grad|, Hxx, Hyy, Hzz)", "configs[2]", n, ms_d, 4 * 16.0, prof_d,
+         {"note": "16 B/pt minimal per output grid (SURVEY.md 8d); cuFFT D2Z/Z2D do the transforms"})
+    for x in hd:
+        ctx.free(x)
+    ctx.free(h)
+
+
+# ---- config 4: YT on a 512^3 periodic density with many basins ----
+def yt():
+    N = 128 if quick else 512
+    side = 4 if quick else 8
+    n = (N, N, N)
+    x2c = S.cell_x2c(5.0 * side, 5.0 * side, 5.0 * side)
+    at, z, al = S.jittered_lattice(side, 4)
+    at = S.snap_to_grid(at, n)
+    h = ctx.alloc(n); ctx.promolecular(h, x2c, at, z, al, nimg=1, rc=8.0)
+    vec, area = S.wscell(x2c / np.array(n, dtype=float)[None, :])
+    om = S.omega(x2c)
+    state = {}
+
+    def build():
+        if "b" in state:
+            state["b"].free()
+        state["b"] = ctx.yt_build(h, vec, area)
+        return state["b"]
+    ms_b, prof_b, b = timed(build, reps=2)
+    b.set_map(b.nmax, np.arange(1, b.nmax + 1, dtype=np.int32))
+    ms_i, prof_i, (vol, ps) = timed(lambda: ctx.integrate(b, [h], om))
+    st = b.stats()
+    phi = st[0] / float(np.prod(n))
+    nhi = 3.0  # mean number of higher neighbours of an IAS point (SURVEY.md 8d probe); the library does not count it
+    f = ctx.download(h, n)
+    chk = {"volume_sum_over_omega": float(vol.sum() / om), "population_sum_vs_grid_sum": float(ps[:, 0].sum() / (f.sum() * om / f.size)),
+           "phi_ias": phi, "nhi_assumed": nhi, "bfs_levels": int(st[1]), "kahn_levels": int(st[2]), "nvec": int(len(area)), "basins": int(b.nmax)}
+    emit("YT build (yt_integrate)", "configs[3] 512 atoms cubic, tie-free", n, ms_b, 24.0 + 12.0 * nhi * phi, prof_b, chk)
+    emit("YT integrate (adjoint sweep, Volume + rho)", "configs[3]", n, ms_i, 4.0 + 8.0 + 12.0 * nhi * phi + 16.0 * phi, prof_i, chk)
+    b.free(); ctx.free(h)
+
+
+# ---- FFT derivative alone at the headline size ----
+def fft_big():
+    N = 256 if quick else 1024
+    n = (N, N, N)
+    x2c = S.cell_x2c(40.0, 40.0, 40.0)
+    at, z, al = S.jittered_lattice(8, 5)
+    h = ctx.alloc(n); ctx.promolecular(h, x2c, S.snap_to_grid(at, n), z, al, nimg=1, rc=8.0)
+    ms, prof, hl = timed(lambda: [ctx.fft_derivative(h, x2c, "lap")], reps=2, cleanup=free_all)
+    free_all(hl)
+    emit("FFT Laplacian (grid3%fft, iff = lap)", "1024^3 headline grid", n, ms, 16.0, prof,
+         {"note": "16 B/pt = read f + write lap; the half-spectrum D2Z + multiply + Z2D moves ~64 B/pt through cuFFT's passes"})
+    ctx.free(h)
+
+
+for fn in (urea, nci, yt, fft_big):
+    try:
+        fn()
+    except Exception as e:  # keep going: one JSON line per failure
+        print(json.dumps({"path": fn.__name__, "error": repr(e)}), flush=True)
+ctx.close()
