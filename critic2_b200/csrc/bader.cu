@@ -1207,8 +1207,13 @@ __host__ __device__ inline int fv_nblocks(int g1, int g2, int g3) {
 }
 struct FillVArgs {
   int n1, n2, n3;
-  int c1, c2, c3;        // stride-2 cube grid = vertex grid
-  int* label;            // owned planes (single GPU: the whole grid), label[x + n1*(y + n2*z)]
+  int c1, c2, c3;        // stride-2 cube grid of the owned planes = vertex grid
+  int nzl, periodic;     // owned planes; periodic = 1: single GPU, z wraps.  Otherwise (z-slab of a multi-GPU run)
+                         // the first and last owned planes are only filled, not tested: their neighbours live on
+                         // another rank and the caller tests them against fresh halos (edge_faces)
+  int nvz;               // vertex layers to visit: c3 (periodic) or c3 + 1 (slab: the layer above the last cube)
+  int zlo;               // global plane of the first owned plane (edge ids are global)
+  int* label;            // owned planes, label[x + n1*(y + n2*zl)], zl = 0 .. nzl-1
   const int* uni2;
   const int* vsafe;
   int* list; int* nlist; int* segcnt;
@@ -1236,7 +1241,8 @@ __global__ void __launch_bounds__(256, 2) k_fill_edge_v(const __grid_constant__ 
   if (tid == 0) { s_count = 0; s_nslow = 0; }
   __syncthreads();
   const size_t s3 = (size_t)n1 * n2, u3 = (size_t)A.c1 * A.c2;
-  const int vz0 = bz * VZC, vz1 = min(vz0 + VZC, A.c3);
+  const int vz0 = bz * VZC, vz1 = min(vz0 + VZC, A.nvz);
+  const int per = A.periodic;
   // ---- phase 1: certified vertices store their fills; the others are collected ----
   {
     const int vx = bx * 32 + lane, vy = by * 8 + (tid >> 5);
@@ -1245,16 +1251,17 @@ __global__ void __launch_bounds__(256, 2) k_fill_edge_v(const __grid_constant__ 
     const int x1 = wrapx(2 * vx - 1, n1), x2 = 2 * vx, y1 = wrapx(2 * vy - 1, n2), y2 = 2 * vy;
     const bool okx1 = vx > 0 || (n1 & 1) == 0, oky1 = vy > 0 || (n2 & 1) == 0;
     const int* vs = A.vsafe + vx + (size_t)A.c1 * vy;
-    int sv_next = vvalid ? __ldg(vs + u3 * vz0) : 0;
+    int sv_next = (vvalid && vz0 < A.c3) ? __ldg(vs + u3 * vz0) : -1;
     for (int vz = vz0; vz < vz1; vz++) {
       const int sv = sv_next;
-      if (vz + 1 < vz1 && vvalid) sv_next = __ldg(vs + u3 * (vz + 1));
+      sv_next = -1;  // the slab's extra layer above the last cube has no certificate
+      if (vz + 1 < vz1 && vz + 1 < A.c3 && vvalid) sv_next = __ldg(vs + u3 * (vz + 1));
       const bool slow = vvalid && sv < 0;
-      if (vvalid && sv >= 0) {
+      if (vvalid && sv >= 0) {  // the 8 cubes around the vertex are owned and uniform: both z planes exist
         const int fl = (int)((unsigned)sv | FILLBIT);
-        const bool okz1 = vz > 0 || (n3 & 1) == 0;
+        const bool okz1 = vz > 0 || (per && (n3 & 1) == 0);
         int* p2 = A.label + s3 * (2 * vz);
-        int* p1 = A.label + s3 * wrapx(2 * vz - 1, n3);
+        int* p1 = A.label + s3 * (per ? wrapx(2 * vz - 1, n3) : max(2 * vz - 1, 0));
         int* r22 = p2 + (size_t)n1 * y2;
         int* r21 = p2 + (size_t)n1 * y1;
         if (okx1) r22[x1] = fl;              // (x2, y2, z2) is the stride-2 lattice point: it keeps its label
@@ -1288,13 +1295,28 @@ __global__ void __launch_bounds__(256, 2) k_fill_edge_v(const __grid_constant__ 
       const int code = s_slow[e];
       const int vx = bx * 32 + (code & 31), vy = by * 8 + ((code >> 5) & 7), vz = vz0 + (code >> 8);
       int X[4], Y[4], Z[4];
+      bool zin[4];  // plane is one of the owned planes (always, when z is periodic)
 #pragma unroll
-      for (int i = 0; i < 4; i++) { X[i] = wrapx(2 * vx - 2 + i, n1); Y[i] = wrapx(2 * vy - 2 + i, n2); Z[i] = wrapx(2 * vz - 2 + i, n3); }
-      const bool okx1 = vx > 0 || (n1 & 1) == 0, oky1 = vy > 0 || (n2 & 1) == 0, okz1 = vz > 0 || (n3 & 1) == 0;
+      for (int i = 0; i < 4; i++) {
+        X[i] = wrapx(2 * vx - 2 + i, n1);
+        Y[i] = wrapx(2 * vy - 2 + i, n2);
+        const int zl = 2 * vz - 2 + i;
+        zin[i] = per || (zl >= 0 && zl < A.nzl);
+        Z[i] = per ? wrapx(zl, n3) : min(max(zl, 0), A.nzl - 1);
+      }
+      const bool okx1 = vx > 0 || (n1 & 1) == 0, oky1 = vy > 0 || (n2 & 1) == 0;
+      // existence of the two owned z planes, and whether their points are tested here
+      const bool okz[2] = {per ? (vz > 0 || (n3 & 1) == 0) : vz > 0, per ? true : 2 * vz < A.nzl};
+      const bool tz[2] = {per != 0 || (2 * vz - 1 >= 1 && 2 * vz - 1 <= A.nzl - 2), per != 0 || (2 * vz >= 1 && 2 * vz <= A.nzl - 2)};
       int Ag[4][2][2];   // in-plane 3x3 agreement around the owned (x, y) positions, per plane
       int own[2][2][2];  // full labels (with FILLBIT) of the owned points [k-1][j-1][i-1]
 #pragma unroll
       for (int k = 0; k < 4; k++) {
+        if (!zin[k]) {  // not this rank's plane: the owned points next to it are not tested in this pass
+#pragma unroll
+          for (int q = 0; q < 4; q++) Ag[k][q >> 1][q & 1] = -1;
+          continue;
+        }
         int l[4][4];
         const size_t zoff = s3 * Z[k], uoff = u3 * (Z[k] >> 1);
 #pragma unroll
@@ -1338,14 +1360,14 @@ __global__ void __launch_bounds__(256, 2) k_fill_edge_v(const __grid_constant__ 
         for (int j = 1; j <= 2; j++)
 #pragma unroll
           for (int i = 1; i <= 2; i++) {
-            if ((i == 1 && !okx1) || (j == 1 && !oky1) || (k == 1 && !okz1)) continue;
+            if ((i == 1 && !okx1) || (j == 1 && !oky1) || !okz[k - 1]) continue;
             const int raw = own[k - 1][j - 1][i - 1];
             if (!((unsigned)raw & FILLBIT)) continue;  // walked points keep what the walkers wrote
-            const bool edge = agree3(Ag[k - 1][j - 1][i - 1], Ag[k][j - 1][i - 1], Ag[k + 1][j - 1][i - 1]) < 0;
-            const int id = X[i] + n1 * (Y[j] + n2 * Z[k]);
-            const bool lattice = i == 2 && j == 2 && k == 2;
-            if (edge) { A.label[id] = raw & LMASK; eid[nedge++] = id; }
-            else if (!lattice) A.label[id] = raw;
+            const bool edge = tz[k - 1] && agree3(Ag[k - 1][j - 1][i - 1], Ag[k][j - 1][i - 1], Ag[k + 1][j - 1][i - 1]) < 0;
+            const size_t off = X[i] + (size_t)n1 * Y[j] + s3 * Z[k];
+            const bool lattice = !((X[i] | Y[j] | Z[k]) & 1);
+            if (edge) { A.label[off] = raw & LMASK; eid[nedge++] = (int)(off + s3 * A.zlo); }
+            else if (!lattice) A.label[off] = raw;
           }
     }
     // queue the edge points of this warp (the order inside a block does not matter: items are cut per segment)
@@ -1633,7 +1655,7 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
     segints = std::max(segints, nfe * FE_SEGCAP);
     nsegmax = std::max(nsegmax, nfe);
     if (nlev > 0) {  // vertex-driven fill + edge pass (single GPU)
-      const size_t nfv = (size_t)fv_nblocks((lev[0].c1 + 31) / 32, (lev[0].c2 + 7) / 8, std::max(1, (lev[0].c3 + VZC - 1) / VZC));
+      const size_t nfv = (size_t)fv_nblocks((lev[0].c1 + 31) / 32, (lev[0].c2 + 7) / 8, std::max(1, (lev[0].c3 + 1 + VZC - 1) / VZC));
       segints = std::max(segints, nfv * FV_SEGCAP);
       nsegmax = std::max(nsegmax, nfv);
     }
@@ -1900,14 +1922,16 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
     const int nfeblk = fe_nblocks(fe_gx, fe_gy, fe_gz);
     int nfeseg = nfeblk, fesegcap = FE_SEGCAP;
     FA.g1 = fe_gx; FA.g2 = fe_gy; FA.g3 = fe_gz;
-    const bool vertex_pass = G == 1 && S.periodic && fixsafe.safe && fixsafe.octet && getenv("C2G_FILL_OLD") == nullptr;
+    const bool vertex_pass = fixsafe.safe && fixsafe.octet && (S.nzl % 2 == 0 || S.periodic) && getenv("C2G_FILL_OLD") == nullptr;
     if (nnl > 0 && vertex_pass) {
       FillVArgs FV;
       FV.n1 = n1; FV.n2 = n2; FV.n3 = n3;
       FV.c1 = lev[0].c1; FV.c2 = lev[0].c2; FV.c3 = lev[0].c3;
+      FV.nzl = S.nzl; FV.periodic = S.periodic; FV.zlo = S.zlo;
+      FV.nvz = FV.c3 + (S.periodic ? 0 : 1);
       FV.label = res->d_label; FV.uni2 = b_uni[0].as<int>(); FV.vsafe = fixsafe.safe;
       FV.list = seglist; FV.nlist = cnt + 1; FV.segcnt = segcnt;
-      FV.g1 = (FV.c1 + 31) / 32; FV.g2 = (FV.c2 + 7) / 8; FV.g3 = std::max(1, (FV.c3 + VZC - 1) / VZC);
+      FV.g1 = (FV.c1 + 31) / 32; FV.g2 = (FV.c2 + 7) / 8; FV.g3 = std::max(1, (FV.nvz + VZC - 1) / VZC);
       nfeseg = fv_nblocks(FV.g1, FV.g2, FV.g3); fesegcap = FV_SEGCAP;
       ctx->prof_begin("bader_fill_edge");
       k_fill_edge_v<<<nfeseg, 256, 0, st>>>(FV);
