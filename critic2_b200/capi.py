@@ -26,7 +26,7 @@ EXPORTS = [
     "c2g_grid_upload", "c2g_grid_upload_slab", "c2g_slab_range", "c2g_slab_bounds_query", "c2g_grid_alloc", "c2g_grid_download", "c2g_grid_download_slab", "c2g_grid_free", "c2g_grid_promolecular",
     "c2g_bader_assign", "c2g_basins_maxima", "c2g_basins_counts", "c2g_basins_set_map", "c2g_basins_labels",
     "c2g_basins_relabel", "c2g_basins_free", "c2g_basins_stats", "c2g_integrate", "c2g_yt_build",
-    "c2g_yt_weights", "c2g_nci_rdg", "c2g_nci_rdg_resident", "c2g_fft_derivative", "c2g_nci_rdg_fourier", "c2g_profile_enable", "c2g_profile_count",
+    "c2g_yt_weights", "c2g_nci_rdg", "c2g_nci_rdg_resident", "c2g_fft_derivative", "c2g_nci_rdg_fourier", "c2g_nci_range", "c2g_profile_enable", "c2g_profile_count",
     "c2g_profile_get", "c2g_profile_reset", "c2g_launch_count", "c2g_flush_l2", "c2g_synchronize", "c2g_timer_start", "c2g_timer_stop",
 ]
 
@@ -166,6 +166,12 @@ class Context:
         return vol, psum
 
     # ---- NCIPLOT ----
+    def nci_range(self, nstep1):
+        """Lattice rows [ilo, ihi) computed by this rank (the whole range on a single GPU)."""
+        a, b = C.c_int(0), C.c_int(0)
+        self._chk(self.lib.c2g_nci_range(self.h, C.c_int(int(nstep1)), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def nci_rdg(self, h, x2c, n, nstep=None, x0=None, xmat=None, nuclei_cart=None, c2xl=None):
         x2c = np.asarray(x2c, dtype=np.float64)
         c2x = np.linalg.inv(x2c)
@@ -174,7 +180,8 @@ class Context:
             xmat = x2c / nstep.astype(np.float64)[None, :]
         x0 = np.zeros(3) if x0 is None else np.ascontiguousarray(x0, dtype=np.float64)
         nuc = np.zeros((0, 3)) if nuclei_cart is None else np.ascontiguousarray(nuclei_cart, dtype=np.float64)
-        shape = (int(nstep[2]), int(nstep[1]), int(nstep[0]))
+        ilo, ihi = self.nci_range(nstep[0])
+        shape = (int(nstep[2]), int(nstep[1]), max(ihi - ilo, 0))
         crho = np.zeros(shape, order="F")
         cgrad = np.zeros(shape, order="F")
         self._chk(self.lib.c2g_nci_rdg(self.h, C.c_int(h), _p(x0, C.c_double), _p(_m33(xmat), C.c_double),
@@ -212,7 +219,8 @@ class Context:
             xmat = x2c / nstep.astype(np.float64)[None, :]
         x0 = np.zeros(3) if x0 is None else np.ascontiguousarray(x0, dtype=np.float64)
         hh = np.ascontiguousarray(handles, dtype=np.int32)
-        shape = (int(nstep[2]), int(nstep[1]), int(nstep[0]))
+        ilo, ihi = self.nci_range(nstep[0])
+        shape = (int(nstep[2]), int(nstep[1]), max(ihi - ilo, 0))
         crho = np.zeros(shape, order="F")
         cgrad = np.zeros(shape, order="F")
         self._chk(self.lib.c2g_nci_rdg_fourier(self.h, _p(hh, C.c_int), _p(x0, C.c_double), _p(_m33(xmat), C.c_double),

@@ -29,7 +29,8 @@ namespace {
 
 struct NciParams {
   int n1, n2, n3;          // rho grid
-  int ns1, ns2, ns3;       // output lattice
+  int ns1, ns2, ns3;       // output lattice (ns1 = the i range computed by this rank)
+  int i0;                  // first lattice index i of this rank (multi-GPU: the lattice is sharded along i)
   double x0[3], xmat[9];   // Cartesian
   double c2x[9], x2c[9], c2xl[9];
   int nnuc;
@@ -73,9 +74,10 @@ __global__ void __launch_bounds__(256) k_nci_rdg(const __grid_constant__ NciPara
   __shared__ double s_grad[BI * BJ * BK];
   const int tid = threadIdx.x;
   const int li = tid % BI, lj = (tid / BI) % BJ, lk = tid / (BI * BJ);
-  const int i = blockIdx.x * BI + li, j = blockIdx.y * BJ + lj, k = blockIdx.z * BK + lk;
+  const int il = blockIdx.x * BI + li, j = blockIdx.y * BJ + lj, k = blockIdx.z * BK + lk;
+  const int i = P.i0 + il;
   double out_rho = 0.0, out_grad = 0.0;
-  if (i < P.ns1 && j < P.ns2 && k < P.ns3) {
+  if (il < P.ns1 && j < P.ns2 && k < P.ns3) {
     // ---- coordinate chain (never fused) ----
     double wx[3];
     {
@@ -363,9 +365,10 @@ __global__ void __launch_bounds__(256) k_nci_rdg_fourier(const __grid_constant__
   __shared__ double s_grad[BI * BJ * BK];
   const int tid = threadIdx.x;
   const int li = tid % BI, lj = (tid / BI) % BJ, lk = tid / (BI * BJ);
-  const int i = blockIdx.x * BI + li, j = blockIdx.y * BJ + lj, k = blockIdx.z * BK + lk;
+  const int il = blockIdx.x * BI + li, j = blockIdx.y * BJ + lj, k = blockIdx.z * BK + lk;
+  const int i = P.i0 + il;
   double out_rho = 0.0, out_grad = 0.0;
-  if (i < P.ns1 && j < P.ns2 && k < P.ns3) {
+  if (il < P.ns1 && j < P.ns2 && k < P.ns3) {
     double wx[3];
     {
       double x[3];
@@ -409,13 +412,22 @@ __global__ void __launch_bounds__(256) k_nci_rdg_fourier(const __grid_constant__
   }
 }
 
+// lattice rows i owned by this rank: an even split of nstep(1) (the slowest index of cgrad(k,j,i), so every rank's
+// part is one contiguous piece of the reference arrays)
+static void nci_range(const c2g_context* ctx, int ns1, int* ilo, int* ihi) {
+  *ilo = (int)((long long)ns1 * ctx->rank / ctx->nranks);
+  *ihi = (int)((long long)ns1 * (ctx->rank + 1) / ctx->nranks);
+}
+
 int nci_launch(c2g_context* ctx, int handle, const double x0[3], const double xmat[9], const int nstep[3],
                const double c2x[9], const double x2c[9], const double c2xl[9], int nnuc, const double* nuc_cart,
                double* d_rho, double* d_grad) {
   const c2g_grid& g = ctx->grids[handle];
   NciParams P;
   P.n1 = g.n[0]; P.n2 = g.n[1]; P.n3 = g.n[2];
-  P.ns1 = nstep[0]; P.ns2 = nstep[1]; P.ns3 = nstep[2];
+  int ilo, ihi;
+  nci_range(ctx, nstep[0], &ilo, &ihi);
+  P.ns1 = ihi - ilo; P.i0 = ilo; P.ns2 = nstep[1]; P.ns3 = nstep[2];
   memcpy(P.x0, x0, sizeof(P.x0));
   memcpy(P.xmat, xmat, sizeof(P.xmat));
   memcpy(P.c2x, c2x, sizeof(P.c2x));
@@ -428,7 +440,8 @@ int nci_launch(c2g_context* ctx, int handle, const double x0[3], const double xm
     C2G_CUDA(ctx, c2g_alloc(ctx, (void**)&d_nuc, sizeof(double) * 3 * nnuc));
     C2G_CUDA(ctx, cudaMemcpyAsync(d_nuc, nuc_cart, sizeof(double) * 3 * nnuc, cudaMemcpyHostToDevice, ctx->stream));
   }
-  dim3 grid((nstep[0] + BI - 1) / BI, (nstep[1] + BJ - 1) / BJ, (nstep[2] + BK - 1) / BK);
+  if (P.ns1 < 1) return C2G_OK;  // more ranks than lattice rows
+  dim3 grid((P.ns1 + BI - 1) / BI, (nstep[1] + BJ - 1) / BJ, (nstep[2] + BK - 1) / BK);
   ctx->prof_begin("nci_rdg");
   k_nci_rdg<<<grid, 256, 0, ctx->stream>>>(P, g.d, d_nuc, d_rho, d_grad);
   ctx->prof_end();
@@ -460,7 +473,9 @@ extern "C" int c2g_nci_rdg(c2g_context* ctx, int handle, const double x0[3], con
   int rc = nci_check(ctx, handle, x0, xmat, nstep, c2x, x2c, c2xl, nnuc, nuc_cart);
   if (rc) return rc;
   if (!crho || !cgrad) return ctx->fail(C2G_ERR_ARG, "c2g_nci_rdg: null output");
-  const size_t nout = (size_t)nstep[0] * nstep[1] * nstep[2];
+  int ilo, ihi;
+  nci_range(ctx, nstep[0], &ilo, &ihi);
+  const size_t nout = (size_t)std::max(ihi - ilo, 0) * nstep[1] * nstep[2];
   double *d_rho = nullptr, *d_grad = nullptr;
   C2G_CUDA(ctx, c2g_alloc(ctx, (void**)&d_rho, sizeof(double) * nout));
   C2G_CUDA(ctx, c2g_alloc(ctx, (void**)&d_grad, sizeof(double) * nout));
@@ -485,7 +500,9 @@ extern "C" int c2g_nci_rdg_resident(c2g_context* ctx, int handle, const double x
   int rc = nci_check(ctx, handle, x0, xmat, nstep, c2x, x2c, c2xl, nnuc, nuc_cart);
   if (rc) return rc;
   if (!hrho || !hgrad) return ctx->fail(C2G_ERR_ARG, "c2g_nci_rdg_resident: null output");
-  const int nout[3] = {nstep[2], nstep[1], nstep[0]};
+  int ilo, ihi;
+  nci_range(ctx, nstep[0], &ilo, &ihi);
+  const int nout[3] = {nstep[2], nstep[1], std::max(ihi - ilo, 1)};
   if ((rc = c2g_grid_alloc(ctx, nout, hrho)) != C2G_OK) return rc;
   if ((rc = c2g_grid_alloc(ctx, nout, hgrad)) != C2G_OK) return rc;
   return nci_launch(ctx, handle, x0, xmat, nstep, c2x, x2c, c2xl, nnuc, nuc_cart, ctx->grids[*hrho].d, ctx->grids[*hgrad].d);
@@ -510,7 +527,9 @@ extern "C" int c2g_nci_rdg_fourier(c2g_context* ctx, const int h[5], const doubl
   }
   NciParams P;
   P.n1 = g0.n[0]; P.n2 = g0.n[1]; P.n3 = g0.n[2];
-  P.ns1 = nstep[0]; P.ns2 = nstep[1]; P.ns3 = nstep[2];
+  int ilo, ihi;
+  nci_range(ctx, nstep[0], &ilo, &ihi);
+  P.ns1 = ihi - ilo; P.i0 = ilo; P.ns2 = nstep[1]; P.ns3 = nstep[2];
   memcpy(P.x0, x0, sizeof(P.x0));
   memcpy(P.xmat, xmat, sizeof(P.xmat));
   memcpy(P.c2x, c2x, sizeof(P.c2x));
@@ -518,11 +537,12 @@ extern "C" int c2g_nci_rdg_fourier(c2g_context* ctx, const int h[5], const doubl
   memcpy(P.c2xl, c2xl, sizeof(P.c2xl));
   P.nnuc = 0;
   P.cst = 2.0 * std::pow(3.0 * 3.14159265358979323846264338328 * 3.14159265358979323846264338328, 1.0 / 3.0);
-  const size_t nout = (size_t)nstep[0] * nstep[1] * nstep[2];
+  if (P.ns1 < 1) return C2G_OK;
+  const size_t nout = (size_t)P.ns1 * nstep[1] * nstep[2];
   DevBuf d_rho, d_grad;
   C2G_CUDA(ctx, d_rho.alloc(ctx, sizeof(double) * nout));
   C2G_CUDA(ctx, d_grad.alloc(ctx, sizeof(double) * nout));
-  dim3 grid((nstep[0] + BI - 1) / BI, (nstep[1] + BJ - 1) / BJ, (nstep[2] + BK - 1) / BK);
+  dim3 grid((P.ns1 + BI - 1) / BI, (nstep[1] + BJ - 1) / BJ, (nstep[2] + BK - 1) / BK);
   ctx->prof_begin("nci_rdg_fourier");
   k_nci_rdg_fourier<<<grid, 256, 0, ctx->stream>>>(P, ctx->grids[h[0]].d, ctx->grids[h[1]].d, ctx->grids[h[2]].d,
                                                    ctx->grids[h[3]].d, ctx->grids[h[4]].d, d_rho.as<double>(), d_grad.as<double>());
@@ -532,5 +552,14 @@ extern "C" int c2g_nci_rdg_fourier(c2g_context* ctx, const int h[5], const doubl
   C2G_CUDA(ctx, cudaMemcpyAsync(cgrad, d_grad.p, sizeof(double) * nout, cudaMemcpyDeviceToHost, ctx->stream));
   C2G_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->prof_collect();
+  return C2G_OK;
+}
+
+// Multi-GPU: the lattice rows i (0-based, half open) this rank computes; c2g_nci_rdg* then fill / return only
+// cgrad(:,:,ilo+1:ihi), which is one contiguous piece of the reference array.  Single GPU: the whole range.
+extern "C" int c2g_nci_range(c2g_context* ctx, int nstep1, int* ilo, int* ihi) {
+  if (!ctx) return C2G_ERR_ARG;
+  if (!ilo || !ihi || nstep1 < 1) return ctx->fail(C2G_ERR_ARG, "c2g_nci_range: bad argument");
+  nci_range(ctx, nstep1, ilo, ihi);
   return C2G_OK;
 }

@@ -139,6 +139,11 @@ int c2g_yt_weights(c2g_basins* res, int idb, double* w);
 int c2g_nci_rdg(c2g_context* ctx, int handle, const double x0[3], const double xmat[9], const int nstep[3],
                 const double c2x[9], const double x2c[9], const double c2xl[9], int nnuc,
                 const double* nuc_cart, double* crho, double* cgrad);
+/* Multi-GPU (c2g_init_multi; the field must be resident on every rank, which c2g_grid_upload_slab ensures): the
+ * output lattice is sharded along its slowest index i.  c2g_nci_range gives this rank's rows [ilo, ihi) (0-based);
+ * every c2g_nci_rdg* call then computes and returns only cgrad(:,:,ilo+1:ihi) / crho(:,:,ilo+1:ihi), one contiguous
+ * piece of the reference arrays.  No collective is involved (NCI shards naturally). */
+int c2g_nci_range(c2g_context* ctx, int nstep1, int* ilo, int* ihi);
 /* same, results stay in HBM (two new grid handles with n = (nstep3,nstep2,nstep1)) */
 int c2g_nci_rdg_resident(c2g_context* ctx, int handle, const double x0[3], const double xmat[9],
                          const int nstep[3], const double c2x[9], const double x2c[9], const double c2xl[9],

@@ -51,3 +51,12 @@ def test_slab_sharded_bader_equals_oracle(nranks, name):
             assert np.array_equal(p[f"vol{algo}"], vref)
             assert np.abs(p[f"ps{algo}"][:, 0] - pref[:, 0]).max() <= 1e-10 * np.abs(pref[:, 0]).max()
             assert int(p[f"cnt{algo}"].sum()) == idg.size
+    # NCIPLOT sharded along i: the ranks' pieces concatenate to the single-process result of the oracle
+    crho_o, cgrad_o = orc.nci_rdg(c["f"], c["x2c"])
+    assert [int(p["nci_ilo"]) for p in parts][1:] == [int(p["nci_ihi"]) for p in parts][:-1]
+    cgrad = np.concatenate([p["cgrad"] for p in parts], axis=2)
+    crho = np.concatenate([p["crho"] for p in parts], axis=2)
+    assert cgrad.shape == cgrad_o.shape
+    rel = np.abs(cgrad - cgrad_o) / np.abs(cgrad_o).max()
+    assert (rel <= 1e-12).mean() >= 0.999 and rel.max() <= 1e-9
+    assert np.abs(np.abs(crho) - np.abs(crho_o)).max() <= 1e-12 * np.abs(crho_o).max()

@@ -29,6 +29,10 @@ for algo in (capi.BADER_EXACT, capi.BADER_FAST):
     vol, ps = ctx.integrate(b, [h, h2], S.omega(x2c))
     out[f"lab{algo}"] = lab; out[f"vol{algo}"] = vol; out[f"ps{algo}"] = ps; out[f"cnt{algo}"] = b.counts()
     b.free()
+# NCIPLOT: the output lattice is sharded along i, no collective
+ilo, ihi = ctx.nci_range(n[0])
+crho, cgrad = ctx.nci_rdg(h, x2c, n)
+out["nci_ilo"] = ilo; out["nci_ihi"] = ihi; out["crho"] = crho; out["cgrad"] = cgrad
 np.savez(os.path.join(outdir, f"rank{rank}.npz"), zlo=zlo, zhi=zhi, **out)
 ctx.close()
 print("rank", rank, "ok", zlo, zhi)
