@@ -1220,7 +1220,10 @@ struct FillVArgs {
   int g1, g2, g3;        // blocks per axis
 };
 __device__ __forceinline__ int agree3(int a, int b, int c) { return (a == b && b == c) ? a : -1; }
-__global__ void __launch_bounds__(256, 2) k_fill_edge_v(const __grid_constant__ FillVArgs A) {
+#ifndef FV_MINB
+#define FV_MINB 3
+#endif
+__global__ void __launch_bounds__(256, FV_MINB) k_fill_edge_v(const __grid_constant__ FillVArgs A) {
   __shared__ int s_count, s_nslow;
   __shared__ unsigned short s_slow[32 * 8 * VZC];  // block-local (lx | ly << 5 | lz << 8) of the uncertified vertices
   const int n1 = A.n1, n2 = A.n2, n3 = A.n3;

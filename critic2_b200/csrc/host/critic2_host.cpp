@@ -210,4 +210,37 @@ void nci_rdg(const system& s, std::vector<double>& crho, std::vector<double>& cg
   check(c2g_grid_free(g_ctx, h), "nciplot");
 }
 
+void grid_fft(const system& s, const grid3& fold, int iff, grid3& fnew) {
+  if (!g_ctx) ferror("fft", "gpu_init was not called");
+  if (fold.f.empty()) ferror("fft", "no input grid");  // grid3mod@proc.f90:1775
+  int h = -1, ho = -1;
+  check(c2g_grid_upload(g_ctx, fold.f.data(), fold.n, &h), "fft");
+  check(c2g_fft_derivative(g_ctx, h, iff, s.m_x2c, &ho), "fft");
+  fnew = grid3();
+  for (int i = 0; i < 3; i++) fnew.n[i] = fold.n[i];  // copy_geometry (:1781)
+  fnew.nvec = fold.nvec; fnew.vec = fold.vec; fnew.area = fold.area;
+  fnew.f.assign(fold.f.size(), 0.0);
+  check(c2g_grid_download(g_ctx, ho, fnew.f.data()), "fft");
+  check(c2g_grid_free(g_ctx, h), "fft");
+  check(c2g_grid_free(g_ctx, ho), "fft");
+}
+
+void nci_rdg_fourier(const system& s, std::vector<double>& crho, std::vector<double>& cgrad) {
+  if (!g_ctx) ferror("nciplot", "gpu_init was not called");
+  const grid3& g = s.grid;
+  int h[5] = {-1, -1, -1, -1, -1};
+  check(c2g_grid_upload(g_ctx, g.f.data(), g.n, &h[0]), "nciplot");
+  const int iffs[4] = {C2G_FT_GRAD, C2G_FT_XX, C2G_FT_YY, C2G_FT_ZZ};  // nci@proc.f90:528-531
+  for (int q = 0; q < 4; q++) check(c2g_fft_derivative(g_ctx, h[0], iffs[q], s.m_x2c, &h[q + 1]), "nciplot");
+  double c2x[9], xmat[9];
+  matinv3(s.m_x2c, c2x);
+  for (int i = 0; i < 3; i++)
+    for (int k = 0; k < 3; k++) xmat[k + 3 * i] = s.m_x2c[k + 3 * i] / g.n[i];
+  const double x0[3] = {0.0, 0.0, 0.0};
+  crho.assign(g.f.size(), 0.0);
+  cgrad.assign(g.f.size(), 0.0);
+  check(c2g_nci_rdg_fourier(g_ctx, h, x0, xmat, g.n, c2x, c2x, crho.data(), cgrad.data()), "nciplot");
+  for (int q = 0; q < 5; q++) check(c2g_grid_free(g_ctx, h[q]), "nciplot");
+}
+
 }  // namespace c2h

@@ -11,7 +11,8 @@
 //   bader@proc.f90:80-234      bader_integrate(s,bas,iref)
 //   yt@proc.f90:38-224         yt_integrate(s,bas)
 //   integration@proc.f90:1170  intgrid_fields(bas,res)
-//   nci@proc.f90:543-605       nciplot loop -> nci_rdg
+//   nci@proc.f90:543-605       nciplot loop -> nci_rdg, nci_rdg_fourier
+//   grid3mod@proc.f90:1757     grid3%fft -> grid_fft
 //   tools_io@proc.F90:1573     ferror(routine,msg,faterr) -> c2h::ferror (throws c2h::fatal_error)
 #pragma once
 
@@ -88,5 +89,9 @@ void yt_weights(const basindat& bas, int idb, std::vector<double>& w);
 // nci@proc.f90:543-605, grid interpolation mode on the field's own lattice:
 // crho, cgrad(0:n3-1,0:n2-1,0:n1-1), third index fastest.
 void nci_rdg(const system& s, std::vector<double>& crho, std::vector<double>& cgrad);
+// the same loop with FOURIER interpolation (nci@proc.f90:527-565): the derived grids are built on the device
+void nci_rdg_fourier(const system& s, std::vector<double>& crho, std::vector<double>& cgrad);
+// grid3%fft (grid3mod@proc.f90:1757-1872): fnew = FFT-derived field of fold; iff = ifformat_as_ft_* (param.F90:225-236)
+void grid_fft(const system& s, const grid3& fold, int iff, grid3& fnew);
 
 }  // namespace c2h

@@ -67,7 +67,74 @@ __device__ __forceinline__ int positive_roots_middle_sign(double hxx, double hyy
   return (npos + nzero >= 2) ? 1 : -1;  // lambda_2 >= 0 -> +
 }
 
-__global__ void __launch_bounds__(256) k_nci_rdg(const __grid_constant__ NciParams P, const double* __restrict__ rho,
+// general point: tensor-product cubic Hermite with central-difference slopes (value, gradient, Hessian in grid
+// units).  Not inlined: the node-aligned lattice never comes here and should not pay for its registers.
+__device__ __noinline__ void tricubic_general(const NciParams& P, const double* __restrict__ rho, const int xs_[4], const int ys_[4],
+                                              const int zs_[4], const double t[3], double& f, double gl[3], double h[6]) {
+  auto G = [&](int a, int b, int c) -> double {  // offsets -1..2
+    return __ldg(rho + xs_[a + 1] + (size_t)P.n1 * (ys_[b + 1] + (size_t)P.n2 * zs_[c + 1]));
+  };
+  {
+      // general point: tensor-product cubic Hermite with central-difference slopes
+      double w[3][4], w1[3][4], w2[3][4];
+#pragma unroll
+      for (int d = 0; d < 3; d++) {
+        const double u = t[d], u2 = u * u, u3 = u2 * u;
+        w[d][0] = 0.5 * (-u3 + 2.0 * u2 - u);
+        w[d][1] = 0.5 * (3.0 * u3 - 5.0 * u2 + 2.0);
+        w[d][2] = 0.5 * (-3.0 * u3 + 4.0 * u2 + u);
+        w[d][3] = 0.5 * (u3 - u2);
+        w1[d][0] = 0.5 * (-3.0 * u2 + 4.0 * u - 1.0);
+        w1[d][1] = 0.5 * (9.0 * u2 - 10.0 * u);
+        w1[d][2] = 0.5 * (-9.0 * u2 + 8.0 * u + 1.0);
+        w1[d][3] = 0.5 * (3.0 * u2 - 2.0 * u);
+        w2[d][0] = 0.5 * (-6.0 * u + 4.0);
+        w2[d][1] = 0.5 * (18.0 * u - 10.0);
+        w2[d][2] = 0.5 * (-18.0 * u + 8.0);
+        w2[d][3] = 0.5 * (6.0 * u - 2.0);
+      }
+      f = 0.0;
+      gl[0] = gl[1] = gl[2] = 0.0;
+#pragma unroll
+      for (int q = 0; q < 6; q++) h[q] = 0.0;
+#pragma unroll 1
+      for (int c = 0; c < 4; c++) {
+        double p0 = 0, px = 0, pxx = 0, py = 0, pxy = 0, pyy = 0;  // contracted over x and y
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+          double r0 = 0, rx = 0, rxx = 0;
+#pragma unroll
+          for (int a = 0; a < 4; a++) {
+            const double v = G(a - 1, b - 1, c - 1);
+            r0 += w[0][a] * v;
+            rx += w1[0][a] * v;
+            rxx += w2[0][a] * v;
+          }
+          p0 += w[1][b] * r0;
+          px += w[1][b] * rx;
+          pxx += w[1][b] * rxx;
+          py += w1[1][b] * r0;
+          pxy += w1[1][b] * rx;
+          pyy += w2[1][b] * r0;
+        }
+        f += w[2][c] * p0;
+        gl[0] += w[2][c] * px;
+        gl[1] += w[2][c] * py;
+        gl[2] += w1[2][c] * p0;
+        h[0] += w[2][c] * pxx;
+        h[1] += w[2][c] * pyy;
+        h[2] += w2[2][c] * p0;
+        h[3] += w[2][c] * pxy;
+        h[4] += w1[2][c] * px;
+        h[5] += w1[2][c] * py;
+      }
+  }
+}
+
+#ifndef NCI_MINB
+#define NCI_MINB 4
+#endif
+__global__ void __launch_bounds__(256, NCI_MINB) k_nci_rdg(const __grid_constant__ NciParams P, const double* __restrict__ rho,
                                                  const double* __restrict__ nuc, double* __restrict__ crho,
                                                  double* __restrict__ cgrad) {
   __shared__ double s_rho[BI * BJ * BK];
@@ -135,59 +202,7 @@ __global__ void __launch_bounds__(256) k_nci_rdg(const __grid_constant__ NciPara
       h[4] = 0.25 * (G(1, 0, 1) - G(-1, 0, 1) - G(1, 0, -1) + G(-1, 0, -1));
       h[5] = 0.25 * (G(0, 1, 1) - G(0, -1, 1) - G(0, 1, -1) + G(0, -1, -1));
     } else {
-      // general point: tensor-product cubic Hermite with central-difference slopes
-      double w[3][4], w1[3][4], w2[3][4];
-#pragma unroll
-      for (int d = 0; d < 3; d++) {
-        const double u = t[d], u2 = u * u, u3 = u2 * u;
-        w[d][0] = 0.5 * (-u3 + 2.0 * u2 - u);
-        w[d][1] = 0.5 * (3.0 * u3 - 5.0 * u2 + 2.0);
-        w[d][2] = 0.5 * (-3.0 * u3 + 4.0 * u2 + u);
-        w[d][3] = 0.5 * (u3 - u2);
-        w1[d][0] = 0.5 * (-3.0 * u2 + 4.0 * u - 1.0);
-        w1[d][1] = 0.5 * (9.0 * u2 - 10.0 * u);
-        w1[d][2] = 0.5 * (-9.0 * u2 + 8.0 * u + 1.0);
-        w1[d][3] = 0.5 * (3.0 * u2 - 2.0 * u);
-        w2[d][0] = 0.5 * (-6.0 * u + 4.0);
-        w2[d][1] = 0.5 * (18.0 * u - 10.0);
-        w2[d][2] = 0.5 * (-18.0 * u + 8.0);
-        w2[d][3] = 0.5 * (6.0 * u - 2.0);
-      }
-      f = 0.0;
-      gl[0] = gl[1] = gl[2] = 0.0;
-#pragma unroll
-      for (int q = 0; q < 6; q++) h[q] = 0.0;
-#pragma unroll 1
-      for (int c = 0; c < 4; c++) {
-        double p0 = 0, px = 0, pxx = 0, py = 0, pxy = 0, pyy = 0;  // contracted over x and y
-#pragma unroll
-        for (int b = 0; b < 4; b++) {
-          double r0 = 0, rx = 0, rxx = 0;
-#pragma unroll
-          for (int a = 0; a < 4; a++) {
-            const double v = G(a - 1, b - 1, c - 1);
-            r0 += w[0][a] * v;
-            rx += w1[0][a] * v;
-            rxx += w2[0][a] * v;
-          }
-          p0 += w[1][b] * r0;
-          px += w[1][b] * rx;
-          pxx += w[1][b] * rxx;
-          py += w1[1][b] * r0;
-          pxy += w1[1][b] * rx;
-          pyy += w2[1][b] * r0;
-        }
-        f += w[2][c] * p0;
-        gl[0] += w[2][c] * px;
-        gl[1] += w[2][c] * py;
-        gl[2] += w1[2][c] * p0;
-        h[0] += w[2][c] * pxx;
-        h[1] += w[2][c] * pyy;
-        h[2] += w2[2][c] * p0;
-        h[3] += w[2][c] * pxy;
-        h[4] += w1[2][c] * px;
-        h[5] += w1[2][c] * py;
-      }
+      tricubic_general(P, rho, xs_, ys_, zs_, t, f, gl, h);
     }
     // to fractional coordinates (:2811-2817)
     const double dn[3] = {(double)P.n1, (double)P.n2, (double)P.n3};

@@ -115,6 +115,29 @@ module critic2_gpu
        real(c_double) :: crho(*), cgrad(*)
        integer(c_int) :: c2g_nci_rdg
      end function c2g_nci_rdg
+     function c2g_fft_derivative(ctx,handle,iff,x2c,hout) bind(c,name="c2g_fft_derivative")
+       import :: c_int, c_ptr, c_double
+       type(c_ptr), value :: ctx
+       integer(c_int), value :: handle, iff
+       real(c_double) :: x2c(3,3)
+       integer(c_int) :: hout
+       integer(c_int) :: c2g_fft_derivative
+     end function c2g_fft_derivative
+     function c2g_grid_download(ctx,handle,f) bind(c,name="c2g_grid_download")
+       import :: c_int, c_ptr, c_double
+       type(c_ptr), value :: ctx
+       integer(c_int), value :: handle
+       real(c_double) :: f(*)
+       integer(c_int) :: c2g_grid_download
+     end function c2g_grid_download
+     function c2g_nci_rdg_fourier(ctx,h,x0,xmat,nstep,c2x,c2xl,crho,cgrad) bind(c,name="c2g_nci_rdg_fourier")
+       import :: c_int, c_ptr, c_double
+       type(c_ptr), value :: ctx
+       integer(c_int) :: h(5), nstep(3)
+       real(c_double) :: x0(3), xmat(3,3), c2x(3,3), c2xl(3,3)
+       real(c_double) :: crho(*), cgrad(*)
+       integer(c_int) :: c2g_nci_rdg_fourier
+     end function c2g_nci_rdg_fourier
   end interface
 
 contains
@@ -294,5 +317,46 @@ contains
        "gpu_nci_rdg")
     call check(c2g_grid_free(ctx,h),"gpu_nci_rdg")
   end subroutine gpu_nci_rdg
+
+  !> grid3%fft on the device (grid3mod@proc.f90:1757-1872): fnew%f = FFT-derived field of fold%f.
+  !> iff is one of the ifformat_as_ft_* codes of param.F90 (the C header uses the same numbers).
+  !> Call site: the body of grid3%fft after copy_geometry (:1781-1784), i.e. LOAD AS LAP/GRAD/..., the
+  !> lap/gmod integrables and the derived grids of NCIPLOT FOURIER.
+  subroutine gpu_grid_fft(fnew,fold,x2c,iff)
+    real*8, intent(inout) :: fnew(:,:,:)
+    real*8, intent(in) :: fold(:,:,:)
+    real*8, intent(in) :: x2c(3,3)
+    integer, intent(in) :: iff
+    integer(c_int) :: n(3), h, hout
+
+    n = int(shape(fold),c_int)
+    call check(c2g_grid_upload(ctx,fold,n,h),"gpu_grid_fft")
+    call check(c2g_fft_derivative(ctx,h,int(iff,c_int),x2c,hout),"gpu_grid_fft")
+    call check(c2g_grid_download(ctx,hout,fnew),"gpu_grid_fft")
+    call check(c2g_grid_free(ctx,h),"gpu_grid_fft")
+    call check(c2g_grid_free(ctx,hout),"gpu_grid_fft")
+  end subroutine gpu_grid_fft
+
+  !> NCIPLOT loop with FOURIER interpolation (nci@proc.f90:527-565): the four derived grids of :528-531 are
+  !> built on the device from the reference field and never leave it.
+  subroutine gpu_nci_rdg_fourier(f,x2c,x0,xmat,nstep,m_c2x,c2xl,crho,cgrad)
+    use param, only: ifformat_as_ft_grad, ifformat_as_ft_xx, ifformat_as_ft_yy, ifformat_as_ft_zz
+    real*8, intent(in) :: f(:,:,:)
+    real*8, intent(in) :: x2c(3,3), x0(3), xmat(3,3), m_c2x(3,3), c2xl(3,3)
+    integer, intent(in) :: nstep(3)
+    real*8, intent(inout) :: crho(0:,0:,0:), cgrad(0:,0:,0:)
+    integer(c_int) :: n(3), h(5), i
+    integer, parameter :: iffs(4) = (/ifformat_as_ft_grad,ifformat_as_ft_xx,ifformat_as_ft_yy,ifformat_as_ft_zz/)
+
+    n = int(shape(f),c_int)
+    call check(c2g_grid_upload(ctx,f,n,h(1)),"gpu_nci_rdg_fourier")
+    do i = 1, 4
+       call check(c2g_fft_derivative(ctx,h(1),int(iffs(i),c_int),x2c,h(i+1)),"gpu_nci_rdg_fourier")
+    end do
+    call check(c2g_nci_rdg_fourier(ctx,h,x0,xmat,int(nstep,c_int),m_c2x,c2xl,crho,cgrad),"gpu_nci_rdg_fourier")
+    do i = 1, 5
+       call check(c2g_grid_free(ctx,h(i)),"gpu_nci_rdg_fourier")
+    end do
+  end subroutine gpu_nci_rdg_fourier
 
 end module critic2_gpu

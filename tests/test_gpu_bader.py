@@ -196,6 +196,45 @@ def test_fast_equals_exact_at_config_size(ctx, N, side):
     ctx.free(h)
 
 
+def test_headline_size_properties(ctx):
+    """BASELINE.json configs[4] at full size (1024^3, 512 atoms, generated in HBM): size-independent properties of
+    the assignment + integration through the C ABI -- every point belongs to exactly one basin (counts sum to N^3,
+    volumes sum to the cell volume), the basin populations add up to the integral over the whole cell obtained with
+    all maxima mapped to one basin (1e-10 relative, north_star), one basin per atom, and the result is reproducible
+    (second call: identical counts; populations to 1e-13, the order of the shared-memory atomics inside a block is free)."""
+    N, side = 1024, 8
+    n = (N, N, N)
+    x2c = S.cell_x2c(5.0 * side, 5.0 * side, 5.0 * side)
+    at, z, al = S.jittered_lattice(side, 5)
+    at = S.snap_to_grid(at, n)
+    h = ctx.alloc(n)
+    ctx.promolecular(h, x2c, at, z, al, nimg=1, rc=8.0)
+    _, car2lat, lid = orc.bader_metrics(x2c, n)
+    om = S.omega(x2c)
+    runs = []
+    for rep in range(2):
+        b = ctx.bader_assign(h, car2lat, lid, algo=capi.BADER_FAST)
+        assert b.nmax == side**3
+        cnt = b.counts()
+        assert int(cnt.sum()) == N**3 and cnt.min() > 0
+        b.set_map(b.nmax, np.arange(1, b.nmax + 1, dtype=np.int32))
+        vol, ps = ctx.integrate(b, [h], om)
+        assert abs(vol.sum() - om) <= 1e-12 * om
+        b.set_map(1, np.ones(b.nmax, dtype=np.int32))
+        vol1, ps1 = ctx.integrate(b, [h], om)
+        assert abs(ps[:, 0].sum() - ps1[0, 0]) <= 1e-10 * abs(ps1[0, 0])
+        # every maximum sits on an atom (the density model has one cusp per snapped atom)
+        pm = (b.maxima() - 1) / np.array(n, dtype=float)
+        d = np.abs(pm[:, None, :] - at[None, :, :])
+        d = np.minimum(d, 1.0 - d).max(axis=2).min(axis=1)
+        assert d.max() <= 1.5 / N
+        runs.append((cnt.copy(), ps.copy()))
+        b.free()
+    assert np.array_equal(runs[0][0], runs[1][0])
+    assert np.abs(runs[0][1] - runs[1][1]).max() <= 1e-13 * np.abs(runs[0][1]).max()
+    ctx.free(h)
+
+
 def test_error_paths(ctx):
     with pytest.raises(capi.C2GError):
         ctx.bader_assign(12345, np.eye(3), np.ones(27))
