@@ -377,19 +377,27 @@ def run_ours(args):
     ctx.download_slab_ptr(h_f2, host_f2.data_ptr())
 
     def step_e2e():
+        """Host buffers in, host results out, through the public C ABI.  Single GPU: the asynchronous entry points
+        let the upload of the second field overlap the assignment on the first, and the download of the labels
+        overlap that upload (PCIe is full duplex); everything is complete at the final synchronize."""
         nonlocal ident
         if world > 1:
             ha = ctx.upload_slab_ptr(host_rho.data_ptr(), n)
             hb = ctx.upload_slab_ptr(host_f2.data_ptr(), n)
         else:
-            ha = ctx.upload_ptr(host_rho.data_ptr(), n)
-            hb = ctx.upload_ptr(host_f2.data_ptr(), n)
+            ha = ctx.upload_ptr_async(host_rho.data_ptr(), n)
+            hb = ctx.upload_ptr_async(host_f2.data_ptr(), n)
         bb = ctx.bader_assign(ha, car2lat, lid, algo=capi.BADER_FAST)
         if ident is None or len(ident) != bb.nmax:
             ident = np.arange(1, bb.nmax + 1, dtype=np.int32)
         bb.set_map(bb.nmax, ident)
-        v, p = ctx.integrate(bb, [ha, hb], omega)
-        bb.labels_ptr(host_idg.data_ptr())
+        if world > 1:
+            v, p = ctx.integrate(bb, [ha, hb], omega)
+            bb.labels_ptr(host_idg.data_ptr())
+        else:
+            bb.labels_ptr_async(host_idg.data_ptr())
+            v, p = ctx.integrate(bb, [ha, hb], omega)
+            ctx.synchronize()
         bb.free(); ctx.free(ha); ctx.free(hb)
         return p
 

@@ -26,7 +26,7 @@ EXPORTS = [
     "c2g_grid_upload", "c2g_grid_upload_slab", "c2g_slab_range", "c2g_slab_bounds_query", "c2g_grid_alloc", "c2g_grid_download", "c2g_grid_download_slab", "c2g_grid_free", "c2g_grid_promolecular",
     "c2g_bader_assign", "c2g_basins_maxima", "c2g_basins_counts", "c2g_basins_set_map", "c2g_basins_labels",
     "c2g_basins_relabel", "c2g_basins_free", "c2g_basins_stats", "c2g_integrate", "c2g_yt_build",
-    "c2g_yt_weights", "c2g_nci_rdg", "c2g_nci_rdg_resident", "c2g_fft_derivative", "c2g_nci_rdg_fourier", "c2g_nci_range", "c2g_profile_enable", "c2g_profile_count",
+    "c2g_yt_weights", "c2g_nci_rdg", "c2g_nci_rdg_resident", "c2g_fft_derivative", "c2g_nci_rdg_fourier", "c2g_nci_range", "c2g_grid_upload_async", "c2g_basins_labels_async", "c2g_profile_enable", "c2g_profile_count",
     "c2g_profile_get", "c2g_profile_reset", "c2g_launch_count", "c2g_flush_l2", "c2g_synchronize", "c2g_timer_start", "c2g_timer_stop",
 ]
 
@@ -267,6 +267,13 @@ class Context:
         self._chk(self.lib.c2g_grid_upload(self.h, C.c_void_p(ptr), _p(n, C.c_int), C.byref(h)))
         return h.value
 
+    def upload_ptr_async(self, ptr, n):
+        """Asynchronous upload from a (pinned) host buffer; see c2g_grid_upload_async."""
+        nn = np.array(n, dtype=np.int32)
+        h = C.c_int(-1)
+        self._chk(self.lib.c2g_grid_upload_async(self.h, C.c_void_p(ptr), _p(nn, C.c_int), C.byref(h)))
+        return h.value
+
     def upload_slab_ptr(self, ptr, n):
         n = np.array(n, dtype=np.int32)
         h = C.c_int(-1)
@@ -310,6 +317,10 @@ class Basins:
         a = np.ascontiguousarray(assigned, dtype=np.int32)
         self.ctx._chk(self.ctx.lib.c2g_basins_relabel(self.h, C.c_int(len(a)), _p(a, C.c_int), C.c_int(nattr_new)))
         self.nattr = nattr_new
+
+    def labels_ptr_async(self, ptr):
+        """Asynchronous download of bas%idg into a (pinned) host buffer; complete after Context.synchronize()."""
+        self.ctx._chk(self.ctx.lib.c2g_basins_labels_async(self.h, C.c_void_p(ptr)))
 
     def labels_ptr(self, ptr):
         """idg (this rank's slab) into a raw host pointer."""

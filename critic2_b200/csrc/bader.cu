@@ -521,6 +521,79 @@ __global__ void __launch_bounds__(256) k_maxima(const __grid_constant__ BaderPar
   }
 }
 
+// Same pass for even n1: a lane owns TWO consecutive x points (one 16-byte load per plane), which halves the
+// shuffles, the edge handling and the address arithmetic per point -- k_maxima is issue-bound (75 % of the issue
+// slots at 3.6 TB/s), not load-bound.  A block = 128 threads = 256 consecutive x points of one row.
+__global__ void __launch_bounds__(128) k_maxima2(const __grid_constant__ BaderParams P, const Slab S,
+                                                 const double* __restrict__ rho, int* __restrict__ cand,
+                                                 int* __restrict__ ncand, int maxcand, const __grid_constant__ CubeFlags CF) {
+  const int n1 = P.n1, n2 = P.n2, n3 = P.n3;
+  const size_t s3 = (size_t)n1 * n2;
+  const int lane = threadIdx.x & 31;
+  const int gx = blockIdx.x * 256 + 2 * threadIdx.x, gy = blockIdx.y;  // first of the two points
+  if (gx - 2 * lane >= n1) return;  // whole warp past the end of the row
+  const int z0 = S.zlo + blockIdx.z * MZC, z1 = min(z0 + MZC, S.zhi);
+  const bool valid = gx < n1;       // n1 is even: both points or none
+  const double* cp = rho + wrapx(gx, n1) + (size_t)n1 * gy;  // periodic images past the end keep the shuffles right
+  const bool edge = lane == 0 || lane == 31;
+  const double* ep = rho + wrapx(lane == 0 ? gx - 1 : gx + 2, n1) + (size_t)n1 * gy;
+  const size_t wrapback = s3 * (size_t)n3;
+  int wz = wrapx(z0 - 1, n3);
+  cp += s3 * wz; ep += s3 * wz;
+  auto next_plane = [&]() {
+    cp += s3; ep += s3;
+    if (++wz == n3) { wz = 0; cp -= wrapback; ep -= wrapback; }
+  };
+  double2 a[MZP + 2];
+  double e[MZP + 2];
+#pragma unroll
+  for (int k = 0; k < MZP + 2; k++) {
+    const bool need = z0 - 1 + k <= z1;
+    a[k] = need ? __ldg(reinterpret_cast<const double2*>(cp)) : make_double2(0.0, 0.0);
+    e[k] = (need && edge) ? __ldg(ep) : 0.0;
+    if (need) next_plane();
+  }
+  for (int zb = z0; zb < z1; zb += MZP) {
+    double2 an[MZP];
+    double en[MZP];
+#pragma unroll
+    for (int k = 0; k < MZP; k++) {
+      const bool need = zb + MZP + 1 + k <= z1;
+      an[k] = need ? __ldg(reinterpret_cast<const double2*>(cp)) : make_double2(0.0, 0.0);
+      en[k] = (need && edge) ? __ldg(ep) : 0.0;
+      if (need) next_plane();
+    }
+#pragma unroll
+    for (int k = 0; k < MZP; k++) {
+      const int iz = zb + k;
+      if (iz < z1) {  // warp-uniform
+        const double2 vm = a[k], vc = a[k + 1], vp = a[k + 2];
+        double xl = __shfl_up_sync(FULL, vc.y, 1), xr = __shfl_down_sync(FULL, vc.x, 1);
+        if (lane == 0) xl = e[k + 1];
+        if (lane == 31) xr = e[k + 1];
+        const bool c0 = vc.x >= xl && vc.x >= vc.y && vc.x >= vm.x && vc.x >= vp.x;
+        const bool c1 = vc.y >= vc.x && vc.y >= xr && vc.y >= vm.y && vc.y >= vp.y;
+        if (valid && (c0 || c1)) {
+#pragma unroll 1
+          for (int q = 0; q < 2; q++) {
+            if (!(q ? c1 : c0)) continue;
+            const int px = gx + q;
+            if (dev_is_max(n1, n2, n3, rho, px, gy, iz)) {
+              const int slot = atomicAdd(ncand, 1);
+              if (slot < maxcand) cand[slot] = px + n1 * (gy + n2 * iz);
+              for (int i = 0; i < CF.nlev; i++)
+                CF.p[i][(px >> (i + 1)) + CF.c1[i] * ((gy >> (i + 1)) + (size_t)CF.c2[i] * ((iz - S.zlo) >> (i + 1)))] = 1;
+            }
+          }
+        }
+      }
+    }
+    a[0] = a[MZP]; a[1] = a[MZP + 1]; e[0] = e[MZP]; e[1] = e[MZP + 1];
+#pragma unroll
+    for (int k = 0; k < MZP; k++) { a[k + 2] = an[k]; e[k + 2] = en[k]; }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // walkers: persistent warps with lane refill.  A warp takes batches of work items from a global cursor;
 // a lane whose trajectory has ended picks up the next item while the other lanes keep stepping, so the
@@ -1487,6 +1560,7 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
   if (!nmax_out || !res_out || !car2lat || !lat_i_dist) return ctx->fail(C2G_ERR_ARG, "c2g_bader_assign: null argument");
   if (handle < 0 || handle >= (int)ctx->grids.size() || !ctx->grids[handle].used)
     return ctx->fail(C2G_ERR_ARG, "c2g_bader_assign: invalid grid handle %d", handle);
+  c2g_grid_ready(ctx, handle);
   const c2g_grid& g = ctx->grids[handle];
   if (g.nn >= (1ll << 31)) return ctx->fail(C2G_ERR_ARG, "c2g_bader_assign: grid too large for int32 indices");
   cudaStream_t st = ctx->stream;
@@ -1567,7 +1641,10 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
     if (S.nzl > 0) {
       dim3 grid((n1 + 255) / 256, n2, (S.nzl + MZC - 1) / MZC);
       ctx->prof_begin("bader_maxima");
-      k_maxima<<<grid, 256, 0, st>>>(P, S, g.d, b_cand.as<int>(), cnt, maxcand, CF);
+      if (n1 % 2 == 0 && ((uintptr_t)g.d % 16) == 0)
+        k_maxima2<<<grid, 128, 0, st>>>(P, S, g.d, b_cand.as<int>(), cnt, maxcand, CF);
+      else
+        k_maxima<<<grid, 256, 0, st>>>(P, S, g.d, b_cand.as<int>(), cnt, maxcand, CF);
       ctx->prof_end();
       C2G_KERNEL_CHECK(ctx);
     }

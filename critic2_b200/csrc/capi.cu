@@ -132,6 +132,17 @@ __global__ void __launch_bounds__(256) k_promolecular_bins(const __grid_constant
 int check_handle(c2g_context* ctx, int h, const char* who) {
   if (h < 0 || h >= (int)ctx->grids.size() || !ctx->grids[h].used)
     return ctx->fail(C2G_ERR_ARG, "%s: invalid grid handle %d", who, h);
+  c2g_grid_ready(ctx, h);  // order the compute stream after an asynchronous upload of this grid
+  return C2G_OK;
+}
+
+// copy streams and the ordering event, created on first use
+int ensure_copy_streams(c2g_context* ctx) {
+  if (!ctx->copy_in) {
+    C2G_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+    C2G_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+    C2G_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_order, cudaEventDisableTiming));
+  }
   return C2G_OK;
 }
 
@@ -201,8 +212,19 @@ void c2g_finalize(c2g_context* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  for (auto& g : ctx->grids)
+  if (ctx->copy_in) {
+    cudaStreamSynchronize(ctx->copy_in);
+    cudaStreamSynchronize(ctx->copy_out);
+    cudaStreamDestroy(ctx->copy_in);
+    cudaStreamDestroy(ctx->copy_out);
+    cudaEventDestroy(ctx->ev_order);
+  }
+  for (void* p : ctx->deferred) c2g_release(ctx, p);
+  ctx->deferred.clear();
+  for (auto& g : ctx->grids) {
+    if (g.ready) cudaEventDestroy(g.ready);
     if (g.used && g.d) c2g_release(ctx, g.d);
+  }
   c2g_mem_trim(ctx);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->flushbuf) cudaFree(ctx->flushbuf);
@@ -242,6 +264,27 @@ int c2g_grid_upload(c2g_context* ctx, const double* f, const int n[3], int* hand
   c2g_grid& g = ctx->grids[*handle];
   C2G_CUDA(ctx, cudaMemcpyAsync(g.d, f, sizeof(double) * g.nn, cudaMemcpyHostToDevice, ctx->stream));
   C2G_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return C2G_OK;
+}
+
+// Asynchronous upload: the copy runs on a separate stream and overlaps the kernels of other calls; every call that
+// reads the grid is ordered after it on the device.  `f` must be page-locked for a real overlap and must stay
+// valid and unchanged until c2g_synchronize (or any call that returns results computed from this grid).
+int c2g_grid_upload_async(c2g_context* ctx, const double* f, const int n[3], int* handle) {
+  if (!ctx) return C2G_ERR_ARG;
+  if (!f) return ctx->fail(C2G_ERR_ARG, "c2g_grid_upload_async: null field");
+  int rc = ensure_copy_streams(ctx);
+  if (rc != C2G_OK) return rc;
+  rc = c2g_grid_alloc(ctx, n, handle);
+  if (rc != C2G_OK) return rc;
+  c2g_grid& g = ctx->grids[*handle];
+  // the block may come from the cache and still be read by work queued on the compute stream
+  C2G_CUDA(ctx, cudaEventRecord(ctx->ev_order, ctx->stream));
+  C2G_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, ctx->ev_order, 0));
+  C2G_CUDA(ctx, cudaMemcpyAsync(g.d, f, sizeof(double) * g.nn, cudaMemcpyHostToDevice, ctx->copy_in));
+  if (!g.ready) C2G_CUDA(ctx, cudaEventCreateWithFlags(&g.ready, cudaEventDisableTiming));
+  C2G_CUDA(ctx, cudaEventRecord(g.ready, ctx->copy_in));
+  g.pending = true;
   return C2G_OK;
 }
 
@@ -319,7 +362,8 @@ int c2g_grid_free(c2g_context* ctx, int handle) {
   int rc = check_handle(ctx, handle, "c2g_grid_free");
   if (rc) return rc;
   c2g_grid& g = ctx->grids[handle];
-  c2g_release(ctx, g.d);
+  c2g_release(ctx, g.d);  // (check_handle has ordered the compute stream after a pending upload)
+  if (g.ready) cudaEventDestroy(g.ready);
   g = c2g_grid();
   return C2G_OK;
 }
@@ -504,6 +548,31 @@ int c2g_basins_labels(c2g_basins* res, int* idg) {
   return C2G_OK;
 }
 
+// Asynchronous variant: the label map runs on the compute stream, the device-to-host copy on a separate stream, so
+// that it overlaps later calls (e.g. c2g_integrate, or the upload of the next field).  `idg` must be page-locked for
+// a real overlap; it is complete after c2g_synchronize.
+int c2g_basins_labels_async(c2g_basins* res, int* idg) {
+  if (!res) return C2G_ERR_ARG;
+  c2g_context* ctx = res->ctx;
+  if (!idg) return ctx->fail(C2G_ERR_ARG, "c2g_basins_labels_async: null output");
+  if (!res->has_map) return ctx->fail(C2G_ERR_STATE, "c2g_basins_labels_async: call c2g_basins_set_map first");
+  int rc = ensure_copy_streams(ctx);
+  if (rc != C2G_OK) return rc;
+  const long long nnl = (long long)res->n[0] * res->n[1] * (res->zhi - res->zlo);
+  if (nnl == 0) return C2G_OK;
+  int* d_out = nullptr;
+  C2G_CUDA(ctx, c2g_alloc(ctx, (void**)&d_out, sizeof(int) * nnl));
+  ctx->prof_begin("map_labels");
+  k_map_labels<<<ctx->nsm * 8, 256, 0, ctx->stream>>>(nnl, res->d_label, res->d_map, d_out, res->kind == 0 ? 0x7fffffff : -1);
+  ctx->prof_end();
+  C2G_KERNEL_CHECK(ctx);
+  C2G_CUDA(ctx, cudaEventRecord(ctx->ev_order, ctx->stream));
+  C2G_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, ctx->ev_order, 0));
+  C2G_CUDA(ctx, cudaMemcpyAsync(idg, d_out, sizeof(int) * nnl, cudaMemcpyDeviceToHost, ctx->copy_out));
+  ctx->deferred.push_back(d_out);  // handed back to the cache by c2g_synchronize, once the copy is done
+  return C2G_OK;
+}
+
 int c2g_basins_stats(c2g_basins* res, long long stats[8]) {
   if (!res || !stats) return C2G_ERR_ARG;
   for (int i = 0; i < 8; i++) stats[i] = res->stats[i];
@@ -575,6 +644,12 @@ int c2g_timer_stop(c2g_context* ctx, double* ms) {
 int c2g_synchronize(c2g_context* ctx) {
   if (!ctx) return C2G_ERR_ARG;
   C2G_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->copy_in) {
+    C2G_CUDA(ctx, cudaStreamSynchronize(ctx->copy_in));
+    C2G_CUDA(ctx, cudaStreamSynchronize(ctx->copy_out));
+  }
+  for (void* p : ctx->deferred) c2g_release(ctx, p);
+  ctx->deferred.clear();
   ctx->prof_collect();
   return C2G_OK;
 }

@@ -23,6 +23,8 @@ struct c2g_grid {
   long long nn = 0;
   double* d = nullptr;  // device, f(n1,n2,n3) index 1 fastest
   bool used = false;
+  cudaEvent_t ready = nullptr;  // c2g_grid_upload_async: recorded on the copy stream after the H2D copy
+  bool pending = false;         // the compute stream has not been ordered after `ready` yet
 };
 
 struct c2g_prof_entry {
@@ -51,6 +53,10 @@ struct c2g_context {
   int rank = 0, nranks = 1;
   void* nccl = nullptr;  // ncclComm_t
   cudaEvent_t t0 = nullptr, t1 = nullptr;  // c2g_timer_*
+  // asynchronous host <-> device copies (c2g_grid_upload_async, c2g_basins_labels_async)
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;
+  cudaEvent_t ev_order = nullptr;
+  std::vector<void*> deferred;  // device blocks still read by copy_out: released by c2g_synchronize
   // device-memory cache (c2g_alloc / c2g_release below)
   std::multimap<size_t, void*> mem_free;           // size -> cached block
   std::unordered_map<void*, size_t> mem_live;      // block handed out -> its size
@@ -218,5 +224,15 @@ struct DevBuf {
   }
   template <class T> T* as() { return (T*)p; }
 };
+
+// order the compute stream after the asynchronous upload of a grid (no-op for synchronously uploaded grids)
+static inline void c2g_grid_ready(c2g_context* ctx, int h) {
+  if (h < 0 || h >= (int)ctx->grids.size()) return;
+  c2g_grid& g = ctx->grids[h];
+  if (g.pending) { cudaStreamWaitEvent(ctx->stream, g.ready, 0); g.pending = false; }
+}
+static inline void c2g_grids_ready_all(c2g_context* ctx) {
+  for (int h = 0; h < (int)ctx->grids.size(); h++) c2g_grid_ready(ctx, h);
+}
 
 static inline int c2g_blocks_for(long long n, int threads) { return (int)((n + threads - 1) / threads); }

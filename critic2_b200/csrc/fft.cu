@@ -138,6 +138,7 @@ extern "C" int c2g_fft_derivative(c2g_context* ctx, int handle, int iff, const d
   if (ctx->nranks > 1) return ctx->fail(C2G_ERR_STATE, "c2g_fft_derivative: single-GPU only (SURVEY.md 8e)");
   CufftApi& api = cufft_api();
   if (!api.ok) return ctx->fail(C2G_ERR_CUDA, "c2g_fft_derivative: cuFFT unavailable: %s", api.err);
+  c2g_grids_ready_all(ctx);
   const int n1 = ctx->grids[handle].n[0], n2 = ctx->grids[handle].n[1], n3 = ctx->grids[handle].n[2];
   const long long nn = ctx->grids[handle].nn;
   cudaStream_t st = ctx->stream;

@@ -212,6 +212,7 @@ extern "C" int c2g_integrate(c2g_context* ctx, c2g_basins* res, int nprop, const
   for (int k = 0; k < nprop; k++) {
     const int h = fieldhandles[k];
     if (h < 0 || h >= (int)ctx->grids.size() || !ctx->grids[h].used) return ctx->fail(C2G_ERR_ARG, "c2g_integrate: invalid field handle %d", h);
+    c2g_grid_ready(ctx, h);
     const c2g_grid& g = ctx->grids[h];
     if (g.n[0] != res->n[0] || g.n[1] != res->n[1] || g.n[2] != res->n[2])
       return ctx->fail(C2G_ERR_ARG, "c2g_integrate: field %d has a different grid size", k + 1);

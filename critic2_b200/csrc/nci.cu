@@ -437,6 +437,7 @@ static void nci_range(const c2g_context* ctx, int ns1, int* ilo, int* ihi) {
 int nci_launch(c2g_context* ctx, int handle, const double x0[3], const double xmat[9], const int nstep[3],
                const double c2x[9], const double x2c[9], const double c2xl[9], int nnuc, const double* nuc_cart,
                double* d_rho, double* d_grad) {
+  c2g_grids_ready_all(ctx);
   const c2g_grid& g = ctx->grids[handle];
   NciParams P;
   P.n1 = g.n[0]; P.n2 = g.n[1]; P.n3 = g.n[2];
@@ -532,6 +533,7 @@ extern "C" int c2g_nci_rdg_fourier(c2g_context* ctx, const int h[5], const doubl
   if (!h || !crho || !cgrad) return ctx->fail(C2G_ERR_ARG, "c2g_nci_rdg_fourier: null argument");
   int rc = nci_check(ctx, h[0], x0, xmat, nstep, c2x, c2x, c2xl, 0, nullptr);
   if (rc) return rc;
+  c2g_grids_ready_all(ctx);
   const c2g_grid& g0 = ctx->grids[h[0]];
   for (int q = 1; q < 5; q++) {
     if (h[q] < 0 || h[q] >= (int)ctx->grids.size() || !ctx->grids[h[q]].used)

@@ -410,6 +410,7 @@ extern "C" int c2g_yt_build(c2g_context* ctx, int handle, int nvec, const int* v
   if (handle < 0 || handle >= (int)ctx->grids.size() || !ctx->grids[handle].used)
     return ctx->fail(C2G_ERR_ARG, "c2g_yt_build: invalid grid handle %d", handle);
   if (nvec < 1 || nvec > MAXVEC) return ctx->fail(C2G_ERR_ARG, "c2g_yt_build: nvec=%d outside 1..%d", nvec, MAXVEC);
+  c2g_grids_ready_all(ctx);
   const c2g_grid& g = ctx->grids[handle];
   if (g.nn >= (1ll << 31)) return ctx->fail(C2G_ERR_ARG, "c2g_yt_build: grid too large for int32 indices");
   cudaStream_t st = ctx->stream;

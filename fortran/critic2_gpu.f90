@@ -115,6 +115,25 @@ module critic2_gpu
        real(c_double) :: crho(*), cgrad(*)
        integer(c_int) :: c2g_nci_rdg
      end function c2g_nci_rdg
+     ! asynchronous upload (copy stream): f must stay allocated and unchanged until c2g_synchronize
+     function c2g_grid_upload_async(ctx,f,n,handle) bind(c,name="c2g_grid_upload_async")
+       import :: c_int, c_ptr, c_double
+       type(c_ptr), value :: ctx
+       real(c_double) :: f(*)
+       integer(c_int) :: n(3), handle
+       integer(c_int) :: c2g_grid_upload_async
+     end function c2g_grid_upload_async
+     function c2g_basins_labels_async(res,idg) bind(c,name="c2g_basins_labels_async")
+       import :: c_int, c_ptr
+       type(c_ptr), value :: res
+       integer(c_int) :: idg(*)
+       integer(c_int) :: c2g_basins_labels_async
+     end function c2g_basins_labels_async
+     function c2g_synchronize(ctx) bind(c,name="c2g_synchronize")
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ctx
+       integer(c_int) :: c2g_synchronize
+     end function c2g_synchronize
      function c2g_fft_derivative(ctx,handle,iff,x2c,hout) bind(c,name="c2g_fft_derivative")
        import :: c_int, c_ptr, c_double
        type(c_ptr), value :: ctx

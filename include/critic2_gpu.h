@@ -61,6 +61,10 @@ const char* c2g_describe(c2g_context* ctx);
 /* Replaces the bas%f copy of intgrid_driver (integration@proc.f90:255-271). */
 int c2g_grid_upload(c2g_context* ctx, const double* f, const int n[3], int* handle);
 int c2g_grid_alloc(c2g_context* ctx, const int n[3], int* handle);
+/* Asynchronous upload on a separate copy stream: returns at once, every call that reads the grid is ordered after
+ * the copy on the device.  `f` should be page-locked (pinned) for a real overlap and must stay valid and unchanged
+ * until c2g_synchronize.  Lets the upload of the second INTEGRABLE field overlap c2g_bader_assign on the first. */
+int c2g_grid_upload_async(c2g_context* ctx, const double* f, const int n[3], int* handle);
 /* Multi-GPU (c2g_init_multi): the grid is sharded as z-slabs f(:,:,zlo+1:zhi) across the ranks
  * (0-based half-open plane range from c2g_slab_range; boundaries are multiples of 4).  Every rank
  * uploads only its own slab; the slabs are replicated over NVLink (NCCL) because the field is
@@ -103,6 +107,9 @@ int c2g_basins_set_map(c2g_basins* res, int nattr, const int* map);
 /* bas%idg(n1,n2,n3) (move_alloc(volnum,bas%idg), bader@proc.f90:229).  Multi-GPU: every rank
  * receives its own slab idg(:,:,zlo+1:zhi). */
 int c2g_basins_labels(c2g_basins* res, int* idg);
+/* Asynchronous variant: the device-to-host copy runs on a separate stream and overlaps later calls; idg (page-locked
+ * for a real overlap) is complete after c2g_synchronize. */
+int c2g_basins_labels_async(c2g_basins* res, int* idg);
 /* int_reorder_gridout's nattr0 full-grid `where` passes (integration@proc.f90:1113-1122,
  * :1139-1144) as one composition of maps: new id = assigned(old id), old ids 1..nattr0. */
 int c2g_basins_relabel(c2g_basins* res, int nattr0, const int* assigned, int nattr_new);

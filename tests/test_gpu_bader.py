@@ -247,3 +247,41 @@ def test_error_paths(ctx):
     with pytest.raises(capi.C2GError):
         b.set_map(1, np.array([5], dtype=np.int32))
     b.free(); ctx.free(h)
+
+
+def test_async_upload_and_labels_match_the_synchronous_calls(ctx):
+    """c2g_grid_upload_async / c2g_basins_labels_async (the e2e path of bench.py): same labels and sums as the
+    synchronous entry points, with the second field uploaded while the assignment runs."""
+    import torch
+    c = cases.make_case("odd_dims")
+    n = c["n"]
+    f2 = cases.second_field(c["f"])
+    _, car2lat, lid = orc.bader_metrics(c["x2c"], n)
+    # synchronous reference
+    h, b, na = gpu_bader(ctx, c, capi.BADER_FAST)
+    h2 = ctx.upload(f2)
+    lab_ref = b.labels(n)
+    vol_ref, ps_ref = ctx.integrate(b, [h, h2], S.omega(c["x2c"]))
+    b.free(); ctx.free(h); ctx.free(h2)
+    # asynchronous path from pinned host buffers
+    nn = int(np.prod(n))
+    pa = torch.empty(nn, dtype=torch.float64, pin_memory=True)
+    pb = torch.empty(nn, dtype=torch.float64, pin_memory=True)
+    pl = torch.empty(nn, dtype=torch.int32, pin_memory=True)
+    pa.numpy()[:] = c["f"].ravel(order="F")
+    pb.numpy()[:] = f2.ravel(order="F")
+    for rep in range(2):  # the second pass reuses cached device blocks
+        ha = ctx.upload_ptr_async(pa.data_ptr(), n)
+        hb = ctx.upload_ptr_async(pb.data_ptr(), n)
+        bb = ctx.bader_assign(ha, car2lat, lid)
+        mp2, na2, _ = H.assign_attractors(bb.maxima(), n, c["x2c"], c["atoms"])
+        bb.set_map(na2, mp2)
+        pl.zero_()
+        bb.labels_ptr_async(pl.data_ptr())
+        vol, ps = ctx.integrate(bb, [ha, hb], S.omega(c["x2c"]))
+        ctx.synchronize()
+        lab = pl.numpy().reshape(n, order="F")
+        assert np.array_equal(lab, lab_ref)
+        assert np.array_equal(vol, vol_ref)
+        assert np.abs(ps - ps_ref).max() <= 1e-12 * np.abs(ps_ref).max()
+        bb.free(); ctx.free(ha); ctx.free(hb)
