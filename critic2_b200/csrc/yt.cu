@@ -185,15 +185,22 @@ __global__ void __launch_bounds__(256) k_indeg(const __grid_constant__ YtParams 
   if (d == 0) order[atomicAdd(otail, 1)] = i;
 }
 
-// Kahn levels, uphill.  ctl[0] = tail, ctl[1] = number of levels; lvl[L] = start of level L in order[]
+// Kahn levels, uphill.  In: ctl[0] = number of in-degree-0 points (level 0, already in order[]).  Out: ctl[0] = points
+// ordered, ctl[1] = number of levels; lvl[L] = start of level L in order[].  The points released while level L is
+// processed are appended behind the end of level L at positions handed out by a PER-LEVEL counter cnt[L+1]
+// (zeroed by the caller), so the end of level L+1 is known after ONE grid barrier per level: nobody touches
+// cnt[L+1] once level L is done.
 __global__ void __launch_bounds__(256) k_kahn(const __grid_constant__ YtParams P, const unsigned* __restrict__ mask,
-                                              const unsigned char* __restrict__ ias, unsigned char* __restrict__ indeg,
-                                              int* __restrict__ order, int* __restrict__ ctl, int* __restrict__ lvl, int maxlvl) {
+                                               const unsigned char* __restrict__ ias, unsigned char* __restrict__ indeg,
+                                               int* __restrict__ order, int* __restrict__ ctl, int* __restrict__ lvl,
+                                               int* __restrict__ cnt, int maxlvl) {
   cg::grid_group grid = cg::this_grid();
+  __shared__ int s_next;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
   int lo = 0, hi = ctl[0], levels = 0;
   while (lo < hi) {
     if (tid == 0 && levels < maxlvl) lvl[levels] = lo;
+    int* next = cnt + min(levels + 1, maxlvl);
     for (int q = lo + tid; q < hi; q += nth) {
       const int i = order[q];
       const Pt p = unlin(P, i);
@@ -206,17 +213,21 @@ __global__ void __launch_bounds__(256) k_kahn(const __grid_constant__ YtParams P
           unsigned* w = (unsigned*)(indeg + (j & ~3));
           const int sh = 8 * (j & 3);
           const unsigned old = atomicSub(w, 1u << sh);
-          if (((old >> sh) & 0xffu) == 1u) order[atomicAdd(ctl, 1)] = j;
+          if (((old >> sh) & 0xffu) == 1u) order[hi + atomicAdd(next, 1)] = j;
         }
       }
     }
     grid.sync();
+    // one L2 read per block, not one per thread (1.5e5 threads reading one address serialise in its L2 slice)
+    if (threadIdx.x == 0) s_next = *((volatile int*)next);
+    __syncthreads();
     lo = hi;
-    hi = ctl[0];
+    hi += s_next;
     levels++;
-    grid.sync();
+    __syncthreads();
   }
   if (tid == 0) {
+    ctl[0] = hi;
     ctl[1] = levels;
     if (levels < maxlvl) lvl[levels] = lo;
   }
@@ -554,13 +565,17 @@ extern "C" int c2g_yt_build(c2g_context* ctx, int handle, int nvec, const int* v
     C2G_KERNEL_CHECK(ctx);
     int blocks = 0, rc;
     if ((rc = coop_grid(ctx, k_kahn, 256, &blocks)) != C2G_OK) return rc;
+    DevBuf b_lcnt;
+    C2G_CUDA(ctx, b_lcnt.alloc(ctx, sizeof(int) * ((size_t)maxlvl + 2)));
+    C2G_CUDA(ctx, cudaMemsetAsync(b_lcnt.p, 0, sizeof(int) * ((size_t)maxlvl + 2), st));
+    int* a_cnt = b_lcnt.as<int>();
     const unsigned* a_mask = S->mask;
     const unsigned char* a_ias = S->ias;
     unsigned char* a_indeg = b_indeg.as<unsigned char>();
     int* a_order = S->order;
     int* a_lvl = S->lvl;
     int a_maxlvl = maxlvl;
-    void* args[] = {(void*)&P, (void*)&a_mask, (void*)&a_ias, (void*)&a_indeg, (void*)&a_order, (void*)&ctl, (void*)&a_lvl, (void*)&a_maxlvl};
+    void* args[] = {(void*)&P, (void*)&a_mask, (void*)&a_ias, (void*)&a_indeg, (void*)&a_order, (void*)&ctl, (void*)&a_lvl, (void*)&a_cnt, (void*)&a_maxlvl};
     ctx->prof_begin("yt_kahn");
     C2G_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_kahn, dim3(blocks), dim3(256), args, 0, st));
     ctx->prof_end();
