@@ -942,15 +942,18 @@ __global__ void __launch_bounds__(256) k_classify(int n1, int n2, int n3, const 
     const int x1 = (x0 + s < n1) ? x0 + s : 0, y1 = (y0 + s < n2) ? y0 + s : 0;
     const size_t p0 = z0 - S.zlo + 1;                              // local plane of z0
     const size_t p1 = ((z0 + s < n3) ? z0 + s : n3) - S.zlo + 1;   // local plane of the upper corners (may be the halo)
-    const int l000 = lbuf[x0 + n1 * y0 + s3 * p0] & LMASK;
-    bool u = !cubemax[t];
-    u = u && ((lbuf[x1 + n1 * y0 + s3 * p0] & LMASK) == l000);
-    u = u && ((lbuf[x0 + n1 * y1 + s3 * p0] & LMASK) == l000);
-    u = u && ((lbuf[x1 + n1 * y1 + s3 * p0] & LMASK) == l000);
-    u = u && ((lbuf[x0 + n1 * y0 + s3 * p1] & LMASK) == l000);
-    u = u && ((lbuf[x1 + n1 * y0 + s3 * p1] & LMASK) == l000);
-    u = u && ((lbuf[x0 + n1 * y1 + s3 * p1] & LMASK) == l000);
-    u = u && ((lbuf[x1 + n1 * y1 + s3 * p1] & LMASK) == l000);
+    // all 8 corner labels in one batch of independent loads (a short-circuit chain would make them 8 dependent
+    // round trips), then one comparison
+    const int* r00 = lbuf + (size_t)n1 * y0 + s3 * p0;
+    const int* r10 = lbuf + (size_t)n1 * y1 + s3 * p0;
+    const int* r01 = lbuf + (size_t)n1 * y0 + s3 * p1;
+    const int* r11 = lbuf + (size_t)n1 * y1 + s3 * p1;
+    const int c0 = r00[x0], c1_ = r00[x1], c2_ = r10[x0], c3_ = r10[x1];
+    const int c4 = r01[x0], c5 = r01[x1], c6 = r11[x0], c7 = r11[x1];
+    const unsigned char hasmax = cubemax[t];
+    const int l000 = c0 & LMASK;
+    const int diff = ((c1_ ^ c0) | (c2_ ^ c0) | (c3_ ^ c0) | (c4 ^ c0) | (c5 ^ c0) | (c6 ^ c0) | (c7 ^ c0)) & LMASK;
+    const bool u = !hasmax && diff == 0;
     uni[t] = u ? l000 : -1;
     nonuni = !u;
     if (FILL && u) {
