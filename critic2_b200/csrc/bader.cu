@@ -12,11 +12,17 @@
 //                    level (s = L0 .. 2): a stride-s cube whose 8 corners agree and that holds no local
 //                    maximum is "uniform" and its stride-s/2 points are filled with the corner label;
 //                    the stride-s/2 points of the other cubes walk, and a walk stops as soon as it
-//                    enters a cube that is uniform together with its 26 neighbour cubes -- the analogue
-//                    of the reference's known==2 interior points at which max_neargrid stops (:447).
-//                    Finally every filled point that has a 26-neighbour with a different label walks
-//                    too, until none is left: the fixed point refine_edge enforces (:300-422, every
-//                    edge point carries the label of its own trajectory).
+//                    reaches a point whose nearest cube-grid vertex is surrounded by 8 uniform cubes of
+//                    one label (octet certificate) -- the analogue of the reference's known==2 interior
+//                    points at which max_neargrid stops (:447).  Finally every filled point that has a
+//                    26-neighbour with a different label walks too, until none is left: the fixed point
+//                    refine_edge enforces (:300-422, every edge point carries the label of its own
+//                    trajectory).  Early stops are logged and re-walked if a later label change voids
+//                    the certificate they relied on (k_requeue).
+// Kernels: k_maxima / k_maxima2 (candidate maxima, streaming), k_walk (persistent path-free walkers),
+// k_walk_big (the rare walks that need the reference's path search), k_classify + k_vsafe (cube
+// classification and certificates per level), k_fill_edge_v (last-level fills + edge detection, driven
+// by the certificates), k_requeue, k_items_* (spatially ordered work items).
 // Labels are indices into the sorted list of candidate maxima; bit 31 (FILLBIT) marks points that were
 // filled, not walked (consumers mask it).
 // Arithmetic: IEEE fp64, evaluation order of the Fortran source, NO fused multiply-add (this

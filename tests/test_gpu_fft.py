@@ -121,3 +121,19 @@ def test_nci_fourier_general_lattice_same_derived_grids(ctx):
     assert np.abs(crho - crho_o).max() <= 1e-12 * np.abs(crho_o).max()
     for hh in hs:
         ctx.free(hh)
+
+
+def test_fft_and_fourier_error_paths(ctx):
+    """Bad calls fail with a status and a message (ferror on the Fortran side), they do not crash."""
+    c = cases.make_case("tiny")
+    h = ctx.upload(c["f"])
+    with pytest.raises(capi.C2GError):
+        ctx.fft_derivative(h, c["x2c"], 99)              # not an ifformat_as_ft_* code
+    with pytest.raises(capi.C2GError):
+        ctx.fft_derivative(12345, c["x2c"], "lap")       # invalid handle
+    with pytest.raises(capi.C2GError):
+        ctx.fft_derivative(h, np.zeros((3, 3)), "lap")   # singular cell
+    other = ctx.upload(np.asfortranarray(np.ones((4, 5, 6))))
+    with pytest.raises(capi.C2GError):
+        ctx.nci_rdg_fourier([h, h, h, h, other], c["x2c"], c["n"])   # derived grid of another shape
+    ctx.free(h); ctx.free(other)
