@@ -174,9 +174,10 @@ __device__ __forceinline__ void walk_init(const BaderParams& P, const double* __
   w.r0 = __ldg(rho + start);
 }
 
+__device__ __forceinline__ int safe_lookup(const SafeMap& sm, int nx, int ny, int nz, int& mapidx);
 template <bool ORTHO>
 __device__ __forceinline__ int walk_step(const BaderParams& P, const double* __restrict__ rho, const MaxHash& h,
-                                         const SafeMap& sm, WState& w, int* path, int cap, int& out) {
+                                         const SafeMap& sm, WState& w, int* path, int cap, int& out, int& sli) {
   const int n1 = P.n1, n2 = P.n2, n3 = P.n3;
   const int s2 = n1, s3 = n1 * n2;
   const int x = w.x, y = w.y, z = w.z, id = w.id;
@@ -239,24 +240,10 @@ __device__ __forceinline__ int walk_step(const BaderParams& P, const double* __r
   if (nid == id) { out = id; return 1; }  // did not move: maximum (:439)
   w.id = nid; w.r0 = rn;
   w.x = nx; w.y = ny; w.z = nz;
+  sli = -1;
   if (sm.safe) {  // quit at a known interior point (:447)
-    const int cz = nz - sm.zlo;
-    if (cz >= 0 && cz < sm.nzl) {
-      int vx, vy, vz;
-      if (sm.octet) {
-        const int hf = (1 << sm.shift) >> 1;
-        vx = (nx + hf) >> sm.shift; vy = (ny + hf) >> sm.shift; vz = (cz + hf) >> sm.shift;
-        if (vx == sm.c1) vx = 0;
-        if (vy == sm.c2) vy = 0;
-        if (vz == sm.c3) vz = sm.wrapz ? 0 : -1;
-      } else {
-        vx = nx >> sm.shift; vy = ny >> sm.shift; vz = cz >> sm.shift;
-      }
-      if (vz >= 0) {
-        const int sl = sm.safe[vx + sm.c1 * (vy + (size_t)sm.c2 * vz)];
-        if (sl >= 0) { out = sl; return 2; }
-      }
-    }
+    const int sl = safe_lookup(sm, nx, ny, nz, sli);
+    if (sl >= 0) { out = sl; return 2; }
   }
   return 0;
 }
@@ -630,7 +617,7 @@ struct WalkArgs {
   int batch;
   int refill_min;           // idle lanes that trigger a refill
   int steps_per_check;      // walker steps between two looks at the work queue
-  int* overflow; int* noverflow; int overcap;
+  int2* overflow; int* noverflow; int overcap;  // (start, index in the dense walker list or -1)
   int* err;
   unsigned long long* nsteps;
   int* next; int* nnext; int nextcap;  // FIX: points whose neighbourhood became non-uniform
@@ -693,7 +680,7 @@ __device__ __forceinline__ void walk_finish(const BaderParams& P, const WalkArgs
   if (A.stop && tidx >= 0) A.stop[tidx] = (st == 2) ? ((A.sm_level << STOP_SHIFT) | sli) : -1;
   if (st == 3) {
     const int slot = atomicAdd(A.noverflow, 1);
-    if (slot < A.overcap) A.overflow[slot] = start;
+    if (slot < A.overcap) A.overflow[slot] = make_int2(start, tidx);
     else atomicExch(A.err, 3);
     return;
   }
@@ -880,21 +867,25 @@ __global__ void __launch_bounds__(256) k_requeue(long long ntotal, const int* __
   }
 }
 
-// rare long trajectories: path buffer in global memory (bigcap entries per walker)
+// The rare walks the persistent walkers hand over (a possible revisit, :484-488): repeated from the start with the
+// whole path in global memory (bigcap entries per walker) and the reference's path search.  They use the level's
+// certificates and log their early stops like every other walker of the level.
 template <bool FIX>
 __global__ void __launch_bounds__(64) k_walk_big(const __grid_constant__ BaderParams P, const __grid_constant__ WalkArgs A,
                                                  int count, int* __restrict__ scratch, int bigcap) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= count) return;
-  const int start = A.overflow[t];
+  const int start = A.overflow[t].x, tidx = A.overflow[t].y;
   WState w;
   walk_init(P, A.rho, w, start);
   const SafeMap nosafe{nullptr, 0, 0, 0, 0, 0, 0, 0, 0};
-  int out = 0, st;
-  do st = walk_step<false>(P, A.rho, A.h, nosafe, w, scratch + (size_t)t * bigcap, bigcap, out); while (st == 0);
+  const SafeMap& sm = (tidx >= 0 && A.stop) ? A.sm : nosafe;  // no stop log, no early stop
+  const int oldlab = FIX ? (A.label_g[start] & LMASK) : 0;
+  int out = 0, st, sli = -1;
+  do st = walk_step<false>(P, A.rho, A.h, sm, w, scratch + (size_t)t * bigcap, bigcap, out, sli); while (st == 0);
   if (A.nsteps) atomicAdd(A.nsteps, (unsigned long long)w.len);
   if (st == 3) { atomicExch(A.err, 2); return; }
-  walk_finish<FIX>(P, A, start, st, out, -1, -1, FIX ? (A.label_g[start] & LMASK) : 0);  // complete trajectory: nothing to log
+  walk_finish<FIX>(P, A, start, st, out, tidx, sli, oldlab);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1759,13 +1750,13 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
   C2G_CUDA(ctx, b_dlist.alloc(ctx, sizeof(int) * (size_t)dcap));
   C2G_CUDA(ctx, b_stop.alloc(ctx, sizeof(int) * (size_t)dcap));
   const long long overcap = std::max<long long>(1024, nnl);  // worst case: every walker of a launch is handed over
-  C2G_CUDA(ctx, b_over.alloc(ctx, sizeof(int) * (size_t)overcap));
+  C2G_CUDA(ctx, b_over.alloc(ctx, sizeof(int2) * (size_t)overcap));
   long long walked = 0, fixpts = 0, fixpasses = 0, noverflow_total = 0, nrequeued = 0;
 
   WalkArgs WA;
   memset(&WA, 0, sizeof(WA));
   WA.rho = g.d; WA.label_g = label_g; WA.h = h; WA.reached = reached; WA.S = S;
-  WA.cursor = cursor; WA.overflow = b_over.as<int>(); WA.noverflow = cnt + 2; WA.overcap = (int)std::min<long long>(overcap, 0x7fffffff);
+  WA.cursor = cursor; WA.overflow = b_over.as<int2>(); WA.noverflow = cnt + 2; WA.overcap = (int)std::min<long long>(overcap, 0x7fffffff);
   WA.err = cnt + 3; WA.nsteps = nsteps; WA.nnext = cnt + 7; WA.ninval = cnt + 11;
   // Refill policy of the persistent walkers.  The dense last level is issue-bound and wants its lanes refilled
   // early; the sparser coarse levels, the top lattice and the fix passes are latency-bound and run faster when a
@@ -1807,7 +1798,7 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
     WalkArgs W2 = WA;
     for (int off = 0; off < nov; off += chunk) {
       const int c = std::min(chunk, nov - off);
-      W2.overflow = b_over.as<int>() + off;
+      W2.overflow = b_over.as<int2>() + off;
       ctx->prof_begin("bader_walk_big");
       if (fix) k_walk_big<true><<<c2g_blocks_for(c, 64), 64, 0, st>>>(P, W2, c, b_scr.as<int>(), bigcap);
       else k_walk_big<false><<<c2g_blocks_for(c, 64), 64, 0, st>>>(P, W2, c, b_scr.as<int>(), bigcap);
