@@ -26,7 +26,7 @@ EXPORTS = [
     "c2g_grid_upload", "c2g_grid_upload_slab", "c2g_slab_range", "c2g_slab_bounds_query", "c2g_grid_alloc", "c2g_grid_download", "c2g_grid_download_slab", "c2g_grid_free", "c2g_grid_promolecular",
     "c2g_bader_assign", "c2g_basins_maxima", "c2g_basins_counts", "c2g_basins_set_map", "c2g_basins_labels",
     "c2g_basins_relabel", "c2g_basins_free", "c2g_basins_stats", "c2g_integrate", "c2g_yt_build",
-    "c2g_yt_weights", "c2g_nci_rdg", "c2g_nci_rdg_resident", "c2g_fft_derivative", "c2g_nci_rdg_fourier", "c2g_nci_range", "c2g_grid_upload_async", "c2g_basins_labels_async", "c2g_profile_enable", "c2g_profile_count",
+    "c2g_yt_weights", "c2g_nci_rdg", "c2g_nci_rdg_resident", "c2g_fft_derivative", "c2g_nci_rdg_fourier", "c2g_nci_range", "c2g_grid_upload_async", "c2g_basins_labels_async", "c2g_grid_parse_text", "c2g_profile_enable", "c2g_profile_count",
     "c2g_profile_get", "c2g_profile_reset", "c2g_launch_count", "c2g_flush_l2", "c2g_synchronize", "c2g_timer_start", "c2g_timer_stop",
 ]
 
@@ -227,6 +227,18 @@ class Context:
                                                _p(nstep, C.c_int), _p(_m33(c2x), C.c_double), _p(_m33(c2x), C.c_double),
                                                _p(crho, C.c_double), _p(cgrad, C.c_double)))
         return crho, cgrad
+
+    # ---- formatted-text grids (cube / CHGCAR numeric blocks) ----
+    def parse_text(self, text: bytes, n, order=0, divisor=1.0):
+        """Numbers of a cube (order=1: k fastest) or CHGCAR (order=0: i fastest) block -> new resident grid.
+        Returns (handle, bytes consumed, values converted on the host)."""
+        nn = np.array(n, dtype=np.int32)
+        h = C.c_int(-1)
+        used = C.c_size_t(0)
+        nhost = C.c_longlong(0)
+        self._chk(self.lib.c2g_grid_parse_text(self.h, C.c_char_p(text), C.c_size_t(len(text)), _p(nn, C.c_int), C.c_int(order),
+                                               C.c_double(divisor), C.byref(h), C.byref(used), C.byref(nhost)))
+        return h.value, used.value, nhost.value
 
     # ---- profiling ----
     def profile_enable(self, on=True):

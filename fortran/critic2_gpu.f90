@@ -134,6 +134,19 @@ module critic2_gpu
        type(c_ptr), value :: ctx
        integer(c_int) :: c2g_synchronize
      end function c2g_synchronize
+     ! formatted-text numeric block (read_cube / read_vasp) -> resident grid
+     function c2g_grid_parse_text(ctx,text,nbytes,n,order,divisor,handle,consumed,nhost) bind(c,name="c2g_grid_parse_text")
+       import :: c_int, c_ptr, c_double, c_size_t, c_long_long, c_char
+       type(c_ptr), value :: ctx
+       character(kind=c_char) :: text(*)
+       integer(c_size_t), value :: nbytes
+       integer(c_int) :: n(3), handle
+       integer(c_int), value :: order
+       real(c_double), value :: divisor
+       integer(c_size_t) :: consumed
+       integer(c_long_long) :: nhost
+       integer(c_int) :: c2g_grid_parse_text
+     end function c2g_grid_parse_text
      function c2g_fft_derivative(ctx,handle,iff,x2c,hout) bind(c,name="c2g_fft_derivative")
        import :: c_int, c_ptr, c_double
        type(c_ptr), value :: ctx
@@ -377,5 +390,24 @@ contains
        call check(c2g_grid_free(ctx,h(i)),"gpu_nci_rdg_fourier")
     end do
   end subroutine gpu_nci_rdg_fourier
+
+  !> The numeric block of a cube (order=1) or CHGCAR (order=0) file: text = the bytes after the header lines
+  !> (read with stream access), f = the grid, divided by `divisor` (det3(x2c) for read_vasp with vscal).
+  !> Replaces the list-directed READ of grid3mod@proc.f90:559 (read_cube) and :884 (read_vasp).
+  subroutine gpu_read_text_block(text,order,divisor,f,consumed)
+    character(kind=c_char), intent(in) :: text(:)
+    integer, intent(in) :: order
+    real*8, intent(in) :: divisor
+    real*8, intent(inout) :: f(:,:,:)
+    integer(c_size_t), intent(out) :: consumed
+    integer(c_int) :: n(3), h
+    integer(c_long_long) :: nhost
+
+    n = int(shape(f),c_int)
+    call check(c2g_grid_parse_text(ctx,text,int(size(text),c_size_t),n,int(order,c_int),divisor,h,consumed,nhost),&
+       "gpu_read_text_block")
+    call check(c2g_grid_download(ctx,h,f),"gpu_read_text_block")
+    call check(c2g_grid_free(ctx,h),"gpu_read_text_block")
+  end subroutine gpu_read_text_block
 
 end module critic2_gpu

@@ -183,6 +183,18 @@ int c2g_fft_derivative(c2g_context* ctx, int handle, int iff, const double x2c[9
 int c2g_nci_rdg_fourier(c2g_context* ctx, const int h[5], const double x0[3], const double xmat[9],
                         const int nstep[3], const double c2x[9], const double c2xl[9], double* crho, double* cgrad);
 
+/* ---- formatted-text grid readers: the numeric block of a cube file (read_cube,
+ * grid3mod@proc.f90:512-568) or of a CHGCAR/CHG/ELFCAR file (read_vasp, :842-913) ---- */
+#define C2G_TEXT_ORDER_I_FASTEST 0 /* (((f(i,j,k),i=1,n1),j=1,n2),k=1,n3): VASP */
+#define C2G_TEXT_ORDER_K_FASTEST 1 /* (((f(i,j,k),k=1,n3),j=1,n2),i=1,n1): Gaussian cube */
+/* text: the bytes that follow the header lines (host memory); the first n1*n2*n3 numbers are converted with
+ * correct rounding (the value a list-directed READ gives), stored as f(n1,n2,n3) in a new resident grid and
+ * divided by `divisor` (det3(x2c) for CHGCAR with vscal, :907-908; 1 otherwise).  consumed (optional) = offset of
+ * the first byte after the last value read (the next CHGCAR block starts there); nhost (optional) = number of
+ * values that needed the host's strtod (results within 2^-98 of a rounding boundary, subnormals, > 19 digits). */
+int c2g_grid_parse_text(c2g_context* ctx, const char* text, size_t nbytes, const int n[3], int order, double divisor,
+                        int* handle, size_t* consumed, long long* nhost);
+
 /* ---- profiling: CUDA-event timings of the kernels launched by the last API call ---- */
 int c2g_profile_enable(c2g_context* ctx, int on);
 int c2g_profile_count(c2g_context* ctx);

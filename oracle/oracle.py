@@ -306,3 +306,45 @@ def nci_rdg_fourier(f, x2c, nstep=None, x0=None, xmat=None, derived=None):
                               _p(nstep, C.c_int), _p(_m33(c2x), C.c_double), _p(_m33(c2x), C.c_double),
                               _p(crho, C.c_double), _p(cgrad, C.c_double))
     return crho, cgrad
+
+
+# ---------------------------------------------------------------------------
+# Formatted-text grids: the numeric block of read_cube (grid3mod@proc.f90:512-568) and read_vasp (:842-913).
+# A list-directed READ converts every field with correct rounding; Python's float() does the same (David Gay's
+# algorithm), so this restatement is exact.  Pure-Python loop: small cases only.
+# ---------------------------------------------------------------------------
+import re as _re
+
+_EXP_LETTER = _re.compile(r"[dDqQ]")
+_BARE_EXP = _re.compile(r"^([+-]?(?:\d+\.?\d*|\.\d+))([+-]\d+)$")
+
+
+def fortran_float(tok: str) -> float:
+    """One list-directed numeric field: E/D/Q exponent letters or a bare signed exponent ("1.5-03")."""
+    t = _EXP_LETTER.sub("E", tok)
+    m = _BARE_EXP.match(t)
+    if m:
+        t = m.group(1) + "E" + m.group(2)
+    return float(t)
+
+
+def parse_text_grid(text, n, order=0, divisor=1.0):
+    """order 0: (((f(i,j,k),i=1,n1),j=1,n2),k=1,n3) (read_vasp); order 1: (((f(i,j,k),k=1,n3),j=1,n2),i=1,n1)
+    (read_cube).  Returns f[n1,n2,n3] (Fortran order) = value / divisor, and the byte offset after the last field."""
+    if isinstance(text, bytes):
+        text = text.decode("ascii")
+    nv = int(n[0]) * int(n[1]) * int(n[2])
+    vals = np.empty(nv)
+    end = 0
+    it = _re.finditer(r"[^ \t\r\n,]+", text)
+    for q in range(nv):
+        m = next(it)
+        vals[q] = fortran_float(m.group(0))
+        end = m.end()
+    if divisor != 1.0:
+        vals = vals / divisor
+    if order == 0:
+        f = vals.reshape(tuple(int(x) for x in n), order="F")
+    else:
+        f = np.asfortranarray(vals.reshape(tuple(int(x) for x in n), order="C"))
+    return f, end

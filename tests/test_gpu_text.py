@@ -1,0 +1,114 @@
+"""GPU parity of the formatted-text grid reader (c2g_grid_parse_text) against the oracle: BIT-EXACT values (correct
+rounding, the result of a list-directed READ), both file orders, the volume division of CHGCAR files, the tokens that
+need the host (rounding-boundary cases, subnormals, long mantissas) and the error paths."""
+import numpy as np
+import pytest
+
+from critic2_b200 import capi
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint64)
+
+
+def check(ctx, text, n, order, divisor=1.0):
+    ref, end = orc.parse_text_grid(text, n, order, divisor)
+    h, used, nhost = ctx.parse_text(text.encode(), n, order, divisor)
+    out = ctx.download(h, n)
+    ctx.free(h)
+    assert np.array_equal(bits(out.ravel(order="F")), bits(ref.ravel(order="F"))), "values differ in some bit"
+    assert used == end
+    return nhost
+
+
+def test_cube_block_k_fastest(ctx):
+    rng = np.random.default_rng(5)
+    n = (17, 9, 23)
+    f = rng.standard_normal(n) * 10.0 ** rng.integers(-40, 4, n)   # vacuum-like tiny values included
+    rows = []
+    for i in range(n[0]):
+        for j in range(n[1]):
+            vals = ["%13.5E" % f[i, j, k] for k in range(n[2])]
+            rows += ["".join(vals[q:q + 6]) for q in range(0, n[2], 6)]   # cube files: 6 per line, new line per (i,j)
+    nhost = check(ctx, "\n".join(rows) + "\n", n, 1)
+    assert nhost == 0
+
+
+def test_chgcar_block_i_fastest_with_volume_and_trailer(ctx):
+    rng = np.random.default_rng(6)
+    n = (20, 18, 16)
+    f = np.abs(rng.standard_normal(n)) * 10.0 ** rng.integers(-3, 4, n)
+    flat = f.ravel(order="F")
+    body = "\n".join(" " + " ".join("%.11E" % v for v in flat[q:q + 5]) for q in range(0, flat.size, 5))
+    text = body + "\naugmentation occupancies   1  33\n  0.1234567E+00 0.7654321E-01\n"
+    nhost = check(ctx, text, n, 0, divisor=987.654321)
+    assert nhost == 0
+
+
+def test_number_forms_and_separators(ctx):
+    toks = ["1", "-2", "+3.", ".5", "-.25e1", "1.5D-03", "2.5d+02", "1.5-03", "7q2", "1E0", "0", "-0.0", "000123.4500E-2",
+            "9007199254740993", "123456789012345678", "1.0E22", "1.0E23", "4.9E-324", "2.2250738585072011E-308", "1.7976931348623157E308",
+            "0.1E-30", "3.14159265358979323846264338327950288", "1e-400", "8.5E-300", "6.02214076E23"]
+    n = (len(toks), 1, 1)
+    text = " , ".join(toks[:5]) + "\t" + "\r\n".join(toks[5:12]) + "\n" + "  ".join(toks[12:]) + "\n"
+    nhost = check(ctx, text, n, 0)
+    assert nhost >= 3   # the subnormal, the > 19 digit mantissa and the underflow go to the host
+
+
+def test_rounding_boundary_tokens(ctx):
+    """Decimal strings of exact midpoints between two doubles (and their neighbours): the double-double path must either
+    be right or hand them to the host."""
+    rng = np.random.default_rng(7)
+    toks = []
+    from fractions import Fraction
+    for _ in range(200):
+        x = float(rng.standard_normal() * 10.0 ** rng.integers(-20, 20))
+        y = np.nextafter(x, np.inf)
+        mid = (Fraction(x) + Fraction(y)) / 2
+        # 19 significant digits of the midpoint (truncated) and of a value just above it
+        e = int(np.floor(np.log10(abs(x)))) if x != 0 else 0
+        scaled = mid / Fraction(10) ** (e - 18)
+        m = int(scaled)
+        for d in (0, 1):
+            toks.append(f"{m + d}E{e - 18}")
+    n = (len(toks), 1, 1)
+    check(ctx, " ".join(toks) + "\n", n, 0)
+
+
+def test_large_block_throughput_and_parity(ctx):
+    rng = np.random.default_rng(8)
+    n = (96, 96, 96)
+    f = np.abs(rng.standard_normal(n)) * 10.0 ** rng.integers(-12, 3, n)
+    flat = f.ravel(order="F")
+    lines = [" ".join("%.11E" % v for v in flat[q:q + 5]) for q in range(0, flat.size, 5)]
+    text = "\n".join(lines) + "\n"
+    h, used, nhost = ctx.parse_text(text.encode(), n, 0, 1.0)
+    out = ctx.download(h, n)
+    ctx.free(h)
+    want = np.array(text.split(), dtype=np.float64).reshape(n, order="F")   # numpy's strtod: correctly rounded
+    assert np.array_equal(bits(out.ravel(order="F")), bits(want.ravel(order="F")))
+    assert nhost == 0 and used == len(text) - 1
+
+
+def test_error_paths(ctx):
+    with pytest.raises(capi.C2GError):
+        ctx.parse_text(b"1.0 2.0 abc 4.0\n", (4, 1, 1))          # not a number
+    with pytest.raises(capi.C2GError):
+        ctx.parse_text(b"1.0 2.0 3.0\n", (4, 1, 1))              # too few values
+    with pytest.raises(capi.C2GError):
+        ctx.parse_text(b"1.0 2.0\n", (2, 1, 1), order=7)         # bad order
+    with pytest.raises(capi.C2GError):
+        ctx.parse_text(b"1.0 2.0\n", (2, 1, 1), divisor=0.0)
+    h, used, _ = ctx.parse_text(b"1.0 2.0 junk\n", (2, 1, 1))   # text after the block is not looked at
+    assert np.array_equal(ctx.download(h, (2, 1, 1)).ravel(), [1.0, 2.0])
+    ctx.free(h)

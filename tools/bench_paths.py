@@ -166,7 +166,39 @@ def fft_big():
     ctx.free(h)
 
 
-for fn in (urea, nci, yt, fft_big):
+# ---- formatted-text reader: a CHGCAR-like E18.11 block ----
+def text_reader():
+    rep = 8 if quick else 512            # 64^3 values of text, repeated: 128^3 or 512^3 values
+    rng = np.random.default_rng(9)
+    base = np.abs(rng.standard_normal(64 ** 3)) * 10.0 ** rng.integers(-6, 4, 64 ** 3)
+    block = ("\n".join(" " + " ".join("%.11E" % v for v in base[q:q + 5]) for q in range(0, base.size, 5)) + "\n").encode()
+    text = block * rep
+    N = round((64 ** 3 * rep) ** (1 / 3))
+    n = (N, N, N)
+    t0 = time.perf_counter()
+    ref = np.array(block.split(), dtype=np.float64)      # numpy's strtod loop, one thread: the CPU side
+    t_cpu = time.perf_counter() - t0
+    state = {}
+
+    def run():
+        if "h" in state:
+            ctx.free(state["h"])
+        state["h"], state["used"], state["nhost"] = ctx.parse_text(text, n, 0, 1.0)
+        return state["h"]
+    ms, prof, h = timed(run, reps=2)
+    out = ctx.download(h, n).ravel(order="F")
+    same = bool(np.array_equal(out[:ref.size].view(np.uint64), ref.view(np.uint64)) and
+                np.array_equal(out[-ref.size:].view(np.uint64), ref.view(np.uint64)))
+    kern = sum(v for k, v in prof.items() if k != "text_h2d")
+    emit("formatted-text grid reader (CHGCAR-like E18.11 block), host text in, resident grid out", "SURVEY 8(f)-1", n, ms,
+         len(text) / float(np.prod(n)) + 8.0, prof,
+         {"bit_exact_vs_numpy_strtod": same, "values_converted_on_host": int(state["nhost"]), "text_bytes": len(text),
+          "kernels_only_ms": round(kern, 3), "kernels_only_GBps": round((2 * len(text) + 8.0 * np.prod(n)) / (kern * 1e-3) / 1e9, 1),
+          "cpu_numpy_values_per_s_1thread": ref.size / t_cpu, "gpu_values_per_s_incl_h2d": float(np.prod(n)) / (ms * 1e-3)})
+    ctx.free(h)
+
+
+for fn in (urea, nci, yt, fft_big, text_reader):
     try:
         fn()
     except Exception as e:  # keep going: one JSON line per failure
