@@ -79,7 +79,10 @@ __device__ __forceinline__ void load_group(Group<NP>& g, long long i, long long 
 }
 
 template <int NP>
-__global__ void __launch_bounds__(256) k_basin_reduce(long long nn, const int* __restrict__ label,
+#ifndef RED_MINB
+#define RED_MINB 4
+#endif
+__global__ void __launch_bounds__(256, RED_MINB) k_basin_reduce(long long nn, const int* __restrict__ label,
                                                       const double* __restrict__ f0, const double* __restrict__ f1,
                                                       const double* __restrict__ f2, const double* __restrict__ f3,
                                                       int nmax, int use_table, int mask, int vec, double* __restrict__ sums,
