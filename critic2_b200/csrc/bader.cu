@@ -1849,7 +1849,8 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
                            const SafeMap& sm, int sm_level, const char* name) -> int {
     if (count <= 0) return C2G_OK;
     if (doff + count > dcap) return ctx->fail(C2G_ERR_OVERFLOW, "walker list overflow");
-    const int batch = count < 64ll * wblocks * 8 ? 32 : 64;
+    int batch = count < 64ll * wblocks * 8 ? 32 : 64;
+    if (const char* e = getenv("C2G_BATCH")) batch = std::max(32, std::min(1024, atoi(e) / 32 * 32));
     const size_t maxitems = (size_t)nseg + (size_t)(count / batch) + 1;
     if (maxitems > itemcap) {
       itemcap = maxitems + maxitems / 4;

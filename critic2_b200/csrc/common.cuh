@@ -57,6 +57,7 @@ struct c2g_context {
   cudaStream_t copy_in = nullptr, copy_out = nullptr;
   cudaEvent_t ev_order = nullptr;
   std::vector<void*> deferred;  // device blocks still read by copy_out: released by c2g_synchronize
+  void* fft_cache = nullptr;    // cuFFT plans per grid shape (fft.cu)
   // device-memory cache (c2g_alloc / c2g_release below)
   std::multimap<size_t, void*> mem_free;           // size -> cached block
   std::unordered_map<void*, size_t> mem_live;      // block handed out -> its size
@@ -160,6 +161,7 @@ struct c2g_basins {
   long long n_ias = 0;
 };
 void c2g_yt_free_state(c2g_basins* res);
+void c2g_fft_free_plans(c2g_context* ctx);
 void c2g_slab_bounds(int n3, int nranks, int rank, int* zlo, int* zhi);
 
 // integrate.cu: one streaming pass of per-maximum sums (sums[p*nmax+m]) and counts

@@ -18,6 +18,7 @@
 #include <cufft.h>
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <cmath>
 
 namespace {
@@ -31,6 +32,10 @@ struct CufftApi {
   decltype(&cufftExecD2Z) ExecD2Z = nullptr;
   decltype(&cufftExecZ2D) ExecZ2D = nullptr;
   decltype(&cufftDestroy) Destroy = nullptr;
+  decltype(&cufftCreate) Create = nullptr;
+  decltype(&cufftSetAutoAllocation) SetAutoAllocation = nullptr;
+  decltype(&cufftMakePlan3d) MakePlan3d = nullptr;
+  decltype(&cufftSetWorkArea) SetWorkArea = nullptr;
 };
 CufftApi& cufft_api() {
   static CufftApi api;
@@ -50,10 +55,25 @@ CufftApi& cufft_api() {
   LOADSYM(ExecD2Z, "cufftExecD2Z")
   LOADSYM(ExecZ2D, "cufftExecZ2D")
   LOADSYM(Destroy, "cufftDestroy")
+  LOADSYM(Create, "cufftCreate")
+  LOADSYM(SetAutoAllocation, "cufftSetAutoAllocation")
+  LOADSYM(MakePlan3d, "cufftMakePlan3d")
+  LOADSYM(SetWorkArea, "cufftSetWorkArea")
 #undef LOADSYM
   api.ok = true;
   return api;
 }
+
+// Plans are kept per context and grid shape (creating a 1024^3 plan costs tens of ms); their work areas are NOT
+// owned by cuFFT: one block from the context's memory cache serves both directions and goes back after the call.
+struct FftPlans {
+  int n[3];
+  cufftHandle pf, pb;
+  size_t work;
+};
+struct FftPlanCache {
+  std::vector<FftPlans> plans;
+};
 
 struct FftParams {
   int n1, n2, n3, nh;  // nh = n1/2 + 1 stored coefficients along index 1
@@ -174,13 +194,34 @@ extern "C" int c2g_fft_derivative(c2g_context* ctx, int handle, int iff, const d
   C2G_CUDA(ctx, b_Y.alloc(ctx, sizeof(double2) * nspec));
   const bool grad = iff == C2G_FT_GRAD;
   if (grad) C2G_CUDA(ctx, b_y.alloc(ctx, sizeof(double) * (size_t)nn));
-  cufftHandle pf = 0, pb = 0;
   // cuFFT is row-major: the slowest dimension first, i.e. (n3, n2, n1) for a Fortran f(n1,n2,n3)
-  if (api.Plan3d(&pf, n3, n2, n1, CUFFT_D2Z) != CUFFT_SUCCESS) return ctx->fail(C2G_ERR_CUDA, "cufftPlan3d(D2Z) failed");
-  if (api.Plan3d(&pb, n3, n2, n1, CUFFT_Z2D) != CUFFT_SUCCESS) { api.Destroy(pf); return ctx->fail(C2G_ERR_CUDA, "cufftPlan3d(Z2D) failed"); }
-  api.SetStream(pf, st);
-  api.SetStream(pb, st);
-  struct PlanGuard { CufftApi& a; cufftHandle f, b; ~PlanGuard() { a.Destroy(f); a.Destroy(b); } } pg{api, pf, pb};
+  if (!ctx->fft_cache) ctx->fft_cache = new FftPlanCache();
+  FftPlanCache* cache = (FftPlanCache*)ctx->fft_cache;
+  FftPlans* pl = nullptr;
+  for (auto& q : cache->plans)
+    if (q.n[0] == n1 && q.n[1] == n2 && q.n[2] == n3) pl = &q;
+  if (!pl) {
+    FftPlans q;
+    q.n[0] = n1; q.n[1] = n2; q.n[2] = n3;
+    size_t wf = 0, wb = 0;
+    if (api.Create(&q.pf) != CUFFT_SUCCESS || api.Create(&q.pb) != CUFFT_SUCCESS) return ctx->fail(C2G_ERR_CUDA, "cufftCreate failed");
+    api.SetAutoAllocation(q.pf, 0);
+    api.SetAutoAllocation(q.pb, 0);
+    if (api.MakePlan3d(q.pf, n3, n2, n1, CUFFT_D2Z, &wf) != CUFFT_SUCCESS || api.MakePlan3d(q.pb, n3, n2, n1, CUFFT_Z2D, &wb) != CUFFT_SUCCESS) {
+      api.Destroy(q.pf); api.Destroy(q.pb);
+      return ctx->fail(C2G_ERR_CUDA, "cufftMakePlan3d failed for %d x %d x %d", n1, n2, n3);
+    }
+    q.work = std::max(wf, wb);
+    api.SetStream(q.pf, st);
+    api.SetStream(q.pb, st);
+    cache->plans.push_back(q);
+    pl = &cache->plans.back();
+  }
+  const cufftHandle pf = pl->pf, pb = pl->pb;
+  DevBuf b_work;
+  C2G_CUDA(ctx, b_work.alloc(ctx, std::max<size_t>(pl->work, 16)));
+  api.SetWorkArea(pf, b_work.p);
+  api.SetWorkArea(pb, b_work.p);
 
   const int blocks = ctx->nsm * 8;
   ctx->prof_begin("fft_forward_cufft");
@@ -209,4 +250,15 @@ extern "C" int c2g_fft_derivative(c2g_context* ctx, int handle, int iff, const d
   C2G_CUDA(ctx, cudaStreamSynchronize(st));
   ctx->prof_collect();
   return C2G_OK;
+}
+
+// called by c2g_finalize
+void c2g_fft_free_plans(c2g_context* ctx) {
+  if (!ctx->fft_cache) return;
+  FftPlanCache* cache = (FftPlanCache*)ctx->fft_cache;
+  CufftApi& api = cufft_api();
+  if (api.ok)
+    for (auto& q : cache->plans) { api.Destroy(q.pf); api.Destroy(q.pb); }
+  delete cache;
+  ctx->fft_cache = nullptr;
 }

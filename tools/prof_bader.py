@@ -18,6 +18,8 @@ at, z, al = S.jittered_lattice(side, 5)
 at = S.snap_to_grid(at, n)
 h = ctx.alloc(n)
 ctx.promolecular(h, x2c, at, z, al, nimg=1, rc=8.0)
+h2 = ctx.alloc(n)   # second INTEGRABLE field, like bench.py (P_f = 2: 20 B/pt in the reduction)
+ctx.promolecular(h2, x2c, at, z * 0.5, al * 1.3, nimg=1, rc=8.0)
 lat2car = x2c / np.array(n, dtype=float)[None, :]
 car2lat = np.linalg.inv(lat2car)
 lid = np.zeros((3, 3, 3))
@@ -31,7 +33,7 @@ for rep in range(reps):
     t = time.time()
     b = ctx.bader_assign(h, car2lat, lid, algo=algo)
     b.set_map(b.nmax, np.arange(1, b.nmax + 1, dtype=np.int32))
-    vol, ps = ctx.integrate(b, [h, h], abs(np.linalg.det(x2c)))
+    vol, ps = ctx.integrate(b, [h, h2], abs(np.linalg.det(x2c)))
     dt = time.time() - t
     prof = ctx.profile()
     print(f"N={N} algo={algo} rep={rep} nmax={b.nmax} wall={dt*1e3:.2f} ms  sum(pop)={ps[:,0].sum():.6f} stats={b.stats()[:6]}")
