@@ -1,0 +1,107 @@
+"""BASELINE.json configs at their full sizes, through the C ABI, checked with size-independent or sub-sampled
+properties (the oracle cannot run 512^3 in test time):
+  configs[2]  NCIPLOT on a 512^3 grid field: the GPU result on a coarse node-aligned sub-lattice against the oracle
+              evaluated on exactly those points (1e-12, north_star's RDG tolerance);
+  configs[3]  YT on a 512^3 many-basin density: the weights partition the cell (volumes sum to omega, populations to
+              the grid integral), every maximum is a basin, the result is reproducible;
+  8(a20)      FFT-derived fields at 512^3: Laplacian / gradient of a plane wave against the analytic result.
+(configs[1] and configs[4] are in test_gpu_bader.py: 256^3 FAST == EXACT referee, 1024^3 properties.)"""
+import numpy as np
+import pytest
+
+import systems as S
+from critic2_b200 import capi
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def test_nciplot_512_subsampled_against_oracle(ctx):
+    N = 512
+    n = (N, N, N)
+    x2c = S.cell_x2c(30.0, 30.0, 30.0)
+    at, z, al = S.random_atoms(24, 3, x2c, dmin=2.0)
+    h = ctx.alloc(n)
+    ctx.promolecular(h, x2c, S.snap_to_grid(at, n), z, al, nimg=0, rc=0.0)
+    hr, hg = ctx.nci_rdg_resident(h, x2c, n)
+    f = ctx.download(h, n)
+    cg = ctx.download(hg, (N, N, N))
+    cr = ctx.download(hr, (N, N, N))
+    st = 32
+    sub = (N // st,) * 3
+    xm = x2c / np.array(n, dtype=float)[None, :] * st
+    cro, cgo = orc.nci_rdg(f, x2c, nstep=sub, x0=np.zeros(3), xmat=xm)
+    sg, sr = cg[::st, ::st, ::st], cr[::st, ::st, ::st]
+    assert np.abs(sg - cgo).max() <= 1e-12 * np.abs(cgo).max()
+    assert np.abs(np.abs(sr) - np.abs(cro)).max() <= 1e-12 * np.abs(cro).max()
+    assert (np.sign(sr) == np.sign(cro)).mean() >= 0.999
+    # an off-node sub-lattice exercises the general interpolant on the same field
+    x0 = x2c @ np.array([0.3711, 0.1234, 0.9017])
+    nst = (9, 10, 11)
+    xm2 = x2c / np.array(nst, dtype=float)[None, :] * 0.37
+    cro2, cgo2 = orc.nci_rdg(f, x2c, nstep=nst, x0=x0, xmat=xm2)
+    cr2, cg2 = ctx.nci_rdg(h, x2c, n, nstep=nst, x0=x0, xmat=xm2)
+    assert np.abs(cg2 - cgo2).max() <= 1e-12 * np.abs(cgo2).max()
+    for hh in (h, hr, hg):
+        ctx.free(hh)
+
+
+def test_yt_512_partition_properties(ctx):
+    N, side = 512, 8
+    n = (N, N, N)
+    x2c = S.cell_x2c(5.0 * side, 5.0 * side, 5.0 * side)
+    at, z, al = S.jittered_lattice(side, 4)
+    at = S.snap_to_grid(at, n)
+    h = ctx.alloc(n)
+    ctx.promolecular(h, x2c, at, z, al, nimg=1, rc=8.0)
+    vec, area = S.wscell(x2c / np.array(n, dtype=float)[None, :])
+    om = S.omega(x2c)
+    res = []
+    for rep in range(2):
+        b = ctx.yt_build(h, vec, area)
+        assert b.nmax == side ** 3
+        b.set_map(b.nmax, np.arange(1, b.nmax + 1, dtype=np.int32))
+        vol, ps = ctx.integrate(b, [h], om)
+        assert vol.min() > 0.0
+        assert abs(vol.sum() - om) <= 1e-10 * om                       # the weights of a point sum to one
+        b.set_map(1, np.ones(b.nmax, dtype=np.int32))                   # all basins merged: the cell integral
+        vol1, ps1 = ctx.integrate(b, [h], om)
+        assert abs(ps[:, 0].sum() - ps1[0, 0]) <= 1e-10 * abs(ps1[0, 0])
+        # maxima come out in decreasing density (the reference's discovery order) and sit on the snapped atoms
+        pm = (b.maxima() - 1) / np.array(n, dtype=float)
+        d = np.abs(pm[:, None, :] - at[None, :, :])
+        assert np.minimum(d, 1.0 - d).max(axis=2).min(axis=1).max() <= 1.5 / N
+        res.append((vol.copy(), ps.copy(), b.stats()[0]))
+        b.free()
+    assert res[0][2] == res[1][2]                                       # same interatomic-surface set
+    assert np.abs(res[0][0] - res[1][0]).max() <= 1e-12 * om
+    assert np.abs(res[0][1] - res[1][1]).max() <= 1e-12 * np.abs(res[0][1]).max()
+    ctx.free(h)
+
+
+def test_fft_fields_512_plane_wave(ctx):
+    N = 512
+    n = (N, N, N)
+    x2c = np.array([[12.0, 1.0, 0.0], [0.0, 11.0, 0.8], [0.0, 0.0, 13.0]])
+    B = 2 * np.pi * np.linalg.inv(x2c).T
+    k = np.array([5, -3, 7])
+    G = B @ k
+    ax = [np.arange(N) / N] * 3
+    phase = 2 * np.pi * (k[0] * ax[0][:, None, None] + k[1] * ax[1][None, :, None] + k[2] * ax[2][None, None, :])
+    f = np.asfortranarray(np.cos(phase))
+    h = ctx.upload(f)
+    hl = ctx.fft_derivative(h, x2c, "lap")
+    lap = ctx.download(hl, n)
+    assert np.abs(lap + (G @ G) * f).max() <= 1e-11 * (G @ G)
+    ctx.free(hl)
+    hg = ctx.fft_derivative(h, x2c, "grad")
+    gm = ctx.download(hg, n)
+    assert np.abs(gm - np.linalg.norm(G) * np.abs(np.sin(phase))).max() <= 1e-11 * np.linalg.norm(G)
+    ctx.free(hg); ctx.free(h)
