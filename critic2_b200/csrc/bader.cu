@@ -713,7 +713,12 @@ __global__ void __launch_bounds__(256, 4) k_walk(const __grid_constant__ BaderPa
   WState w;
   Nb nb;
   unsigned long long steps = 0;
+  int pend_st = 0, pend_out = 0;  // a finished walk waits here until the next look at the queue: one pass for all lanes
   for (;;) {
+    if (pend_st) {
+      walk_finish<FIX>(P, A, start, pend_st, pend_out, A.list ? tidx : -1, sli, oldlab);
+      pend_st = 0;
+    }
     const unsigned idle = __ballot_sync(FULL, !active);
     if (idle == FULL || (!done && __popc(idle) >= A.refill_min)) {
       if (qpos >= qend && !done) {
@@ -757,7 +762,7 @@ __global__ void __launch_bounds__(256, 4) k_walk(const __grid_constant__ BaderPa
         const int st = walk_step_pipe<ORTHO>(P, A.rho, A.h, A.sm, w, nb, sl, sli, out);
         if (st) {
           if (STATS) steps += (unsigned)w.len;
-          walk_finish<FIX>(P, A, start, st, out, A.list ? tidx : -1, sli, oldlab);
+          pend_st = st; pend_out = out;
           active = false;
         }
       }
