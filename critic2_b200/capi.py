@@ -231,7 +231,7 @@ class Context:
     # ---- formatted-text grids (cube / CHGCAR numeric blocks) ----
     def parse_text(self, text: bytes, n, order=0, divisor=1.0):
         """Numbers of a cube (order=1: k fastest) or CHGCAR (order=0: i fastest) block -> new resident grid.
-        Returns (handle, bytes consumed, values converted on the host)."""
+        Returns (handle, bytes consumed, values that took the exact multi-word path on the device)."""
         nn = np.array(n, dtype=np.int32)
         h = C.c_int(-1)
         used = C.c_size_t(0)

@@ -13,9 +13,10 @@
 // Conversion is CORRECTLY ROUNDED (what a list-directed READ / strtod gives):
 //   * m < 2^53 and |e10| <= 22: one IEEE multiplication or division by an exact power of ten (Clinger's fast path);
 //   * otherwise m * 10^e10 in double-double arithmetic (106-bit powers of ten from pow10_dd.h, error < 2^-98); the
-//     high word is the correctly rounded result unless the low word is within that error of a rounding boundary --
-//     those tokens, subnormal results, overflows and mantissas longer than 19 digits are listed and converted by
-//     strtod on the host (never seen on cube / CHGCAR data; the tests force them).
+//     high word is the correctly rounded result unless the low word is within that error of a rounding boundary;
+//   * those tokens, subnormal results, overflows and mantissas longer than 19 digits take an exact multi-word
+//     integer comparison of the decimal value with the midpoints around a candidate (decimal_exact), also on the
+//     device (never needed on cube / CHGCAR data; the tests force it).  Nothing is converted on the host.
 // Separators: blank, tab, newline, carriage return, comma.  Exponent letters E, D, Q (either case) or a bare sign
 // ("1.5-03").  The r*c repeat form of list-directed input is not supported (neither format writes it).
 #include "common.cuh"
@@ -99,8 +100,7 @@ struct ParseArgs {
   int n1, n2, n3, order;     // order 0: i fastest in the file (CHGCAR), 1: k fastest (cube)
   double divisor;            // every value is divided by this (1 = no scaling)
   double* out;
-  // tokens to be converted on the host: (token index, byte offset)
-  long long* fb_tok; unsigned long long* fb_pos; int* nfb; int fbcap;
+  int* nfb;                  // tokens that took the exact big-integer path
   int* err;                  // 0 ok, 1 bad character, 2 token too long
   unsigned long long* errpos;
   unsigned long long* consumed;  // byte offset just past the last value read
@@ -148,6 +148,142 @@ __device__ __forceinline__ bool dec_to_double(unsigned long long m, int e10, dou
   if (pow2 && fabs(arl - 0.25 * ulp) <= tol) return false;
   v = rh;
   return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Exact conversion for the tokens the fast paths cannot decide (result within 2^-98 of a rounding boundary,
+// subnormal or huge results, mantissas longer than 19 digits): the decimal value D = mant * 10^q, with ALL digits of
+// the token in a multi-word integer, is compared exactly with the midpoints around a candidate double, and the
+// candidate is moved until D lies between them; ties go to the even mantissa (IEEE round-to-nearest-even, what
+// strtod and a list-directed READ do).  Rare (never on cube / CHGCAR data), so it is written for clarity, not speed.
+// ------------------------------------------------------------------------------------------------
+constexpr int BIGW = 56;  // 1792 bits: 60 digits (200 bits) * 5^400 (929 bits) and shifts of up to ~1100 bits never meet
+struct Big {
+  unsigned w[BIGW];
+  int n;  // words in use (>= 1)
+};
+__device__ void big_set(Big& b, unsigned long long v) {
+  b.w[0] = (unsigned)v; b.w[1] = (unsigned)(v >> 32);
+  b.n = b.w[1] ? 2 : 1;
+}
+__device__ void big_mul_add(Big& b, unsigned k, unsigned add) {  // b = b * k + add
+  unsigned long long carry = add;
+  for (int i = 0; i < b.n; i++) {
+    const unsigned long long t = (unsigned long long)b.w[i] * k + carry;
+    b.w[i] = (unsigned)t;
+    carry = t >> 32;
+  }
+  if (carry && b.n < BIGW) b.w[b.n++] = (unsigned)carry;
+}
+__device__ void big_mul_pow5(Big& b, int e) {
+  for (; e >= 13; e -= 13) big_mul_add(b, 1220703125u, 0);  // 5^13
+  for (; e > 0; e--) big_mul_add(b, 5u, 0);
+}
+__device__ void big_shl(Big& b, int s) {
+  const int ws = s >> 5, bs = s & 31;
+  if (b.n == 1 && b.w[0] == 0) return;
+  int nn = b.n + ws + 1;
+  if (nn > BIGW) nn = BIGW;
+  for (int i = nn - 1; i >= 0; i--) {
+    const int src = i - ws;
+    unsigned lo = (src >= 0 && src < b.n) ? b.w[src] : 0u;
+    unsigned below = (src - 1 >= 0 && src - 1 < b.n) ? b.w[src - 1] : 0u;
+    b.w[i] = bs ? ((lo << bs) | (below >> (32 - bs))) : lo;
+  }
+  b.n = nn;
+  while (b.n > 1 && b.w[b.n - 1] == 0) b.n--;
+}
+__device__ int big_cmp(const Big& a, const Big& b) {
+  if (a.n != b.n) return a.n > b.n ? 1 : -1;
+  for (int i = a.n - 1; i >= 0; i--)
+    if (a.w[i] != b.w[i]) return a.w[i] > b.w[i] ? 1 : -1;
+  return 0;
+}
+// sign of  mant * 10^q  -  t * 2^e2
+__device__ int cmp_decimal_binary(const Big& mant, int q, unsigned long long t, int e2) {
+  Big L = mant, R;
+  big_set(R, t);
+  if (q > 0) big_mul_pow5(L, q);
+  if (q < 0) big_mul_pow5(R, -q);
+  const int d = q - e2;  // net power of two on the left
+  if (d >= 0) big_shl(L, d); else big_shl(R, -d);
+  return big_cmp(L, R);
+}
+__device__ __forceinline__ void dbl_decompose(double c, unsigned long long& M, int& E) {
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(c);
+  const int ex = (int)((bits >> 52) & 0x7ff);
+  const unsigned long long fr = bits & ((1ull << 52) - 1);
+  if (ex == 0) { M = fr; E = -1074; } else { M = fr | (1ull << 52); E = ex - 1075; }
+}
+// tok: the token (sign already consumed by the caller or not -- handled here), terminated by a separator
+__device__ __noinline__ double decimal_exact(const unsigned char* tok) {
+  int p = 0;
+  if (tok[p] == '+' || tok[p] == '-') p++;
+  Big mant;
+  big_set(mant, 0);
+  int nd = 0, frac = 0;
+  bool dot = false;
+  unsigned long long m19 = 0;
+  int n19 = 0;
+  for (;; p++) {
+    const unsigned char ch = tok[p];
+    if (ch >= '0' && ch <= '9') {
+      if (nd > 0 || ch != '0') {
+        big_mul_add(mant, 10u, (unsigned)(ch - '0'));
+        nd++;
+        if (n19 < 19) { m19 = m19 * 10ull + (unsigned)(ch - '0'); n19++; }
+      }
+      if (dot) frac++;
+    } else if (ch == '.' && !dot) dot = true;
+    else break;
+  }
+  int ex = 0;
+  {
+    unsigned char ch = tok[p];
+    if (ch == 'e' || ch == 'E' || ch == 'd' || ch == 'D' || ch == 'q' || ch == 'Q' || ch == '+' || ch == '-') {
+      if (!(ch == '+' || ch == '-')) ch = tok[++p];
+      bool eneg = false;
+      if (ch == '+' || ch == '-') { eneg = ch == '-'; ch = tok[++p]; }
+      while (ch >= '0' && ch <= '9') { if (ex < 100000) ex = ex * 10 + (ch - '0'); ch = tok[++p]; }
+      if (eneg) ex = -ex;
+    }
+  }
+  if (nd == 0) return 0.0;
+  const int q = ex - frac;
+  const int dexp = q + nd - 1;  // decimal exponent of the leading digit
+  if (dexp > 309) return __longlong_as_double(0x7ff0000000000000ll);
+  if (dexp < -326) return 0.0;
+  // candidate from plain doubles (a few ulp off at worst; the loop below repairs it)
+  double c = (double)m19;
+  int q19 = q + (nd - n19);
+  while (q19 > 0) { const int s = q19 > 300 ? 300 : q19; c *= c2g_pow10_hi[s]; q19 -= s; }
+  while (q19 < 0) { const int s = -q19 > 300 ? 300 : -q19; c /= c2g_pow10_hi[s]; q19 += s; }
+  const double dmax = __longlong_as_double(0x7fefffffffffffffll);
+  if (!(c <= dmax)) c = dmax;
+  for (int it = 0; it < 128; it++) {
+    unsigned long long M;
+    int E;
+    dbl_decompose(c, M, E);
+    // D against the midpoint above c: (2M+1) * 2^(E-1)
+    const int up = cmp_decimal_binary(mant, q, 2 * M + 1, E - 1);
+    if (up > 0 || (up == 0 && (M & 1))) {
+      if (c == dmax) return __longlong_as_double(0x7ff0000000000000ll);
+      c = __longlong_as_double(__double_as_longlong(c) + 1);
+      if (up == 0) return c;  // tie resolved to the even neighbour
+      continue;
+    }
+    if (up == 0) return c;
+    if (c == 0.0) return c;
+    const double pr = __longlong_as_double(__double_as_longlong(c) - 1);
+    unsigned long long Mp;
+    int Ep;
+    dbl_decompose(pr, Mp, Ep);
+    const int dn = cmp_decimal_binary(mant, q, 2 * Mp + 1, Ep - 1);
+    if (dn < 0) { c = pr; continue; }
+    if (dn == 0) return (Mp & 1) ? c : pr;
+    return c;
+  }
+  return c;
 }
 
 __global__ void __launch_bounds__(TTHREADS) k_tok_parse(const __grid_constant__ ParseArgs A) {
@@ -257,27 +393,21 @@ __global__ void __launch_bounds__(TTHREADS) k_tok_parse(const __grid_constant__ 
       const long long j = r % A.n2, i = r / A.n2;
       idx = (size_t)i + (size_t)A.n1 * ((size_t)j + (size_t)A.n2 * (size_t)k);
     }
-    if (ok) {
-      if (neg) v = -v;
-      if (A.divisor != 1.0) v = v / A.divisor;
-      A.out[idx] = v;
-    } else {
-      const int slot = atomicAdd(A.nfb, 1);
-      if (slot < A.fbcap) { A.fb_tok[slot] = (long long)idx; A.fb_pos[slot] = (unsigned long long)(cbase + pstart); }
+    if (!ok) {  // exact big-integer path (counted)
+      v = decimal_exact(s_b + pstart);
+      atomicAdd(A.nfb, 1);
     }
+    if (neg) v = -v;
+    if (A.divisor != 1.0) v = v / A.divisor;
+    A.out[idx] = v;
   }
-}
-
-__global__ void k_patch(int n, const long long* __restrict__ idx, const double* __restrict__ val, double* __restrict__ out) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < n) out[idx[t]] = val[t];
 }
 
 }  // namespace
 
 // Parses the first n1*n2*n3 numbers of `text` (host memory, nbytes bytes) into a new resident grid.
 extern "C" int c2g_grid_parse_text(c2g_context* ctx, const char* text, size_t nbytes, const int n[3], int order, double divisor,
-                                   int* handle, size_t* consumed, long long* nhost) {
+                                   int* handle, size_t* consumed, long long* nslow) {
   if (!ctx) return C2G_ERR_ARG;
   if (!text || !n || !handle) return ctx->fail(C2G_ERR_ARG, "c2g_grid_parse_text: null argument");
   if (order != C2G_TEXT_ORDER_I_FASTEST && order != C2G_TEXT_ORDER_K_FASTEST) return ctx->fail(C2G_ERR_ARG, "c2g_grid_parse_text: bad order %d", order);
@@ -291,7 +421,7 @@ extern "C" int c2g_grid_parse_text(c2g_context* ctx, const char* text, size_t nb
   if (nchunk == 0) return ctx->fail(C2G_ERR_ARG, "c2g_grid_parse_text: empty text");
   if (nchunk > 0x7fffffffull) return ctx->fail(C2G_ERR_ARG, "c2g_grid_parse_text: text too large");
   const size_t padded = nchunk * TCHUNK + TTAIL + 16;
-  DevBuf b_text, b_cnt, b_off, b_ctl, b_fbt, b_fbp;
+  DevBuf b_text, b_cnt, b_off, b_ctl;
   C2G_CUDA(ctx, b_text.alloc(ctx, padded));
   C2G_CUDA(ctx, cudaMemsetAsync((char*)b_text.p + nbytes, ' ', padded - nbytes, st));
   ctx->prof_begin("text_h2d");
@@ -300,9 +430,6 @@ extern "C" int c2g_grid_parse_text(c2g_context* ctx, const char* text, size_t nb
   C2G_CUDA(ctx, b_cnt.alloc(ctx, sizeof(int) * nchunk));
   C2G_CUDA(ctx, b_off.alloc(ctx, sizeof(long long) * nchunk));
   C2G_CUDA(ctx, b_ctl.alloc(ctx, 64));
-  const int fbcap = 1 << 20;
-  C2G_CUDA(ctx, b_fbt.alloc(ctx, sizeof(long long) * fbcap));
-  C2G_CUDA(ctx, b_fbp.alloc(ctx, sizeof(unsigned long long) * fbcap));
   // ctl (8-byte slots): [0] total tokens, [1] errpos, [2] consumed, [3] err (int) | nfb (int)
   unsigned long long hctl[8] = {0, ~0ull, 0, 0, 0, 0, 0, 0};
   C2G_CUDA(ctx, cudaMemcpyAsync(b_ctl.p, hctl, 64, cudaMemcpyHostToDevice, st));
@@ -315,7 +442,6 @@ extern "C" int c2g_grid_parse_text(c2g_context* ctx, const char* text, size_t nb
   ParseArgs A;
   A.text = (const unsigned char*)b_text.p; A.nbytes = nbytes; A.off = b_off.as<long long>(); A.nvalues = nvalues;
   A.n1 = n[0]; A.n2 = n[1]; A.n3 = n[2]; A.order = order; A.divisor = divisor; A.out = ctx->grids[*handle].d;
-  A.fb_tok = b_fbt.as<long long>(); A.fb_pos = b_fbp.as<unsigned long long>(); A.fbcap = fbcap;
   A.errpos = ctl + 1; A.consumed = ctl + 2; A.err = (int*)(ctl + 3); A.nfb = (int*)(ctl + 3) + 1;
   ctx->prof_begin("text_parse");
   k_tok_parse<<<(unsigned)nchunk, TTHREADS, 0, st>>>(A);
@@ -328,38 +454,8 @@ extern "C" int c2g_grid_parse_text(c2g_context* ctx, const char* text, size_t nb
   if (err == 1) return ctx->fail(C2G_ERR_ARG, "c2g_grid_parse_text: not a number at byte %llu", hctl[1]);
   if (err == 2) return ctx->fail(C2G_ERR_ARG, "c2g_grid_parse_text: token longer than %d bytes at byte %llu", TTAIL - 2, hctl[1]);
   if (ntok < nvalues) return ctx->fail(C2G_ERR_ARG, "c2g_grid_parse_text: %lld values expected, %lld found", nvalues, ntok);
-  if (nfb > fbcap) return ctx->fail(C2G_ERR_OVERFLOW, "c2g_grid_parse_text: %d values need host conversion (limit %d)", nfb, fbcap);
-  if (nfb > 0) {  // rare tokens: exact conversion with strtod on the host
-    std::vector<long long> ftok(nfb);
-    std::vector<unsigned long long> fpos(nfb);
-    C2G_CUDA(ctx, cudaMemcpyAsync(ftok.data(), b_fbt.p, sizeof(long long) * nfb, cudaMemcpyDeviceToHost, st));
-    C2G_CUDA(ctx, cudaMemcpyAsync(fpos.data(), b_fbp.p, sizeof(unsigned long long) * nfb, cudaMemcpyDeviceToHost, st));
-    C2G_CUDA(ctx, cudaStreamSynchronize(st));
-    std::vector<double> fval(nfb);
-    for (int q = 0; q < nfb; q++) {
-      std::string tk;
-      for (size_t p = fpos[q]; p < nbytes && tk.size() < 400; p++) {
-        char c = text[p];
-        if (c == ' ' || c == '\n' || c == '\t' || c == '\r' || c == ',') break;
-        if (c == 'd' || c == 'D' || c == 'q' || c == 'Q') c = 'E';
-        tk.push_back(c);
-      }
-      // a bare-sign exponent ("1.5-03"): insert the E
-      for (size_t p = 1; p < tk.size(); p++)
-        if ((tk[p] == '+' || tk[p] == '-') && tk[p - 1] != 'E' && tk[p - 1] != 'e') { tk.insert(p, "E"); break; }
-      double v = strtod(tk.c_str(), nullptr);
-      if (divisor != 1.0) v = v / divisor;
-      fval[q] = v;
-    }
-    DevBuf b_val;
-    C2G_CUDA(ctx, b_val.alloc(ctx, sizeof(double) * nfb));
-    C2G_CUDA(ctx, cudaMemcpyAsync(b_val.p, fval.data(), sizeof(double) * nfb, cudaMemcpyHostToDevice, st));
-    k_patch<<<c2g_blocks_for(nfb, 256), 256, 0, st>>>(nfb, b_fbt.as<long long>(), b_val.as<double>(), ctx->grids[*handle].d);
-    C2G_KERNEL_CHECK(ctx);
-    C2G_CUDA(ctx, cudaStreamSynchronize(st));
-  }
   if (consumed) *consumed = (size_t)hctl[2];
-  if (nhost) *nhost = nfb;
+  if (nslow) *nslow = nfb;
   ctx->prof_collect();
   hg.ok = true;
   return C2G_OK;

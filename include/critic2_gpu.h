@@ -190,10 +190,11 @@ int c2g_nci_rdg_fourier(c2g_context* ctx, const int h[5], const double x0[3], co
 /* text: the bytes that follow the header lines (host memory); the first n1*n2*n3 numbers are converted with
  * correct rounding (the value a list-directed READ gives), stored as f(n1,n2,n3) in a new resident grid and
  * divided by `divisor` (det3(x2c) for CHGCAR with vscal, :907-908; 1 otherwise).  consumed (optional) = offset of
- * the first byte after the last value read (the next CHGCAR block starts there); nhost (optional) = number of
- * values that needed the host's strtod (results within 2^-98 of a rounding boundary, subnormals, > 19 digits). */
+ * the first byte after the last value read (the next CHGCAR block starts there); nslow (optional) = number of
+ * values that took the exact multi-word path on the device (results within 2^-98 of a rounding boundary, subnormals,
+ * more than 19 digits); nothing is converted on the host. */
 int c2g_grid_parse_text(c2g_context* ctx, const char* text, size_t nbytes, const int n[3], int order, double divisor,
-                        int* handle, size_t* consumed, long long* nhost);
+                        int* handle, size_t* consumed, long long* nslow);
 
 /* ---- profiling: CUDA-event timings of the kernels launched by the last API call ---- */
 int c2g_profile_enable(c2g_context* ctx, int on);

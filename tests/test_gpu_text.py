@@ -1,6 +1,6 @@
 """GPU parity of the formatted-text grid reader (c2g_grid_parse_text) against the oracle: BIT-EXACT values (correct
 rounding, the result of a list-directed READ), both file orders, the volume division of CHGCAR files, the tokens that
-need the host (rounding-boundary cases, subnormals, long mantissas) and the error paths."""
+take the exact multi-word path on the device (rounding-boundary cases, subnormals, long mantissas; nothing is converted on the host) and the error paths."""
 import numpy as np
 import pytest
 
@@ -62,12 +62,12 @@ def test_number_forms_and_separators(ctx):
     n = (len(toks), 1, 1)
     text = " , ".join(toks[:5]) + "\t" + "\r\n".join(toks[5:12]) + "\n" + "  ".join(toks[12:]) + "\n"
     nhost = check(ctx, text, n, 0)
-    assert nhost >= 3   # the subnormal, the > 19 digit mantissa and the underflow go to the host
+    assert nhost >= 3   # the subnormal, the > 19 digit mantissa and the underflow take the exact multi-word path
 
 
 def test_rounding_boundary_tokens(ctx):
     """Decimal strings of exact midpoints between two doubles (and their neighbours): the double-double path must either
-    be right or hand them to the host."""
+    be right or hand them to the exact multi-word comparison."""
     rng = np.random.default_rng(7)
     toks = []
     from fractions import Fraction
@@ -81,8 +81,23 @@ def test_rounding_boundary_tokens(ctx):
         m = int(scaled)
         for d in (0, 1):
             toks.append(f"{m + d}E{e - 18}")
+    # exact midpoints with all their digits (ties: round to even) and 40-digit strings just around them
+    for _ in range(100):
+        x = float(abs(rng.standard_normal()) * 10.0 ** rng.integers(-15, 15))
+        y = np.nextafter(x, np.inf)
+        mid = (Fraction(x) + Fraction(y)) / 2
+        num, den = mid.numerator, mid.denominator        # den is a power of two: the decimal expansion is finite
+        k = den.bit_length() - 1
+        digits = str(num * 5 ** k)                         # mid = digits * 10^-k
+        if len(digits) <= 58:
+            toks.append(f"{digits}E-{k}")
+            toks.append(f"{digits}1E-{k + 1}")
+            toks.append(f"{int(digits) - 1}9E-{k + 1}")
+    toks += ["2.4703282292062327208e-324", "2.4703282292062327209e-324", "4.9406564584124654e-324", "1.7976931348623158079e308",
+             "1.7976931348623158080e308", "1e-330", "1e400", "0.000000000000000000000000000000000000001e-300"]
     n = (len(toks), 1, 1)
-    check(ctx, " ".join(toks) + "\n", n, 0)
+    nslow = check(ctx, " ".join(toks) + "\n", n, 0)
+    assert nslow > 100
 
 
 def test_large_block_throughput_and_parity(ctx):

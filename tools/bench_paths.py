@@ -192,7 +192,7 @@ def text_reader():
     kern = sum(v for k, v in prof.items() if k != "text_h2d")
     emit("formatted-text grid reader (CHGCAR-like E18.11 block), host text in, resident grid out", "SURVEY 8(f)-1", n, ms,
          len(text) / float(np.prod(n)) + 8.0, prof,
-         {"bit_exact_vs_numpy_strtod": same, "values_converted_on_host": int(state["nhost"]), "text_bytes": len(text),
+         {"bit_exact_vs_numpy_strtod": same, "values_on_exact_slow_path": int(state["nhost"]), "text_bytes": len(text),
           "kernels_only_ms": round(kern, 3), "kernels_only_GBps": round((2 * len(text) + 8.0 * np.prod(n)) / (kern * 1e-3) / 1e9, 1),
           "cpu_numpy_values_per_s_1thread": ref.size / t_cpu, "gpu_values_per_s_incl_h2d": float(np.prod(n)) / (ms * 1e-3)})
     ctx.free(h)
