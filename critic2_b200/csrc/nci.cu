@@ -35,6 +35,7 @@ struct NciParams {
   double c2x[9], x2c[9], c2xl[9];
   int nnuc;
   double cst;  // 2 (3 pi^2)^(1/3), nci@proc.f90:91, evaluated once on the host
+  int ortho;   // c2xl is diagonal: the skipped products of the Cartesian transforms are exact zeros
 };
 
 constexpr int BI = 32, BJ = 2, BK = 4;  // lanes run along i (the contiguous index of rho): coalesced stencil loads; 4 consecutive k = one 32 B output sector
@@ -215,34 +216,43 @@ __global__ void __launch_bounds__(256, NCI_MINB) k_nci_rdg(const __grid_constant
     H[0][2] = H[2][0] = h[4] * dn[0] * dn[2];
     H[1][2] = H[2][1] = h[5] * dn[1] * dn[2];
     // to Cartesian (grid3mod@proc.f90:1747-1750): yp = matmul(transpose(c2xl),yp); ypp = c2xl^T ypp c2xl
-    double gc[3];
+    double gc[3], HC[3][3];
+    if (P.ortho) {  // orthogonal cell: same values, a fraction of the fp64 work (this kernel is FP64-pipe bound)
 #pragma unroll
-    for (int a = 0; a < 3; a++) {
-      double s = __dmul_rn(P.c2xl[0 + 3 * a], yp[0]);
-      s = __dadd_rn(s, __dmul_rn(P.c2xl[1 + 3 * a], yp[1]));
-      s = __dadd_rn(s, __dmul_rn(P.c2xl[2 + 3 * a], yp[2]));
-      gc[a] = s;
+      for (int a = 0; a < 3; a++) {
+        gc[a] = __dmul_rn(P.c2xl[4 * a], yp[a]);
+#pragma unroll
+        for (int b = 0; b < 3; b++) HC[a][b] = (P.c2xl[4 * a] * H[a][b]) * P.c2xl[4 * b];
+      }
+    } else {
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        double s = __dmul_rn(P.c2xl[0 + 3 * a], yp[0]);
+        s = __dadd_rn(s, __dmul_rn(P.c2xl[1 + 3 * a], yp[1]));
+        s = __dadd_rn(s, __dmul_rn(P.c2xl[2 + 3 * a], yp[2]));
+        gc[a] = s;
+      }
+      double T[3][3];
+#pragma unroll
+      for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++) {
+          // (only sign(lambda_2) is taken from the Cartesian Hessian: fused multiply-adds are as good as any order)
+          double s = P.c2xl[3 * a] * H[0][b];
+          s = fma(P.c2xl[1 + 3 * a], H[1][b], s);
+          s = fma(P.c2xl[2 + 3 * a], H[2][b], s);
+          T[a][b] = s;
+        }
+#pragma unroll
+      for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++) {
+          double s = T[a][0] * P.c2xl[3 * b];
+          s = fma(T[a][1], P.c2xl[1 + 3 * b], s);
+          s = fma(T[a][2], P.c2xl[2 + 3 * b], s);
+          HC[a][b] = s;
+        }
     }
-    double T[3][3], HC[3][3];
-#pragma unroll
-    for (int a = 0; a < 3; a++)
-#pragma unroll
-      for (int b = 0; b < 3; b++) {
-        // (only sign(lambda_2) is taken from the Cartesian Hessian: fused multiply-adds are as good as any order)
-        double s = P.c2xl[3 * a] * H[0][b];
-        s = fma(P.c2xl[1 + 3 * a], H[1][b], s);
-        s = fma(P.c2xl[2 + 3 * a], H[2][b], s);
-        T[a][b] = s;
-      }
-#pragma unroll
-    for (int a = 0; a < 3; a++)
-#pragma unroll
-      for (int b = 0; b < 3; b++) {
-        double s = T[a][0] * P.c2xl[3 * b];
-        s = fma(T[a][1], P.c2xl[1 + 3 * b], s);
-        s = fma(T[a][2], P.c2xl[2 + 3 * b], s);
-        HC[a][b] = s;
-      }
     // nucleus rule (fieldmod@proc.f90:1148-1155): zero gradient within 1e-5 bohr of an atom
     if (P.nnuc > 0) {
       double wc[3];
@@ -450,6 +460,7 @@ int nci_launch(c2g_context* ctx, int handle, const double x0[3], const double xm
   memcpy(P.x2c, x2c, sizeof(P.x2c));
   memcpy(P.c2xl, c2xl, sizeof(P.c2xl));
   P.nnuc = nnuc;
+  P.ortho = (c2xl[1] == 0.0 && c2xl[2] == 0.0 && c2xl[3] == 0.0 && c2xl[5] == 0.0 && c2xl[6] == 0.0 && c2xl[7] == 0.0) ? 1 : 0;
   P.cst = 2.0 * std::pow(3.0 * 3.14159265358979323846264338328 * 3.14159265358979323846264338328, 1.0 / 3.0);
   double* d_nuc = nullptr;
   if (nnuc > 0) {
@@ -553,6 +564,7 @@ extern "C" int c2g_nci_rdg_fourier(c2g_context* ctx, const int h[5], const doubl
   memcpy(P.x2c, c2x, sizeof(P.x2c));  // unused in this mode
   memcpy(P.c2xl, c2xl, sizeof(P.c2xl));
   P.nnuc = 0;
+  P.ortho = 0;
   P.cst = 2.0 * std::pow(3.0 * 3.14159265358979323846264338328 * 3.14159265358979323846264338328, 1.0 / 3.0);
   if (P.ns1 < 1) return C2G_OK;
   const size_t nout = (size_t)P.ns1 * nstep[1] * nstep[2];
