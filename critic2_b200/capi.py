@@ -26,7 +26,7 @@ EXPORTS = [
     "c2g_grid_upload", "c2g_grid_upload_slab", "c2g_slab_range", "c2g_slab_bounds_query", "c2g_grid_alloc", "c2g_grid_download", "c2g_grid_download_slab", "c2g_grid_free", "c2g_grid_promolecular",
     "c2g_bader_assign", "c2g_basins_maxima", "c2g_basins_counts", "c2g_basins_set_map", "c2g_basins_labels",
     "c2g_basins_relabel", "c2g_basins_free", "c2g_basins_stats", "c2g_integrate", "c2g_yt_build",
-    "c2g_yt_weights", "c2g_nci_rdg", "c2g_nci_rdg_resident", "c2g_fft_derivative", "c2g_nci_rdg_fourier", "c2g_nci_range", "c2g_grid_upload_async", "c2g_basins_labels_async", "c2g_grid_parse_text", "c2g_profile_enable", "c2g_profile_count",
+    "c2g_yt_weights", "c2g_nci_rdg", "c2g_nci_rdg_resident", "c2g_fft_derivative", "c2g_nci_rdg_fourier", "c2g_nci_range", "c2g_grid_upload_async", "c2g_basins_labels_async", "c2g_grid_parse_text", "c2g_grid_format_text", "c2g_profile_enable", "c2g_profile_count",
     "c2g_profile_get", "c2g_profile_reset", "c2g_launch_count", "c2g_flush_l2", "c2g_synchronize", "c2g_timer_start", "c2g_timer_stop",
 ]
 
@@ -239,6 +239,27 @@ class Context:
         self._chk(self.lib.c2g_grid_parse_text(self.h, C.c_char_p(text), C.c_size_t(len(text)), _p(nn, C.c_int), C.c_int(order),
                                                C.c_double(divisor), C.byref(h), C.byref(used), C.byref(nhost)))
         return h.value, used.value, nhost.value
+
+    def format_text_size(self, h, layout, width, digits, scale):
+        nb = C.c_size_t(0)
+        self._chk(self.lib.c2g_grid_format_text(self.h, C.c_int(h), C.c_int(layout), None, C.c_int(width), C.c_int(digits),
+                                                C.c_int(scale), None, C.c_size_t(0), C.byref(nb)))
+        return nb.value
+
+    def format_text_into(self, h, layout, width, digits, scale, ptr, cap, ishift=None):
+        """Step 2 into a caller-owned host buffer (raw pointer, e.g. pinned); returns the number of bytes written."""
+        nb = C.c_size_t(0)
+        sh = None if ishift is None else _p(np.ascontiguousarray(ishift, dtype=np.int32), C.c_int)
+        self._chk(self.lib.c2g_grid_format_text(self.h, C.c_int(h), C.c_int(layout), sh, C.c_int(width), C.c_int(digits),
+                                                C.c_int(scale), C.c_void_p(ptr), C.c_size_t(cap), C.byref(nb)))
+        return nb.value
+
+    def format_text(self, h, layout, width, digits, scale, ishift=None):
+        """Value block of a cube file from a resident grid (see c2g_grid_format_text); returns bytes."""
+        n = self.format_text_size(h, layout, width, digits, scale)
+        buf = np.empty(n, dtype=np.uint8)
+        self.format_text_into(h, layout, width, digits, scale, buf.ctypes.data, n, ishift)
+        return buf.tobytes()
 
     # ---- profiling ----
     def profile_enable(self, on=True):

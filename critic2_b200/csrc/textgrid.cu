@@ -403,6 +403,140 @@ __global__ void __launch_bounds__(TTHREADS) k_tok_parse(const __grid_constant__ 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Formatted output: the value loops of writegrid_cube (crystalmod@write.f90:3556-3565, formats (1p,6(" ",E12.5E3)) and
+// (6(" ",E22.14E3))) and of NCIPLOT's write_cube_body (nci@proc.f90:916-932, (6(" ",1p,e13.5e3))).  One thread per
+// value: S significant digits, CORRECTLY ROUNDED (nearest, ties to even -- what the Fortran run-time library prints),
+// laid out by the rules of the Ew.dEe edit descriptor with scale factor k (Fortran 2018 13.7.2.3.3): k = 1:
+// [-]d.ddd..E+eee with d digits after the point, k = 0: [-]0.ddd..E+eee; right-justified in w characters; a field
+// that does not fit (e.g. a NEGATIVE value in 1p,E12.5E3, which needs 13 characters) is w asterisks, like the
+// reference prints it.  Digits: |x| * 10^p in double-double; if the fraction is within 2^-96 of one half the decision
+// is made exactly with the multi-word comparison above.
+// ------------------------------------------------------------------------------------------------
+struct FormatArgs {
+  const double* f;
+  int n1, n2, n3;        // resident grid shape
+  int layout;            // 0: rows along index 1 as stored; 1: cube order (rows along index 3) with ishift
+  int s1, s2, s3;
+  int w, d, k;           // Ew.dE3 with scale factor k (0 or 1)
+  long long nrows; int L;
+  long long rowbytes;
+  unsigned char* out;
+};
+
+__device__ __forceinline__ void dd_mul_d(double ah, double al, double bh, double bl, double& rh, double& rl) {
+  double p, e;
+  two_prod(ah, bh, p, e);
+  e += ah * bl + al * bh;
+  fast_two_sum(p, e, rh, rl);
+}
+// ax > 0 finite: N = the S leading digits, correctly rounded; e10 = decimal exponent of the first digit
+__device__ void dec_digits(double ax, int S, unsigned long long& N, int& e10) {
+  unsigned long long M;
+  int E;
+  dbl_decompose(ax, M, E);
+  int e = (int)floor(log10(ax));
+  unsigned long long p10S = 1;
+  for (int q = 0; q < S; q++) p10S *= 10ull;
+  for (int it = 0; it < 6; it++) {
+    const int p = S - 1 - e;
+    double yh, yl;
+    if (p >= 0) {
+      const int pa = p > C2G_POW10_MAX ? C2G_POW10_MAX : p;
+      dd_mul_d(ax, 0.0, c2g_pow10_hi[pa], c2g_pow10_lo[pa], yh, yl);
+      if (p > pa) dd_mul_d(yh, yl, c2g_pow10_hi[p - pa], c2g_pow10_lo[p - pa], yh, yl);
+    } else {
+      const double ph = c2g_pow10_hi[-p], pl = c2g_pow10_lo[-p];
+      const double q1 = ax / ph;
+      double pp, ee;
+      two_prod(q1, ph, pp, ee);
+      const double r = ((ax - pp) - ee) - q1 * pl;
+      fast_two_sum(q1, r / ph, yh, yl);
+    }
+    double nf = floor(yh);
+    double frac = (yh - nf) + yl;
+    if (frac < 0.0) { nf -= 1.0; frac += 1.0; }
+    if (frac >= 1.0) { nf += 1.0; frac -= 1.0; }
+    const unsigned long long n = (unsigned long long)nf;
+    if (n >= p10S) { e++; continue; }            // the estimate of the exponent was one too small
+    if (n < p10S / 10ull) { e--; continue; }     // ... or one too large
+    unsigned long long Nr;
+    if (fabs(frac - 0.5) <= 1.3e-29 * (nf + 1.0)) {  // too close to call: exact comparison of n + 1/2 with ax * 10^p
+      Big mant;
+      big_set(mant, 2ull * n + 1ull);
+      const int c = cmp_decimal_binary(mant, -p, M, E + 1);
+      Nr = c > 0 ? n : (c < 0 ? n + 1 : n + (n & 1ull));
+    } else {
+      Nr = frac > 0.5 ? n + 1 : n;
+    }
+    if (Nr >= p10S) { Nr = p10S / 10ull; e++; }  // 9.99..96 rounds up to 10.0..0
+    N = Nr; e10 = e;
+    return;
+  }
+  N = p10S / 10ull; e10 = e;  // not reached
+}
+
+__global__ void __launch_bounds__(256) k_format(const __grid_constant__ FormatArgs A) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= A.nrows * A.L) return;
+  const long long r = t / A.L;
+  const int c = (int)(t % A.L);
+  size_t src;
+  if (A.layout == 0) src = (size_t)t;
+  else {
+    const int iix = (int)(r / A.n2), iiy = (int)(r % A.n2);
+    const int ix = (iix + A.s1) % A.n1, iy = (iiy + A.s2) % A.n2, iz = (c + A.s3) % A.n3;
+    src = (size_t)ix + (size_t)A.n1 * ((size_t)iy + (size_t)A.n2 * iz);
+  }
+  const double x = A.f[src];
+  const int w = A.w, S = A.d + (A.k == 1 ? 1 : 0);
+  char buf[32];
+  int len = 0;
+  const long long bits = __double_as_longlong(x);
+  const bool neg = bits < 0;
+  const int ex = (int)((bits >> 52) & 0x7ff);
+  if (ex == 0x7ff) {
+    const bool isnan_ = (bits & ((1ll << 52) - 1)) != 0;
+    if (isnan_) { buf[0] = 'N'; buf[1] = 'a'; buf[2] = 'N'; len = 3; }
+    else {
+      if (neg) buf[len++] = '-';
+      const char* word = (w >= 8 + (neg ? 1 : 0)) ? "Infinity" : "Inf";
+      for (int q = 0; word[q]; q++) buf[len++] = word[q];
+    }
+  } else {
+    unsigned long long N = 0;
+    int e10 = 0;
+    if (x != 0.0) dec_digits(fabs(x), S, N, e10);
+    int pexp = (x == 0.0) ? 0 : (A.k == 1 ? e10 : e10 + 1);
+    char dig[20];
+    for (int q = S - 1; q >= 0; q--) { dig[q] = (char)('0' + (int)(N % 10ull)); N /= 10ull; }
+    const int body = (A.k == 1 ? 1 + 1 + (S - 1) : 2 + S) + 5;  // digits, point, E+eee
+    bool lead0 = A.k == 0;
+    int need = body + (neg ? 1 : 0);
+    if (need > w && lead0) { lead0 = false; need--; }  // the zero before the point is optional
+    if (need <= w) {
+      if (neg) buf[len++] = '-';
+      if (A.k == 1) { buf[len++] = dig[0]; buf[len++] = '.'; for (int q = 1; q < S; q++) buf[len++] = dig[q]; }
+      else { if (lead0) buf[len++] = '0'; buf[len++] = '.'; for (int q = 0; q < S; q++) buf[len++] = dig[q]; }
+      buf[len++] = 'E';
+      buf[len++] = pexp < 0 ? '-' : '+';
+      const int ae = pexp < 0 ? -pexp : pexp;
+      buf[len++] = (char)('0' + ae / 100); buf[len++] = (char)('0' + (ae / 10) % 10); buf[len++] = (char)('0' + ae % 10);
+    } else {
+      len = w + 1;  // asterisks
+    }
+  }
+  unsigned char* o = A.out + (size_t)r * A.rowbytes + (size_t)c * (w + 1) + c / 6;
+  *o++ = ' ';
+  if (len > w) { for (int q = 0; q < w; q++) o[q] = '*'; }
+  else {
+    const int pad = w - len;
+    for (int q = 0; q < pad; q++) o[q] = ' ';
+    for (int q = 0; q < len; q++) o[pad + q] = (unsigned char)buf[q];
+  }
+  if (c % 6 == 5 || c == A.L - 1) o[w] = '\n';
+}
+
 }  // namespace
 
 // Parses the first n1*n2*n3 numbers of `text` (host memory, nbytes bytes) into a new resident grid.
@@ -458,5 +592,47 @@ extern "C" int c2g_grid_parse_text(c2g_context* ctx, const char* text, size_t nb
   if (nslow) *nslow = nfb;
   ctx->prof_collect();
   hg.ok = true;
+  return C2G_OK;
+}
+
+// Formats a resident grid as the value block of a cube file.  out == NULL: only *nbytes (the size needed) is set.
+extern "C" int c2g_grid_format_text(c2g_context* ctx, int handle, int layout, const int ishift[3], int width, int digits, int scale,
+                                    char* out, size_t cap, size_t* nbytes) {
+  if (!ctx) return C2G_ERR_ARG;
+  if (!nbytes) return ctx->fail(C2G_ERR_ARG, "c2g_grid_format_text: null argument");
+  if (handle < 0 || handle >= (int)ctx->grids.size() || !ctx->grids[handle].used)
+    return ctx->fail(C2G_ERR_ARG, "c2g_grid_format_text: invalid grid handle %d", handle);
+  if (layout != C2G_TEXT_ROWS_INDEX1 && layout != C2G_TEXT_ROWS_INDEX3) return ctx->fail(C2G_ERR_ARG, "c2g_grid_format_text: bad layout %d", layout);
+  if ((scale != 0 && scale != 1) || digits < 1 || digits + scale > 17 || width < 1 || width > 30)
+    return ctx->fail(C2G_ERR_ARG, "c2g_grid_format_text: unsupported edit descriptor E%d.%dE3 with %dP", width, digits, scale);
+  c2g_grid_ready(ctx, handle);
+  const c2g_grid& g = ctx->grids[handle];
+  FormatArgs A;
+  A.f = g.d; A.n1 = g.n[0]; A.n2 = g.n[1]; A.n3 = g.n[2]; A.layout = layout;
+  A.s1 = A.s2 = A.s3 = 0;
+  if (ishift && layout == C2G_TEXT_ROWS_INDEX3) {
+    A.s1 = ((ishift[0] % A.n1) + A.n1) % A.n1; A.s2 = ((ishift[1] % A.n2) + A.n2) % A.n2; A.s3 = ((ishift[2] % A.n3) + A.n3) % A.n3;
+  }
+  A.w = width; A.d = digits; A.k = scale;
+  if (layout == C2G_TEXT_ROWS_INDEX1) { A.L = A.n1; A.nrows = (long long)A.n2 * A.n3; }
+  else { A.L = A.n3; A.nrows = (long long)A.n1 * A.n2; }
+  A.rowbytes = (long long)A.L * (width + 1) + (A.L + 5) / 6;
+  const size_t total = (size_t)A.nrows * (size_t)A.rowbytes;
+  *nbytes = total;
+  if (!out || cap == 0) return C2G_OK;  // step 1: the size only
+  if (cap < total) return ctx->fail(C2G_ERR_ARG, "c2g_grid_format_text: output buffer too small (%zu < %zu)", cap, total);
+  DevBuf b_out;
+  C2G_CUDA(ctx, b_out.alloc(ctx, total));
+  A.out = (unsigned char*)b_out.p;
+  const long long nval = A.nrows * A.L;
+  ctx->prof_begin("text_format");
+  k_format<<<(unsigned)((nval + 255) / 256), 256, 0, ctx->stream>>>(A);
+  ctx->prof_end();
+  C2G_KERNEL_CHECK(ctx);
+  ctx->prof_begin("text_d2h");
+  C2G_CUDA(ctx, cudaMemcpyAsync(out, b_out.p, total, cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->prof_end(0);
+  C2G_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->prof_collect();
   return C2G_OK;
 }

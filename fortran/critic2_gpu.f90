@@ -147,6 +147,17 @@ module critic2_gpu
        integer(c_long_long) :: nhost
        integer(c_int) :: c2g_grid_parse_text
      end function c2g_grid_parse_text
+     ! formatted output of a resident grid (writegrid_cube / write_cube_body value loops)
+     function c2g_grid_format_text(ctx,handle,layout,ishift,width,digits,scale,out,cap,nbytes) bind(c,name="c2g_grid_format_text")
+       import :: c_int, c_ptr, c_size_t, c_char
+       type(c_ptr), value :: ctx
+       integer(c_int), value :: handle, layout, width, digits, scale
+       integer(c_int) :: ishift(3)
+       character(kind=c_char) :: out(*)
+       integer(c_size_t), value :: cap
+       integer(c_size_t) :: nbytes
+       integer(c_int) :: c2g_grid_format_text
+     end function c2g_grid_format_text
      function c2g_fft_derivative(ctx,handle,iff,x2c,hout) bind(c,name="c2g_fft_derivative")
        import :: c_int, c_ptr, c_double
        type(c_ptr), value :: ctx
@@ -409,5 +420,28 @@ contains
     call check(c2g_grid_download(ctx,h,f),"gpu_read_text_block")
     call check(c2g_grid_free(ctx,h),"gpu_read_text_block")
   end subroutine gpu_read_text_block
+
+  !> The value block of a cube file from a host array: g(i,j,k) in cube order with the shift of writegrid_cube
+  !> (layout 1: width 12, digits 5, scale 1; precisecube: 22, 14, 0), or c(k,j,i) of write_cube_body (layout 0:
+  !> 13, 5, 1).  The text is written to unit lu (opened with access="stream") in one piece.
+  subroutine gpu_write_text_block(lu,g,layout,ishift,width,digits,scale)
+    integer, intent(in) :: lu, layout, ishift(3), width, digits, scale
+    real*8, intent(in) :: g(:,:,:)
+    integer(c_int) :: n(3), h
+    integer(c_size_t) :: nbytes
+    character(kind=c_char), allocatable :: text(:)
+
+    n = int(shape(g),c_int)
+    call check(c2g_grid_upload(ctx,g,n,h),"gpu_write_text_block")
+    allocate(text(1))
+    call check(c2g_grid_format_text(ctx,h,int(layout,c_int),int(ishift,c_int),int(width,c_int),int(digits,c_int),&
+       int(scale,c_int),text,0_c_size_t,nbytes),"gpu_write_text_block")   ! step 1: size (cap = 0 with out ignored)
+    deallocate(text)
+    allocate(text(nbytes))
+    call check(c2g_grid_format_text(ctx,h,int(layout,c_int),int(ishift,c_int),int(width,c_int),int(digits,c_int),&
+       int(scale,c_int),text,nbytes,nbytes),"gpu_write_text_block")
+    write (lu) text
+    call check(c2g_grid_free(ctx,h),"gpu_write_text_block")
+  end subroutine gpu_write_text_block
 
 end module critic2_gpu

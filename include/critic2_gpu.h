@@ -196,6 +196,20 @@ int c2g_nci_rdg_fourier(c2g_context* ctx, const int h[5], const double x0[3], co
 int c2g_grid_parse_text(c2g_context* ctx, const char* text, size_t nbytes, const int n[3], int order, double divisor,
                         int* handle, size_t* consumed, long long* nslow);
 
+/* Formatted output of a resident grid: the value loops of writegrid_cube (crystalmod@write.f90:3556-3565) and of
+ * NCIPLOT's write_cube_body (nci@proc.f90:916-932): every value as " " + Ew.dE3 with scale factor `scale` (0 or 1),
+ * 6 per line, a new line after each row; digits correctly rounded (nearest even), fields that do not fit are
+ * asterisks like the Fortran run-time prints them.
+ *   layout C2G_TEXT_ROWS_INDEX1: rows run along the first (fastest) index as stored -- the crho/cgrad(k,j,i) arrays of
+ *     c2g_nci_rdg_resident with (6(" ",1p,e13.5e3)): width 13, digits 5, scale 1;
+ *   layout C2G_TEXT_ROWS_INDEX3: cube order of a field f(i,j,k), rows along k for i outer, j inner, with the optional
+ *     shift ishift(3) of writegrid_cube: (1p,6(" ",E12.5E3)) = 12, 5, 1 or precisecube (6(" ",E22.14E3)) = 22, 14, 0.
+ * out == NULL or cap == 0: only *nbytes is set (step 1); otherwise out(cap) receives *nbytes characters (step 2). */
+#define C2G_TEXT_ROWS_INDEX1 0
+#define C2G_TEXT_ROWS_INDEX3 1
+int c2g_grid_format_text(c2g_context* ctx, int handle, int layout, const int ishift[3], int width, int digits, int scale,
+                         char* out, size_t cap, size_t* nbytes);
+
 /* ---- profiling: CUDA-event timings of the kernels launched by the last API call ---- */
 int c2g_profile_enable(c2g_context* ctx, int on);
 int c2g_profile_count(c2g_context* ctx);

@@ -348,3 +348,66 @@ def parse_text_grid(text, n, order=0, divisor=1.0):
     else:
         f = np.asfortranarray(vals.reshape(tuple(int(x) for x in n), order="C"))
     return f, end
+
+
+# ---------------------------------------------------------------------------
+# Formatted output of grid values: writegrid_cube (crystalmod@write.f90:3556-3565) and NCIPLOT's write_cube_body
+# (nci@proc.f90:916-932).  Restates the Ew.dE3 edit descriptor with scale factor k (Fortran 2018 13.7.2.3.3) on top of
+# Python's decimal module (exact binary -> decimal, round-half-even like the Fortran run-time library).
+# NOT pinned against a Fortran compiler (none in the image): the asterisk rule for fields that do not fit and the
+# optional leading zero follow the standard's text.
+# ---------------------------------------------------------------------------
+import decimal as _dec
+import math as _math
+
+
+def fortran_e(x: float, w: int, d: int, k: int) -> str:
+    """One value in Ew.dE3 with scale factor k (0 or 1), right-justified; asterisks if it does not fit."""
+    if _math.isnan(x):
+        s = "NaN"
+    elif _math.isinf(x):
+        neg = x < 0
+        s = ("-" if neg else "") + ("Infinity" if w >= 8 + (1 if neg else 0) else "Inf")
+    else:
+        S = d + (1 if k == 1 else 0)
+        neg = _math.copysign(1.0, x) < 0
+        if x == 0.0:
+            N, e10 = 0, 0
+            pexp = 0
+        else:
+            with _dec.localcontext() as c:
+                c.prec = 1200
+                D = _dec.Decimal(abs(x))
+                e10 = D.adjusted()
+                N = int(D.scaleb(-(e10 - S + 1)).quantize(_dec.Decimal(1), rounding=_dec.ROUND_HALF_EVEN))
+            if N == 10 ** S:
+                N //= 10
+                e10 += 1
+            pexp = e10 if k == 1 else e10 + 1
+        dig = str(N).rjust(S, "0")
+        body = (dig[0] + "." + dig[1:]) if k == 1 else ("0." + dig)
+        s = ("-" if neg else "") + body + "E" + ("-" if pexp < 0 else "+") + "%03d" % abs(pexp)
+        if len(s) > w and k == 0:
+            s = s.replace("0.", ".", 1)   # the zero before the point is optional
+    return "*" * w if len(s) > w else s.rjust(w)
+
+
+def format_text_grid(f, layout, w, d, k, ishift=(0, 0, 0)):
+    """layout 0: rows along index 1 of f as stored (NCI crho(k,j,i)); layout 1: cube order of f(i,j,k) with ishift.
+    Every value " " + Ew.dE3, 6 per line, new line after each row."""
+    f = _f64(f)
+    n1, n2, n3 = f.shape
+    out = []
+    if layout == 0:
+        for c in range(n3):
+            for b in range(n2):
+                row = [" " + fortran_e(float(f[a, b, c]), w, d, k) for a in range(n1)]
+                out += ["".join(row[q:q + 6]) + "\n" for q in range(0, n1, 6)]
+    else:
+        for iix in range(n1):
+            ix = (iix + ishift[0]) % n1
+            for iiy in range(n2):
+                iy = (iiy + ishift[1]) % n2
+                row = [" " + fortran_e(float(f[ix, iy, (iiz + ishift[2]) % n3]), w, d, k) for iiz in range(n3)]
+                out += ["".join(row[q:q + 6]) + "\n" for q in range(0, n3, 6)]
+    return "".join(out).encode()

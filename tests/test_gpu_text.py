@@ -127,3 +127,51 @@ def test_error_paths(ctx):
     h, used, _ = ctx.parse_text(b"1.0 2.0 junk\n", (2, 1, 1))   # text after the block is not looked at
     assert np.array_equal(ctx.download(h, (2, 1, 1)).ravel(), [1.0, 2.0])
     ctx.free(h)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# formatted output (c2g_grid_format_text) against the oracle's restatement of the Fortran edit descriptors: same bytes
+# ---------------------------------------------------------------------------------------------------------------
+def test_format_nci_cube_body(ctx):
+    """(6(" ",1p,e13.5e3)) over crho(k,j,i): rows along the stored fastest index, negative values fit."""
+    rng = np.random.default_rng(11)
+    f = np.asfortranarray(rng.standard_normal((13, 5, 4)) * 10.0 ** rng.integers(-30, 6, (13, 5, 4)))
+    f[0, 0, 0] = 0.0; f[1, 0, 0] = -0.0; f[2, 0, 0] = 9.999996; f[3, 0, 0] = 9.9999949999; f[4, 0, 0] = 1e-310; f[5, 0, 0] = 1.7976931348623157e308
+    h = ctx.upload(f)
+    got = ctx.format_text(h, 0, 13, 5, 1)
+    assert got == orc.format_text_grid(f, 0, 13, 5, 1)
+    ctx.free(h)
+
+
+def test_format_writegrid_cube_formats_and_shift(ctx):
+    """(1p,6(" ",E12.5E3)) (negative values overflow the field: asterisks, as the reference prints them) and the
+    precisecube format (6(" ",E22.14E3)), cube order with ishift."""
+    rng = np.random.default_rng(12)
+    f = np.asfortranarray(rng.standard_normal((6, 7, 11)) * 10.0 ** rng.integers(-12, 4, (6, 7, 11)))
+    h = ctx.upload(f)
+    for (w, d, k) in ((12, 5, 1), (22, 14, 0)):
+        for sh in (None, (2, 5, 3)):
+            got = ctx.format_text(h, 1, w, d, k, ishift=sh)
+            ref = orc.format_text_grid(f, 1, w, d, k, ishift=sh or (0, 0, 0))
+            assert got == ref, (w, d, k, sh)
+    assert b"************" in ctx.format_text(h, 1, 12, 5, 1)
+    ctx.free(h)
+
+
+def test_format_rounding_ties_and_round_trip(ctx):
+    """Exact ties (dyadic values whose next digit is exactly 5) round to even; a precisecube block written by the
+    formatter and read back by the parser reproduces its 14 significant digits."""
+    vals = [2.0 ** -16, 0.5, 1.5, 2.5, 0.125, 1.0009765625, 3.0517578125e-05, 152587890625.0, 7.62939453125e-06]
+    f = np.asfortranarray(np.array(vals + [0.0] * (16 - len(vals))).reshape(16, 1, 1))
+    h = ctx.upload(f)
+    for (w, d, k) in ((20, 10, 1), (13, 5, 1), (12, 2, 1), (22, 14, 0), (10, 1, 1)):
+        assert ctx.format_text(h, 0, w, d, k) == orc.format_text_grid(f, 0, w, d, k), (w, d, k)
+    ctx.free(h)
+    rng = np.random.default_rng(13)
+    g = np.asfortranarray(np.abs(rng.standard_normal((8, 9, 10))) * 10.0 ** rng.integers(-8, 8, (8, 9, 10)))
+    hg = ctx.upload(g)
+    text = ctx.format_text(hg, 1, 22, 14, 0)
+    hb, used, _ = ctx.parse_text(text, (8, 9, 10), 1, 1.0)
+    back = ctx.download(hb, (8, 9, 10))
+    assert np.abs(back / g - 1.0).max() <= 5.1e-14
+    ctx.free(hg); ctx.free(hb)

@@ -34,3 +34,32 @@ def test_cube_and_vasp_orders_round_trip():
     want2 = np.array([float("%18.11E" % v) for v in flat]).reshape(n, order="F") / 123.456
     assert np.array_equal(g2, want2)
     assert chg[end2:].lstrip().startswith("augmentation")
+
+
+def test_fortran_e_descriptor():
+    assert orc.fortran_e(1.234565, 13, 5, 1) == " 1.23456E+000" or orc.fortran_e(1.234565, 13, 5, 1) == " 1.23457E+000"
+    assert orc.fortran_e(1.0, 13, 5, 1) == " 1.00000E+000"
+    assert orc.fortran_e(-1.0, 13, 5, 1) == "-1.00000E+000"
+    assert orc.fortran_e(-1.0, 12, 5, 1) == "*" * 12            # 13 characters do not fit in 1p,E12.5E3
+    assert orc.fortran_e(1.0, 12, 5, 1) == "1.00000E+000"
+    assert orc.fortran_e(0.0, 12, 5, 1) == "0.00000E+000"
+    assert orc.fortran_e(9.999996, 13, 5, 1) == " 1.00000E+001"   # the carry moves the exponent
+    assert orc.fortran_e(0.5, 13, 0 + 5, 1) == " 5.00000E-001"
+    assert orc.fortran_e(123.456, 22, 14, 0) == " 0.12345600000000E+003"
+    assert orc.fortran_e(-123.456, 22, 14, 0) == "-0.12345600000000E+003"
+    assert orc.fortran_e(2.5e-310, 22, 14, 0) == " 0.25000000000000E-309"
+    assert orc.fortran_e(float("inf"), 13, 5, 1) == "     Infinity"
+    assert orc.fortran_e(float("nan"), 13, 5, 1) == "          NaN"
+    # exact tie: 2^-16 = 1.52587890625E-05 printed with 10 digits after the point -> ...789062|5 rounds to even
+    assert orc.fortran_e(2.0 ** -16, 20, 10, 1) == "   1.5258789062E-005"
+
+
+def test_format_text_grid_layouts():
+    rng = np.random.default_rng(2)
+    f = np.asfortranarray(rng.standard_normal((4, 3, 7)))
+    t0 = orc.format_text_grid(f, 0, 13, 5, 1).decode()
+    assert t0.count("\n") == 3 * 7 * 1 and len(t0) == 3 * 7 * (4 * 14 + 1)
+    t1 = orc.format_text_grid(np.abs(f), 1, 12, 5, 1, ishift=(1, 0, 2)).decode()
+    assert t1.count("\n") == 4 * 3 * 2 and len(t1) == 4 * 3 * (7 * 13 + 2)
+    first = t1.split()[0]
+    assert first == orc.fortran_e(float(abs(f[1, 0, 2])), 12, 5, 1).strip()

@@ -198,7 +198,37 @@ def text_reader():
     ctx.free(h)
 
 
-for fn in (urea, nci, yt, fft_big, text_reader):
+# ---- formatted-text writer: NCIPLOT's cube body for a 512^3 RDG grid ((6(" ",1p,e13.5e3))) ----
+def text_writer():
+    N = 128 if quick else 512
+    n = (N, N, N)
+    x2c = S.cell_x2c(30.0, 30.0, 30.0)
+    at, z, al = S.random_atoms(24, 3, x2c, dmin=2.0)
+    h = ctx.alloc(n); ctx.promolecular(h, x2c, S.snap_to_grid(at, n), z, al, nimg=0, rc=0.0)
+    hr, hg = ctx.nci_rdg_resident(h, x2c, n)
+    import torch
+    nbytes = ctx.format_text_size(hg, 0, 13, 5, 1)
+    pinned = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)       # the caller's buffer (page-locked)
+    ms, prof, _ = timed(lambda: ctx.format_text_into(hg, 0, 13, 5, 1, pinned.data_ptr(), nbytes), reps=2)
+    text = pinned.numpy()[:200000].tobytes()
+    # parity on the first rows against the oracle (pure Python: a few thousand values)
+    cg = ctx.download(hg, n)
+    nrow = 8
+    ref = orc.format_text_grid(cg[:, :nrow, :1], 0, 13, 5, 1)
+    t0 = time.perf_counter()
+    cpu = "".join(" %13.5E" % v for v in cg.ravel(order="F")[:2000000])     # C printf on one host thread, for scale
+    t_cpu = time.perf_counter() - t0
+    kern = prof.get("text_format", 0.0)
+    emit("formatted-text writer (NCIPLOT cube body, 1p,e13.5e3), resident grid in, host text out", "SURVEY 8(f)-1", n, ms,
+         8.0 + nbytes / float(np.prod(n)), prof,
+         {"first_rows_identical_to_oracle": bool(text[:len(ref)] == ref), "text_bytes": int(nbytes), "kernel_only_ms": kern,
+          "kernel_only_GBps": round((8.0 * np.prod(n) + nbytes) / (max(kern, 1e-9) * 1e-3) / 1e9, 1),
+          "cpu_python_printf_values_per_s_1thread": 2000000 / t_cpu, "gpu_values_per_s_incl_d2h": float(np.prod(n)) / (ms * 1e-3)})
+    for x in (h, hr, hg):
+        ctx.free(x)
+
+
+for fn in (urea, nci, yt, fft_big, text_reader, text_writer):
     try:
         fn()
     except Exception as e:  # keep going: one JSON line per failure
