@@ -410,9 +410,6 @@ struct CubeFlags {
 // s: [(TY+2)][34] buffer of T.  Every thread contributes its own value; threads with hslot >= 0 also a
 // halo value.  Returns Op(3x3 neighbourhood) of the thread's point.  One __syncthreads per call; the
 // caller alternates between two buffers so that no second barrier is needed.
-struct OpMaxF {
-  static __device__ __forceinline__ float c3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
-};
 struct OpAgree {  // common value of three labels, or -1
   static __device__ __forceinline__ int c3(int a, int b, int c) { return (a == b && b == c) ? a : -1; }
 };
@@ -1756,7 +1753,7 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
   C2G_CUDA(ctx, b_stop.alloc(ctx, sizeof(int) * (size_t)dcap));
   const long long overcap = std::max<long long>(1024, nnl);  // worst case: every walker of a launch is handed over
   C2G_CUDA(ctx, b_over.alloc(ctx, sizeof(int2) * (size_t)overcap));
-  long long walked = 0, fixpts = 0, fixpasses = 0, noverflow_total = 0, nrequeued = 0;
+  long long walked = 0, fixpts = 0, fixpasses = 0, noverflow_total = 0;
 
   WalkArgs WA;
   memset(&WA, 0, sizeof(WA));

@@ -576,7 +576,6 @@ extern "C" int c2g_yt_build(c2g_context* ctx, int handle, int nvec, const int* v
   const int maxlvl = 1 << 22;
   C2G_CUDA(ctx, c2g_alloc(ctx, (void**)&S->order, sizeof(int) * std::max(nias, 1)));
   C2G_CUDA(ctx, c2g_alloc(ctx, (void**)&S->lvl, sizeof(int) * (maxlvl + 1)));
-  long long nrec = 0;
   if (nias > 0) {
     C2G_CUDA(ctx, b_indeg.alloc(ctx, ((size_t)nn + 3) / 4 * 4));
     C2G_CUDA(ctx, cudaMemsetAsync(b_indeg.p, 0, ((size_t)nn + 3) / 4 * 4, st));
@@ -624,7 +623,6 @@ extern "C" int c2g_yt_build(c2g_context* ctx, int handle, int nvec, const int* v
       C2G_KERNEL_CHECK(ctx);
     }
   }
-  (void)nrec;
   C2G_CUDA(ctx, cudaStreamSynchronize(st));
   res->stats[0] = nias;
   res->stats[1] = bfs_levels;
