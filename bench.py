@@ -353,6 +353,14 @@ def run_ours(args):
             traffic, traffic_src = tj[key]["dram_bytes_per_step"], tj[key]["source"]
     except (OSError, ValueError, KeyError):
         pass
+    kms = {k: v[0] / args.steps for k, v in prof.items()}
+    dk = max(kms, key=kms.get) if kms else None
+    dominant = None if dk is None else {
+        "name": dk + (" (k_walk, last-level launch)" if dk == "bader_walk_l1" else ""), "ms": round(kms[dk], 4),
+        "share_of_kernel_group": round(kms[dk] / max(assign_ms + integ_ms, 1e-9), 4),
+        "note": "the walkers are issue-bound, not HBM-bound (ncu: 78 % of the issue slots busy, 19 of 32 lanes active, L2 hit "
+                "81 %; profiles/r01k_ncu_full_1024_table.txt): an HBM fraction of this launch alone would be meaningless, so "
+                "`achieved` is the algorithmic bytes of the whole step over the time of the whole kernel group"}
     roofline = {
         "bound": "hbm", "kernel": "BADER assign+integrate kernel group (k_maxima, k_walk, k_classify, k_vsafe, k_fill_edge_v, k_requeue, "
                                   "k_basin_reduce); dominant: k_walk (last-level launch, bader_walk_l1)",
@@ -364,6 +372,7 @@ def run_ours(args):
             "integrate": {"ms": integ_ms, "GBps": ALG_BYTES_INTEGRATE * nloc / max(integ_ms, 1e-9) / 1e6},
         },
         "kernels_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in prof.items()},
+        "dominant_kernel": dominant,
         "kernel_group_ms_max_over_ranks": kern_ms,
     }
 
