@@ -132,14 +132,19 @@ __global__ void __launch_bounds__(256) k_seed(const __grid_constant__ YtParams P
   }
 }
 
-// downward closure: persistent cooperative BFS.  ctl[0] = tail, ctl[1] = number of levels
+// downward closure: persistent cooperative BFS.  In: ctl[0] = number of seeds (already in queue[]).  Out: ctl[0] =
+// queue length, ctl[1] = number of levels.  Like k_kahn: the points found while a level is processed are appended
+// behind its end through a per-level counter, so one grid barrier per level is enough.
 __global__ void __launch_bounds__(256) k_bfs(const __grid_constant__ YtParams P, const unsigned* __restrict__ mask,
-                                             unsigned char* __restrict__ ias, int* __restrict__ queue, int* __restrict__ ctl) {
+                                             unsigned char* __restrict__ ias, int* __restrict__ queue, int* __restrict__ ctl,
+                                             int* __restrict__ cnt, int maxlvl) {
   cg::grid_group grid = cg::this_grid();
+  __shared__ int s_next;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
   const unsigned full = (P.nvec >= 32) ? 0xffffffffu : ((1u << P.nvec) - 1u);
   int lo = 0, hi = ctl[0], levels = 0;
   while (lo < hi) {
+    int* next = cnt + min(levels + 1, maxlvl);
     for (int q = lo + tid; q < hi; q += nth) {
       const int i = queue[q];
       const Pt p = unlin(P, i);
@@ -149,21 +154,23 @@ __global__ void __launch_bounds__(256) k_bfs(const __grid_constant__ YtParams P,
         lower &= lower - 1;
         const int j = nbr(P, p, k);
         if (!ias[j]) {
-          // byte flags: claim through a 32-bit CAS on the containing word
+          // byte flags: claim through a 32-bit atomic on the containing word
           unsigned* w = (unsigned*)(ias + (j & ~3));
           const unsigned bit = 1u << (8 * (j & 3));
           const unsigned old = atomicOr(w, bit);
-          if (!(old & bit)) queue[atomicAdd(ctl, 1)] = j;
+          if (!(old & bit)) queue[hi + atomicAdd(next, 1)] = j;
         }
       }
     }
     grid.sync();
+    if (threadIdx.x == 0) s_next = *((volatile int*)next);
+    __syncthreads();
     lo = hi;
-    hi = ctl[0];
+    hi += s_next;
     levels++;
-    grid.sync();
+    __syncthreads();
   }
-  if (tid == 0) ctl[1] = levels;
+  if (tid == 0) { ctl[0] = hi; ctl[1] = levels; }
 }
 
 // in-degree of every IAS point = number of IAS points below it among its neighbours
@@ -556,7 +563,13 @@ extern "C" int c2g_yt_build(c2g_context* ctx, int handle, int nvec, const int* v
     const unsigned* a_mask = S->mask;
     unsigned char* a_ias = S->ias;
     int* a_queue = b_queue.as<int>();
-    void* args[] = {(void*)&P, (void*)&a_mask, (void*)&a_ias, (void*)&a_queue, (void*)&ctl};
+    const int bfs_maxlvl = 1 << 20;  // more levels than any grid dimension allows; the counter index saturates
+    DevBuf b_bcnt;
+    C2G_CUDA(ctx, b_bcnt.alloc(ctx, sizeof(int) * ((size_t)bfs_maxlvl + 2)));
+    C2G_CUDA(ctx, cudaMemsetAsync(b_bcnt.p, 0, sizeof(int) * ((size_t)bfs_maxlvl + 2), st));
+    int* a_bcnt = b_bcnt.as<int>();
+    int a_bmax = bfs_maxlvl;
+    void* args[] = {(void*)&P, (void*)&a_mask, (void*)&a_ias, (void*)&a_queue, (void*)&ctl, (void*)&a_bcnt, (void*)&a_bmax};
     ctx->prof_begin("yt_bfs");
     C2G_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_bfs, dim3(blocks), dim3(256), args, 0, st));
     ctx->prof_end();
