@@ -243,4 +243,30 @@ void nci_rdg_fourier(const system& s, std::vector<double>& crho, std::vector<dou
   for (int q = 0; q < 5; q++) check(c2g_grid_free(g_ctx, h[q]), "nciplot");
 }
 
+size_t grid_read_text(const std::string& text, bool k_fastest, double divisor, grid3& g) {
+  if (!g_ctx) ferror("read_cube", "gpu_init was not called");
+  int h = -1;
+  size_t consumed = 0;
+  long long nslow = 0;
+  check(c2g_grid_parse_text(g_ctx, text.data(), text.size(), g.n, k_fastest ? C2G_TEXT_ORDER_K_FASTEST : C2G_TEXT_ORDER_I_FASTEST,
+                            divisor, &h, &consumed, &nslow), "read_cube");
+  g.f.assign((size_t)g.n[0] * g.n[1] * g.n[2], 0.0);
+  check(c2g_grid_download(g_ctx, h, g.f.data()), "read_cube");
+  check(c2g_grid_free(g_ctx, h), "read_cube");
+  return consumed;
+}
+
+std::string grid_write_text(const grid3& g, bool cube_order, const int ishift[3], int width, int digits, int scale) {
+  if (!g_ctx) ferror("writegrid_cube", "gpu_init was not called");
+  int h = -1;
+  check(c2g_grid_upload(g_ctx, g.f.data(), g.n, &h), "writegrid_cube");
+  const int layout = cube_order ? C2G_TEXT_ROWS_INDEX3 : C2G_TEXT_ROWS_INDEX1;
+  size_t nbytes = 0;
+  check(c2g_grid_format_text(g_ctx, h, layout, ishift, width, digits, scale, nullptr, 0, &nbytes), "writegrid_cube");
+  std::string out(nbytes, ' ');
+  check(c2g_grid_format_text(g_ctx, h, layout, ishift, width, digits, scale, &out[0], out.size(), &nbytes), "writegrid_cube");
+  check(c2g_grid_free(g_ctx, h), "writegrid_cube");
+  return out;
+}
+
 }  // namespace c2h

@@ -13,6 +13,8 @@
 //   integration@proc.f90:1170  intgrid_fields(bas,res)
 //   nci@proc.f90:543-605       nciplot loop -> nci_rdg, nci_rdg_fourier
 //   grid3mod@proc.f90:1757     grid3%fft -> grid_fft
+//   grid3mod@proc.f90:559,884  read_cube / read_vasp value blocks -> grid_read_text
+//   crystalmod@write.f90:3556  writegrid_cube / write_cube_body value loops -> grid_write_text
 //   tools_io@proc.F90:1573     ferror(routine,msg,faterr) -> c2h::ferror (throws c2h::fatal_error)
 #pragma once
 
@@ -93,5 +95,11 @@ void nci_rdg(const system& s, std::vector<double>& crho, std::vector<double>& cg
 void nci_rdg_fourier(const system& s, std::vector<double>& crho, std::vector<double>& cgrad);
 // grid3%fft (grid3mod@proc.f90:1757-1872): fnew = FFT-derived field of fold; iff = ifformat_as_ft_* (param.F90:225-236)
 void grid_fft(const system& s, const grid3& fold, int iff, grid3& fnew);
+// the value block of read_cube (k_fastest = true, grid3mod@proc.f90:559) / read_vasp (false, :884; divisor = det3(x2c)
+// with vscal): g.n must be set; fills g.f; returns the offset of the first byte after the last value
+size_t grid_read_text(const std::string& text, bool k_fastest, double divisor, grid3& g);
+// the value loops of writegrid_cube (cube_order = true: width 12, digits 5, scale 1, or precisecube 22, 14, 0;
+// crystalmod@write.f90:3556-3565) and write_cube_body (cube_order = false: 13, 5, 1; nci@proc.f90:916-932)
+std::string grid_write_text(const grid3& g, bool cube_order, const int ishift[3], int width, int digits, int scale);
 
 }  // namespace c2h

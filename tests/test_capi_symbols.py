@@ -72,7 +72,7 @@ def test_host_mirror_library_exports_the_reference_driver_names():
     assert os.path.exists(lib), "run __graft_entry__.build()"
     syms = subprocess.run(["nm", "-DC", "--defined-only", lib], capture_output=True, text=True).stdout
     for name in ("c2h::bader_integrate", "c2h::yt_integrate", "c2h::intgrid_fields", "c2h::yt_weights", "c2h::nci_rdg",
-                 "c2h::nci_rdg_fourier", "c2h::grid_fft",
+                 "c2h::nci_rdg_fourier", "c2h::grid_fft", "c2h::grid_read_text", "c2h::grid_write_text",
                  "c2h::ferror", "c2h::gpu_init", "c2h::system::identify_atom", "c2h::system::are_lclose"):
         assert name in syms, name
     und = subprocess.run(["nm", "-DC", "--undefined-only", lib], capture_output=True, text=True).stdout
