@@ -175,3 +175,22 @@ def test_format_rounding_ties_and_round_trip(ctx):
     back = ctx.download(hb, (8, 9, 10))
     assert np.abs(back / g - 1.0).max() <= 5.1e-14
     ctx.free(hg); ctx.free(hb)
+
+
+def test_text_golden_fixture(ctx):
+    """The committed golden vectors (tests/golden/text_golden.json): reader bit patterns and writer fields."""
+    import json, os, struct
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "text_golden.json")))
+    toks, want = g["reader"]["tokens"], g["reader"]["bits"]
+    h, _, _ = ctx.parse_text((" ".join(toks) + "\n").encode(), (len(toks), 1, 1), 0, 1.0)
+    got = ctx.download(h, (len(toks), 1, 1)).ravel()
+    ctx.free(h)
+    assert ["%016x" % v for v in got.view(np.uint64)] == want
+    vals = np.array([struct.unpack("<d", struct.pack("<Q", int(b, 16)))[0] for b in g["writer"]["values_bits"]])
+    hv = ctx.upload(np.asfortranarray(vals.reshape(-1, 1, 1)))
+    for key, fields in g["writer"]["fields"].items():
+        w, d, k = (int(x) for x in key.split(","))
+        text = ctx.format_text(hv, 0, w, d, k).decode()
+        got_fields = [text[q * (w + 1) + q // 6 + 1: q * (w + 1) + q // 6 + 1 + w] for q in range(len(vals))]
+        assert got_fields == fields, key
+    ctx.free(hv)

@@ -63,3 +63,15 @@ def test_format_text_grid_layouts():
     assert t1.count("\n") == 4 * 3 * 2 and len(t1) == 4 * 3 * (7 * 13 + 2)
     first = t1.split()[0]
     assert first == orc.fortran_e(float(abs(f[1, 0, 2])), 12, 5, 1).strip()
+
+
+def test_text_golden_fixture_matches_the_oracle():
+    """tests/golden/text_golden.json (made by tests/golden/make_text_golden.py) against the oracle as it is now."""
+    import json, os, struct
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "text_golden.json")))
+    for t, b in zip(g["reader"]["tokens"], g["reader"]["bits"]):
+        assert "%016x" % struct.unpack("<Q", struct.pack("<d", orc.fortran_float(t)))[0] == b, t
+    vals = [struct.unpack("<d", struct.pack("<Q", int(b, 16)))[0] for b in g["writer"]["values_bits"]]
+    for key, fields in g["writer"]["fields"].items():
+        w, d, k = (int(x) for x in key.split(","))
+        assert [orc.fortran_e(v, w, d, k) for v in vals] == fields
