@@ -25,7 +25,7 @@ EXPORTS = [
     "c2g_init", "c2g_nccl_unique_id", "c2g_init_multi", "c2g_finalize", "c2g_last_error", "c2g_describe",
     "c2g_grid_upload", "c2g_grid_upload_slab", "c2g_slab_range", "c2g_slab_bounds_query", "c2g_grid_alloc", "c2g_grid_download", "c2g_grid_download_slab", "c2g_grid_free", "c2g_grid_promolecular",
     "c2g_bader_assign", "c2g_basins_maxima", "c2g_basins_counts", "c2g_basins_set_map", "c2g_basins_labels",
-    "c2g_basins_relabel", "c2g_basins_free", "c2g_basins_stats", "c2g_integrate", "c2g_yt_build",
+    "c2g_basins_relabel", "c2g_basins_free", "c2g_basins_stats", "c2g_integrate", "c2g_integrate_multipoles", "c2g_yt_build",
     "c2g_yt_weights", "c2g_nci_rdg", "c2g_nci_rdg_resident", "c2g_fft_derivative", "c2g_nci_rdg_fourier", "c2g_nci_range", "c2g_grid_upload_async", "c2g_basins_labels_async", "c2g_grid_parse_text", "c2g_grid_format_text", "c2g_profile_enable", "c2g_profile_count",
     "c2g_profile_get", "c2g_profile_reset", "c2g_launch_count", "c2g_flush_l2", "c2g_synchronize", "c2g_timer_start", "c2g_timer_stop",
 ]
@@ -164,6 +164,30 @@ class Context:
         self._chk(self.lib.c2g_integrate(self.h, basins.h, C.c_int(len(fh)), _p(fh, C.c_int), C.c_double(omega),
                                          _p(psum, C.c_double), _p(vol, C.c_double)))
         return vol, psum
+
+    def integrate_multipoles(self, basins, fieldhandle, lmax, xattr, x2c, omega, x2xr=None, xr2c=None, ws=None,
+                             isortho=None, isortho_del=False, domask=None):
+        """mpole[(lmax+1)^2, nattr] (integration@proc.f90:1302-1361).  xattr (3, nattr) crystallographic; the cell
+        arguments are those of crystal%shortest: an orthogonal m_x2c alone, or x2xr / xr2c / ws (3, ws_nf) Cartesian."""
+        x2c = np.asarray(x2c, dtype=np.float64)
+        if isortho is None:
+            isortho = bool(np.all(x2c - np.diag(np.diag(x2c)) == 0.0))
+        xa = np.asfortranarray(np.asarray(xattr, dtype=np.float64).reshape(3, -1))
+        nattr = basins.nattr
+        if xa.shape[1] != nattr:
+            raise C2GError(f"xattr has {xa.shape[1]} columns, the basins have {nattr} attractors")
+        a = _m33(x2c)
+        b = _m33(np.eye(3) if x2xr is None else x2xr)
+        c = _m33(x2c if xr2c is None else xr2c)
+        w = np.zeros((3, 0), order="F") if ws is None else np.asfortranarray(ws, dtype=np.float64)
+        dm = None if domask is None else np.ascontiguousarray(domask, dtype=np.uint8)
+        mp = np.zeros(((lmax + 1) ** 2, nattr), order="F")
+        self._chk(self.lib.c2g_integrate_multipoles(
+            self.h, basins.h, C.c_int(int(fieldhandle)), C.c_int(int(lmax)), _p(xa, C.c_double),
+            None if dm is None else _p(dm, C.c_ubyte), C.c_int(int(isortho)), C.c_int(int(isortho_del)), _p(a, C.c_double),
+            _p(b, C.c_double), _p(c, C.c_double), C.c_int(w.shape[1]), _p(w, C.c_double) if w.shape[1] else None,
+            C.c_double(omega), _p(mp, C.c_double)))
+        return mp
 
     # ---- NCIPLOT ----
     def nci_range(self, nstep1):

@@ -739,20 +739,15 @@ int c2g_yt_integrate_impl(c2g_context* ctx, c2g_basins* res, int nprop, const in
   return C2G_OK;
 }
 
-extern "C" int c2g_yt_weights(c2g_basins* res, int idb, double* w) {
-  if (!res) return C2G_ERR_ARG;
+// weights of basin idb (yt_weights, yt@proc.f90:476-499) into a device array of nn doubles, on ctx->stream
+int c2g_yt_weights_device(c2g_basins* res, int idb, double* d_w) {
   c2g_context* ctx = res->ctx;
-  if (res->kind != 1) return ctx->fail(C2G_ERR_STATE, "c2g_yt_weights: not a YT result");
-  if (!res->has_map) return ctx->fail(C2G_ERR_STATE, "c2g_yt_weights: call c2g_basins_set_map first");
-  if (!w || idb < 1 || idb > res->nattr) return ctx->fail(C2G_ERR_ARG, "c2g_yt_weights: unknown basin %d", idb);
   YtState* S = yt_state(res);
   const long long nn = res->nn;
   const double* rho = ctx->grids[res->gridh].d;
   cudaStream_t st = ctx->stream;
-  DevBuf b_w;
-  C2G_CUDA(ctx, b_w.alloc(ctx, sizeof(double) * nn));
   ctx->prof_begin("yt_init_w");
-  k_init_w<<<ctx->nsm * 8, 256, 0, st>>>(nn, res->d_label, res->d_map, idb, b_w.as<double>());
+  k_init_w<<<ctx->nsm * 8, 256, 0, st>>>(nn, res->d_label, res->d_map, idb, d_w);
   ctx->prof_end();
   C2G_KERNEL_CHECK(ctx);
   if (S->nias > 0) {
@@ -763,14 +758,28 @@ extern "C" int c2g_yt_weights(c2g_basins* res, int idb, double* w) {
     const int* a_order = S->order;
     const int* a_lvl = S->lvl;
     int a_nl = S->nlevels;
-    double* a_w = b_w.as<double>();
+    double* a_w = d_w;
     void* args[] = {(void*)&S->P, (void*)&rho, (void*)&a_mask, (void*)&a_csum, (void*)&a_order, (void*)&a_lvl, (void*)&a_nl, (void*)&a_w};
     ctx->prof_begin("yt_sweep_down");
     C2G_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_sweep_down, dim3(blocks), dim3(256), args, 0, st));
     ctx->prof_end();
   }
-  C2G_CUDA(ctx, cudaMemcpyAsync(w, b_w.p, sizeof(double) * nn, cudaMemcpyDeviceToHost, st));
-  C2G_CUDA(ctx, cudaStreamSynchronize(st));
+  return C2G_OK;
+}
+
+extern "C" int c2g_yt_weights(c2g_basins* res, int idb, double* w) {
+  if (!res) return C2G_ERR_ARG;
+  c2g_context* ctx = res->ctx;
+  if (res->kind != 1) return ctx->fail(C2G_ERR_STATE, "c2g_yt_weights: not a YT result");
+  if (!res->has_map) return ctx->fail(C2G_ERR_STATE, "c2g_yt_weights: call c2g_basins_set_map first");
+  if (!w || idb < 1 || idb > res->nattr) return ctx->fail(C2G_ERR_ARG, "c2g_yt_weights: unknown basin %d", idb);
+  const long long nn = res->nn;
+  DevBuf b_w;
+  C2G_CUDA(ctx, b_w.alloc(ctx, sizeof(double) * nn));
+  int rc = c2g_yt_weights_device(res, idb, b_w.as<double>());
+  if (rc != C2G_OK) return rc;
+  C2G_CUDA(ctx, cudaMemcpyAsync(w, b_w.p, sizeof(double) * nn, cudaMemcpyDeviceToHost, ctx->stream));
+  C2G_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->prof_collect();
   return C2G_OK;
 }

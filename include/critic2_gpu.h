@@ -125,6 +125,21 @@ int c2g_basins_stats(c2g_basins* res, long long stats[8]);
 int c2g_integrate(c2g_context* ctx, c2g_basins* res, int nprop, const int* fieldhandles, double omega,
                   double* psum, double* vol);
 
+/* ---- INTEGRABLE id MULTIPOLES [lmax]: basin multipole moments (integration@proc.f90:1302-1361) ---- */
+/* mpole((lmax+1)^2, nattr) column-major, real regular solid harmonics in genrlm_real's order
+ * (tools_math@proc.f90:273-306: C00, C11, C10, S11, C22, C21, C20, S21, S22, ...):
+ *   Bader labels (:1338-1358): mpole(:,ix) = sum over the points of basin ix of rrlm(dv) * fint,
+ *   YT weights  (:1316-1336): mpole(:,m)  = sum over |w_m| >= 1e-15 of rrlm(dv) * fint * w_m, basins with
+ *                                           domask(m) == 0 (the reference's docelatom(icp(m))) are skipped;
+ *   dv = shortest(p/n - xattr(:,basin)), then * omega / ntot (:1360).  xattr(3,nattr) crystallographic.
+ * The cell arguments are what crystal%shortest reads (crystalmod@proc.f90:1056-1085): isortho, isortho_del, m_x2c,
+ * m_x2xr, m_xr2c and ws_ineighc(3,ws_nf) (Cartesian); the last four may be NULL / 0 when isortho != 0.
+ * domask may be NULL (all basins).  lmax <= 10 (the reference default is 5, systemmod@proc.f90:1014). */
+int c2g_integrate_multipoles(c2g_context* ctx, c2g_basins* res, int fieldhandle, int lmax, const double* xattr,
+                             const unsigned char* domask, int isortho, int isortho_del, const double x2c[9],
+                             const double x2xr[9], const double xr2c[9], int nws, const double* ws_ineighc,
+                             double omega, double* mpole);
+
 /* ---- YT: Yu-Trinkle weights (yt@proc.f90:77-211) ---- */
 /* vec(3,nvec), area(nvec): Voronoi-relevant grid steps and facet areas from grid3%init_geometry
  * (grid3mod@proc.f90:3197).  Maxima are returned in decreasing density (= reference discovery order). */

@@ -1361,6 +1361,201 @@ void orc_nci_rdg_fourier(const double* f, const double* fgrad, const double* fxx
       }
 }
 
+// ---------------------------------------------------------------------------
+// Multipoles of the basins: the `else` branch of intgrid_fields,
+// src/integration@proc.f90:1302-1361 (INTEGRABLE id MULTIPOLES [lmax]).
+// ---------------------------------------------------------------------------
+}  // extern "C"
+namespace {
+
+// crystal%shortest, src/crystalmod@proc.f90:1056-1085.  x (cryst.) -> shortest lattice-translated copy (Cartesian).
+// matmul(A,x)_i = A(i,1)x1 + A(i,2)x2 + A(i,3)x3, accumulated left to right; norm2 as sqrt of the sum of squares.
+struct OrcCell {
+  int isortho, isortho_del, nws;
+  const double *x2c, *x2xr, *xr2c, *ws;  // 3x3 column-major; ws(3,nws) Cartesian (ws_ineighc)
+};
+inline void matvec3(const double* m, const double* x, double* y) {
+  for (int i = 0; i < 3; i++) y[i] = m[i] * x[0] + m[i + 3] * x[1] + m[i + 6] * x[2];
+}
+inline void orc_shortest(const OrcCell& c, double x[3]) {
+  double t[3];
+  if (c.isortho) {
+    for (int i = 0; i < 3; i++) t[i] = x[i] - (double)std::lround(x[i]);
+    matvec3(c.x2c, t, x);
+    return;
+  }
+  matvec3(c.x2xr, x, t);
+  for (int i = 0; i < 3; i++) t[i] = t[i] - (double)std::lround(t[i]);
+  matvec3(c.xr2c, t, x);
+  double dist = std::sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+  if (!c.isortho_del) {
+    const double x0[3] = {x[0], x[1], x[2]};
+    for (int i = 0; i < c.nws; i++) {
+      const double xt[3] = {x0[0] + c.ws[3 * i], x0[1] + c.ws[3 * i + 1], x0[2] + c.ws[3 * i + 2]};
+      const double d = std::sqrt(xt[0] * xt[0] + xt[1] * xt[1] + xt[2] * xt[2]);
+      if (d < dist) {
+        x[0] = xt[0]; x[1] = xt[1]; x[2] = xt[2];
+        dist = d;
+      }
+    }
+  }
+}
+
+// tosphere, src/tools_math@proc.f90:381-406
+inline void orc_tosphere(const double v[3], double& r, double tp[2]) {
+  const double eps = 1e-14, pi = 3.14159265358979323846;
+  r = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+  tp[0] = tp[1] = 0.0;
+  if (r > eps) {
+    const double t1 = v[2] / r;
+    if (t1 >= 1.0) tp[0] = 0.0;
+    else if (t1 <= -1.0) tp[0] = pi;
+    else tp[0] = std::acos(t1);
+    if (std::fabs(v[0]) > eps || std::fabs(v[1]) > eps) tp[1] = std::atan2(v[1], v[0]);
+  }
+}
+
+// genylm, src/tools_math@proc.f90:314-377 (Masters & Richards-Dinger recursion), ylm(l*(l+1)+m), 0-based
+inline void orc_genylm(int lmax, const double tp[2], std::complex<double>* ylm) {
+  const double fourpi = 12.566370614359172954;
+  ylm[0] = 0.28209479177387814347;
+  if (lmax == 0) return;
+  std::vector<double> x(lmax + 1);
+  std::vector<std::complex<double>> z(lmax + 1);
+  const double sn = std::sin(tp[0]), cs = std::cos(tp[0]);
+  for (int m = 1; m <= lmax; m++) {
+    const double t1 = (double)m * tp[1];
+    z[m] = std::complex<double>(std::cos(t1), std::sin(t1));
+  }
+  for (int l = 1; l <= lmax; l++) {
+    x[l] = (l % 2 == 0) ? 1.0 : -1.0;
+    double dx = 0.0;
+    for (int m = l; m >= 1; m--) {
+      const double t1 = std::sqrt((double)((l + m) * (l - m + 1)));
+      x[m - 1] = -(sn * dx + (double)(2 * m) * cs * x[m]) / t1;
+      dx = sn * x[m] * t1;
+    }
+    double t1 = sn, sum = 0.0;
+    for (int m = 1; m <= l; m++) {
+      x[m] = t1 * x[m];
+      sum = sum + x[m] * x[m];
+      t1 = t1 * sn;
+    }
+    sum = 2.0 * sum + x[0] * x[0];
+    t1 = std::sqrt((double)(2 * l + 1) / (fourpi * sum));
+    const int lm0 = l * (l + 1);
+    ylm[lm0] = t1 * x[0];
+    for (int m = 1; m <= l; m++) {
+      const double a = t1 * x[m];  // t1*x(m)*z(m), left to right
+      ylm[lm0 + m] = std::complex<double>(a * z[m].real(), a * z[m].imag());
+      ylm[lm0 - m] = std::conj(ylm[lm0 + m]);
+      if (m % 2 != 0) ylm[lm0 - m] = -ylm[lm0 - m];
+    }
+  }
+}
+
+// r**l with an integer exponent as gfortran evaluates it (libgcc __powidf2: square and multiply)
+inline double orc_powi(double x, int m) {
+  unsigned n = (unsigned)m;
+  double y = (n % 2) ? x : 1.0;
+  while (n >>= 1) {
+    x = x * x;
+    if (n % 2) y *= x;
+  }
+  return y;
+}
+
+// genrlm_real, src/tools_math@proc.f90:273-306
+inline void orc_genrlm_real(int lmax, double r, const double tp[2], double* rrlm, std::complex<double>* rlm) {
+  const double pi = 3.14159265358979323846, sh = 1.0 / std::sqrt(2.0);
+  const std::complex<double> img(0.0, 1.0);
+  orc_genylm(lmax, tp, rlm);
+  for (int l = 0; l <= lmax; l++) {
+    const int imin = l * l, imax = (l + 1) * (l + 1);
+    const double s = std::sqrt(4.0 * pi / (double)(2 * l + 1)), rl = orc_powi(r, l);
+    for (int i = imin; i < imax; i++) rlm[i] = std::complex<double>(rlm[i].real() * s * rl, rlm[i].imag() * s * rl);
+    int ip = imin + l;
+    rrlm[ip] = rlm[ip].real();
+    for (int m = 1; m <= l; m++) {
+      ip = imin + l + m;
+      const int im = imin + l - m;
+      const double iphas = (m % 2 == 0) ? 1.0 : -1.0;
+      const std::complex<double> a = iphas * rlm[ip] + rlm[im];
+      const std::complex<double> b = -iphas * img * rlm[ip] + img * rlm[im];
+      rrlm[im] = sh * a.real();
+      rrlm[ip] = sh * b.real();
+    }
+  }
+}
+
+}  // namespace
+extern "C" {
+
+// Bader / isosurface branch (integration@proc.f90:1338-1358): mpole(:,ix) += rrlm(p/n - xattr(:,ix)) * fint(p),
+// loop order i1, i2, i3 (i3 innermost), then mpole * omega / ntot (:1360).  idg == 0 (points of a discarded
+// attractor) are skipped; the reference would read xattr(:,0) there.  mpole((lmax+1)^2, nattr) column-major.
+void orc_multipoles_bader(const int* idg, const int* n, int nattr, const double* xattr, int lmax, const double* fint,
+                          int isortho, int isortho_del, const double* x2c, const double* x2xr, const double* xr2c, int nws,
+                          const double* ws, double omega, double* mpole) {
+  const OrcCell cell{isortho, isortho_del, nws, x2c, x2xr, xr2c, ws};
+  const int nlm = (lmax + 1) * (lmax + 1);
+  std::vector<double> rrlm(nlm);
+  std::vector<std::complex<double>> rlm(nlm);
+  for (size_t e = 0; e < (size_t)nlm * nattr; e++) mpole[e] = 0.0;
+  for (int i1 = 0; i1 < n[0]; i1++)
+    for (int i2 = 0; i2 < n[1]; i2++)
+      for (int i3 = 0; i3 < n[2]; i3++) {
+        const size_t q = (size_t)i1 + (size_t)n[0] * ((size_t)i2 + (size_t)n[1] * i3);
+        const int ix = idg[q];
+        if (ix < 1 || ix > nattr) continue;
+        double dv[3] = {(double)i1 / (double)n[0] - xattr[3 * (ix - 1)], (double)i2 / (double)n[1] - xattr[3 * (ix - 1) + 1],
+                        (double)i3 / (double)n[2] - xattr[3 * (ix - 1) + 2]};
+        orc_shortest(cell, dv);
+        double r, tp[2];
+        orc_tosphere(dv, r, tp);
+        orc_genrlm_real(lmax, r, tp, rrlm.data(), rlm.data());
+        double* out = mpole + (size_t)nlm * (ix - 1);
+        for (int e = 0; e < nlm; e++) out[e] = out[e] + rrlm[e] * fint[q];
+      }
+  const double ntot = (double)n[0] * (double)n[1] * (double)n[2];
+  for (size_t e = 0; e < (size_t)nlm * nattr; e++) mpole[e] = mpole[e] * omega / ntot;
+}
+
+// YT branch (integration@proc.f90:1316-1336) for ONE basin: w = yt_weights(idb); points with |w| < 1e-15 are
+// skipped; mpole_m += rrlm(p/n - xattr_m) * fint * w; scaled by omega/ntot like :1360.  mpole_m((lmax+1)^2).
+void orc_multipoles_weighted(const double* w, const int* n, const double* xattr_m, int lmax, const double* fint, int isortho,
+                             int isortho_del, const double* x2c, const double* x2xr, const double* xr2c, int nws,
+                             const double* ws, double omega, double* mpole_m) {
+  const OrcCell cell{isortho, isortho_del, nws, x2c, x2xr, xr2c, ws};
+  const int nlm = (lmax + 1) * (lmax + 1);
+  std::vector<double> rrlm(nlm);
+  std::vector<std::complex<double>> rlm(nlm);
+  for (int e = 0; e < nlm; e++) mpole_m[e] = 0.0;
+  for (int i1 = 0; i1 < n[0]; i1++)
+    for (int i2 = 0; i2 < n[1]; i2++)
+      for (int i3 = 0; i3 < n[2]; i3++) {
+        const size_t q = (size_t)i1 + (size_t)n[0] * ((size_t)i2 + (size_t)n[1] * i3);
+        if (std::fabs(w[q]) < 1e-15) continue;
+        double dv[3] = {(double)i1 / (double)n[0] - xattr_m[0], (double)i2 / (double)n[1] - xattr_m[1],
+                        (double)i3 / (double)n[2] - xattr_m[2]};
+        orc_shortest(cell, dv);
+        double r, tp[2];
+        orc_tosphere(dv, r, tp);
+        orc_genrlm_real(lmax, r, tp, rrlm.data(), rlm.data());
+        for (int e = 0; e < nlm; e++) mpole_m[e] = mpole_m[e] + rrlm[e] * fint[q] * w[q];
+      }
+  const double ntot = (double)n[0] * (double)n[1] * (double)n[2];
+  for (int e = 0; e < nlm; e++) mpole_m[e] = mpole_m[e] * omega / ntot;
+}
+
+// one evaluation of genrlm_real(lmax, tosphere(v)) for the known-answer tests
+void orc_rlm_real(const double* v, int lmax, double* rrlm) {
+  double r, tp[2];
+  orc_tosphere(v, r, tp);
+  std::vector<std::complex<double>> rlm((lmax + 1) * (lmax + 1));
+  orc_genrlm_real(lmax, r, tp, rrlm, rlm.data());
+}
+
 int orc_num_threads() {
 #ifdef _OPENMP
   return omp_get_max_threads();

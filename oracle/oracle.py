@@ -202,6 +202,59 @@ def integrate_yt(d: YtData, fields, omega):
     return vol, psum
 
 
+class Cell:
+    """What crystal%shortest reads (crystalmod@proc.f90:1056-1085): isortho, isortho_del, m_x2c, m_x2xr, m_xr2c
+    and the Cartesian Wigner-Seitz neighbour vectors ws_ineighc(3, ws_nf)."""
+
+    def __init__(self, x2c, x2xr=None, xr2c=None, ws=None, isortho=None, isortho_del=False):
+        self.x2c = np.asarray(x2c, dtype=np.float64)
+        off = self.x2c - np.diag(np.diag(self.x2c))
+        self.isortho = bool(np.all(off == 0.0)) if isortho is None else bool(isortho)
+        self.isortho_del = bool(isortho_del)
+        self.x2xr = np.eye(3) if x2xr is None else np.asarray(x2xr, dtype=np.float64)
+        self.xr2c = self.x2c.copy() if xr2c is None else np.asarray(xr2c, dtype=np.float64)
+        self.ws = np.zeros((3, 0), order="F") if ws is None else np.asfortranarray(ws, dtype=np.float64)
+
+    def args(self):
+        self._keep = (_m33(self.x2c), _m33(self.x2xr), _m33(self.xr2c), self.ws)
+        a, b, c, w = self._keep
+        return (C.c_int(int(self.isortho)), C.c_int(int(self.isortho_del)), _p(a, C.c_double), _p(b, C.c_double),
+                _p(c, C.c_double), C.c_int(w.shape[1]), _p(w, C.c_double))
+
+
+def multipoles_bader(idg, xattr, lmax, fint, cell: Cell, omega):
+    """mpole[(lmax+1)^2, nattr] of integration@proc.f90:1338-1360 (Bader / isosurface branch)."""
+    idg = _i32(idg)
+    fint = _f64(fint)
+    n = np.array(idg.shape, dtype=np.int32)
+    xattr = _f64(np.asarray(xattr, dtype=np.float64).reshape(3, -1))
+    nattr = xattr.shape[1]
+    mp = np.zeros(((lmax + 1) ** 2, nattr), order="F")
+    lib().orc_multipoles_bader(_p(idg, C.c_int), _p(n, C.c_int), C.c_int(nattr), _p(xattr, C.c_double), C.c_int(lmax),
+                               _p(fint, C.c_double), *cell.args(), C.c_double(omega), _p(mp, C.c_double))
+    return mp
+
+
+def multipoles_weighted(w, xattr_m, lmax, fint, cell: Cell, omega):
+    """One column mpole(:, m) of the YT branch (integration@proc.f90:1316-1336, :1360) from the weights of basin m."""
+    w = _f64(w)
+    fint = _f64(fint)
+    n = np.array(w.shape, dtype=np.int32)
+    xm = np.ascontiguousarray(xattr_m, dtype=np.float64)
+    mp = np.zeros((lmax + 1) ** 2)
+    lib().orc_multipoles_weighted(_p(w, C.c_double), _p(n, C.c_int), _p(xm, C.c_double), C.c_int(lmax),
+                                  _p(fint, C.c_double), *cell.args(), C.c_double(omega), _p(mp, C.c_double))
+    return mp
+
+
+def rlm_real(v, lmax):
+    """genrlm_real(lmax, tosphere(v)) (tools_math@proc.f90:273-306, :381-406)."""
+    v = np.ascontiguousarray(v, dtype=np.float64)
+    out = np.zeros((lmax + 1) ** 2)
+    lib().orc_rlm_real(_p(v, C.c_double), C.c_int(lmax), _p(out, C.c_double))
+    return out
+
+
 def tricubic_matrix():
     c = np.zeros((64, 64), order="F")
     lib().orc_tricubic_matrix(_p(c, C.c_double))
