@@ -134,7 +134,7 @@ struct c2g_context {
 // result of an assignment (BADER or YT), device resident
 struct c2g_basins {
   c2g_context* ctx = nullptr;
-  int kind = 0;  // 0 = bader, 1 = yt
+  int kind = 0;  // 0 = bader, 1 = yt, 2 = isosurface regions (plain labels like bader, -1 = below the contour value)
   int gridh = -1;
   int n[3] = {0, 0, 0};
   long long nn = 0;

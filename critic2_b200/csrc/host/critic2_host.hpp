@@ -47,6 +47,10 @@ struct grid3 {
 struct system {
   double m_x2c[9] = {0};       // crystallographic -> Cartesian, column-major (crystalmod)
   double omega = 0.0;          // cell volume
+  // what crystal%shortest reads (crystalmod.f90:173-209, crystalmod@proc.f90:1056-1085); filled by set_cell
+  bool isortho = false, isortho_del = false;
+  double m_x2xr[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, m_xr2c[9] = {0};
+  std::vector<double> ws_ineighc;  // (3,ws_nf) Cartesian
   std::vector<double> xat;     // atoms (nuclear CPs of the reference field), crystallographic, (3,nat)
   grid3 grid;                  // sy%f(iref)%grid
   int nat() const { return (int)(xat.size() / 3); }
@@ -86,6 +90,10 @@ void yt_integrate(system& s, basindat& bas);
 // integration@proc.f90:1170-1391: res[k].psum(i) = integral of fint[k] over basin i; vol(i) = basin volume.
 void intgrid_fields(const system& s, const basindat& bas, const std::vector<const double*>& fint,
                     std::vector<int_result>& res, std::vector<double>& vol);
+// integration@proc.f90:1302-1361 (INTEGRABLE ... MULTIPOLES): mpole((lmax+1)^2, nattr), genrlm_real's order; docelatom
+// (may be empty) is the per-attractor mask of the YT branch (:1318).
+void intgrid_multipoles(const system& s, const basindat& bas, const double* fint, int lmax,
+                        const std::vector<unsigned char>& docelatom, std::vector<double>& mpole);
 // yt@proc.f90:476-499 (yt_weights with idb): dense weight field of one basin.
 void yt_weights(const basindat& bas, int idb, std::vector<double>& w);
 // nci@proc.f90:543-605, grid interpolation mode on the field's own lattice:

@@ -36,6 +36,11 @@ int main(int argc, char** argv) {
     for (int i = 0; i < bas.nattr; i++) std::printf("%s%.17g", i ? ", " : "", res[0].psum[i]);
     std::printf("], \"vol\": [");
     for (int i = 0; i < bas.nattr; i++) std::printf("%s%.17g", i ? ", " : "", vol[i]);
+    // INTEGRABLE 1 MULTIPOLES 2
+    std::vector<double> mpole;
+    c2h::intgrid_multipoles(s, bas, bas.f.data(), 2, {}, mpole);
+    std::printf("], \"mpole_lmax2\": [");
+    for (size_t i = 0; i < mpole.size(); i++) std::printf("%s%.17g", i ? ", " : "", mpole[i]);
     std::printf("]}\n");
     // error behaviour: a bad call must raise like ferror(...,faterr)
     bool raised = false;

@@ -240,7 +240,7 @@ extern "C" int c2g_integrate(c2g_context* ctx, c2g_basins* res, int nprop, const
     const int np = std::min(4, nprop - k0);
     const double* fp[4] = {nullptr, nullptr, nullptr, nullptr};
     for (int p = 0; p < np; p++) fp[p] = ctx->grids[fieldhandles[k0 + p]].d + plane * res->zlo;
-    rc = c2g_launch_basin_reduce(ctx, nnl, res->d_label, LABEL_MASK, np > 0 ? np : 0, fp, nmax, d_sums + (size_t)k0 * nmax,
+    rc = c2g_launch_basin_reduce(ctx, nnl, res->d_label, res->kind == 0 ? LABEL_MASK : -1, np > 0 ? np : 0, fp, nmax, d_sums + (size_t)k0 * nmax,
                                  first ? d_counts : nullptr);
     first = false;
   }

@@ -183,7 +183,8 @@ __global__ void __launch_bounds__(MP_THREADS) k_multipoles(const __grid_constant
           w = __ldg(a.w + i);
           lab = fabs(w) < 1e-15 ? -1 : a.idb - 1;
         } else {
-          lab = __ldg(a.map + (__ldg(a.label + i) & a.mask)) - 1;
+          const int l = __ldg(a.label + i) & a.mask;  // isosurface regions: -1 below the contour value
+          lab = l >= 0 ? __ldg(a.map + l) - 1 : -1;
         }
         f = __ldg(a.fint + i);
       }
@@ -264,12 +265,12 @@ extern "C" int c2g_integrate_multipoles(c2g_context* ctx, c2g_basins* res, int f
   a.map = res->d_map;
   const size_t plane = (size_t)res->n[0] * res->n[1];
 
-  if (res->kind == 0) {
-    // Bader labels: this rank's z-slab, partial moments all-reduced below
+  if (res->kind != 1) {
+    // Bader labels (or isosurface regions): this rank's z-slab, partial moments all-reduced below
     a.z0 = (unsigned)res->zlo;
     a.nnl = (unsigned)(plane * (size_t)(res->zhi - res->zlo));
     a.label = res->d_label;
-    a.mask = 0x7fffffff;
+    a.mask = res->kind == 0 ? 0x7fffffff : -1;
     a.fint = g.d + plane * res->zlo;
     if (a.nnl > 0) {
       ctx->prof_begin("multipoles");

@@ -783,3 +783,173 @@ extern "C" int c2g_yt_weights(c2g_basins* res, int idb, double* w) {
   ctx->prof_collect();
   return C2G_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// ISOSURFACE regions: yt_isosurface, src/yt@proc.f90:233-390.
+//
+// The reference sweeps the sorted grid once more: a point at or above the contour value takes the region of its
+// higher neighbours when they agree, else the smallest of their regions, and records imap(other) = smallest for
+// every other one -- overwriting what an earlier contact stored (:319-331).  Read as a whole:
+//   region(i) = min over the higher neighbours of region(.) = the smallest discovery number among the maxima that
+//               i reaches on ascending paths.  Interior points of the YT partition reach one maximum (their YT
+//               label); the IAS points take ONE downhill min-sweep over the Kahn levels that c2g_yt_build kept.
+//   imap(b)   = the smallest region at the LAST contact (lowest (rho, index)) at which b was not the smallest:
+//               three passes of atomicMin over the IAS points (density key, index, then the write).
+// The chains of imap are followed on the host exactly like :337-351, surviving regions keep their discovery numbers
+// and bas%nattr is the number of survivors (the reference's behaviour, not a renumbering).
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+__device__ __forceinline__ unsigned long long rho_key(double r) {  // order-preserving map of a double onto u64
+  const unsigned long long b = (unsigned long long)__double_as_longlong(r);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+__global__ void __launch_bounds__(256) k_iso_sweep(const __grid_constant__ YtParams P, const unsigned* __restrict__ mask,
+                                                   const int* __restrict__ order, const int* __restrict__ lvl, int nlevels,
+                                                   int* __restrict__ lab) {
+  cg::grid_group grid = cg::this_grid();
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  for (int L = nlevels - 1; L >= 0; L--) {
+    const int lo = lvl[L], hi = lvl[L + 1];
+    for (int q = lo + tid; q < hi; q += nth) {
+      const int i = order[q];
+      const Pt p = unlin(P, i);
+      int mn = 0x7fffffff;
+      unsigned hm = mask[i];
+      while (hm) {
+        const int k = __ffs(hm) - 1;
+        hm &= hm - 1;
+        mn = min(mn, __ldcg(lab + nbr(P, p, k)));
+      }
+      lab[i] = mn;
+    }
+    grid.sync();
+  }
+}
+
+// contacts: IAS points at or above isov whose higher neighbours carry different regions
+template <int PASS>
+__global__ void __launch_bounds__(256) k_iso_contacts(const __grid_constant__ YtParams P, const double* __restrict__ rho,
+                                                      const unsigned* __restrict__ mask, const int* __restrict__ order, int nias,
+                                                      double isov, const int* __restrict__ lab,
+                                                      unsigned long long* __restrict__ minkey, int* __restrict__ minidx,
+                                                      int* __restrict__ imap) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nias) return;
+  const int i = order[q];
+  const double ri = __ldg(rho + i);
+  if (ri < isov) return;
+  const Pt p = unlin(P, i);
+  const int imin = lab[i];  // = min over the higher neighbours
+  const unsigned long long key = rho_key(ri);
+  unsigned hm = mask[i];
+  while (hm) {
+    const int k = __ffs(hm) - 1;
+    hm &= hm - 1;
+    const int b = lab[nbr(P, p, k)];
+    if (b == imin) continue;
+    if (PASS == 0) atomicMin(minkey + b, key);
+    if (PASS == 1 && minkey[b] == key) atomicMin(minidx + b, i);
+    if (PASS == 2 && minkey[b] == key && minidx[b] == i) imap[b] = imin + 1;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_iso_final(long long nn, const double* __restrict__ rho, double isov, int* __restrict__ lab) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nn; i += stride)
+    if (__ldg(rho + i) < isov) lab[i] = -1;
+}
+
+}  // namespace
+
+extern "C" int c2g_yt_isosurface(c2g_basins* yt, double isov, int* nraw_out, int* nattr_out, c2g_basins** res_out) {
+  if (!yt) return C2G_ERR_ARG;
+  c2g_context* ctx = yt->ctx;
+  if (yt->kind != 1 || !yt->yt) return ctx->fail(C2G_ERR_STATE, "c2g_yt_isosurface: not a YT result (call c2g_yt_build on the field first)");
+  if (!nraw_out || !nattr_out || !res_out) return ctx->fail(C2G_ERR_ARG, "c2g_yt_isosurface: null argument");
+  if (!(isov == isov)) return ctx->fail(C2G_ERR_ARG, "c2g_yt_isosurface: the contour value is NaN");
+  if (!ctx->grids[yt->gridh].used) return ctx->fail(C2G_ERR_STATE, "c2g_yt_isosurface: the field was freed");
+  YtState* S = yt_state(yt);
+  const long long nn = yt->nn;
+  const double* rho = ctx->grids[yt->gridh].d;
+  cudaStream_t st = ctx->stream;
+
+  // regions before merging = maxima at or above the contour value; they lead the (rho, index)-descending list
+  const int nmax = yt->nmax;
+  std::vector<double> mr(nmax);
+  {
+    DevBuf b_l, b_r;
+    C2G_CUDA(ctx, b_l.alloc(ctx, sizeof(int) * nmax));
+    C2G_CUDA(ctx, b_r.alloc(ctx, sizeof(double) * nmax));
+    C2G_CUDA(ctx, cudaMemcpyAsync(b_l.p, yt->max_lin.data(), sizeof(int) * nmax, cudaMemcpyHostToDevice, st));
+    k_gather<<<c2g_blocks_for(nmax, 256), 256, 0, st>>>(nmax, b_l.as<int>(), rho, b_r.as<double>());
+    C2G_KERNEL_CHECK(ctx);
+    C2G_CUDA(ctx, cudaMemcpyAsync(mr.data(), b_r.p, sizeof(double) * nmax, cudaMemcpyDeviceToHost, st));
+    C2G_CUDA(ctx, cudaStreamSynchronize(st));
+  }
+  int nraw = 0;
+  while (nraw < nmax && !(mr[nraw] < isov)) nraw++;
+
+  c2g_basins* res = new c2g_basins();
+  res->ctx = ctx; res->kind = 2; res->gridh = yt->gridh;
+  res->n[0] = yt->n[0]; res->n[1] = yt->n[1]; res->n[2] = yt->n[2]; res->nn = nn;
+  res->zlo = 0; res->zhi = yt->n[2];
+  res->nmax = nraw;
+  res->max_lin.assign(yt->max_lin.begin(), yt->max_lin.begin() + nraw);
+  struct Guard { c2g_basins* r; bool ok = false; ~Guard() { if (!ok) c2g_basins_free(r); } } guard{res};
+  C2G_CUDA(ctx, c2g_alloc(ctx, (void**)&res->d_label, sizeof(int) * nn));
+  int* lab = res->d_label;
+  C2G_CUDA(ctx, cudaMemcpyAsync(lab, yt->d_label, sizeof(int) * nn, cudaMemcpyDeviceToDevice, st));
+  std::vector<int> imap(std::max(nraw, 1), 0);
+  if (S->nias > 0 && nraw > 0) {
+    int blocks = 0, rc;
+    if ((rc = coop_grid(ctx, k_iso_sweep, 256, &blocks)) != C2G_OK) return rc;
+    const unsigned* a_mask = S->mask;
+    const int* a_order = S->order;
+    const int* a_lvl = S->lvl;
+    int a_nl = S->nlevels;
+    void* args[] = {(void*)&S->P, (void*)&a_mask, (void*)&a_order, (void*)&a_lvl, (void*)&a_nl, (void*)&lab};
+    ctx->prof_begin("iso_sweep");
+    C2G_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_iso_sweep, dim3(blocks), dim3(256), args, 0, st));
+    ctx->prof_end();
+    DevBuf b_key, b_idx, b_imap;
+    C2G_CUDA(ctx, b_key.alloc(ctx, sizeof(unsigned long long) * nraw));
+    C2G_CUDA(ctx, b_idx.alloc(ctx, sizeof(int) * nraw));
+    C2G_CUDA(ctx, b_imap.alloc(ctx, sizeof(int) * nraw));
+    C2G_CUDA(ctx, cudaMemsetAsync(b_key.p, 0xff, sizeof(unsigned long long) * nraw, st));
+    C2G_CUDA(ctx, cudaMemsetAsync(b_idx.p, 0x7f, sizeof(int) * nraw, st));
+    C2G_CUDA(ctx, cudaMemsetAsync(b_imap.p, 0, sizeof(int) * nraw, st));
+    const int nb = c2g_blocks_for(S->nias, 256);
+    ctx->prof_begin("iso_contacts");
+    k_iso_contacts<0><<<nb, 256, 0, st>>>(S->P, rho, S->mask, S->order, S->nias, isov, lab, b_key.as<unsigned long long>(), b_idx.as<int>(), b_imap.as<int>());
+    k_iso_contacts<1><<<nb, 256, 0, st>>>(S->P, rho, S->mask, S->order, S->nias, isov, lab, b_key.as<unsigned long long>(), b_idx.as<int>(), b_imap.as<int>());
+    k_iso_contacts<2><<<nb, 256, 0, st>>>(S->P, rho, S->mask, S->order, S->nias, isov, lab, b_key.as<unsigned long long>(), b_idx.as<int>(), b_imap.as<int>());
+    ctx->prof_end(3);
+    C2G_KERNEL_CHECK(ctx);
+    C2G_CUDA(ctx, cudaMemcpyAsync(imap.data(), b_imap.p, sizeof(int) * nraw, cudaMemcpyDeviceToHost, st));
+    C2G_CUDA(ctx, cudaStreamSynchronize(st));
+  }
+  ctx->prof_begin("iso_final");
+  k_iso_final<<<ctx->nsm * 8, 256, 0, st>>>(nn, rho, isov, lab);
+  ctx->prof_end();
+  C2G_KERNEL_CHECK(ctx);
+  // :337-351 -- follow the chains; survivors keep their numbers, nattr = number of survivors
+  std::vector<int> map(std::max(nraw, 1), 0);
+  int nattr = 0;
+  for (int i = 1; i <= nraw; i++) {
+    int r = i;
+    if (imap[i - 1] == 0) nattr++;
+    else
+      while (imap[r - 1] != 0) r = imap[r - 1];
+    map[i - 1] = r;
+  }
+  int rc = c2g_basins_set_map(res, nraw, map.data());
+  if (rc != C2G_OK) return rc;
+  ctx->prof_collect();
+  guard.ok = true;
+  *nraw_out = nraw;
+  *nattr_out = nattr;
+  *res_out = res;
+  return C2G_OK;
+}

@@ -12,7 +12,7 @@ module critic2_gpu
   private
 
   public :: gpu_enabled, gpu_init, gpu_end
-  public :: gpu_bader_integrate, gpu_yt_integrate, gpu_integrate_fields, gpu_nci_rdg
+  public :: gpu_bader_integrate, gpu_yt_integrate, gpu_integrate_fields, gpu_integrate_multipoles, gpu_nci_rdg
 
   logical :: gpu_enabled = .false.        !< set by gpu_init (environment variable CRITIC2_GPU=1)
   type(c_ptr) :: ctx = c_null_ptr         !< c2g_context
@@ -106,6 +106,17 @@ module critic2_gpu
        real(c_double) :: psum(*), vol(*)
        integer(c_int) :: c2g_integrate
      end function c2g_integrate
+     function c2g_integrate_multipoles(ctx,res,fieldhandle,lmax,xattr,domask,isortho,isortho_del,x2c,x2xr,xr2c,&
+        nws,ws_ineighc,omega,mpole) bind(c,name="c2g_integrate_multipoles")
+       import :: c_int, c_ptr, c_double, c_signed_char
+       type(c_ptr), value :: ctx, res
+       integer(c_int), value :: fieldhandle, lmax, isortho, isortho_del, nws
+       real(c_double) :: xattr(3,*), x2c(3,3), x2xr(3,3), xr2c(3,3), ws_ineighc(3,*)
+       integer(c_signed_char) :: domask(*)
+       real(c_double), value :: omega
+       real(c_double) :: mpole(*)
+       integer(c_int) :: c2g_integrate_multipoles
+     end function c2g_integrate_multipoles
      function c2g_nci_rdg(ctx,handle,x0,xmat,nstep,c2x,x2c,c2xl,nnuc,nuc,crho,cgrad) bind(c,name="c2g_nci_rdg")
        import :: c_int, c_ptr, c_double
        type(c_ptr), value :: ctx
@@ -346,6 +357,41 @@ contains
        call check(c2g_grid_free(ctx,h(k)),"gpu_integrate_fields")
     end do
   end subroutine gpu_integrate_fields
+
+  !> GPU body of the multipole branch of intgrid_fields (src/integration@proc.f90:1302-1361): replaces both the
+  !> YT loop over basins (:1316-1336) and the Bader/isosurface loop under omp critical (:1338-1358), and the final
+  !> scaling (:1360).  fint is the integrand grid of property k; mpole((lmax+1)**2,bas%nattr) = res(k)%mpole.
+  subroutine gpu_integrate_multipoles(c,bas,lmax,fint,mpole)
+    use crystalmod, only: crystal
+    use types, only: basindat
+    type(crystal), intent(in) :: c
+    type(basindat), intent(in) :: bas
+    integer, intent(in) :: lmax
+    real*8, intent(in) :: fint(:,:,:)
+    real*8, intent(out) :: mpole(:,:)
+    integer(c_int) :: h, n(3), nws
+    integer(c_signed_char) :: domask(max(bas%nattr,1))
+    real*8 :: wsdum(3,1)
+    integer :: m
+
+    n = int(bas%n,c_int)
+    do m = 1, bas%nattr   ! bas%docelatom(bas%icp(m)) of :1318; the Bader branch does not look at it
+       domask(m) = merge(1_c_signed_char,0_c_signed_char,bas%docelatom(bas%icp(m)))
+    end do
+    call check(c2g_grid_upload(ctx,fint,n,h),"gpu_integrate_multipoles")
+    nws = 0
+    if (allocated(c%ws_ineighc)) nws = int(c%ws_nf,c_int)
+    if (nws > 0) then
+       call check(c2g_integrate_multipoles(ctx,basins,h,int(lmax,c_int),bas%xattr,domask,&
+          merge(1_c_int,0_c_int,c%isortho),merge(1_c_int,0_c_int,c%isortho_del),c%m_x2c,c%m_x2xr,c%m_xr2c,&
+          nws,c%ws_ineighc,c%omega,mpole),"gpu_integrate_multipoles")
+    else
+       call check(c2g_integrate_multipoles(ctx,basins,h,int(lmax,c_int),bas%xattr,domask,&
+          merge(1_c_int,0_c_int,c%isortho),merge(1_c_int,0_c_int,c%isortho_del),c%m_x2c,c%m_x2xr,c%m_xr2c,&
+          0_c_int,wsdum,c%omega,mpole),"gpu_integrate_multipoles")
+    end if
+    call check(c2g_grid_free(ctx,h),"gpu_integrate_multipoles")
+  end subroutine gpu_integrate_multipoles
 
   !> GPU body of the nciplot loop (src/nci@proc.f90:540-606), grid interpolation mode, no fragments.
   subroutine gpu_nci_rdg(f,x0,xmat,nstep,m_c2x,m_x2c,c2xl,nuc,crho,cgrad)

@@ -153,6 +153,17 @@ int c2g_yt_weights(c2g_basins* res, int idb, double* w);
 /* statistics: [0] IAS points, [1] flux records (sum of nhi over IAS points), [2] sweep levels */
 /* (use c2g_basins_stats) */
 
+/* ---- ISOSURFACE: regions of f >= isov (yt_isosurface, yt@proc.f90:233-390) ---- */
+/* yt: the result of c2g_yt_build on the field (its stencil, maxima order and sweep levels are reused).  Returns a new
+ * c2g_basins whose labels are the reference's bas%idg: 0 below the contour value, else the region id -- regions that
+ * touch are merged onto the smaller id through imap exactly like :319-351, INCLUDING the reference's behaviour that
+ * a later contact overwrites imap(b) and that surviving regions keep their discovery numbers.  nraw = regions before
+ * merging (ids run up to nraw), nattr = survivors (the reference's final bas%nattr); c2g_basins_maxima gives the
+ * nraw regional maxima in discovery order (bas%xattr = its first nattr columns, :359).  The map is already set:
+ * c2g_basins_labels, c2g_integrate (plain sums like the Bader branch, ids 1..nraw) and c2g_integrate_multipoles work on
+ * the result.  A DISCARD expression (:304-311) is evaluated by the host parser and is not supported here. */
+int c2g_yt_isosurface(c2g_basins* yt, double isov, int* nraw, int* nattr, c2g_basins** res);
+
 /* ---- NCIPLOT: reduced density gradient loop (nci@proc.f90:543-605, grid mode) ---- */
 /* x0(3) Cartesian origin, xmat(3,3) Cartesian step vectors, nstep(3); c2x/x2c crystal matrices,
  * c2xl grid matrix (grid3mod.f90 c2xl); nnuc nuclei (Cartesian, 3 x nnuc) for the zero-gradient-at-

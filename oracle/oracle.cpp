@@ -765,6 +765,83 @@ int orc_yt_integrate(const double* f, const int* n, int nvec, const int* vec, co
   return 0;
 }
 
+// ---------------------------------------------------------------------------
+// yt_isosurface, src/yt@proc.f90:233-390 (ISOSURFACE keyword): regions of the super-level set f >= isov under the
+// Voronoi-stencil connectivity, numbered like the reference does -- including its two quirks:
+//  * imap(b) is OVERWRITTEN by every later contact of region b (:327-331), so an earlier merge of b can be lost;
+//  * the surviving regions keep their discovery numbers (:337-351: no renumbering), while bas%nattr becomes the
+//    NUMBER of survivors and bas%xattr is cut to that many columns (:359).
+// The DISCARD expression (:304-311) is not restated: it is evaluated by the host's expression parser.
+// Out: idg(n1,n2,n3) spatial region ids (0 below isov), nraw = regions before merging (bas%nattr at :334),
+// nattr = survivors, xattr(3,nraw) = coordinates of every regional maximum in discovery order.
+// ---------------------------------------------------------------------------
+int orc_yt_isosurface(const double* f, const int* n, int nvec, const int* vec, double isov, int stable, int* idg, int* nraw,
+                      int* nattr, double* xattr, int maxattr) {
+  const int n1 = n[0], n2 = n[1], n3 = n[2];
+  const long nn = (long)n1 * n2 * n3;
+  const double* g = f;
+  std::vector<int> io(nn), iio(nn);
+  for (long i = 0; i < nn; i++) io[i] = (int)i + 1;
+  if (stable) {
+    std::stable_sort(io.begin(), io.end(), [&](int a, int b) { return g[a - 1] < g[b - 1]; });
+  } else {
+    if (orc_qcksort_r8(g, io.data(), 1, (int)nn) != 0) return -1;  // (:276-280)
+  }
+  for (long i = 0; i < nn; i++) iio[io[i] - 1] = (int)i + 1;
+  std::vector<int> ibasin(nn, 0), ihi(nvec), imap;
+  imap.reserve(1024);
+  int na = 0;
+  auto modulo = [](int a, int b) { int r = a % b; return r < 0 ? r + b : r; };
+  for (long ii = nn; ii >= 1; ii--) {  // (:295-333)
+    const int i = io[ii - 1];
+    if (g[i - 1] < isov) continue;
+    const int k0 = i - 1;
+    const int ib[3] = {k0 % n1, (k0 / n1) % n2, (k0 / (n1 * n2)) % n3};
+    int nhi = 0;
+    for (int k = 0; k < nvec; k++) {
+      const int j = modulo(ib[0] + vec[3 * k], n1) + n1 * (modulo(ib[1] + vec[3 * k + 1], n2) + n2 * modulo(ib[2] + vec[3 * k + 2], n3)) + 1;
+      const int jj = iio[j - 1];
+      if (jj > ii) ihi[nhi++] = jj;
+    }
+    if (nhi == 0) {
+      if (na + 1 > maxattr) return -2;
+      na++;
+      imap.push_back(0);
+      ibasin[ii - 1] = na;
+      xattr[3 * (na - 1)] = (double)ib[0] / n1;
+      xattr[3 * (na - 1) + 1] = (double)ib[1] / n2;
+      xattr[3 * (na - 1) + 2] = (double)ib[2] / n3;
+    } else {
+      bool interior = true;
+      for (int k = 1; k < nhi; k++) interior = interior && (ibasin[ihi[k] - 1] == ibasin[ihi[0] - 1]);
+      if (interior) {
+        ibasin[ii - 1] = ibasin[ihi[0] - 1];
+      } else {
+        int imin = ibasin[ihi[0] - 1];
+        for (int k = 1; k < nhi; k++) imin = std::min(imin, ibasin[ihi[k] - 1]);
+        ibasin[ii - 1] = imin;
+        for (int k = 0; k < nhi; k++)
+          if (ibasin[ihi[k] - 1] != imin) imap[ibasin[ihi[k] - 1] - 1] = imin;
+      }
+    }
+  }
+  *nraw = na;
+  std::vector<int> root(na + 1, 0);
+  int cnt = 0;
+  for (int i = 1; i <= na; i++) {  // (:337-351): `where (ibasin == i) ibasin = ii`, as one composed map
+    int r = i;
+    if (imap[i - 1] == 0) cnt++;
+    else
+      while (imap[r - 1] != 0) r = imap[r - 1];
+    root[i] = r;
+  }
+  // the `where` passes run for i = 1, 2, ...: a point relabelled to ii < i is not touched again (ii's pass is over),
+  // and roots are never relabelled, so the composition is exactly root[]
+  *nattr = cnt;
+  for (long q = 0; q < nn; q++) idg[q] = root[ibasin[iio[q] - 1]];  // (:356)
+  return 0;
+}
+
 // yt_weights for one basin (yt@proc.f90:476-499 / :502-524): w is spatial (n1,n2,n3).
 void orc_yt_weights(long nn, int nvec, const int* nlo, const int* ibasin, const int* iio, const int* inear,
                     const double* fnear, int idb, double* w) {

@@ -182,6 +182,25 @@ def yt_integrate(f, x2c, vec, area, atoms=None, ratom=1.0, atexist=True, stable=
     return d
 
 
+def yt_isosurface(f, vec, isov, stable=False, maxattr=None):
+    """yt_isosurface (yt@proc.f90:233-390) without a DISCARD expression.
+    Returns (idg[n1,n2,n3], nraw, nattr, xattr[3,nraw])."""
+    f = _f64(f)
+    n = np.array(f.shape, dtype=np.int32)
+    vec = _i32(np.asarray(vec, dtype=np.int32).reshape(-1, 3).T)
+    if maxattr is None:
+        maxattr = 100000
+    idg = np.zeros(f.shape, dtype=np.int32, order="F")
+    nraw, nattr = C.c_int(0), C.c_int(0)
+    xattr = np.zeros((3, maxattr), order="F")
+    rc = lib().orc_yt_isosurface(_p(f, C.c_double), _p(n, C.c_int), C.c_int(vec.shape[1]), _p(vec, C.c_int),
+                                 C.c_double(isov), C.c_int(1 if stable else 0), _p(idg, C.c_int), C.byref(nraw),
+                                 C.byref(nattr), _p(xattr, C.c_double), C.c_int(maxattr))
+    if rc != 0:
+        raise RuntimeError(f"orc_yt_isosurface failed rc={rc}")
+    return idg, nraw.value, nattr.value, xattr[:, : nraw.value].copy()
+
+
 def yt_weights(d: YtData, idb: int, shape):
     w = np.zeros(shape, order="F")
     lib().orc_yt_weights(C.c_long(d.nn), C.c_int(d.nvec), _p(d.nlo, C.c_int), _p(d.ibasin, C.c_int),

@@ -52,3 +52,9 @@ def test_host_mirror_bader_and_integrable(name):
     # (tools_math det3), numpy with an LU factorisation: the two differ by a few ulp (north_star allows 1e-10)
     assert np.abs(np.array(r["vol"]) - vref).max() <= 1e-14 * np.abs(vref).max()
     assert np.abs(np.array(r["pop"]) - pref[:, 0]).max() <= 1e-10 * np.abs(pref[:, 0]).max()
+    # INTEGRABLE ... MULTIPOLES 2 through intgrid_multipoles (attractors = atoms here)
+    xattr = np.asfortranarray(np.asarray(c["atoms"], dtype=float).T)
+    mref = orc.multipoles_bader(idg, xattr, 2, c["f"], orc.Cell(x2c), S.omega(x2c))
+    got = np.array(r["mpole_lmax2"]).reshape(mref.shape, order="F")
+    rmax = 0.5 * np.linalg.norm(x2c, axis=0).sum()
+    assert np.abs(got - mref).max() <= 1e-10 * np.abs(pref[:, 0]).max() * rmax ** 2

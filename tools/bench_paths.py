@@ -6,7 +6,7 @@ time of the call on the library's stream (best of `reps` after a warm-up), achie
 peak (MEASURED_PEAKS.json, else the 6650 GB/s fallback) and a size-independent or sub-sampled parity check
 against the oracle.  bench.py stays the headline (configs[4]); this file is evidence for the rows next to it.
 
-usage: python tools/bench_paths.py [--quick]
+usage: python tools/bench_paths.py [--quick] [--only=name,name]
 """
 import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -228,7 +228,50 @@ def text_writer():
         ctx.free(x)
 
 
-for fn in (urea, nci, yt, fft_big, text_reader, text_writer):
+# ---- INTEGRABLE ... MULTIPOLES 5 (the reference default lmax) on the urea-like 256^3 Bader basins ----
+def multipoles():
+    N = 128 if quick else 256
+    n = (N, N, N)
+    x2c = S.cell_x2c(10.52, 10.52, 8.85)
+    at, z, al = S.random_atoms(16, 2, x2c, dmin=2.0)
+    at = S.snap_to_grid(at, n)
+    h = ctx.alloc(n); ctx.promolecular(h, x2c, at, z, al, nimg=1, rc=0.0)
+    _, car2lat, lid = orc.bader_metrics(x2c, n)
+    om = S.omega(x2c)
+    b = ctx.bader_assign(h, car2lat, lid)
+    pm = b.maxima()
+    b.set_map(b.nmax, np.arange(1, b.nmax + 1, dtype=np.int32))
+    xattr = ((pm - 1) / np.array(n, dtype=float)).T
+    for lmax in (5, 2):
+        ms, prof, mp = timed(lambda: ctx.integrate_multipoles(b, h, lmax, xattr, x2c, om))
+        _, ps = ctx.integrate(b, [h], om)
+        chk = {"lmax": lmax, "moments_per_basin": (lmax + 1) ** 2, "basins": int(b.nmax),
+               "monopole_vs_population_max_rel": float(np.abs(mp[0] - ps[:, 0]).max() / np.abs(ps[:, 0]).max()),
+               "note": "FP64-pipe bound (acos, atan2, lmax+1 sincos, the genylm recursion per point), 12 algorithmic B/pt"}
+        if lmax == 5:
+            # sub-volume parity + CPU side: the oracle on the first 16 planes of the same labels and field
+            f = ctx.download(h, n); idg = b.labels(n)
+            sub_f = np.asfortranarray(f[:, :, :16]); sub_l = np.asfortranarray(idg[:, :, :16])
+            t0 = time.perf_counter()
+            # same point coordinates need the same n3: evaluate the oracle on the full grid with labels zeroed elsewhere
+            lab0 = np.zeros_like(idg); lab0[:, :, :16] = sub_l
+            ref = orc.multipoles_bader(lab0, xattr, lmax, f, orc.Cell(x2c), om)
+            t_cpu = time.perf_counter() - t0
+            hz = ctx.upload(np.asfortranarray(np.where(lab0 > 0, f, 0.0)))
+            got = ctx.integrate_multipoles(b, hz, lmax, xattr, x2c, om)
+            ctx.free(hz)
+            scale = np.abs(ref[0]).max() * (0.5 * np.linalg.norm(x2c, axis=0).sum()) ** np.repeat(np.arange(lmax + 1), 2 * np.arange(lmax + 1) + 1)
+            chk["subvolume_max_err_over_scale"] = float((np.abs(got - ref) / scale[:, None]).max())
+            chk["cpu_oracle_points_per_s_1thread"] = float(sub_f.size / t_cpu)
+        emit("INTEGRABLE MULTIPOLES (Bader basins, lmax = %d)" % lmax, "configs[1] urea-like 16 atoms, tetragonal", n, ms, 12.0, prof, chk)
+    b.free(); ctx.free(h)
+
+
+only = [a.split("=", 1)[1].split(",") for a in sys.argv if a.startswith("--only=")]
+for fn in (urea, nci, yt, fft_big, text_reader, text_writer, multipoles):
+    if only and fn.__name__ not in only[0]:
+        continue
+
     try:
         fn()
     except Exception as e:  # keep going: one JSON line per failure
