@@ -514,6 +514,13 @@ int c2g_basins_set_map(c2g_basins* res, int nattr, const int* map) {
   return C2G_OK;
 }
 
+int c2g_basins_nattr(c2g_basins* res, int* nattr) {
+  if (!res || !nattr) return C2G_ERR_ARG;
+  if (!res->has_map) return res->ctx->fail(C2G_ERR_STATE, "c2g_basins_nattr: no map set");
+  *nattr = res->nattr;
+  return C2G_OK;
+}
+
 int c2g_basins_relabel(c2g_basins* res, int nattr0, const int* assigned, int nattr_new) {
   if (!res) return C2G_ERR_ARG;
   c2g_context* ctx = res->ctx;

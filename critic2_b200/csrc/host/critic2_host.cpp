@@ -191,24 +191,53 @@ void yt_integrate(system& s, basindat& bas) {
   finish_assignment(s, bas, nmax, "yt_integrate");
 }
 
+void yt_isosurface(system& s, basindat& bas) {
+  if (!g_ctx) ferror("yt_isosurface", "gpu_init was not called");
+  if (s.grid.nvec <= 0) ferror("yt_isosurface", "the grid has no Voronoi stencil (init_geometry)");
+  upload_field(bas, "yt_isosurface");
+  int nmax = 0, nraw = 0, nattr = 0;
+  c2g_basins* yt = nullptr;
+  check(c2g_yt_build(g_ctx, g_hgrid, s.grid.nvec, s.grid.vec.data(), s.grid.area.data(), &nmax, &yt), "yt_isosurface");
+  const int rc = c2g_yt_isosurface(yt, bas.isov, &nraw, &nattr, &g_basins);
+  c2g_basins_free(yt);
+  check(rc, "yt_isosurface");
+  bas.is_yt = false;
+  std::vector<int> pmax(3 * (size_t)std::max(nraw, 1));
+  check(c2g_basins_maxima(g_basins, pmax.data()), "yt_isosurface");
+  bas.nattr = nattr;  // survivors; ids in idg run up to nraw (yt@proc.f90:337-352)
+  bas.xattr.assign(3 * (size_t)nattr, 0.0);
+  for (int i = 0; i < nattr; i++)
+    for (int k = 0; k < 3; k++) bas.xattr[3 * i + k] = (pmax[3 * i + k] - 1.0) / bas.n[k];
+  bas.idg.assign(bas.f.size(), 0);
+  check(c2g_basins_labels(g_basins, bas.idg.data()), "yt_isosurface");
+}
+
 void intgrid_fields(const system& s, const basindat& bas, const std::vector<const double*>& fint, std::vector<int_result>& res,
                     std::vector<double>& vol) {
   if (!g_ctx || !g_basins) ferror("intgrid_fields", "no basin assignment on the device");
   const int nprop = (int)fint.size();
   std::vector<int> h(nprop, -1);
   for (int k = 0; k < nprop; k++) check(c2g_grid_upload(g_ctx, fint[k], bas.n, &h[k]), "intgrid_fields");
-  std::vector<double> psum((size_t)bas.nattr * std::max(nprop, 1));
-  vol.assign(bas.nattr, 0.0);
-  check(c2g_integrate(g_ctx, g_basins, nprop, h.data(), s.omega, psum.data(), vol.data()), "intgrid_fields");
+  // rows written by the library: bas.nattr, except after yt_isosurface, where region ids run beyond the number of
+  // surviving regions; the reference's loops stop at bas%nattr (integration@proc.f90:1208, :1290) and so does this copy
+  int nrow = 0;
+  check(c2g_basins_nattr(g_basins, &nrow), "intgrid_fields");
+  if (nrow < bas.nattr) ferror("intgrid_fields", "inconsistent number of attractors");
+  std::vector<double> psum((size_t)nrow * std::max(nprop, 1)), v(nrow, 0.0);
+  check(c2g_integrate(g_ctx, g_basins, nprop, h.data(), s.omega, psum.data(), v.data()), "intgrid_fields");
   for (int k = 0; k < nprop; k++) check(c2g_grid_free(g_ctx, h[k]), "intgrid_fields");
+  vol.assign(v.begin(), v.begin() + bas.nattr);
   res.assign(nprop, int_result());
-  for (int k = 0; k < nprop; k++) res[k].psum.assign(psum.begin() + (size_t)k * bas.nattr, psum.begin() + (size_t)(k + 1) * bas.nattr);
+  for (int k = 0; k < nprop; k++) res[k].psum.assign(psum.begin() + (size_t)k * nrow, psum.begin() + (size_t)k * nrow + bas.nattr);
 }
 
 void intgrid_multipoles(const system& s, const basindat& bas, const double* fint, int lmax,
                         const std::vector<unsigned char>& docelatom, std::vector<double>& mpole) {
   if (!g_ctx || !g_basins) ferror("intgrid_fields", "no basin assignment on the device");
   if (!docelatom.empty() && (int)docelatom.size() != bas.nattr) ferror("intgrid_fields", "docelatom has the wrong size");
+  int nrow = 0;
+  check(c2g_basins_nattr(g_basins, &nrow), "intgrid_fields");
+  if (nrow != bas.nattr) ferror("intgrid_fields", "multipoles need one attractor position per basin id");
   int h = -1;
   check(c2g_grid_upload(g_ctx, fint, bas.n, &h), "intgrid_fields");
   mpole.assign((size_t)(lmax + 1) * (lmax + 1) * bas.nattr, 0.0);

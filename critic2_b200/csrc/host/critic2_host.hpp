@@ -71,6 +71,7 @@ struct basindat {
   std::vector<double> xattr;   // (3,nattr) crystallographic
   std::vector<int> idg;        // idg(n1,n2,n3)
   bool is_yt = false;          // weights live on the device (the reference's luw scratch unit)
+  double isov = 0.0;           // ISOSURFACE: contour value (already negated by the driver for LOWER, integration@proc.f90:260)
 };
 
 // types.f90:394-410 (the sums only)
@@ -87,6 +88,9 @@ bool gpu_enabled();
 void bader_integrate(system& s, basindat& bas);
 // yt@proc.f90:38-224.  bas.idg = spatial basin id, 0 on interatomic-surface points.
 void yt_integrate(system& s, basindat& bas);
+// yt@proc.f90:233-390 (no DISCARD expression): regions of f >= bas.isov.  bas.idg = region ids in the reference's
+// numbering, bas.nattr = surviving regions, bas.xattr = the first nattr regional maxima (:359).
+void yt_isosurface(system& s, basindat& bas);
 // integration@proc.f90:1170-1391: res[k].psum(i) = integral of fint[k] over basin i; vol(i) = basin volume.
 void intgrid_fields(const system& s, const basindat& bas, const std::vector<const double*>& fint,
                     std::vector<int_result>& res, std::vector<double>& vol);

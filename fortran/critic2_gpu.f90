@@ -12,7 +12,7 @@ module critic2_gpu
   private
 
   public :: gpu_enabled, gpu_init, gpu_end
-  public :: gpu_bader_integrate, gpu_yt_integrate, gpu_integrate_fields, gpu_integrate_multipoles, gpu_nci_rdg
+  public :: gpu_bader_integrate, gpu_yt_integrate, gpu_yt_isosurface, gpu_integrate_fields, gpu_integrate_multipoles, gpu_nci_rdg
 
   logical :: gpu_enabled = .false.        !< set by gpu_init (environment variable CRITIC2_GPU=1)
   type(c_ptr) :: ctx = c_null_ptr         !< c2g_context
@@ -67,6 +67,20 @@ module critic2_gpu
        type(c_ptr) :: res
        integer(c_int) :: c2g_yt_build
      end function c2g_yt_build
+     function c2g_yt_isosurface(yt,isov,nraw,nattr,res) bind(c,name="c2g_yt_isosurface")
+       import :: c_int, c_ptr, c_double
+       type(c_ptr), value :: yt
+       real(c_double), value :: isov
+       integer(c_int) :: nraw, nattr
+       type(c_ptr) :: res
+       integer(c_int) :: c2g_yt_isosurface
+     end function c2g_yt_isosurface
+     function c2g_basins_nattr(res,nattr) bind(c,name="c2g_basins_nattr")
+       import :: c_int, c_ptr
+       type(c_ptr), value :: res
+       integer(c_int) :: nattr
+       integer(c_int) :: c2g_basins_nattr
+     end function c2g_basins_nattr
      function c2g_basins_maxima(res,pmax) bind(c,name="c2g_basins_maxima")
        import :: c_int, c_ptr
        type(c_ptr), value :: res
@@ -331,6 +345,43 @@ contains
     call realloc(bas%xattr,3,bas%nattr)
   end subroutine gpu_yt_integrate
 
+  !> GPU body of yt_isosurface (src/yt@proc.f90:233-390) for an empty DISCARD expression (with an expression the
+  !> caller keeps the CPU routine: the expression is evaluated by the host parser, :304-311).  Fills bas%nattr,
+  !> bas%xattr and bas%idg like the reference (surviving regions keep their discovery numbers, :337-359); the
+  !> regions stay on the device for gpu_integrate_fields / gpu_integrate_multipoles.
+  subroutine gpu_yt_isosurface(s,bas)
+    use systemmod, only: system
+    use types, only: basindat, realloc
+    type(system), intent(inout) :: s
+    type(basindat), intent(inout) :: bas
+    integer(c_int) :: nmax, n(3), nvec, nraw, nattr
+    integer(c_int), allocatable :: pmax(:,:)
+    type(c_ptr) :: yt, regions
+    integer :: i
+
+    n = int(bas%n,c_int)
+    nvec = int(s%f(s%iref)%grid%nvec,c_int)
+    if (hgrid >= 0) call check(c2g_grid_free(ctx,hgrid),"gpu_yt_isosurface")
+    call check(c2g_grid_upload(ctx,bas%f,n,hgrid),"gpu_yt_isosurface")
+    if (c_associated(basins)) call c2g_basins_free(basins)
+    call check(c2g_yt_build(ctx,hgrid,nvec,s%f(s%iref)%grid%vec,s%f(s%iref)%grid%area,nmax,yt),"gpu_yt_isosurface")
+    call check(c2g_yt_isosurface(yt,bas%isov,nraw,nattr,regions),"gpu_yt_isosurface")
+    call c2g_basins_free(yt)
+    basins = regions
+    allocate(pmax(3,max(nraw,1)))
+    call check(c2g_basins_maxima(basins,pmax),"gpu_yt_isosurface")
+    if (allocated(bas%xattr)) deallocate(bas%xattr)
+    allocate(bas%xattr(3,max(nraw,1)))
+    do i = 1, nraw
+       bas%xattr(:,i) = real(pmax(:,i)-1,8) / real(bas%n,8)      ! dv of :301
+    end do
+    bas%nattr = nattr                                           ! :352
+    if (allocated(bas%idg)) deallocate(bas%idg)
+    allocate(bas%idg(bas%n(1),bas%n(2),bas%n(3)))
+    call check(c2g_basins_labels(basins,bas%idg),"gpu_yt_isosurface")
+    call realloc(bas%xattr,3,bas%nattr)                         ! :359
+  end subroutine gpu_yt_isosurface
+
   !> GPU body of the two per-attractor loops of intgrid_fields (src/integration@proc.f90:1205-1219 and
   !> :1288-1301).  fint holds the nprop integrand grids already built by the host code (:1235-1280).
   subroutine gpu_integrate_fields(bas,nprop,fint,omega,psum,vol,assigned,nattr_new)
@@ -341,7 +392,8 @@ contains
     real*8, intent(in) :: omega
     real*8, intent(out) :: psum(:,:), vol(:)
     integer, intent(in), optional :: assigned(:), nattr_new
-    integer(c_int) :: h(nprop), n(3)
+    integer(c_int) :: h(nprop), n(3), nrow
+    real*8, allocatable :: psum0(:,:), vol0(:)
     integer :: k
 
     n = int(bas%n,c_int)
@@ -352,7 +404,13 @@ contains
     do k = 1, nprop
        call check(c2g_grid_upload(ctx,fint(:,:,:,k),n,h(k)),"gpu_integrate_fields")
     end do
-    call check(c2g_integrate(ctx,basins,int(nprop,c_int),h,omega,psum,vol),"gpu_integrate_fields")
+    ! rows written by the library: bas%nattr, except after gpu_yt_isosurface (region ids run beyond the number of
+    ! surviving regions); the reference's loops stop at bas%nattr (:1208, :1290) and so does this copy
+    call check(c2g_basins_nattr(basins,nrow),"gpu_integrate_fields")
+    allocate(psum0(nrow,max(nprop,1)),vol0(nrow))
+    call check(c2g_integrate(ctx,basins,int(nprop,c_int),h,omega,psum0,vol0),"gpu_integrate_fields")
+    psum(1:bas%nattr,1:nprop) = psum0(1:bas%nattr,1:nprop)
+    vol(1:bas%nattr) = vol0(1:bas%nattr)
     do k = 1, nprop
        call check(c2g_grid_free(ctx,h(k)),"gpu_integrate_fields")
     end do
@@ -364,17 +422,23 @@ contains
   subroutine gpu_integrate_multipoles(c,bas,lmax,fint,mpole)
     use crystalmod, only: crystal
     use types, only: basindat
+    use tools_io, only: ferror, faterr
     type(crystal), intent(in) :: c
     type(basindat), intent(in) :: bas
     integer, intent(in) :: lmax
     real*8, intent(in) :: fint(:,:,:)
     real*8, intent(out) :: mpole(:,:)
-    integer(c_int) :: h, n(3), nws
+    integer(c_int) :: h, n(3), nws, nrow
     integer(c_signed_char) :: domask(max(bas%nattr,1))
     real*8 :: wsdum(3,1)
     integer :: m
 
     n = int(bas%n,c_int)
+    ! after gpu_yt_isosurface with merged regions the ids in idg exceed bas%nattr and the reference itself reads
+    ! xattr(:,ix) out of bounds (:1346): refuse instead of guessing
+    call check(c2g_basins_nattr(basins,nrow),"gpu_integrate_multipoles")
+    if (nrow /= bas%nattr) &
+       call ferror("gpu_integrate_multipoles","region ids exceed the number of attractors (merged isosurface regions)",faterr)
     do m = 1, bas%nattr   ! bas%docelatom(bas%icp(m)) of :1318; the Bader branch does not look at it
        domask(m) = merge(1_c_signed_char,0_c_signed_char,bas%docelatom(bas%icp(m)))
     end do

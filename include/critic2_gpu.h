@@ -104,6 +104,9 @@ int c2g_basins_maxima(c2g_basins* res, int* pmax);
 int c2g_basins_counts(c2g_basins* res, long long* counts);
 /* map(nmax): maximum -> basin id (1..nattr; 0 = discarded attractor, points stay unassigned). */
 int c2g_basins_set_map(c2g_basins* res, int nattr, const int* map);
+/* Number of basin ids of the current map = rows of psum / vol / mpole written by c2g_integrate and
+ * c2g_integrate_multipoles (for an ISOSURFACE result: nraw, the largest region id). */
+int c2g_basins_nattr(c2g_basins* res, int* nattr);
 /* bas%idg(n1,n2,n3) (move_alloc(volnum,bas%idg), bader@proc.f90:229).  Multi-GPU: every rank
  * receives its own slab idg(:,:,zlo+1:zhi). */
 int c2g_basins_labels(c2g_basins* res, int* idg);
