@@ -26,7 +26,7 @@ EXPORTS = [
     "c2g_grid_upload", "c2g_grid_upload_slab", "c2g_slab_range", "c2g_slab_bounds_query", "c2g_grid_alloc", "c2g_grid_download", "c2g_grid_download_slab", "c2g_grid_free", "c2g_grid_promolecular",
     "c2g_bader_assign", "c2g_basins_maxima", "c2g_basins_counts", "c2g_basins_set_map", "c2g_basins_labels",
     "c2g_basins_relabel", "c2g_basins_nattr", "c2g_basins_free", "c2g_basins_stats", "c2g_integrate", "c2g_integrate_multipoles", "c2g_yt_build",
-    "c2g_yt_weights", "c2g_yt_isosurface", "c2g_nci_rdg", "c2g_nci_rdg_resident", "c2g_fft_derivative", "c2g_nci_rdg_fourier", "c2g_nci_range", "c2g_grid_upload_async", "c2g_basins_labels_async", "c2g_grid_parse_text", "c2g_grid_format_text", "c2g_profile_enable", "c2g_profile_count",
+    "c2g_yt_weights", "c2g_basins_weight_grid", "c2g_yt_isosurface", "c2g_nci_rdg", "c2g_nci_rdg_resident", "c2g_fft_derivative", "c2g_nci_rdg_fourier", "c2g_nci_range", "c2g_grid_upload_async", "c2g_basins_labels_async", "c2g_grid_parse_text", "c2g_grid_format_text", "c2g_profile_enable", "c2g_profile_count",
     "c2g_profile_get", "c2g_profile_reset", "c2g_launch_count", "c2g_flush_l2", "c2g_synchronize", "c2g_timer_start", "c2g_timer_stop",
 ]
 
@@ -397,6 +397,12 @@ class Basins:
         w = np.zeros(tuple(int(x) for x in shape), order="F")
         self.ctx._chk(self.ctx.lib.c2g_yt_weights(self.h, C.c_int(idb), _p(w, C.c_double)))
         return w
+
+    def weight_grid(self, idb):
+        """Resident weight field of basin idb (int_cubew, integration@proc.f90:4449-4459); returns a grid handle."""
+        h = C.c_int(-1)
+        self.ctx._chk(self.ctx.lib.c2g_basins_weight_grid(self.h, C.c_int(idb), C.byref(h)))
+        return h.value
 
     def isosurface(self, isov):
         """yt_isosurface (yt@proc.f90:233-390) on a YT result: (regions Basins, nraw, nattr)."""

@@ -581,6 +581,39 @@ int c2g_basins_labels_async(c2g_basins* res, int* idg) {
   return C2G_OK;
 }
 
+// indicator field of one basin: w = 1 where map(label) == idb, else 0 (int_cubew, integration@proc.f90:4455-4458)
+__global__ void k_indicator(long long nn, const int* __restrict__ label, const int* __restrict__ map, int mask, int idb,
+                            double* __restrict__ w) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nn; i += stride) {
+    const int l = label[i] & mask;
+    w[i] = (l >= 0 && __ldg(map + l) == idb) ? 1.0 : 0.0;
+  }
+}
+
+int c2g_basins_weight_grid(c2g_basins* res, int idb, int* handle) {
+  if (!res) return C2G_ERR_ARG;
+  c2g_context* ctx = res->ctx;
+  if (!handle) return ctx->fail(C2G_ERR_ARG, "c2g_basins_weight_grid: null handle");
+  if (!res->has_map) return ctx->fail(C2G_ERR_STATE, "c2g_basins_weight_grid: call c2g_basins_set_map first");
+  if (idb < 1 || idb > res->nattr) return ctx->fail(C2G_ERR_ARG, "c2g_basins_weight_grid: unknown basin %d", idb);
+  if (ctx->nranks > 1 && res->kind == 0)
+    return ctx->fail(C2G_ERR_STATE, "c2g_basins_weight_grid: Bader labels are sharded on a multi-GPU context");
+  int rc = c2g_grid_alloc(ctx, res->n, handle);
+  if (rc != C2G_OK) return rc;
+  double* w = ctx->grids[*handle].d;
+  if (res->kind == 1) {
+    rc = c2g_yt_weights_device(res, idb, w);
+  } else {
+    ctx->prof_begin("basin_indicator");
+    k_indicator<<<ctx->nsm * 8, 256, 0, ctx->stream>>>(res->nn, res->d_label, res->d_map, res->kind == 0 ? 0x7fffffff : -1, idb, w);
+    ctx->prof_end();
+    if (cudaGetLastError() != cudaSuccess) rc = ctx->fail(C2G_ERR_CUDA, "k_indicator launch failed");
+  }
+  if (rc != C2G_OK) { c2g_grid_free(ctx, *handle); *handle = -1; return rc; }
+  return C2G_OK;
+}
+
 int c2g_basins_stats(c2g_basins* res, long long stats[8]) {
   if (!res || !stats) return C2G_ERR_ARG;
   for (int i = 0; i < 8; i++) stats[i] = res->stats[i];

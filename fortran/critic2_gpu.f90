@@ -12,7 +12,8 @@ module critic2_gpu
   private
 
   public :: gpu_enabled, gpu_init, gpu_end
-  public :: gpu_bader_integrate, gpu_yt_integrate, gpu_yt_isosurface, gpu_integrate_fields, gpu_integrate_multipoles, gpu_nci_rdg
+  public :: gpu_bader_integrate, gpu_yt_integrate, gpu_yt_isosurface, gpu_integrate_fields, gpu_integrate_multipoles
+  public :: gpu_nci_rdg, gpu_nci_rdg_fourier, gpu_grid_fft, gpu_read_text_block, gpu_write_text_block, gpu_wcube_block
 
   logical :: gpu_enabled = .false.        !< set by gpu_init (environment variable CRITIC2_GPU=1)
   type(c_ptr) :: ctx = c_null_ptr         !< c2g_context
@@ -81,6 +82,13 @@ module critic2_gpu
        integer(c_int) :: nattr
        integer(c_int) :: c2g_basins_nattr
      end function c2g_basins_nattr
+     function c2g_basins_weight_grid(res,idb,handle) bind(c,name="c2g_basins_weight_grid")
+       import :: c_int, c_ptr
+       type(c_ptr), value :: res
+       integer(c_int), value :: idb
+       integer(c_int) :: handle
+       integer(c_int) :: c2g_basins_weight_grid
+     end function c2g_basins_weight_grid
      function c2g_basins_maxima(res,pmax) bind(c,name="c2g_basins_maxima")
        import :: c_int, c_ptr
        type(c_ptr), value :: res
@@ -553,5 +561,29 @@ contains
     write (lu) text
     call check(c2g_grid_free(ctx,h),"gpu_write_text_block")
   end subroutine gpu_write_text_block
+
+  !> WCUBE (int_cubew, src/integration@proc.f90:4449-4462): the value block of the weight cube of attractor i, from
+  !> the basins resident on the device -- the YT weights (:4451) or the indicator of idg == i (:4455-4458) -- written to
+  !> unit lu (access="stream") after the header lines of writegrid_cube; the weights never visit the host.
+  subroutine gpu_wcube_block(lu,i,ishift,precisecube)
+    integer, intent(in) :: lu, i, ishift(3)
+    logical, intent(in) :: precisecube
+    integer(c_int) :: h, width, digits, scale
+    integer(c_size_t) :: nbytes
+    character(kind=c_char), allocatable :: text(:)
+
+    width = 12; digits = 5; scale = 1                      ! (1p,6(" ",E12.5E3)), crystalmod@write.f90:3563
+    if (precisecube) then
+       width = 22; digits = 14; scale = 0                  ! (6(" ",E22.14E3)), :3559
+    end if
+    call check(c2g_basins_weight_grid(basins,int(i,c_int),h),"gpu_wcube_block")
+    allocate(text(1))
+    call check(c2g_grid_format_text(ctx,h,1_c_int,int(ishift,c_int),width,digits,scale,text,0_c_size_t,nbytes),"gpu_wcube_block")
+    deallocate(text)
+    allocate(text(nbytes))
+    call check(c2g_grid_format_text(ctx,h,1_c_int,int(ishift,c_int),width,digits,scale,text,nbytes,nbytes),"gpu_wcube_block")
+    write (lu) text
+    call check(c2g_grid_free(ctx,h),"gpu_wcube_block")
+  end subroutine gpu_wcube_block
 
 end module critic2_gpu

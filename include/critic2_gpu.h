@@ -153,6 +153,11 @@ int c2g_yt_build(c2g_context* ctx, int handle, int nvec, const int* vec, const d
 /* (use c2g_basins_labels) */
 /* dense weight field of one basin, w(n1,n2,n3) (yt_weights, yt@proc.f90:476-499). */
 int c2g_yt_weights(c2g_basins* res, int idb, double* w);
+/* WCUBE (int_cubew, integration@proc.f90:4428-4466): the weight field of basin idb as a RESIDENT grid -- the YT
+ * weights (yt_weights with idb, :4451) or, for Bader labels and ISOSURFACE regions, w = 1 where idg == idb
+ * (:4455-4458).  Pass the handle to c2g_grid_format_text (layout 1) for the value block of the cube file, then
+ * c2g_grid_free it.  Single-GPU contexts only for Bader labels (they are sharded otherwise). */
+int c2g_basins_weight_grid(c2g_basins* res, int idb, int* handle);
 /* statistics: [0] IAS points, [1] flux records (sum of nhi over IAS points), [2] sweep levels */
 /* (use c2g_basins_stats) */
 

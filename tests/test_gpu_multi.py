@@ -51,6 +51,16 @@ def test_slab_sharded_bader_equals_oracle(nranks, name):
             assert np.array_equal(p[f"vol{algo}"], vref)
             assert np.abs(p[f"ps{algo}"][:, 0] - pref[:, 0]).max() <= 1e-10 * np.abs(pref[:, 0]).max()
             assert int(p[f"cnt{algo}"].sum()) == idg.size
+    # multipoles: slab partials all-reduced, identical on every rank up to the order of the atomic adds
+    if nattr == len(c["atoms"]):
+        ortho = bool(np.all(c["x2c"] - np.diag(np.diag(c["x2c"])) == 0.0))
+        cell = orc.Cell(c["x2c"]) if ortho else orc.Cell(c["x2c"], ws=c["x2c"] @ S.wscell(c["x2c"])[0].T.astype(float))
+        xattr = np.asarray(c["atoms"], dtype=float).T
+        mref = orc.multipoles_bader(idg, xattr, 3, c["f"], cell, S.omega(c["x2c"]))
+        rmax = 0.5 * np.linalg.norm(c["x2c"], axis=0).sum()
+        scale = np.abs(mref[0]).max() * rmax ** np.repeat(np.arange(4), 2 * np.arange(4) + 1)
+        for p in parts:
+            assert np.all(np.abs(p["mpole"] - mref) <= 1e-10 * scale[:, None])
     # NCIPLOT sharded along i: the ranks' pieces concatenate to the single-process result of the oracle
     crho_o, cgrad_o = orc.nci_rdg(c["f"], c["x2c"])
     assert [int(p["nci_ilo"]) for p in parts][1:] == [int(p["nci_ihi"]) for p in parts][:-1]

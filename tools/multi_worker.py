@@ -28,6 +28,12 @@ for algo in (capi.BADER_EXACT, capi.BADER_FAST):
     lab = b.labels((n[0], n[1], max(zhi - zlo, 0)))
     vol, ps = ctx.integrate(b, [h, h2], S.omega(x2c))
     out[f"lab{algo}"] = lab; out[f"vol{algo}"] = vol; out[f"ps{algo}"] = ps; out[f"cnt{algo}"] = b.counts()
+    if algo == capi.BADER_FAST:  # multipoles: per-slab partial moments, all-reduced over NCCL
+        ortho = bool(np.all(x2c - np.diag(np.diag(x2c)) == 0.0))
+        kw = {} if ortho else dict(ws=np.asfortranarray(x2c @ S.wscell(x2c)[0].T.astype(float)))
+        xattr = np.asarray(c["atoms"], dtype=float).T
+        if xattr.shape[1] == na:
+            out["mpole"] = ctx.integrate_multipoles(b, h, 3, xattr, x2c, S.omega(x2c), **kw)
     b.free()
 # NCIPLOT: the output lattice is sharded along i, no collective
 ilo, ihi = ctx.nci_range(n[0])
