@@ -244,7 +244,7 @@ extern "C" int c2g_integrate(c2g_context* ctx, c2g_basins* res, int nprop, const
                                  first ? d_counts : nullptr);
     first = false;
   }
-  if (rc == C2G_OK && ctx->nranks > 1) {
+  if (rc == C2G_OK && ctx->nranks > 1 && res->kind == 0) {  // Bader labels are z-slabs; ISOSURFACE regions are replicas
     ncclComm_t comm = (ncclComm_t)ctx->nccl;
     ctx->prof_begin("basin_allreduce_nccl");
     ncclResult_t r1 = ncclAllReduce(d_sums, d_sums, hs.size(), ncclDouble, ncclSum, comm, ctx->stream);

@@ -278,7 +278,7 @@ extern "C" int c2g_integrate_multipoles(c2g_context* ctx, c2g_basins* res, int f
       ctx->prof_end();
       if (e != cudaSuccess) return ctx->fail(C2G_ERR_CUDA, "k_multipoles launch: %s", cudaGetErrorString(e));
     }
-    if (ctx->nranks > 1) {
+    if (ctx->nranks > 1 && res->kind == 0) {  // z-slabs of Bader labels; ISOSURFACE regions are replicated on every rank
       ctx->prof_begin("multipoles_allreduce_nccl");
       ncclResult_t r = ncclAllReduce(a.sums, a.sums, (size_t)nlm * nattr, ncclDouble, ncclSum, (ncclComm_t)ctx->nccl, ctx->stream);
       ctx->prof_end();

@@ -229,6 +229,14 @@ def test_headline_size_properties(ctx):
         d = np.minimum(d, 1.0 - d).max(axis=2).min(axis=1)
         assert d.max() <= 1.5 / N
         runs.append((cnt.copy(), ps.copy()))
+        if rep == 1:
+            # INTEGRABLE ... MULTIPOLES at the headline size: the monopole of every basin is its population, the
+            # first moments about the attractor are small against (basin radius) x population (near-spherical atoms)
+            b.set_map(b.nmax, np.arange(1, b.nmax + 1, dtype=np.int32))
+            mpole = ctx.integrate_multipoles(b, h, 5, pm.T, x2c, om)
+            assert mpole.shape == (36, b.nmax)
+            assert np.abs(mpole[0] - ps[:, 0]).max() <= 1e-10 * np.abs(ps[:, 0]).max()
+            assert np.all(np.isfinite(mpole)) and np.abs(mpole[1:4]).max() <= 2.5 * np.abs(ps[:, 0]).max()
         b.free()
     assert np.array_equal(runs[0][0], runs[1][0])
     assert np.abs(runs[0][1] - runs[1][1]).max() <= 1e-13 * np.abs(runs[0][1]).max()

@@ -79,6 +79,27 @@ def test_yt_512_partition_properties(ctx):
         d = np.abs(pm[:, None, :] - at[None, :, :])
         assert np.minimum(d, 1.0 - d).max(axis=2).min(axis=1).max() <= 1.5 / N
         res.append((vol.copy(), ps.copy(), b.stats()[0]))
+        if rep == 1:
+            # ISOSURFACE at the config size: above every saddle the regions are the 512 separate atomic caps;
+            # lower, regions merge (survivors <= regions, ids <= regions); a point is in a region iff f >= isov
+            f = ctx.download(h, n)
+            peak = f[tuple((np.round(pm * N).astype(int) % N).T)]
+            hi = float(0.5 * peak.min())
+            reg, nraw, nsurv = b.isosurface(hi)
+            assert nraw == side ** 3 and nsurv <= nraw
+            lab = reg.labels(n)
+            assert np.array_equal(lab > 0, f >= hi) and lab.max() <= nraw
+            vol_r, _ = ctx.integrate(reg, [h], om)
+            assert abs(vol_r.sum() * f.size / om - np.count_nonzero(f >= hi)) < 0.5
+            reg.free()
+            lo = float(np.quantile(f[::8, ::8, ::8], 0.3))
+            reg, nraw2, nsurv2 = b.isosurface(lo)
+            assert nraw2 == side ** 3 and 1 <= nsurv2 <= nraw2
+            lab = reg.labels(n)
+            assert np.array_equal(lab > 0, f >= lo)
+            assert len(np.unique(lab[::4, ::4, ::4])) - 1 <= nsurv2
+            reg.free()
+            del f, lab
         b.free()
     assert res[0][2] == res[1][2]                                       # same interatomic-surface set
     assert np.abs(res[0][0] - res[1][0]).max() <= 1e-12 * om
