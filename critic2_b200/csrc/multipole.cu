@@ -8,13 +8,14 @@
 //   then mpole = mpole * omega / ntot (:1360).
 // The reference runs the Bader loop under an `omp critical` and the YT loop once per basin over the full grid.
 //
-// Per point this is ~10^3 fp64 operations (acos, atan2, lmax+1 sincos, the Masters & Richards-Dinger recursion
-// of genylm, src/tools_math@proc.f90:314-377) against 12 bytes of HBM traffic (label + field value): the kernel is
-// FP64-pipe bound, not HBM bound.  Layout: persistent warps walk contiguous chunks of the (slab of the) grid, one
+// Per point this is several hundred fp64 operations (the Masters & Richards-Dinger recursion of genylm,
+// src/tools_math@proc.f90:314-377, with its divisions and square roots) against 12 bytes of HBM traffic (label +
+// field value): the kernel is FP64-pipe bound, not HBM bound.  Layout: persistent warps walk contiguous chunks of the (slab of the) grid, one
 // point per lane; a lane keeps the (lmax+1)^2 partial moments of the warp's current basin in registers (lmax <= 5,
 // the reference's default) and the warp reduces them with shuffles only when the basin changes, as k_basin_reduce
-// does.  Arithmetic follows the Fortran evaluation order (the file is built with -fmad=false); acos / atan2 / sin /
-// cos come from the CUDA math library (<= 2 ulp), so parity is a tolerance (1e-10 of the sum of |terms|), not bits.
+// does.  The recursion follows the Fortran evaluation order (the file is built with -fmad=false); the angles of
+// tosphere are replaced by their sines and cosines taken directly from the vector (see add_point), so parity is a
+// tolerance (1e-10 of the sum of |terms|; measured ~1e-15), not bits.
 #include "common.cuh"
 
 namespace {
@@ -93,23 +94,32 @@ __device__ __forceinline__ void add_point(double (&acc)[(LCAP + 1) * (LCAP + 1)]
   constexpr double pi = 3.14159265358979323846, fourpi = 12.566370614359172954, eps = 1e-14;
   const double sh = 1.0 / sqrt(2.0);
   const double r = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
-  double th = 0.0, ph = 0.0;
-  if (r > eps) {
-    const double t1 = v[2] / r;
-    if (t1 >= 1.0) th = 0.0;
-    else if (t1 <= -1.0) th = pi;
-    else th = acos(t1);
-    if (fabs(v[0]) > eps || fabs(v[1]) > eps) ph = atan2(v[1], v[0]);
-  }
   // l = 0: rlm(1) = ylm(1) * sqrt(4 pi / 1) * r**0
   acc[0] += ((0.28209479177387814347 * sqrt(4.0 * pi / 1.0) * 1.0) * f) * w;
   if (lmax == 0) return;
-  double sn, cs;
-  sincos(th, &sn, &cs);
+  // The reference goes through the angles: theta = acos(z/r), phi = atan2(y,x), then sin/cos(theta) and
+  // cos/sin(m phi).  The same quantities without transcendentals: cos(theta) = z/r, sin(theta) = rho/r with
+  // rho = sqrt(x^2+y^2), cos(phi) = x/rho, sin(phi) = y/rho and the angle-addition recurrence for m phi (error
+  // <~ m ulp).  This is the better-conditioned form (acos loses half the digits near the poles) and takes the kernel
+  // off the libm slow paths; the branches of tosphere are kept (r <= eps, |z/r| >= 1, |x|,|y| <= eps).
+  double sn = 0.0, cs = 1.0, c1 = 1.0, s1 = 0.0;
+  if (r > eps) {
+    const double t1 = v[2] / r;
+    const double rho2 = v[0] * v[0] + v[1] * v[1];
+    const double rho = sqrt(rho2);
+    if (t1 >= 1.0) { cs = 1.0; sn = 0.0; }
+    else if (t1 <= -1.0) { cs = -1.0; sn = 1.2246467991473532e-16; }  // cos(pi), sin(pi) in fp64
+    else { cs = t1; sn = rho / r; }
+    if (fabs(v[0]) > eps || fabs(v[1]) > eps) { c1 = v[0] / rho; s1 = v[1] / rho; }
+  }
   double zc[LCAP + 1], zs[LCAP + 1];
+  zc[1] = c1; zs[1] = s1;
 #pragma unroll
-  for (int m = 1; m <= LCAP; m++)
-    if (m <= lmax) sincos((double)m * ph, &zs[m], &zc[m]);
+  for (int m = 2; m <= LCAP; m++)
+    if (m <= lmax) {
+      zc[m] = zc[m - 1] * c1 - zs[m - 1] * s1;
+      zs[m] = zs[m - 1] * c1 + zc[m - 1] * s1;
+    }
   double x[LCAP + 1];
 #pragma unroll
   for (int l = 1; l <= LCAP; l++) {

@@ -149,6 +149,15 @@ def yt():
            "phi_ias": phi, "nhi_assumed": nhi, "bfs_levels": int(st[1]), "kahn_levels": int(st[2]), "nvec": int(len(area)), "basins": int(b.nmax)}
     emit("YT build (yt_integrate)", "configs[3] 512 atoms cubic, tie-free", n, ms_b, 24.0 + 12.0 * nhi * phi, prof_b, chk)
     emit("YT integrate (adjoint sweep, Volume + rho)", "configs[3]", n, ms_i, 4.0 + 8.0 + 12.0 * nhi * phi + 16.0 * phi, prof_i, chk)
+    # ISOSURFACE regions on the same YT levels (yt_isosurface): median contour value -> merged regions
+    isov = float(np.quantile(f[::8, ::8, ::8], 0.5))
+    ms_s, prof_s, (reg, nraw, nsurv) = timed(lambda: b.isosurface(isov), reps=2, cleanup=lambda o: o[0].free())
+    lab = reg.labels(n)
+    emit("ISOSURFACE regions (yt_isosurface) from the resident YT levels", "configs[3], contour at the median density", n, ms_s,
+         8.0 + 4.0 + 4.0, prof_s,
+         {"regions_before_merging": int(nraw), "surviving_regions": int(nsurv), "labels_positive_iff_above_contour":
+          bool(np.array_equal(lab > 0, f >= isov)), "note": "16 B/pt = read rho + read YT label + write region"})
+    reg.free()
     b.free(); ctx.free(h)
 
 
