@@ -25,7 +25,6 @@ constexpr int MP_LCAP_MAX = 10;    // larger lmax: same code, accumulators spill
 constexpr int MP_CHUNK_ITERS = 8;  // 256 consecutive points per warp chunk
 constexpr int MP_THREADS = 128;     // ~160 registers per thread: 3 blocks (12 warps) per SM
 constexpr int MP_BLOCKS_PER_SM = 3;
-constexpr int MP_TABLE_MAX = 6144;  // doubles of shared memory per block (48 KB) for the per-block moment table
 
 struct MpArgs {
   int n1, n2, n3;
@@ -43,8 +42,6 @@ struct MpArgs {
   int idb;
   const double* fint;     // integrand, owned planes
   double* sums;           // (nlm, nattr)
-  double* partials;       // non-null: per-block tables [block][nattr*nlm] filled from shared memory (no global atomics)
-  int ntab;               // nattr*nlm when the table fits in shared memory, else 0
 };
 
 __device__ __forceinline__ void matvec3(const double* m, const double* x, double* y) {
@@ -165,15 +162,6 @@ __global__ void __launch_bounds__(MP_THREADS) k_multipoles(const __grid_constant
   const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
   const unsigned chunk = 32u * MP_CHUNK_ITERS;
   const unsigned plane = (unsigned)a.n1 * (unsigned)a.n2;
-  // A few basins mean a few hundred hot addresses: global fp64 atomics on them serialise in the L2 atomic unit
-  // (measured ~10 M same-address adds/s, as in integrate.cu).  When nattr*nlm doubles fit, the moments go to a
-  // per-block shared-memory table instead and the block tables are summed in a fixed order afterwards.
-  extern __shared__ double s_mp[];
-  if (a.ntab) {
-    for (int e = threadIdx.x; e < a.ntab; e += blockDim.x) s_mp[e] = 0.0;
-    __syncthreads();
-  }
-  double* const sink = a.ntab ? s_mp : a.sums;
   double acc[NLM];
 #pragma unroll
   for (int e = 0; e < NLM; e++) acc[e] = 0.0;
@@ -187,7 +175,7 @@ __global__ void __launch_bounds__(MP_THREADS) k_multipoles(const __grid_constant
           double s = acc[e];
 #pragma unroll
           for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-          if (lane == 0) atomicAdd(sink + (size_t)cur * a.nlm + e, s);
+          if (lane == 0) atomicAdd(a.sums + (size_t)cur * a.nlm + e, s);
         }
       }
     }
@@ -230,29 +218,13 @@ __global__ void __launch_bounds__(MP_THREADS) k_multipoles(const __grid_constant
     }
   }
   flush();
-  if (a.ntab) {
-    __syncthreads();
-    double* out = a.partials + (size_t)blockIdx.x * a.ntab;
-    for (int e = threadIdx.x; e < a.ntab; e += blockDim.x) out[e] = s_mp[e];
-  }
-}
-
-// sums[e] += sum over blocks of partials[b][e], in block order
-__global__ void __launch_bounds__(256) k_mp_reduce(int nblocks, int ntab, const double* __restrict__ partials, double* __restrict__ sums) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= ntab) return;
-  double s = 0.0;
-  for (int b = 0; b < nblocks; b++) s += partials[(size_t)b * ntab + e];
-  sums[e] += s;
 }
 
 template <bool YT>
 cudaError_t launch(c2g_context* ctx, const MpArgs& a) {
   const int blocks = ctx->nsm * MP_BLOCKS_PER_SM;
-  const size_t smem = sizeof(double) * (size_t)a.ntab;
-  if (a.lmax <= MP_LCAP_FAST) k_multipoles<MP_LCAP_FAST, YT><<<blocks, MP_THREADS, smem, ctx->stream>>>(a);
-  else k_multipoles<MP_LCAP_MAX, YT><<<blocks, MP_THREADS, smem, ctx->stream>>>(a);
-  if (a.ntab) k_mp_reduce<<<c2g_blocks_for(a.ntab, 256), 256, 0, ctx->stream>>>(blocks, a.ntab, a.partials, a.sums);
+  if (a.lmax <= MP_LCAP_FAST) k_multipoles<MP_LCAP_FAST, YT><<<blocks, MP_THREADS, 0, ctx->stream>>>(a);
+  else k_multipoles<MP_LCAP_MAX, YT><<<blocks, MP_THREADS, 0, ctx->stream>>>(a);
   return cudaGetLastError();
 }
 
@@ -300,12 +272,6 @@ extern "C" int c2g_integrate_multipoles(c2g_context* ctx, c2g_basins* res, int f
   a.ws = b_ws.as<double>();
   a.xattr = b_xattr.as<double>();
   a.sums = b_sums.as<double>();
-  DevBuf b_part(ctx);
-  if ((long long)nlm * nattr <= MP_TABLE_MAX) {
-    a.ntab = nlm * nattr;
-    C2G_CUDA(ctx, b_part.alloc(ctx, sizeof(double) * (size_t)a.ntab * ctx->nsm * MP_BLOCKS_PER_SM));
-    a.partials = b_part.as<double>();
-  }
   a.map = res->d_map;
   const size_t plane = (size_t)res->n[0] * res->n[1];
 
@@ -319,7 +285,7 @@ extern "C" int c2g_integrate_multipoles(c2g_context* ctx, c2g_basins* res, int f
     if (a.nnl > 0) {
       ctx->prof_begin("multipoles");
       cudaError_t e = launch<false>(ctx, a);
-      ctx->prof_end(a.ntab ? 2 : 1);
+      ctx->prof_end();
       if (e != cudaSuccess) return ctx->fail(C2G_ERR_CUDA, "k_multipoles launch: %s", cudaGetErrorString(e));
     }
     if (ctx->nranks > 1 && res->kind == 0) {  // z-slabs of Bader labels; ISOSURFACE regions are replicated on every rank
