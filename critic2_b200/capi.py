@@ -25,7 +25,7 @@ EXPORTS = [
     "c2g_init", "c2g_nccl_unique_id", "c2g_init_multi", "c2g_finalize", "c2g_last_error", "c2g_describe",
     "c2g_grid_upload", "c2g_grid_upload_slab", "c2g_slab_range", "c2g_slab_bounds_query", "c2g_grid_alloc", "c2g_grid_download", "c2g_grid_download_slab", "c2g_grid_free", "c2g_grid_promolecular",
     "c2g_bader_assign", "c2g_basins_maxima", "c2g_basins_counts", "c2g_basins_set_map", "c2g_basins_labels",
-    "c2g_basins_relabel", "c2g_basins_nattr", "c2g_basins_free", "c2g_basins_stats", "c2g_integrate", "c2g_integrate_multipoles", "c2g_yt_build",
+    "c2g_basins_relabel", "c2g_basins_nattr", "c2g_basins_free", "c2g_basins_stats", "c2g_integrate", "c2g_integrate_multipoles", "c2g_basins_remap", "c2g_yt_build",
     "c2g_yt_weights", "c2g_basins_weight_grid", "c2g_yt_isosurface", "c2g_nci_rdg", "c2g_nci_rdg_resident", "c2g_fft_derivative", "c2g_nci_rdg_fourier", "c2g_nci_range", "c2g_grid_upload_async", "c2g_basins_labels_async", "c2g_grid_parse_text", "c2g_grid_format_text", "c2g_profile_enable", "c2g_profile_count",
     "c2g_profile_get", "c2g_profile_reset", "c2g_launch_count", "c2g_flush_l2", "c2g_synchronize", "c2g_timer_start", "c2g_timer_stop",
 ]
@@ -188,6 +188,34 @@ class Context:
             _p(b, C.c_double), _p(c, C.c_double), C.c_int(w.shape[1]), _p(w, C.c_double) if w.shape[1] else None,
             C.c_double(omega), _p(mp, C.c_double)))
         return mp
+
+    def basins_remap(self, basins, xattr, x2c, shape=None, x2xr=None, xr2c=None, ws=None, isortho=None, isortho_del=False,
+                     maxattn=None, want_idg1=True):
+        """bader_remap / yt_remap: (nattn, idg1 or None, iatt[nattn], ilvec[3,nattn]).  shape: (n1, n2, nz_owned) of idg1."""
+        x2c = np.asarray(x2c, dtype=np.float64)
+        if isortho is None:
+            isortho = bool(np.all(x2c - np.diag(np.diag(x2c)) == 0.0))
+        xa = np.asfortranarray(np.asarray(xattr, dtype=np.float64).reshape(3, -1))
+        nattr = basins.nattr
+        a, b, c = _m33(x2c), _m33(np.eye(3) if x2xr is None else x2xr), _m33(x2c if xr2c is None else xr2c)
+        c2x = _m33(np.linalg.inv(x2c))
+        w = np.zeros((3, 0), order="F") if ws is None else np.asfortranarray(ws, dtype=np.float64)
+        cap = max(nattr * 27, 1) if maxattn is None else maxattn
+        idg1 = np.zeros(tuple(int(v) for v in shape), dtype=np.int32, order="F") if (want_idg1 and shape is not None) else None
+        while True:
+            iatt = np.zeros(cap, dtype=np.int32)
+            ilvec = np.zeros((3, cap), dtype=np.int32, order="F")
+            nattn = C.c_int(0)
+            rc = self.lib.c2g_basins_remap(
+                self.h, basins.h, _p(xa, C.c_double), _p(c2x, C.c_double), C.c_int(int(isortho)), C.c_int(int(isortho_del)),
+                _p(a, C.c_double), _p(b, C.c_double), _p(c, C.c_double), C.c_int(w.shape[1]),
+                _p(w, C.c_double) if w.shape[1] else None, C.c_int(cap), C.byref(nattn), _p(iatt, C.c_int), _p(ilvec, C.c_int),
+                None if idg1 is None else _p(idg1, C.c_int))
+            if rc == 6 and nattn.value > cap and maxattn is None:   # C2G_ERR_OVERFLOW: retry with the size needed
+                cap = nattn.value
+                continue
+            self._chk(rc)
+            return nattn.value, idg1, iatt[: nattn.value].copy(), ilvec[:, : nattn.value].copy()
 
     # ---- NCIPLOT ----
     def nci_range(self, nstep1):

@@ -18,6 +18,8 @@
 // tolerance (1e-10 of the sum of |terms|; measured ~1e-15), not bits.
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace {
 
 constexpr int MP_LCAP_FAST = 5;    // register-resident accumulators (36 per lane)
@@ -318,5 +320,197 @@ extern "C" int c2g_integrate_multipoles(c2g_context* ctx, c2g_basins* res, int f
   ctx->prof_collect();
   const double ntot = (double)res->nn;
   for (size_t e = 0; e < hs.size(); e++) mpole[e] = hs[e] * omega / ntot;  // :1360
+  return C2G_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Attractor images for DELOC: bader_remap (src/bader@proc.f90:237-296) and yt_remap (src/yt@proc.f90:533-594).
+//
+// For every point: x = p/n - xattr(:,basin), xs = shortest(x), lattice vector pl = nint(x - c2x(xs)).  Points with
+// pl /= 0 belong to the image (basin, pl) of their attractor; the reference numbers the images nattr+1, nattr+2, ...
+// in the order in which its scan (index 1 fastest) first meets them and searches a growing list for every such
+// point.  Here: one pass takes atomicMin(first[basin][pl], linear index) over a dense (nattr x 7^3) table, the host
+// sorts the few occupied entries by that first index (= the reference's numbering; YT: by basin, then first index,
+// like its basin-outer loop), a second pass writes idg1 through the resulting table.  Same `shortest` as above.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int RM_R = 3, RM_W = 2 * RM_R + 1, RM_CODES = RM_W * RM_W * RM_W;
+
+struct RemapArgs {
+  MpArgs a;
+  double c2x[9];
+  int* first;        // (RM_CODES, nattr): smallest linear index of a point of image (basin, code)
+  const int* idmap;  // apply pass: (RM_CODES, nattr) -> new id
+  int* out;          // apply pass: idg1 of the owned planes
+  int* err;
+  int apply;
+};
+
+template <bool YT>
+__global__ void __launch_bounds__(256) k_remap(const __grid_constant__ RemapArgs r) {
+  const MpArgs& a = r.a;
+  const unsigned plane = (unsigned)a.n1 * (unsigned)a.n2;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.nnl; i += stride) {
+    int lab;
+    if (YT) {
+      lab = fabs(__ldg(a.w + i)) < 1e-15 ? -1 : a.idb - 1;
+    } else {
+      const int l = __ldg(a.label + i) & a.mask;
+      lab = l >= 0 ? __ldg(a.map + l) - 1 : -1;
+    }
+    if (lab < 0) {
+      if (r.apply) r.out[i] = 0;
+      continue;
+    }
+    const unsigned g = (unsigned)i + a.z0 * plane;
+    const unsigned iz = g / plane, q = g - iz * plane, iy = q / (unsigned)a.n1, ix = q - iy * (unsigned)a.n1;
+    const double x[3] = {(double)ix / (double)a.n1 - __ldg(a.xattr + 3 * lab), (double)iy / (double)a.n2 - __ldg(a.xattr + 3 * lab + 1),
+                         (double)iz / (double)a.n3 - __ldg(a.xattr + 3 * lab + 2)};
+    double xs[3] = {x[0], x[1], x[2]}, xc[3];
+    shortest(a, xs);
+    matvec3(r.c2x, xs, xc);
+    const int p0 = (int)round(x[0] - xc[0]), p1 = (int)round(x[1] - xc[1]), p2 = (int)round(x[2] - xc[2]);
+    if ((p0 | p1 | p2) == 0) {
+      if (r.apply) r.out[i] = lab + 1;
+      continue;
+    }
+    if (abs(p0) > RM_R || abs(p1) > RM_R || abs(p2) > RM_R) {
+      atomicExch(r.err, 1);
+      continue;
+    }
+    const int code = ((p0 + RM_R) * RM_W + (p1 + RM_R)) * RM_W + (p2 + RM_R);
+    if (r.apply) r.out[i] = __ldg(r.idmap + (size_t)lab * RM_CODES + code);
+    else atomicMin(r.first + (size_t)lab * RM_CODES + code, (int)g);
+  }
+}
+
+}  // namespace
+
+extern "C" int c2g_basins_remap(c2g_context* ctx, c2g_basins* res, const double* xattr, const double c2x[9], int isortho,
+                                int isortho_del, const double x2c[9], const double x2xr[9], const double xr2c[9], int nws,
+                                const double* ws_ineighc, int maxattn, int* nattn_out, int* iatt, int* ilvec, int* idg1) {
+  if (!ctx) return C2G_ERR_ARG;
+  if (!res || !xattr || !c2x || !x2c || !nattn_out || !iatt || !ilvec) return ctx->fail(C2G_ERR_ARG, "c2g_basins_remap: bad argument");
+  if (!isortho && (!x2xr || !xr2c || nws < 0 || (nws > 0 && !ws_ineighc)))
+    return ctx->fail(C2G_ERR_ARG, "c2g_basins_remap: a non-orthogonal cell needs x2xr, xr2c and the WS neighbours");
+  if (!res->has_map) return ctx->fail(C2G_ERR_STATE, "c2g_basins_remap: call c2g_basins_set_map first");
+  if (res->kind == 1 && idg1) return ctx->fail(C2G_ERR_ARG, "c2g_basins_remap: yt_remap has no idg1 output");
+  const int nattr = res->nattr;
+  if (maxattn < nattr) { *nattn_out = nattr; return ctx->fail(C2G_ERR_OVERFLOW, "c2g_basins_remap: maxattn < nattr"); }
+  for (int i = 0; i < nattr; i++) {
+    iatt[i] = i + 1;
+    ilvec[3 * i] = ilvec[3 * i + 1] = ilvec[3 * i + 2] = 0;
+  }
+  *nattn_out = nattr;
+  if (nattr == 0) return C2G_OK;
+  cudaStream_t st = ctx->stream;
+
+  RemapArgs r;
+  memset(&r, 0, sizeof(r));
+  MpArgs& a = r.a;
+  a.n1 = res->n[0]; a.n2 = res->n[1]; a.n3 = res->n[2];
+  a.isortho = isortho ? 1 : 0; a.isortho_del = isortho_del ? 1 : 0; a.nws = isortho ? 0 : nws;
+  for (int i = 0; i < 9; i++) {
+    a.x2c[i] = x2c[i];
+    a.x2xr[i] = (!isortho) ? x2xr[i] : 0.0;
+    a.xr2c[i] = (!isortho) ? xr2c[i] : 0.0;
+    r.c2x[i] = c2x[i];
+  }
+  DevBuf b_ws(ctx), b_xattr(ctx), b_first(ctx), b_idmap(ctx), b_err(ctx), b_w(ctx), b_out(ctx);
+  if (a.nws > 0) {
+    C2G_CUDA(ctx, b_ws.alloc(ctx, sizeof(double) * 3 * a.nws));
+    C2G_CUDA(ctx, cudaMemcpyAsync(b_ws.p, ws_ineighc, sizeof(double) * 3 * a.nws, cudaMemcpyHostToDevice, st));
+  }
+  C2G_CUDA(ctx, b_xattr.alloc(ctx, sizeof(double) * 3 * nattr));
+  C2G_CUDA(ctx, cudaMemcpyAsync(b_xattr.p, xattr, sizeof(double) * 3 * nattr, cudaMemcpyHostToDevice, st));
+  const size_t ntab = (size_t)nattr * RM_CODES;
+  C2G_CUDA(ctx, b_first.alloc(ctx, sizeof(int) * ntab));
+  C2G_CUDA(ctx, cudaMemsetAsync(b_first.p, 0x7f, sizeof(int) * ntab, st));
+  C2G_CUDA(ctx, b_err.alloc(ctx, sizeof(int)));
+  C2G_CUDA(ctx, cudaMemsetAsync(b_err.p, 0, sizeof(int), st));
+  a.ws = b_ws.as<double>();
+  a.xattr = b_xattr.as<double>();
+  a.map = res->d_map;
+  r.first = b_first.as<int>();
+  r.err = b_err.as<int>();
+  const size_t plane = (size_t)res->n[0] * res->n[1];
+  const int blocks = ctx->nsm * 8;
+
+  if (res->kind != 1) {
+    a.z0 = (unsigned)res->zlo;
+    a.nnl = (unsigned)(plane * (size_t)(res->zhi - res->zlo));
+    a.label = res->d_label;
+    a.mask = res->kind == 0 ? 0x7fffffff : -1;
+    if (a.nnl > 0) {
+      ctx->prof_begin("remap_scan");
+      k_remap<false><<<blocks, 256, 0, st>>>(r);
+      ctx->prof_end();
+      C2G_KERNEL_CHECK(ctx);
+    }
+    if (ctx->nranks > 1 && res->kind == 0) {  // the first point of an image may lie in another rank's slab
+      ncclResult_t rr = ncclAllReduce(r.first, r.first, ntab, ncclInt, ncclMin, (ncclComm_t)ctx->nccl, st);
+      if (rr != ncclSuccess) return ctx->fail(C2G_ERR_NCCL, "c2g_basins_remap: ncclAllReduce failed");
+    }
+  } else {
+    a.z0 = 0;
+    a.nnl = (unsigned)res->nn;
+    C2G_CUDA(ctx, b_w.alloc(ctx, sizeof(double) * res->nn));
+    a.w = b_w.as<double>();
+    for (int m = 1; m <= nattr; m++) {
+      int rc = c2g_yt_weights_device(res, m, b_w.as<double>());
+      if (rc != C2G_OK) return rc;
+      a.idb = m;
+      ctx->prof_begin("remap_scan_yt");
+      k_remap<true><<<blocks, 256, 0, st>>>(r);
+      ctx->prof_end();
+      C2G_KERNEL_CHECK(ctx);
+    }
+  }
+  std::vector<int> first(ntab);
+  int herr = 0;
+  C2G_CUDA(ctx, cudaMemcpyAsync(first.data(), r.first, sizeof(int) * ntab, cudaMemcpyDeviceToHost, st));
+  C2G_CUDA(ctx, cudaMemcpyAsync(&herr, r.err, sizeof(int), cudaMemcpyDeviceToHost, st));
+  C2G_CUDA(ctx, cudaStreamSynchronize(st));
+  if (herr) return ctx->fail(C2G_ERR_OVERFLOW, "c2g_basins_remap: a lattice vector outside -%d..%d (cell not reduced?)", RM_R, RM_R);
+  // images in the reference's order of first appearance
+  struct Img { int first, basin, code; };
+  std::vector<Img> imgs;
+  for (int b = 0; b < nattr; b++)
+    for (int c = 0; c < RM_CODES; c++)
+      if (first[(size_t)b * RM_CODES + c] != 0x7f7f7f7f) imgs.push_back({first[(size_t)b * RM_CODES + c], b, c});
+  if (res->kind == 1)
+    std::sort(imgs.begin(), imgs.end(), [](const Img& p, const Img& q) { return p.basin != q.basin ? p.basin < q.basin : p.first < q.first; });
+  else
+    std::sort(imgs.begin(), imgs.end(), [](const Img& p, const Img& q) { return p.first < q.first; });
+  const int nattn = nattr + (int)imgs.size();
+  *nattn_out = nattn;
+  if (nattn > maxattn) return ctx->fail(C2G_ERR_OVERFLOW, "c2g_basins_remap: %d attractor images, maxattn = %d", nattn, maxattn);
+  std::vector<int> idmap(ntab, 0);
+  for (size_t k = 0; k < imgs.size(); k++) {
+    const int id = nattr + (int)k;  // 0-based slot
+    iatt[id] = imgs[k].basin + 1;
+    const int c = imgs[k].code;
+    ilvec[3 * id] = c / (RM_W * RM_W) - RM_R;
+    ilvec[3 * id + 1] = (c / RM_W) % RM_W - RM_R;
+    ilvec[3 * id + 2] = c % RM_W - RM_R;
+    idmap[(size_t)imgs[k].basin * RM_CODES + c] = id + 1;
+  }
+  if (idg1 && a.nnl > 0) {
+    C2G_CUDA(ctx, b_idmap.alloc(ctx, sizeof(int) * ntab));
+    C2G_CUDA(ctx, cudaMemcpyAsync(b_idmap.p, idmap.data(), sizeof(int) * ntab, cudaMemcpyHostToDevice, st));
+    C2G_CUDA(ctx, b_out.alloc(ctx, sizeof(int) * (size_t)a.nnl));
+    r.idmap = b_idmap.as<int>();
+    r.out = b_out.as<int>();
+    r.apply = 1;
+    ctx->prof_begin("remap_apply");
+    k_remap<false><<<blocks, 256, 0, st>>>(r);
+    ctx->prof_end();
+    C2G_KERNEL_CHECK(ctx);
+    C2G_CUDA(ctx, cudaMemcpyAsync(idg1, r.out, sizeof(int) * (size_t)a.nnl, cudaMemcpyDeviceToHost, st));
+    C2G_CUDA(ctx, cudaStreamSynchronize(st));
+  }
+  ctx->prof_collect();
   return C2G_OK;
 }

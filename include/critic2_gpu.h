@@ -143,6 +143,19 @@ int c2g_integrate_multipoles(c2g_context* ctx, c2g_basins* res, int fieldhandle,
                              const double x2xr[9], const double xr2c[9], int nws, const double* ws_ineighc,
                              double omega, double* mpole);
 
+/* ---- DELOC attractor images: bader_remap (bader@proc.f90:237-296), yt_remap (yt@proc.f90:533-594) ---- */
+/* For every point: x = p/n - xattr(:,basin), xs = shortest(x), lattice vector nint(x - c2x(xs)); a non-zero vector
+ * makes the point a member of an IMAGE of its attractor.  iatt(1:nattr) = 1..nattr, ilvec(:,1:nattr) = 0; the images
+ * follow, numbered in the order in which the reference's scan (index 1 fastest) first meets them (YT: basin by basin,
+ * points with |w| >= 1e-15).  iatt(nattn): attractor of every image, ilvec(3,nattn): its lattice vector,
+ * idg1(n1,n2,n3) (Bader labels / ISOSURFACE regions only, may be NULL; must be NULL for a YT result): image id per
+ * point.  c2x = crystal%m_c2x; the other cell arguments as in c2g_integrate_multipoles.  Caller-allocated outputs of
+ * capacity maxattn; when there are more images the call returns C2G_ERR_OVERFLOW with *nattn set to the number
+ * needed, and the caller retries.  Multi-GPU Bader: idg1 is the rank's slab, iatt/ilvec are global. */
+int c2g_basins_remap(c2g_context* ctx, c2g_basins* res, const double* xattr, const double c2x[9], int isortho,
+                     int isortho_del, const double x2c[9], const double x2xr[9], const double xr2c[9], int nws,
+                     const double* ws_ineighc, int maxattn, int* nattn, int* iatt, int* ilvec, int* idg1);
+
 /* ---- YT: Yu-Trinkle weights (yt@proc.f90:77-211) ---- */
 /* vec(3,nvec), area(nvec): Voronoi-relevant grid steps and facet areas from grid3%init_geometry
  * (grid3mod@proc.f90:3197).  Maxima are returned in decreasing density (= reference discovery order). */

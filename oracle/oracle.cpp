@@ -1625,6 +1625,93 @@ void orc_multipoles_weighted(const double* w, const int* n, const double* xattr_
   for (int e = 0; e < nlm; e++) mpole_m[e] = mpole_m[e] * omega / ntot;
 }
 
+// bader_remap, src/bader@proc.f90:237-296 (DELOC): attractor images.  A point whose shortest vector to its attractor
+// differs from the in-cell difference by a lattice vector p /= 0 belongs to the image (attractor, p); images are
+// numbered nattr+1, nattr+2, ... in the order in which the scan (m1 fastest, m3 slowest) first meets them.
+// Out: idg1(n1,n2,n3), iatt(nattn), ilvec(3,nattn), *nattn.  Returns -2 when maxattn is too small.  idg == 0 is
+// skipped (the reference would read xattr(:,0)).
+int orc_bader_remap(const int* idg, const int* n, int nattr, const double* xattr, const double* c2x, int isortho,
+                    int isortho_del, const double* x2c, const double* x2xr, const double* xr2c, int nws, const double* ws,
+                    int maxattn, int* nattn_out, int* iatt, int* ilvec, int* idg1) {
+  const OrcCell cell{isortho, isortho_del, nws, x2c, x2xr, xr2c, ws};
+  if (nattr > maxattn) return -2;
+  int nattn = nattr;
+  for (int i = 0; i < nattr; i++) {
+    iatt[i] = i + 1;
+    ilvec[3 * i] = ilvec[3 * i + 1] = ilvec[3 * i + 2] = 0;
+  }
+  for (int m3 = 0; m3 < n[2]; m3++)
+    for (int m2 = 0; m2 < n[1]; m2++)
+      for (int m1 = 0; m1 < n[0]; m1++) {
+        const size_t q = (size_t)m1 + (size_t)n[0] * ((size_t)m2 + (size_t)n[1] * m3);
+        const int b = idg[q];
+        idg1[q] = b;
+        if (b < 1 || b > nattr) continue;
+        const double x[3] = {(double)m1 / (double)n[0] - xattr[3 * (b - 1)], (double)m2 / (double)n[1] - xattr[3 * (b - 1) + 1],
+                             (double)m3 / (double)n[2] - xattr[3 * (b - 1) + 2]};
+        double xs[3] = {x[0], x[1], x[2]}, xc[3];
+        orc_shortest(cell, xs);
+        matvec3(c2x, xs, xc);
+        const int p[3] = {(int)std::lround(x[0] - xc[0]), (int)std::lround(x[1] - xc[1]), (int)std::lround(x[2] - xc[2])};
+        if (p[0] != 0 || p[1] != 0 || p[2] != 0) {
+          bool found = false;
+          for (int i = nattr; i < nattn; i++)
+            if (iatt[i] == b && ilvec[3 * i] == p[0] && ilvec[3 * i + 1] == p[1] && ilvec[3 * i + 2] == p[2]) {
+              found = true;
+              idg1[q] = i + 1;
+              break;
+            }
+          if (!found) {
+            if (nattn + 1 > maxattn) return -2;
+            ilvec[3 * nattn] = p[0]; ilvec[3 * nattn + 1] = p[1]; ilvec[3 * nattn + 2] = p[2];
+            iatt[nattn] = b;
+            nattn++;
+            idg1[q] = nattn;
+          }
+        }
+      }
+  *nattn_out = nattn;
+  return 0;
+}
+
+// One basin of yt_remap, src/yt@proc.f90:557-589: w = yt_weights(idb = ib); the images of basin ib met by the points
+// with |w| >= 1e-15 are appended to (iatt, ilvec) in scan order.  *nattn is updated in place (start it at nattr with
+// iatt(i) = i, ilvec = 0 like :546-554).
+int orc_yt_remap_basin(const double* w, const int* n, int nattr, int ib, const double* xattr_i, const double* c2x, int isortho,
+                       int isortho_del, const double* x2c, const double* x2xr, const double* xr2c, int nws, const double* ws,
+                       int maxattn, int* nattn_io, int* iatt, int* ilvec) {
+  const OrcCell cell{isortho, isortho_del, nws, x2c, x2xr, xr2c, ws};
+  int nattn = *nattn_io;
+  for (int m3 = 0; m3 < n[2]; m3++)
+    for (int m2 = 0; m2 < n[1]; m2++)
+      for (int m1 = 0; m1 < n[0]; m1++) {
+        const size_t q = (size_t)m1 + (size_t)n[0] * ((size_t)m2 + (size_t)n[1] * m3);
+        if (std::fabs(w[q]) < 1e-15) continue;
+        const double x[3] = {(double)m1 / (double)n[0] - xattr_i[0], (double)m2 / (double)n[1] - xattr_i[1],
+                             (double)m3 / (double)n[2] - xattr_i[2]};
+        double xs[3] = {x[0], x[1], x[2]}, xc[3];
+        orc_shortest(cell, xs);
+        matvec3(c2x, xs, xc);
+        const int p[3] = {(int)std::lround(x[0] - xc[0]), (int)std::lround(x[1] - xc[1]), (int)std::lround(x[2] - xc[2])};
+        if (p[0] != 0 || p[1] != 0 || p[2] != 0) {
+          bool found = false;
+          for (int j = nattr; j < nattn; j++)
+            if (iatt[j] == ib && ilvec[3 * j] == p[0] && ilvec[3 * j + 1] == p[1] && ilvec[3 * j + 2] == p[2]) {
+              found = true;
+              break;
+            }
+          if (!found) {
+            if (nattn + 1 > maxattn) return -2;
+            ilvec[3 * nattn] = p[0]; ilvec[3 * nattn + 1] = p[1]; ilvec[3 * nattn + 2] = p[2];
+            iatt[nattn] = ib;
+            nattn++;
+          }
+        }
+      }
+  *nattn_io = nattn;
+  return 0;
+}
+
 // one evaluation of genrlm_real(lmax, tosphere(v)) for the known-answer tests
 void orc_rlm_real(const double* v, int lmax, double* rrlm) {
   double r, tp[2];

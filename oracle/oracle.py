@@ -266,6 +266,48 @@ def multipoles_weighted(w, xattr_m, lmax, fint, cell: Cell, omega):
     return mp
 
 
+def bader_remap(idg, xattr, cell: Cell, maxattn=None):
+    """bader_remap (bader@proc.f90:237-296): (nattn, idg1, iatt[nattn], ilvec[3,nattn])."""
+    idg = _i32(idg)
+    n = np.array(idg.shape, dtype=np.int32)
+    xattr = _f64(np.asarray(xattr, dtype=np.float64).reshape(3, -1))
+    nattr = xattr.shape[1]
+    maxattn = nattr * 125 if maxattn is None else maxattn
+    c2x = _m33(np.linalg.inv(cell.x2c))
+    iatt = np.zeros(maxattn, dtype=np.int32)
+    ilvec = np.zeros((3, maxattn), dtype=np.int32, order="F")
+    idg1 = np.zeros(idg.shape, dtype=np.int32, order="F")
+    nattn = C.c_int(0)
+    rc = lib().orc_bader_remap(_p(idg, C.c_int), _p(n, C.c_int), C.c_int(nattr), _p(xattr, C.c_double), _p(c2x, C.c_double),
+                               *cell.args(), C.c_int(maxattn), C.byref(nattn), _p(iatt, C.c_int), _p(ilvec, C.c_int),
+                               _p(idg1, C.c_int))
+    if rc != 0:
+        raise RuntimeError(f"orc_bader_remap failed rc={rc}")
+    return nattn.value, idg1, iatt[: nattn.value].copy(), ilvec[:, : nattn.value].copy()
+
+
+def yt_remap(d: "YtData", shape, xattr, cell: Cell, maxattn=None):
+    """yt_remap (yt@proc.f90:533-594): (nattn, iatt[nattn], ilvec[3,nattn])."""
+    xattr = _f64(np.asarray(xattr, dtype=np.float64).reshape(3, -1))
+    nattr = xattr.shape[1]
+    n = np.array(shape, dtype=np.int32)
+    maxattn = nattr * 125 if maxattn is None else maxattn
+    c2x = _m33(np.linalg.inv(cell.x2c))
+    iatt = np.zeros(maxattn, dtype=np.int32)
+    iatt[:nattr] = np.arange(1, nattr + 1)
+    ilvec = np.zeros((3, maxattn), dtype=np.int32, order="F")
+    nattn = C.c_int(nattr)
+    for ib in range(1, nattr + 1):
+        w = _f64(yt_weights(d, ib, tuple(int(v) for v in shape)))
+        xi = np.ascontiguousarray(xattr[:, ib - 1])
+        rc = lib().orc_yt_remap_basin(_p(w, C.c_double), _p(n, C.c_int), C.c_int(nattr), C.c_int(ib), _p(xi, C.c_double),
+                                      _p(c2x, C.c_double), *cell.args(), C.c_int(maxattn), C.byref(nattn), _p(iatt, C.c_int),
+                                      _p(ilvec, C.c_int))
+        if rc != 0:
+            raise RuntimeError(f"orc_yt_remap_basin failed rc={rc}")
+    return nattn.value, iatt[: nattn.value].copy(), ilvec[:, : nattn.value].copy()
+
+
 def rlm_real(v, lmax):
     """genrlm_real(lmax, tosphere(v)) (tools_math@proc.f90:273-306, :381-406)."""
     v = np.ascontiguousarray(v, dtype=np.float64)

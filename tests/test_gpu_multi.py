@@ -61,6 +61,10 @@ def test_slab_sharded_bader_equals_oracle(nranks, name):
         scale = np.abs(mref[0]).max() * rmax ** np.repeat(np.arange(4), 2 * np.arange(4) + 1)
         for p in parts:
             assert np.all(np.abs(p["mpole"] - mref) <= 1e-10 * scale[:, None])
+        nattn_o, idg1_o, iatt_o, ilvec_o = orc.bader_remap(idg, xattr, cell)
+        assert np.array_equal(np.concatenate([p["rm_idg1"] for p in parts], axis=2), idg1_o)
+        for p in parts:
+            assert np.array_equal(p["rm_iatt"], iatt_o) and np.array_equal(p["rm_ilvec"], ilvec_o)
     # NCIPLOT sharded along i: the ranks' pieces concatenate to the single-process result of the oracle
     crho_o, cgrad_o = orc.nci_rdg(c["f"], c["x2c"])
     assert [int(p["nci_ilo"]) for p in parts][1:] == [int(p["nci_ihi"]) for p in parts][:-1]

@@ -34,6 +34,9 @@ for algo in (capi.BADER_EXACT, capi.BADER_FAST):
         xattr = np.asarray(c["atoms"], dtype=float).T
         if xattr.shape[1] == na:
             out["mpole"] = ctx.integrate_multipoles(b, h, 3, xattr, x2c, S.omega(x2c), **kw)
+            # DELOC attractor images: per-slab first-appearance tables min-reduced over NCCL, idg1 per slab
+            nattn, idg1, iatt, ilvec = ctx.basins_remap(b, xattr, x2c, shape=(n[0], n[1], max(zhi - zlo, 0)), **kw)
+            out["rm_idg1"] = idg1; out["rm_iatt"] = iatt; out["rm_ilvec"] = ilvec
     b.free()
 # NCIPLOT: the output lattice is sharded along i, no collective
 ilo, ihi = ctx.nci_range(n[0])
