@@ -13,7 +13,7 @@ module critic2_gpu
 
   public :: gpu_enabled, gpu_init, gpu_end
   public :: gpu_bader_integrate, gpu_yt_integrate, gpu_yt_isosurface, gpu_integrate_fields, gpu_integrate_multipoles
-  public :: gpu_nci_rdg, gpu_nci_rdg_fourier, gpu_grid_fft, gpu_read_text_block, gpu_write_text_block, gpu_wcube_block
+  public :: gpu_nci_rdg, gpu_nci_rdg_fourier, gpu_grid_fft, gpu_read_text_block, gpu_write_text_block, gpu_wcube_block, gpu_basins_remap
 
   logical :: gpu_enabled = .false.        !< set by gpu_init (environment variable CRITIC2_GPU=1)
   type(c_ptr) :: ctx = c_null_ptr         !< c2g_context
@@ -89,6 +89,16 @@ module critic2_gpu
        integer(c_int) :: handle
        integer(c_int) :: c2g_basins_weight_grid
      end function c2g_basins_weight_grid
+     function c2g_basins_remap(ctx,res,xattr,c2x,isortho,isortho_del,x2c,x2xr,xr2c,nws,ws_ineighc,maxattn,nattn,&
+        iatt,ilvec,idg1) bind(c,name="c2g_basins_remap")
+       import :: c_int, c_ptr, c_double
+       type(c_ptr), value :: ctx, res
+       real(c_double) :: xattr(3,*), c2x(3,3), x2c(3,3), x2xr(3,3), xr2c(3,3), ws_ineighc(3,*)
+       integer(c_int), value :: isortho, isortho_del, nws, maxattn
+       integer(c_int) :: nattn, iatt(*), ilvec(3,*)
+       type(c_ptr), value :: idg1          ! c_loc of idg1(n1,n2,n3), or c_null_ptr (yt_remap)
+       integer(c_int) :: c2g_basins_remap
+     end function c2g_basins_remap
      function c2g_basins_maxima(res,pmax) bind(c,name="c2g_basins_maxima")
        import :: c_int, c_ptr
        type(c_ptr), value :: res
@@ -561,6 +571,56 @@ contains
     write (lu) text
     call check(c2g_grid_free(ctx,h),"gpu_write_text_block")
   end subroutine gpu_write_text_block
+
+  !> GPU body of bader_remap (src/bader@proc.f90:237-296) and yt_remap (src/yt@proc.f90:533-594): the attractor
+  !> images used by the delocalization indices.  Same outputs as the reference: nattn, iatt, ilvec and, for Bader
+  !> basins, idg1.  The basins of the last gpu_bader_integrate / gpu_yt_integrate call are used.
+  subroutine gpu_basins_remap(c,bas,nattn,ilvec,iatt,idg1)
+    use crystalmod, only: crystal
+    use types, only: basindat
+    type(crystal), intent(in) :: c
+    type(basindat), intent(in) :: bas
+    integer, intent(out) :: nattn
+    integer, allocatable, intent(inout) :: iatt(:), ilvec(:,:)
+    integer, allocatable, intent(inout), target, optional :: idg1(:,:,:)
+    integer(c_int) :: cap, ier, nws, nn
+    integer(c_int), allocatable :: iatt_(:), ilvec_(:,:)
+    type(c_ptr) :: pidg1
+    real*8 :: wsdum(3,1)
+
+    pidg1 = c_null_ptr
+    if (present(idg1)) then
+       if (allocated(idg1)) deallocate(idg1)
+       allocate(idg1(bas%n(1),bas%n(2),bas%n(3)))
+       pidg1 = c_loc(idg1)
+    end if
+    nws = 0
+    if (allocated(c%ws_ineighc)) nws = int(c%ws_nf,c_int)
+    cap = int(27*max(bas%nattr,1),c_int)
+    do
+       if (allocated(iatt_)) deallocate(iatt_,ilvec_)
+       allocate(iatt_(cap),ilvec_(3,cap))
+       if (nws > 0) then
+          ier = c2g_basins_remap(ctx,basins,bas%xattr,c%m_c2x,merge(1_c_int,0_c_int,c%isortho),&
+             merge(1_c_int,0_c_int,c%isortho_del),c%m_x2c,c%m_x2xr,c%m_xr2c,nws,c%ws_ineighc,cap,nn,iatt_,ilvec_,pidg1)
+       else
+          ier = c2g_basins_remap(ctx,basins,bas%xattr,c%m_c2x,merge(1_c_int,0_c_int,c%isortho),&
+             merge(1_c_int,0_c_int,c%isortho_del),c%m_x2c,c%m_x2xr,c%m_xr2c,0_c_int,wsdum,cap,nn,iatt_,ilvec_,pidg1)
+       end if
+       if (ier == 6 .and. nn > cap) then     ! C2G_ERR_OVERFLOW: nn = capacity needed
+          cap = nn
+          cycle
+       end if
+       call check(ier,"gpu_basins_remap")
+       exit
+    end do
+    nattn = nn
+    if (allocated(iatt)) deallocate(iatt)
+    if (allocated(ilvec)) deallocate(ilvec)
+    allocate(iatt(nattn),ilvec(3,nattn))
+    iatt = iatt_(1:nattn)
+    ilvec = ilvec_(:,1:nattn)
+  end subroutine gpu_basins_remap
 
   !> WCUBE (int_cubew, src/integration@proc.f90:4449-4462): the value block of the weight cube of attractor i, from
   !> the basins resident on the device -- the YT weights (:4451) or the indicator of idg == i (:4455-4458) -- written to
