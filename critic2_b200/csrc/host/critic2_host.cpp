@@ -229,6 +229,13 @@ void intgrid_fields(const system& s, const basindat& bas, const std::vector<cons
   vol.assign(v.begin(), v.begin() + bas.nattr);
   res.assign(nprop, int_result());
   for (int k = 0; k < nprop; k++) res[k].psum.assign(psum.begin() + (size_t)k * nrow, psum.begin() + (size_t)k * nrow + bas.nattr);
+  // ONLY / ONLY_RANGE: the reference leaves the sums of the attractors it skips at zero (integration@proc.f90:1210, :1292)
+  if ((int)bas.docelatom.size() == bas.nattr)
+    for (int i = 0; i < bas.nattr; i++)
+      if (!bas.docelatom[i]) {
+        vol[i] = 0.0;
+        for (int k = 0; k < nprop; k++) res[k].psum[i] = 0.0;
+      }
 }
 
 void intgrid_multipoles(const system& s, const basindat& bas, const double* fint, int lmax,

@@ -71,6 +71,7 @@ struct basindat {
   std::vector<double> xattr;   // (3,nattr) crystallographic
   std::vector<int> idg;        // idg(n1,n2,n3)
   bool is_yt = false;          // weights live on the device (the reference's luw scratch unit)
+  std::vector<unsigned char> docelatom;  // per attractor (docelatom(icp(i)), ONLY / ONLY_RANGE); empty = all
   double isov = 0.0;           // ISOSURFACE: contour value (already negated by the driver for LOWER, integration@proc.f90:260)
 };
 

@@ -429,6 +429,16 @@ contains
     call check(c2g_integrate(ctx,basins,int(nprop,c_int),h,omega,psum0,vol0),"gpu_integrate_fields")
     psum(1:bas%nattr,1:nprop) = psum0(1:bas%nattr,1:nprop)
     vol(1:bas%nattr) = vol0(1:bas%nattr)
+    ! ONLY / ONLY_RANGE: the reference skips the attractors with docelatom = .false. and leaves their sums at zero
+    ! (:1210, :1292); the device integrates every basin in the same pass, so the rows are cleared here
+    if (allocated(bas%docelatom) .and. allocated(bas%icp)) then
+       do k = 1, bas%nattr
+          if (.not.bas%docelatom(bas%icp(k))) then
+             psum(k,1:nprop) = 0d0
+             vol(k) = 0d0
+          end if
+       end do
+    end if
     do k = 1, nprop
        call check(c2g_grid_free(ctx,h(k)),"gpu_integrate_fields")
     end do
