@@ -1712,6 +1712,174 @@ int orc_yt_remap_basin(const double* w, const int* n, int nattr, int ib, const d
   return 0;
 }
 
+// ---------------------------------------------------------------------------
+// HIRSHFELD on a grid: promolecular_array3 / promolecular_atom (src/crystalmod@complex.f90:436-470,
+// src/crystalmod@env.f90:622-748), grid1%interp (src/grid1mod@proc.f90:86-137) and the loop of
+// intgrid_hirshfeld_fields (src/integration@proc.f90:1552-1596).
+// The reference finds the atoms near a point with its block environment (list_near_atoms); the sums below run over the
+// same set -- every periodic image within the species cutoff -- enumerated by brute force, so values agree to
+// rounding (the order of the additions differs), not bit for bit.
+// Species tables: spc_ngrid, spc_off (offset into rtab/ftab), spc_rmax (g%rmax), spc_rcut = min(cutrad(z), g%rmax),
+// spc_a, spc_b (r(i) = a exp(b (i-1))); ngrid = 0 marks a species without a usable grid (skipped).
+// ---------------------------------------------------------------------------
+}  // extern "C"
+namespace {
+
+struct OrcSpecies {
+  int nspc;
+  const int *ngrid, *off;
+  const double *a, *b, *rmax, *rcut, *rtab, *ftab;
+};
+
+// grid1%interp, value only (grid1mod@proc.f90:86-137): 4-node Lagrange on the logarithmic grid
+inline double orc_grid1_interp(const OrcSpecies& S, int is, double r0) {
+  const int ng = S.ngrid[is];
+  if (ng <= 0) return 0.0;
+  if (r0 >= S.rmax[is]) return 0.0;
+  const double* rg = S.rtab + S.off[is];
+  const double* fg = S.ftab + S.off[is];
+  int ir;
+  double r;
+  if (r0 <= rg[0]) { ir = 1; r = rg[0]; }
+  else { ir = 1 + (int)std::floor(std::log(r0 / S.a[is]) / S.b[is]); r = r0; }
+  const int i0 = std::min(std::max(ir, 2), ng - 2) - 2;  // nodes i0+1 .. i0+4 (1-based) = rg[i0 .. i0+3]
+  double rr[4], dr1[4], x1[4][4];
+  for (int i = 0; i < 4; i++) {
+    rr[i] = rg[i0 + i];
+    dr1[i] = r - rr[i];
+    for (int j = 0; j < i; j++) {
+      x1[i][j] = 1.0 / (rr[i] - rr[j]);
+      x1[j][i] = -x1[i][j];
+    }
+  }
+  double f = 0.0;
+  for (int i = 0; i < 4; i++) {
+    double prod = 1.0;
+    for (int j = 0; j < 4; j++) {
+      if (i == j) continue;
+      prod = prod * dr1[j] * x1[i][j];
+    }
+    f = f + fg[i0 + i] * prod;
+  }
+  return f;
+}
+
+struct OrcImage { int atom; double x[3]; };
+
+// every periodic image of every atom that can lie within the largest cutoff of some point of the cell
+inline std::vector<OrcImage> orc_images(const double* x2c, int nat, const double* xat, double rcutmax) {
+  // plane spacings h_i = 1 / |row i of c2x|
+  double c2x[9];
+  {
+    auto A = [&](int i, int j) { return x2c[i + 3 * j]; };
+    const double det = A(0, 0) * (A(1, 1) * A(2, 2) - A(1, 2) * A(2, 1)) - A(0, 1) * (A(1, 0) * A(2, 2) - A(1, 2) * A(2, 0)) +
+                       A(0, 2) * (A(1, 0) * A(2, 1) - A(1, 1) * A(2, 0));
+    const double d = 1.0 / det;
+    c2x[0] = (A(1, 1) * A(2, 2) - A(1, 2) * A(2, 1)) * d; c2x[3] = (A(0, 2) * A(2, 1) - A(0, 1) * A(2, 2)) * d; c2x[6] = (A(0, 1) * A(1, 2) - A(0, 2) * A(1, 1)) * d;
+    c2x[1] = (A(1, 2) * A(2, 0) - A(1, 0) * A(2, 2)) * d; c2x[4] = (A(0, 0) * A(2, 2) - A(0, 2) * A(2, 0)) * d; c2x[7] = (A(0, 2) * A(1, 0) - A(0, 0) * A(1, 2)) * d;
+    c2x[2] = (A(1, 0) * A(2, 1) - A(1, 1) * A(2, 0)) * d; c2x[5] = (A(0, 1) * A(2, 0) - A(0, 0) * A(2, 1)) * d; c2x[8] = (A(0, 0) * A(1, 1) - A(0, 1) * A(1, 0)) * d;
+  }
+  int m[3];
+  for (int i = 0; i < 3; i++) {
+    const double g = std::sqrt(c2x[i] * c2x[i] + c2x[i + 3] * c2x[i + 3] + c2x[i + 6] * c2x[i + 6]);  // 1/h_i
+    m[i] = (int)std::ceil(rcutmax * g) + 1;
+  }
+  std::vector<OrcImage> im;
+  for (int a = 0; a < nat; a++)
+    for (int l1 = -m[0]; l1 <= m[0]; l1++)
+      for (int l2 = -m[1]; l2 <= m[1]; l2++)
+        for (int l3 = -m[2]; l3 <= m[2]; l3++) {
+          const double xf[3] = {xat[3 * a] - std::floor(xat[3 * a]) + l1, xat[3 * a + 1] - std::floor(xat[3 * a + 1]) + l2,
+                                xat[3 * a + 2] - std::floor(xat[3 * a + 2]) + l3};
+          OrcImage q;
+          q.atom = a;
+          matvec3(x2c, xf, q.x);
+          im.push_back(q);
+        }
+  return im;
+}
+
+}  // namespace
+extern "C" {
+
+double orc_grid1_interp_value(int ngrid, double a, double b, double rmax, const double* rtab, const double* ftab, double r0) {
+  const int off = 0;
+  const double rcut = rmax;
+  const OrcSpecies S{1, &ngrid, &off, &a, &b, &rmax, &rcut, rtab, ftab};
+  return orc_grid1_interp(S, 0, r0);
+}
+
+// promolecular_array3 (crystalmod@complex.f90:436-470) with the optional fragment (infrag(nat), may be null = all atoms)
+void orc_promolecular_grid(const int* n, const double* x2c, int nat, const double* xat, const int* ispc, int nspc,
+                           const int* spc_ngrid, const int* spc_off, const double* spc_a, const double* spc_b,
+                           const double* spc_rmax, const double* spc_rcut, const double* rtab, const double* ftab,
+                           const unsigned char* infrag, double* out) {
+  const OrcSpecies S{nspc, spc_ngrid, spc_off, spc_a, spc_b, spc_rmax, spc_rcut, rtab, ftab};
+  double rcutmax = 0.0;
+  for (int i = 0; i < nspc; i++) rcutmax = std::max(rcutmax, spc_rcut[i]);
+  const std::vector<OrcImage> im = orc_images(x2c, nat, xat, rcutmax);
+#pragma omp parallel for schedule(dynamic)
+  for (int k = 0; k < n[2]; k++)
+    for (int j = 0; j < n[1]; j++)
+      for (int i = 0; i < n[0]; i++) {
+        const double xf[3] = {(double)i / (double)n[0], (double)j / (double)n[1], (double)k / (double)n[2]};
+        double xc[3];
+        matvec3(x2c, xf, xc);
+        double f = 0.0;
+        for (const OrcImage& q : im) {
+          if (infrag && !infrag[q.atom]) continue;
+          const int is = ispc[q.atom] - 1;
+          if (spc_ngrid[is] <= 0) continue;
+          const double d0 = xc[0] - q.x[0], d1 = xc[1] - q.x[1], d2 = xc[2] - q.x[2];
+          double r = std::sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+          if (r > spc_rcut[is]) continue;                                   // list_near_atoms(up2dsp), env.f90:692, :713
+          r = std::max(std::max(r, rtab[spc_off[is]]), 1e-14);              // :724
+          double rho = orc_grid1_interp(S, is, r);
+          rho = std::max(rho, 0.0);                                         // :726
+          f = f + rho;
+        }
+        out[(size_t)i + (size_t)n[0] * ((size_t)j + (size_t)n[1] * k)] = f;
+      }
+}
+
+// intgrid_hirshfeld_fields, integration@proc.f90:1552-1596: psum(nat,nprop), vol(nat); domask(nat) = docelatom(icp(.))
+void orc_hirshfeld_fields(const int* n, const double* x2c, int nat, const double* xat, const int* ispc, int nspc,
+                          const int* spc_ngrid, const int* spc_off, const double* spc_a, const double* spc_b,
+                          const double* spc_rmax, const double* spc_rcut, const double* rtab, const double* ftab,
+                          const double* promol, const unsigned char* domask, int nprop, const double* const* fields, double omega,
+                          double* psum, double* vol) {
+  const OrcSpecies S{nspc, spc_ngrid, spc_off, spc_a, spc_b, spc_rmax, spc_rcut, rtab, ftab};
+  double rcutmax = 0.0;
+  for (int i = 0; i < nspc; i++) rcutmax = std::max(rcutmax, spc_rcut[i]);
+  const std::vector<OrcImage> im = orc_images(x2c, nat, xat, rcutmax);
+  std::vector<double> acc((size_t)nat * (nprop + 1), 0.0);
+  for (int k = 0; k < n[2]; k++)
+    for (int j = 0; j < n[1]; j++)
+      for (int i = 0; i < n[0]; i++) {
+        const size_t q0 = (size_t)i + (size_t)n[0] * ((size_t)j + (size_t)n[1] * k);
+        const double xf[3] = {(double)i / (double)n[0], (double)j / (double)n[1], (double)k / (double)n[2]};
+        double xc[3];
+        matvec3(x2c, xf, xc);
+        const double fac = 1.0 / std::max(promol[q0], VSMALL);
+        for (const OrcImage& q : im) {
+          if (domask && !domask[q.atom]) continue;
+          const int is = ispc[q.atom] - 1;
+          if (spc_ngrid[is] <= 0) continue;
+          const double d0 = xc[0] - q.x[0], d1 = xc[1] - q.x[1], d2 = xc[2] - q.x[2];
+          const double r = std::sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+          if (r > spc_rcut[is]) continue;
+          const double tosum = fac * orc_grid1_interp(S, is, r);             // :1566-1567
+          acc[(size_t)q.atom * (nprop + 1) + nprop] += tosum;               // volume (:1574)
+          for (int l = 0; l < nprop; l++) acc[(size_t)q.atom * (nprop + 1) + l] += tosum * fields[l][q0];  // :1576
+        }
+      }
+  const double ntot = (double)n[0] * (double)n[1] * (double)n[2];
+  for (int a = 0; a < nat; a++) {
+    vol[a] = acc[(size_t)a * (nprop + 1) + nprop] * omega / ntot;           // :1590
+    for (int l = 0; l < nprop; l++) psum[a + (size_t)nat * l] = acc[(size_t)a * (nprop + 1) + l] * omega / ntot;
+  }
+}
+
 // one evaluation of genrlm_real(lmax, tosphere(v)) for the known-answer tests
 void orc_rlm_real(const double* v, int lmax, double* rrlm) {
   double r, tp[2];

@@ -308,6 +308,67 @@ def yt_remap(d: "YtData", shape, xattr, cell: Cell, maxattn=None):
     return nattn.value, iatt[: nattn.value].copy(), ilvec[:, : nattn.value].copy()
 
 
+class AtomicGrids:
+    """The grid1 objects of the species (grid1mod.f90): logarithmic radial grids r(i) = a exp(b (i-1)) with the atomic
+    density f(i), g%rmax, and the cutoff min(cutrad(z), g%rmax) used by promolecular_atom (crystalmod@env.f90:671-684)."""
+
+    def __init__(self, tables):
+        """tables: list of dicts with keys a, b, ngrid, f (array), optional rcut."""
+        self.nspc = len(tables)
+        self.ngrid = np.array([t["ngrid"] for t in tables], dtype=np.int32)
+        self.off = np.concatenate([[0], np.cumsum(self.ngrid)[:-1]]).astype(np.int32)
+        self.a = np.array([t["a"] for t in tables], dtype=np.float64)
+        self.b = np.array([t["b"] for t in tables], dtype=np.float64)
+        rs = [t["a"] * np.exp(t["b"] * np.arange(t["ngrid"])) for t in tables]
+        self.rtab = np.concatenate(rs).astype(np.float64)
+        self.ftab = np.concatenate([np.asarray(t["f"], dtype=np.float64) for t in tables])
+        self.rmax = np.array([r[-1] for r in rs], dtype=np.float64)           # g%rmax = r(ngrid)
+        self.rcut = np.array([min(t.get("rcut", r[-1]), r[-1]) for t, r in zip(tables, rs)], dtype=np.float64)
+
+    def args(self):
+        return (C.c_int(self.nspc), _p(self.ngrid, C.c_int), _p(self.off, C.c_int), _p(self.a, C.c_double), _p(self.b, C.c_double),
+                _p(self.rmax, C.c_double), _p(self.rcut, C.c_double), _p(self.rtab, C.c_double), _p(self.ftab, C.c_double))
+
+    def interp(self, isp, r0):
+        lib().orc_grid1_interp_value.restype = C.c_double
+        o, ng = int(self.off[isp]), int(self.ngrid[isp])
+        rt, ft = self.rtab[o:o + ng].copy(), self.ftab[o:o + ng].copy()
+        return float(lib().orc_grid1_interp_value(C.c_int(ng), C.c_double(self.a[isp]), C.c_double(self.b[isp]),
+                                                  C.c_double(self.rmax[isp]), _p(rt, C.c_double), _p(ft, C.c_double), C.c_double(r0)))
+
+
+def promolecular_grid(n, x2c, atoms, ispc, grids: AtomicGrids, infrag=None):
+    """promolecular_array3 (crystalmod@complex.f90:436-470): f[n1,n2,n3]; ispc 1-based species of every atom."""
+    n = np.array(n, dtype=np.int32)
+    xat = _f64(np.asarray(atoms, dtype=np.float64).T)
+    isp = np.ascontiguousarray(ispc, dtype=np.int32)
+    fr = None if infrag is None else np.ascontiguousarray(infrag, dtype=np.uint8)
+    out = np.zeros(tuple(int(v) for v in n), order="F")
+    x2cf = _m33(x2c)
+    lib().orc_promolecular_grid(_p(n, C.c_int), _p(x2cf, C.c_double), C.c_int(xat.shape[1]), _p(xat, C.c_double), _p(isp, C.c_int),
+                                *grids.args(), None if fr is None else _p(fr, C.c_ubyte), _p(out, C.c_double))
+    return out
+
+
+def hirshfeld_fields(promol, x2c, atoms, ispc, grids: AtomicGrids, fields, omega, domask=None):
+    """intgrid_hirshfeld_fields (integration@proc.f90:1552-1596): (vol[nat], psum[nat, nprop])."""
+    promol = _f64(promol)
+    n = np.array(promol.shape, dtype=np.int32)
+    xat = _f64(np.asarray(atoms, dtype=np.float64).T)
+    nat = xat.shape[1]
+    isp = np.ascontiguousarray(ispc, dtype=np.int32)
+    dm = None if domask is None else np.ascontiguousarray(domask, dtype=np.uint8)
+    fl = [_f64(x) for x in fields]
+    arr = (C.POINTER(C.c_double) * max(len(fl), 1))(*[_p(x, C.c_double) for x in fl])
+    vol = np.zeros(nat)
+    psum = np.zeros((nat, len(fl)), order="F")
+    x2cf = _m33(x2c)
+    lib().orc_hirshfeld_fields(_p(n, C.c_int), _p(x2cf, C.c_double), C.c_int(nat), _p(xat, C.c_double), _p(isp, C.c_int),
+                               *grids.args(), _p(promol, C.c_double), None if dm is None else _p(dm, C.c_ubyte),
+                               C.c_int(len(fl)), arr, C.c_double(omega), _p(psum, C.c_double), _p(vol, C.c_double))
+    return vol, psum
+
+
 def rlm_real(v, lmax):
     """genrlm_real(lmax, tosphere(v)) (tools_math@proc.f90:273-306, :381-406)."""
     v = np.ascontiguousarray(v, dtype=np.float64)
