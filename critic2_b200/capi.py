@@ -25,7 +25,7 @@ EXPORTS = [
     "c2g_init", "c2g_nccl_unique_id", "c2g_init_multi", "c2g_finalize", "c2g_last_error", "c2g_describe",
     "c2g_grid_upload", "c2g_grid_upload_slab", "c2g_slab_range", "c2g_slab_bounds_query", "c2g_grid_alloc", "c2g_grid_download", "c2g_grid_download_slab", "c2g_grid_free", "c2g_grid_promolecular",
     "c2g_bader_assign", "c2g_basins_maxima", "c2g_basins_counts", "c2g_basins_set_map", "c2g_basins_labels",
-    "c2g_basins_relabel", "c2g_basins_nattr", "c2g_basins_free", "c2g_basins_stats", "c2g_integrate", "c2g_integrate_multipoles", "c2g_basins_remap", "c2g_yt_build",
+    "c2g_basins_relabel", "c2g_basins_nattr", "c2g_basins_free", "c2g_basins_stats", "c2g_integrate", "c2g_integrate_multipoles", "c2g_promolecular_grid", "c2g_hirshfeld_integrate", "c2g_basins_remap", "c2g_yt_build",
     "c2g_yt_weights", "c2g_basins_weight_grid", "c2g_yt_isosurface", "c2g_nci_rdg", "c2g_nci_rdg_resident", "c2g_fft_derivative", "c2g_nci_rdg_fourier", "c2g_nci_range", "c2g_grid_upload_async", "c2g_basins_labels_async", "c2g_grid_parse_text", "c2g_grid_format_text", "c2g_profile_enable", "c2g_profile_count",
     "c2g_profile_get", "c2g_profile_reset", "c2g_launch_count", "c2g_flush_l2", "c2g_synchronize", "c2g_timer_start", "c2g_timer_stop",
 ]
@@ -216,6 +216,47 @@ class Context:
                 continue
             self._chk(rc)
             return nattn.value, idg1, iatt[: nattn.value].copy(), ilvec[:, : nattn.value].copy()
+
+    # ---- HIRSHFELD ----
+    @staticmethod
+    def _species_args(tab):
+        """tab: dict of arrays ngrid, off, a, b, rmax, rcut, rtab, ftab (see include/critic2_gpu.h)."""
+        ng = np.ascontiguousarray(tab["ngrid"], dtype=np.int32)
+        off = np.ascontiguousarray(tab["off"], dtype=np.int32)
+        arrs = [np.ascontiguousarray(tab[k], dtype=np.float64) for k in ("a", "b", "rmax", "rcut", "rtab", "ftab")]
+        keep = (ng, off, *arrs)
+        return keep, (C.c_int(len(ng)), _p(ng, C.c_int), _p(off, C.c_int), *[_p(x, C.c_double) for x in arrs])
+
+    def promolecular_grid(self, n, x2c, atoms, ispc, tab, infrag=None):
+        """promolecular_array3 (crystalmod@complex.f90:436-470) as a resident grid; returns the handle."""
+        n = np.array(n, dtype=np.int32)
+        xat = np.asfortranarray(np.asarray(atoms, dtype=np.float64).T)
+        isp = np.ascontiguousarray(ispc, dtype=np.int32)
+        fr = None if infrag is None else np.ascontiguousarray(infrag, dtype=np.uint8)
+        keep, sargs = self._species_args(tab)
+        x2cf = _m33(x2c)
+        h = C.c_int(-1)
+        self._chk(self.lib.c2g_promolecular_grid(self.h, _p(n, C.c_int), _p(x2cf, C.c_double), C.c_int(xat.shape[1]),
+                                                 _p(xat, C.c_double), _p(isp, C.c_int), *sargs,
+                                                 None if fr is None else _p(fr, C.c_ubyte), C.byref(h)))
+        return h.value
+
+    def hirshfeld_integrate(self, hpromol, x2c, atoms, ispc, tab, fieldhandles, omega, domask=None):
+        """intgrid_hirshfeld_fields (integration@proc.f90:1552-1596): (vol[nat], psum[nat, nprop])."""
+        xat = np.asfortranarray(np.asarray(atoms, dtype=np.float64).T)
+        nat = xat.shape[1]
+        isp = np.ascontiguousarray(ispc, dtype=np.int32)
+        dm = None if domask is None else np.ascontiguousarray(domask, dtype=np.uint8)
+        fh = np.array(list(fieldhandles), dtype=np.int32)
+        keep, sargs = self._species_args(tab)
+        x2cf = _m33(x2c)
+        psum = np.zeros((nat, len(fh)), order="F")
+        vol = np.zeros(nat)
+        self._chk(self.lib.c2g_hirshfeld_integrate(self.h, C.c_int(int(hpromol)), _p(x2cf, C.c_double), C.c_int(nat),
+                                                   _p(xat, C.c_double), _p(isp, C.c_int), *sargs,
+                                                   None if dm is None else _p(dm, C.c_ubyte), C.c_int(len(fh)), _p(fh, C.c_int),
+                                                   C.c_double(omega), _p(psum, C.c_double), _p(vol, C.c_double)))
+        return vol, psum
 
     # ---- NCIPLOT ----
     def nci_range(self, nstep1):

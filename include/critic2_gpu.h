@@ -156,6 +156,28 @@ int c2g_basins_remap(c2g_context* ctx, c2g_basins* res, const double* xattr, con
                      int isortho_del, const double x2c[9], const double x2xr[9], const double xr2c[9], int nws,
                      const double* ws_ineighc, int maxattn, int* nattn, int* iatt, int* ilvec, int* idg1);
 
+/* ---- HIRSHFELD on a grid (hirshfeld@proc.f90:28-89, integration@proc.f90:264-267, :1397-1597) ---- */
+/* Atomic radial grids (grid1mod.f90) per species s = 1..nspc: spc_ngrid(s) nodes r(i) = a exp(b (i-1)) stored at
+ * rtab(spc_off(s) + i), densities at ftab(...), spc_rmax = g%rmax, spc_rcut = min(cutrad(z), g%rmax)
+ * (crystalmod@env.f90:671-684); spc_ngrid(s) = 0 marks a species without a usable grid (z = 0, z - qat <= 0, not
+ * initialised).  Atoms: xat(3,nat) crystallographic, ispc(nat) 1-based species.
+ * c2g_promolecular_grid = promolecular_array3 (crystalmod@complex.f90:436-470): the promolecular density on the grid as a
+ * resident field (bas%f of the HIRSHFELD driver); infrag(nat) (may be NULL) restricts the sum to a fragment, e.g. one
+ * atom for hirsh_weights (hirshfeld@proc.f90:78-86: w = that grid / max(bas%f, vsmall)). */
+int c2g_promolecular_grid(c2g_context* ctx, const int n[3], const double x2c[9], int nat, const double* xat, const int* ispc,
+                          int nspc, const int* spc_ngrid, const int* spc_off, const double* spc_a, const double* spc_b,
+                          const double* spc_rmax, const double* spc_rcut, const double* rtab, const double* ftab,
+                          const unsigned char* infrag, int* handle);
+/* The grid loop of intgrid_hirshfeld_fields (integration@proc.f90:1552-1596): psum(nat,nprop) column-major =
+ * sum_p rho_A(p) / max(rho_pro(p), vsmall) * f_k(p) * omega/ntot over every image of atom A within its cutoff,
+ * vol(nat) the same without f_k; atoms with domask(A) == 0 (docelatom(icp(A)), may be NULL) stay at zero.
+ * hpromol: the resident promolecular grid (bas%f). */
+int c2g_hirshfeld_integrate(c2g_context* ctx, int hpromol, const double x2c[9], int nat, const double* xat, const int* ispc,
+                            int nspc, const int* spc_ngrid, const int* spc_off, const double* spc_a, const double* spc_b,
+                            const double* spc_rmax, const double* spc_rcut, const double* rtab, const double* ftab,
+                            const unsigned char* domask, int nprop, const int* fieldhandles, double omega, double* psum,
+                            double* vol);
+
 /* ---- YT: Yu-Trinkle weights (yt@proc.f90:77-211) ---- */
 /* vec(3,nvec), area(nvec): Voronoi-relevant grid steps and facet areas from grid3%init_geometry
  * (grid3mod@proc.f90:3197).  Maxima are returned in decreasing density (= reference discovery order). */
