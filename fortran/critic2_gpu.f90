@@ -13,7 +13,7 @@ module critic2_gpu
 
   public :: gpu_enabled, gpu_init, gpu_end
   public :: gpu_bader_integrate, gpu_yt_integrate, gpu_yt_isosurface, gpu_integrate_fields, gpu_integrate_multipoles
-  public :: gpu_nci_rdg, gpu_nci_rdg_fourier, gpu_grid_fft, gpu_read_text_block, gpu_write_text_block, gpu_wcube_block, gpu_basins_remap
+  public :: gpu_nci_rdg, gpu_nci_rdg_fourier, gpu_grid_fft, gpu_read_text_block, gpu_write_text_block, gpu_wcube_block, gpu_basins_remap, gpu_hirshfeld_fields
 
   logical :: gpu_enabled = .false.        !< set by gpu_init (environment variable CRITIC2_GPU=1)
   type(c_ptr) :: ctx = c_null_ptr         !< c2g_context
@@ -99,6 +99,28 @@ module critic2_gpu
        type(c_ptr), value :: idg1          ! c_loc of idg1(n1,n2,n3), or c_null_ptr (yt_remap)
        integer(c_int) :: c2g_basins_remap
      end function c2g_basins_remap
+     function c2g_promolecular_grid(ctx,n,x2c,nat,xat,ispc,nspc,spc_ngrid,spc_off,spc_a,spc_b,spc_rmax,spc_rcut,rtab,ftab,&
+        infrag,handle) bind(c,name="c2g_promolecular_grid")
+       import :: c_int, c_ptr, c_double
+       type(c_ptr), value :: ctx
+       integer(c_int) :: n(3), ispc(*), spc_ngrid(*), spc_off(*), handle
+       integer(c_int), value :: nat, nspc
+       real(c_double) :: x2c(3,3), xat(3,*), spc_a(*), spc_b(*), spc_rmax(*), spc_rcut(*), rtab(*), ftab(*)
+       type(c_ptr), value :: infrag        ! c_loc of an integer(c_signed_char) mask(nat), or c_null_ptr
+       integer(c_int) :: c2g_promolecular_grid
+     end function c2g_promolecular_grid
+     function c2g_hirshfeld_integrate(ctx,hpromol,x2c,nat,xat,ispc,nspc,spc_ngrid,spc_off,spc_a,spc_b,spc_rmax,spc_rcut,&
+        rtab,ftab,domask,nprop,fieldhandles,omega,psum,vol) bind(c,name="c2g_hirshfeld_integrate")
+       import :: c_int, c_ptr, c_double
+       type(c_ptr), value :: ctx
+       integer(c_int), value :: hpromol, nat, nspc, nprop
+       integer(c_int) :: ispc(*), spc_ngrid(*), spc_off(*), fieldhandles(*)
+       real(c_double) :: x2c(3,3), xat(3,*), spc_a(*), spc_b(*), spc_rmax(*), spc_rcut(*), rtab(*), ftab(*)
+       type(c_ptr), value :: domask
+       real(c_double), value :: omega
+       real(c_double) :: psum(*), vol(*)
+       integer(c_int) :: c2g_hirshfeld_integrate
+     end function c2g_hirshfeld_integrate
      function c2g_basins_maxima(res,pmax) bind(c,name="c2g_basins_maxima")
        import :: c_int, c_ptr
        type(c_ptr), value :: res
@@ -631,6 +653,84 @@ contains
     iatt = iatt_(1:nattn)
     ilvec = ilvec_(:,1:nattn)
   end subroutine gpu_basins_remap
+
+  !> Pack the atomic radial grids of the species of c (grid1mod agrid) and its atoms for the HIRSHFELD entry points:
+  !> cutoffs as in promolecular_atom (src/crystalmod@env.f90:671-684).
+  subroutine pack_atomic_grids(c,xat,ispc,ngrid,off,a,b,rmax,rcut,rtab,ftab)
+    use crystalmod, only: crystal
+    use grid1mod, only: agrid
+    use global, only: cutrad
+    use param, only: maxzat
+    type(crystal), intent(in) :: c
+    real*8, allocatable, intent(out) :: xat(:,:), a(:), b(:), rmax(:), rcut(:), rtab(:), ftab(:)
+    integer(c_int), allocatable, intent(out) :: ispc(:), ngrid(:), off(:)
+    integer :: i, iz, ntab
+
+    allocate(xat(3,c%ncel),ispc(c%ncel),ngrid(c%nspc),off(c%nspc),a(c%nspc),b(c%nspc),rmax(c%nspc),rcut(c%nspc))
+    do i = 1, c%ncel
+       xat(:,i) = c%atcel(i)%x
+       ispc(i) = int(c%atcel(i)%is,c_int)
+    end do
+    ngrid = 0; off = 0; a = 1d0; b = 1d0; rmax = 0d0; rcut = 0d0
+    ntab = 0
+    do i = 1, c%nspc
+       iz = c%spc(i)%z
+       if (iz == 0 .or. iz > maxzat) cycle
+       if (.not.agrid(iz)%isinit) cycle
+       if (agrid(iz)%z - agrid(iz)%qat <= 0) cycle            ! interp returns zero (grid1mod@proc.f90:101)
+       ngrid(i) = int(agrid(iz)%ngrid,c_int)
+       off(i) = int(ntab,c_int)
+       a(i) = agrid(iz)%a; b(i) = agrid(iz)%b; rmax(i) = agrid(iz)%rmax
+       rcut(i) = min(cutrad(iz),agrid(iz)%rmax)
+       ntab = ntab + agrid(iz)%ngrid
+    end do
+    allocate(rtab(max(ntab,1)),ftab(max(ntab,1)))
+    do i = 1, c%nspc
+       if (ngrid(i) == 0) cycle
+       iz = c%spc(i)%z
+       rtab(off(i)+1:off(i)+ngrid(i)) = agrid(iz)%r(1:ngrid(i))
+       ftab(off(i)+1:off(i)+ngrid(i)) = agrid(iz)%f(1:ngrid(i))
+    end do
+  end subroutine pack_atomic_grids
+
+  !> HIRSHFELD on a grid: bas%f = promolecular density (src/integration@proc.f90:264-267, promolecular_array3 without
+  !> zpsp or fragment) kept resident, then the grid loop of intgrid_hirshfeld_fields (:1552-1596) for the nprop
+  !> integrand grids of fint (built by the host code, :1452-1527) -- psum(nattr,nprop), vol(nattr) are the psuml
+  !> columns already scaled by omega/ntot (:1590).  With download = .true. bas%f is also copied back to the host.
+  subroutine gpu_hirshfeld_fields(c,bas,nprop,fint,psum,vol,download)
+    use crystalmod, only: crystal
+    use types, only: basindat
+    type(crystal), intent(in) :: c
+    type(basindat), intent(inout) :: bas
+    integer, intent(in) :: nprop
+    real*8, intent(in) :: fint(:,:,:,:)
+    real*8, intent(out) :: psum(:,:), vol(:)
+    logical, intent(in) :: download
+    real*8, allocatable :: xat(:,:), a(:), b(:), rmax(:), rcut(:), rtab(:), ftab(:)
+    integer(c_int), allocatable :: ispc(:), ngrid(:), off(:)
+    integer(c_signed_char), allocatable, target :: domask(:)
+    integer(c_int) :: hp, h(max(nprop,1)), n(3)
+    integer :: k
+
+    n = int(bas%n,c_int)
+    call pack_atomic_grids(c,xat,ispc,ngrid,off,a,b,rmax,rcut,rtab,ftab)
+    call check(c2g_promolecular_grid(ctx,n,c%m_x2c,int(c%ncel,c_int),xat,ispc,int(c%nspc,c_int),ngrid,off,a,b,rmax,rcut,&
+       rtab,ftab,c_null_ptr,hp),"gpu_hirshfeld_fields")
+    if (download) call check(c2g_grid_download(ctx,hp,bas%f),"gpu_hirshfeld_fields")
+    allocate(domask(c%ncel))
+    do k = 1, c%ncel          ! attractors = atoms of the complete list (hirsh_grid, src/hirshfeld@proc.f90:44-49)
+       domask(k) = merge(1_c_signed_char,0_c_signed_char,bas%docelatom(bas%icp(k)))
+    end do
+    do k = 1, nprop
+       call check(c2g_grid_upload(ctx,fint(:,:,:,k),n,h(k)),"gpu_hirshfeld_fields")
+    end do
+    call check(c2g_hirshfeld_integrate(ctx,hp,c%m_x2c,int(c%ncel,c_int),xat,ispc,int(c%nspc,c_int),ngrid,off,a,b,rmax,rcut,&
+       rtab,ftab,c_loc(domask),int(nprop,c_int),h,c%omega,psum,vol),"gpu_hirshfeld_fields")
+    do k = 1, nprop
+       call check(c2g_grid_free(ctx,h(k)),"gpu_hirshfeld_fields")
+    end do
+    call check(c2g_grid_free(ctx,hp),"gpu_hirshfeld_fields")
+  end subroutine gpu_hirshfeld_fields
 
   !> WCUBE (int_cubew, src/integration@proc.f90:4449-4462): the value block of the weight cube of attractor i, from
   !> the basins resident on the device -- the YT weights (:4451) or the indicator of idg == i (:4455-4458) -- written to
