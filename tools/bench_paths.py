@@ -276,8 +276,32 @@ def multipoles():
     b.free(); ctx.free(h)
 
 
+# ---- HIRSHFELD on the urea-like 256^3 grid: promolecular density + atomic integrals (synthetic Slater-type radial grids) ----
+def hirshfeld():
+    from test_oracle_hirshfeld import slater_tables
+    N = 64 if quick else 256
+    n = (N, N, N)
+    x2c = S.cell_x2c(10.52, 10.52, 8.85)
+    at, z, al = S.random_atoms(16, 2, x2c, dmin=2.0)
+    ispc = np.arange(1, 17, dtype=np.int32)                     # one species per atom (its own Z, alpha)
+    g = slater_tables(z, al, ngrid=600, a=1e-4, rmax=12.0)
+    tab = dict(ngrid=g.ngrid, off=g.off, a=g.a, b=g.b, rmax=g.rmax, rcut=g.rcut, rtab=g.rtab, ftab=g.ftab)
+    ms_p, prof_p, hp = timed(lambda: [ctx.promolecular_grid(n, x2c, at, ispc, tab)], reps=2, cleanup=free_all)
+    hp = hp[0]
+    om = S.omega(x2c)
+    ms_h, prof_h, (vol, ps) = timed(lambda: ctx.hirshfeld_integrate(hp, x2c, at, ispc, tab, [hp], om), reps=2)
+    chk = {"atoms": 16, "cutoff_bohr": 12.0, "volume_sum_over_omega": float(vol.sum() / om),
+           "population_sum_vs_Z": float(ps[:, 0].sum() / np.sum(z)), "note": "FP64-pipe bound (log + 12 divisions per image and point)"}
+    if quick:   # full parity against the oracle at the quick size
+        ref = orc.promolecular_grid(n, x2c, at, ispc, g)
+        chk["promolecular_max_rel_err_vs_oracle"] = float(np.abs(ctx.download(hp, n) - ref).max() / ref.max())
+    emit("HIRSHFELD: promolecular density on the grid (promolecular_array3)", "configs[1] cell, 16 atoms", n, ms_p, 8.0, prof_p, chk)
+    emit("HIRSHFELD: atomic integrals (intgrid_hirshfeld_fields loop, Volume + 1 field)", "configs[1] cell, 16 atoms", n, ms_h, 16.0, prof_h, chk)
+    ctx.free(hp)
+
+
 only = [a.split("=", 1)[1].split(",") for a in sys.argv if a.startswith("--only=")]
-for fn in (urea, nci, yt, fft_big, text_reader, text_writer, multipoles):
+for fn in (urea, nci, yt, fft_big, text_reader, text_writer, multipoles, hirshfeld):
     if only and fn.__name__ not in only[0]:
         continue
 
