@@ -1,6 +1,7 @@
 // critic2_host.cpp -- see critic2_host.hpp.  Calls the C ABI only; no field arithmetic happens here.
 #include "critic2_host.hpp"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -254,6 +255,57 @@ void intgrid_multipoles(const system& s, const basindat& bas, const double* fint
                                  nws ? s.ws_ineighc.data() : nullptr, s.omega, mpole.data()),
         "intgrid_fields");
   check(c2g_grid_free(g_ctx, h), "intgrid_fields");
+}
+
+void basins_remap(const system& s, const basindat& bas, int& nattn, std::vector<int>& iatt, std::vector<int>& ilvec,
+                  std::vector<int>* idg1) {
+  if (!g_ctx || !g_basins) ferror("bader_remap", "no basin assignment on the device");
+  double c2x[9];
+  matinv3(s.m_x2c, c2x);
+  const int nws = (int)(s.ws_ineighc.size() / 3);
+  if (idg1) idg1->assign(bas.f.size(), 0);
+  int cap = 27 * std::max(bas.nattr, 1);
+  for (;;) {
+    iatt.assign(cap, 0);
+    ilvec.assign(3 * (size_t)cap, 0);
+    const int ier = c2g_basins_remap(g_ctx, g_basins, bas.xattr.data(), c2x, s.isortho ? 1 : 0, s.isortho_del ? 1 : 0, s.m_x2c,
+                                     s.m_x2xr, s.m_xr2c, nws, nws ? s.ws_ineighc.data() : nullptr, cap, &nattn, iatt.data(),
+                                     ilvec.data(), idg1 ? idg1->data() : nullptr);
+    if (ier == C2G_ERR_OVERFLOW && nattn > cap) { cap = nattn; continue; }  // the capacity needed comes back in nattn
+    check(ier, "bader_remap");
+    break;
+  }
+  iatt.resize(nattn);
+  ilvec.resize(3 * (size_t)nattn);
+}
+
+void hirshfeld_fields(const system& s, basindat& bas, const std::vector<int>& ispc, const atomic_grids& g,
+                      const std::vector<const double*>& fint, std::vector<int_result>& res, std::vector<double>& vol) {
+  if (!g_ctx) ferror("intgrid_hirshfeld_fields", "gpu_init was not called");
+  const int nat = s.nat(), nprop = (int)fint.size();
+  if ((int)ispc.size() != nat) ferror("intgrid_hirshfeld_fields", "one species per atom is required");
+  if (g.nspc() == 0) ferror("intgrid_hirshfeld_fields", "hirshfeld requires atomic grids");  // integration@proc.f90:1544
+  int hp = -1;
+  check(c2g_promolecular_grid(g_ctx, bas.n, s.m_x2c, nat, s.xat.data(), ispc.data(), g.nspc(), g.ngrid.data(), g.off.data(),
+                              g.a.data(), g.b.data(), g.rmax.data(), g.rcut.data(), g.rtab.data(), g.ftab.data(), nullptr, &hp),
+        "intgrid_hirshfeld_fields");
+  bas.f.assign((size_t)bas.n[0] * bas.n[1] * bas.n[2], 0.0);
+  check(c2g_grid_download(g_ctx, hp, bas.f.data()), "intgrid_hirshfeld_fields");   // bas%f = promolecular density (:264-267)
+  bas.nattr = nat;                                                               // hirsh_grid: the atoms are the attractors
+  bas.xattr = s.xat;
+  std::vector<int> h(std::max(nprop, 1), -1);
+  for (int k = 0; k < nprop; k++) check(c2g_grid_upload(g_ctx, fint[k], bas.n, &h[k]), "intgrid_hirshfeld_fields");
+  std::vector<double> psum((size_t)nat * std::max(nprop, 1), 0.0);
+  vol.assign(nat, 0.0);
+  const bool masked = (int)bas.docelatom.size() == nat;
+  check(c2g_hirshfeld_integrate(g_ctx, hp, s.m_x2c, nat, s.xat.data(), ispc.data(), g.nspc(), g.ngrid.data(), g.off.data(), g.a.data(),
+                                g.b.data(), g.rmax.data(), g.rcut.data(), g.rtab.data(), g.ftab.data(),
+                                masked ? bas.docelatom.data() : nullptr, nprop, h.data(), s.omega, psum.data(), vol.data()),
+        "intgrid_hirshfeld_fields");
+  for (int k = 0; k < nprop; k++) check(c2g_grid_free(g_ctx, h[k]), "intgrid_hirshfeld_fields");
+  check(c2g_grid_free(g_ctx, hp), "intgrid_hirshfeld_fields");
+  res.assign(nprop, int_result());
+  for (int k = 0; k < nprop; k++) res[k].psum.assign(psum.begin() + (size_t)k * nat, psum.begin() + (size_t)(k + 1) * nat);
 }
 
 void yt_weights(const basindat& bas, int idb, std::vector<double>& w) {

@@ -11,6 +11,10 @@
 //   bader@proc.f90:80-234      bader_integrate(s,bas,iref)
 //   yt@proc.f90:38-224         yt_integrate(s,bas)
 //   integration@proc.f90:1170  intgrid_fields(bas,res)
+//   integration@proc.f90:1302  multipole branch of intgrid_fields -> intgrid_multipoles
+//   yt@proc.f90:233-390        yt_isosurface(s,bas)
+//   bader@proc.f90:237-296     bader_remap / yt@proc.f90:533-594 yt_remap -> basins_remap
+//   integration@proc.f90:1397  intgrid_hirshfeld_fields (+ promolecular_array3 for bas%f) -> hirshfeld_fields
 //   nci@proc.f90:543-605       nciplot loop -> nci_rdg, nci_rdg_fourier
 //   grid3mod@proc.f90:1757     grid3%fft -> grid_fft
 //   grid3mod@proc.f90:559,884  read_cube / read_vasp value blocks -> grid_read_text
@@ -99,6 +103,21 @@ void intgrid_fields(const system& s, const basindat& bas, const std::vector<cons
 // (may be empty) is the per-attractor mask of the YT branch (:1318).
 void intgrid_multipoles(const system& s, const basindat& bas, const double* fint, int lmax,
                         const std::vector<unsigned char>& docelatom, std::vector<double>& mpole);
+// bader@proc.f90:237-296 / yt@proc.f90:533-594 (DELOC): attractor images of the basins of the last bader_integrate /
+// yt_integrate call.  iatt(nattn), ilvec(3,nattn); idg1 (Bader only, pass nullptr otherwise) is resized to the grid.
+void basins_remap(const system& s, const basindat& bas, int& nattn, std::vector<int>& iatt, std::vector<int>& ilvec,
+                  std::vector<int>* idg1);
+// grid1mod.f90: the atomic radial grids of the species, packed like fortran/critic2_gpu.f90's pack_atomic_grids
+struct atomic_grids {
+  std::vector<int> ngrid, off;                 // per species; ngrid = 0: no usable grid
+  std::vector<double> a, b, rmax, rcut;        // r(i) = a exp(b (i-1)); rcut = min(cutrad(z), rmax)
+  std::vector<double> rtab, ftab;              // concatenated r(i), f(i)
+  int nspc() const { return (int)ngrid.size(); }
+};
+// HIRSHFELD on a grid (integration@proc.f90:264-267 and :1552-1596): fills bas.f with the promolecular density of the
+// atoms s.xat with species ispc (1-based), then res[k].psum(A) / vol(A) per atom; bas.docelatom = the ONLY mask.
+void hirshfeld_fields(const system& s, basindat& bas, const std::vector<int>& ispc, const atomic_grids& g,
+                      const std::vector<const double*>& fint, std::vector<int_result>& res, std::vector<double>& vol);
 // yt@proc.f90:476-499 (yt_weights with idb): dense weight field of one basin.
 void yt_weights(const basindat& bas, int idb, std::vector<double>& w);
 // nci@proc.f90:543-605, grid interpolation mode on the field's own lattice:
