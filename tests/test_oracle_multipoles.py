@@ -149,7 +149,7 @@ def test_device_formulation_of_the_harmonics_matches_the_angle_form_on_grid_vect
     worst = 0.0
     for v in vs:
         r = np.sqrt(v @ v)
-        sc = np.array([max(r, 1e-300) ** l for l in range(lmax + 1) for _ in range(2 * l + 1)])
+        sc = np.array([max(r, 1.0) ** l if r == 0.0 else r ** l for l in range(lmax + 1) for _ in range(2 * l + 1)])
         worst = max(worst, (np.abs(_rlm_device_formulation(v, lmax) - orc.rlm_real(v, lmax)) / sc).max())
     assert worst <= 1e-12, worst
     v = np.array([0.0, 1e-7, -1.0])                                    # not a grid vector: acos is ill-conditioned here
