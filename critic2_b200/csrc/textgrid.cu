@@ -534,7 +534,12 @@ __global__ void __launch_bounds__(256) k_format(const __grid_constant__ FormatAr
     for (int q = 0; q < pad; q++) o[q] = ' ';
     for (int q = 0; q < len; q++) o[pad + q] = (unsigned char)buf[q];
   }
-  if (c % 6 == 5 || c == A.L - 1) o[w] = '\n';
+  // end of record: after the 6th value of a line the format reverts; when the data list ends inside the group
+  // 6(" ",E...) the literal " " that precedes the next data edit descriptor is still written (Fortran format
+  // control) -- a partial line therefore ends with a blank, as in the reference's own cube files
+  // (tests/005_plot/ref/029_cube_precise_0[12].cube)
+  if (c % 6 == 5) o[w] = '\n';
+  else if (c == A.L - 1) { o[w] = ' '; o[w + 1] = '\n'; }
 }
 
 }  // namespace
@@ -616,7 +621,7 @@ extern "C" int c2g_grid_format_text(c2g_context* ctx, int handle, int layout, co
   A.w = width; A.d = digits; A.k = scale;
   if (layout == C2G_TEXT_ROWS_INDEX1) { A.L = A.n1; A.nrows = (long long)A.n2 * A.n3; }
   else { A.L = A.n3; A.nrows = (long long)A.n1 * A.n2; }
-  A.rowbytes = (long long)A.L * (width + 1) + (A.L + 5) / 6;
+  A.rowbytes = (long long)A.L * (width + 1) + (A.L + 5) / 6 + (A.L % 6 != 0 ? 1 : 0);  // + the blank that ends a partial line
   const size_t total = (size_t)A.nrows * (size_t)A.rowbytes;
   *nbytes = total;
   if (!out || cap == 0) return C2G_OK;  // step 1: the size only

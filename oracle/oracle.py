@@ -569,7 +569,9 @@ def fortran_e(x: float, w: int, d: int, k: int) -> str:
 
 def format_text_grid(f, layout, w, d, k, ishift=(0, 0, 0)):
     """layout 0: rows along index 1 of f as stored (NCI crho(k,j,i)); layout 1: cube order of f(i,j,k) with ishift.
-    Every value " " + Ew.dE3, 6 per line, new line after each row."""
+    Every value " " + Ew.dE3, 6 per line, new line after each row.  A line with fewer than 6 values ends with a blank:
+    when the data list ends inside the group 6(" ",E...) the literal that precedes the next data edit descriptor is still
+    written (Fortran format control); pinned by the reference's own outputs, tests/005_plot/ref/029_cube_precise_0[12].cube."""
     f = _f64(f)
     n1, n2, n3 = f.shape
     out = []
@@ -577,12 +579,12 @@ def format_text_grid(f, layout, w, d, k, ishift=(0, 0, 0)):
         for c in range(n3):
             for b in range(n2):
                 row = [" " + fortran_e(float(f[a, b, c]), w, d, k) for a in range(n1)]
-                out += ["".join(row[q:q + 6]) + "\n" for q in range(0, n1, 6)]
+                out += ["".join(row[q:q + 6]) + (" \n" if len(row[q:q + 6]) < 6 else "\n") for q in range(0, n1, 6)]
     else:
         for iix in range(n1):
             ix = (iix + ishift[0]) % n1
             for iiy in range(n2):
                 iy = (iiy + ishift[1]) % n2
                 row = [" " + fortran_e(float(f[ix, iy, (iiz + ishift[2]) % n3]), w, d, k) for iiz in range(n3)]
-                out += ["".join(row[q:q + 6]) + "\n" for q in range(0, n3, 6)]
+                out += ["".join(row[q:q + 6]) + (" \n" if len(row[q:q + 6]) < 6 else "\n") for q in range(0, n3, 6)]
     return "".join(out).encode()

@@ -194,3 +194,27 @@ def test_text_golden_fixture(ctx):
         got_fields = [text[q * (w + 1) + q // 6 + 1: q * (w + 1) + q // 6 + 1 + w] for q in range(len(vals))]
         assert got_fields == fields, key
     ctx.free(hv)
+
+
+def test_writer_against_the_reference_cube_files(ctx):
+    """PINNED by critic2's own outputs (tests/golden/cube_golden.json, from the reference's nodata tests
+    005_plot/013_cube_simple and 029_cube_precise): the device writer reproduces the value blocks of those cube files
+    byte for byte -- fields, six values per line, and the blank that ends a partial line."""
+    import json, os
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cube_golden.json")))
+    for name, b in g["blocks"].items():
+        vals = np.array(b["text"].split(), dtype=np.float64).reshape(1, b["rows"], b["n3"])
+        h = ctx.upload(np.asfortranarray(vals))
+        assert ctx.format_text(h, 1, 22, 14, 0).decode() == b["text"], name
+        ctx.free(h)
+    p = g["pairs"]
+    f = np.asfortranarray(np.array(p["precise_text"].split(), dtype=np.float64).reshape(2, 2, 2))
+    h = ctx.upload(f)
+    assert ctx.format_text(h, 1, 22, 14, 0).decode() == p["precise_text"]
+    assert ctx.format_text(h, 1, 12, 5, 1).decode() == p["standard_text"]
+    ctx.free(h)
+    fields = g["precise_fields"]
+    hv = ctx.upload(np.asfortranarray(np.array(fields, dtype=np.float64).reshape(-1, 1, 1)))
+    text = ctx.format_text(hv, 0, 22, 14, 0).decode()
+    assert [text[q * 23 + q // 6 + 1: q * 23 + q // 6 + 23] for q in range(len(fields))] == fields
+    ctx.free(hv)

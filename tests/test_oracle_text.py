@@ -58,9 +58,9 @@ def test_format_text_grid_layouts():
     rng = np.random.default_rng(2)
     f = np.asfortranarray(rng.standard_normal((4, 3, 7)))
     t0 = orc.format_text_grid(f, 0, 13, 5, 1).decode()
-    assert t0.count("\n") == 3 * 7 * 1 and len(t0) == 3 * 7 * (4 * 14 + 1)
+    assert t0.count("\n") == 3 * 7 * 1 and len(t0) == 3 * 7 * (4 * 14 + 1 + 1)      # 4 < 6 values: blank + new line
     t1 = orc.format_text_grid(np.abs(f), 1, 12, 5, 1, ishift=(1, 0, 2)).decode()
-    assert t1.count("\n") == 4 * 3 * 2 and len(t1) == 4 * 3 * (7 * 13 + 2)
+    assert t1.count("\n") == 4 * 3 * 2 and len(t1) == 4 * 3 * (7 * 13 + 2 + 1)  # lines of 6 and 1 values: the short one ends with a blank
     first = t1.split()[0]
     assert first == orc.fortran_e(float(abs(f[1, 0, 2])), 12, 5, 1).strip()
 
@@ -75,3 +75,26 @@ def test_text_golden_fixture_matches_the_oracle():
     for key, fields in g["writer"]["fields"].items():
         w, d, k = (int(x) for x in key.split(","))
         assert [orc.fortran_e(v, w, d, k) for v in vals] == fields
+
+
+def _cube_gold():
+    import json, os
+    return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cube_golden.json")))
+
+
+def test_writer_against_the_reference_cube_files():
+    """PINNED: tests/golden/cube_golden.json holds value fields and raw value blocks of cube files written by critic2
+    itself (its nodata tests 005_plot/013_cube_simple and 029_cube_precise; extracted by tests/golden/make_cube_golden.py).
+    The restated edit descriptors must reproduce them byte for byte: the E22.14E3 fields (incl. the sign and the leading
+    zero), the 1P E12.5E3 fields, six values per line and the blank that ends a partial line."""
+    g = _cube_gold()
+    for fld in g["precise_fields"]:                       # 1200 fields: 14 digits -> double -> the same 14 digits
+        assert orc.fortran_e(float(fld), 22, 14, 0) == fld
+    for name, b in g["blocks"].items():                   # 4 rows of 10 values: lines of 6 + 4, cube order (layout 1)
+        vals = np.array(b["text"].split(), dtype=np.float64).reshape(1, b["rows"], b["n3"])
+        assert orc.format_text_grid(np.asfortranarray(vals), 1, 22, 14, 0).decode() == b["text"], name
+    p = g["pairs"]                                        # the same 2x2x2 grid written by standardcube and precisecube
+    vals = np.array(p["precise_text"].split(), dtype=np.float64).reshape(2, 2, 2)     # (ix, iy, iz), iz fastest in the file
+    f = np.asfortranarray(vals)
+    assert orc.format_text_grid(f, 1, 22, 14, 0).decode() == p["precise_text"]
+    assert orc.format_text_grid(f, 1, 12, 5, 1).decode() == p["standard_text"]
