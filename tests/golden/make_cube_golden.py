@@ -16,7 +16,7 @@ def body(path):
     return n, lines[6 + nat:]
 
 
-gold = {"source": "critic2 tests/005_plot/ref (013_cube_simple_04/09/14.cube, 029_cube_precise_01/02.cube)", "precise_fields": [],
+gold = {"source": "critic2 tests/005_plot/ref (013_cube_simple_04/09/14.cube, 029_cube_precise_01/02.cube, 016_cube_grid_01/02.cube), tests/015_grdplot/ref (005_nciplot_basic-gen-grad/dens.cube)", "precise_fields": [],
         "blocks": {}}
 for name in ("013_cube_simple_04.cube", "013_cube_simple_09.cube", "013_cube_simple_14.cube"):
     n, lines = body(os.path.join(REF, name))
@@ -29,5 +29,15 @@ for name in ("013_cube_simple_04.cube", "013_cube_simple_09.cube", "013_cube_sim
 n1, l1 = body(os.path.join(REF, "029_cube_precise_01.cube"))
 n2, l2 = body(os.path.join(REF, "029_cube_precise_02.cube"))
 gold["pairs"] = {"n": n1, "standard_text": "\n".join(l1[:4]) + "\n", "precise_text": "\n".join(l2[:4]) + "\n"}
+# the same 10x10x10 grid written plainly and with `shift 4 4 4` (005_plot/016_cube_grid): pins ishift of writegrid_cube
+ng, lg1 = body(os.path.join(REF, "016_cube_grid_01.cube"))
+_, lg2 = body(os.path.join(REF, "016_cube_grid_02.cube"))
+gold["shift"] = {"n": ng, "ishift": [4, 4, 4], "plain_text": "\n".join(lg1[:2 * ng[0] * ng[1]]) + "\n",
+                 "shifted_text": "\n".join(lg2[:2 * ng[0] * ng[1]]) + "\n"}
+# NCIPLOT's write_cube_body, (6(" ",1p,e13.5e3)): 015_grdplot/005_nciplot_basic (nstep 2 2 2)
+NCI = "/root/reference/tests/015_grdplot/ref"
+for tag in ("grad", "dens"):
+    nn, ln = body(os.path.join(NCI, "005_nciplot_basic-gen-%s.cube" % tag))
+    gold["nci_" + tag] = {"n": nn, "text": "\n".join(ln[:nn[0] * nn[1]]) + "\n"}
 json.dump(gold, open(OUT, "w"), indent=0)
 print("wrote", OUT, len(gold["precise_fields"]), "fields")

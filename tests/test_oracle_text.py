@@ -98,3 +98,22 @@ def test_writer_against_the_reference_cube_files():
     f = np.asfortranarray(vals)
     assert orc.format_text_grid(f, 1, 22, 14, 0).decode() == p["precise_text"]
     assert orc.format_text_grid(f, 1, 12, 5, 1).decode() == p["standard_text"]
+
+
+def test_writer_shift_and_nci_layout_against_the_reference_files():
+    """PINNED by critic2's outputs: (a) the same 10x10x10 grid written by `cube grid` plainly and with `shift 4 4 4`
+    (tests/005_plot/016_cube_grid) -- the ishift indexing of writegrid_cube (crystalmod@write.f90:3556-3565);
+    (b) the grad / dens cubes of NCIPLOT's write_cube_body, (6(" ",1p,e13.5e3)) (tests/015_grdplot/005_nciplot_basic)."""
+    g = _cube_gold()
+    s = g["shift"]
+    f = np.asfortranarray(np.array(s["plain_text"].split(), dtype=np.float64).reshape(s["n"]))   # (ix, iy, iz), iz fastest
+    assert orc.format_text_grid(f, 1, 22, 14, 0).decode() == s["plain_text"]
+    assert orc.format_text_grid(f, 1, 22, 14, 0, ishift=tuple(s["ishift"])).decode() == s["shifted_text"]
+    # and back: the reader on the reference's own text (read_cube's loop order: k fastest)
+    back, used = orc.parse_text_grid(s["shifted_text"].encode(), tuple(s["n"]), 1, 1.0)
+    sh = np.roll(f, shift=(-4, -4, -4), axis=(0, 1, 2))
+    assert np.array_equal(back, sh) and used <= len(s["shifted_text"])
+    for key in ("nci_grad", "nci_dens"):
+        b = g[key]
+        c = np.array(b["text"].split(), dtype=np.float64).reshape(b["n"][2], b["n"][1], b["n"][0], order="F")  # c(k,j,i)
+        assert orc.format_text_grid(c, 0, 13, 5, 1).decode() == b["text"], key
