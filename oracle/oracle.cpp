@@ -9,10 +9,17 @@
 // PARITY STATUS: "parity unpinned".  critic2 is Fortran; no Fortran compiler
 // exists in this image and the input grids of the reference's golden .cro files
 // (tests/009_intgrid/ref/*.cro) are not shipped, so this restatement cannot be
-// pinned against outputs of the reference itself.  It is pinned by line-by-line
-// review against the cited source ranges, by the published tricubic matrix
-// (checked against src/grid3mod@proc.f90:76-340 when /root/reference exists),
-// and by analytic known-answer tests (tests/test_oracle_*.py).
+// pinned against outputs of the reference itself for BADER, YT and the grid-field
+// NCI path.  Those are pinned by line-by-line review against the cited source
+// ranges, by the published tricubic matrix (checked against
+// src/grid3mod@proc.f90:76-340 when /root/reference exists), and by analytic
+// known-answer tests (tests/test_oracle_*.py).  PINNED by the reference's own
+// outputs (golden files of its nodata tests, tests/golden/cube_golden.json): the
+// promolecular density (promolecular_atom + grid1%interp, reproduces the urea
+// density cube of 015_grdplot/005_nciplot_basic to its six printed digits), the
+// RDG formula (the gradient cube of the same test), the real solid harmonics
+// (closed forms in the comment block of genrlm_real); the Fortran edit
+// descriptors of the cube writers are restated in oracle.py and pinned there.
 //
 // All file:line citations are relative to the critic2 source tree.
 //

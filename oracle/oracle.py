@@ -2,8 +2,10 @@
 
 TEST INFRASTRUCTURE ONLY -- see the header of oracle/oracle.cpp.  Only tests/,
 __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
-import this module.  Parity status: "parity unpinned" (no Fortran compiler and
-no reference input grids in this image).
+import this module.  Parity status: "parity unpinned" for BADER / YT / grid-field NCI
+(no Fortran compiler and no reference input grids in this image); pinned by critic2's
+own outputs for the cube writer (fortran_e / format_text_grid), the promolecular
+density and the RDG formula (tests/golden/cube_golden.json, see oracle.cpp's header).
 
 Arrays are Fortran-ordered numpy arrays f[n1,n2,n3] (index 1 fastest in memory).
 3x3 matrices are numpy arrays M[i,j] passed in Fortran (column-major) order.
