@@ -39,5 +39,10 @@ NCI = "/root/reference/tests/015_grdplot/ref"
 for tag in ("grad", "dens"):
     nn, ln = body(os.path.join(NCI, "005_nciplot_basic-gen-%s.cube" % tag))
     gold["nci_" + tag] = {"n": nn, "text": "\n".join(ln[:nn[0] * nn[1]]) + "\n"}
+# the same grid written as a CHGCAR (005_plot/017_cube_files): values times the cell volume, index 1 fastest, 5 per line
+chg = open(os.path.join(REF, "017_cube_files.CHGCAR")).read().split("\n")
+k0 = [i for i, l in enumerate(chg) if l.split() == ["10", "10", "10"]][0]
+gold["chgcar"] = {"n": [10, 10, 10], "cell_bohr": [10.51632592951, 10.51632592951, 8.85147720644],
+                  "text": "\n".join(chg[k0 + 1:k0 + 1 + 200]) + "\n"}
 json.dump(gold, open(OUT, "w"), indent=0)
 print("wrote", OUT, len(gold["precise_fields"]), "fields")

@@ -117,3 +117,16 @@ def test_writer_shift_and_nci_layout_against_the_reference_files():
         b = g[key]
         c = np.array(b["text"].split(), dtype=np.float64).reshape(b["n"][2], b["n"][1], b["n"][0], order="F")  # c(k,j,i)
         assert orc.format_text_grid(c, 0, 13, 5, 1).decode() == b["text"], key
+
+
+def test_reader_orders_and_volume_scaling_against_the_reference_files():
+    """PINNED by critic2's outputs: tests/005_plot/017_cube_files writes ONE 10x10x10 grid as a cube file (k fastest) and
+    as a CHGCAR (values times the cell volume, i fastest).  Read back with read_cube's and read_vasp's conventions
+    (grid3mod@proc.f90:559, :884-908: order and the division by det3(x2c)) the two must be the same field."""
+    g = _cube_gold()
+    n = tuple(g["chgcar"]["n"])
+    a, b, c = g["chgcar"]["cell_bohr"]
+    fc, _ = orc.parse_text_grid(g["shift"]["plain_text"].encode(), n, 1, 1.0)           # the cube block (016 = 017: same grid)
+    fv, used = orc.parse_text_grid(g["chgcar"]["text"].encode(), n, 0, a * b * c)      # the CHGCAR block
+    assert used <= len(g["chgcar"]["text"])
+    assert np.abs(fv / fc - 1.0).max() <= 1e-12                                        # both files carry 14 digits
