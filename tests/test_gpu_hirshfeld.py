@@ -72,3 +72,22 @@ def test_hirshfeld_error_paths(ctx):
         ctx.promolecular_grid(n, x2c, atoms, np.array([1, 5, 1], dtype=np.int32), tab_of(g))
     with pytest.raises(capi.C2GError, match="handle"):
         ctx.hirshfeld_integrate(999, x2c, atoms, ispc, tab_of(g), [], 1.0)
+
+
+def test_promolecular_grid_of_urea_reproduces_the_reference_cube(ctx):
+    """PINNED by critic2's own output: the device evaluates the promolecular density of the library urea crystal on the
+    10x10x10 grid of the reference's nodata test 005_plot/016_cube_grid (atomic grids built from the reference's data
+    files, tests/golden/urea_atomic_grids.npz) and must reproduce the 1000 values of the reference's cube file, 14
+    printed digits, to 1e-11; the Hirshfeld volumes of that density then partition the cell."""
+    from test_oracle_promolecular_reference import golden_urea_grid, urea_fixture
+    x2c, atoms, ispc, g = urea_fixture()
+    n = (10, 10, 10)
+    h = ctx.promolecular_grid(n, x2c, atoms, ispc, tab_of(g))
+    rho = ctx.download(h, n)
+    assert np.abs(rho / golden_urea_grid() - 1.0).max() <= 1e-11
+    om = S.omega(x2c)
+    vol, ps = ctx.hirshfeld_integrate(h, x2c, atoms, ispc, tab_of(g), [h], om)
+    assert abs(vol.sum() - om) <= 1e-10 * om
+    vol_o, ps_o = orc.hirshfeld_fields(rho, x2c, atoms, ispc, g, [rho], om)
+    assert np.abs(ps - ps_o).max() <= TOL * np.abs(ps_o).max() and np.abs(vol - vol_o).max() <= TOL * np.abs(vol_o).max()
+    ctx.free(h)
