@@ -38,7 +38,21 @@ struct BaderParams {
   int in1, in2, in3;  // max(n - 6, 0): points with 3 <= p < n-3 take steps that never touch a periodic seam
   double c2l[9];   // car2lat, column-major
   double lid[27];  // lat_i_dist, (d1+1)*9+(d2+1)*3+(d3+1)
+  unsigned mg1, mg12;  // id / n1 and id / (n1*n2) for 0 <= id < 2^31 as (id * mg) >> (31 + sh), see fastdiv_make
+  int sh1, sh12;
 };
+
+// Division of 0 <= v < 2^31 by a run-time constant d >= 1 (round-up method): with l = ceil(log2 d) and
+// m = floor(2^(31+l) / d) + 1 (< 2^32), m*d - 2^(31+l) is in [1, d] <= 2^l, hence floor(v*m / 2^(31+l)) = v / d.
+inline void fastdiv_make(unsigned d, unsigned& m, int& sh) {
+  int l = 0;
+  while ((1ull << l) < d) l++;
+  m = (unsigned)((1ull << (31 + l)) / d + 1ull);
+  sh = l;
+}
+__device__ __forceinline__ int fastdiv(int v, unsigned m, int sh) {
+  return (int)(((unsigned long long)(unsigned)v * m) >> (31 + sh));
+}
 
 constexpr unsigned FILLBIT = 0x80000000u;
 constexpr int LMASK = 0x7fffffff;
@@ -144,6 +158,7 @@ __device__ __noinline__ bool dev_on_path(const int* path, int len, int nid) {
 struct SafeMap {
   int* safe;  // nullptr = disabled; entries are set to -1 when a label inside the certified region changes
   int shift, c1, c2, c3, zlo, nzl, octet, wrapz;
+  int hf;  // octet: half a cube, (1 << shift) >> 1
 };
 constexpr int STOP_SHIFT = 28;             // stop code = (level index << 28) | map index
 constexpr int STOP_MASK = (1 << STOP_SHIFT) - 1;
@@ -286,6 +301,25 @@ __device__ __forceinline__ int safe_lookup(const SafeMap& sm, int nx, int ny, in
   if (cz < 0 || cz >= sm.nzl) return -1;
   mapidx = (nx >> sm.shift) + sm.c1 * ((ny >> sm.shift) + sm.c2 * (cz >> sm.shift));
   return sm.safe[mapidx];
+}
+// The same lookup with the branch on the certificate kind hoisted (warp-uniform) and nothing recomputed per call.
+__device__ __forceinline__ int safe_lookup2(const SafeMap& sm, int x, int y, int z, int& mapidx) {
+  const int cz = z - sm.zlo;
+  int vx, vy, vz;
+  bool ok = (unsigned)cz < (unsigned)sm.nzl;
+  if (sm.octet) {
+    const int hf = sm.hf;
+    vx = (x + hf) >> sm.shift; vy = (y + hf) >> sm.shift; vz = (cz + hf) >> sm.shift;
+    vx = vx == sm.c1 ? 0 : vx;
+    vy = vy == sm.c2 ? 0 : vy;
+    const bool top = vz == sm.c3;
+    ok = ok && (!top || sm.wrapz);
+    vz = top ? 0 : vz;
+  } else {
+    vx = x >> sm.shift; vy = y >> sm.shift; vz = cz >> sm.shift;
+  }
+  mapidx = vx + sm.c1 * (vy + sm.c2 * vz);
+  return ok ? sm.safe[mapidx] : -1;  // plain load: entries may be invalidated while walkers run
 }
 // w: current point with w.r0, nb = its neighbours, sl = early-termination label of its cube (all loaded by
 // the previous call or by the caller for the start point, where sl must be -1)
@@ -600,6 +634,7 @@ struct WalkArgs {
   const int* list;          // nullptr: lattice mode; otherwise the dense list of every walker so far
   long long flat_base;      // flat mode: items are list[flat_base .. flat_base + count)
   long long count;
+  const int* count_dev;     // k_walk2: non-null = the number of entries is read from device memory (no host round trip)
   int* stop;                // stop log parallel to `list`: where a walk was cut short (stop code), or -1
   int sm_level;             // level index of `sm` (goes into the stop code)
   SafeMap maps[MAXLEV];     // FIX: every early-termination map in use, for invalidation
@@ -691,6 +726,10 @@ __device__ __forceinline__ void walk_finish(const BaderParams& P, const WalkArgs
   if (FIX && oldlab != lab) claim_neighbours(P, A, start);
 }
 
+__device__ __noinline__ int walk_item_lattice(int n1, int n2, int zlo, int lat_s, int lat_m1, int lat_m2, int t) {
+  const int lx = t % lat_m1, ly = (t / lat_m1) % lat_m2, lz = t / (lat_m1 * lat_m2);
+  return lx * lat_s + n1 * (ly * lat_s + n2 * (zlo + lz * lat_s));
+}
 __device__ __forceinline__ int walk_item(const BaderParams& P, const WalkArgs& A, int t) {
   if (A.list) return A.list[t];
   const int lx = (int)(t % A.lat_m1), ly = (int)((t / A.lat_m1) % A.lat_m2), lz = (int)(t / ((long long)A.lat_m1 * A.lat_m2));
@@ -762,6 +801,201 @@ __global__ void __launch_bounds__(256, 4) k_walk(const __grid_constant__ BaderPa
           pend_st = st; pend_out = out;
           active = false;
         }
+      }
+    }
+  }
+  if (STATS && A.nsteps && steps) atomicAdd(A.nsteps, steps);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_walk2: the production walkers.  Same trajectories, same decisions, same results as k_walk; what differs is
+// the schedule.  A step keeps NO state besides (point, dr, largest density on the path): all loads of a step
+// (density of the point, its 6 neighbours, its certificate) are issued together at the top of the step, so that
+// starting a new trajectory costs a handful of instructions.  That makes it cheap to refill EVERY idle lane
+// before EVERY step: the warp holds the next 32 start points in a register (one coalesced load, a second chunk
+// is already in flight), and idle lanes take theirs with one shuffle.  With k_walk's refill thresholds
+// (20 / 24 idle lanes) 19 of 32 lanes were active on the last level.
+// Work distribution: chunks of 32 consecutive entries of the dense, spatially ordered walker list (or of the
+// lattice numbering), handed out through a global cursor.
+// The tests of step k+1 that k_walk made at the end of step k are made at the top of step k+1, in the same
+// order: possible revisit (density not above the path's maximum: hand over to k_walk_big), then the certificate.
+// ------------------------------------------------------------------------------------------------
+// nint(v) for a finite |v| < 1.5 as a double (returned) and as an int (d), on the integer ALU: |v| >= 0.5 iff the high
+// word of |v| is >= that of 0.5.  NaN and infinities give 0 (such a walk ends "did not move", like with nint_di).
+__device__ __forceinline__ double nint_bits(double v, int& d) {
+  const int hi = __double2hiint(v);
+  const bool big = (unsigned)((hi & 0x7fffffff) - 0x3fe00000) < (unsigned)(0x7ff00000 - 0x3fe00000);
+  const int ahi = big ? ((hi & (int)0x80000000) | 0x3ff00000) : 0;
+  d = big ? ((hi >> 31) | 1) : 0;
+  return __hiloint2double(ahi, 0);
+}
+// g, or 0 when both neighbours are strictly below the centre (rho_grad_dir, :553-558): two chained predicates, one select
+__device__ __forceinline__ double zero_if_both_less(double g, double p, double m, double r0) {
+  double out;
+  asm("{\n\t.reg .pred q;\n\tsetp.lt.f64 q, %2, %4;\n\tsetp.lt.and.f64 q, %3, %4, q;\n\t"
+      "selp.f64 %0, 0d0000000000000000, %1, q;\n\t}"
+      : "=d"(out) : "d"(g), "d"(p), "d"(m), "d"(r0));
+  return out;
+}
+template <bool ORTHO, bool FIX, bool STATS>
+__global__ void __launch_bounds__(256, 4) k_walk2(const __grid_constant__ BaderParams P, const __grid_constant__ WalkArgs A) {
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  const int n1 = P.n1, n2 = P.n2, n3 = P.n3;
+  const int s2 = n1, s3 = n1 * n2;
+  const int total = A.count_dev ? __ldg(A.count_dev) : (int)A.count;  // < 2^31: the lists hold at most nn entries
+  const int nchunk = (total + 31) >> 5;
+  const int* const list = A.list ? A.list + A.flat_base : nullptr;
+  const int tbase = (int)A.flat_base;
+  unsigned* const cur32 = reinterpret_cast<unsigned*>(A.cursor);  // low word of the (zeroed) 64-bit cursor
+  auto grab = [&]() -> int {  // chunk ids beyond nchunk are clamped: at most one surplus grab per warp and rotation
+    unsigned b = 0;
+    if (lane == 0) b = atomicAdd(cur32, 1u);
+    return (int)min(__shfl_sync(FULL, b, 0), (unsigned)nchunk);
+  };
+  auto load_chunk = [&](int c) -> int {  // start point of entry 32 c + lane
+    const int t = (c << 5) + lane;
+    if (t >= total) return -1;
+    return list ? __ldg(list + t) : walk_item_lattice(P.n1, P.n2, A.S.zlo, A.lat_s, A.lat_m1, A.lat_m2, t);
+  };
+  int c0 = grab();
+  int pre = load_chunk(c0);
+  int c1 = grab();
+  int pre2 = load_chunk(c1);
+  int navail = min(32, total - (c0 << 5));  // entries of `pre` (<= 0: none)
+  int consumed = 0;                                                    // ... already handed out
+  bool active = false, first = true;
+  int id = 0, x = 0, y = 0, z = 0, start = 0, tidx = -1, oldlab = 0;
+  double dr0 = 0.0, dr1 = 0.0, dr2 = 0.0, rhomax = 0.0;
+  int pend_st = 0, pend_out = 0, pend_sli = -1;
+  unsigned long long steps = 0;
+  for (;;) {
+    if (pend_st) {  // one pass for all lanes whose walk ended in the previous step
+      walk_finish<FIX>(P, A, start, pend_st, pend_out, list ? tidx : -1, pend_sli, oldlab);
+      pend_st = 0;
+    }
+    const unsigned idle = __ballot_sync(FULL, !active);
+    if (__popc(idle) >= A.refill_min) {
+      if (consumed == navail && c0 < nchunk) {  // next chunk (already loaded); fetch the one after it
+        c0 = c1; pre = pre2; consumed = 0;
+        navail = min(32, total - (c0 << 5));
+        c1 = grab();
+        pre2 = load_chunk(c1);
+      }
+      const int take = min(__popc(idle), navail - consumed);
+      if (take > 0) {
+        const int r = __popc(idle & lt);
+        const int s = __shfl_sync(FULL, pre, (consumed + r) & 31);
+        if (!active && r < take) {
+          start = id = s;
+          tidx = tbase + (c0 << 5) + consumed + r;
+          z = fastdiv(s, P.mg12, P.sh12);
+          const int rem = s - z * s3;
+          y = fastdiv(rem, P.mg1, P.sh1);
+          x = rem - y * n1;
+          dr0 = dr1 = dr2 = 0.0;
+          rhomax = __longlong_as_double((long long)0xfff0000000000000ull);  // -inf: the start point is never a revisit
+          first = true;
+          if (FIX) oldlab = A.label_g[s] & LMASK;
+          active = true;
+        }
+        consumed += take;
+      } else if (idle == FULL) {
+        break;  // nothing in flight and nothing left to hand out (c0 >= nchunk: the cursor only grows)
+      }
+    }
+    if (active) {
+      if (STATS) steps++;
+      const double* c = A.rho + id;
+      // the point and its next point stay clear of the periodic seams: no wrapping anywhere in this step
+      const bool inner = (unsigned)(x - 3) < (unsigned)P.in1 && (unsigned)(y - 3) < (unsigned)P.in2 &&
+                         (unsigned)(z - 3) < (unsigned)P.in3;
+      double r0, xp, xm, yp, ym, zp, zm;
+      r0 = __ldg(c);
+      if (inner) {
+        xp = __ldg(c + 1); xm = __ldg(c - 1);
+        yp = __ldg(c + s2); ym = __ldg(c - s2);
+        zp = __ldg(c + s3); zm = __ldg(c - s3);
+      } else {
+        xp = __ldg(c + ((x + 1 == n1) ? 1 - n1 : 1));
+        xm = __ldg(c + ((x == 0) ? n1 - 1 : -1));
+        yp = __ldg(c + ((y + 1 == n2) ? s2 - s3 : s2));
+        ym = __ldg(c + ((y == 0) ? s3 - s2 : -s2));
+        zp = __ldg(c + ((z + 1 == n3) ? s3 - s3 * n3 : s3));
+        zm = __ldg(c + ((z == 0) ? s3 * n3 - s3 : -s3));
+      }
+      int sli = -1, sl = -1;
+      if (!first && A.sm.safe) sl = safe_lookup2(A.sm, x, y, z, sli);  // the start point is never looked up
+      int st = 0, out = 0;
+      if (r0 <= rhomax) {
+        st = 3;  // possibly a point of this path (known(pm) == 1, :487): k_walk_big answers exactly
+      } else if (sl >= 0) {
+        st = 2; out = sl;  // quit at a known interior point (:447)
+      } else {
+        // rho_grad_dir (:532-567)
+        const double gl0 = zero_if_both_less((xp - xm) * 0.5, xp, xm, r0);
+        const double gl1 = zero_if_both_less((yp - ym) * 0.5, yp, ym, r0);
+        const double gl2 = zero_if_both_less((zp - zm) * 0.5, zp, zm, r0);
+        double g0, g1, g2;
+        if (ORTHO) {
+          g0 = P.c2l[0] * (gl0 * P.c2l[0]);
+          g1 = P.c2l[4] * (gl1 * P.c2l[4]);
+          g2 = P.c2l[8] * (gl2 * P.c2l[8]);
+        } else {
+          const double gc0 = gl0 * P.c2l[0] + gl1 * P.c2l[1] + gl2 * P.c2l[2];
+          const double gc1 = gl0 * P.c2l[3] + gl1 * P.c2l[4] + gl2 * P.c2l[5];
+          const double gc2 = gl0 * P.c2l[6] + gl1 * P.c2l[7] + gl2 * P.c2l[8];
+          g0 = P.c2l[0] * gc0 + P.c2l[3] * gc1 + P.c2l[6] * gc2;
+          g1 = P.c2l[1] * gc0 + P.c2l[4] * gc1 + P.c2l[7] * gc2;
+          g2 = P.c2l[2] * gc0 + P.c2l[5] * gc1 + P.c2l[8] * gc2;
+        }
+        double gmax = fabs(g0);
+        {
+          const double t1 = fabs(g1), t2 = fabs(g2);
+          gmax = t1 > gmax ? t1 : gmax;
+          gmax = t2 > gmax ? t2 : gmax;
+        }
+        const int oid = id;
+        if (gmax < 1e-30) {  // (:468-476)
+          dr0 = dr1 = dr2 = 0.0;
+          if (hash_lookup(A.h, id) >= 0) {
+            st = 1; out = id;
+          } else {
+            id = dev_step_ongrid(P, A.rho, x, y, z, r0);
+            z = fastdiv(id, P.mg12, P.sh12);
+            const int rem = id - z * s3;
+            y = fastdiv(rem, P.mg1, P.sh1);
+            x = rem - y * n1;
+            if (id == oid) st = 3;
+          }
+        } else {  // (:477-483)
+          const double coeff = 1.0 / gmax;
+          g0 = coeff * g0; g1 = coeff * g1; g2 = coeff * g2;
+          int d0, d1, d2, e0, e1, e2;
+          const double a0 = nint_bits(g0, d0), a1 = nint_bits(g1, d1), a2 = nint_bits(g2, d2);
+          const double t0 = dr0 + g0 - a0, t1 = dr1 + g1 - a1, t2 = dr2 + g2 - a2;
+          const double b0 = nint_bits(t0, e0), b1 = nint_bits(t1, e1), b2 = nint_bits(t2, e2);
+          dr0 = t0 - b0; dr1 = t1 - b1; dr2 = t2 - b2;
+          d0 += e0; d1 += e1; d2 += e2;
+          if (inner) {
+            x += d0; y += d1; z += d2;
+            id += d0 + n1 * (d1 + n2 * d2);
+          } else {
+            x = wrap2(x + d0, n1);
+            y = wrap2(y + d1, n2);
+            z = wrap2(z + d2, n3);
+            id = x + n1 * (y + n2 * z);
+          }
+          // did not move although the gradient is not zero: k_walk_big (k_walk hands these over as well)
+          if (id == oid) st = 3;
+        }
+        // known(p) = 1 (:484); harmless when the walk has just ended
+        rhomax = r0 > rhomax ? r0 : rhomax;
+        first = false;
+      }
+      if (st) {
+        pend_st = st; pend_out = out; pend_sli = sli;
+        active = false;
       }
     }
   }
@@ -880,7 +1114,7 @@ __global__ void __launch_bounds__(64) k_walk_big(const __grid_constant__ BaderPa
   const int start = A.overflow[t].x, tidx = A.overflow[t].y;
   WState w;
   walk_init(P, A.rho, w, start);
-  const SafeMap nosafe{nullptr, 0, 0, 0, 0, 0, 0, 0, 0};
+  const SafeMap nosafe{nullptr, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   const SafeMap& sm = (tidx >= 0 && A.stop) ? A.sm : nosafe;  // no stop log, no early stop
   const int oldlab = FIX ? (A.label_g[start] & LMASK) : 0;
   int out = 0, st, sli = -1;
@@ -1573,6 +1807,8 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
   P.in1 = std::max(P.n1 - 6, 0); P.in2 = std::max(P.n2 - 6, 0); P.in3 = std::max(P.n3 - 6, 0);
   memcpy(P.c2l, car2lat, sizeof(P.c2l));
   memcpy(P.lid, lat_i_dist, sizeof(P.lid));
+  fastdiv_make((unsigned)P.n1, P.mg1, P.sh1);
+  fastdiv_make((unsigned)P.n1 * (unsigned)P.n2, P.mg12, P.sh12);
   const int n1 = P.n1, n2 = P.n2, n3 = P.n3;
   const size_t plane = (size_t)n1 * n2;
   // diagonal car2lat (orthogonal cell): the off-diagonal products are exact zeros and can be skipped
@@ -1773,6 +2009,7 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
   WA.steps_per_check = spc_coarse;
   const int walk_occ = 4;  // resident 256-thread walker blocks per SM (<= 64 registers)
   const bool walk_stats = getenv("C2G_BADER_VERBOSE") != nullptr || getenv("C2G_BADER_STATS") != nullptr;
+  const bool walk_old = getenv("C2G_WALK_OLD") != nullptr;  // k_walk (threshold refill) instead of k_walk2
   const int wblocks = ctx->nsm * walk_occ;
 
   auto check_err = [&]() -> int {
@@ -1818,6 +2055,21 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
     const int blocks = (int)std::min<long long>(wblocks, (count + 255) / 256);
     ctx->prof_begin(name);
     const int variant = (ortho ? 4 : 0) | (fix ? 2 : 0) | (walk_stats ? 1 : 0);
+    if (!walk_old) {
+      // k_walk2 refills idle lanes before every step once `refill_min` lanes are idle (default 1)
+      WA.refill_min = 1;
+      if (const char* e = getenv("C2G_W2_REFILL")) WA.refill_min = std::max(1, std::min(32, atoi(e)));
+      switch (variant) {
+        case 0: k_walk2<false, false, false><<<blocks, 256, 0, st>>>(P, WA); break;
+        case 1: k_walk2<false, false, true><<<blocks, 256, 0, st>>>(P, WA); break;
+        case 2: k_walk2<false, true, false><<<blocks, 256, 0, st>>>(P, WA); break;
+        case 3: k_walk2<false, true, true><<<blocks, 256, 0, st>>>(P, WA); break;
+        case 4: k_walk2<true, false, false><<<blocks, 256, 0, st>>>(P, WA); break;
+        case 5: k_walk2<true, false, true><<<blocks, 256, 0, st>>>(P, WA); break;
+        case 6: k_walk2<true, true, false><<<blocks, 256, 0, st>>>(P, WA); break;
+        default: k_walk2<true, true, true><<<blocks, 256, 0, st>>>(P, WA); break;
+      }
+    } else
     switch (variant) {
       case 0: k_walk<false, false, false><<<blocks, 256, 0, st>>>(P, WA); break;
       case 1: k_walk<false, false, true><<<blocks, 256, 0, st>>>(P, WA); break;
@@ -1837,7 +2089,7 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
   auto walk_lattice = [&](long long count, int lat_s, const char* name) -> int {
     if (count <= 0) return C2G_OK;
     WA.list = nullptr; WA.stop = nullptr; WA.items = nullptr; WA.nitems = 0; WA.flat_base = 0; WA.count = count;
-    WA.sm = SafeMap{nullptr, 0, 0, 0, 0, 0, 0, 0, 0}; WA.sm_level = 0;
+    WA.sm = SafeMap{nullptr, 0, 0, 0, 0, 0, 0, 0, 0, 0}; WA.sm_level = 0;
     WA.refill_min = lat_s == 1 ? refill_fine : refill_coarse;
     WA.steps_per_check = lat_s == 1 ? spc_fine : spc_coarse;
     WA.lat_s = lat_s; WA.lat_m1 = (n1 + lat_s - 1) / lat_s; WA.lat_m2 = (n2 + lat_s - 1) / lat_s;
@@ -1869,7 +2121,7 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
                                         b_dlist.as<int>(), doff);
     C2G_KERNEL_CHECK(ctx);
     ctx->launches += 3;
-    WA.list = b_dlist.as<int>(); WA.stop = b_stop.as<int>(); WA.flat_base = 0; WA.count = count;
+    WA.list = b_dlist.as<int>(); WA.stop = b_stop.as<int>(); WA.flat_base = doff; WA.count = count;
     WA.items = b_items.as<int2>(); WA.nitems = (int)std::min<size_t>(maxitems, 0x7fffffff); WA.nitems_dev = cnt + 10;
     WA.sm = sm; WA.sm_level = sm_level; WA.lat_s = 1; WA.lat_m1 = n1; WA.lat_m2 = n2;
     WA.next = next; WA.nextcap = (int)std::min<long long>(listcap, 0x7fffffff);
@@ -1895,7 +2147,7 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
     doff += count;
     return launch_walk(count, fix, name);
   };
-  const SafeMap nosafe{nullptr, 0, 0, 0, 0, 0, 0, 0, 0};
+  const SafeMap nosafe{nullptr, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 
   int rc;
   if (algo == C2G_BADER_EXACT) {
@@ -1959,10 +2211,10 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
             const int px = (n1 % L.s) == 0, py = (n2 % L.s) == 0;
             const int pz = (S.periodic && (n3 % L.s) == 0) ? 1 : 0;
             k_vsafe<<<sg, 256, 0, st>>>(L.c1, L.c2, L.c3, px, py, pz, (S.nzl % L.s) == 0 ? 1 : 0, b_uni[i].as<int>(), b_safe[i].as<int>());
-            sm = SafeMap{b_safe[i].as<int>(), i + 1, L.c1, L.c2, L.c3, S.zlo, S.nzl, 1, pz};
+            sm = SafeMap{b_safe[i].as<int>(), i + 1, L.c1, L.c2, L.c3, S.zlo, S.nzl, 1, pz, (1 << (i + 1)) >> 1};
           } else {
             k_safe<<<sg, 256, 0, st>>>(L.c1, L.c2, L.c3, b_uni[i].as<int>(), b_safe[i].as<int>());
-            sm = SafeMap{b_safe[i].as<int>(), i + 1, L.c1, L.c2, L.c3, S.zlo, S.nzl, 0, 0};
+            sm = SafeMap{b_safe[i].as<int>(), i + 1, L.c1, L.c2, L.c3, S.zlo, S.nzl, 0, 0, 0};
           }
           ctx->prof_end();
           C2G_KERNEL_CHECK(ctx);

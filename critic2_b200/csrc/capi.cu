@@ -499,7 +499,12 @@ int c2g_basins_counts(c2g_basins* res, long long* counts) {
   return C2G_OK;
 }
 
-int c2g_basins_set_map(c2g_basins* res, int nattr, const int* map) {
+// reclose: YT only -- the map is the attractor identification of the sweep itself (yt@proc.f90:129-168), so the
+// interior / IAS classification follows it; false for the later relabelling of int_reorder_gridout, which renames
+// basins and leaves the IAS points alone (integration@proc.f90:1139-1144)
+static int set_map_impl(c2g_basins* res, int nattr, const int* map, bool reclose);
+int c2g_basins_set_map(c2g_basins* res, int nattr, const int* map) { return set_map_impl(res, nattr, map, true); }
+static int set_map_impl(c2g_basins* res, int nattr, const int* map, bool reclose) {
   if (!res) return C2G_ERR_ARG;
   c2g_context* ctx = res->ctx;
   if (!map || nattr < 0) return ctx->fail(C2G_ERR_ARG, "c2g_basins_set_map: bad argument");
@@ -511,6 +516,7 @@ int c2g_basins_set_map(c2g_basins* res, int nattr, const int* map) {
   C2G_CUDA(ctx, cudaMemcpyAsync(res->d_map, res->map.data(), sizeof(int) * res->nmax, cudaMemcpyHostToDevice, ctx->stream));
   C2G_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   res->has_map = true;
+  if (res->kind == 1 && reclose) return c2g_yt_apply_map(res);
   return C2G_OK;
 }
 
@@ -531,7 +537,7 @@ int c2g_basins_relabel(c2g_basins* res, int nattr0, const int* assigned, int nat
     const int old = res->map[i];
     m[i] = old > 0 ? assigned[old - 1] : 0;
   }
-  return c2g_basins_set_map(res, nattr_new, m.data());
+  return set_map_impl(res, nattr_new, m.data(), false);
 }
 
 int c2g_basins_labels(c2g_basins* res, int* idg) {

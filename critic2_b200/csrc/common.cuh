@@ -161,6 +161,7 @@ struct c2g_basins {
   long long n_ias = 0;
 };
 void c2g_yt_free_state(c2g_basins* res);
+int c2g_yt_apply_map(c2g_basins* res);  // yt.cu: IAS closure for the current maximum -> basin map
 int c2g_yt_weights_device(c2g_basins* res, int idb, double* d_w);  // yt.cu: weights of one basin into a device array
 void c2g_fft_free_plans(c2g_context* ctx);
 void c2g_slab_bounds(int n3, int nranks, int rank, int* zlo, int* zhi);

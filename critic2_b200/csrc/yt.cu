@@ -112,20 +112,43 @@ __global__ void __launch_bounds__(256) k_jump(long long nn, int* __restrict__ up
   if (up[u] != u) *changed = 1;
 }
 
-// seeds of the IAS closure; label = candidate basin (index into maxima) for now
+// terminal maximum (linear id) -> index in the ordered maxima list, in place
+__global__ void __launch_bounds__(256) k_cand_index(long long nn, int* __restrict__ up, const int* __restrict__ hk,
+                                                    const int* __restrict__ hv, unsigned hmask) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  int last_t = -1, last_o = -1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nn; i += stride) {
+    const int t = up[i];
+    if (t != last_t) {
+      unsigned s = ((unsigned)t * 2654435761u) & hmask;
+      while (hk[s] != t) s = (s + 1) & hmask;
+      last_t = t;
+      last_o = hv[s];
+    }
+    up[i] = last_o;
+  }
+}
+
+// Seeds of the IAS closure (yt@proc.f90:170-173): a point below at least one other point is an IAS point when the
+// basins of its higher neighbours differ or one of them has none.  cand = index of the maximum reached by steepest
+// ascent; map (may be null = every maximum is its own basin) = maximum -> basin id as the reference's sweep writes it
+// into ibasin (identify_atom / are_lclose merge maxima into one attractor, a DISCARDed maximum keeps 0, :129-168).
 __global__ void __launch_bounds__(256) k_seed(const __grid_constant__ YtParams P, const unsigned* __restrict__ mask,
-                                              const int* __restrict__ up, unsigned char* __restrict__ ias,
-                                              int* __restrict__ queue, int* __restrict__ qtail) {
+                                              const int* __restrict__ cand, const int* __restrict__ map,
+                                              unsigned char* __restrict__ ias, int* __restrict__ queue, int* __restrict__ qtail) {
   const long long nn = (long long)P.n1 * P.n2 * P.n3;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nn) return;
   const unsigned m = mask[i];
   if (m == 0) return;
   const Pt p = unlin(P, (int)i);
-  const int c0 = up[i];
-  bool seed = false;
+  const int c0 = map ? __ldg(map + cand[i]) : cand[i] + 1;  // basin of the steepest higher neighbour
+  bool seed = c0 == 0;
   for (int k = 0; k < P.nvec; k++)
-    if (m & (1u << k)) seed = seed || (up[nbr(P, p, k)] != c0);
+    if (m & (1u << k)) {
+      const int cj = cand[nbr(P, p, k)];
+      seed = seed || ((map ? __ldg(map + cj) : cj + 1) != c0);
+    }
   if (seed) {
     ias[i] = 1;
     queue[atomicAdd(qtail, 1)] = (int)i;
@@ -345,22 +368,10 @@ __global__ void __launch_bounds__(256) k_interior(const __grid_constant__ YtPara
 }
 
 // final labels: interior -> index of its maximum in the ordered list, IAS -> -1
-__global__ void __launch_bounds__(256) k_yt_labels(long long nn, const int* __restrict__ up, const unsigned char* __restrict__ ias,
-                                                   const int* __restrict__ hk, const int* __restrict__ hv, unsigned hmask,
+__global__ void __launch_bounds__(256) k_yt_labels(long long nn, const int* __restrict__ cand, const unsigned char* __restrict__ ias,
                                                    int* __restrict__ label) {
   const long long stride = (long long)gridDim.x * blockDim.x;
-  int last_t = -1, last_o = -1;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nn; i += stride) {
-    if (ias[i]) { label[i] = -1; continue; }
-    const int t = up[i];
-    if (t != last_t) {
-      unsigned s = ((unsigned)t * 2654435761u) & hmask;
-      while (hk[s] != t) s = (s + 1) & hmask;
-      last_t = t;
-      last_o = hv[s];
-    }
-    label[i] = last_o;
-  }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nn; i += stride) label[i] = ias[i] ? -1 : cand[i];
 }
 
 // downhill sweep for the weight field of one basin (yt_weights): w on IAS points by levels, descending
@@ -421,10 +432,13 @@ struct YtState {
   unsigned char* ias = nullptr;
   int* order = nullptr;
   int* lvl = nullptr;
+  int* cand = nullptr;            // index of the maximum every point reaches by steepest ascent
+  std::vector<int> closure_map;   // maximum -> basin map the IAS closure was built with (empty: one basin per maximum)
   int nlevels = 0;
   int nias = 0;
   c2g_context* ctx = nullptr;
   ~YtState() {
+    c2g_release(ctx, cand);
     c2g_release(ctx, mask);
     c2g_release(ctx, csum);
     c2g_release(ctx, ias);
@@ -442,6 +456,140 @@ void c2g_yt_free_state(c2g_basins* res) {
     delete yt_state(res);
     res->yt = nullptr;
   }
+}
+
+// IAS closure, labels and sweep levels for a given maximum -> basin map (device array, null = one basin per maximum).
+// Run by c2g_yt_build with the identity and again by c2g_basins_set_map when the caller's attractor identification
+// merges maxima (identify_atom / are_lclose) or discards one: the reference classifies every point with the merged
+// ids already in ibasin (yt@proc.f90:129-186), so a point between two maxima of ONE attractor is interior there.
+static int yt_closure(c2g_context* ctx, c2g_basins* res, const int* d_map) {
+  YtState* S = yt_state(res);
+  const YtParams& P = S->P;
+  cudaStream_t st = ctx->stream;
+  const long long nn = res->nn;
+  const int nb = c2g_blocks_for(nn, 256);
+  DevBuf b_ctl, b_queue, b_indeg;
+  C2G_CUDA(ctx, b_ctl.alloc(ctx, 64));
+  int* ctl = b_ctl.as<int>();
+  int hctl[4];
+  // seeds + closure
+  C2G_CUDA(ctx, b_queue.alloc(ctx, sizeof(int) * nn));
+  C2G_CUDA(ctx, cudaMemsetAsync(S->ias, 0, ((size_t)nn + 3) / 4 * 4, st));
+  C2G_CUDA(ctx, cudaMemsetAsync(ctl, 0, 64, st));
+  ctx->prof_begin("yt_seed");
+  k_seed<<<nb, 256, 0, st>>>(P, S->mask, S->cand, d_map, S->ias, b_queue.as<int>(), ctl);
+  ctx->prof_end();
+  C2G_KERNEL_CHECK(ctx);
+  {
+    int blocks = 0, rc;
+    if ((rc = coop_grid(ctx, k_bfs, 256, &blocks)) != C2G_OK) return rc;
+    const unsigned* a_mask = S->mask;
+    unsigned char* a_ias = S->ias;
+    int* a_queue = b_queue.as<int>();
+    const int bfs_maxlvl = 1 << 20;  // more levels than any grid dimension allows; the counter index saturates
+    DevBuf b_bcnt;
+    C2G_CUDA(ctx, b_bcnt.alloc(ctx, sizeof(int) * ((size_t)bfs_maxlvl + 2)));
+    C2G_CUDA(ctx, cudaMemsetAsync(b_bcnt.p, 0, sizeof(int) * ((size_t)bfs_maxlvl + 2), st));
+    int* a_bcnt = b_bcnt.as<int>();
+    int a_bmax = bfs_maxlvl;
+    void* args[] = {(void*)&P, (void*)&a_mask, (void*)&a_ias, (void*)&a_queue, (void*)&ctl, (void*)&a_bcnt, (void*)&a_bmax};
+    ctx->prof_begin("yt_bfs");
+    C2G_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_bfs, dim3(blocks), dim3(256), args, 0, st));
+    ctx->prof_end();
+  }
+  C2G_CUDA(ctx, cudaMemcpyAsync(hctl, ctl, 16, cudaMemcpyDeviceToHost, st));
+  C2G_CUDA(ctx, cudaStreamSynchronize(st));
+  const int nias = hctl[0];
+  const int bfs_levels = hctl[1];
+  S->nias = nias;
+  res->n_ias = nias;
+  // labels
+  ctx->prof_begin("yt_labels");
+  k_yt_labels<<<ctx->nsm * 8, 256, 0, st>>>(nn, S->cand, S->ias, res->d_label);
+  ctx->prof_end();
+  C2G_KERNEL_CHECK(ctx);
+  // Kahn levels of the IAS graph
+  const int maxlvl = 1 << 22;
+  c2g_release(ctx, S->order); S->order = nullptr;
+  C2G_CUDA(ctx, c2g_alloc(ctx, (void**)&S->order, sizeof(int) * std::max(nias, 1)));
+  if (!S->lvl) C2G_CUDA(ctx, c2g_alloc(ctx, (void**)&S->lvl, sizeof(int) * (maxlvl + 1)));
+  S->nlevels = 0;
+  if (nias > 0) {
+    C2G_CUDA(ctx, b_indeg.alloc(ctx, ((size_t)nn + 3) / 4 * 4));
+    C2G_CUDA(ctx, cudaMemsetAsync(b_indeg.p, 0, ((size_t)nn + 3) / 4 * 4, st));
+    C2G_CUDA(ctx, cudaMemsetAsync(ctl, 0, 64, st));
+    ctx->prof_begin("yt_indeg");
+    k_indeg<<<c2g_blocks_for(nias, 256), 256, 0, st>>>(P, S->mask, S->ias, b_queue.as<int>(), nias, b_indeg.as<unsigned char>(),
+                                                       S->order, ctl);
+    ctx->prof_end();
+    C2G_KERNEL_CHECK(ctx);
+    int blocks = 0, rc;
+    if ((rc = coop_grid(ctx, k_kahn, 256, &blocks)) != C2G_OK) return rc;
+    DevBuf b_lcnt;
+    C2G_CUDA(ctx, b_lcnt.alloc(ctx, sizeof(int) * ((size_t)maxlvl + 2)));
+    C2G_CUDA(ctx, cudaMemsetAsync(b_lcnt.p, 0, sizeof(int) * ((size_t)maxlvl + 2), st));
+    int* a_cnt = b_lcnt.as<int>();
+    const unsigned* a_mask = S->mask;
+    const unsigned char* a_ias = S->ias;
+    unsigned char* a_indeg = b_indeg.as<unsigned char>();
+    int* a_order = S->order;
+    int* a_lvl = S->lvl;
+    int a_maxlvl = maxlvl;
+    void* args[] = {(void*)&P, (void*)&a_mask, (void*)&a_ias, (void*)&a_indeg, (void*)&a_order, (void*)&ctl, (void*)&a_lvl, (void*)&a_cnt, (void*)&a_maxlvl};
+    ctx->prof_begin("yt_kahn");
+    C2G_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_kahn, dim3(blocks), dim3(256), args, 0, st));
+    ctx->prof_end();
+    C2G_CUDA(ctx, cudaMemcpyAsync(hctl, ctl, 16, cudaMemcpyDeviceToHost, st));
+    C2G_CUDA(ctx, cudaStreamSynchronize(st));
+    if (hctl[0] != nias) return ctx->fail(C2G_ERR_STATE, "YT: flux graph is not acyclic (%d of %d ordered)", hctl[0], nias);
+    if (hctl[1] >= maxlvl) return ctx->fail(C2G_ERR_OVERFLOW, "YT: more than %d sweep levels", maxlvl);
+    S->nlevels = hctl[1];
+    if (getenv("C2G_YT_NO_LEVEL_SORT") == nullptr && S->nlevels > 0) {  // spatial order inside every level
+      DevBuf b_k0, b_k1, b_tmp;
+      C2G_CUDA(ctx, b_k0.alloc(ctx, sizeof(unsigned long long) * (size_t)nias));
+      C2G_CUDA(ctx, b_k1.alloc(ctx, sizeof(unsigned long long) * (size_t)nias));
+      int lbits = 1;
+      while ((1ll << lbits) < (long long)S->nlevels + 1) lbits++;
+      size_t tmpbytes = 0;
+      cub::DeviceRadixSort::SortKeys(nullptr, tmpbytes, b_k0.as<unsigned long long>(), b_k1.as<unsigned long long>(), nias, 0, 32 + lbits, st);
+      C2G_CUDA(ctx, b_tmp.alloc(ctx, tmpbytes));
+      ctx->prof_begin("yt_level_sort");
+      k_level_keys<<<c2g_blocks_for(nias, 256), 256, 0, st>>>(nias, S->nlevels, S->lvl, S->order, b_k0.as<unsigned long long>());
+      cub::DeviceRadixSort::SortKeys(b_tmp.p, tmpbytes, b_k0.as<unsigned long long>(), b_k1.as<unsigned long long>(), nias, 0, 32 + lbits, st);
+      k_level_unkey<<<c2g_blocks_for(nias, 256), 256, 0, st>>>(nias, b_k1.as<unsigned long long>(), S->order);
+      ctx->prof_end(3);
+      C2G_KERNEL_CHECK(ctx);
+    }
+  }
+  C2G_CUDA(ctx, cudaStreamSynchronize(st));
+  res->stats[0] = nias;
+  res->stats[1] = bfs_levels;
+  res->stats[2] = S->nlevels;
+  return C2G_OK;
+}
+
+// called by c2g_basins_set_map (capi.cu) for YT results: rebuild the closure if the map changes the partition
+int c2g_yt_apply_map(c2g_basins* res) {
+  c2g_context* ctx = res->ctx;
+  YtState* S = yt_state(res);
+  if (!S) return ctx->fail(C2G_ERR_STATE, "c2g_basins_set_map: YT state missing");
+  // plain map: every maximum is a basin of its own and none is discarded -> the closure of c2g_yt_build
+  bool plain = true;
+  {
+    std::vector<char> seen(res->nattr + 1, 0);
+    for (int m = 0; m < res->nmax && plain; m++) {
+      const int b = res->map[m];
+      if (b <= 0 || seen[b]) plain = false; else seen[b] = 1;
+    }
+  }
+  std::vector<int> key;
+  if (!plain) key = res->map;
+  if (key == S->closure_map) return C2G_OK;
+  int rc = yt_closure(ctx, res, plain ? nullptr : res->d_map);
+  if (rc != C2G_OK) return rc;
+  S->closure_map.swap(key);
+  ctx->prof_collect();
+  return C2G_OK;
 }
 
 extern "C" int c2g_yt_build(c2g_context* ctx, int handle, int nvec, const int* vec, const double* area, int* nmax_out,
@@ -483,7 +631,7 @@ extern "C" int c2g_yt_build(c2g_context* ctx, int handle, int nvec, const int* v
   C2G_CUDA(ctx, c2g_alloc(ctx, (void**)&S->mask, sizeof(unsigned) * nn));
   C2G_CUDA(ctx, c2g_alloc(ctx, (void**)&S->csum, sizeof(double) * nn));
   C2G_CUDA(ctx, c2g_alloc(ctx, (void**)&S->ias, ((size_t)nn + 3) / 4 * 4));
-  DevBuf b_up, b_ctl, b_maxl, b_queue, b_indeg;
+  DevBuf b_up, b_ctl, b_maxl;
   C2G_CUDA(ctx, b_up.alloc(ctx, sizeof(int) * nn));
   C2G_CUDA(ctx, b_ctl.alloc(ctx, 64));
   int maxcap = (int)std::min<long long>(nn, std::max<long long>(1 << 16, nn / 64));
@@ -549,97 +697,18 @@ extern "C" int c2g_yt_build(c2g_context* ctx, int handle, int nvec, const int* v
     C2G_CUDA(ctx, cudaStreamSynchronize(st));
     if (!hctl[2]) break;
   }
-  // seeds + closure
-  C2G_CUDA(ctx, b_queue.alloc(ctx, sizeof(int) * nn));
-  C2G_CUDA(ctx, cudaMemsetAsync(S->ias, 0, ((size_t)nn + 3) / 4 * 4, st));
-  C2G_CUDA(ctx, cudaMemsetAsync(ctl, 0, 64, st));
-  ctx->prof_begin("yt_seed");
-  k_seed<<<nb, 256, 0, st>>>(P, S->mask, b_up.as<int>(), S->ias, b_queue.as<int>(), ctl);
+  // terminal maxima -> indices into the ordered list; kept for the closure (which depends on the maximum -> basin map)
+  ctx->prof_begin("yt_cand");
+  k_cand_index<<<ctx->nsm * 8, 256, 0, st>>>(nn, b_up.as<int>(), b_hk.as<int>(), b_hv.as<int>(), hsize - 1);
   ctx->prof_end();
   C2G_KERNEL_CHECK(ctx);
+  S->cand = b_up.as<int>();
+  b_up.p = nullptr;  // ownership moves to the state
   {
-    int blocks = 0, rc;
-    if ((rc = coop_grid(ctx, k_bfs, 256, &blocks)) != C2G_OK) return rc;
-    const unsigned* a_mask = S->mask;
-    unsigned char* a_ias = S->ias;
-    int* a_queue = b_queue.as<int>();
-    const int bfs_maxlvl = 1 << 20;  // more levels than any grid dimension allows; the counter index saturates
-    DevBuf b_bcnt;
-    C2G_CUDA(ctx, b_bcnt.alloc(ctx, sizeof(int) * ((size_t)bfs_maxlvl + 2)));
-    C2G_CUDA(ctx, cudaMemsetAsync(b_bcnt.p, 0, sizeof(int) * ((size_t)bfs_maxlvl + 2), st));
-    int* a_bcnt = b_bcnt.as<int>();
-    int a_bmax = bfs_maxlvl;
-    void* args[] = {(void*)&P, (void*)&a_mask, (void*)&a_ias, (void*)&a_queue, (void*)&ctl, (void*)&a_bcnt, (void*)&a_bmax};
-    ctx->prof_begin("yt_bfs");
-    C2G_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_bfs, dim3(blocks), dim3(256), args, 0, st));
-    ctx->prof_end();
-  }
-  C2G_CUDA(ctx, cudaMemcpyAsync(hctl, ctl, 16, cudaMemcpyDeviceToHost, st));
-  C2G_CUDA(ctx, cudaStreamSynchronize(st));
-  const int nias = hctl[0];
-  const int bfs_levels = hctl[1];
-  S->nias = nias;
-  res->n_ias = nias;
-  // labels
-  ctx->prof_begin("yt_labels");
-  k_yt_labels<<<ctx->nsm * 8, 256, 0, st>>>(nn, b_up.as<int>(), S->ias, b_hk.as<int>(), b_hv.as<int>(), hsize - 1, res->d_label);
-  ctx->prof_end();
-  C2G_KERNEL_CHECK(ctx);
-  // Kahn levels of the IAS graph
-  const int maxlvl = 1 << 22;
-  C2G_CUDA(ctx, c2g_alloc(ctx, (void**)&S->order, sizeof(int) * std::max(nias, 1)));
-  C2G_CUDA(ctx, c2g_alloc(ctx, (void**)&S->lvl, sizeof(int) * (maxlvl + 1)));
-  if (nias > 0) {
-    C2G_CUDA(ctx, b_indeg.alloc(ctx, ((size_t)nn + 3) / 4 * 4));
-    C2G_CUDA(ctx, cudaMemsetAsync(b_indeg.p, 0, ((size_t)nn + 3) / 4 * 4, st));
-    C2G_CUDA(ctx, cudaMemsetAsync(ctl, 0, 64, st));
-    ctx->prof_begin("yt_indeg");
-    k_indeg<<<c2g_blocks_for(nias, 256), 256, 0, st>>>(P, S->mask, S->ias, b_queue.as<int>(), nias, b_indeg.as<unsigned char>(),
-                                                       S->order, ctl);
-    ctx->prof_end();
-    C2G_KERNEL_CHECK(ctx);
-    int blocks = 0, rc;
-    if ((rc = coop_grid(ctx, k_kahn, 256, &blocks)) != C2G_OK) return rc;
-    DevBuf b_lcnt;
-    C2G_CUDA(ctx, b_lcnt.alloc(ctx, sizeof(int) * ((size_t)maxlvl + 2)));
-    C2G_CUDA(ctx, cudaMemsetAsync(b_lcnt.p, 0, sizeof(int) * ((size_t)maxlvl + 2), st));
-    int* a_cnt = b_lcnt.as<int>();
-    const unsigned* a_mask = S->mask;
-    const unsigned char* a_ias = S->ias;
-    unsigned char* a_indeg = b_indeg.as<unsigned char>();
-    int* a_order = S->order;
-    int* a_lvl = S->lvl;
-    int a_maxlvl = maxlvl;
-    void* args[] = {(void*)&P, (void*)&a_mask, (void*)&a_ias, (void*)&a_indeg, (void*)&a_order, (void*)&ctl, (void*)&a_lvl, (void*)&a_cnt, (void*)&a_maxlvl};
-    ctx->prof_begin("yt_kahn");
-    C2G_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_kahn, dim3(blocks), dim3(256), args, 0, st));
-    ctx->prof_end();
-    C2G_CUDA(ctx, cudaMemcpyAsync(hctl, ctl, 16, cudaMemcpyDeviceToHost, st));
-    C2G_CUDA(ctx, cudaStreamSynchronize(st));
-    if (hctl[0] != nias) return ctx->fail(C2G_ERR_STATE, "YT: flux graph is not acyclic (%d of %d ordered)", hctl[0], nias);
-    if (hctl[1] >= maxlvl) return ctx->fail(C2G_ERR_OVERFLOW, "YT: more than %d sweep levels", maxlvl);
-    S->nlevels = hctl[1];
-    if (getenv("C2G_YT_NO_LEVEL_SORT") == nullptr && S->nlevels > 0) {  // spatial order inside every level
-      DevBuf b_k0, b_k1, b_tmp;
-      C2G_CUDA(ctx, b_k0.alloc(ctx, sizeof(unsigned long long) * (size_t)nias));
-      C2G_CUDA(ctx, b_k1.alloc(ctx, sizeof(unsigned long long) * (size_t)nias));
-      int lbits = 1;
-      while ((1ll << lbits) < (long long)S->nlevels + 1) lbits++;
-      size_t tmpbytes = 0;
-      cub::DeviceRadixSort::SortKeys(nullptr, tmpbytes, b_k0.as<unsigned long long>(), b_k1.as<unsigned long long>(), nias, 0, 32 + lbits, st);
-      C2G_CUDA(ctx, b_tmp.alloc(ctx, tmpbytes));
-      ctx->prof_begin("yt_level_sort");
-      k_level_keys<<<c2g_blocks_for(nias, 256), 256, 0, st>>>(nias, S->nlevels, S->lvl, S->order, b_k0.as<unsigned long long>());
-      cub::DeviceRadixSort::SortKeys(b_tmp.p, tmpbytes, b_k0.as<unsigned long long>(), b_k1.as<unsigned long long>(), nias, 0, 32 + lbits, st);
-      k_level_unkey<<<c2g_blocks_for(nias, 256), 256, 0, st>>>(nias, b_k1.as<unsigned long long>(), S->order);
-      ctx->prof_end(3);
-      C2G_KERNEL_CHECK(ctx);
-    }
+    int rc = yt_closure(ctx, res, nullptr);
+    if (rc != C2G_OK) return rc;
   }
   C2G_CUDA(ctx, cudaStreamSynchronize(st));
-  res->stats[0] = nias;
-  res->stats[1] = bfs_levels;
-  res->stats[2] = S->nlevels;
   res->stats[4] = nmax;
   ctx->prof_collect();
   guard.ok = true;

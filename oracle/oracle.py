@@ -184,6 +184,35 @@ def yt_integrate(f, x2c, vec, area, atoms=None, ratom=1.0, atexist=True, stable=
     return d
 
 
+def yt_reclassify(d, f, vec, mp, shape):
+    """The classification loop of yt_integrate (yt@proc.f90:108-186) replayed in pure Python on the oracle's rank
+    permutation d.iio with a GIVEN maximum -> basin map `mp` (1-based ids in the order in which the sweep meets the
+    maxima; 0 = a maximum rejected by the DISCARD expression, :152-166, which the C++ oracle does not evaluate).
+    Small grids only.  Returns the spatial basin ids (0 = IAS or unassigned)."""
+    n1, n2, n3 = shape
+    nn = n1 * n2 * n3
+    vec = np.asarray(vec, dtype=np.int64).reshape(-1, 3)
+    rank = np.asarray(d.iio, dtype=np.int64) - 1          # rank (0-based) of every spatial point
+    order = np.empty(nn, dtype=np.int64)
+    order[rank] = np.arange(nn)                            # spatial point of every rank
+    idx = np.arange(nn)
+    x, y, z = idx % n1, (idx // n1) % n2, idx // (n1 * n2)
+    nb = np.stack([((x + v[0]) % n1) + n1 * (((y + v[1]) % n2) + n2 * ((z + v[2]) % n3)) for v in vec], axis=1)
+    nbrank = rank[nb]
+    ib = np.zeros(nn, dtype=np.int32)                      # by spatial point
+    nfound = 0
+    for r in range(nn - 1, -1, -1):
+        i = order[r]
+        hi = nb[i][nbrank[i] > r]
+        if len(hi) == 0:
+            ib[i] = mp[nfound]
+            nfound += 1
+        else:
+            b0 = ib[hi[0]]
+            ib[i] = b0 if (b0 != 0 and np.all(ib[hi] == b0)) else 0
+    return ib.reshape(shape, order="F")
+
+
 def yt_isosurface(f, vec, isov, stable=False, maxattr=None):
     """yt_isosurface (yt@proc.f90:233-390) without a DISCARD expression.
     Returns (idg[n1,n2,n3], nraw, nattr, xattr[3,nraw])."""

@@ -1,0 +1,142 @@
+"""BADER / YT label parity at the BASELINE.json sizes (pytest -m gpu): the device labels against the oracle's
+faithful sequential bader_integrate (bader@proc.f90:151-224, 300-422) on EVERY point.
+
+  256^3 class (configs[1] urea-like cell, the headline model, heterogeneous basins, a molecule in vacuum, a flat
+  non-cubic cell): the oracle runs inside the test (4-15 s each);
+  512^3 (the size BASELINE.json's metric names): the oracle runs inside the test (~100 s);
+  1024^3 (configs[4], the bench workload): the oracle needs ~20 min, so it was run once by tools/golden_at_size.py on
+  a B200 box and its label SHA-256 + points per basin are committed (tests/golden/bader_at_size.json); the test
+  asserts the density hash (the generator is deterministic), the FAST labels against that fixture and FAST == the
+  exact-walk referee on the device.
+The densities are generated in HBM (c2g_promolecular) and downloaded for the oracle: both sides see the same array.
+"""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import sized_cases as Z
+import systems as S
+from critic2_b200 import capi
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "bader_at_size.json")
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a.ravel(order="F")).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return json.load(open(GOLDEN)) if os.path.exists(GOLDEN) else {}
+
+
+def device_labels(ctx, h, c, algo):
+    n, x2c, at = c["n"], c["x2c"], c["atoms"]
+    _, car2lat, lid = orc.bader_metrics(x2c, n)
+    b = ctx.bader_assign(h, car2lat, lid, algo=algo)
+    mp, dist = Z.atom_map(b.maxima(), n, x2c, at)
+    assert dist.max() <= 1.0  # ratom of the atoms mode (integration@proc.f90:246-248 -> identify_atom)
+    b.set_map(len(at), mp)
+    lab = b.labels(n)
+    nmax = b.nmax
+    b.free()
+    return lab, nmax
+
+
+def generate(ctx, c):
+    h = ctx.alloc(c["n"])
+    ctx.promolecular(h, c["x2c"], c["atoms"], c["z"], c["alpha"], nimg=c["nimg"], rc=c["rc"])
+    return h
+
+
+@pytest.mark.parametrize("name", ["urea256", "head256", "hetero192", "molvac256", "flat160"])
+def test_labels_vs_oracle_256_class(ctx, golden, name):
+    c = Z.CASES[name]()
+    h = generate(ctx, c)
+    f = ctx.download(h, c["n"])
+    idg, nattr, _, _ = orc.bader_integrate(f, c["x2c"], atoms=c["atoms"])
+    if name in golden:  # the oracle and the generator have not drifted since the fixture was made
+        assert sha(f) == golden[name]["rho_sha256"]
+        assert sha(idg) == golden[name]["labels_sha256"]
+    for algo in (capi.BADER_FAST, capi.BADER_EXACT):
+        lab, nmax = device_labels(ctx, h, c, algo)
+        assert np.count_nonzero(lab != idg) == 0, f"{name}: algo {algo} differs from the oracle"
+    ctx.free(h)
+
+
+@pytest.mark.parametrize("name,l0", [("head256", "32"), ("hetero192", "32"), ("molvac256", "16"), ("urea256", "32")])
+def test_forced_top_stride_vs_oracle(ctx, name, l0):
+    """C2G_BADER_L0 overrides the basin-size guard on the top lattice stride: strides up to 32 (the one the 1024^3
+    run does not reach on its own is 32; it uses 16) must give the same labels -- the fills of wide cubes are only
+    ever a starting guess, the edge fix and the stop log repair them."""
+    c = Z.CASES[name]()
+    h = generate(ctx, c)
+    f = ctx.download(h, c["n"])
+    idg, _, _, _ = orc.bader_integrate(f, c["x2c"], atoms=c["atoms"])
+    os.environ["C2G_BADER_L0"] = l0
+    try:
+        lab, _ = device_labels(ctx, h, c, capi.BADER_FAST)
+    finally:
+        del os.environ["C2G_BADER_L0"]
+    assert np.count_nonzero(lab != idg) == 0
+    ctx.free(h)
+
+
+def test_labels_vs_oracle_512(ctx, golden):
+    """The 512^3 size of BASELINE.json's metric: every label against the oracle (serial, ~100 s on the host)."""
+    c = Z.CASES["head512"]()
+    h = generate(ctx, c)
+    f = ctx.download(h, c["n"])
+    idg, nattr, _, _ = orc.bader_integrate(f, c["x2c"], atoms=c["atoms"])
+    assert nattr == len(c["atoms"])
+    if "head512" in golden:
+        assert sha(f) == golden["head512"]["rho_sha256"]
+        assert sha(idg) == golden["head512"]["labels_sha256"]
+    lab, nmax = device_labels(ctx, h, c, capi.BADER_FAST)
+    assert nmax == nattr and np.count_nonzero(lab != idg) == 0
+    lab_e, _ = device_labels(ctx, h, c, capi.BADER_EXACT)
+    assert np.array_equal(lab, lab_e)
+    ctx.free(h)
+
+
+def test_headline_1024_against_the_cached_oracle_run(ctx, golden):
+    """configs[4]: labels of the bench workload against the committed result of the oracle's 1024^3 run."""
+    assert "head1024" in golden, "tests/golden/bader_at_size.json has no 1024^3 fixture (tools/golden_at_size.py head1024)"
+    g = golden["head1024"]
+    c = Z.CASES["head1024"]()
+    h = generate(ctx, c)
+    f = ctx.download(h, c["n"])
+    assert sha(f) == g["rho_sha256"], "the density generator changed: rerun tools/golden_at_size.py head1024"
+    del f
+    lab, nmax = device_labels(ctx, h, c, capi.BADER_FAST)
+    assert nmax == g["nattr"] == len(c["atoms"])
+    assert np.array_equal(np.bincount(lab.ravel(), minlength=nmax + 1), np.array(g["counts"]))
+    assert sha(lab) == g["labels_sha256"], "1024^3 FAST labels differ from the oracle's"
+    lab_e, _ = device_labels(ctx, h, c, capi.BADER_EXACT)
+    assert np.array_equal(lab, lab_e), "FAST differs from the exact-walk referee at 1024^3"
+    ctx.free(h)
+
+
+def test_yt_labels_vs_oracle_256(ctx):
+    """YT at 256^3 (configs[1] cell, nvec = 6): spatial basin ids against the oracle's qcksort + sweep
+    (yt@proc.f90:108-188), integrals to 1e-10."""
+    c = Z.CASES["urea256"]()
+    n, x2c = c["n"], c["x2c"]
+    h = generate(ctx, c)
+    f = ctx.download(h, n)
+    vec, area = S.wscell(x2c / np.array(n, dtype=float)[None, :])
+    d = orc.yt_integrate(f, x2c, vec, area, atoms=c["atoms"])
+    b = ctx.yt_build(h, vec, area)
+    mp, dist = Z.atom_map(b.maxima(), n, x2c, c["atoms"])
+    b.set_map(len(c["atoms"]), mp)
+    assert np.array_equal(b.labels(n), d.spatial_basin(n))
+    vol, ps = ctx.integrate(b, [h], S.omega(x2c))
+    vref, pref = orc.integrate_yt(d, [f], S.omega(x2c))
+    assert np.abs(vol - vref).max() <= 1e-10 * np.abs(vref).max()
+    assert np.abs(ps[:, 0] - pref[:, 0]).max() <= 1e-10 * np.abs(pref[:, 0]).max()
+    b.free(); ctx.free(h)

@@ -115,3 +115,26 @@ def test_nci_rdg_exponential_density_known_answer():
     assert np.allclose(np.abs(crho[0, 0, :]), rho1 * 100.0, rtol=1e-15)
     # lambda_2 = 0 exactly here (1-D field): sign(rho, +0) = +
     assert (crho > 0).all()
+
+
+def test_yt_classification_follows_the_attractor_map():
+    """The interior / IAS rule of yt@proc.f90:170-186 uses the MERGED attractor ids: the pure-Python replay of the
+    loop (oracle.yt_reclassify) reproduces the C++ oracle with one basin per maximum and with `ratom 2` merging two
+    pairs of maxima; the merged run has far fewer IAS points than the raw one."""
+    import helpers as H
+    n = (32, 32, 32)
+    x2c = S.cell_x2c(6.0, 6.0, 6.0)
+    at = S.snap_to_grid(np.array([[0.25, 0.25, 0.25], [0.25 + 1.0 / 6.0, 0.25, 0.25], [0.75, 0.70, 0.30], [0.30, 0.75, 0.75]]), n)
+    f = orc.promolecular(n, x2c, at, np.array([4.0, 3.5, 6.0, 2.0]), np.array([2.0, 2.1, 2.4, 1.6]), nimg=1)
+    vec, area = S.wscell(x2c / np.array(n, dtype=float)[None, :])
+    d0 = orc.yt_integrate(f, x2c, vec, area, atoms=None, ratom=1e-90, atexist=False)
+    assert d0.nattr == 4
+    assert np.array_equal(orc.yt_reclassify(d0, f, vec, np.arange(1, 5), n), d0.spatial_basin(n))
+    d2 = orc.yt_integrate(f, x2c, vec, area, atoms=None, ratom=2.0, atexist=False)
+    assert d2.nattr == 3
+    pm = np.round(d0.xattr.T * np.array(n)).astype(int) + 1
+    mp, na, _ = H.assign_attractors(pm, n, x2c, None, ratom=2.0, atexist=False)
+    assert na == 3
+    r2 = orc.yt_reclassify(d0, f, vec, mp, n)
+    assert np.array_equal(r2, d2.spatial_basin(n))
+    assert (r2 == 0).sum() < (d0.spatial_basin(n) == 0).sum()
