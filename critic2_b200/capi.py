@@ -22,7 +22,7 @@ FT_CODES = {"x": 33, "y": 34, "z": 35, "xx": 36, "xy": 37, "xz": 38, "yy": 39, "
 ORDER_INDEX, ORDER_SCAN = 0, 1
 
 EXPORTS = [
-    "c2g_init", "c2g_nccl_unique_id", "c2g_init_multi", "c2g_finalize", "c2g_last_error", "c2g_describe",
+    "c2g_init", "c2g_init_devices", "c2g_nccl_unique_id", "c2g_init_multi", "c2g_finalize", "c2g_last_error", "c2g_describe",
     "c2g_grid_upload", "c2g_grid_upload_slab", "c2g_slab_range", "c2g_slab_bounds_query", "c2g_grid_alloc", "c2g_grid_download", "c2g_grid_download_slab", "c2g_grid_free", "c2g_grid_promolecular",
     "c2g_bader_assign", "c2g_basins_maxima", "c2g_basins_counts", "c2g_basins_set_map", "c2g_basins_labels",
     "c2g_basins_relabel", "c2g_basins_nattr", "c2g_basins_free", "c2g_basins_stats", "c2g_integrate", "c2g_integrate_multipoles", "c2g_promolecular_grid", "c2g_hirshfeld_integrate", "c2g_basins_remap", "c2g_yt_build",
@@ -72,10 +72,14 @@ def slab_bounds(n3, nranks, rank):
 class Context:
     """One c2g_context (one GPU)."""
 
-    def __init__(self, device=0, rank=0, nranks=1, nccl_uid=None):
+    def __init__(self, device=0, rank=0, nranks=1, nccl_uid=None, ngpus=None):
+        """device: one GPU.  rank / nranks / nccl_uid: one process per GPU (c2g_init_multi).  ngpus: ONE process driving
+        devices 0..ngpus-1 (c2g_init_devices) -- every method then takes and returns whole arrays."""
         self.lib = load()
         self.h = C.c_void_p()
-        if nranks > 1:
+        if ngpus is not None:
+            rc = self.lib.c2g_init_devices(C.c_int(int(ngpus)), C.byref(self.h))
+        elif nranks > 1:
             rc = self.lib.c2g_init_multi(C.c_int(device), C.c_int(rank), C.c_int(nranks), nccl_uid, C.byref(self.h))
         else:
             rc = self.lib.c2g_init(C.c_int(device), C.byref(self.h))

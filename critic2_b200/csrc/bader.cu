@@ -28,6 +28,7 @@
 // Arithmetic: IEEE fp64, evaluation order of the Fortran source, NO fused multiply-add (this
 // translation unit is compiled with -fmad=false; the reference is built -O3 without -march/-ffast-math).
 #include "common.cuh"
+#include "group.h"
 
 #include <algorithm>
 
@@ -1793,6 +1794,7 @@ void c2g_slab_bounds(int n3, int nranks, int rank, int* zlo, int* zhi) {
 extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2lat[9], const double lat_i_dist[27],
                                 int algo, int order, int* nmax_out, c2g_basins** res_out) {
   if (!ctx) return C2G_ERR_ARG;
+  if (ctx->group) return grp_bader_assign(ctx, handle, car2lat, lat_i_dist, algo, order, nmax_out, res_out);
   if (!nmax_out || !res_out || !car2lat || !lat_i_dist) return ctx->fail(C2G_ERR_ARG, "c2g_bader_assign: null argument");
   if (handle < 0 || handle >= (int)ctx->grids.size() || !ctx->grids[handle].used)
     return ctx->fail(C2G_ERR_ARG, "c2g_bader_assign: invalid grid handle %d", handle);

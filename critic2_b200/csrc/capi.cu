@@ -1,6 +1,7 @@
 // capi.cu -- context, resident grids, basin bookkeeping and profiling entry points of the C ABI
 // declared in include/critic2_gpu.h.
 #include "common.cuh"
+#include "group.h"
 
 #include <dlfcn.h>
 
@@ -210,6 +211,7 @@ int c2g_init_multi(int device, int rank, int nranks, const void* uid128, c2g_con
 
 void c2g_finalize(c2g_context* ctx) {
   if (!ctx) return;
+  if (ctx->group) { c2g_group_finalize(ctx); return; }
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->copy_in) {
@@ -242,6 +244,7 @@ const char* c2g_describe(c2g_context* ctx) { return ctx ? ctx->desc.c_str() : ""
 
 int c2g_grid_alloc(c2g_context* ctx, const int n[3], int* handle) {
   if (!ctx) return C2G_ERR_ARG;
+  if (ctx->group) return grp_grid_alloc(ctx, n, handle);
   if (!n || !handle || n[0] < 1 || n[1] < 1 || n[2] < 1) return ctx->fail(C2G_ERR_ARG, "c2g_grid_alloc: bad shape");
   c2g_grid g;
   g.n[0] = n[0]; g.n[1] = n[1]; g.n[2] = n[2];
@@ -259,6 +262,7 @@ int c2g_grid_alloc(c2g_context* ctx, const int n[3], int* handle) {
 
 int c2g_grid_upload(c2g_context* ctx, const double* f, const int n[3], int* handle) {
   if (!ctx) return C2G_ERR_ARG;
+  if (ctx->group) return f ? grp_grid_upload(ctx, f, n, handle) : ctx->fail(C2G_ERR_ARG, "c2g_grid_upload: null field");
   if (!f) return ctx->fail(C2G_ERR_ARG, "c2g_grid_upload: null field");
   int rc = c2g_grid_alloc(ctx, n, handle);
   if (rc != C2G_OK) return rc;
@@ -273,6 +277,7 @@ int c2g_grid_upload(c2g_context* ctx, const double* f, const int n[3], int* hand
 // valid and unchanged until c2g_synchronize (or any call that returns results computed from this grid).
 int c2g_grid_upload_async(c2g_context* ctx, const double* f, const int n[3], int* handle) {
   if (!ctx) return C2G_ERR_ARG;
+  if (ctx->group) return c2g_grid_upload(ctx, f, n, handle);  // multi-device: the slab scatter is synchronous
   if (!f) return ctx->fail(C2G_ERR_ARG, "c2g_grid_upload_async: null field");
   int rc = ensure_copy_streams(ctx);
   if (rc != C2G_OK) return rc;
@@ -297,12 +302,13 @@ int c2g_slab_bounds_query(int n3, int nranks, int rank, int* zlo, int* zhi) {
 
 int c2g_slab_range(c2g_context* ctx, int n3, int* zlo, int* zhi) {
   if (!ctx || !zlo || !zhi || n3 < 1) return C2G_ERR_ARG;
-  c2g_slab_bounds(n3, ctx->nranks, ctx->rank, zlo, zhi);
+  c2g_slab_bounds(n3, ctx->nranks, ctx->rank, zlo, zhi);  // a multi-device context has nranks = 1: the caller holds whole arrays
   return C2G_OK;
 }
 
 int c2g_grid_upload_slab(c2g_context* ctx, const double* fslab, const int n[3], int* handle) {
   if (!ctx) return C2G_ERR_ARG;
+  if (ctx->group) return c2g_grid_upload(ctx, fslab, n, handle);  // one process: the caller holds the whole array
   int rc = c2g_grid_alloc(ctx, n, handle);
   if (rc != C2G_OK) return rc;
   c2g_grid& g = ctx->grids[*handle];
@@ -334,6 +340,7 @@ int c2g_grid_upload_slab(c2g_context* ctx, const double* fslab, const int n[3], 
 
 int c2g_grid_download(c2g_context* ctx, int handle, double* f) {
   if (!ctx) return C2G_ERR_ARG;
+  if (ctx->group) return f ? grp_grid_download(ctx, handle, f) : ctx->fail(C2G_ERR_ARG, "c2g_grid_download: null output");
   int rc = check_handle(ctx, handle, "c2g_grid_download");
   if (rc) return rc;
   if (!f) return ctx->fail(C2G_ERR_ARG, "c2g_grid_download: null output");
@@ -345,6 +352,7 @@ int c2g_grid_download(c2g_context* ctx, int handle, double* f) {
 
 int c2g_grid_download_slab(c2g_context* ctx, int handle, double* fslab) {
   if (!ctx) return C2G_ERR_ARG;
+  if (ctx->group) return c2g_grid_download(ctx, handle, fslab);
   int rc = check_handle(ctx, handle, "c2g_grid_download_slab");
   if (rc) return rc;
   c2g_grid& g = ctx->grids[handle];
@@ -360,6 +368,7 @@ int c2g_grid_download_slab(c2g_context* ctx, int handle, double* fslab) {
 
 int c2g_grid_free(c2g_context* ctx, int handle) {
   if (!ctx) return C2G_ERR_ARG;
+  if (ctx->group) return grp_grid_free(ctx, handle);
   int rc = check_handle(ctx, handle, "c2g_grid_free");
   if (rc) return rc;
   c2g_grid& g = ctx->grids[handle];
@@ -372,6 +381,7 @@ int c2g_grid_free(c2g_context* ctx, int handle) {
 int c2g_grid_promolecular(c2g_context* ctx, int handle, const double x2c[9], int nat, const double* xat,
                           const double* zat, const double* alpha, int nimg, double rc) {
   if (!ctx) return C2G_ERR_ARG;
+  if (ctx->group) return grp_grid_promolecular(ctx, handle, x2c, nat, xat, zat, alpha, nimg, rc);
   int r = check_handle(ctx, handle, "c2g_grid_promolecular");
   if (r) return r;
   if (!x2c || nat < 1 || !xat || !zat || !alpha || nimg < 0) return ctx->fail(C2G_ERR_ARG, "c2g_grid_promolecular: bad argument");
@@ -475,6 +485,7 @@ int c2g_basins_maxima(c2g_basins* res, int* pmax) {
 
 int c2g_basins_counts(c2g_basins* res, long long* counts) {
   if (!res || !counts) return C2G_ERR_ARG;
+  if (!res->parts.empty()) return grp_basins_counts(res, counts);
   c2g_context* ctx = res->ctx;
   if (res->kind != 0) return ctx->fail(C2G_ERR_STATE, "c2g_basins_counts: Bader results only");
   if (res->counts.empty() && res->nmax > 0) {  // one 4 B/pt pass, on demand
@@ -506,6 +517,7 @@ static int set_map_impl(c2g_basins* res, int nattr, const int* map, bool reclose
 int c2g_basins_set_map(c2g_basins* res, int nattr, const int* map) { return set_map_impl(res, nattr, map, true); }
 static int set_map_impl(c2g_basins* res, int nattr, const int* map, bool reclose) {
   if (!res) return C2G_ERR_ARG;
+  if (!res->parts.empty()) return map ? grp_basins_set_map(res, nattr, map, false, 0) : C2G_ERR_ARG;
   c2g_context* ctx = res->ctx;
   if (!map || nattr < 0) return ctx->fail(C2G_ERR_ARG, "c2g_basins_set_map: bad argument");
   for (int i = 0; i < res->nmax; i++)
@@ -529,6 +541,7 @@ int c2g_basins_nattr(c2g_basins* res, int* nattr) {
 
 int c2g_basins_relabel(c2g_basins* res, int nattr0, const int* assigned, int nattr_new) {
   if (!res) return C2G_ERR_ARG;
+  if (!res->parts.empty()) return assigned ? grp_basins_set_map(res, nattr_new, assigned, true, nattr0) : C2G_ERR_ARG;
   c2g_context* ctx = res->ctx;
   if (!res->has_map) return ctx->fail(C2G_ERR_STATE, "c2g_basins_relabel: no map set");
   if (nattr0 != res->nattr || !assigned) return ctx->fail(C2G_ERR_ARG, "c2g_basins_relabel: nattr0 mismatch");
@@ -542,6 +555,7 @@ int c2g_basins_relabel(c2g_basins* res, int nattr0, const int* assigned, int nat
 
 int c2g_basins_labels(c2g_basins* res, int* idg) {
   if (!res) return C2G_ERR_ARG;
+  if (!res->parts.empty()) return idg ? grp_basins_labels(res, idg) : C2G_ERR_ARG;
   c2g_context* ctx = res->ctx;
   if (!idg) return ctx->fail(C2G_ERR_ARG, "c2g_basins_labels: null output");
   if (!res->has_map) return ctx->fail(C2G_ERR_STATE, "c2g_basins_labels: call c2g_basins_set_map first");
@@ -567,6 +581,7 @@ int c2g_basins_labels(c2g_basins* res, int* idg) {
 // a real overlap; it is complete after c2g_synchronize.
 int c2g_basins_labels_async(c2g_basins* res, int* idg) {
   if (!res) return C2G_ERR_ARG;
+  if (!res->parts.empty()) return c2g_basins_labels(res, idg);
   c2g_context* ctx = res->ctx;
   if (!idg) return ctx->fail(C2G_ERR_ARG, "c2g_basins_labels_async: null output");
   if (!res->has_map) return ctx->fail(C2G_ERR_STATE, "c2g_basins_labels_async: call c2g_basins_set_map first");
@@ -601,6 +616,8 @@ int c2g_basins_weight_grid(c2g_basins* res, int idb, int* handle) {
   if (!res) return C2G_ERR_ARG;
   c2g_context* ctx = res->ctx;
   if (!handle) return ctx->fail(C2G_ERR_ARG, "c2g_basins_weight_grid: null handle");
+  if (!res->parts.empty() || ctx->parent)
+    return ctx->fail(C2G_ERR_STATE, "c2g_basins_weight_grid: not available on a multi-device context (labels are sharded; use a single-device context for WCUBE)");
   if (!res->has_map) return ctx->fail(C2G_ERR_STATE, "c2g_basins_weight_grid: call c2g_basins_set_map first");
   if (idb < 1 || idb > res->nattr) return ctx->fail(C2G_ERR_ARG, "c2g_basins_weight_grid: unknown basin %d", idb);
   if (ctx->nranks > 1 && res->kind == 0)
@@ -628,6 +645,7 @@ int c2g_basins_stats(c2g_basins* res, long long stats[8]) {
 
 void c2g_basins_free(c2g_basins* res) {
   if (!res) return;
+  if (!res->parts.empty()) { grp_basins_free(res); return; }
   if (res->d_lbuf) c2g_release(res->ctx, res->d_lbuf);
   else if (res->d_label) c2g_release(res->ctx, res->d_label);
   if (res->d_map) c2g_release(res->ctx, res->d_map);
@@ -640,11 +658,13 @@ void c2g_basins_free(c2g_basins* res) {
 // ---- profiling ----
 int c2g_profile_enable(c2g_context* ctx, int on) {
   if (!ctx) return C2G_ERR_ARG;
+  if (ctx->group) return grp_profile_enable(ctx, on);
   ctx->prof_on = on != 0;
   return C2G_OK;
 }
-int c2g_profile_count(c2g_context* ctx) { return ctx ? (int)ctx->prof.size() : 0; }
+int c2g_profile_count(c2g_context* ctx) { return ctx ? (int)(ctx->group ? c2g_group_sub(ctx, 0) : ctx)->prof.size() : 0; }
 int c2g_profile_get(c2g_context* ctx, int i, char name[64], double* ms, int* launches) {
+  if (ctx && ctx->group) return grp_profile_get(ctx, i, name, ms, launches);
   if (!ctx || i < 0 || i >= (int)ctx->prof.size()) return C2G_ERR_ARG;
   snprintf(name, 64, "%s", ctx->prof[i].name.c_str());
   if (ms) *ms = ctx->prof[i].ms;
@@ -653,15 +673,17 @@ int c2g_profile_get(c2g_context* ctx, int i, char name[64], double* ms, int* lau
 }
 int c2g_profile_reset(c2g_context* ctx) {
   if (!ctx) return C2G_ERR_ARG;
+  if (ctx->group) return grp_profile_reset(ctx);
   cudaStreamSynchronize(ctx->stream);
   ctx->prof_collect();
   ctx->prof.clear();
   return C2G_OK;
 }
-long long c2g_launch_count(c2g_context* ctx) { return ctx ? ctx->launches : 0; }
+long long c2g_launch_count(c2g_context* ctx) { return ctx ? (ctx->group ? grp_launch_count(ctx) : ctx->launches) : 0; }
 
 int c2g_flush_l2(c2g_context* ctx) {
   if (!ctx) return C2G_ERR_ARG;
+  if (ctx->group) return c2g_group_run(ctx, [](int, c2g_context* s) { return c2g_flush_l2(s); });
   if (!ctx->flushbuf) {
     ctx->flushbytes = (size_t)256 << 20;  // 256 MiB > 126 MB L2
     C2G_CUDA(ctx, cudaMalloc(&ctx->flushbuf, ctx->flushbytes));
@@ -673,12 +695,14 @@ int c2g_flush_l2(c2g_context* ctx) {
 
 int c2g_timer_start(c2g_context* ctx) {
   if (!ctx) return C2G_ERR_ARG;
+  if (ctx->group) return grp_timer_start(ctx);
   if (!ctx->t0) { C2G_CUDA(ctx, cudaEventCreate(&ctx->t0)); C2G_CUDA(ctx, cudaEventCreate(&ctx->t1)); }
   C2G_CUDA(ctx, cudaEventRecord(ctx->t0, ctx->stream));
   return C2G_OK;
 }
 
 int c2g_timer_stop(c2g_context* ctx, double* ms) {
+  if (ctx && ctx->group) return ms ? grp_timer_stop(ctx, ms) : C2G_ERR_ARG;
   if (!ctx || !ms || !ctx->t0) return C2G_ERR_ARG;
   C2G_CUDA(ctx, cudaEventRecord(ctx->t1, ctx->stream));
   C2G_CUDA(ctx, cudaEventSynchronize(ctx->t1));
@@ -690,6 +714,7 @@ int c2g_timer_stop(c2g_context* ctx, double* ms) {
 
 int c2g_synchronize(c2g_context* ctx) {
   if (!ctx) return C2G_ERR_ARG;
+  if (ctx->group) return grp_synchronize(ctx);
   C2G_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (ctx->copy_in) {
     C2G_CUDA(ctx, cudaStreamSynchronize(ctx->copy_in));

@@ -33,7 +33,10 @@ struct c2g_prof_entry {
   int launches = 0;
 };
 
+struct c2g_group;  // group.cu: the devices and worker threads of a c2g_init_devices context
 struct c2g_context {
+  c2g_group* group = nullptr;  // non-null: this context drives several devices of one process (group.cu)
+  c2g_context* parent = nullptr;  // non-null: this is the per-device context of a multi-device context
   int device = 0;
   int nsm = C2G_NSM_FALLBACK;
   cudaStream_t stream = nullptr;
@@ -133,6 +136,7 @@ struct c2g_context {
 
 // result of an assignment (BADER or YT), device resident
 struct c2g_basins {
+  std::vector<c2g_basins*> parts;  // multi-device context: the z-slab result of every device (group.cu)
   c2g_context* ctx = nullptr;
   int kind = 0;  // 0 = bader, 1 = yt, 2 = isosurface regions (plain labels like bader, -1 = below the contour value)
   int gridh = -1;

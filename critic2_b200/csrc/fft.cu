@@ -14,6 +14,7 @@
 // up to rounding.  |grad f| (iff = 42) shares one forward transform between its three components.
 // cuFFT is resolved with dlopen (like NCCL) so the library loads on machines without it.
 #include "common.cuh"
+#include "group.h"
 
 #include <cufft.h>
 #include <dlfcn.h>
@@ -151,6 +152,7 @@ __global__ void __launch_bounds__(256) k_fft_finish(long long nn, const double* 
 
 extern "C" int c2g_fft_derivative(c2g_context* ctx, int handle, int iff, const double x2c[9], int* hout) {
   if (!ctx) return C2G_ERR_ARG;
+  if (ctx->group) return grp_fft_derivative(ctx, handle, iff, x2c, hout);
   if (!x2c || !hout) return ctx->fail(C2G_ERR_ARG, "c2g_fft_derivative: null argument");
   if (handle < 0 || handle >= (int)ctx->grids.size() || !ctx->grids[handle].used)
     return ctx->fail(C2G_ERR_ARG, "c2g_fft_derivative: invalid grid handle %d", handle);

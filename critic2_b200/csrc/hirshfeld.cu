@@ -12,6 +12,7 @@
 // shared-memory table (warp shuffles first) and one set of global fp64 atomics per block at the end.
 // Values agree with the reference to rounding (different order of the additions), not bit for bit: tolerance 1e-10.
 #include "common.cuh"
+#include "group.h"
 
 #include <algorithm>
 #include <cmath>
@@ -318,6 +319,7 @@ extern "C" int c2g_promolecular_grid(c2g_context* ctx, const int n[3], const dou
                                      const double* spc_b, const double* spc_rmax, const double* spc_rcut, const double* rtab,
                                      const double* ftab, const unsigned char* infrag, int* handle) {
   if (!ctx) return C2G_ERR_ARG;
+  C2G_NOT_ON_GROUP(ctx, "c2g_promolecular_grid");
   if (!handle) return ctx->fail(C2G_ERR_ARG, "c2g_promolecular_grid: null handle");
   HSetup S;
   int rc = h_setup(ctx, "c2g_promolecular_grid", n, x2c, nat, xat, ispc, nspc, spc_ngrid, spc_off, spc_a, spc_b, spc_rmax, spc_rcut, rtab,
@@ -347,6 +349,7 @@ extern "C" int c2g_hirshfeld_integrate(c2g_context* ctx, int hpromol, const doub
                                        const double* ftab, const unsigned char* domask, int nprop, const int* fieldhandles,
                                        double omega, double* psum, double* vol) {
   if (!ctx) return C2G_ERR_ARG;
+  C2G_NOT_ON_GROUP(ctx, "c2g_hirshfeld_integrate");
   if (hpromol < 0 || hpromol >= (int)ctx->grids.size() || !ctx->grids[hpromol].used)
     return ctx->fail(C2G_ERR_ARG, "c2g_hirshfeld_integrate: invalid promolecular grid handle %d", hpromol);
   if (nprop < 0 || (nprop > 0 && (!fieldhandles || !psum))) return ctx->fail(C2G_ERR_ARG, "c2g_hirshfeld_integrate: bad argument");

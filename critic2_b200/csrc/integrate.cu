@@ -12,6 +12,7 @@
 // the lanes' partial sums reduced with shuffles and added to the per-maximum accumulators.
 // HBM traffic: 4 B (label) + 8 B per field per point.
 #include "common.cuh"
+#include "group.h"
 
 namespace {
 
@@ -210,6 +211,8 @@ int c2g_yt_integrate_impl(c2g_context* ctx, c2g_basins* res, int nprop, const in
 extern "C" int c2g_integrate(c2g_context* ctx, c2g_basins* res, int nprop, const int* fieldhandles, double omega,
                              double* psum, double* vol) {
   if (!ctx) return C2G_ERR_ARG;
+  if (ctx->group && res && !res->parts.empty()) return grp_integrate(ctx, res, nprop, fieldhandles, omega, psum, vol);
+  if (ctx->group && res) { ctx = res->ctx; cudaSetDevice(ctx->device); }  // a YT result lives on the first device
   if (!res || nprop < 0 || (nprop > 0 && (!fieldhandles || !psum))) return ctx->fail(C2G_ERR_ARG, "c2g_integrate: bad argument");
   if (!res->has_map) return ctx->fail(C2G_ERR_STATE, "c2g_integrate: call c2g_basins_set_map first");
   for (int k = 0; k < nprop; k++) {

@@ -17,6 +17,7 @@
 // tosphere are replaced by their sines and cosines taken directly from the vector (see add_point), so parity is a
 // tolerance (1e-10 of the sum of |terms|; measured ~1e-15), not bits.
 #include "common.cuh"
+#include "group.h"
 
 #include <algorithm>
 
@@ -237,6 +238,9 @@ extern "C" int c2g_integrate_multipoles(c2g_context* ctx, c2g_basins* res, int f
                                         const double x2xr[9], const double xr2c[9], int nws, const double* ws_ineighc,
                                         double omega, double* mpole) {
   if (!ctx) return C2G_ERR_ARG;
+  if (ctx->group && res && !res->parts.empty())
+    return grp_integrate_multipoles(ctx, res, fieldhandle, lmax, xattr, domask, isortho, isortho_del, x2c, x2xr, xr2c, nws, ws_ineighc, omega, mpole);
+  if (ctx->group && res) { ctx = res->ctx; cudaSetDevice(ctx->device); }
   if (!res || !xattr || !mpole || !x2c) return ctx->fail(C2G_ERR_ARG, "c2g_integrate_multipoles: bad argument");
   if (lmax < 0 || lmax > MP_LCAP_MAX)
     return ctx->fail(C2G_ERR_ARG, "c2g_integrate_multipoles: lmax = %d out of range (0..%d)", lmax, MP_LCAP_MAX);
@@ -392,6 +396,9 @@ extern "C" int c2g_basins_remap(c2g_context* ctx, c2g_basins* res, const double*
                                 int isortho_del, const double x2c[9], const double x2xr[9], const double xr2c[9], int nws,
                                 const double* ws_ineighc, int maxattn, int* nattn_out, int* iatt, int* ilvec, int* idg1) {
   if (!ctx) return C2G_ERR_ARG;
+  if (ctx->group && res && !res->parts.empty())
+    return grp_basins_remap(ctx, res, xattr, c2x, isortho, isortho_del, x2c, x2xr, xr2c, nws, ws_ineighc, maxattn, nattn_out, iatt, ilvec, idg1);
+  if (ctx->group && res) { ctx = res->ctx; cudaSetDevice(ctx->device); }
   if (!res || !xattr || !c2x || !x2c || !nattn_out || !iatt || !ilvec) return ctx->fail(C2G_ERR_ARG, "c2g_basins_remap: bad argument");
   if (!isortho && (!x2xr || !xr2c || nws < 0 || (nws > 0 && !ws_ineighc)))
     return ctx->fail(C2G_ERR_ARG, "c2g_basins_remap: a non-orthogonal cell needs x2xr, xr2c and the WS neighbours");

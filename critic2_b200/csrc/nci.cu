@@ -22,6 +22,7 @@
 // fastest index of rho) for the stencil loads, results are staged in shared memory and written with k
 // fastest, which is the reference's cgrad(k,j,i) layout.  HBM traffic: 8 B read + 16 B written per point.
 #include "common.cuh"
+#include "group.h"
 
 #include <cmath>
 
@@ -497,6 +498,7 @@ extern "C" int c2g_nci_rdg(c2g_context* ctx, int handle, const double x0[3], con
                            const double c2x[9], const double x2c[9], const double c2xl[9], int nnuc,
                            const double* nuc_cart, double* crho, double* cgrad) {
   if (!ctx) return C2G_ERR_ARG;
+  if (ctx->group) return grp_nci_rdg(ctx, handle, x0, xmat, nstep, c2x, x2c, c2xl, nnuc, nuc_cart, crho, cgrad);
   int rc = nci_check(ctx, handle, x0, xmat, nstep, c2x, x2c, c2xl, nnuc, nuc_cart);
   if (rc) return rc;
   if (!crho || !cgrad) return ctx->fail(C2G_ERR_ARG, "c2g_nci_rdg: null output");
@@ -524,6 +526,7 @@ extern "C" int c2g_nci_rdg_resident(c2g_context* ctx, int handle, const double x
                                     const int nstep[3], const double c2x[9], const double x2c[9], const double c2xl[9],
                                     int nnuc, const double* nuc_cart, int* hrho, int* hgrad) {
   if (!ctx) return C2G_ERR_ARG;
+  C2G_NOT_ON_GROUP(ctx, "c2g_nci_rdg_resident");
   int rc = nci_check(ctx, handle, x0, xmat, nstep, c2x, x2c, c2xl, nnuc, nuc_cart);
   if (rc) return rc;
   if (!hrho || !hgrad) return ctx->fail(C2G_ERR_ARG, "c2g_nci_rdg_resident: null output");
@@ -541,6 +544,7 @@ extern "C" int c2g_nci_rdg_fourier(c2g_context* ctx, const int h[5], const doubl
                                    const int nstep[3], const double c2x[9], const double c2xl[9], double* crho,
                                    double* cgrad) {
   if (!ctx) return C2G_ERR_ARG;
+  if (ctx->group) return grp_nci_rdg_fourier(ctx, h, x0, xmat, nstep, c2x, c2xl, crho, cgrad);
   if (!h || !crho || !cgrad) return ctx->fail(C2G_ERR_ARG, "c2g_nci_rdg_fourier: null argument");
   int rc = nci_check(ctx, h[0], x0, xmat, nstep, c2x, c2x, c2xl, 0, nullptr);
   if (rc) return rc;
@@ -588,6 +592,7 @@ extern "C" int c2g_nci_rdg_fourier(c2g_context* ctx, const int h[5], const doubl
 // cgrad(:,:,ilo+1:ihi), which is one contiguous piece of the reference array.  Single GPU: the whole range.
 extern "C" int c2g_nci_range(c2g_context* ctx, int nstep1, int* ilo, int* ihi) {
   if (!ctx) return C2G_ERR_ARG;
+  if (ctx->group) { if (!ilo || !ihi) return C2G_ERR_ARG; *ilo = 0; *ihi = nstep1; return C2G_OK; }  // the caller holds whole arrays
   if (!ilo || !ihi || nstep1 < 1) return ctx->fail(C2G_ERR_ARG, "c2g_nci_range: bad argument");
   nci_range(ctx, nstep1, ilo, ihi);
   return C2G_OK;

@@ -20,6 +20,7 @@
 // Separators: blank, tab, newline, carriage return, comma.  Exponent letters E, D, Q (either case) or a bare sign
 // ("1.5-03").  The r*c repeat form of list-directed input is not supported (neither format writes it).
 #include "common.cuh"
+#include "group.h"
 
 #include <cstdlib>
 #include <string>
@@ -548,6 +549,7 @@ __global__ void __launch_bounds__(256) k_format(const __grid_constant__ FormatAr
 extern "C" int c2g_grid_parse_text(c2g_context* ctx, const char* text, size_t nbytes, const int n[3], int order, double divisor,
                                    int* handle, size_t* consumed, long long* nslow) {
   if (!ctx) return C2G_ERR_ARG;
+  C2G_NOT_ON_GROUP(ctx, "c2g_grid_parse_text");
   if (!text || !n || !handle) return ctx->fail(C2G_ERR_ARG, "c2g_grid_parse_text: null argument");
   if (order != C2G_TEXT_ORDER_I_FASTEST && order != C2G_TEXT_ORDER_K_FASTEST) return ctx->fail(C2G_ERR_ARG, "c2g_grid_parse_text: bad order %d", order);
   if (divisor == 0.0) return ctx->fail(C2G_ERR_ARG, "c2g_grid_parse_text: zero divisor");
@@ -604,6 +606,7 @@ extern "C" int c2g_grid_parse_text(c2g_context* ctx, const char* text, size_t nb
 extern "C" int c2g_grid_format_text(c2g_context* ctx, int handle, int layout, const int ishift[3], int width, int digits, int scale,
                                     char* out, size_t cap, size_t* nbytes) {
   if (!ctx) return C2G_ERR_ARG;
+  C2G_NOT_ON_GROUP(ctx, "c2g_grid_format_text");
   if (!nbytes) return ctx->fail(C2G_ERR_ARG, "c2g_grid_format_text: null argument");
   if (handle < 0 || handle >= (int)ctx->grids.size() || !ctx->grids[handle].used)
     return ctx->fail(C2G_ERR_ARG, "c2g_grid_format_text: invalid grid handle %d", handle);

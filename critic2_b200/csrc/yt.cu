@@ -24,6 +24,7 @@
 // Flux fractions fnear = chi/max(csum,vsmall) are recomputed from rho (a stencil) instead of being
 // stored as the reference's dense inear/fnear(nvec,nn) arrays.
 #include "common.cuh"
+#include "group.h"
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -595,6 +596,7 @@ int c2g_yt_apply_map(c2g_basins* res) {
 extern "C" int c2g_yt_build(c2g_context* ctx, int handle, int nvec, const int* vec, const double* area, int* nmax_out,
                             c2g_basins** res_out) {
   if (!ctx) return C2G_ERR_ARG;
+  C2G_FIRST_DEVICE(ctx);  // YT does not shard (replicas only)
   if (!vec || !area || !nmax_out || !res_out) return ctx->fail(C2G_ERR_ARG, "c2g_yt_build: null argument");
   if (handle < 0 || handle >= (int)ctx->grids.size() || !ctx->grids[handle].used)
     return ctx->fail(C2G_ERR_ARG, "c2g_yt_build: invalid grid handle %d", handle);

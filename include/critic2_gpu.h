@@ -48,7 +48,16 @@ typedef struct c2g_basins c2g_basins;   /* result of a BADER or YT assignment (d
 /* ---- context ---- */
 /* Create a context on CUDA device `device` (single-GPU use). */
 int c2g_init(int device, c2g_context** ctx);
-/* Multi-GPU: one process per GPU.  `nccl_uid` is the 128-byte ncclUniqueId created by
+/* Multi-GPU from ONE process -- the form critic2 needs (src/critic2.F90:24-106 is a single program; SURVEY.md 8b
+ * `c2g_init(ngpus)`): the context drives devices 0..ngpus-1 of the box with one worker thread per device and its own
+ * NCCL communicator.  Every entry point below takes WHOLE host arrays exactly as on one GPU: c2g_grid_upload scatters
+ * the z-slabs of the array (each device copies its slab, NVLink replicates them), c2g_bader_assign / c2g_integrate /
+ * c2g_integrate_multipoles / c2g_basins_remap run sharded over NCCL, c2g_basins_labels assembles idg(n1,n2,n3),
+ * c2g_nci_rdg* shard the output rows.  c2g_fft_derivative runs replicated, c2g_yt_* on the first device ("replicas
+ * only").  The text codec, HIRSHFELD, WCUBE weight grids and c2g_nci_rdg_resident return C2G_ERR_STATE
+ * on such a context.  ngpus = 1 is c2g_init(0). */
+int c2g_init_devices(int ngpus, c2g_context** ctx);
+/* Multi-GPU, one process per GPU.  `nccl_uid` is the 128-byte ncclUniqueId created by
  * c2g_nccl_unique_id() on rank 0 and distributed by the caller (MPI/torch.distributed/file). */
 int c2g_nccl_unique_id(void* uid128);
 int c2g_init_multi(int device, int rank, int nranks, const void* nccl_uid128, c2g_context** ctx);

@@ -58,10 +58,12 @@ def molecule_in_vacuum(N=256):
 
 
 def flat_cell(N=160):
-    """Non-cubic grid and cell: 2N x N x N/2+4 points, orthorhombic 20 x 10 x 5.5 bohr, 12 atoms."""
-    n = (2 * N, N, N // 2 + 4)
-    x2c = S.cell_x2c(20.0, 10.0, 5.5)
-    at, z, al = S.random_atoms(12, 21, x2c, dmin=2.2)
+    """Non-cubic grid and cell: 2N x N x 0.8N+4 points, orthorhombic 20 x 10 x 8.2 bohr, 16 atoms.  (A 5.5 bohr thin
+    variant of this cell is degenerate like tests/cases.py DEGENERATE_CASES: atoms interact with their own images and
+    the sequential reference keeps scan-order dependent labels there -- 54 of 4.3e6 points in round 2's run.)"""
+    n = (2 * N, N, (4 * N) // 5 + 4)
+    x2c = S.cell_x2c(20.0, 10.0, 8.2)
+    at, z, al = S.random_atoms(16, 21, x2c, dmin=2.2)
     return dict(n=n, x2c=x2c, atoms=S.snap_to_grid(at, n), z=z, alpha=al, nimg=1, rc=0.0)
 
 

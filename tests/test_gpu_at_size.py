@@ -60,7 +60,7 @@ def test_labels_vs_oracle_256_class(ctx, golden, name):
     h = generate(ctx, c)
     f = ctx.download(h, c["n"])
     idg, nattr, _, _ = orc.bader_integrate(f, c["x2c"], atoms=c["atoms"])
-    if name in golden:  # the oracle and the generator have not drifted since the fixture was made
+    if name in golden and name != "_about":  # the oracle and the generator have not drifted since the fixture was made
         assert sha(f) == golden[name]["rho_sha256"]
         assert sha(idg) == golden[name]["labels_sha256"]
     for algo in (capi.BADER_FAST, capi.BADER_EXACT):
