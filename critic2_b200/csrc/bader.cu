@@ -154,13 +154,28 @@ __device__ __noinline__ bool dev_on_path(const int* path, int len, int nid) {
 //              labelled safe[c] and hold no maximum (every point of c has a uniform 5x5x5 neighbourhood);
 //   octet = 1: safe[v] >= 0 means the 8 cubes that meet at cube-grid vertex v are uniformly labelled and hold
 //              no maximum; a point q is looked up at its nearest vertex v = (q + 2^(shift-1)) >> shift, whose
-//              8 cubes contain the whole 3x3x3 neighbourhood of q.
+//              8 cubes contain the whole 3x3x3 neighbourhood of q;
+//   pack  = 1: (octet map of the stride-2 cubes only) an entry carries, above its 23-bit label, one flag for each of
+//              the 8 points {2v-1, 2v}^3 whose nearest vertex is v: the octets of ALL the vertices that cover the
+//              point's 5x5x5 neighbourhood hold with the same label (k_pack5).  A walk stops at such a point only
+//              when its flag is set: the margin at which the reference's refine_edge walks stop (known == 2 is
+//              cleared in the 26-neighbourhood of every edge point, bader@proc.f90:756-771, :367-388, so a walk only
+//              ends on a point whose 26 neighbours are not edge points either).  Octets of wider cubes cover the
+//              5x5x5 neighbourhood of their points by themselves.
 // Covers the owned cube layers only.
 struct SafeMap {
   int* safe;  // nullptr = disabled; entries are set to -1 when a label inside the certified region changes
   int shift, c1, c2, c3, zlo, nzl, octet, wrapz;
   int hf;  // octet: half a cube, (1 << shift) >> 1
+  int pack;
 };
+constexpr int CERT_LBITS = 23;                       // label bits of a packed entry
+constexpr int CERT_LMASK = (1 << CERT_LBITS) - 1;
+// label certified for the point (x, y, cz) by entry e of a packed map, or -1
+__device__ __forceinline__ int cert_unpack(int e, int x, int y, int cz) {
+  const int pidx = ((x & 1) ^ 1) | (((y & 1) ^ 1) << 1) | (((cz & 1) ^ 1) << 2);
+  return (e >= 0 && ((e >> (CERT_LBITS + pidx)) & 1)) ? (e & CERT_LMASK) : -1;
+}
 constexpr int STOP_SHIFT = 28;             // stop code = (level index << 28) | map index
 constexpr int STOP_MASK = (1 << STOP_SHIFT) - 1;
 
@@ -297,7 +312,8 @@ __device__ __forceinline__ int safe_lookup(const SafeMap& sm, int nx, int ny, in
     if (vz == sm.c3) { ok = ok && sm.wrapz; vz = 0; }
     if (!ok) return -1;
     mapidx = vx + sm.c1 * (vy + sm.c2 * vz);
-    return sm.safe[mapidx];  // plain load: entries may be invalidated while walkers run
+    const int e = sm.safe[mapidx];  // plain load: entries may be invalidated while walkers run
+    return sm.pack ? cert_unpack(e, nx, ny, cz) : e;
   }
   if (cz < 0 || cz >= sm.nzl) return -1;
   mapidx = (nx >> sm.shift) + sm.c1 * ((ny >> sm.shift) + sm.c2 * (cz >> sm.shift));
@@ -320,7 +336,8 @@ __device__ __forceinline__ int safe_lookup2(const SafeMap& sm, int x, int y, int
     vx = x >> sm.shift; vy = y >> sm.shift; vz = cz >> sm.shift;
   }
   mapidx = vx + sm.c1 * (vy + sm.c2 * vz);
-  return ok ? sm.safe[mapidx] : -1;  // plain load: entries may be invalidated while walkers run
+  const int e = ok ? sm.safe[mapidx] : -1;  // plain load: entries may be invalidated while walkers run
+  return sm.pack ? cert_unpack(e, x, y, cz) : e;
 }
 // w: current point with w.r0, nb = its neighbours, sl = early-termination label of its cube (all loaded by
 // the previous call or by the caller for the start point, where sl must be -1)
@@ -667,15 +684,18 @@ __device__ __noinline__ void claim_neighbours(const BaderParams& P, const WalkAr
     if (!sm.safe) continue;
     const int cz = z - sm.zlo;
     if (cz < 0 || cz >= sm.nzl) continue;
-    const int cx = x >> sm.shift, cy = y >> sm.shift, cl = cz >> sm.shift;
-    const int lo = sm.octet ? 0 : -1;  // octet: vertices c, c+1; cube certificate: cubes c-1, c, c+1
-    for (int dz = lo; dz <= 1; dz++) {
+    // entries whose certified region contains the point.  Octet: vertices c, c+1 (3x3x3 of the points they serve;
+    // for cubes of stride >= 4 that is their 5x5x5 as well); packed octets of the stride-2 cubes: every vertex that
+    // serves a point within 2 cells, (p-1)>>1 .. (p+3)>>1; cube certificate: cubes c-1, c, c+1
+    int cx = x >> sm.shift, cy = y >> sm.shift, cl = cz >> sm.shift, lo = sm.octet ? 0 : -1, hi = 1;
+    if (sm.pack) { cx = (x - 1) >> 1; cy = (y - 1) >> 1; cl = (cz - 1) >> 1; lo = 0; hi = 2; }
+    for (int dz = lo; dz <= hi; dz++) {
       int vz = cl + dz;
-      if (vz == sm.c3) { if (sm.octet && sm.wrapz) vz = 0; else continue; }
-      if (vz < 0) continue;
-      for (int dy = lo; dy <= 1; dy++) {
+      if (vz >= sm.c3) { if (sm.octet && sm.wrapz) vz -= sm.c3; else continue; }
+      if (vz < 0) { if (sm.octet && sm.wrapz) vz += sm.c3; else continue; }
+      for (int dy = lo; dy <= hi; dy++) {
         const int vy = wrapx(cy + dy, sm.c2);
-        for (int dx = lo; dx <= 1; dx++) {
+        for (int dx = lo; dx <= hi; dx++) {
           const int vx = wrapx(cx + dx, sm.c1);
           int* e = sm.safe + vx + sm.c1 * (vy + (size_t)sm.c2 * vz);
           if (*e >= 0 && atomicExch(e, -1) >= 0) atomicAdd(A.ninval, 1);
@@ -1003,6 +1023,192 @@ __global__ void __launch_bounds__(256, 4) k_walk2(const __grid_constant__ BaderP
   if (STATS && A.nsteps && steps) atomicAdd(A.nsteps, steps);
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_walk3: block-cooperative walkers with stable compaction.  Same trajectories, same decisions, same results as
+// k_walk; what differs is how lanes are kept busy.  k_walk refills a warp only when 20 (24) of its lanes are idle,
+// because refilling single lanes mixes walkers of different age in one warp and their loads stop coalescing: 19 of
+// 32 lanes were active on the last level.  Here the 256 threads of a block take `steps_per_check` steps, then --
+// once `refill_min` threads are idle -- the surviving walkers are packed, IN THEIR ORDER, into the first threads of
+// the block through shared memory, and the free threads at the end take the next consecutive entries of the dense,
+// spatially ordered walker list.  A warp therefore always holds walkers that started next to each other at about the
+// same time (a cohort, or the packed survivors of neighbouring cohorts), and whole warps -- not scattered lanes --
+// run dry at the end of a launch.  The step is the lean one of k_walk2 (all loads of a step issued together at its
+// top, no state besides point, dr and the largest density on the path).
+// ------------------------------------------------------------------------------------------------
+template <bool ORTHO, bool FIX, bool STATS>
+__global__ void __launch_bounds__(256, 4) k_walk3(const __grid_constant__ BaderParams P, const __grid_constant__ WalkArgs A) {
+  __shared__ int s_wc[8];
+  __shared__ int s_chunk[2];                       // first entry and number of entries handed to the block
+  __shared__ int s_id[256], s_start[256], s_tidx[256], s_old[256];
+  __shared__ double s_dr[3][256], s_rm[256];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int n1 = P.n1, n2 = P.n2, n3 = P.n3;
+  const int s2 = n1, s3 = n1 * n2;
+  const int total = (int)A.count;                  // < 2^31: the lists hold at most nn entries
+  const int* const list = A.list ? A.list + A.flat_base : nullptr;
+  const int tbase = (int)A.flat_base;
+  unsigned* const cur32 = reinterpret_cast<unsigned*>(A.cursor);  // low word of the (zeroed) 64-bit cursor
+  bool active = false, first = true, exhausted = false;           // exhausted: block-uniform
+  int id = 0, x = 0, y = 0, z = 0, start = 0, tidx = -1, oldlab = 0;
+  double dr0 = 0.0, dr1 = 0.0, dr2 = 0.0, rhomax = 0.0;
+  unsigned long long steps = 0;
+  for (;;) {
+    // ---- pack the survivors, refill the free threads ----
+    const int nact = __syncthreads_count(active);
+    if (nact == 0 && exhausted) break;
+    if (256 - nact >= A.refill_min || nact == 0) {
+      const unsigned m = __ballot_sync(FULL, active);
+      if (lane == 0) s_wc[wid] = __popc(m);
+      if (tid == 0) {
+        int base = 0, n = 0;
+        if (!exhausted) {
+          const int need = 256 - nact;
+          const unsigned b = atomicAdd(cur32, (unsigned)need);
+          base = (int)min(b, (unsigned)total);
+          n = min(need, total - base);
+        }
+        s_chunk[0] = base; s_chunk[1] = n;
+      }
+      __syncthreads();
+      if (active) {
+        int slot = __popc(m & ((1u << lane) - 1u));
+        for (int w = 0; w < wid; w++) slot += s_wc[w];
+        s_id[slot] = id; s_start[slot] = start; s_tidx[slot] = tidx;
+        if (FIX) s_old[slot] = oldlab;
+        s_dr[0][slot] = dr0; s_dr[1][slot] = dr1; s_dr[2][slot] = dr2; s_rm[slot] = rhomax;
+      }
+      __syncthreads();
+      const int cbase = s_chunk[0], cn = s_chunk[1];
+      if (cn < 256 - nact) exhausted = true;
+      active = false;
+      int s = -1;
+      if (tid < nact) {
+        s = s_id[tid]; start = s_start[tid]; tidx = s_tidx[tid];
+        if (FIX) oldlab = s_old[tid];
+        dr0 = s_dr[0][tid]; dr1 = s_dr[1][tid]; dr2 = s_dr[2][tid]; rhomax = s_rm[tid];
+        first = false;
+        active = true;
+      } else if (tid - nact < cn) {
+        const int t = cbase + tid - nact;
+        s = list ? __ldg(list + t) : walk_item_lattice(P.n1, P.n2, A.S.zlo, A.lat_s, A.lat_m1, A.lat_m2, t);
+        start = s; tidx = tbase + t;
+        dr0 = dr1 = dr2 = 0.0;
+        rhomax = __longlong_as_double((long long)0xfff0000000000000ull);  // -inf: the start point is never a revisit
+        first = true;
+        if (FIX) oldlab = A.label_g[s] & LMASK;
+        active = true;
+      }
+      if (active) {
+        id = s;
+        z = fastdiv(s, P.mg12, P.sh12);
+        const int rem = s - z * s3;
+        y = fastdiv(rem, P.mg1, P.sh1);
+        x = rem - y * n1;
+      }
+      // the shared arrays are written again only after the next __syncthreads_count
+    }
+    // ---- a few steps ----
+    int pend_st = 0, pend_out = 0, pend_sli = -1;
+#pragma unroll 1
+    for (int k = 0; k < A.steps_per_check; k++) {
+      if (!active) break;
+      if (STATS) steps++;
+      const double* c = A.rho + id;
+      // the point and its next point stay clear of the periodic seams: no wrapping anywhere in this step
+      const bool inner = (unsigned)(x - 3) < (unsigned)P.in1 && (unsigned)(y - 3) < (unsigned)P.in2 &&
+                         (unsigned)(z - 3) < (unsigned)P.in3;
+      double r0, xp, xm, yp, ym, zp, zm;
+      r0 = __ldg(c);
+      if (inner) {
+        xp = __ldg(c + 1); xm = __ldg(c - 1);
+        yp = __ldg(c + s2); ym = __ldg(c - s2);
+        zp = __ldg(c + s3); zm = __ldg(c - s3);
+      } else {
+        xp = __ldg(c + ((x + 1 == n1) ? 1 - n1 : 1));
+        xm = __ldg(c + ((x == 0) ? n1 - 1 : -1));
+        yp = __ldg(c + ((y + 1 == n2) ? s2 - s3 : s2));
+        ym = __ldg(c + ((y == 0) ? s3 - s2 : -s2));
+        zp = __ldg(c + ((z + 1 == n3) ? s3 - s3 * n3 : s3));
+        zm = __ldg(c + ((z == 0) ? s3 * n3 - s3 : -s3));
+      }
+      int sli = -1, sl = -1;
+      if (!first && A.sm.safe) sl = safe_lookup2(A.sm, x, y, z, sli);  // the start point is never looked up
+      int st = 0, out = 0;
+      if (r0 <= rhomax) {
+        st = 3;  // possibly a point of this path (known(pm) == 1, :487): k_walk_big answers exactly
+      } else if (sl >= 0) {
+        st = 2; out = sl;  // quit at a known interior point (:447)
+      } else {
+        // rho_grad_dir (:532-567)
+        const double gl0 = zero_if_both_less((xp - xm) * 0.5, xp, xm, r0);
+        const double gl1 = zero_if_both_less((yp - ym) * 0.5, yp, ym, r0);
+        const double gl2 = zero_if_both_less((zp - zm) * 0.5, zp, zm, r0);
+        double g0, g1, g2;
+        if (ORTHO) {
+          g0 = P.c2l[0] * (gl0 * P.c2l[0]);
+          g1 = P.c2l[4] * (gl1 * P.c2l[4]);
+          g2 = P.c2l[8] * (gl2 * P.c2l[8]);
+        } else {
+          const double gc0 = gl0 * P.c2l[0] + gl1 * P.c2l[1] + gl2 * P.c2l[2];
+          const double gc1 = gl0 * P.c2l[3] + gl1 * P.c2l[4] + gl2 * P.c2l[5];
+          const double gc2 = gl0 * P.c2l[6] + gl1 * P.c2l[7] + gl2 * P.c2l[8];
+          g0 = P.c2l[0] * gc0 + P.c2l[3] * gc1 + P.c2l[6] * gc2;
+          g1 = P.c2l[1] * gc0 + P.c2l[4] * gc1 + P.c2l[7] * gc2;
+          g2 = P.c2l[2] * gc0 + P.c2l[5] * gc1 + P.c2l[8] * gc2;
+        }
+        double gmax = fabs(g0);
+        {
+          const double t1 = fabs(g1), t2 = fabs(g2);
+          gmax = t1 > gmax ? t1 : gmax;
+          gmax = t2 > gmax ? t2 : gmax;
+        }
+        const int oid = id;
+        if (gmax < 1e-30) {  // (:468-476)
+          dr0 = dr1 = dr2 = 0.0;
+          if (hash_lookup(A.h, id) >= 0) {
+            st = 1; out = id;
+          } else {
+            id = dev_step_ongrid(P, A.rho, x, y, z, r0);
+            z = fastdiv(id, P.mg12, P.sh12);
+            const int rem = id - z * s3;
+            y = fastdiv(rem, P.mg1, P.sh1);
+            x = rem - y * n1;
+            if (id == oid) st = 3;
+          }
+        } else {  // (:477-483)
+          const double coeff = 1.0 / gmax;
+          g0 = coeff * g0; g1 = coeff * g1; g2 = coeff * g2;
+          int d0, d1, d2, e0, e1, e2;
+          const double a0 = nint_bits(g0, d0), a1 = nint_bits(g1, d1), a2 = nint_bits(g2, d2);
+          const double t0 = dr0 + g0 - a0, t1 = dr1 + g1 - a1, t2 = dr2 + g2 - a2;
+          const double b0 = nint_bits(t0, e0), b1 = nint_bits(t1, e1), b2 = nint_bits(t2, e2);
+          dr0 = t0 - b0; dr1 = t1 - b1; dr2 = t2 - b2;
+          d0 += e0; d1 += e1; d2 += e2;
+          if (inner) {
+            x += d0; y += d1; z += d2;
+            id += d0 + n1 * (d1 + n2 * d2);
+          } else {
+            x = wrap2(x + d0, n1);
+            y = wrap2(y + d1, n2);
+            z = wrap2(z + d2, n3);
+            id = x + n1 * (y + n2 * z);
+          }
+          // did not move although the gradient is not zero: k_walk_big (k_walk hands these over as well)
+          if (id == oid) st = 3;
+        }
+        rhomax = r0 > rhomax ? r0 : rhomax;  // known(p) = 1 (:484)
+        first = false;
+      }
+      if (st) {
+        pend_st = st; pend_out = out; pend_sli = sli;
+        active = false;
+      }
+    }
+    if (pend_st) walk_finish<FIX>(P, A, start, pend_st, pend_out, list ? tidx : -1, pend_sli, oldlab);
+  }
+  if (STATS && A.nsteps && steps) atomicAdd(A.nsteps, steps);
+}
+
 // cut the non-empty segments of a segmented list into work items of at most `batch` entries, IN SEGMENT
 // ORDER (segments are numbered super-block by super-block, and that order is what keeps the walkers that are
 // in flight together inside one L2-sized region).  Three small launches: items per 256-segment block,
@@ -1301,6 +1507,50 @@ __global__ void __launch_bounds__(256) k_vsafe(int c1, int c2, int c3, int px, i
   }
 }
 
+// packed certificates of the stride-2 level (SafeMap::pack): out[v] = E[v] | flags << CERT_LBITS, where E is the octet
+// map of k_vsafe and flag (ix | iy << 1 | iz << 2) belongs to the point (2vx-1+ix, 2vy-1+iy, 2vz-1+iz).  The 5x5x5
+// neighbourhood of an even coordinate 2v lies inside the octet of v; that of an odd coordinate 2v-1 needs the octets of
+// v-1 and v.  x, y, z wrap like in k_vsafe (px, py, pz); the vertices below the first owned layer of a z-slab do not exist.
+__global__ void __launch_bounds__(256) k_pack5(int c1, int c2, int c3, int px, int py, int pz, const int* __restrict__ E,
+                                               int* __restrict__ out) {
+  const int vx = blockIdx.x * 32 + (threadIdx.x & 31), vy = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (vx >= c1 || vy >= c2) return;
+  const int z0 = blockIdx.z * MZC, z1 = min(z0 + MZC, c3);
+  const size_t s3 = (size_t)c1 * c2;
+  const int xm = vx ? vx - 1 : (px ? c1 - 1 : -1), ym = vy ? vy - 1 : (py ? c2 - 1 : -1);
+  // the four columns (vx, vy), (vx-1, vy), (vx, vy-1), (vx-1, vy-1); a column that does not exist reads as -2
+  const int* col[4] = {E + vx + (size_t)c1 * vy, xm >= 0 ? E + xm + (size_t)c1 * vy : nullptr,
+                       ym >= 0 ? E + vx + (size_t)c1 * ym : nullptr, (xm >= 0 && ym >= 0) ? E + xm + (size_t)c1 * ym : nullptr};
+  int lo[4], cu[4];  // layers vz-1 and vz, marching upwards
+  const int zb = z0 > 0 ? z0 - 1 : (pz ? c3 - 1 : -1);
+#pragma unroll
+  for (int k = 0; k < 4; k++) lo[k] = (col[k] && zb >= 0) ? __ldg(col[k] + s3 * zb) : -2;
+  for (int vz = z0; vz < z1; vz++) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) cu[k] = col[k] ? __ldg(col[k] + s3 * vz) : -2;
+    const int e0 = cu[0];
+    int res = -1;
+    if (e0 >= 0) {
+      // ok[m]: the vertex shifted down along the axes in m (1 = x, 2 = y, 4 = z) carries e0 as well
+      const bool o1 = cu[1] == e0, o2 = cu[2] == e0, o3 = cu[3] == e0;
+      const bool o4 = lo[0] == e0, o5 = lo[1] == e0, o6 = lo[2] == e0, o7 = lo[3] == e0;
+      // flag index: bit set = even coordinate 2v, clear = odd coordinate 2v-1 (needs the lower vertex along that axis)
+      int flags = 1 << 7;                                   // (even, even, even): the octet of v alone
+      flags |= (o1 ? 1 : 0) << 6;                           // x odd
+      flags |= (o2 ? 1 : 0) << 5;                           // y odd
+      flags |= ((o1 && o2 && o3) ? 1 : 0) << 4;             // x, y odd
+      flags |= (o4 ? 1 : 0) << 3;                           // z odd
+      flags |= ((o1 && o4 && o5) ? 1 : 0) << 2;             // x, z odd
+      flags |= ((o2 && o4 && o6) ? 1 : 0) << 1;             // y, z odd
+      flags |= ((o1 && o2 && o3 && o4 && o5 && o6 && o7) ? 1 : 0);  // x, y, z odd
+      res = e0 | (flags << CERT_LBITS);
+    }
+    out[vx + (size_t)c1 * vy + s3 * vz] = res;
+#pragma unroll
+    for (int k = 0; k < 4; k++) lo[k] = cu[k];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // fill + edge detection, one streaming pass over the label planes [za, zb) of this rank.
 // RULE: the labels of the last level are materialised here -- a point that is not on the stride-2 lattice
@@ -1526,6 +1776,7 @@ struct FillVArgs {
   int* label;            // owned planes, label[x + n1*(y + n2*zl)], zl = 0 .. nzl-1
   const int* uni2;
   const int* vsafe;
+  int pack;              // vsafe entries are packed (SafeMap::pack): the label is the low CERT_LBITS bits
   int* list; int* nlist; int* segcnt;
   int g1, g2, g3;        // blocks per axis
 };
@@ -1564,9 +1815,10 @@ __global__ void __launch_bounds__(256, FV_MINB) k_fill_edge_v(const __grid_const
     const int x1 = wrapx(2 * vx - 1, n1), x2 = 2 * vx, y1 = wrapx(2 * vy - 1, n2), y2 = 2 * vy;
     const bool okx1 = vx > 0 || (n1 & 1) == 0, oky1 = vy > 0 || (n2 & 1) == 0;
     const int* vs = A.vsafe + vx + (size_t)A.c1 * vy;
+    const int lmask = A.pack ? CERT_LMASK : LMASK;
     int sv_next = (vvalid && vz0 < A.c3) ? __ldg(vs + u3 * vz0) : -1;
     for (int vz = vz0; vz < vz1; vz++) {
-      const int sv = sv_next;
+      const int sv = sv_next < 0 ? -1 : (sv_next & lmask);
       sv_next = -1;  // the slab's extra layer above the last cube has no certificate
       if (vz + 1 < vz1 && vz + 1 < A.c3 && vvalid) sv_next = __ldg(vs + u3 * (vz + 1));
       const bool slow = vvalid && sv < 0;
@@ -2011,8 +2263,21 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
   WA.steps_per_check = spc_coarse;
   const int walk_occ = 4;  // resident 256-thread walker blocks per SM (<= 64 registers)
   const bool walk_stats = getenv("C2G_BADER_VERBOSE") != nullptr || getenv("C2G_BADER_STATS") != nullptr;
-  const bool walk_old = getenv("C2G_WALK_OLD") != nullptr;  // k_walk (threshold refill) instead of k_walk2
+  // k_walk2 (every idle lane refilled before every step) is an opt-in experiment: it keeps 30 of 32 lanes busy but
+  // its lanes no longer move as cohorts of neighbours, every load then touches up to 32 cache lines, and the last
+  // level took 26.4 ms against k_walk's 10.6 ms at 1024^3 (profiles/r02b_bench_1024_kwalk2_rejected.json)
+  const bool walk_old = getenv("C2G_WALK2") == nullptr;
   const int wblocks = ctx->nsm * walk_occ;
+  // which launches use the block-cooperative walkers (k_walk3): 1 = last level, 2 = edge fix, 4 = coarse levels, 8 = top lattice
+  // per class (last level / every other launch): idle threads of a block that trigger a pack + refill, steps between looks
+  // (B200, 1024^3: last level 11.95 -> 10.17 ms at 8 steps / 32 idle; edge fix 5.01 -> 2.45, stride-2 level 3.49 -> 3.10,
+  // stride-4 level 1.90 -> 1.68 ms at 16 steps / 128 idle; profiles/r02g_sweep_walk3.txt)
+  int walk3_mask = 15, w3_idle = 32, w3_k = 8, w3_idle_c = 128, w3_k_c = 16;
+  if (const char* e = getenv("C2G_WALK3")) walk3_mask = atoi(e);
+  if (const char* e = getenv("C2G_W3_IDLE")) w3_idle = std::max(1, std::min(256, atoi(e)));
+  if (const char* e = getenv("C2G_W3_K")) w3_k = std::max(1, std::min(64, atoi(e)));
+  if (const char* e = getenv("C2G_W3_IDLEC")) w3_idle_c = std::max(1, std::min(256, atoi(e)));
+  if (const char* e = getenv("C2G_W3_KC")) w3_k_c = std::max(1, std::min(64, atoi(e)));
 
   auto check_err = [&]() -> int {
     switch (hcnt[3]) {
@@ -2057,7 +2322,22 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
     const int blocks = (int)std::min<long long>(wblocks, (count + 255) / 256);
     ctx->prof_begin(name);
     const int variant = (ortho ? 4 : 0) | (fix ? 2 : 0) | (walk_stats ? 1 : 0);
-    if (!walk_old) {
+    // launch class: 8 = top lattice, 4 = coarse levels, 1 = last level, 2 = edge fix (bits of C2G_WALK3)
+    const int cls = fix ? 2 : (WA.list == nullptr ? 8 : (WA.sm_level == 0 ? 1 : 4));
+    if (walk3_mask & cls) {
+      // k_walk3: refill_min = idle threads of the block that trigger a pack + refill, steps_per_check = steps between two looks
+      WA.refill_min = cls == 1 ? w3_idle : w3_idle_c; WA.steps_per_check = cls == 1 ? w3_k : w3_k_c;
+      switch (variant) {
+        case 0: k_walk3<false, false, false><<<blocks, 256, 0, st>>>(P, WA); break;
+        case 1: k_walk3<false, false, true><<<blocks, 256, 0, st>>>(P, WA); break;
+        case 2: k_walk3<false, true, false><<<blocks, 256, 0, st>>>(P, WA); break;
+        case 3: k_walk3<false, true, true><<<blocks, 256, 0, st>>>(P, WA); break;
+        case 4: k_walk3<true, false, false><<<blocks, 256, 0, st>>>(P, WA); break;
+        case 5: k_walk3<true, false, true><<<blocks, 256, 0, st>>>(P, WA); break;
+        case 6: k_walk3<true, true, false><<<blocks, 256, 0, st>>>(P, WA); break;
+        default: k_walk3<true, true, true><<<blocks, 256, 0, st>>>(P, WA); break;
+      }
+    } else if (!walk_old) {
       // k_walk2 refills idle lanes before every step once `refill_min` lanes are idle (default 1)
       WA.refill_min = 1;
       if (const char* e = getenv("C2G_W2_REFILL")) WA.refill_min = std::max(1, std::min(32, atoi(e)));
@@ -2091,7 +2371,7 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
   auto walk_lattice = [&](long long count, int lat_s, const char* name) -> int {
     if (count <= 0) return C2G_OK;
     WA.list = nullptr; WA.stop = nullptr; WA.items = nullptr; WA.nitems = 0; WA.flat_base = 0; WA.count = count;
-    WA.sm = SafeMap{nullptr, 0, 0, 0, 0, 0, 0, 0, 0, 0}; WA.sm_level = 0;
+    WA.sm = SafeMap{nullptr, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; WA.sm_level = 0;
     WA.refill_min = lat_s == 1 ? refill_fine : refill_coarse;
     WA.steps_per_check = lat_s == 1 ? spc_fine : spc_coarse;
     WA.lat_s = lat_s; WA.lat_m1 = (n1 + lat_s - 1) / lat_s; WA.lat_m2 = (n2 + lat_s - 1) / lat_s;
@@ -2170,8 +2450,10 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
     // voided certificate walk again (k_requeue).  safe_maxs: coarsest cube stride whose certificates are used.
     int safe_maxs = 16;
     if (const char* e = getenv("C2G_SAFE_MAXS")) safe_maxs = atoi(e);
-    // certificate: 1 = octet (uniform 3x3x3 point neighbourhood), 2 = cube + 26 neighbour cubes (5x5x5, the
-    // margin at which the reference's refine_edge walks stop)
+    // certificate: 1 = octets; at the stride-2 level with the per-point 5x5x5 flags of k_pack5 (the margin at which
+    // the reference's refine_edge walks stop), 2 = cube + 26 neighbour cubes (coarser 5x5x5 rule, experiments),
+    // 3 = bare octets at every level (3x3x3 at stride 2: leaves a few wrong labels on ridge-running trajectories,
+    // 3 of 7.1e6 points in tests/sized_cases.py hetero192; kept for measurements only)
     int cert = 1;
     if (const char* e = getenv("C2G_CERT")) cert = atoi(e);
     const bool verbose = getenv("C2G_BADER_VERBOSE") != nullptr;
@@ -2209,16 +2491,29 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
         if (use_safe && L.s <= safe_maxs) {
           const dim3 sg((L.c1 + 31) / 32, (L.c2 + TY - 1) / TY, (L.c3 + MZC - 1) / MZC);
           ctx->prof_begin(i == 0 ? "bader_safe2" : "bader_safe");
-          if (cert == 1) {
+          if (cert == 1 || cert == 3) {
             const int px = (n1 % L.s) == 0, py = (n2 % L.s) == 0;
             const int pz = (S.periodic && (n3 % L.s) == 0) ? 1 : 0;
-            k_vsafe<<<sg, 256, 0, st>>>(L.c1, L.c2, L.c3, px, py, pz, (S.nzl % L.s) == 0 ? 1 : 0, b_uni[i].as<int>(), b_safe[i].as<int>());
-            sm = SafeMap{b_safe[i].as<int>(), i + 1, L.c1, L.c2, L.c3, S.zlo, S.nzl, 1, pz, (1 << (i + 1)) >> 1};
+            // stride-2 level: an octet only covers the 3x3x3 neighbourhood of its points; the walkers need 5x5x5 (the
+            // reference's margin), so the octets go to a scratch array and k_pack5 adds the per-point flags.  Labels
+            // that do not fit the packed entry (> 8.4e6 maxima: noise): no certificates at this level.
+            const bool pack = i == 0 && cert == 1;
+            if (pack && ncand > CERT_LMASK) {
+              ctx->prof_end(0);
+            } else {
+              int* octets = pack ? b_list[2].as<int>() : b_safe[i].as<int>();  // the flat lists are idle until the edge fix
+              k_vsafe<<<sg, 256, 0, st>>>(L.c1, L.c2, L.c3, px, py, pz, (S.nzl % L.s) == 0 ? 1 : 0, b_uni[i].as<int>(), octets);
+              if (pack) {
+                k_pack5<<<sg, 256, 0, st>>>(L.c1, L.c2, L.c3, px, py, pz, octets, b_safe[i].as<int>());
+              }
+              sm = SafeMap{b_safe[i].as<int>(), i + 1, L.c1, L.c2, L.c3, S.zlo, S.nzl, 1, pz, (1 << (i + 1)) >> 1, pack ? 1 : 0};
+              ctx->prof_end(pack ? 2 : 1);
+            }
           } else {
             k_safe<<<sg, 256, 0, st>>>(L.c1, L.c2, L.c3, b_uni[i].as<int>(), b_safe[i].as<int>());
-            sm = SafeMap{b_safe[i].as<int>(), i + 1, L.c1, L.c2, L.c3, S.zlo, S.nzl, 0, 0, 0};
+            sm = SafeMap{b_safe[i].as<int>(), i + 1, L.c1, L.c2, L.c3, S.zlo, S.nzl, 0, 0, 0, 0};
+            ctx->prof_end();
           }
-          ctx->prof_end();
           C2G_KERNEL_CHECK(ctx);
         }
       }
@@ -2266,7 +2561,7 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
       FV.c1 = lev[0].c1; FV.c2 = lev[0].c2; FV.c3 = lev[0].c3;
       FV.nzl = S.nzl; FV.periodic = S.periodic; FV.zlo = S.zlo;
       FV.nvz = FV.c3 + (S.periodic ? 0 : 1);
-      FV.label = res->d_label; FV.uni2 = b_uni[0].as<int>(); FV.vsafe = fixsafe.safe;
+      FV.label = res->d_label; FV.uni2 = b_uni[0].as<int>(); FV.vsafe = fixsafe.safe; FV.pack = fixsafe.pack;
       FV.list = seglist; FV.nlist = cnt + 1; FV.segcnt = segcnt;
       FV.g1 = (FV.c1 + 31) / 32; FV.g2 = (FV.c2 + 7) / 8; FV.g3 = std::max(1, (FV.nvz + VZC - 1) / VZC);
       nfeseg = fv_nblocks(FV.g1, FV.g2, FV.g3); fesegcap = FV_SEGCAP;

@@ -69,6 +69,24 @@ def test_labels_vs_oracle_256_class(ctx, golden, name):
     ctx.free(h)
 
 
+def test_degenerate_cell_is_reported_not_asserted(ctx):
+    """flat160d: ridge-running trajectories; the reference's labels depend on its scan order there (21 refine_edge
+    iterations).  The three labellings -- oracle (sequential reference), exact-walk referee, FAST -- may differ in a
+    few points per million; the counts are printed and bounded, populations agree to the same fraction."""
+    c = Z.CASES["flat160d"]()
+    h = generate(ctx, c)
+    f = ctx.download(h, c["n"])
+    idg, nattr, _, stats = orc.bader_integrate(f, c["x2c"], atoms=c["atoms"])
+    lab_f, nmax = device_labels(ctx, h, c, capi.BADER_FAST)
+    lab_e, _ = device_labels(ctx, h, c, capi.BADER_EXACT)
+    nn = float(np.prod(c["n"]))
+    d_fo, d_eo, d_fe = (int(np.count_nonzero(a != b)) for a, b in ((lab_f, idg), (lab_e, idg), (lab_f, lab_e)))
+    print(f"flat160d: refine iterations of the oracle {stats[0]}; FAST vs oracle {d_fo}, EXACT vs oracle {d_eo}, FAST vs EXACT {d_fe} of {int(nn)}")
+    assert nmax == nattr
+    assert max(d_fo, d_eo, d_fe) <= 2e-5 * nn
+    ctx.free(h)
+
+
 @pytest.mark.parametrize("name,l0", [("head256", "32"), ("hetero192", "32"), ("molvac256", "16"), ("urea256", "32")])
 def test_forced_top_stride_vs_oracle(ctx, name, l0):
     """C2G_BADER_L0 overrides the basin-size guard on the top lattice stride: strides up to 32 (the one the 1024^3

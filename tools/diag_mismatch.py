@@ -13,7 +13,8 @@ from oracle import oracle as orc
 
 ctx = capi.Context(0)
 VARIANTS = [("default", {}), ("no early stop", {"C2G_NO_EARLY_STOP": "1"}), ("L0=4", {"C2G_BADER_L0": "4"}),
-            ("certificates only at stride 2", {"C2G_SAFE_MAXS": "2"}), ("old walker kernel", {"C2G_WALK_OLD": "1"})]
+            ("certificates only at stride 2", {"C2G_SAFE_MAXS": "2"}), ("per-lane refill walkers (k_walk2)", {"C2G_WALK2": "1"}), ("5x5x5 cube certificates", {"C2G_CERT": "2"}), ("bare octets (3x3x3 at stride 2, round 1)", {"C2G_CERT": "3"}),
+            ("block-cooperative walkers (k_walk3) for every launch", {"C2G_WALK3": "15"})]
 for name in sys.argv[1:]:
     c = Z.CASES[name]()
     n, x2c, at = c["n"], c["x2c"], c["atoms"]
