@@ -250,10 +250,10 @@ def config_dict(size, side, world, nmax=None):
 
 def run_reference(args):
     """critic2's own CPU algorithm for the path (the oracle port: critic2 is Fortran and no Fortran compiler exists in
-    this image).  --size <= 512: every step is one pass over the FULL grid of our arm's config (same_config).  Larger
-    sizes (the 1024^3 default would take ~15 min per pass): every step is one pass over a bounded 256x256x128 sample of
-    the same density model, and the JSON line says so.  The run stops early when the next pass would take the whole
-    run beyond ~150 s; `steps` is the number of passes actually timed."""
+    this image).  --size <= 512: every step is one pass over the FULL grid of our arm's config (same_config).  The
+    1024^3 default would take ~20 min per pass: every step is then one FULL pass over the 512^3 grid of the same density
+    model (the other size the metric names; the grid of our arm's `also_512` line), and the JSON line says so.  The
+    run stops early when the next pass would take the whole run beyond ~150 s; `steps` is the number of passes timed."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -261,7 +261,15 @@ def run_reference(args):
     size = args.size
     side = max(2, size // 128)
     full = size <= 512
-    sample_n = (size, size, size) if full else (256, 256, 128)
+    # 1024^3 would take ~20 min per pass on one host core: the reference arm then times the FULL 512^3 grid of the same
+    # density model -- the other size BASELINE.json's metric names, and exactly the grid of our arm's `also_512` line
+    # (C2G_REF_SAMPLE=1: the bounded 256x256x128 sample instead, ~10 s per pass)
+    if full:
+        sample_n = (size, size, size)
+    elif os.environ.get("C2G_REF_SAMPLE"):
+        sample_n = (256, 256, 128)
+    else:
+        sample_n = (512, 512, 512)
     res = cpu_baseline_run(sample_n=sample_n, steps=max(1, args.steps), budget_s=float(os.environ.get("C2G_REF_BUDGET_S", "150")))
     out = {
         "impl": "reference", "metric": "grid points/s, BADER assign+integrate", "value": res["value"], "unit": "grid points/s",
@@ -269,13 +277,16 @@ def run_reference(args):
         "ms_per_step": res["seconds"] * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": config_dict(size, side, max(1, args.gpus)),
         "same_config_as_gpu_arm": bool(full),
+        "same_grid_as_gpu_arm_also_512": bool(list(res["grid"]) == [512, 512, 512]),
         "timed_grid": res["grid"],
         "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": res["value"], "unit": "grid points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": ("critic2 (Fortran) cannot be compiled in this image; this is the C++ restatement in oracle/ of the reference's own "
                  "CPU algorithm. " + ("Timed on the full grid of the config." if full else
-                 "ms_per_step and value are those of the bounded sample named in timed_grid / cpu_baseline.sample, NOT of a full "
-                 f"{size}^3 pass (points/s is size-independent to ~20 % for this serial algorithm); run --size 512 for a same-grid comparison.")),
+                 "ms_per_step and value are those of ONE FULL pass over the grid named in timed_grid / cpu_baseline.sample (the 512^3 "
+                 "workload of the same density model = the grid of the GPU arm's also_512 line), NOT of a full "
+                 f"{size}^3 pass, which takes ~20 min on one host core (measured once: tests/golden/bader_at_size.json, head1024, "
+                 "oracle_seconds); points/s of this serial algorithm is size-independent to ~15 % (0.81e6 at 1024^3, 0.92e6 at 512^3).")),
         "wall_s": time.perf_counter() - t_all,
     }
     print(json.dumps(out), flush=True)
@@ -482,6 +493,32 @@ def run_ours(args):
         also = {"grid": [512, 512, 512], "atoms": side5 ** 3, "steps": k5, "ms_per_step": ms5, "value": float(np.prod(n5)) / (ms5 * 1e-3),
                 "unit": "grid points/s", "roofline_frac_of_step": ALG_BYTES_TOTAL * float(np.prod(n5)) / (ms5 * 1e-3) / 1e9 / peak,
                 "volume_sum_over_omega": float(v5.sum() / om5)}
+        # the same grid end to end (pinned host buffers in, labels + sums out): the line the reference arm's default run
+        # (one full 512^3 pass on the host) is the same-grid counterpart of
+        nn5 = int(np.prod(n5))
+        hr5 = torch.empty(nn5, dtype=torch.float64, pin_memory=True)
+        hf5 = torch.empty(nn5, dtype=torch.float64, pin_memory=True)
+        hi5 = torch.empty(nn5, dtype=torch.int32, pin_memory=True)
+        ctx.download_slab_ptr(g1, hr5.data_ptr()); ctx.download_slab_ptr(g2, hf5.data_ptr())
+
+        def e2e512():
+            ha = ctx.upload_ptr_async(hr5.data_ptr(), n5)
+            hb = ctx.upload_ptr_async(hf5.data_ptr(), n5)
+            b5 = ctx.bader_assign(ha, c5, l5, algo=capi.BADER_FAST)
+            b5.set_map(b5.nmax, id5[: b5.nmax])
+            b5.labels_ptr_async(hi5.data_ptr())
+            r = ctx.integrate(b5, [ha, hb], om5)
+            ctx.synchronize()
+            b5.free(); ctx.free(ha); ctx.free(hb)
+            return r
+        e2e512()
+        ctx.synchronize(); t5 = time.perf_counter()
+        for _ in range(3):
+            e2e512()
+        ms5e = (time.perf_counter() - t5) * 1e3 / 3
+        also["e2e"] = {"value": float(nn5) / (ms5e * 1e-3), "unit": "grid points/s", "ms_per_step": ms5e, "steps": 3,
+                       "h2d_bytes_per_step": 2 * 8 * nn5, "d2h_bytes_per_step": 4 * nn5 + 8 * 3 * side5 ** 3}
+        del hr5, hf5, hi5
         ctx.free(g1); ctx.free(g2)
 
     # ---- CPU baseline beside it (rank 0, N=1 only; bounded sample) ----

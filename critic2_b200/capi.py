@@ -26,7 +26,7 @@ EXPORTS = [
     "c2g_grid_upload", "c2g_grid_upload_slab", "c2g_slab_range", "c2g_slab_bounds_query", "c2g_grid_alloc", "c2g_grid_download", "c2g_grid_download_slab", "c2g_grid_free", "c2g_grid_promolecular",
     "c2g_bader_assign", "c2g_basins_maxima", "c2g_basins_counts", "c2g_basins_set_map", "c2g_basins_labels",
     "c2g_basins_relabel", "c2g_basins_nattr", "c2g_basins_free", "c2g_basins_stats", "c2g_integrate", "c2g_integrate_multipoles", "c2g_promolecular_grid", "c2g_hirshfeld_integrate", "c2g_basins_remap", "c2g_yt_build",
-    "c2g_yt_weights", "c2g_basins_weight_grid", "c2g_yt_isosurface", "c2g_nci_rdg", "c2g_nci_rdg_resident", "c2g_fft_derivative", "c2g_nci_rdg_fourier", "c2g_nci_range", "c2g_grid_upload_async", "c2g_basins_labels_async", "c2g_grid_parse_text", "c2g_grid_format_text", "c2g_profile_enable", "c2g_profile_count",
+    "c2g_yt_weights", "c2g_yt_export", "c2g_basins_weight_grid", "c2g_yt_isosurface", "c2g_nci_rdg", "c2g_nci_rdg_resident", "c2g_fft_derivative", "c2g_nci_rdg_fourier", "c2g_nci_range", "c2g_grid_upload_async", "c2g_basins_labels_async", "c2g_grid_parse_text", "c2g_grid_format_text", "c2g_profile_enable", "c2g_profile_count",
     "c2g_profile_get", "c2g_profile_reset", "c2g_launch_count", "c2g_flush_l2", "c2g_synchronize", "c2g_timer_start", "c2g_timer_stop",
 ]
 
@@ -465,6 +465,16 @@ class Basins:
         s = np.zeros(8, dtype=np.int64)
         self.ctx._chk(self.ctx.lib.c2g_basins_stats(self.h, _p(s, C.c_longlong)))
         return s
+
+    def yt_export(self, shape, nvec, full=True):
+        """ytdata record (yt.f90:36-45): (nlo, ibasin, iio, inear, fnear), position-indexed like the reference's."""
+        nn = int(np.prod(shape))
+        nlo = np.zeros(nn, dtype=np.int32); ibasin = np.zeros(nn, dtype=np.int32); iio = np.zeros(nn, dtype=np.int32)
+        inear = np.zeros((nvec, nn), dtype=np.int32, order="F") if full else None
+        fnear = np.zeros((nvec, nn), dtype=np.float64, order="F") if full else None
+        self.ctx._chk(self.ctx.lib.c2g_yt_export(self.h, _p(nlo, C.c_int), _p(ibasin, C.c_int), _p(iio, C.c_int),
+                                                 _p(inear, C.c_int) if full else None, _p(fnear, C.c_double) if full else None))
+        return nlo, ibasin, iio, inear, fnear
 
     def yt_weights(self, idb, shape):
         w = np.zeros(tuple(int(x) for x in shape), order="F")

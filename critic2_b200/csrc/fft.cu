@@ -157,7 +157,8 @@ extern "C" int c2g_fft_derivative(c2g_context* ctx, int handle, int iff, const d
   if (handle < 0 || handle >= (int)ctx->grids.size() || !ctx->grids[handle].used)
     return ctx->fail(C2G_ERR_ARG, "c2g_fft_derivative: invalid grid handle %d", handle);
   if (iff < C2G_FT_X || iff > C2G_FT_POT) return ctx->fail(C2G_ERR_ARG, "c2g_fft_derivative: unknown derivative code %d", iff);
-  if (ctx->nranks > 1) return ctx->fail(C2G_ERR_STATE, "c2g_fft_derivative: single-GPU only (SURVEY.md 8e)");
+  // multi-GPU contexts hold the field replicated on every rank: the derived field is computed by every rank on its own
+  // copy (replicas only) -- no collective, the result is again a replicated resident grid
   CufftApi& api = cufft_api();
   if (!api.ok) return ctx->fail(C2G_ERR_CUDA, "c2g_fft_derivative: cuFFT unavailable: %s", api.err);
   c2g_grids_ready_all(ctx);

@@ -856,6 +856,127 @@ extern "C" int c2g_yt_weights(c2g_basins* res, int idb, double* w) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// ytdata export (yt.f90:36-45; written at yt@proc.f90:191-199, read back by yt_weights :399-530, int_reorder_gridout
+// integration@proc.f90:1125-1158 and the BASINS / DI consumers): the record the reference keeps on a scratch file,
+// indexed by the POSITION of a point in the density-sorted list (1 = lowest).  The device never sorts for its own
+// work; here the permutation is materialised once: a stable radix sort of (rho, index) -- the reference's qcksort
+// order whenever no two densities tie -- then one pass per chunk of positions gathers, for every
+// point kk, the IAS points ii below it that send flux to it, in the order in which the reference's sweep appends
+// them (decreasing ii), with fnear = chi / max(csum, vsmall) of the lower point (:177-186).
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) k_exp_keys(long long nn, const double* __restrict__ rho, unsigned long long* __restrict__ key,
+                                                  int* __restrict__ val) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nn) return;
+  // order-preserving map of an IEEE double onto an unsigned integer (-0.0 sorts below +0.0; the reference compares
+  // them equal, which only matters for tied data)
+  const unsigned long long b = (unsigned long long)__double_as_longlong(rho[i]);
+  key[i] = (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+  val[i] = (int)i;
+}
+__global__ void __launch_bounds__(256) k_exp_iio(long long nn, const int* __restrict__ io, int* __restrict__ iio) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < nn) iio[io[p]] = (int)p + 1;
+}
+// positions [p0, p0 + np): ibasin, nlo and the inear / fnear columns
+__global__ void __launch_bounds__(128) k_exp_points(const __grid_constant__ YtParams P, long long p0, int np, const double* __restrict__ rho,
+                                                    const unsigned* __restrict__ mask, const double* __restrict__ csum,
+                                                    const unsigned char* __restrict__ ias, const int* __restrict__ label,
+                                                    const int* __restrict__ map, const int* __restrict__ io, const int* __restrict__ iio,
+                                                    int* __restrict__ nlo, int* __restrict__ ibasin, int* __restrict__ inear,
+                                                    double* __restrict__ fnear) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= np) return;
+  const int j = io[p0 + t];
+  const int l = label[j];
+  ibasin[t] = l >= 0 ? __ldg(map + l) : 0;
+  const Pt pj = unlin(P, j);
+  const double rj = rho[j];
+  const unsigned mj = mask[j];
+  int pos[MAXVEC];
+  double fl[MAXVEC];
+  int cnt = 0;
+  for (int k = 0; k < P.nvec; k++) {
+    if ((mj >> k) & 1u) continue;           // that neighbour is higher than j
+    const int i = nbr(P, pj, k);
+    if (i == j || !ias[i]) continue;        // only IAS points keep their flux records (:177)
+    // j = i + vec(opp[k]) is a higher neighbour of i: chi as in k_scan / :121
+    const double chi = fmax(P.area[P.opp[k]] * (rj - rho[i]), VSMALL);
+    const int pi = iio[i];
+    // insertion into the list ordered by decreasing position (the reference appends while ii runs downwards)
+    int q = cnt++;
+    const double f = chi / fmax(csum[i], VSMALL);
+    while (q > 0 && pos[q - 1] < pi) { pos[q] = pos[q - 1]; fl[q] = fl[q - 1]; q--; }
+    pos[q] = pi; fl[q] = f;
+  }
+  nlo[t] = cnt;
+  if (inear)
+    for (int q = 0; q < P.nvec; q++) inear[(size_t)t * P.nvec + q] = q < cnt ? pos[q] : 0;
+  if (fnear)
+    for (int q = 0; q < P.nvec; q++) fnear[(size_t)t * P.nvec + q] = q < cnt ? fl[q] : 0.0;
+}
+}  // namespace
+
+extern "C" int c2g_yt_export(c2g_basins* res, int* nlo, int* ibasin, int* iio, int* inear, double* fnear) {
+  if (!res) return C2G_ERR_ARG;
+  c2g_context* ctx = res->ctx;
+  if (res->kind != 1 || !res->yt) return ctx->fail(C2G_ERR_STATE, "c2g_yt_export: not a YT result");
+  if (!res->has_map) return ctx->fail(C2G_ERR_STATE, "c2g_yt_export: call c2g_basins_set_map first");
+  if (!nlo || !ibasin || !iio) return ctx->fail(C2G_ERR_ARG, "c2g_yt_export: null output");
+  cudaSetDevice(ctx->device);
+  YtState* S = yt_state(res);
+  const YtParams& P = S->P;
+  const long long nn = res->nn;
+  cudaStream_t st = ctx->stream;
+  c2g_grid_ready(ctx, res->gridh);
+  const double* rho = ctx->grids[res->gridh].d;
+  DevBuf b_key, b_key2, b_val, b_io, b_iio, b_tmp;
+  C2G_CUDA(ctx, b_key.alloc(ctx, sizeof(unsigned long long) * nn));
+  C2G_CUDA(ctx, b_key2.alloc(ctx, sizeof(unsigned long long) * nn));
+  C2G_CUDA(ctx, b_val.alloc(ctx, sizeof(int) * nn));
+  C2G_CUDA(ctx, b_io.alloc(ctx, sizeof(int) * nn));
+  C2G_CUDA(ctx, b_iio.alloc(ctx, sizeof(int) * nn));
+  const int nb = c2g_blocks_for(nn, 256);
+  ctx->prof_begin("yt_export_sort");
+  k_exp_keys<<<nb, 256, 0, st>>>(nn, rho, b_key.as<unsigned long long>(), b_val.as<int>());
+  size_t tmpbytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmpbytes, b_key.as<unsigned long long>(), b_key2.as<unsigned long long>(), b_val.as<int>(),
+                                  b_io.as<int>(), (int)nn, 0, 64, st);
+  C2G_CUDA(ctx, b_tmp.alloc(ctx, tmpbytes));
+  cub::DeviceRadixSort::SortPairs(b_tmp.p, tmpbytes, b_key.as<unsigned long long>(), b_key2.as<unsigned long long>(), b_val.as<int>(),
+                                  b_io.as<int>(), (int)nn, 0, 64, st);
+  k_exp_iio<<<nb, 256, 0, st>>>(nn, b_io.as<int>(), b_iio.as<int>());
+  ctx->prof_end(3);
+  C2G_KERNEL_CHECK(ctx);
+  C2G_CUDA(ctx, cudaMemcpyAsync(iio, b_iio.p, sizeof(int) * nn, cudaMemcpyDeviceToHost, st));
+  b_key.reset(); b_key2.reset(); b_val.reset(); b_tmp.reset();
+  // chunks of positions: the inear / fnear columns of 512^3 points with 14 stencil vectors are 22 GB
+  const int chunk = (int)std::min<long long>(nn, 1ll << 24);
+  DevBuf b_nlo, b_ib, b_in, b_fn;
+  C2G_CUDA(ctx, b_nlo.alloc(ctx, sizeof(int) * chunk));
+  C2G_CUDA(ctx, b_ib.alloc(ctx, sizeof(int) * chunk));
+  if (inear) C2G_CUDA(ctx, b_in.alloc(ctx, sizeof(int) * (size_t)chunk * P.nvec));
+  if (fnear) C2G_CUDA(ctx, b_fn.alloc(ctx, sizeof(double) * (size_t)chunk * P.nvec));
+  for (long long p0 = 0; p0 < nn; p0 += chunk) {
+    const int np = (int)std::min<long long>(chunk, nn - p0);
+    ctx->prof_begin("yt_export_points");
+    k_exp_points<<<c2g_blocks_for(np, 128), 128, 0, st>>>(P, p0, np, rho, S->mask, S->csum, S->ias, res->d_label, res->d_map,
+                                                          b_io.as<int>(), b_iio.as<int>(), b_nlo.as<int>(), b_ib.as<int>(),
+                                                          inear ? b_in.as<int>() : nullptr, fnear ? b_fn.as<double>() : nullptr);
+    ctx->prof_end();
+    C2G_KERNEL_CHECK(ctx);
+    C2G_CUDA(ctx, cudaMemcpyAsync(nlo + p0, b_nlo.p, sizeof(int) * np, cudaMemcpyDeviceToHost, st));
+    C2G_CUDA(ctx, cudaMemcpyAsync(ibasin + p0, b_ib.p, sizeof(int) * np, cudaMemcpyDeviceToHost, st));
+    if (inear) C2G_CUDA(ctx, cudaMemcpyAsync(inear + (size_t)p0 * P.nvec, b_in.p, sizeof(int) * (size_t)np * P.nvec, cudaMemcpyDeviceToHost, st));
+    if (fnear) C2G_CUDA(ctx, cudaMemcpyAsync(fnear + (size_t)p0 * P.nvec, b_fn.p, sizeof(double) * (size_t)np * P.nvec, cudaMemcpyDeviceToHost, st));
+    C2G_CUDA(ctx, cudaStreamSynchronize(st));
+  }
+  ctx->prof_collect();
+  return C2G_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // ISOSURFACE regions: yt_isosurface, src/yt@proc.f90:233-390.
 //
 // The reference sweeps the sorted grid once more: a point at or above the contour value takes the region of its

@@ -197,6 +197,14 @@ int c2g_yt_build(c2g_context* ctx, int handle, int nvec, const int* vec, const d
 /* (use c2g_basins_labels) */
 /* dense weight field of one basin, w(n1,n2,n3) (yt_weights, yt@proc.f90:476-499). */
 int c2g_yt_weights(c2g_basins* res, int idb, double* w);
+/* The ytdata record (yt.f90:36-45) that yt_integrate writes to bas%luw (yt@proc.f90:191-199) and that yt_weights
+ * (:399-530), int_reorder_gridout (integration@proc.f90:1125-1158) and the BASINS / DI consumers read back, for hosts
+ * that keep using their own yt_weights: nlo(nn), ibasin(nn), iio(nn), inear(nvec,nn), fnear(nvec,nn), all indexed by
+ * the position of a point in the density-sorted list (1 = lowest) except iio (grid index -> position).  ibasin
+ * carries the ids of the current c2g_basins_set_map / c2g_basins_relabel (what int_reorder_gridout rewrites).  The order
+ * is that of a stable sort of (density, index) = the reference's qcksort order on tie-free data.  inear / fnear may be
+ * NULL (they are nvec*nn entries each). */
+int c2g_yt_export(c2g_basins* res, int* nlo, int* ibasin, int* iio, int* inear, double* fnear);
 /* WCUBE (int_cubew, integration@proc.f90:4428-4466): the weight field of basin idb as a RESIDENT grid -- the YT
  * weights (yt_weights with idb, :4451) or, for Bader labels and ISOSURFACE regions, w = 1 where idg == idb
  * (:4455-4458).  Pass the handle to c2g_grid_format_text (layout 1) for the value block of the cube file, then

@@ -208,3 +208,31 @@ def test_yt_merged_and_discarded_maxima_follow_the_map(ctx, mode):
         lab2 = b.labels(n)
         assert np.array_equal(lab2 == 0, ias_before)
     b.free(); ctx.free(h)
+
+
+@pytest.mark.parametrize("name", ["cubic48", "triclinic", "odd_dims"])
+def test_yt_export_reproduces_the_ytdata_record(ctx, name):
+    """c2g_yt_export against the oracle's ytdata (yt.f90:36-45: nlo, ibasin, iio, inear, fnear as yt_integrate writes them
+    to bas%luw, yt@proc.f90:191-199): integers bit-exact, flux fractions bit-exact (same operations, same order)."""
+    c = cases.make_case(name)
+    n, x2c = c["n"], c["x2c"]
+    vec, area = S.wscell(x2c / np.array(n, dtype=float)[None, :])
+    d = orc.yt_integrate(c["f"], x2c, vec, area, atoms=c["atoms"])
+    h = ctx.upload(c["f"])
+    b = ctx.yt_build(h, vec, area)
+    mp, na, _ = H.assign_attractors(b.maxima(), n, x2c, c["atoms"])
+    b.set_map(na, mp)
+    nlo, ibasin, iio, inear, fnear = b.yt_export(n, len(area))
+    assert np.array_equal(iio, d.iio)
+    assert np.array_equal(ibasin, d.ibasin)
+    assert np.array_equal(nlo, d.nlo)
+    assert np.array_equal(inear, d.inear)
+    assert np.array_equal(fnear, d.fnear)
+    # the reference's own yt_weights run on the exported record gives the weights of c2g_yt_weights
+    dd = orc.YtData(d.nn, d.nvec)
+    dd.nlo, dd.ibasin, dd.iio, dd.inear, dd.fnear, dd.nattr = nlo, ibasin, iio, inear, fnear, na
+    for idb in (1, na):
+        assert np.abs(orc.yt_weights(dd, idb, n) - b.yt_weights(idb, n)).max() <= 1e-12
+    nlo2, ib2, iio2, _, _ = b.yt_export(n, len(area), full=False)
+    assert np.array_equal(nlo2, nlo) and np.array_equal(ib2, ibasin) and np.array_equal(iio2, iio)
+    b.free(); ctx.free(h)
