@@ -171,10 +171,15 @@ struct SafeMap {
 };
 constexpr int CERT_LBITS = 23;                       // label bits of a packed entry
 constexpr int CERT_LMASK = (1 << CERT_LBITS) - 1;
+constexpr int CERT_VOID = (int)0x80000000;           // packed entry without a certificate: negative AND no flag set, so
+                                                     // that the walkers test one bit and everyone else the sign
+// flag of the point (x, y, cz) in a packed entry: bit CERT_LBITS + (x odd) + 2 (y odd) + 4 (cz odd)
+__device__ __forceinline__ int cert_flagbit(int x, int y, int cz) {
+  return CERT_LBITS + ((x & 1) | ((y & 1) << 1) | ((cz & 1) << 2));
+}
 // label certified for the point (x, y, cz) by entry e of a packed map, or -1
 __device__ __forceinline__ int cert_unpack(int e, int x, int y, int cz) {
-  const int pidx = ((x & 1) ^ 1) | (((y & 1) ^ 1) << 1) | (((cz & 1) ^ 1) << 2);
-  return (e >= 0 && ((e >> (CERT_LBITS + pidx)) & 1)) ? (e & CERT_LMASK) : -1;
+  return ((e >> cert_flagbit(x, y, cz)) & 1) ? (e & CERT_LMASK) : -1;
 }
 constexpr int STOP_SHIFT = 28;             // stop code = (level index << 28) | map index
 constexpr int STOP_MASK = (1 << STOP_SHIFT) - 1;
@@ -336,8 +341,8 @@ __device__ __forceinline__ int safe_lookup2(const SafeMap& sm, int x, int y, int
     vx = x >> sm.shift; vy = y >> sm.shift; vz = cz >> sm.shift;
   }
   mapidx = vx + sm.c1 * (vy + sm.c2 * vz);
-  const int e = ok ? sm.safe[mapidx] : -1;  // plain load: entries may be invalidated while walkers run
-  return sm.pack ? cert_unpack(e, x, y, cz) : e;
+  const int e = ok ? sm.safe[mapidx] : CERT_VOID;  // plain load: entries may be invalidated while walkers run
+  return sm.pack ? cert_unpack(e, x, y, cz) : e;     // (CERT_VOID is negative: "none" for the other map kinds too)
 }
 // w: current point with w.r0, nb = its neighbours, sl = early-termination label of its cube (all loaded by
 // the previous call or by the caller for the start point, where sl must be -1)
@@ -698,7 +703,7 @@ __device__ __noinline__ void claim_neighbours(const BaderParams& P, const WalkAr
         for (int dx = lo; dx <= hi; dx++) {
           const int vx = wrapx(cx + dx, sm.c1);
           int* e = sm.safe + vx + sm.c1 * (vy + (size_t)sm.c2 * vz);
-          if (*e >= 0 && atomicExch(e, -1) >= 0) atomicAdd(A.ninval, 1);
+          if (*e >= 0 && atomicExch(e, sm.pack ? CERT_VOID : -1) >= 0) atomicAdd(A.ninval, 1);
         }
       }
     }
@@ -848,6 +853,13 @@ __device__ __forceinline__ double nint_bits(double v, int& d) {
   const bool big = (unsigned)((hi & 0x7fffffff) - 0x3fe00000) < (unsigned)(0x7ff00000 - 0x3fe00000);
   const int ahi = big ? ((hi & (int)0x80000000) | 0x3ff00000) : 0;
   d = big ? ((hi >> 31) | 1) : 0;
+  return __hiloint2double(ahi, 0);
+}
+// Fortran nint of a finite |v| < 2.5 with |nint| <= 1 expected (|v| < 1.5), as a double: one fp64 compare, the sign of v
+// pasted onto 1.0, one select.  NaN gives 0 (such a walk ends "did not move", like with nint_di).
+__device__ __forceinline__ double nint_half(double v) {
+  const int hi = __double2hiint(v);
+  const int ahi = fabs(v) >= 0.5 ? ((hi & (int)0x80000000) | 0x3ff00000) : 0;
   return __hiloint2double(ahi, 0);
 }
 // g, or 0 when both neighbours are strictly below the centre (rho_grad_dir, :553-558): two chained predicates, one select
@@ -1035,7 +1047,8 @@ __global__ void __launch_bounds__(256, 4) k_walk2(const __grid_constant__ BaderP
 // run dry at the end of a launch.  The step is the lean one of k_walk2 (all loads of a step issued together at its
 // top, no state besides point, dr and the largest density on the path).
 // ------------------------------------------------------------------------------------------------
-template <bool ORTHO, bool FIX, bool STATS>
+// CERT: 0 = no certificates (top lattice), 1 = any SafeMap, 2 = the packed octets of the stride-2 level
+template <bool ORTHO, bool FIX, bool STATS, int CERT>
 __global__ void __launch_bounds__(256, 4) k_walk3(const __grid_constant__ BaderParams P, const __grid_constant__ WalkArgs A) {
   __shared__ int s_wc[8];
   __shared__ int s_chunk[2];                       // first entry and number of entries handed to the block
@@ -1132,7 +1145,26 @@ __global__ void __launch_bounds__(256, 4) k_walk3(const __grid_constant__ BaderP
         zm = __ldg(c + ((z == 0) ? s3 * n3 - s3 : -s3));
       }
       int sli = -1, sl = -1;
-      if (!first && A.sm.safe) sl = safe_lookup2(A.sm, x, y, z, sli);  // the start point is never looked up
+      if (CERT == 2) {
+        if (!first) {  // the start point is never looked up
+          const SafeMap& sm = A.sm;
+          const int cz = z - sm.zlo;
+          int vx = (x + 1) >> 1, vy = (y + 1) >> 1, vz = (cz + 1) >> 1;
+          bool ok = true;
+          if (!(inner && A.S.periodic)) {  // near a seam, or a z-slab: the vertex may wrap or lie outside the owned layers
+            vx = vx == sm.c1 ? 0 : vx;
+            vy = vy == sm.c2 ? 0 : vy;
+            const bool top = vz == sm.c3;
+            ok = (unsigned)cz < (unsigned)sm.nzl && (!top || sm.wrapz);
+            vz = top ? 0 : vz;
+          }
+          sli = vx + sm.c1 * (vy + sm.c2 * vz);
+          const int e = ok ? sm.safe[sli] : CERT_VOID;  // plain load: entries may be voided while walkers run
+          sl = cert_unpack(e, x, y, cz);
+        }
+      } else if (CERT == 1) {
+        if (!first) sl = safe_lookup2(A.sm, x, y, z, sli);
+      }
       int st = 0, out = 0;
       if (r0 <= rhomax) {
         st = 3;  // possibly a point of this path (known(pm) == 1, :487): k_walk_big answers exactly
@@ -1156,12 +1188,10 @@ __global__ void __launch_bounds__(256, 4) k_walk3(const __grid_constant__ BaderP
           g1 = P.c2l[1] * gc0 + P.c2l[4] * gc1 + P.c2l[7] * gc2;
           g2 = P.c2l[2] * gc0 + P.c2l[5] * gc1 + P.c2l[8] * gc2;
         }
-        double gmax = fabs(g0);
-        {
-          const double t1 = fabs(g1), t2 = fabs(g2);
-          gmax = t1 > gmax ? t1 : gmax;
-          gmax = t2 > gmax ? t2 : gmax;
-        }
+        // maxval(abs(grad)): the component of largest magnitude is selected as it is, its sign goes at the end
+        double gsel = fabs(g1) > fabs(g0) ? g1 : g0;
+        gsel = fabs(g2) > fabs(gsel) ? g2 : gsel;
+        const double gmax = fabs(gsel);
         const int oid = id;
         if (gmax < 1e-30) {  // (:468-476)
           dr0 = dr1 = dr2 = 0.0;
@@ -1178,12 +1208,12 @@ __global__ void __launch_bounds__(256, 4) k_walk3(const __grid_constant__ BaderP
         } else {  // (:477-483)
           const double coeff = 1.0 / gmax;
           g0 = coeff * g0; g1 = coeff * g1; g2 = coeff * g2;
-          int d0, d1, d2, e0, e1, e2;
-          const double a0 = nint_bits(g0, d0), a1 = nint_bits(g1, d1), a2 = nint_bits(g2, d2);
+          // pm = p + nint(g) + nint(dr + g - nint(g)); the sum of the two nints is exact (0, +-1, +-2) and converted once
+          const double a0 = nint_half(g0), a1 = nint_half(g1), a2 = nint_half(g2);
           const double t0 = dr0 + g0 - a0, t1 = dr1 + g1 - a1, t2 = dr2 + g2 - a2;
-          const double b0 = nint_bits(t0, e0), b1 = nint_bits(t1, e1), b2 = nint_bits(t2, e2);
+          const double b0 = nint_half(t0), b1 = nint_half(t1), b2 = nint_half(t2);
           dr0 = t0 - b0; dr1 = t1 - b1; dr2 = t2 - b2;
-          d0 += e0; d1 += e1; d2 += e2;
+          const int d0 = __double2int_rn(a0 + b0), d1 = __double2int_rn(a1 + b1), d2 = __double2int_rn(a2 + b2);
           if (inner) {
             x += d0; y += d1; z += d2;
             id += d0 + n1 * (d1 + n2 * d2);
@@ -1196,7 +1226,7 @@ __global__ void __launch_bounds__(256, 4) k_walk3(const __grid_constant__ BaderP
           // did not move although the gradient is not zero: k_walk_big (k_walk hands these over as well)
           if (id == oid) st = 3;
         }
-        rhomax = r0 > rhomax ? r0 : rhomax;  // known(p) = 1 (:484)
+        rhomax = r0;  // known(p) = 1 (:484): r0 > rhomax here, so the largest density on the path is r0
         first = false;
       }
       if (st) {
@@ -1507,8 +1537,9 @@ __global__ void __launch_bounds__(256) k_vsafe(int c1, int c2, int c3, int px, i
   }
 }
 
-// packed certificates of the stride-2 level (SafeMap::pack): out[v] = E[v] | flags << CERT_LBITS, where E is the octet
-// map of k_vsafe and flag (ix | iy << 1 | iz << 2) belongs to the point (2vx-1+ix, 2vy-1+iy, 2vz-1+iz).  The 5x5x5
+// packed certificates of the stride-2 level (SafeMap::pack): out[v] = E[v] | flags << CERT_LBITS (CERT_VOID where E[v]
+// is none), where E is the octet map of k_vsafe and flag (ox | oy << 1 | oz << 2) belongs to the point
+// (2vx - ox, 2vy - oy, 2vz - oz).  The 5x5x5
 // neighbourhood of an even coordinate 2v lies inside the octet of v; that of an odd coordinate 2v-1 needs the octets of
 // v-1 and v.  x, y, z wrap like in k_vsafe (px, py, pz); the vertices below the first owned layer of a z-slab do not exist.
 __global__ void __launch_bounds__(256) k_pack5(int c1, int c2, int c3, int px, int py, int pz, const int* __restrict__ E,
@@ -1529,20 +1560,20 @@ __global__ void __launch_bounds__(256) k_pack5(int c1, int c2, int c3, int px, i
 #pragma unroll
     for (int k = 0; k < 4; k++) cu[k] = col[k] ? __ldg(col[k] + s3 * vz) : -2;
     const int e0 = cu[0];
-    int res = -1;
+    int res = CERT_VOID;
     if (e0 >= 0) {
       // ok[m]: the vertex shifted down along the axes in m (1 = x, 2 = y, 4 = z) carries e0 as well
       const bool o1 = cu[1] == e0, o2 = cu[2] == e0, o3 = cu[3] == e0;
       const bool o4 = lo[0] == e0, o5 = lo[1] == e0, o6 = lo[2] == e0, o7 = lo[3] == e0;
-      // flag index: bit set = even coordinate 2v, clear = odd coordinate 2v-1 (needs the lower vertex along that axis)
-      int flags = 1 << 7;                                   // (even, even, even): the octet of v alone
-      flags |= (o1 ? 1 : 0) << 6;                           // x odd
-      flags |= (o2 ? 1 : 0) << 5;                           // y odd
-      flags |= ((o1 && o2 && o3) ? 1 : 0) << 4;             // x, y odd
-      flags |= (o4 ? 1 : 0) << 3;                           // z odd
-      flags |= ((o1 && o4 && o5) ? 1 : 0) << 2;             // x, z odd
-      flags |= ((o2 && o4 && o6) ? 1 : 0) << 1;             // y, z odd
-      flags |= ((o1 && o2 && o3 && o4 && o5 && o6 && o7) ? 1 : 0);  // x, y, z odd
+      // flag index (cert_flagbit): bit set = odd coordinate 2v-1 (needs the lower vertex along that axis)
+      int flags = 1;                                        // (even, even, even): the octet of v alone
+      flags |= (o1 ? 1 : 0) << 1;                           // x odd
+      flags |= (o2 ? 1 : 0) << 2;                           // y odd
+      flags |= ((o1 && o2 && o3) ? 1 : 0) << 3;             // x, y odd
+      flags |= (o4 ? 1 : 0) << 4;                           // z odd
+      flags |= ((o1 && o4 && o5) ? 1 : 0) << 5;             // x, z odd
+      flags |= ((o2 && o4 && o6) ? 1 : 0) << 6;             // y, z odd
+      flags |= ((o1 && o2 && o3 && o4 && o5 && o6 && o7) ? 1 : 0) << 7;  // x, y, z odd
       res = e0 | (flags << CERT_LBITS);
     }
     out[vx + (size_t)c1 * vy + s3 * vz] = res;
@@ -2125,7 +2156,8 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
   int* cnt = b_cnt.as<int>();
   unsigned long long* nsteps = (unsigned long long*)(cnt + 4);
   unsigned long long* cursor = (unsigned long long*)(cnt + 8);
-  int hcnt[16];
+  if (!ctx->hpin) C2G_CUDA(ctx, cudaHostAlloc((void**)&ctx->hpin, 64 * sizeof(int), cudaHostAllocDefault));
+  int* const hcnt = ctx->hpin;  // page-locked: the counter read-backs between the launches are plain DMA writes
   for (int attempt = 0;; attempt++) {
     C2G_CUDA(ctx, b_cand.alloc(ctx, sizeof(int) * (size_t)maxcand));
     C2G_CUDA(ctx, cudaMemsetAsync(cnt, 0, 64, st));
@@ -2327,16 +2359,24 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
     if (walk3_mask & cls) {
       // k_walk3: refill_min = idle threads of the block that trigger a pack + refill, steps_per_check = steps between two looks
       WA.refill_min = cls == 1 ? w3_idle : w3_idle_c; WA.steps_per_check = cls == 1 ? w3_k : w3_k_c;
+      const int certk = WA.sm.safe == nullptr ? 0 : ((WA.sm.pack && WA.sm.octet && WA.sm.shift == 1) ? 2 : 1);
+#define C2G_W3(O, F, T)                                                            \
+  do {                                                                             \
+    if (certk == 2) k_walk3<O, F, T, 2><<<blocks, 256, 0, st>>>(P, WA);            \
+    else if (certk == 1) k_walk3<O, F, T, 1><<<blocks, 256, 0, st>>>(P, WA);       \
+    else k_walk3<O, F, T, 0><<<blocks, 256, 0, st>>>(P, WA);                       \
+  } while (0)
       switch (variant) {
-        case 0: k_walk3<false, false, false><<<blocks, 256, 0, st>>>(P, WA); break;
-        case 1: k_walk3<false, false, true><<<blocks, 256, 0, st>>>(P, WA); break;
-        case 2: k_walk3<false, true, false><<<blocks, 256, 0, st>>>(P, WA); break;
-        case 3: k_walk3<false, true, true><<<blocks, 256, 0, st>>>(P, WA); break;
-        case 4: k_walk3<true, false, false><<<blocks, 256, 0, st>>>(P, WA); break;
-        case 5: k_walk3<true, false, true><<<blocks, 256, 0, st>>>(P, WA); break;
-        case 6: k_walk3<true, true, false><<<blocks, 256, 0, st>>>(P, WA); break;
-        default: k_walk3<true, true, true><<<blocks, 256, 0, st>>>(P, WA); break;
+        case 0: C2G_W3(false, false, false); break;
+        case 1: C2G_W3(false, false, true); break;
+        case 2: C2G_W3(false, true, false); break;
+        case 3: C2G_W3(false, true, true); break;
+        case 4: C2G_W3(true, false, false); break;
+        case 5: C2G_W3(true, false, true); break;
+        case 6: C2G_W3(true, true, false); break;
+        default: C2G_W3(true, true, true); break;
       }
+#undef C2G_W3
     } else if (!walk_old) {
       // k_walk2 refills idle lanes before every step once `refill_min` lanes are idle (default 1)
       WA.refill_min = 1;

@@ -224,6 +224,7 @@ void c2g_finalize(c2g_context* ctx) {
   for (void* p : ctx->deferred) c2g_release(ctx, p);
   ctx->deferred.clear();
   c2g_fft_free_plans(ctx);
+  if (ctx->hpin) { cudaFreeHost(ctx->hpin); ctx->hpin = nullptr; }
   for (auto& g : ctx->grids) {
     if (g.ready) cudaEventDestroy(g.ready);
     if (g.used && g.d) c2g_release(ctx, g.d);

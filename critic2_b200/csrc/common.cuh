@@ -61,6 +61,8 @@ struct c2g_context {
   cudaEvent_t ev_order = nullptr;
   std::vector<void*> deferred;  // device blocks still read by copy_out: released by c2g_synchronize
   void* fft_cache = nullptr;    // cuFFT plans per grid shape (fft.cu)
+  int* hpin = nullptr;          // page-locked scratch (64 ints) for the small counter read-backs between launches:
+                                // a copy into pageable memory is staged by the driver and costs tens of microseconds more
   // device-memory cache (c2g_alloc / c2g_release below)
   std::multimap<size_t, void*> mem_free;           // size -> cached block
   std::unordered_map<void*, size_t> mem_live;      // block handed out -> its size
