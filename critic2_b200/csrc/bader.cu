@@ -657,7 +657,8 @@ struct WalkArgs {
   const int* list;          // nullptr: lattice mode; otherwise the dense list of every walker so far
   long long flat_base;      // flat mode: items are list[flat_base .. flat_base + count)
   long long count;
-  const int* count_dev;     // k_walk2: non-null = the number of entries is read from device memory (no host round trip)
+  const int* count_dev;     // k_walk2 / k_walk3: non-null = the number of entries is read from device memory (no host round trip)
+  const int* base_dev;      // k_walk3: non-null = flat_base is read from device memory as well
   int* stop;                // stop log parallel to `list`: where a walk was cut short (stop code), or -1
   int sm_level;             // level index of `sm` (goes into the stop code)
   SafeMap maps[MAXLEV];     // FIX: every early-termination map in use, for invalidation
@@ -1057,9 +1058,9 @@ __global__ void __launch_bounds__(256, 4) k_walk3(const __grid_constant__ BaderP
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int n1 = P.n1, n2 = P.n2, n3 = P.n3;
   const int s2 = n1, s3 = n1 * n2;
-  const int total = (int)A.count;                  // < 2^31: the lists hold at most nn entries
-  const int* const list = A.list ? A.list + A.flat_base : nullptr;
-  const int tbase = (int)A.flat_base;
+  const int total = A.count_dev ? __ldg(A.count_dev) : (int)A.count;  // < 2^31: the lists hold at most nn entries
+  const int tbase = A.base_dev ? __ldg(A.base_dev) : (int)A.flat_base;
+  const int* const list = A.list ? A.list + tbase : nullptr;
   unsigned* const cur32 = reinterpret_cast<unsigned*>(A.cursor);  // low word of the (zeroed) 64-bit cursor
   bool active = false, first = true, exhausted = false;           // exhausted: block-uniform
   int id = 0, x = 0, y = 0, z = 0, start = 0, tidx = -1, oldlab = 0;
@@ -1270,7 +1271,10 @@ __global__ void __launch_bounds__(256) k_items_count(int nseg, int batch, const 
   block_excl_scan_256(c, s_warp, te);
   if (threadIdx.x == 0) blocksum[blockIdx.x] = make_int2(ti, te);
 }
-__global__ void __launch_bounds__(256) k_items_scan(int nblk, int2* __restrict__ blocksum, int* __restrict__ nitems, int* __restrict__ nentries) {
+// doff (optional): entries of the dense walker list in use, in device memory; a list that would overflow (capacity dcap)
+// raises err = 5 and hands out nothing
+__global__ void __launch_bounds__(256) k_items_scan(int nblk, int2* __restrict__ blocksum, int* __restrict__ nitems, int* __restrict__ nentries,
+                                                    const int* __restrict__ doff, long long dcap, int* __restrict__ err) {
   __shared__ int s_warp[8];
   int ci = 0, ce = 0;
   for (int i0 = 0; i0 < nblk; i0 += 256) {
@@ -1282,14 +1286,22 @@ __global__ void __launch_bounds__(256) k_items_scan(int nblk, int2* __restrict__
     if (i < nblk) blocksum[i] = make_int2(ci + ei, ce + ee);
     ci += ti; ce += te;
   }
-  if (threadIdx.x == 0) { *nitems = ci; *nentries = ce; }
+  if (threadIdx.x == 0) {
+    if (doff && (long long)*doff + ce > dcap) { atomicExch(err, 5); ci = 0; ce = 0; }
+    *nitems = ci; *nentries = ce;
+  }
 }
 // writes the items and copies the entries of the segments, in segment order, into the dense list at dbase
 __global__ void __launch_bounds__(256) k_items_write(int nseg, int segcap, int batch, const int* __restrict__ segcnt,
                                                      const int2* __restrict__ blocksum, const int* __restrict__ seglist,
-                                                     int2* __restrict__ items, int* __restrict__ dlist, long long dbase) {
+                                                     int2* __restrict__ items, int* __restrict__ dlist, long long dbase,
+                                                     const int* __restrict__ doff, const int* __restrict__ nentries) {
   __shared__ int s_warp[8];
   __shared__ int s_c[256], s_e[256];
+  if (doff) {  // offsets in device memory (no host round trip): nothing to do when nothing was queued or the list is full
+    if (*nentries == 0) return;
+    dbase = *doff;
+  }
   const int b = blockIdx.x * 256 + threadIdx.x;
   const int c = b < nseg ? segcnt[b] : 0;
   const int k = (c + batch - 1) / batch;
@@ -1297,7 +1309,8 @@ __global__ void __launch_bounds__(256) k_items_write(int nseg, int segcap, int b
   const int2 bs = blocksum[blockIdx.x];
   const int ibase = bs.x + block_excl_scan_256(k, s_warp, total);
   const int ebase = bs.y + block_excl_scan_256(c, s_warp, total);
-  for (int j = 0; j < k; j++) items[ibase + j] = make_int2((int)(dbase + ebase + j * batch), min(batch, c - j * batch));
+  if (items)  // k_walk3 walks the dense list itself and needs no items
+    for (int j = 0; j < k; j++) items[ibase + j] = make_int2((int)(dbase + ebase + j * batch), min(batch, c - j * batch));
   s_c[threadIdx.x] = c; s_e[threadIdx.x] = ebase;
   __syncthreads();
   if (total == 0) return;
@@ -1310,10 +1323,54 @@ __global__ void __launch_bounds__(256) k_items_write(int nseg, int segcap, int b
   }
 }
 
+// ---- device-side bookkeeping of the assignment: with these the host enqueues a whole level (classification, list
+// compaction, walkers, hand-over walks) without reading a single counter back ----
+// counter layout (ints); [0..12] as documented in c2g_bader_assign
+constexpr int C_NLIST = 1, C_NOVER = 2, C_ERR = 3, C_NNEXT = 7, C_NITEMS = 10, C_NINVAL = 11, C_NENT = 12, C_DOFF = 13, C_BIGCUR = 14,
+              C_WALKED = 15, C_INVSEEN = 16, C_FIXPTS = 17, C_OVERTOT = 18, C_FLATN = 19, C_NPASS = 20, C_NCNT = 64;
+// a flat list (edge-fix passes) -> the end of the dense list; its length is read from device memory
+__global__ void __launch_bounds__(256) k_items_flat(const int* __restrict__ src, int* __restrict__ cnt, long long dcap, int* __restrict__ dlist) {
+  const int count = cnt[C_FLATN], dbase = cnt[C_DOFF];
+  const bool full = (long long)dbase + count > dcap;
+  const long long stride = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (!full)
+    for (long long e = t0; e < count; e += stride) dlist[dbase + e] = src[e];
+  // the counters are read by every block above: they are written by the single-thread kernel that follows
+}
+__global__ void k_items_flat_end(int* __restrict__ cnt, long long dcap) {
+  const int count = cnt[C_FLATN], dbase = cnt[C_DOFF];
+  const bool full = (long long)dbase + count > dcap;
+  if (full) atomicExch(cnt + C_ERR, 5);
+  cnt[C_NENT] = full ? 0 : count;
+}
+// end of a group of walker launches: their entries now belong to the dense list; the hand-over list is empty again
+__global__ void k_walk_end(int* __restrict__ cnt, int fix) {
+  const int ne = cnt[C_NENT];
+  cnt[C_DOFF] += ne;
+  cnt[C_WALKED] += ne;
+  if (fix) cnt[C_FIXPTS] += ne;
+  cnt[C_NENT] = 0; cnt[C_NITEMS] = 0;
+  cnt[C_OVERTOT] += cnt[C_NOVER];
+  cnt[C_NOVER] = 0; cnt[C_BIGCUR] = 0;
+  cnt[8] = 0; cnt[9] = 0;  // work cursor
+}
+// start of an edge-fix pass: the list built by the previous pass is consumed, a new one is started
+__global__ void k_fix_begin(int* __restrict__ cnt, int first) {
+  const int n = cnt[C_NNEXT];
+  cnt[C_FLATN] = n;
+  cnt[C_NNEXT] = 0;
+  if (n + (first ? cnt[C_NLIST] : 0) > 0) cnt[C_NPASS] += 1;
+}
+__global__ void k_requeue_end(int* __restrict__ cnt) { cnt[C_INVSEEN] = cnt[C_NINVAL]; }
+
 // re-queue the walkers whose early stop rested on a certificate that has been invalidated since
 __global__ void __launch_bounds__(256) k_requeue(long long ntotal, const int* __restrict__ dlist, int* __restrict__ stop,
                                                  const __grid_constant__ WalkArgs A, int* __restrict__ out, int* __restrict__ nout,
-                                                 int outcap) {
+                                                 int outcap, const int* __restrict__ cnt) {
+  if (cnt) {  // device-side gate: nothing to do unless a certificate was voided since the last pass
+    if (cnt[C_INVSEEN] == cnt[C_NINVAL]) return;
+    ntotal = cnt[C_DOFF];
+  }
   const int lane = threadIdx.x & 31;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long t0 = (long long)blockIdx.x * blockDim.x; t0 < ntotal; t0 += stride) {
@@ -1359,6 +1416,29 @@ __global__ void __launch_bounds__(64) k_walk_big(const __grid_constant__ BaderPa
   if (A.nsteps) atomicAdd(A.nsteps, (unsigned long long)w.len);
   if (st == 3) { atomicExch(A.err, 2); return; }
   walk_finish<FIX>(P, A, start, st, out, tidx, sli, oldlab);
+}
+
+// The same walks with the number of hand-overs read from device memory: a fixed grid takes them one by one through a
+// cursor, every thread owns a path buffer of `bigcap` entries.
+template <bool FIX>
+__global__ void __launch_bounds__(64) k_walk_big2(const __grid_constant__ BaderParams P, const __grid_constant__ WalkArgs A,
+                                                  int* __restrict__ cnt, int* __restrict__ scratch, int bigcap) {
+  const int nov = min(cnt[C_NOVER], A.overcap);
+  if (nov == 0) return;
+  int* path = scratch + (size_t)(blockIdx.x * blockDim.x + threadIdx.x) * bigcap;
+  const SafeMap nosafe{nullptr, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int t = atomicAdd(cnt + C_BIGCUR, 1); t < nov; t = atomicAdd(cnt + C_BIGCUR, 1)) {
+    const int start = A.overflow[t].x, tidx = A.overflow[t].y;
+    WState w;
+    walk_init(P, A.rho, w, start);
+    const SafeMap& sm = (tidx >= 0 && A.stop) ? A.sm : nosafe;  // no stop log, no early stop
+    const int oldlab = FIX ? (A.label_g[start] & LMASK) : 0;
+    int out = 0, st, sli = -1;
+    do st = walk_step<false>(P, A.rho, A.h, sm, w, path, bigcap, out, sli); while (st == 0);
+    if (A.nsteps) atomicAdd(A.nsteps, (unsigned long long)w.len);
+    if (st == 3) { atomicExch(A.err, 2); continue; }
+    walk_finish<FIX>(P, A, start, st, out, tidx, sli, oldlab);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2150,7 +2230,7 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
   // ---- K0: candidate maxima of the slab ----
   DevBuf b_cand, b_cnt;
   int maxcand = (int)std::max<long long>(1, std::min<long long>(nnl, std::max<long long>(1 << 16, nnl / 64)));
-  C2G_CUDA(ctx, b_cnt.alloc(ctx, 64));
+  C2G_CUDA(ctx, b_cnt.alloc(ctx, C_NCNT * sizeof(int)));
   // counters: [0] ncand, [1] nlist, [2] noverflow, [3] err ; [4..5] nsteps (u64) ; [6] scratch for collectives,
   //           [7] nnext ; [8..9] work cursor (u64) ; [10] number of work items
   int* cnt = b_cnt.as<int>();
@@ -2160,7 +2240,7 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
   int* const hcnt = ctx->hpin;  // page-locked: the counter read-backs between the launches are plain DMA writes
   for (int attempt = 0;; attempt++) {
     C2G_CUDA(ctx, b_cand.alloc(ctx, sizeof(int) * (size_t)maxcand));
-    C2G_CUDA(ctx, cudaMemsetAsync(cnt, 0, 64, st));
+    C2G_CUDA(ctx, cudaMemsetAsync(cnt, 0, C_NCNT * sizeof(int), st));
     for (int i = 0; i < CF.nlev; i++) C2G_CUDA(ctx, cudaMemsetAsync(CF.p[i], 0, lev[i].nc, st));
     if (S.nzl > 0) {
       dim3 grid((n1 + 255) / 256, n2, (S.nzl + MZC - 1) / MZC);
@@ -2172,7 +2252,7 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
       ctx->prof_end();
       C2G_KERNEL_CHECK(ctx);
     }
-    C2G_CUDA(ctx, cudaMemcpyAsync(hcnt, cnt, 64, cudaMemcpyDeviceToHost, st));
+    C2G_CUDA(ctx, cudaMemcpyAsync(hcnt, cnt, C_NCNT * sizeof(int), cudaMemcpyDeviceToHost, st));
     C2G_CUDA(ctx, cudaStreamSynchronize(st));
     if (hcnt[0] <= maxcand) break;
     if (attempt > 0) return ctx->fail(C2G_ERR_OVERFLOW, "candidate maxima list overflow");
@@ -2311,6 +2391,17 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
   if (const char* e = getenv("C2G_W3_IDLEC")) w3_idle_c = std::max(1, std::min(256, atoi(e)));
   if (const char* e = getenv("C2G_W3_KC")) w3_k_c = std::max(1, std::min(64, atoi(e)));
 
+  // Device-side bookkeeping (default): the host enqueues whole levels without reading a counter back -- list lengths,
+  // the fill of the dense walker list and the hand-over walks are handled by k_items_*, k_walk_end and k_walk_big2 from
+  // counters in device memory; the host synchronises once for the candidate maxima, then only in the edge-fix loop
+  // (after the second pass and after every later one) and at the end.  C2G_SYNC_LEVELS=1, the per-level statistics of
+  // C2G_BADER_VERBOSE and the older walker kernels keep the host-driven flow (a read-back after every launch group).
+  const bool verbose = getenv("C2G_BADER_VERBOSE") != nullptr;
+  const bool async = algo != C2G_BADER_EXACT && walk3_mask == 15 && !verbose && getenv("C2G_SYNC_LEVELS") == nullptr;
+  const int bigcap2 = (int)std::min<long long>(g.nn, 1 << 16), bigthreads2 = 16 * 64;
+  DevBuf b_bigscr;
+  if (async) C2G_CUDA(ctx, b_bigscr.alloc(ctx, sizeof(int) * (size_t)bigthreads2 * bigcap2));
+
   auto check_err = [&]() -> int {
     switch (hcnt[3]) {
       case 0: return C2G_OK;
@@ -2322,7 +2413,16 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
   };
   // read the counters; re-walk the trajectories whose path buffer overflowed
   auto drain = [&](bool fix) -> int {
-    C2G_CUDA(ctx, cudaMemcpyAsync(hcnt, cnt, 64, cudaMemcpyDeviceToHost, st));
+    if (async) {
+      ctx->prof_begin("bader_walk_big");
+      if (fix) k_walk_big2<true><<<bigthreads2 / 64, 64, 0, st>>>(P, WA, cnt, b_bigscr.as<int>(), bigcap2);
+      else k_walk_big2<false><<<bigthreads2 / 64, 64, 0, st>>>(P, WA, cnt, b_bigscr.as<int>(), bigcap2);
+      k_walk_end<<<1, 1, 0, st>>>(cnt, fix ? 1 : 0);
+      ctx->prof_end(2);
+      C2G_KERNEL_CHECK(ctx);
+      return C2G_OK;
+    }
+    C2G_CUDA(ctx, cudaMemcpyAsync(hcnt, cnt, C_NCNT * sizeof(int), cudaMemcpyDeviceToHost, st));
     C2G_CUDA(ctx, cudaStreamSynchronize(st));
     int rc = check_err();
     if (rc) return rc;
@@ -2344,14 +2444,14 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
       C2G_KERNEL_CHECK(ctx);
     }
     C2G_CUDA(ctx, cudaMemsetAsync(cnt + 2, 0, sizeof(int), st));
-    C2G_CUDA(ctx, cudaMemcpyAsync(hcnt, cnt, 64, cudaMemcpyDeviceToHost, st));
+    C2G_CUDA(ctx, cudaMemcpyAsync(hcnt, cnt, C_NCNT * sizeof(int), cudaMemcpyDeviceToHost, st));
     C2G_CUDA(ctx, cudaStreamSynchronize(st));
     hcnt[2] = 0;
     return check_err();
   };
   auto launch_walk = [&](long long count, bool fix, const char* name) -> int {
     C2G_CUDA(ctx, cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), st));
-    const int blocks = (int)std::min<long long>(wblocks, (count + 255) / 256);
+    const int blocks = WA.count_dev ? wblocks : (int)std::min<long long>(wblocks, (count + 255) / 256);
     ctx->prof_begin(name);
     const int variant = (ortho ? 4 : 0) | (fix ? 2 : 0) | (walk_stats ? 1 : 0);
     // launch class: 8 = top lattice, 4 = coarse levels, 1 = last level, 2 = edge fix (bits of C2G_WALK3)
@@ -2404,13 +2504,14 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
     }
     ctx->prof_end();
     C2G_KERNEL_CHECK(ctx);
-    walked += count;
+    if (!WA.count_dev) walked += count;  // otherwise counted on the device (C_WALKED)
     return C2G_OK;
   };
   // walkers over the stride-lat_s lattice of the slab (complete trajectories, nothing logged)
   auto walk_lattice = [&](long long count, int lat_s, const char* name) -> int {
     if (count <= 0) return C2G_OK;
     WA.list = nullptr; WA.stop = nullptr; WA.items = nullptr; WA.nitems = 0; WA.flat_base = 0; WA.count = count;
+    WA.count_dev = nullptr; WA.base_dev = nullptr;
     WA.sm = SafeMap{nullptr, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; WA.sm_level = 0;
     WA.refill_min = lat_s == 1 ? refill_fine : refill_coarse;
     WA.steps_per_check = lat_s == 1 ? spc_fine : spc_coarse;
@@ -2423,6 +2524,27 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
   // walkers over a segmented list: its entries are first copied, in segment order, to the end of the dense list
   auto walk_segments = [&](const int* seglist, const int* segcnt, int nseg, int segcap, long long count, bool fix, int* next,
                            const SafeMap& sm, int sm_level, const char* name) -> int {
+    if (async) {  // lengths and offsets stay on the device; a full dense list raises err = 5 there
+      const int nblk = c2g_blocks_for(nseg, 256);
+      if ((size_t)nblk > blksumcap) {
+        blksumcap = (size_t)nblk;
+        C2G_CUDA(ctx, b_blksum.alloc(ctx, sizeof(int2) * blksumcap));
+      }
+      k_items_count<<<nblk, 256, 0, st>>>(nseg, 64, segcnt, b_blksum.as<int2>());
+      k_items_scan<<<1, 256, 0, st>>>(nblk, b_blksum.as<int2>(), cnt + C_NITEMS, cnt + C_NENT, cnt + C_DOFF, dcap, cnt + C_ERR);
+      k_items_write<<<nblk, 256, 0, st>>>(nseg, segcap, 64, segcnt, b_blksum.as<int2>(), seglist, nullptr, b_dlist.as<int>(), 0,
+                                          cnt + C_DOFF, cnt + C_NENT);
+      C2G_KERNEL_CHECK(ctx);
+      ctx->launches += 3;
+      WA.list = b_dlist.as<int>(); WA.stop = b_stop.as<int>(); WA.flat_base = 0; WA.count = 0;
+      WA.count_dev = cnt + C_NENT; WA.base_dev = cnt + C_DOFF;
+      WA.items = nullptr; WA.nitems = 0; WA.nitems_dev = cnt + C_NITEMS;
+      WA.sm = sm; WA.sm_level = sm_level; WA.lat_s = 1; WA.lat_m1 = n1; WA.lat_m2 = n2;
+      WA.next = next; WA.nextcap = (int)std::min<long long>(listcap, 0x7fffffff);
+      WA.batch = 64;
+      return launch_walk(0, fix, name);
+    }
+    WA.count_dev = nullptr; WA.base_dev = nullptr;
     if (count <= 0) return C2G_OK;
     if (doff + count > dcap) return ctx->fail(C2G_ERR_OVERFLOW, "walker list overflow");
     int batch = count < 64ll * wblocks * 8 ? 32 : 64;
@@ -2438,9 +2560,9 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
       C2G_CUDA(ctx, b_blksum.alloc(ctx, sizeof(int2) * blksumcap));
     }
     k_items_count<<<nblk, 256, 0, st>>>(nseg, batch, segcnt, b_blksum.as<int2>());
-    k_items_scan<<<1, 256, 0, st>>>(nblk, b_blksum.as<int2>(), cnt + 10, cnt + 12);
+    k_items_scan<<<1, 256, 0, st>>>(nblk, b_blksum.as<int2>(), cnt + 10, cnt + 12, nullptr, 0, nullptr);
     k_items_write<<<nblk, 256, 0, st>>>(nseg, segcap, batch, segcnt, b_blksum.as<int2>(), seglist, b_items.as<int2>(),
-                                        b_dlist.as<int>(), doff);
+                                        b_dlist.as<int>(), doff, nullptr, nullptr);
     C2G_KERNEL_CHECK(ctx);
     ctx->launches += 3;
     WA.list = b_dlist.as<int>(); WA.stop = b_stop.as<int>(); WA.flat_base = doff; WA.count = count;
@@ -2456,6 +2578,20 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
   };
   // walkers over a flat list (edge-fix passes): copied to the end of the dense list as well
   auto walk_flat = [&](const int* list, long long count, bool fix, int* next, const SafeMap& sm, int sm_level, const char* name) -> int {
+    if (async) {  // the list length is cnt[C_FLATN] (k_fix_begin)
+      k_items_flat<<<ctx->nsm * 4, 256, 0, st>>>(list, cnt, dcap, b_dlist.as<int>());
+      k_items_flat_end<<<1, 1, 0, st>>>(cnt, dcap);
+      C2G_KERNEL_CHECK(ctx);
+      ctx->launches += 2;
+      WA.list = b_dlist.as<int>(); WA.stop = b_stop.as<int>(); WA.flat_base = 0; WA.count = 0;
+      WA.count_dev = cnt + C_NENT; WA.base_dev = cnt + C_DOFF;
+      WA.items = nullptr; WA.nitems = 0;
+      WA.sm = sm; WA.sm_level = sm_level; WA.lat_s = 1; WA.lat_m1 = n1; WA.lat_m2 = n2;
+      WA.next = next; WA.nextcap = (int)std::min<long long>(listcap, 0x7fffffff);
+      WA.batch = 32;
+      return launch_walk(0, fix, name);
+    }
+    WA.count_dev = nullptr; WA.base_dev = nullptr;
     if (count <= 0) return C2G_OK;
     if (doff + count > dcap) return ctx->fail(C2G_ERR_OVERFLOW, "walker list overflow");
     C2G_CUDA(ctx, cudaMemcpyAsync(b_dlist.as<int>() + doff, list, sizeof(int) * (size_t)count, cudaMemcpyDeviceToDevice, st));
@@ -2496,7 +2632,6 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
     // 3 of 7.1e6 points in tests/sized_cases.py hetero192; kept for measurements only)
     int cert = 1;
     if (const char* e = getenv("C2G_CERT")) cert = atoi(e);
-    const bool verbose = getenv("C2G_BADER_VERBOSE") != nullptr;
     unsigned long long steps_prev = 0;
     auto report = [&](const char* what, long long count) {
       if (!verbose) return;
@@ -2558,9 +2693,12 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
         }
       }
       WA.maps[i] = sm;
-      C2G_CUDA(ctx, cudaMemcpyAsync(hcnt, cnt, 64, cudaMemcpyDeviceToHost, st));
-      C2G_CUDA(ctx, cudaStreamSynchronize(st));
-      const long long nw = hcnt[1];
+      long long nw = 1;  // device-side bookkeeping: the count stays in cnt[C_NLIST] / segcnt
+      if (!async) {
+        C2G_CUDA(ctx, cudaMemcpyAsync(hcnt, cnt, C_NCNT * sizeof(int), cudaMemcpyDeviceToHost, st));
+        C2G_CUDA(ctx, cudaStreamSynchronize(st));
+        nw = hcnt[1];
+      }
       if ((rc = walk_segments(seglist, segcnt, ntile, CLS_SEGCAP, nw, false, nullptr, sm, i, wname[i])) != C2G_OK) return rc;
       if ((rc = drain(false)) != C2G_OK) return rc;
       report(wname[i], nw);
@@ -2626,8 +2764,55 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
     // list the filled neighbours of the points that changed and the walkers whose certificate was voided.
     bool first = true;
     int ninval_seen = 0;
+    if (async) {
+      // Passes 1 and 2 are enqueued without looking at the counters (an empty pass costs a few empty launches); from then
+      // on the host reads the length of the list the last pass built and stops when it is empty on every rank.
+      for (int pass = 0;; pass++) {
+        if (pass >= 2) {
+          C2G_CUDA(ctx, cudaMemcpyAsync(hcnt, cnt, C_NCNT * sizeof(int), cudaMemcpyDeviceToHost, st));
+          C2G_CUDA(ctx, cudaStreamSynchronize(st));
+          if ((rc = check_err()) != C2G_OK) return rc;
+          int any = hcnt[C_NNEXT] > 0 ? 1 : 0;
+          if (G > 1) {
+            C2G_CUDA(ctx, cudaMemcpyAsync(cnt + 6, &any, sizeof(int), cudaMemcpyHostToDevice, st));
+            C2G_NCCL(ctx, ncclAllReduce(cnt + 6, cnt + 6, 1, ncclInt32, ncclMax, comm, st));
+            C2G_CUDA(ctx, cudaMemcpyAsync(&any, cnt + 6, sizeof(int), cudaMemcpyDeviceToHost, st));
+            C2G_CUDA(ctx, cudaStreamSynchronize(st));
+          }
+          if (any == 0) break;
+        }
+        int* in = b_list[cur].as<int>();
+        int* out = b_list[cur == 1 ? 2 : 1].as<int>();
+        k_fix_begin<<<1, 1, 0, st>>>(cnt, first ? 1 : 0);
+        ctx->launches += 1;
+        if (first) {
+          if ((rc = walk_segments(seglist, segcnt, nfeseg, fesegcap, 1, true, out, fixsafe, 0, "bader_walk_fix")) != C2G_OK) return rc;
+          if ((rc = drain(true)) != C2G_OK) return rc;
+        }
+        if ((rc = walk_flat(in, 1, true, out, fixsafe, 0, "bader_walk_fix")) != C2G_OK) return rc;
+        if ((rc = drain(true)) != C2G_OK) return rc;
+        // walkers whose certificate has been voided since the last pass go back into the list (gated on the device)
+        ctx->prof_begin("bader_requeue");
+        k_requeue<<<ctx->nsm * 8, 256, 0, st>>>(0, b_dlist.as<int>(), b_stop.as<int>(), WA, out, cnt + C_NNEXT,
+                                                 (int)std::min<long long>(listcap, 0x7fffffff), cnt);
+        k_requeue_end<<<1, 1, 0, st>>>(cnt);
+        ctx->prof_end(2);
+        C2G_KERNEL_CHECK(ctx);
+        if (G > 1) {
+          if ((rc = exchange_halos(ctx, lbuf, plane, S, 3)) != C2G_OK) return rc;
+          if (nnl > 0 && (rc = edge_faces(out, cnt + 7)) != C2G_OK) return rc;
+        }
+        cur = (cur == 1) ? 2 : 1;
+        first = false;
+        if (pass > 100000) return ctx->fail(C2G_ERR_STATE, "edge refinement did not converge");
+      }
+      fixpasses = hcnt[C_NPASS] + 1;
+      fixpts = hcnt[C_FIXPTS];
+      walked += hcnt[C_WALKED];
+      noverflow_total = hcnt[C_OVERTOT];
+    } else
     for (;;) {
-      C2G_CUDA(ctx, cudaMemcpyAsync(hcnt, cnt, 64, cudaMemcpyDeviceToHost, st));
+      C2G_CUDA(ctx, cudaMemcpyAsync(hcnt, cnt, C_NCNT * sizeof(int), cudaMemcpyDeviceToHost, st));
       C2G_CUDA(ctx, cudaStreamSynchronize(st));
       if ((rc = check_err()) != C2G_OK) return rc;
       const int nseg1 = first ? hcnt[1] : 0, nflat = hcnt[7];
@@ -2652,7 +2837,7 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
         ninval_seen = hcnt[11];
         ctx->prof_begin("bader_requeue");
         k_requeue<<<ctx->nsm * 8, 256, 0, st>>>(doff, b_dlist.as<int>(), b_stop.as<int>(), WA, out, cnt + 7,
-                                                 (int)std::min<long long>(listcap, 0x7fffffff));
+                                                 (int)std::min<long long>(listcap, 0x7fffffff), nullptr);
         ctx->prof_end();
         C2G_KERNEL_CHECK(ctx);
       }
@@ -2671,7 +2856,7 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
   if (G > 1) C2G_NCCL(ctx, ncclAllReduce(reached, reached, ncand, ncclUint8, ncclMax, comm, st));
   std::vector<unsigned char> hreached(ncand);
   C2G_CUDA(ctx, cudaMemcpyAsync(hreached.data(), reached, ncand, cudaMemcpyDeviceToHost, st));
-  C2G_CUDA(ctx, cudaMemcpyAsync(hcnt, cnt, 64, cudaMemcpyDeviceToHost, st));
+  C2G_CUDA(ctx, cudaMemcpyAsync(hcnt, cnt, C_NCNT * sizeof(int), cudaMemcpyDeviceToHost, st));
   C2G_CUDA(ctx, cudaStreamSynchronize(st));
   if ((rc = check_err()) != C2G_OK) return rc;
   std::vector<int> cand2out(ncand, -1);

@@ -38,11 +38,9 @@ struct CufftApi {
   decltype(&cufftMakePlan3d) MakePlan3d = nullptr;
   decltype(&cufftSetWorkArea) SetWorkArea = nullptr;
 };
-CufftApi& cufft_api() {
-  static CufftApi api;
-  static bool tried = false;
-  if (tried) return api;
-  tried = true;
+// loaded once; thread-safe (a multi-device context calls this from one host thread per device at the same time)
+static CufftApi cufft_load() {
+  CufftApi api;
   void* h = dlopen("libcufft.so.11", RTLD_NOW | RTLD_GLOBAL);
   if (!h) h = dlopen("libcufft.so", RTLD_NOW | RTLD_GLOBAL);
   if (!h) h = dlopen("/usr/local/cuda/lib64/libcufft.so.11", RTLD_NOW | RTLD_GLOBAL);
@@ -62,6 +60,10 @@ CufftApi& cufft_api() {
   LOADSYM(SetWorkArea, "cufftSetWorkArea")
 #undef LOADSYM
   api.ok = true;
+  return api;
+}
+CufftApi& cufft_api() {
+  static CufftApi api = cufft_load();  // C++11: initialised exactly once, other threads wait
   return api;
 }
 
