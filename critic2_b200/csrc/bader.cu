@@ -2241,7 +2241,9 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
   for (int attempt = 0;; attempt++) {
     C2G_CUDA(ctx, b_cand.alloc(ctx, sizeof(int) * (size_t)maxcand));
     C2G_CUDA(ctx, cudaMemsetAsync(cnt, 0, C_NCNT * sizeof(int), st));
+    ctx->prof_begin("bader_clear_flags");
     for (int i = 0; i < CF.nlev; i++) C2G_CUDA(ctx, cudaMemsetAsync(CF.p[i], 0, lev[i].nc, st));
+    ctx->prof_end(CF.nlev);
     if (S.nzl > 0) {
       dim3 grid((n1 + 255) / 256, n2, (S.nzl + MZC - 1) / MZC);
       ctx->prof_begin("bader_maxima");
@@ -2530,12 +2532,13 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
         blksumcap = (size_t)nblk;
         C2G_CUDA(ctx, b_blksum.alloc(ctx, sizeof(int2) * blksumcap));
       }
+      ctx->prof_begin("bader_items");
       k_items_count<<<nblk, 256, 0, st>>>(nseg, 64, segcnt, b_blksum.as<int2>());
       k_items_scan<<<1, 256, 0, st>>>(nblk, b_blksum.as<int2>(), cnt + C_NITEMS, cnt + C_NENT, cnt + C_DOFF, dcap, cnt + C_ERR);
       k_items_write<<<nblk, 256, 0, st>>>(nseg, segcap, 64, segcnt, b_blksum.as<int2>(), seglist, nullptr, b_dlist.as<int>(), 0,
                                           cnt + C_DOFF, cnt + C_NENT);
+      ctx->prof_end(3);
       C2G_KERNEL_CHECK(ctx);
-      ctx->launches += 3;
       WA.list = b_dlist.as<int>(); WA.stop = b_stop.as<int>(); WA.flat_base = 0; WA.count = 0;
       WA.count_dev = cnt + C_NENT; WA.base_dev = cnt + C_DOFF;
       WA.items = nullptr; WA.nitems = 0; WA.nitems_dev = cnt + C_NITEMS;
@@ -2559,12 +2562,13 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
       blksumcap = (size_t)nblk;
       C2G_CUDA(ctx, b_blksum.alloc(ctx, sizeof(int2) * blksumcap));
     }
+    ctx->prof_begin("bader_items");
     k_items_count<<<nblk, 256, 0, st>>>(nseg, batch, segcnt, b_blksum.as<int2>());
     k_items_scan<<<1, 256, 0, st>>>(nblk, b_blksum.as<int2>(), cnt + 10, cnt + 12, nullptr, 0, nullptr);
     k_items_write<<<nblk, 256, 0, st>>>(nseg, segcap, batch, segcnt, b_blksum.as<int2>(), seglist, b_items.as<int2>(),
                                         b_dlist.as<int>(), doff, nullptr, nullptr);
+    ctx->prof_end(3);
     C2G_KERNEL_CHECK(ctx);
-    ctx->launches += 3;
     WA.list = b_dlist.as<int>(); WA.stop = b_stop.as<int>(); WA.flat_base = doff; WA.count = count;
     WA.items = b_items.as<int2>(); WA.nitems = (int)std::min<size_t>(maxitems, 0x7fffffff); WA.nitems_dev = cnt + 10;
     WA.sm = sm; WA.sm_level = sm_level; WA.lat_s = 1; WA.lat_m1 = n1; WA.lat_m2 = n2;
@@ -2579,10 +2583,11 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
   // walkers over a flat list (edge-fix passes): copied to the end of the dense list as well
   auto walk_flat = [&](const int* list, long long count, bool fix, int* next, const SafeMap& sm, int sm_level, const char* name) -> int {
     if (async) {  // the list length is cnt[C_FLATN] (k_fix_begin)
+      ctx->prof_begin("bader_items");
       k_items_flat<<<ctx->nsm * 4, 256, 0, st>>>(list, cnt, dcap, b_dlist.as<int>());
       k_items_flat_end<<<1, 1, 0, st>>>(cnt, dcap);
+      ctx->prof_end(2);
       C2G_KERNEL_CHECK(ctx);
-      ctx->launches += 2;
       WA.list = b_dlist.as<int>(); WA.stop = b_stop.as<int>(); WA.flat_base = 0; WA.count = 0;
       WA.count_dev = cnt + C_NENT; WA.base_dev = cnt + C_DOFF;
       WA.items = nullptr; WA.nitems = 0;
@@ -2771,14 +2776,17 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
         if (pass >= 2) {
           C2G_CUDA(ctx, cudaMemcpyAsync(hcnt, cnt, C_NCNT * sizeof(int), cudaMemcpyDeviceToHost, st));
           C2G_CUDA(ctx, cudaStreamSynchronize(st));
-          if ((rc = check_err()) != C2G_OK) return rc;
-          int any = hcnt[C_NNEXT] > 0 ? 1 : 0;
+          // a rank that failed must not leave the others waiting in the next collective: the error flag travels with
+          // the "any work left" reduction (2 = some rank failed) and every rank returns
+          int any = hcnt[3] != 0 ? 2 : (hcnt[C_NNEXT] > 0 ? 1 : 0);
           if (G > 1) {
             C2G_CUDA(ctx, cudaMemcpyAsync(cnt + 6, &any, sizeof(int), cudaMemcpyHostToDevice, st));
             C2G_NCCL(ctx, ncclAllReduce(cnt + 6, cnt + 6, 1, ncclInt32, ncclMax, comm, st));
             C2G_CUDA(ctx, cudaMemcpyAsync(&any, cnt + 6, sizeof(int), cudaMemcpyDeviceToHost, st));
             C2G_CUDA(ctx, cudaStreamSynchronize(st));
           }
+          if ((rc = check_err()) != C2G_OK) return rc;
+          if (any == 2) return ctx->fail(C2G_ERR_STATE, "c2g_bader_assign: another rank failed in the edge refinement");
           if (any == 0) break;
         }
         int* in = b_list[cur].as<int>();
@@ -2814,15 +2822,16 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
     for (;;) {
       C2G_CUDA(ctx, cudaMemcpyAsync(hcnt, cnt, C_NCNT * sizeof(int), cudaMemcpyDeviceToHost, st));
       C2G_CUDA(ctx, cudaStreamSynchronize(st));
-      if ((rc = check_err()) != C2G_OK) return rc;
       const int nseg1 = first ? hcnt[1] : 0, nflat = hcnt[7];
-      int any = nseg1 + nflat > 0 ? 1 : 0;
+      int any = hcnt[3] != 0 ? 2 : (nseg1 + nflat > 0 ? 1 : 0);  // 2: this rank failed -- agreed on by every rank below
       if (G > 1) {
         C2G_CUDA(ctx, cudaMemcpyAsync(cnt + 6, &any, sizeof(int), cudaMemcpyHostToDevice, st));
         C2G_NCCL(ctx, ncclAllReduce(cnt + 6, cnt + 6, 1, ncclInt32, ncclMax, comm, st));
         C2G_CUDA(ctx, cudaMemcpyAsync(&any, cnt + 6, sizeof(int), cudaMemcpyDeviceToHost, st));
         C2G_CUDA(ctx, cudaStreamSynchronize(st));
       }
+      if ((rc = check_err()) != C2G_OK) return rc;
+      if (any == 2) return ctx->fail(C2G_ERR_STATE, "c2g_bader_assign: another rank failed in the edge refinement");
       fixpasses++;
       if (any == 0) break;
       fixpts += nseg1 + nflat;

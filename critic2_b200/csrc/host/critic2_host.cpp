@@ -56,6 +56,11 @@ double shortest(const double x2c[9], const double dxin[3]) {
 
 // the per-maximum attractor identification of bader@proc.f90:160-199 / yt@proc.f90:129-168
 void identify_attractors(system& s, basindat& bas, int nmax, const std::vector<int>& pmax, std::vector<int>& map) {
+  // a maximum that is neither an atom nor a known attractor is kept only if the DISCARD expression vanishes there
+  // (:184-190); a discarded one gets map 0 -- the library then treats every point below it as the reference does
+  // (Bader: label 0; YT: ibasin = 0, which turns the points below into interatomic-surface points, yt@proc.f90:170)
+  if (!bas.expr.empty())
+    ferror("identify_attractors", "DISCARD expressions need critic2's arithmetic module (use the Fortran shim, which calls s%eval)");
   map.assign(nmax, 0);
   for (int i = 0; i < nmax; i++) {
     const double dv[3] = {(pmax[3 * i] - 1.0) / bas.n[0], (pmax[3 * i + 1] - 1.0) / bas.n[1], (pmax[3 * i + 2] - 1.0) / bas.n[2]};
@@ -86,9 +91,10 @@ void upload_field(const basindat& bas, const char* routine) {
 void finish_assignment(system& s, basindat& bas, int nmax, const char* routine) {
   std::vector<int> pmax(3 * (size_t)nmax), map;
   check(c2g_basins_maxima(g_basins, pmax.data()), routine);
-  if (bas.atexist) {  // atoms are the first attractors (bader@proc.f90:102-111)
-    bas.nattr = s.nat();
-    bas.xattr = s.xat;
+  if (bas.atexist) {  // the cell CP list of the reference field seeds the attractors (bader@proc.f90:113-118)
+    const std::vector<double>& seeds = s.cpcel.empty() ? s.xat : s.cpcel;
+    bas.nattr = (int)(seeds.size() / 3);
+    bas.xattr = seeds;
   } else {
     bas.nattr = 0;
     bas.xattr.clear();

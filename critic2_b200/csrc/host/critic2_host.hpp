@@ -56,6 +56,9 @@ struct system {
   double m_x2xr[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, m_xr2c[9] = {0};
   std::vector<double> ws_ineighc;  // (3,ws_nf) Cartesian
   std::vector<double> xat;     // atoms (nuclear CPs of the reference field), crystallographic, (3,nat)
+  std::vector<double> cpcel;   // sy%f(iref)%cpcel(:)%x, (3,ncpcel): the nuclei followed by any critical points found or
+                               // loaded before the integration (non-nuclear maxima).  They seed the attractor list
+                               // (bader@proc.f90:113-118, yt@proc.f90:66-76).  Empty = no CP beyond the nuclei: xat is used.
   grid3 grid;                  // sy%f(iref)%grid
   int nat() const { return (int)(xat.size() / 3); }
   // crystalmod@env.f90:593-614: id (1-based) of the atom within distmax of x (cryst.), 0 if none
@@ -77,6 +80,9 @@ struct basindat {
   bool is_yt = false;          // weights live on the device (the reference's luw scratch unit)
   std::vector<unsigned char> docelatom;  // per attractor (docelatom(icp(i)), ONLY / ONLY_RANGE); empty = all
   double isov = 0.0;           // ISOSURFACE: contour value (already negated by the driver for LOWER, integration@proc.f90:260)
+  std::string expr;            // DISCARD expression (bas%expr).  It is evaluated by critic2's arithmetic module per new
+                               // maximum (bader@proc.f90:184-190, yt@proc.f90:152-166): the Fortran shim calls s%eval; this
+                               // C++ mirror has no expression evaluator and REFUSES a non-empty expression (ferror)
 };
 
 // types.f90:394-410 (the sums only)

@@ -83,7 +83,9 @@ template <int NP>
 #ifndef RED_MINB
 #define RED_MINB 4
 #endif
-__global__ void __launch_bounds__(256, RED_MINB) k_basin_reduce(long long nn, const int* __restrict__ label,
+// three and four integrand grids need 90-118 registers: under the 64-register bound of 4 resident blocks they spilled
+// 240-576 bytes (profiles/r01q_ptxas_v.txt); they run 2 blocks per SM instead (no spills)
+__global__ void __launch_bounds__(256, (NP <= 2 ? RED_MINB : 2)) k_basin_reduce(long long nn, const int* __restrict__ label,
                                                       const double* __restrict__ f0, const double* __restrict__ f1,
                                                       const double* __restrict__ f2, const double* __restrict__ f3,
                                                       int nmax, int use_table, int mask, int vec, double* __restrict__ sums,

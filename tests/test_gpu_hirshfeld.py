@@ -91,3 +91,26 @@ def test_promolecular_grid_of_urea_reproduces_the_reference_cube(ctx):
     vol_o, ps_o = orc.hirshfeld_fields(rho, x2c, atoms, ispc, g, [rho], om)
     assert np.abs(ps - ps_o).max() <= TOL * np.abs(ps_o).max() and np.abs(vol - vol_o).max() <= TOL * np.abs(vol_o).max()
     ctx.free(h)
+
+
+def test_multi_round_image_culling(ctx):
+    """A 3.2 bohr cell with 24 atoms and 9 bohr cutoffs: about 2700 atom images reach every point, more than the 2048
+    entries the per-tile culling list holds, so every tile needs a second (and third) culling round (hirshfeld.cu,
+    HB_LIST)."""
+    x2c = S.cell_x2c(3.2, 3.0, 3.4, 90, 96, 90)
+    rng = np.random.default_rng(3)
+    atoms = rng.uniform(0, 1, (24, 3))
+    ispc = np.array([1, 2] * 12, dtype=np.int32)
+    g = slater_tables([6.0, 1.0], [2.1, 1.7])
+    n = (12, 11, 13)
+    om = S.omega(x2c)
+    ref = orc.promolecular_grid(n, x2c, atoms, ispc, g)
+    h = ctx.promolecular_grid(n, x2c, atoms, ispc, tab_of(g))
+    got = ctx.download(h, n)
+    assert np.abs(got - ref).max() <= TOL * ref.max()
+    vol_o, ps_o = orc.hirshfeld_fields(ref, x2c, atoms, ispc, g, [ref], om)
+    vol, ps = ctx.hirshfeld_integrate(h, x2c, atoms, ispc, tab_of(g), [h], om)
+    assert np.abs(vol - vol_o).max() <= TOL * np.abs(vol_o).max()
+    assert np.abs(ps - ps_o).max() <= TOL * np.abs(ps_o).max()
+    assert abs(vol.sum() - om) <= 1e-9 * om
+    ctx.free(h)
