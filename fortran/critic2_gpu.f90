@@ -13,7 +13,7 @@ module critic2_gpu
 
   public :: gpu_enabled, gpu_init, gpu_end
   public :: gpu_bader_integrate, gpu_yt_integrate, gpu_yt_isosurface, gpu_integrate_fields, gpu_integrate_multipoles
-  public :: gpu_nci_rdg, gpu_nci_rdg_fourier, gpu_grid_fft, gpu_read_text_block, gpu_write_text_block, gpu_wcube_block, gpu_basins_remap, gpu_hirshfeld_fields
+  public :: gpu_nci_rdg, gpu_nci_rdg_fourier, gpu_grid_fft, gpu_read_text_block, gpu_write_text_block, gpu_wcube_block, gpu_basins_remap, gpu_hirshfeld_fields, gpu_yt_export
 
   logical :: gpu_enabled = .false.        !< set by gpu_init (environment variable CRITIC2_GPU=1)
   type(c_ptr) :: ctx = c_null_ptr         !< c2g_context
@@ -27,6 +27,21 @@ module critic2_gpu
        type(c_ptr) :: ctx
        integer(c_int) :: c2g_init
      end function c2g_init
+     !> one process, ngpus devices (critic2 is a single process): z-slabs and NCCL live inside the library
+     function c2g_init_devices(ngpus,ctx) bind(c,name="c2g_init_devices")
+       import :: c_int, c_ptr
+       integer(c_int), value :: ngpus
+       type(c_ptr) :: ctx
+       integer(c_int) :: c2g_init_devices
+     end function c2g_init_devices
+     !> the ytdata record (yt.f90:36-45) for hosts that keep their own yt_weights; inear/fnear may be c_null_ptr
+     function c2g_yt_export(res,nlo,ibasin,iio,inear,fnear) bind(c,name="c2g_yt_export")
+       import :: c_int, c_ptr
+       type(c_ptr), value :: res
+       integer(c_int) :: nlo(*), ibasin(*), iio(*)
+       type(c_ptr), value :: inear, fnear
+       integer(c_int) :: c2g_yt_export
+     end function c2g_yt_export
      subroutine c2g_finalize(ctx) bind(c,name="c2g_finalize")
        import :: c_ptr
        type(c_ptr), value :: ctx
@@ -265,11 +280,20 @@ contains
 
   subroutine gpu_init()
     character(len=8) :: val
-    integer :: stat
+    integer :: stat, ngpus
     call get_environment_variable("CRITIC2_GPU",val,status=stat)
     if (stat /= 0) return
     if (trim(val) /= "1") return
-    call check(c2g_init(0_c_int,ctx),"gpu_init")
+    ! CRITIC2_GPUS=N (2, 4, 8): the same calls drive N devices of the node; grids are sharded as z-slabs inside the library
+    ngpus = 1
+    call get_environment_variable("CRITIC2_GPUS",val,status=stat)
+    if (stat == 0) read (val,*,iostat=stat) ngpus
+    if (stat /= 0 .or. ngpus < 1) ngpus = 1
+    if (ngpus > 1) then
+       call check(c2g_init_devices(int(ngpus,c_int),ctx),"gpu_init")
+    else
+       call check(c2g_init(0_c_int,ctx),"gpu_init")
+    end if
     gpu_enabled = .true.
   end subroutine gpu_init
 
@@ -384,6 +408,27 @@ contains
     call check(c2g_basins_labels(basins,bas%idg),"gpu_yt_integrate")   ! spatial ids, 0 = IAS point
     call realloc(bas%xattr,3,bas%nattr)
   end subroutine gpu_yt_integrate
+
+  !> The ytdata record of the last gpu_yt_integrate (yt.f90:36-45), for the consumers that call the host's own
+  !> yt_weights(din=...) (BASINS, DI: integration@proc.f90:1125-1158, yt@proc.f90:399-530).  Same arrays as the ones
+  !> yt_integrate writes to bas%luw (:191-199), in the order of a stable (density, index) sort.
+  subroutine gpu_yt_export(bas,dat)
+    use yt, only: ytdata
+    use systemmod, only: sy
+    use types, only: basindat
+    type(basindat), intent(in) :: bas
+    type(ytdata), intent(inout), target :: dat
+    integer :: nn, nvec
+
+    nn = bas%n(1)*bas%n(2)*bas%n(3)
+    nvec = sy%f(sy%iref)%grid%nvec
+    dat%nbasin = bas%nattr
+    dat%nn = nn
+    dat%nvec = nvec
+    if (allocated(dat%nlo)) deallocate(dat%nlo,dat%ibasin,dat%iio,dat%inear,dat%fnear)
+    allocate(dat%nlo(nn),dat%ibasin(nn),dat%iio(nn),dat%inear(nvec,nn),dat%fnear(nvec,nn))
+    call check(c2g_yt_export(basins,dat%nlo,dat%ibasin,dat%iio,c_loc(dat%inear),c_loc(dat%fnear)),"gpu_yt_export")
+  end subroutine gpu_yt_export
 
   !> GPU body of yt_isosurface (src/yt@proc.f90:233-390) for an empty DISCARD expression (with an expression the
   !> caller keeps the CPU routine: the expression is evaluated by the host parser, :304-311).  Fills bas%nattr,
