@@ -1314,12 +1314,15 @@ __global__ void __launch_bounds__(256) k_items_write(int nseg, int segcap, int b
   s_c[threadIdx.x] = c; s_e[threadIdx.x] = ebase;
   __syncthreads();
   if (total == 0) return;
-  for (int sg = 0; sg < 256; sg++) {  // cooperative, coalesced copy of each segment's entries
+  // coalesced copy of the segments' entries, one warp per segment (most segments are empty or hold a few dozen entries:
+  // with the whole block on every segment the loop was a chain of 256 dependent rounds, 0.13-0.22 ms per level)
+  const int lane = threadIdx.x & 31;
+  for (int sg = threadIdx.x >> 5; sg < 256; sg += 8) {
     const int cs = s_c[sg];
     if (cs == 0) continue;
     const int* src = seglist + (size_t)(blockIdx.x * 256 + sg) * segcap;
     int* dst = dlist + dbase + s_e[sg];
-    for (int e = threadIdx.x; e < cs; e += 256) dst[e] = src[e];
+    for (int e = lane; e < cs; e += 32) dst[e] = src[e];
   }
 }
 
