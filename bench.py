@@ -398,14 +398,15 @@ def run_ours(args):
     kms = {k: v[0] / args.steps for k, v in prof.items()}
     dk = max(kms, key=kms.get) if kms else None
     dominant = None if dk is None else {
-        "name": dk + (" (k_walk, last-level launch)" if dk == "bader_walk_l1" else ""), "ms": round(kms[dk], 4),
+        "name": dk + (" (k_walk3, last-level launch)" if dk == "bader_walk_l1" else ""), "ms": round(kms[dk], 4),
         "share_of_kernel_group": round(kms[dk] / max(assign_ms + integ_ms, 1e-9), 4),
-        "note": "the walkers are issue-bound, not HBM-bound (ncu: 78 % of the issue slots busy, 19 of 32 lanes active, L2 hit "
-                "81 %; profiles/r01k_ncu_full_1024_table.txt): an HBM fraction of this launch alone would be meaningless, so "
-                "`achieved` is the algorithmic bytes of the whole step over the time of the whole kernel group"}
+        "note": "the walkers are issue-bound, not HBM-bound (ncu, profiles/r02m_ncu_step_1024_table.txt: 67 % of the issue slots busy, "
+                "24 of 32 lanes active, 227 warp instructions per step, L1 / L2 hit 75 %, 5.7 GB of DRAM traffic for 7.4e8 steps): an HBM "
+                "fraction of this launch alone would be meaningless, so `achieved` is the algorithmic bytes of the whole step over the "
+                "time of the whole kernel group"}
     roofline = {
-        "bound": "hbm", "kernel": "BADER assign+integrate kernel group (k_maxima, k_walk, k_classify, k_vsafe, k_fill_edge_v, k_requeue, "
-                                  "k_basin_reduce); dominant: k_walk (last-level launch, bader_walk_l1)",
+        "bound": "hbm", "kernel": "BADER assign+integrate kernel group (k_maxima2, k_walk3, k_walk_big2, k_classify, k_vsafe, k_pack5, k_items_*, "
+                                  "k_fill_edge_v, k_requeue, k_basin_reduce); dominant: k_walk3 (last-level launch, bader_walk_l1)",
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
         "algorithmic_bytes_per_point": ALG_BYTES_TOTAL, "points_per_launch_group": nloc, "traffic": traffic,
         "traffic_source": traffic_src,
@@ -548,6 +549,39 @@ def run_ours(args):
     return 0
 
 
+def run_other_config(args):
+    """The BASELINE.json configs that are not the headline, as driver-visible bench lines: `--config urea256 | nci512 |
+    yt512 | fft1024 | hirshfeld | multipoles` runs the matching path of tools/bench_paths.py (same library, same C ABI,
+    inputs resident in HBM, CUDA-event timing, a parity check per path) and prints one contract-shaped JSON line per
+    path it measures."""
+    import subprocess
+    fn = {"urea256": "urea", "nci512": "nci", "yt512": "yt", "fft1024": "fft_big", "hirshfeld": "hirshfeld",
+          "multipoles": "multipoles"}[args.config]
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_paths.py"), f"--only={fn}"], capture_output=True, text=True)
+    n = 0
+    for line in out.stdout.splitlines():
+        if not line.startswith("{"):
+            continue
+        d = json.loads(line)
+        if "error" in d:
+            print(json.dumps({"metric": "grid points/s", "config": {"workload": args.config}, "error": d["error"]}), flush=True)
+            continue
+        n += 1
+        print(json.dumps({
+            "metric": "grid points/s, " + d["path"], "value": d["points_per_s"], "unit": "grid points/s", "n_gpus": 1, "steps": 3,
+            "warmup": 1, "ms_per_step": d["ms"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": d["path"] + " -- " + d["config"], "grid": d["grid"],
+                                            "l2": "inputs larger than the 126 MB L2 (>= 1 GB per field at 512^3)"},
+            "roofline": {"bound": "hbm", "achieved": d["achieved_GBps"], "peak": d["peak_GBps"], "unit": "GB/s", "frac": d["frac"],
+                         "peak_source": d["peak_source"], "algorithmic_bytes_per_point": d["algorithmic_bytes_per_point"],
+                         "traffic": None, "kernels_ms_per_step": d["kernels_ms"]},
+            "check": d["check"], "gpu_launches": None}), flush=True)
+    if n == 0:
+        sys.stderr.write(out.stderr[-2000:])
+        return 1
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -556,9 +590,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=1024, help="grid points per axis (default: the 1024^3 headline config)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--config", default="bader1024", choices=["bader1024", "urea256", "nci512", "yt512", "fft1024", "hirshfeld", "multipoles"],
+                    help="bader1024 = the headline (BASELINE.json configs[4], default); the others run one path of tools/bench_paths.py")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.config != "bader1024":
+        return run_other_config(args)
     return run_ours(args)
 
 
