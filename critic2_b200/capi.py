@@ -26,7 +26,7 @@ EXPORTS = [
     "c2g_grid_upload", "c2g_grid_upload_slab", "c2g_slab_range", "c2g_slab_bounds_query", "c2g_grid_alloc", "c2g_grid_download", "c2g_grid_download_slab", "c2g_grid_free", "c2g_grid_promolecular",
     "c2g_bader_assign", "c2g_basins_maxima", "c2g_basins_counts", "c2g_basins_set_map", "c2g_basins_labels",
     "c2g_basins_relabel", "c2g_basins_nattr", "c2g_basins_free", "c2g_basins_stats", "c2g_integrate", "c2g_integrate_multipoles", "c2g_promolecular_grid", "c2g_hirshfeld_integrate", "c2g_basins_remap", "c2g_yt_build",
-    "c2g_yt_weights", "c2g_yt_export", "c2g_basins_weight_grid", "c2g_yt_isosurface", "c2g_nci_rdg", "c2g_nci_rdg_resident", "c2g_fft_derivative", "c2g_nci_rdg_fourier", "c2g_nci_range", "c2g_grid_upload_async", "c2g_basins_labels_async", "c2g_grid_parse_text", "c2g_grid_format_text", "c2g_profile_enable", "c2g_profile_count",
+    "c2g_yt_weights", "c2g_yt_export", "c2g_voronoi_grid", "c2g_basins_weight_grid", "c2g_yt_isosurface", "c2g_nci_rdg", "c2g_nci_rdg_resident", "c2g_fft_derivative", "c2g_nci_rdg_fourier", "c2g_nci_range", "c2g_grid_upload_async", "c2g_basins_labels_async", "c2g_grid_parse_text", "c2g_grid_format_text", "c2g_profile_enable", "c2g_profile_count",
     "c2g_profile_get", "c2g_profile_reset", "c2g_launch_count", "c2g_flush_l2", "c2g_synchronize", "c2g_timer_start", "c2g_timer_stop",
 ]
 
@@ -244,6 +244,17 @@ class Context:
                                                  _p(xat, C.c_double), _p(isp, C.c_int), *sargs,
                                                  None if fr is None else _p(fr, C.c_ubyte), C.byref(h)))
         return h.value
+
+    def voronoi_grid(self, n, x2c, atoms):
+        """voronoi_grid (hirshfeld@proc.f90:93-122): Basins whose labels are the nearest-atom ids; the map is already set."""
+        nn = np.array(n, dtype=np.int32)
+        xat = np.ascontiguousarray(atoms, dtype=np.float64)
+        res = C.c_void_p()
+        self._chk(self.lib.c2g_voronoi_grid(self.h, _p(nn, C.c_int), _p(_m33(x2c), C.c_double), C.c_int(len(xat)), _p(xat, C.c_double),
+                                            C.byref(res)))
+        b = Basins(self, res, len(xat))
+        b.nattr = len(xat)
+        return b
 
     def hirshfeld_integrate(self, hpromol, x2c, atoms, ispc, tab, fieldhandles, omega, domask=None):
         """intgrid_hirshfeld_fields (integration@proc.f90:1552-1596): (vol[nat], psum[nat, nprop])."""

@@ -403,3 +403,169 @@ extern "C" int c2g_hirshfeld_integrate(c2g_context* ctx, int hpromol, const doub
   ctx->prof_collect();
   return C2G_OK;
 }
+
+// =================================================================================================
+// VORONOI on a grid: voronoi_grid (src/hirshfeld@proc.f90:93-122) = crystal%nearest_atom_grid
+// (src/crystalmod@proc.f90:1138-1167): idg(i,j,k) = complete-list id of the atom nearest to the grid node.
+// The reference asks its block environment for the nearest atom of every node (nearest_atom ->
+// list_near_atoms(up2n = 1), crystalmod@env.f90:516-563).  Here the host enumerates every atom image within half the
+// longest body diagonal of the cell (no point of the cell is farther than that from an image of ANY atom); a block
+// owns a tile of 256 consecutive points, warp 0 finds the image nearest to the tile's reference point (d0) and keeps
+// the images within d0 + 2 * (tile radius) of it -- a superset of the nearest image of every point of the tile -- and
+// every lane runs over the survivors.
+// Distances are compared as the reference computes them (Cartesian difference, sum of squares in x, y, z order);
+// TIES between equidistant atoms go to the lower atom id.  The reference's choice among exactly equidistant atoms
+// follows the block traversal and merge sort of list_near_atoms, which is not restated: parity is claimed for nodes
+// whose nearest atom is unique, ties are counted by the tests.
+// =================================================================================================
+namespace {
+struct VParams {
+  int n1, n2, n3;
+  unsigned nn;
+  double x2c[9];
+  int nimg;
+  const int* img_atom;
+  const double* img_x;
+};
+__global__ void __launch_bounds__(HB_THREADS) k_voronoi(const __grid_constant__ VParams V, unsigned ntiles, int* __restrict__ label) {
+  __shared__ Cull c;
+  __shared__ int s_list[HB_LIST];
+  __shared__ double s_d0;
+  HParams P;  // tile_point only reads the grid shape and the cell
+  P.n1 = V.n1; P.n2 = V.n2; P.n3 = V.n3; P.nn = V.nn;
+  for (int i = 0; i < 9; i++) P.x2c[i] = V.x2c[i];
+  for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const Tile t = tile_point(P, tile);
+    const double radius = tile_sphere(c, t);
+    // distance of the reference point to its nearest image
+    if (threadIdx.x < 32) {
+      double best = 1e300;
+      for (int m = threadIdx.x; m < V.nimg; m += 32) {
+        const double dx = __ldg(V.img_x + 3 * m) - c.cx, dy = __ldg(V.img_x + 3 * m + 1) - c.cy, dz = __ldg(V.img_x + 3 * m + 2) - c.cz;
+        best = fmin(best, dx * dx + dy * dy + dz * dz);
+      }
+      for (int o = 16; o; o >>= 1) best = fmin(best, __shfl_xor_sync(0xffffffffu, best, o));
+      if (threadIdx.x == 0) s_d0 = sqrt(best);
+    }
+    __syncthreads();
+    const double lim = (s_d0 + 2.0 * radius) * 1.000001 + 1e-9;
+    double dbest = 1e300;
+    int abest = 0x7fffffff;
+    bool more;
+    do {  // culling rounds of HB_LIST images, in list order
+      if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        int cnt = 0, base = c.next;
+        __syncwarp();
+        for (; base < V.nimg && cnt + 32 <= HB_LIST; base += 32) {
+          const int m = base + lane;
+          bool keep = false;
+          if (m < V.nimg) {
+            const double dx = __ldg(V.img_x + 3 * m) - c.cx, dy = __ldg(V.img_x + 3 * m + 1) - c.cy, dz = __ldg(V.img_x + 3 * m + 2) - c.cz;
+            keep = dx * dx + dy * dy + dz * dz <= lim * lim;
+          }
+          const unsigned bal = __ballot_sync(0xffffffffu, keep);
+          if (keep) s_list[cnt + __popc(bal & ((1u << lane) - 1u))] = m;
+          cnt += __popc(bal);
+        }
+        if (lane == 0) { c.cnt = cnt; c.next = base; }
+      }
+      __syncthreads();
+      const int cnt = c.cnt;
+      more = c.next < V.nimg;  // read while nobody writes it: warp 0 rewrites c.next at the top of the next round
+      for (int q = 0; q < cnt; q++) {
+        const int m = s_list[q];
+        const double dx = t.x - __ldg(V.img_x + 3 * m), dy = t.y - __ldg(V.img_x + 3 * m + 1), dz = t.z - __ldg(V.img_x + 3 * m + 2);
+        const double d2 = dx * dx + dy * dy + dz * dz;
+        const int a = __ldg(V.img_atom + m);
+        if (d2 < dbest || (d2 == dbest && a < abest)) { dbest = d2; abest = a; }
+      }
+      __syncthreads();
+    } while (more);
+    if (t.valid) label[t.i] = abest;
+    __syncthreads();
+  }
+}
+}  // namespace
+
+extern "C" int c2g_voronoi_grid(c2g_context* ctx, const int n[3], const double x2c[9], int nat, const double* xat, c2g_basins** res_out) {
+  if (!ctx) return C2G_ERR_ARG;
+  C2G_NOT_ON_GROUP(ctx, "c2g_voronoi_grid");
+  if (!n || !x2c || nat < 1 || !xat || !res_out) return ctx->fail(C2G_ERR_ARG, "c2g_voronoi_grid: bad argument");
+  const long long nn = (long long)n[0] * n[1] * n[2];
+  if (n[0] < 1 || n[1] < 1 || n[2] < 1 || nn >= (1ll << 31)) return ctx->fail(C2G_ERR_ARG, "c2g_voronoi_grid: bad grid shape");
+  auto A = [&](int i, int j) { return x2c[i + 3 * j]; };
+  const double det = A(0, 0) * (A(1, 1) * A(2, 2) - A(1, 2) * A(2, 1)) - A(0, 1) * (A(1, 0) * A(2, 2) - A(1, 2) * A(2, 0)) +
+                     A(0, 2) * (A(1, 0) * A(2, 1) - A(1, 1) * A(2, 0));
+  if (det == 0.0) return ctx->fail(C2G_ERR_ARG, "c2g_voronoi_grid: singular cell");
+  // reciprocal rows (plane spacings) and the longest body diagonal
+  const double d = 1.0 / det;
+  double c2x[9];
+  c2x[0] = (A(1, 1) * A(2, 2) - A(1, 2) * A(2, 1)) * d; c2x[3] = (A(0, 2) * A(2, 1) - A(0, 1) * A(2, 2)) * d; c2x[6] = (A(0, 1) * A(1, 2) - A(0, 2) * A(1, 1)) * d;
+  c2x[1] = (A(1, 2) * A(2, 0) - A(1, 0) * A(2, 2)) * d; c2x[4] = (A(0, 0) * A(2, 2) - A(0, 2) * A(2, 0)) * d; c2x[7] = (A(0, 2) * A(1, 0) - A(0, 0) * A(1, 2)) * d;
+  c2x[2] = (A(1, 0) * A(2, 1) - A(1, 1) * A(2, 0)) * d; c2x[5] = (A(0, 1) * A(2, 0) - A(0, 0) * A(2, 1)) * d; c2x[8] = (A(0, 0) * A(1, 1) - A(0, 1) * A(1, 0)) * d;
+  double diag = 0.0;
+  for (int s1 = -1; s1 <= 1; s1 += 2)
+    for (int s2 = -1; s2 <= 1; s2 += 2) {
+      double v[3];
+      for (int i = 0; i < 3; i++) v[i] = x2c[i] + s1 * x2c[i + 3] + s2 * x2c[i + 6];
+      diag = std::max(diag, std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]));
+    }
+  const double reach = 0.5 * diag * 1.0001;
+  int m[3];
+  for (int i = 0; i < 3; i++) m[i] = (int)std::ceil(reach * std::sqrt(c2x[i] * c2x[i] + c2x[i + 3] * c2x[i + 3] + c2x[i + 6] * c2x[i + 6])) + 1;
+  const long long nimg_ll = (long long)nat * (2 * m[0] + 1) * (2 * m[1] + 1) * (2 * m[2] + 1);
+  if (nimg_ll > 50000000ll) return ctx->fail(C2G_ERR_ARG, "c2g_voronoi_grid: %lld atom images", nimg_ll);
+  std::vector<int> h_atom;
+  std::vector<double> h_x;
+  for (int a = 0; a < nat; a++)
+    for (int l1 = -m[0]; l1 <= m[0]; l1++)
+      for (int l2 = -m[1]; l2 <= m[1]; l2++)
+        for (int l3 = -m[2]; l3 <= m[2]; l3++) {
+          const double xf[3] = {xat[3 * a] - std::floor(xat[3 * a]) + l1, xat[3 * a + 1] - std::floor(xat[3 * a + 1]) + l2,
+                                xat[3 * a + 2] - std::floor(xat[3 * a + 2]) + l3};
+          h_atom.push_back(a);
+          for (int i = 0; i < 3; i++) h_x.push_back(x2c[i] * xf[0] + x2c[i + 3] * xf[1] + x2c[i + 6] * xf[2]);
+        }
+  cudaStream_t st = ctx->stream;
+  DevBuf b_atom, b_x;
+  C2G_CUDA(ctx, b_atom.alloc(ctx, sizeof(int) * h_atom.size()));
+  C2G_CUDA(ctx, b_x.alloc(ctx, sizeof(double) * h_x.size()));
+  C2G_CUDA(ctx, cudaMemcpyAsync(b_atom.p, h_atom.data(), sizeof(int) * h_atom.size(), cudaMemcpyHostToDevice, st));
+  C2G_CUDA(ctx, cudaMemcpyAsync(b_x.p, h_x.data(), sizeof(double) * h_x.size(), cudaMemcpyHostToDevice, st));
+  c2g_basins* res = new c2g_basins();
+  res->ctx = ctx; res->kind = 2; res->gridh = -1;   // plain labels like ISOSURFACE regions: one "maximum" per atom
+  res->n[0] = n[0]; res->n[1] = n[1]; res->n[2] = n[2]; res->nn = nn;
+  res->zlo = 0; res->zhi = n[2];
+  res->nmax = nat;
+  res->max_lin.assign(nat, 0);
+  for (int a = 0; a < nat; a++) {  // grid node nearest to the atom (for c2g_basins_maxima; the attractors are the atoms themselves)
+    long long id = 0, stride = 1;
+    for (int i = 0; i < 3; i++) {
+      const double f = xat[3 * a + i] - std::floor(xat[3 * a + i]);
+      const long long k = ((long long)std::llround(f * n[i])) % n[i];
+      id += k * stride; stride *= n[i];
+    }
+    res->max_lin[a] = (int)id;
+  }
+  struct Guard { c2g_basins* r; bool ok = false; ~Guard() { if (!ok) c2g_basins_free(r); } } guard{res};
+  C2G_CUDA(ctx, c2g_alloc(ctx, (void**)&res->d_label, sizeof(int) * nn));
+  VParams V;
+  V.n1 = n[0]; V.n2 = n[1]; V.n3 = n[2]; V.nn = (unsigned)nn;
+  for (int i = 0; i < 9; i++) V.x2c[i] = x2c[i];
+  V.nimg = (int)h_atom.size(); V.img_atom = b_atom.as<int>(); V.img_x = b_x.as<double>();
+  const unsigned ntiles = (V.nn + HB_THREADS - 1) / HB_THREADS;
+  ctx->prof_begin("voronoi_nearest_atom");
+  k_voronoi<<<std::min<unsigned>(ntiles, (unsigned)ctx->nsm * 8u), HB_THREADS, 0, st>>>(V, ntiles, res->d_label);
+  ctx->prof_end();
+  C2G_KERNEL_CHECK(ctx);
+  C2G_CUDA(ctx, cudaStreamSynchronize(st));  // the host image vectors go out of scope
+  std::vector<int> ident(nat);
+  for (int a = 0; a < nat; a++) ident[a] = a + 1;
+  int rc = c2g_basins_set_map(res, nat, ident.data());
+  if (rc != C2G_OK) return rc;
+  ctx->prof_collect();
+  guard.ok = true;
+  *res_out = res;
+  return C2G_OK;
+}

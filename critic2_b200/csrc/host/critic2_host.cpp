@@ -219,6 +219,20 @@ void yt_isosurface(system& s, basindat& bas) {
   check(c2g_basins_labels(g_basins, bas.idg.data()), "yt_isosurface");
 }
 
+void voronoi_grid(system& s, basindat& bas) {
+  if (!g_ctx) ferror("voronoi_grid", "gpu_init was not called");
+  if (s.nat() < 1) ferror("voronoi_grid", "system does not have crystal");
+  if (g_basins) { c2g_basins_free(g_basins); g_basins = nullptr; }
+  // atoms are the attractors (hirshfeld@proc.f90:108-117); nodes -> nearest atom (:120)
+  const std::vector<double>& seeds = s.cpcel.empty() ? s.xat : s.cpcel;
+  bas.nattr = bas.atexist ? (int)(seeds.size() / 3) : 0;
+  bas.xattr = bas.atexist ? seeds : std::vector<double>();
+  check(c2g_voronoi_grid(g_ctx, bas.n, s.m_x2c, s.nat(), s.xat.data(), &g_basins), "voronoi_grid");
+  bas.is_yt = false;
+  bas.idg.assign((size_t)bas.n[0] * bas.n[1] * bas.n[2], 0);
+  check(c2g_basins_labels(g_basins, bas.idg.data()), "voronoi_grid");
+}
+
 void intgrid_fields(const system& s, const basindat& bas, const std::vector<const double*>& fint, std::vector<int_result>& res,
                     std::vector<double>& vol) {
   if (!g_ctx || !g_basins) ferror("intgrid_fields", "no basin assignment on the device");

@@ -102,6 +102,9 @@ void yt_integrate(system& s, basindat& bas);
 // yt@proc.f90:233-390 (no DISCARD expression): regions of f >= bas.isov.  bas.idg = region ids in the reference's
 // numbering, bas.nattr = surviving regions, bas.xattr = the first nattr regional maxima (:359).
 void yt_isosurface(system& s, basindat& bas);
+// hirshfeld@proc.f90:93-122 (VORONOI): bas.idg = id of the atom nearest to every grid node (crystal%nearest_atom_grid),
+// attractors = the atoms; intgrid_fields then integrates over it like over Bader basins.  bas.n must be set.
+void voronoi_grid(system& s, basindat& bas);
 // integration@proc.f90:1170-1391: res[k].psum(i) = integral of fint[k] over basin i; vol(i) = basin volume.
 void intgrid_fields(const system& s, const basindat& bas, const std::vector<const double*>& fint,
                     std::vector<int_result>& res, std::vector<double>& vol);

@@ -13,7 +13,7 @@ module critic2_gpu
 
   public :: gpu_enabled, gpu_init, gpu_end
   public :: gpu_bader_integrate, gpu_yt_integrate, gpu_yt_isosurface, gpu_integrate_fields, gpu_integrate_multipoles
-  public :: gpu_nci_rdg, gpu_nci_rdg_fourier, gpu_grid_fft, gpu_read_text_block, gpu_write_text_block, gpu_wcube_block, gpu_basins_remap, gpu_hirshfeld_fields, gpu_yt_export
+  public :: gpu_nci_rdg, gpu_nci_rdg_fourier, gpu_grid_fft, gpu_read_text_block, gpu_write_text_block, gpu_wcube_block, gpu_basins_remap, gpu_hirshfeld_fields, gpu_yt_export, gpu_voronoi_grid
 
   logical :: gpu_enabled = .false.        !< set by gpu_init (environment variable CRITIC2_GPU=1)
   type(c_ptr) :: ctx = c_null_ptr         !< c2g_context
@@ -42,6 +42,15 @@ module critic2_gpu
        type(c_ptr), value :: inear, fnear
        integer(c_int) :: c2g_yt_export
      end function c2g_yt_export
+     function c2g_voronoi_grid(ctx,n,x2c,nat,xat,res) bind(c,name="c2g_voronoi_grid")
+       import :: c_int, c_ptr, c_double
+       type(c_ptr), value :: ctx
+       integer(c_int) :: n(3)
+       real(c_double) :: x2c(3,3), xat(3,*)
+       integer(c_int), value :: nat
+       type(c_ptr) :: res
+       integer(c_int) :: c2g_voronoi_grid
+     end function c2g_voronoi_grid
      subroutine c2g_finalize(ctx) bind(c,name="c2g_finalize")
        import :: c_ptr
        type(c_ptr), value :: ctx
@@ -408,6 +417,37 @@ contains
     call check(c2g_basins_labels(basins,bas%idg),"gpu_yt_integrate")   ! spatial ids, 0 = IAS point
     call realloc(bas%xattr,3,bas%nattr)
   end subroutine gpu_yt_integrate
+
+  !> GPU body of voronoi_grid (src/hirshfeld@proc.f90:93-122): the atoms are the attractors, bas%idg = nearest atom of
+  !> every grid node (crystal%nearest_atom_grid).  The basins stay on the device for gpu_integrate_fields.
+  subroutine gpu_voronoi_grid(s,bas)
+    use systemmod, only: system
+    use types, only: basindat
+    type(system), intent(inout) :: s
+    type(basindat), intent(inout) :: bas
+    integer :: i
+    real(c_double), allocatable :: xat(:,:)
+
+    if (allocated(bas%xattr)) deallocate(bas%xattr)
+    allocate(bas%xattr(3,s%f(s%iref)%ncpcel))
+    bas%xattr = 0d0
+    bas%nattr = 0
+    if (bas%atexist) then
+       bas%nattr = s%f(s%iref)%ncpcel
+       do i = 1, s%f(s%iref)%ncpcel
+          bas%xattr(:,i) = s%f(s%iref)%cpcel(i)%x
+       end do
+    end if
+    allocate(xat(3,s%c%ncel))
+    do i = 1, s%c%ncel
+       xat(:,i) = s%c%atcel(i)%x
+    end do
+    if (c_associated(basins)) call c2g_basins_free(basins)
+    call check(c2g_voronoi_grid(ctx,int(bas%n,c_int),s%c%m_x2c,int(s%c%ncel,c_int),xat,basins),"gpu_voronoi_grid")
+    if (allocated(bas%idg)) deallocate(bas%idg)
+    allocate(bas%idg(bas%n(1),bas%n(2),bas%n(3)))
+    call check(c2g_basins_labels(basins,bas%idg),"gpu_voronoi_grid")
+  end subroutine gpu_voronoi_grid
 
   !> The ytdata record of the last gpu_yt_integrate (yt.f90:36-45), for the consumers that call the host's own
   !> yt_weights(din=...) (BASINS, DI: integration@proc.f90:1125-1158, yt@proc.f90:399-530).  Same arrays as the ones

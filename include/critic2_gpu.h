@@ -186,6 +186,14 @@ int c2g_hirshfeld_integrate(c2g_context* ctx, int hpromol, const double x2c[9], 
                             const double* spc_rmax, const double* spc_rcut, const double* rtab, const double* ftab,
                             const unsigned char* domask, int nprop, const int* fieldhandles, double omega, double* psum,
                             double* vol);
+/* ---- VORONOI on a grid: voronoi_grid (hirshfeld@proc.f90:93-122) = crystal%nearest_atom_grid (crystalmod@proc.f90:1138-1167) ---- */
+/* idg(i,j,k) = complete-list id (1-based, the order of xat) of the atom nearest to the grid node, any periodic image.  The
+ * result is a c2g_basins with plain labels and the identity map already set (the attractors of VORONOI are the atoms,
+ * :108-117): c2g_basins_labels gives bas%idg, c2g_integrate / c2g_integrate_multipoles the atomic properties exactly like the
+ * Bader branch of intgrid_fields.  Nodes equidistant from two atoms go to the lower id (the reference's choice follows the
+ * traversal order of list_near_atoms; such nodes are a set of measure zero unless the structure is symmetric about them).
+ * Single-device contexts. */
+int c2g_voronoi_grid(c2g_context* ctx, const int n[3], const double x2c[9], int nat, const double* xat, c2g_basins** res);
 
 /* ---- YT: Yu-Trinkle weights (yt@proc.f90:77-211) ---- */
 /* vec(3,nvec), area(nvec): Voronoi-relevant grid steps and facet areas from grid3%init_geometry

@@ -619,3 +619,32 @@ def format_text_grid(f, layout, w, d, k, ishift=(0, 0, 0)):
                 row = [" " + fortran_e(float(f[ix, iy, (iiz + ishift[2]) % n3]), w, d, k) for iiz in range(n3)]
                 out += ["".join(row[q:q + 6]) + (" \n" if len(row[q:q + 6]) < 6 else "\n") for q in range(0, n3, 6)]
     return "".join(out).encode()
+
+
+def voronoi_grid(n, x2c, atoms, reach_cells=3):
+    """nearest_atom_grid (crystalmod@proc.f90:1138-1167; voronoi_grid, hirshfeld@proc.f90:93-122) by brute force in numpy:
+    for every grid node x = ((i-1)/n1, (j-1)/n2, (k-1)/n3) the 1-based id of the nearest atom over the lattice
+    translations -reach_cells..reach_cells, the distance as the reference computes it (Cartesian difference, norm2).
+    Returns (idg[n1,n2,n3] int32 with ties resolved to the LOWER id, gap[n1,n2,n3] = relative distance gap to the nearest
+    OTHER atom: the reference's choice at gap == 0 follows the traversal order of list_near_atoms, which is not restated)."""
+    n = tuple(int(v) for v in n)
+    x2c = np.asarray(x2c, dtype=np.float64)
+    at = np.asarray(atoms, dtype=np.float64)
+    at = at - np.floor(at)
+    g = np.stack(np.meshgrid(*[np.arange(m) / m for m in n], indexing="ij"), -1).reshape(-1, 3)
+    pc = g @ x2c.T
+    r = range(-reach_cells, reach_cells + 1)
+    shifts = np.array([[a, b, c] for a in r for b in r for c in r], dtype=np.float64)
+    best = np.full((len(at), len(g)), np.inf)
+    for ia, a in enumerate(at):
+        img = (a[None, :] + shifts) @ x2c.T
+        for k0 in range(0, len(img), 64):
+            d = pc[None, :, :] - img[k0:k0 + 64, None, :]
+            d2 = d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1] + d[..., 2] * d[..., 2]
+            best[ia] = np.minimum(best[ia], d2.min(axis=0))
+    order = np.argsort(best, axis=0, kind="stable")
+    idg = (order[0] + 1).astype(np.int32)
+    d1 = np.sqrt(best[order[0], np.arange(len(g))])
+    d2 = np.sqrt(best[order[1], np.arange(len(g))]) if len(at) > 1 else np.full(len(g), np.inf)
+    gap = np.ones(len(g)) if len(at) == 1 else (d2 - d1) / np.maximum(d2, 1e-300)   # a single atom has no competitor
+    return idg.reshape(n), gap.reshape(n)
