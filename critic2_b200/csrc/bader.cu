@@ -1462,23 +1462,45 @@ constexpr int SB_X = 4, SB_Y = 16, SB_Z = 16;
 __host__ __device__ inline int cls_nblocks(int t1, int t2, int t3) {
   return ((t1 + SB_X - 1) / SB_X) * ((t2 + SB_Y - 1) / SB_Y) * ((t3 + SB_Z - 1) / SB_Z) * (SB_X * SB_Y * SB_Z);
 }
+// Geometry of a classification pass, computed once on the host: the kernel used to derive it per thread with eight
+// run-time integer divisions (~150 of its 380 instructions per warp; it is issue-bound).
+struct ClsGeom {
+  int c1, c2, c3;       // cubes per axis (owned layers in z)
+  int t1, t2, t3;       // tiles per axis
+  int s1, s12;          // super-blocks along x, and along x times y
+  unsigned mg1, mg12;   // fastdiv magics of s1 and s12
+  int sh1, sh12;
+};
+inline ClsGeom cls_geom(int n1, int n2, int nzl, int s) {
+  ClsGeom G;
+  G.c1 = (n1 + s - 1) / s; G.c2 = (n2 + s - 1) / s; G.c3 = (nzl + s - 1) / s;
+  G.t1 = (G.c1 + CLS_TX - 1) / CLS_TX; G.t2 = (G.c2 + CLS_TY - 1) / CLS_TY; G.t3 = (G.c3 + CLS_TZ - 1) / CLS_TZ;
+  G.s1 = std::max(1, (G.t1 + SB_X - 1) / SB_X);
+  const int s2 = std::max(1, (G.t2 + SB_Y - 1) / SB_Y);
+  G.s12 = G.s1 * s2;
+  fastdiv_make((unsigned)G.s1, G.mg1, G.sh1);
+  fastdiv_make((unsigned)G.s12, G.mg12, G.sh12);
+  return G;
+}
 template <bool FILL>
-__global__ void __launch_bounds__(256) k_classify(int n1, int n2, int n3, const Slab S, int s, int* __restrict__ lbuf,
+__global__ void __launch_bounds__(256) k_classify(int n1, int n2, int n3, const Slab S, int s, const __grid_constant__ ClsGeom G,
+                                                  int* __restrict__ lbuf,
                                                   const unsigned char* __restrict__ cubemax, int* __restrict__ uni,
                                                   int* __restrict__ list, int* __restrict__ segcnt, int* __restrict__ ntotal) {
   __shared__ unsigned char s_nu[256];   // cube is non-uniform: its new points walk
   __shared__ int s_row[64];             // entries per row (iz, py) of the tile, then their exclusive prefix
-  const int c1 = (n1 + s - 1) / s, c2 = (n2 + s - 1) / s, c3 = (S.nzl + s - 1) / s;
-  const int t1 = (c1 + CLS_TX - 1) / CLS_TX, t2 = (c2 + CLS_TY - 1) / CLS_TY, t3 = (c3 + CLS_TZ - 1) / CLS_TZ;
+  const int c1 = G.c1, c2 = G.c2, c3 = G.c3;
+  const int t1 = G.t1, t2 = G.t2, t3 = G.t3;
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   int tx, ty, tz;
   {
-    const int sb = b / (SB_X * SB_Y * SB_Z), w = b % (SB_X * SB_Y * SB_Z);
-    const int s1 = (t1 + SB_X - 1) / SB_X, s2 = (t2 + SB_Y - 1) / SB_Y;
-    tx = (sb % s1) * SB_X + w % SB_X;
-    ty = ((sb / s1) % s2) * SB_Y + (w / SB_X) % SB_Y;
-    tz = (sb / (s1 * s2)) * SB_Z + w / (SB_X * SB_Y);
+    const int sb = b / (SB_X * SB_Y * SB_Z), w = b % (SB_X * SB_Y * SB_Z);   // compile-time divisors
+    const int sz = fastdiv(sb, G.mg12, G.sh12), r = sb - sz * G.s12;
+    const int sy = fastdiv(r, G.mg1, G.sh1), sx = r - sy * G.s1;
+    tx = sx * SB_X + w % SB_X;
+    ty = sy * SB_Y + (w / SB_X) % SB_Y;
+    tz = sz * SB_Z + w / (SB_X * SB_Y);
   }
   if (tx >= t1 || ty >= t2 || tz >= t3) {  // padding block of a ragged super-block
     if (tid == 0) segcnt[b] = 0;
@@ -2664,10 +2686,10 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
       if (nnl > 0) {
         ctx->prof_begin(i == 0 ? "bader_classify2" : "bader_classify");
         if (i == 0)
-          k_classify<false><<<ntile, 256, 0, st>>>(n1, n2, n3, S, L.s, lbuf, b_cubemax[i].as<unsigned char>(), b_uni[i].as<int>(),
+          k_classify<false><<<ntile, 256, 0, st>>>(n1, n2, n3, S, L.s, cls_geom(n1, n2, S.nzl, L.s), lbuf, b_cubemax[i].as<unsigned char>(), b_uni[i].as<int>(),
                                                    seglist, segcnt, cnt + 1);
         else
-          k_classify<true><<<ntile, 256, 0, st>>>(n1, n2, n3, S, L.s, lbuf, b_cubemax[i].as<unsigned char>(), b_uni[i].as<int>(),
+          k_classify<true><<<ntile, 256, 0, st>>>(n1, n2, n3, S, L.s, cls_geom(n1, n2, S.nzl, L.s), lbuf, b_cubemax[i].as<unsigned char>(), b_uni[i].as<int>(),
                                                   seglist, segcnt, cnt + 1);
         ctx->prof_end();
         C2G_KERNEL_CHECK(ctx);
