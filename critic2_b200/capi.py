@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcritic2_gpu.so")
+# C2G_LIB_PATH: another build of the same library (kernel-variant experiments, tools/); the product is the in-tree file
+LIB_PATH = os.environ.get("C2G_LIB_PATH") or os.path.join(_HERE, "libcritic2_gpu.so")
 _lib = None
 
 BADER_FAST, BADER_EXACT = 0, 1

@@ -501,7 +501,13 @@ __device__ __forceinline__ void halo_decode(int h, int& col, int& row) {
 // No shared memory, no barriers: one coalesced 8-byte load per point.  Marks the cubes of every level that
 // contain a maximum.
 constexpr int MZC = 32;  // planes per block
-constexpr int MZP = 4;   // planes per prefetch group of k_maxima
+#ifndef C2G_MZP
+#define C2G_MZP 4
+#endif
+#ifndef C2G_MAX2_MINB
+#define C2G_MAX2_MINB 1
+#endif
+constexpr int MZP = C2G_MZP;   // planes per prefetch group of k_maxima
 __global__ void __launch_bounds__(256) k_maxima(const __grid_constant__ BaderParams P, const Slab S,
                                                 const double* __restrict__ rho, int* __restrict__ cand,
                                                 int* __restrict__ ncand, int maxcand, const __grid_constant__ CubeFlags CF) {
@@ -571,7 +577,7 @@ __global__ void __launch_bounds__(256) k_maxima(const __grid_constant__ BaderPar
 // Same pass for even n1: a lane owns TWO consecutive x points (one 16-byte load per plane), which halves the
 // shuffles, the edge handling and the address arithmetic per point -- k_maxima is issue-bound (75 % of the issue
 // slots at 3.6 TB/s), not load-bound.  A block = 128 threads = 256 consecutive x points of one row.
-__global__ void __launch_bounds__(128) k_maxima2(const __grid_constant__ BaderParams P, const Slab S,
+__global__ void __launch_bounds__(128, C2G_MAX2_MINB) k_maxima2(const __grid_constant__ BaderParams P, const Slab S,
                                                  const double* __restrict__ rho, int* __restrict__ cand,
                                                  int* __restrict__ ncand, int maxcand, const __grid_constant__ CubeFlags CF) {
   const int n1 = P.n1, n2 = P.n2, n3 = P.n3;
