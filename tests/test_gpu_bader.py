@@ -293,3 +293,23 @@ def test_async_upload_and_labels_match_the_synchronous_calls(ctx):
         assert np.array_equal(vol, vol_ref)
         assert np.abs(ps - ps_ref).max() <= 1e-12 * np.abs(ps_ref).max()
         bb.free(); ctx.free(ha); ctx.free(hb)
+
+
+@pytest.mark.parametrize("env", [{"C2G_SYNC_LEVELS": "1"}, {"C2G_WALK3": "0"}, {"C2G_WALK3": "0", "C2G_WALK2": "1"},
+                                 {"C2G_WALK3": "5"}, {"C2G_CERT": "2"}, {"C2G_NO_EARLY_STOP": "1"}, {"C2G_FILL_OLD": "1"}],
+                         ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()))
+@pytest.mark.parametrize("name", ["cubic48", "odd_dims", "triclinic"])
+def test_fallback_flows_and_kernels_give_the_same_labels(ctx, name, env):
+    """The switches of DESIGN.md 9b select older kernels and flows that stay in the library for measurements (host-driven
+    level loop, k_walk, k_walk2, mixed kernels, cube certificates, no early stop, the full-stencil fill pass): every one
+    of them must still produce the oracle's labels."""
+    c = cases.make_case(name)
+    idg, nattr, _, _ = orc.bader_integrate(c["f"], c["x2c"], atoms=c["atoms"])
+    os.environ.update(env)
+    try:
+        h, b, na = gpu_bader(ctx, c, capi.BADER_FAST)
+    finally:
+        for k in env:
+            del os.environ[k]
+    assert na == nattr and np.count_nonzero(b.labels(c["n"]) != idg) == 0
+    b.free(); ctx.free(h)
