@@ -1058,9 +1058,12 @@ __global__ void __launch_bounds__(256, 4) k_walk2(const __grid_constant__ BaderP
 #ifndef C2G_W3_NT
 #define C2G_W3_NT 256   // threads per block of k_walk3 (512: measured)
 #endif
+#ifndef C2G_W3_MINB
+#define C2G_W3_MINB (1024 / C2G_W3_NT)   // resident blocks per SM the register allocation aims at
+#endif
 constexpr int W3_NT = C2G_W3_NT;
 template <bool ORTHO, bool FIX, bool STATS, int CERT>
-__global__ void __launch_bounds__(W3_NT, 1024 / W3_NT) k_walk3(const __grid_constant__ BaderParams P, const __grid_constant__ WalkArgs A) {
+__global__ void __launch_bounds__(W3_NT, C2G_W3_MINB) k_walk3(const __grid_constant__ BaderParams P, const __grid_constant__ WalkArgs A) {
   __shared__ int s_wc[W3_NT / 32];
   __shared__ int s_chunk[2];                       // first entry and number of entries handed to the block
   __shared__ int s_id[W3_NT], s_start[W3_NT], s_tidx[W3_NT], s_old[W3_NT];
@@ -2410,7 +2413,7 @@ extern "C" int c2g_bader_assign(c2g_context* ctx, int handle, const double car2l
   if (const char* e = getenv("C2G_REFILL_COARSE")) refill_coarse = std::max(1, std::min(32, atoi(e)));
   WA.refill_min = refill_coarse;
   WA.steps_per_check = spc_coarse;
-  const int walk_occ = 4;  // resident 256-thread walker blocks per SM (<= 64 registers)
+  const int walk_occ = std::max(4, C2G_W3_MINB * W3_NT / 256);  // resident 256-thread walker blocks per SM (<= 64 registers)
   const bool walk_stats = getenv("C2G_BADER_VERBOSE") != nullptr || getenv("C2G_BADER_STATS") != nullptr;
   // k_walk2 (every idle lane refilled before every step) is an opt-in experiment: it keeps 30 of 32 lanes busy but
   // its lanes no longer move as cohorts of neighbours, every load then touches up to 32 cache lines, and the last
